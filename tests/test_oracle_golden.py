@@ -1,0 +1,105 @@
+"""Pin the oracle (oracle/) against vectors produced by the reference's own modules
+(tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import logmel as olm
+from oracle.frontend import AudioProcessorPort, lips_u8_to_model_input
+from oracle.av_models import MidFusionFastOracle
+from multimodal_lipread_b200 import synthetic
+
+
+@pytest.fixture(scope="module")
+def lg(golden_dir):
+    return np.load(os.path.join(golden_dir, "logmel_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def mg(golden_dir):
+    return np.load(os.path.join(golden_dir, "midfusion_golden.npz"))
+
+
+def test_window_and_filterbank_match_torchaudio(lg):
+    assert np.abs(olm.hann_window() - lg["window"]).max() < 5e-7   # torch builds it in fp32
+    fb = olm.melscale_fbanks()
+    assert fb.shape == (201, 80)
+    assert np.abs(fb - lg["fb"]).max() < 1e-5          # torchaudio builds fb in fp32
+    assert (lg["fb"] > 0).sum() == 392 and ((lg["fb"] > 0).sum(0) > 0).all()
+    assert abs(float((lg["window"].astype(np.float64) ** 2).sum()) - 150.0) < 1e-4
+
+
+def test_port_reproduces_reference_bitwise(lg):
+    ap = AudioProcessorPort()
+    wave = torch.from_numpy(lg["wave"])
+    out = ap.batch_frontend_loop(wave).numpy()
+    ref = lg["out"]
+    assert np.abs(out - ref).max() == 0.0              # same torch, same call sequence
+
+
+def test_float64_restatement_matches_reference(lg):
+    """fp32 reference vs float64 restatement: fp32 round-off only (<= ~2e-4 abs)."""
+    ref = lg["out"].astype(np.float64)
+    out = olm.logmel_frontend(lg["wave"], window=lg["window"], fb=lg["fb"])
+    n = ref.shape[0] - 1                                # last clip is silence, checked below
+    err = np.abs(out[:n] - ref[:n]).max(axis=(1, 2))
+    scale = np.abs(ref[:n]).max(axis=(1, 2))
+    assert (err <= 1e-4 * scale).all(), (err, scale)
+    # Silent clip: every log-mel value is ln(1e-9), so (x - mean) is pure fp32 round-off in the
+    # reference (a constant -0.9994...), amplified by the 1e-9-regularised division.  Exact
+    # arithmetic gives 0; the restatement (and the CUDA kernel) return that.
+    assert np.unique(ref[n]).size == 1 and abs(ref[n]).max() <= 1.0
+    assert (out[n] == 0.0).all()
+
+
+def test_raw_logmel_and_padding_value(lg):
+    raw = olm.log_mel(lg["wave"], window=lg["window"], fb=lg["fb"])
+    ref = lg["logmel_raw"].astype(np.float64)
+    assert raw.shape == ref.shape == (8, 80, 126)
+    assert np.abs(raw - ref).max() < 2e-3               # un-normalised log power, values ~ 5..20
+    assert np.allclose(ref[-1], np.log(1e-9), atol=1e-5)
+
+
+def test_frames_reflect_padding():
+    x = np.arange(20000, dtype=np.float64)
+    fr = olm.frames(x)
+    assert fr.shape == (126, 400)
+    assert fr[0, 0] == 200 and fr[0, 199] == 1 and fr[0, 200] == 0 and fr[0, 399] == 199
+    assert fr[125, 399] == 19998 - 199 and fr[125, 200] == 19998
+    assert fr[125, 199] == 19999
+
+
+@pytest.mark.parametrize("size", [44, 88])
+def test_midfusion_oracle_matches_reference(mg, size):
+    torch.manual_seed(0)
+    model = MidFusionFastOracle(40)
+    model.train()
+    assert [n for n, _ in model.named_parameters()] == list(mg["param_names"])
+    assert list(model.state_dict().keys()) == list(mg["state_keys"])
+    wsum0 = np.array([p.detach().double().sum().item() for p in model.parameters()])
+    np.testing.assert_allclose(wsum0, mg[f"wsum_before_{size}"], rtol=0, atol=0)   # same seeded init
+    B = 2
+    wav = synthetic.make_waveforms(B, pad_fraction=0.5)
+    mel = AudioProcessorPort().batch_frontend_loop(wav)
+    video = lips_u8_to_model_input(synthetic.make_lips_u8(B, size=size))
+    labels = synthetic.make_labels(B, 40)
+    opt = torch.optim.Adam(model.parameters(), lr=3e-4)
+    opt.zero_grad()
+    logits = model(mel, video)
+    loss = torch.nn.functional.cross_entropy(logits, labels)
+    loss.backward()
+    np.testing.assert_allclose(logits.detach().numpy(), mg[f"logits_{size}"], rtol=1e-5, atol=1e-6)
+    assert abs(loss.item() - float(mg[f"loss_{size}"])) < 1e-6
+    gnorm = np.array([p.grad.double().norm().item() for p in model.parameters()])
+    np.testing.assert_allclose(gnorm, mg[f"grad_norm_{size}"], rtol=1e-4, atol=1e-7)
+    opt.step()
+    wsum1 = np.array([p.detach().double().sum().item() for p in model.parameters()])
+    np.testing.assert_allclose(wsum1, mg[f"wsum_after_{size}"], rtol=1e-5, atol=1e-4)
+    sd = model.state_dict()
+    np.testing.assert_allclose(sd["video_cnn.features.0.1.running_mean"].numpy(), mg[f"rm_stem_{size}"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(sd["video_cnn.features.12.1.running_var"].numpy(), mg[f"rv_last_{size}"], rtol=1e-5, atol=1e-7)
+    model.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(model(mel, video).numpy(), mg[f"logits_eval_{size}"], rtol=1e-5, atol=1e-6)
