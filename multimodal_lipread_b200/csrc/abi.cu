@@ -1,0 +1,38 @@
+// ABI bookkeeping: version, thread-local error message, launch counter, cached device attributes.
+#include "common.cuh"
+#include <atomic>
+#include <mutex>
+
+namespace lr {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+char* last_error_buf() { return g_err; }
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+int sm_count() {
+    // Immutable after first use; one value per process is enough (one process drives one GPU).
+    static int n = [] {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+        return v;
+    }();
+    return n;
+}
+
+}  // namespace lr
+
+extern "C" int lr_version(void) { return LR_ABI_VERSION; }
+extern "C" const char* lr_last_error(void) { return lr::last_error_buf(); }
+extern "C" unsigned long long lr_launch_count(void) { return lr::g_launches.load(std::memory_order_relaxed); }

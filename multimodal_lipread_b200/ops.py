@@ -1,0 +1,72 @@
+"""torch.library custom ops (`torch.ops.lipread.*`) over the C ABI.  CUDA only: calling an op with
+CPU tensors raises NotImplementedError from the dispatcher -- there is no CPU kernel to fall to."""
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+
+def _ptr(t):
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(t, dtype, name):
+    if not t.is_cuda:
+        raise _lib.LipreadError(f"{name} must be a CUDA tensor (lipread_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.LipreadError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.LipreadError(f"{name} must be contiguous")
+
+
+# ---------------------------------------------------------------- K1 log-mel
+@torch.library.custom_op("lipread::logmel_plan", mutates_args=(), device_types="cuda")
+def logmel_plan(window: torch.Tensor, fb: torch.Tensor) -> torch.Tensor:
+    _need(window, torch.float32, "window")
+    _need(fb, torch.float32, "fb")
+    if window.numel() != 400 or tuple(fb.shape) != (201, 80):
+        raise _lib.LipreadError("logmel_plan expects window[400] and fb[201,80]")
+    n = lib.lr_logmel_plan_bytes()
+    plan = torch.empty(n, dtype=torch.uint8, device=window.device)
+    check(lib.lr_logmel_plan_init(_ptr(window), _ptr(fb), _ptr(plan), n, _stream()))
+    return plan
+
+
+@logmel_plan.register_fake
+def _(window, fb):
+    return window.new_empty(lib.lr_logmel_plan_bytes(), dtype=torch.uint8)
+
+
+@torch.library.custom_op("lipread::logmel", mutates_args=(), device_types="cuda")
+def logmel(wav: torch.Tensor, plan: torch.Tensor, n_out: int, mode: int) -> torch.Tensor:
+    """wav (B, 20000) f32 -> (B, 80, n_out) f32.  mode 0: log-mel + normalise + crop; 1: raw log-mel."""
+    _need(wav, torch.float32, "wav")
+    if wav.dim() != 2 or wav.shape[1] != 20000:
+        raise _lib.LipreadError(f"wav must be (B, 20000), got {tuple(wav.shape)}")
+    out = torch.empty(wav.shape[0], 80, n_out, dtype=torch.float32, device=wav.device)
+    check(lib.lr_logmel_fwd(_ptr(wav), _ptr(plan), _ptr(out), wav.shape[0], n_out, mode, _stream()))
+    return out
+
+
+@logmel.register_fake
+def _(wav, plan, n_out, mode):
+    return wav.new_empty(wav.shape[0], 80, n_out)
+
+
+@torch.library.custom_op("lipread::normalize", mutates_args=(), device_types="cuda")
+def normalize(x: torch.Tensor) -> torch.Tensor:
+    """Row-wise (x - mean) / (std_unbiased + 1e-9) over all but the first dimension."""
+    _need(x, torch.float32, "x")
+    out = torch.empty_like(x)
+    b = x.shape[0]
+    check(lib.lr_normalize_fwd(_ptr(x), _ptr(out), b, x.numel() // max(b, 1), _stream()))
+    return out
+
+
+@normalize.register_fake
+def _(x):
+    return torch.empty_like(x)
