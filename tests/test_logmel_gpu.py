@@ -61,7 +61,8 @@ def test_seeded_clips_match_oracle(ap, kind):
     port = AudioProcessorPort()
     ref64b = olm.logmel_frontend(wav.numpy(), window=port.window.numpy(), fb=port.fb.numpy())
     assert (_normwise(out, ref64b) <= RTOL_NORMWISE).all(), _normwise(out, ref64b).max()
-    assert (_normwise(out, ref64) <= 2 * RTOL_NORMWISE).all()
+    # float64 window/fb instead of the fp32 buffers: only the oracle-side buffer rounding is added
+    assert (_normwise(out, ref64) <= RTOL_NORMWISE + _normwise(ref64b, ref64)).all()
     ref32 = port.batch_frontend_loop(wav).numpy()
     noise = _normwise(ref32.astype(np.float64), ref64b)
     assert (_normwise(out, ref32) <= RTOL_NORMWISE + noise).all()
