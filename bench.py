@@ -222,7 +222,7 @@ def main():
         wl.step_device()
     e1.record()
     barrier()
-    launches = wl.launches_per_step() * args.steps if wl.launches_per_step() else _lib.launch_count() - l0
+    launches = (wl.launches_per_step() or 0) * args.steps or (_lib.launch_count() - l0)
     ms_total = e0.elapsed_time(e1)
     kernel_ms = wl.kernel_ms()                      # dominant-kernel time per launch (CUDA events), or None
     # end to end from pinned host memory

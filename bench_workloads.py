@@ -78,3 +78,86 @@ class LogmelWorkload:
 
     def extra(self):
         return {"clips_per_sec": None}
+
+
+class AvTrainWorkload:
+    """audio_video middle_fusion_fast train step on synthetic GLips-shaped clips (audio_video/train.py:61-67):
+    log-mel -> forward -> CE -> backward -> (NCCL allreduce) -> Adam, all in lipread_b200 kernels."""
+    dtype = "f32"
+
+    def __init__(self, dev, batch, cfg, rank, world):
+        import torch.distributed as dist
+        from multimodal_lipread_b200.audio_video_models import MidFusionFast
+        self.dev, self.batch, self.world, self.cfg = dev, batch, world, cfg
+        torch.manual_seed(0)                                   # identical replicas on every rank
+        self.model = MidFusionFast(cfg["num_classes"]).to(dev).train()
+        self.model.configure_optimizer(lr=3e-4)
+        # a ring of distinct input batches larger than L2 (126 MB), resident in HBM
+        per_batch = batch * (20000 * 4 + 29 * cfg["size"] * cfg["size"] * 3)
+        self.ring = max(2, min(64, (160 * 1024 * 1024) // per_batch + 1))
+        g = 1000 + rank
+        self.host = []
+        for i in range(self.ring):
+            wav = synthetic.make_waveforms(batch, seed=g * 100 + i).pin_memory()
+            lips = synthetic.make_lips_u8(batch, size=cfg["size"], seed=g * 100 + 50 + i, grayscale=cfg["grayscale"]).pin_memory()
+            lab = synthetic.make_labels(batch, cfg["num_classes"], seed=g * 100 + 77 + i).pin_memory()
+            self.host.append((wav, lips, lab))
+        self.devb = [(w.to(dev), l.to(dev), y.to(dev)) for w, l, y in self.host]
+        self.stage = tuple(torch.empty_like(t) for t in self.devb[0])
+        self.i = 0
+        self.loss_host = torch.zeros(1).pin_memory()
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host[0])
+        self.d2h_bytes = 4
+        self.allreduce = None
+        if world > 1:
+            def allreduce(grad):
+                dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+            self.allreduce = allreduce
+        self.timer = _KernelTimer()
+        self.last_loss = None
+
+    def units_per_step(self):
+        return self.batch
+
+    def launches_per_step(self):
+        return self.model.launches_per_step()
+
+    def reset_kernel_timer(self):
+        self.timer.reset()
+
+    def kernel_ms(self):
+        return None
+
+    def _step(self, wav, lips, lab):
+        loss, _ = self.model.train_step(wav, lips, lab, grad_allreduce=self.allreduce, world=self.world)
+        self.last_loss = loss
+        return loss
+
+    def step_device(self):
+        w, l, y = self.devb[self.i % self.ring]
+        self.i += 1
+        return self._step(w, l, y)
+
+    def step_e2e(self):
+        w, l, y = self.host[self.i % self.ring]
+        self.i += 1
+        for dst, src in zip(self.stage, (w, l, y)):
+            dst.copy_(src, non_blocking=True)
+        loss = self._step(*self.stage)
+        self.loss_host.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.loss_host
+
+    def roofline(self, kernel_ms, ms_step, peaks):
+        # whole-step view: algorithmic minimum HBM traffic of the step is not well defined for a 300-kernel
+        # step, so the step-level figure reported is fp32 FLOP throughput of the model math (3x forward)
+        size = self.cfg["size"]
+        fwd_gflop = 0.630 if size == 88 else 0.256           # SURVEY.md 8(a) a16, per clip
+        tf = 3 * fwd_gflop * self.batch / (ms_step / 1e3) / 1e3
+        return {"kernel": "whole train step (see profiles/ for the per-kernel launch list)", "bound": "hbm",
+                "achieved": None, "peak": peaks["hbm"], "unit": "GB/s", "frac": None, "traffic": None,
+                "peak_source": peaks["src"], "step_model_tflops": tf}
+
+    def extra(self):
+        return {"final_loss": float(self.last_loss.item()) if self.last_loss is not None else None,
+                "input_ring_batches": self.ring}

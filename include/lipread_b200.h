@@ -40,6 +40,9 @@ int lr_version(void);
 const char* lr_last_error(void);
 /* Number of kernels this library has launched in the calling process (all threads). */
 unsigned long long lr_launch_count(void);
+/* Zero `bytes` bytes of device memory on `stream` (cudaMemsetAsync: per-step clearing of the BatchNorm
+ * statistic arena and of the flat gradient buffer; a memset node under graph capture). */
+int lr_memset(void* ptr, size_t bytes, lr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K1  log-mel frontend
@@ -70,6 +73,105 @@ int lr_logmel_fwd(const float* wav /*[B,20000]*/, const void* plan, float* out, 
 
 /* normalize_spectrogram alone on [B, n] rows: (x - mean)/(std_unbiased + 1e-9). */
 int lr_normalize_fwd(const float* x, float* out, int B, int n, lr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Trunk / head building blocks.  Activations are channels-last fp32: a (F, H, W, C) frame batch is a
+ * row-major [rows = F*H*W, C] matrix, so the 1x1 convolutions of torchvision's MobileNetV3 / the SE and
+ * classifier linears / nn.LSTM's projections are all lr_gemm calls on it.
+ * ------------------------------------------------------------------------------------------ */
+enum { LR_ACT_NONE = 0, LR_ACT_RELU = 1, LR_ACT_HSWISH = 2, LR_ACT_HSIGMOID = 3 };
+
+/* C[M,N] = act(A.B + bias) + R, optional per-column sum / sum-of-squares into double stats[2N]
+ * (train-mode BatchNorm statistics of a conv output), optional split-K with atomic accumulation.
+ *   a_trans 0: A is [M][K] (lda);  1: A is [K][M] (lda)     b_trans 0: B is [N][K] (ldb);  1: B is [K][N] (ldb)
+ * replaces: nn.Conv2d(k=1) / nn.Linear forward, dgrad and wgrad (cuDNN / cuBLAS in the reference), e.g.
+ * audio_video/models/middle_fusion_fast.py:13,20-25 and torchvision mobilenetv3 Conv2dNormActivation. */
+int lr_gemm(const float* A, long long lda, int a_trans, const float* B, long long ldb, int b_trans, float* C,
+            long long ldc, int M, int N, int K, const float* bias, int act, const float* R, long long ldr,
+            double* stats, int ksplit, lr_stream_t stream);
+
+/* MobileNetV3 stem: Conv2d(3,16,3,stride=2,padding=1,bias=False) on frames addressed in the caller's own
+ * layout: element (b, t, c, h, w) at x[b*sb + t*st + c*sc + h*sh + w*sw] (uint8 if is_u8 else float), times
+ * `scale` (1/255 for uint8 .npy frames).  Folds video/data_utils/dataset_loader.py:90,96 (/255, permute) and
+ * the TimeDistributed permute/contiguous/view of audio_video/models/middle_fusion_fast.py:32-33.
+ * y: [B*T, Ho, Wo, 16] raw conv output; stats: double[32] accumulated (caller zeroes). */
+int lr_stem_conv_fwd(const void* x, int is_u8, int B, int T, int H, int W, long long sb, long long st,
+                     long long sc, long long sh, long long sw, float scale, const float* w /*[16,3,3,3]*/,
+                     float* y, double* stats, lr_stream_t stream);
+int lr_stem_conv_wgrad(const void* x, int is_u8, int B, int T, int H, int W, long long sb, long long st,
+                       long long sc, long long sh, long long sw, float scale, const float* dy,
+                       float* dw /*[16,3,3,3], accumulated*/, lr_stream_t stream);
+
+/* Depthwise k x k convolution (k in {3,5}, stride in {1,2}, padding k/2, no bias), x: [F,H,W,C],
+ * w: [C,1,k,k] (torch layout), y: [F,Ho,Wo,C]; stats as above.  dw is accumulated into. */
+int lr_dwconv_fwd(const float* x, const float* w, float* y, double* stats, int F, int H, int W, int C, int k,
+                  int stride, lr_stream_t stream);
+int lr_dwconv_dgrad(const float* dy, const float* w, float* dx, int F, int H, int W, int C, int k, int stride,
+                    lr_stream_t stream);
+int lr_dwconv_wgrad(const float* dy, const float* x, float* dw, int F, int H, int W, int C, int k, int stride,
+                    lr_stream_t stream);
+
+/* nn.BatchNorm2d (+ activation, + residual add) on [rows, C].  training != 0: batch statistics from
+ * `stats` (double[2C] sum / sum of squares over the rows), running_mean / running_var / num_batches_tracked
+ * updated exactly as torch does (unbiased variance, momentum); training == 0: running statistics.
+ * z = act(bn(x)) + residual. */
+int lr_bn_act_fwd(const float* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
+                  float* running_var, long long* num_batches_tracked, float eps, float momentum, int act,
+                  int training, const float* residual, float* z, long long rows, int C, lr_stream_t stream);
+/* dx from dz (gradient of z); dgamma / dbeta accumulated into; sums: double[2C] scratch zeroed by the caller.
+ * The residual branch's gradient is dz itself. */
+int lr_bn_act_bwd(const float* x, const double* stats, const float* gamma, const float* beta,
+                  const float* running_mean, const float* running_var, float eps, int act, int training,
+                  const float* dz, double* sums, float* dx, float* dgamma, float* dbeta, long long rows, int C,
+                  lr_stream_t stream);
+
+/* Per-frame reductions over the HW pixels of [F, HW, C]:  mode 0: p = mean(a)  (AdaptiveAvgPool2d(1), SE squeeze);
+ * mode 1: p = sum(a * g)  (gradient of the SE gate). */
+int lr_frame_reduce(const float* a, const float* g, float* p, int F, int HW, int C, int mode, lr_stream_t stream);
+/* out[f,hw,c] = a[f,hw,c] * s[f,c] + dp[f,c] / HW   (either term may be absent: a == NULL or dp == NULL):
+ * SE excitation forward, SE backward, average-pool backward. */
+int lr_frame_scale(const float* a, const float* s, const float* dp, float* out, int F, int HW, int C,
+                   lr_stream_t stream);
+/* dy *= act'(.) expressed through the activation OUTPUT y (ReLU, hard-sigmoid), in place. */
+int lr_act_bwd(float* dy, const float* y, long long n, int act, lr_stream_t stream);
+/* db[n] += sum_m dY[m*ld + n]  (bias gradients) */
+int lr_colsum(const float* dY, long long ld, long long M, int N, float* db, lr_stream_t stream);
+
+/* One direction of one nn.LSTM layer over `nsteps` <= T steps of its walk (forward: t = 0.., reverse: t = T-1..).
+ * xproj: [B*T, 4H] = x W_ih^T + b_ih + b_hh (one lr_gemm); out rows (b*T+t) with stride ldo; gates / cst / hprev
+ * ([B,T,4H], [B,T,H], [B,T,H]) are saved for the backward pass when non-NULL. */
+int lr_lstm_fwd(const float* xproj, long long ldx, const float* bhh /*[4H] or NULL, added to xproj*/,
+                const float* whh, float* out, long long ldo, float* gates, float* cst, float* hprev, int B, int T,
+                int H, int nsteps, int reverse, lr_stream_t stream);
+/* BPTT: dgates[B,T,4H] (gradient of the gate pre-activations) for the visited steps.  External gradient of
+ * the outputs: dout_step < 0: dout[(b*T+t)*ldo + k] for every t; dout_step >= 0: only h at t == dout_step
+ * receives dout[b*ldo + k] (a head that reads out[:, -1]). */
+int lr_lstm_bwd(const float* dout, long long ldo, int dout_step, const float* gates, const float* cst, const float* whh,
+                float* dgates, int B, int T, int H, int nsteps, int reverse, lr_stream_t stream);
+
+/* dst[r*ldd + c] = src[r*lds + c]  (strided row gather, e.g. out[:, -1] of a sequence into the fusion row) */
+int lr_copy2d(float* dst, long long ldd, const float* src, long long lds, int rows, int cols, lr_stream_t stream);
+
+/* MidFusionFast audio branch: Conv2d(1,16,3,padding=1) + ReLU + MaxPool2d(2) fused
+ * (audio_video/models/middle_fusion_fast.py:8-12,28-29): x [B,H,W] -> out rows of 16*(H/2)*(W/2) (stride ldo),
+ * arg: uint8 arg-max code per output (saved for the backward). */
+int lr_audio_conv_fwd(const float* x, const float* w, const float* bias, float* out, long long ldo,
+                      unsigned char* arg, int B, int H, int W, lr_stream_t stream);
+int lr_audio_conv_bwd(const float* x, const float* dA, long long lda, const unsigned char* arg, float* dw, float* db,
+                      int B, int H, int W, lr_stream_t stream);
+
+/* nn.CrossEntropyLoss(mean) forward + gradient (audio_video/train.py:129,65): loss += mean CE (caller zeroes),
+ * dlogits = (softmax - onehot) * inv_n (may be NULL), correct += #(argmax == label) (may be NULL). */
+int lr_ce_loss(const float* logits, const long long* labels, float* loss, float* dlogits, int* correct, int B, int C,
+               float inv_n, lr_stream_t stream);
+
+/* torch.optim.Adam step on flat buffers (audio_video/train.py:130,67).  state: device struct
+ * {float step, bc1, bc2_sqrt, lr} (lr_adam_state_bytes()); the step counter advances on the device so the
+ * call can be replayed from a CUDA graph.  g is multiplied by grad_scale first (1/world after the allreduce);
+ * weight_decay is the coupled L2 form torch.optim.Adam uses. */
+size_t lr_adam_state_bytes(void);
+int lr_adam_step(float* p, const float* g, float* m, float* v, void* state, long long n, float beta1, float beta2,
+                 float eps, float weight_decay, float grad_scale, lr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -36,3 +36,12 @@ int sm_count() {
 extern "C" int lr_version(void) { return LR_ABI_VERSION; }
 extern "C" const char* lr_last_error(void) { return lr::last_error_buf(); }
 extern "C" unsigned long long lr_launch_count(void) { return lr::g_launches.load(std::memory_order_relaxed); }
+
+// Zero-fill through the copy engine (a memset node under graph capture, not a kernel launch).
+extern "C" int lr_memset(void* ptr, size_t bytes, lr_stream_t stream) {
+    if (bytes == 0) return LR_OK;
+    LR_CHECK_ARG(ptr, "lr_memset: null pointer");
+    cudaError_t e = cudaMemsetAsync(ptr, 0, bytes, stream);
+    if (e != cudaSuccess) return lr::fail(LR_ECUDA, "lr_memset: %s", cudaGetErrorString(e));
+    return LR_OK;
+}

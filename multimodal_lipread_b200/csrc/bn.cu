@@ -1,0 +1,381 @@
+// Channels-last [rows, C] kernels around the convolutions (fp32):
+//   train-mode BatchNorm (+activation, +residual) forward / backward with the batch statistics taken from
+//   the double sum / sum-of-squares the producing conv emitted (torch.nn.BatchNorm2d in training mode:
+//   biased variance for normalisation, unbiased for running_var, momentum update, num_batches_tracked),
+//   eval-mode BatchNorm (running statistics), per-frame average pooling, squeeze-excitation scale,
+//   element-wise activation backward and bias-gradient column sums.
+// torchvision MobileNetV3 call sites: Conv2dNormActivation, SqueezeExcitation, avgpool
+// (audio_video/models/middle_fusion_fast.py:15-17,34).
+#include "nn_common.cuh"
+
+namespace bn {
+
+constexpr int TH = 256;
+
+struct Bn {
+    long long rows; int C;
+    const double* stats;            // [2C] sum, sumsq of x over rows (train) -- null in eval mode
+    const float* gamma; const float* beta;
+    float* running_mean; float* running_var; long long* nbt;
+    float eps, momentum;
+    int act, training;
+};
+
+// per-thread BN coefficients of the thread's 4 channels
+struct Coef { float4 scale, shift, mean, invstd; };
+
+__device__ __forceinline__ void coef1(const Bn& b, int c, float& scale, float& shift, float& mean, float& invstd) {
+    if (b.training) {
+        const double n = (double)b.rows;
+        const double m = b.stats[c] / n;
+        double var = b.stats[b.C + c] / n - m * m;
+        if (var < 0.0) var = 0.0;
+        mean = (float)m;
+        invstd = (float)(1.0 / sqrt(var + (double)b.eps));
+    } else {
+        mean = b.running_mean[c];
+        invstd = 1.0f / sqrtf(b.running_var[c] + b.eps);
+    }
+    scale = b.gamma[c] * invstd;
+    shift = b.beta[c] - mean * scale;
+}
+__device__ __forceinline__ Coef coef4(const Bn& b, int c) {
+    Coef k;
+    coef1(b, c, k.scale.x, k.shift.x, k.mean.x, k.invstd.x);
+    coef1(b, c + 1, k.scale.y, k.shift.y, k.mean.y, k.invstd.y);
+    coef1(b, c + 2, k.scale.z, k.shift.z, k.mean.z, k.invstd.z);
+    coef1(b, c + 3, k.scale.w, k.shift.w, k.mean.w, k.invstd.w);
+    return k;
+}
+
+// z = act(x * scale + shift) (+ residual).  Block (0,0) also performs the running-statistics update.
+__global__ void __launch_bounds__(TH)
+bn_act_fwd_kernel(const Bn b, const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ z,
+                  int rows_per_block) {
+    const nn::CgMap map(b.C, blockIdx.y * blockDim.x);
+    if (b.training && b.running_mean && blockIdx.x == 0 && blockIdx.y == 0) {
+        for (int c = threadIdx.x; c < b.C; c += blockDim.x) {
+            const double n = (double)b.rows;
+            const double m = b.stats[c] / n;
+            double var = b.stats[b.C + c] / n - m * m;
+            if (var < 0.0) var = 0.0;
+            const double unb = n > 1.0 ? var * n / (n - 1.0) : var;
+            b.running_mean[c] = (1.f - b.momentum) * b.running_mean[c] + b.momentum * (float)m;
+            b.running_var[c] = (1.f - b.momentum) * b.running_var[c] + b.momentum * (float)unb;
+        }
+        if (threadIdx.x == 0 && b.nbt) *b.nbt += 1;
+    }
+    if (!map.active) return;
+    const int c = map.cg * 4;
+    const Coef k = coef4(b, c);
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(b.rows, r0 + rows_per_block);
+    for (long long r = r0 + map.rlane; r < r1; r += map.rpp) {
+        const float4 v = nn::ld4(x + r * b.C + c);
+        float4 o;
+        o.x = nn::act_fwd(fmaf(v.x, k.scale.x, k.shift.x), b.act);
+        o.y = nn::act_fwd(fmaf(v.y, k.scale.y, k.shift.y), b.act);
+        o.z = nn::act_fwd(fmaf(v.z, k.scale.z, k.shift.z), b.act);
+        o.w = nn::act_fwd(fmaf(v.w, k.scale.w, k.shift.w), b.act);
+        if (res) { const float4 q = nn::ld4(res + r * b.C + c); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+        nn::st4(z + r * b.C + c, o);
+    }
+}
+
+// backward pass 1: dy = dz * act'(u), u = x*scale + shift;  sums[c] += dy, sums[C+c] += dy * xhat
+__global__ void __launch_bounds__(TH)
+bn_act_bwd_reduce_kernel(const Bn b, const float* __restrict__ x, const float* __restrict__ dz,
+                         double* __restrict__ sums, int rows_per_block) {
+    extern __shared__ float sh[];                       // [2C]
+    for (int i = threadIdx.x; i < 2 * b.C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const nn::CgMap map(b.C, blockIdx.y * blockDim.x);
+    if (map.active) {
+        const int c = map.cg * 4;
+        const Coef k = coef4(b, c);
+        const long long r0 = (long long)blockIdx.x * rows_per_block;
+        const long long r1 = min(b.rows, r0 + rows_per_block);
+        float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+        for (long long r = r0 + map.rlane; r < r1; r += map.rpp) {
+            const float4 v = nn::ld4(x + r * b.C + c);
+            const float4 g = nn::ld4(dz + r * b.C + c);
+            const float d0 = g.x * nn::act_grad(fmaf(v.x, k.scale.x, k.shift.x), b.act);
+            const float d1 = g.y * nn::act_grad(fmaf(v.y, k.scale.y, k.shift.y), b.act);
+            const float d2 = g.z * nn::act_grad(fmaf(v.z, k.scale.z, k.shift.z), b.act);
+            const float d3 = g.w * nn::act_grad(fmaf(v.w, k.scale.w, k.shift.w), b.act);
+            s1.x += d0; s1.y += d1; s1.z += d2; s1.w += d3;
+            s2.x = fmaf(d0, (v.x - k.mean.x) * k.invstd.x, s2.x);
+            s2.y = fmaf(d1, (v.y - k.mean.y) * k.invstd.y, s2.y);
+            s2.z = fmaf(d2, (v.z - k.mean.z) * k.invstd.z, s2.z);
+            s2.w = fmaf(d3, (v.w - k.mean.w) * k.invstd.w, s2.w);
+        }
+        atomicAdd(&sh[c], s1.x); atomicAdd(&sh[c + 1], s1.y); atomicAdd(&sh[c + 2], s1.z); atomicAdd(&sh[c + 3], s1.w);
+        atomicAdd(&sh[b.C + c], s2.x); atomicAdd(&sh[b.C + c + 1], s2.y);
+        atomicAdd(&sh[b.C + c + 2], s2.z); atomicAdd(&sh[b.C + c + 3], s2.w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * b.C; i += blockDim.x) nn::atomic_add_double(sums + i, (double)sh[i]);
+}
+
+// backward pass 2: dx = gamma*invstd * (dy - mean(dy) - xhat * mean(dy*xhat))   (training)
+//                  dx = gamma*invstd * dy                                        (eval)
+// block (0,0) writes dgamma += sum(dy*xhat), dbeta += sum(dy).
+__global__ void __launch_bounds__(TH)
+bn_act_bwd_apply_kernel(const Bn b, const float* __restrict__ x, const float* __restrict__ dz,
+                        const double* __restrict__ sums, float* __restrict__ dx, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta, int rows_per_block) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && dgamma) {
+        for (int c = threadIdx.x; c < b.C; c += blockDim.x) {
+            dbeta[c] += (float)sums[c];
+            dgamma[c] += (float)sums[b.C + c];
+        }
+    }
+    const nn::CgMap map(b.C, blockIdx.y * blockDim.x);
+    if (!map.active) return;
+    const int c = map.cg * 4;
+    const Coef k = coef4(b, c);
+    const double inv_n = b.training ? 1.0 / (double)b.rows : 0.0;
+    const float m1[4] = {(float)(sums[c] * inv_n), (float)(sums[c + 1] * inv_n), (float)(sums[c + 2] * inv_n),
+                         (float)(sums[c + 3] * inv_n)};
+    const float m2[4] = {(float)(sums[b.C + c] * inv_n), (float)(sums[b.C + c + 1] * inv_n),
+                         (float)(sums[b.C + c + 2] * inv_n), (float)(sums[b.C + c + 3] * inv_n)};
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(b.rows, r0 + rows_per_block);
+    for (long long r = r0 + map.rlane; r < r1; r += map.rpp) {
+        const float4 v = nn::ld4(x + r * b.C + c);
+        const float4 g = nn::ld4(dz + r * b.C + c);
+        float4 o;
+        o.x = k.scale.x * (g.x * nn::act_grad(fmaf(v.x, k.scale.x, k.shift.x), b.act) - m1[0] - (v.x - k.mean.x) * k.invstd.x * m2[0]);
+        o.y = k.scale.y * (g.y * nn::act_grad(fmaf(v.y, k.scale.y, k.shift.y), b.act) - m1[1] - (v.y - k.mean.y) * k.invstd.y * m2[1]);
+        o.z = k.scale.z * (g.z * nn::act_grad(fmaf(v.z, k.scale.z, k.shift.z), b.act) - m1[2] - (v.z - k.mean.z) * k.invstd.z * m2[2]);
+        o.w = k.scale.w * (g.w * nn::act_grad(fmaf(v.w, k.scale.w, k.shift.w), b.act) - m1[3] - (v.w - k.mean.w) * k.invstd.w * m2[3]);
+        nn::st4(dx + r * b.C + c, o);
+    }
+}
+
+// ------------------------------------------------------------------------- per-frame pooling / SE
+// mode 0: p[f,c]  = mean_hw a[f,hw,c]
+// mode 1: p[f,c]  = sum_hw a[f,hw,c] * g[f,hw,c]        (ds of the SE scale)
+__global__ void __launch_bounds__(TH)
+frame_reduce_kernel(const float* __restrict__ a, const float* __restrict__ g, float* __restrict__ p, int HW, int C,
+                    int mode) {
+    extern __shared__ float sh[];                       // [C]
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    const long long f = blockIdx.x;
+    for (int cg0 = 0; cg0 < (C >> 2); cg0 += blockDim.x) {
+        const nn::CgMap map(C, cg0);
+        if (!map.active) continue;
+        const int c = map.cg * 4;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = map.rlane; r < HW; r += map.rpp) {
+            const long long off = (f * HW + r) * C + c;
+            float4 v = nn::ld4(a + off);
+            if (mode == 1) { const float4 w = nn::ld4(g + off); v.x *= w.x; v.y *= w.y; v.z *= w.z; v.w *= w.w; }
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        atomicAdd(&sh[c], s.x); atomicAdd(&sh[c + 1], s.y); atomicAdd(&sh[c + 2], s.z); atomicAdd(&sh[c + 3], s.w);
+    }
+    __syncthreads();
+    const float sc = mode == 0 ? 1.f / (float)HW : 1.f;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) p[f * C + i] = sh[i] * sc;
+}
+
+// out[f,hw,c] = (a ? a[f,hw,c] * s[f,c] : 0) + (dp ? dp[f,c] * inv_hw : 0)
+//   SE forward            : a = activation, s = gate, dp = null
+//   SE backward           : a = db, s = gate, dp = gradient of the pooled value
+//   avg-pool backward     : a = null, dp = gradient of the pooled value
+__global__ void __launch_bounds__(TH)
+frame_scale_kernel(const float* __restrict__ a, const float* __restrict__ s, const float* __restrict__ dp,
+                   float* __restrict__ out, long long rows, int HW, int C, float inv_hw, int rows_per_block) {
+    const nn::CgMap map(C, blockIdx.y * blockDim.x);
+    if (!map.active) return;
+    const int c = map.cg * 4;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(rows, r0 + rows_per_block);
+    for (long long r = r0 + map.rlane; r < r1; r += map.rpp) {
+        const long long f = r / HW;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a) {
+            const float4 v = nn::ld4(a + r * C + c), g = nn::ld4(s + f * C + c);
+            o.x = v.x * g.x; o.y = v.y * g.y; o.z = v.z * g.z; o.w = v.w * g.w;
+        }
+        if (dp) {
+            const float4 d = nn::ld4(dp + f * C + c);
+            o.x = fmaf(d.x, inv_hw, o.x); o.y = fmaf(d.y, inv_hw, o.y); o.z = fmaf(d.z, inv_hw, o.z); o.w = fmaf(d.w, inv_hw, o.w);
+        }
+        nn::st4(out + r * C + c, o);
+    }
+}
+
+// dy *= act'(y) with the derivative expressed through the OUTPUT (ReLU, hard-sigmoid), in place
+__global__ void __launch_bounds__(TH)
+act_bwd_kernel(float* __restrict__ dy, const float* __restrict__ y, long long n, int act) {
+    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < n; i += (long long)gridDim.x * TH)
+        dy[i] *= nn::act_grad_from_out(y[i], act);
+}
+
+// db[n] += sum_m dY[m, n]   (row stride ld)
+__global__ void __launch_bounds__(TH)
+colsum_kernel(const float* __restrict__ dY, long long ld, long long M, int N, float* __restrict__ db,
+              int rows_per_block) {
+    // thread -> column (coalesced), y-lanes over rows
+    const int cols = min(N, TH);
+    const int rpp = TH / cols;
+    const int rl = threadIdx.x / cols;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(M, r0 + rows_per_block);
+    if (rl >= rpp) return;
+    for (int n = blockIdx.y * cols + threadIdx.x % cols; n < N; n += gridDim.y * cols) {
+        float s = 0.f;
+        for (long long r = r0 + rl; r < r1; r += rpp) s += dY[r * ld + n];
+        atomicAdd(&db[n], s);
+    }
+}
+
+__global__ void __launch_bounds__(TH)
+copy2d_kernel(float* __restrict__ dst, long long ldd, const float* __restrict__ src, long long lds, int rows, int cols) {
+    const long long n = (long long)rows * cols;
+    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < n; i += (long long)gridDim.x * TH) {
+        const long long r = i / cols; const int c = int(i - r * cols);
+        dst[r * ldd + c] = src[r * lds + c];
+    }
+}
+
+}  // namespace bn
+
+// ------------------------------------------------------------------------------------------ C ABI
+static int rows_per_block_for(long long rows, int C, int* grid_x) {
+    const int ncg = C >> 2;
+    const int w = ncg < bn::TH ? ncg : bn::TH;
+    const int rpp = bn::TH / w;
+    long long rpb = (rows + (long long)lr::sm_count() * 8 - 1) / ((long long)lr::sm_count() * 8);
+    rpb = ((rpb + rpp - 1) / rpp) * rpp;
+    if (rpb < rpp) rpb = rpp;
+    *grid_x = (int)((rows + rpb - 1) / rpb);
+    return (int)rpb;
+}
+
+static bn::Bn make_bn(long long rows, int C, const double* stats, const float* gamma, const float* beta, float* rm,
+                      float* rv, long long* nbt, float eps, float momentum, int act, int training) {
+    bn::Bn b;
+    b.rows = rows; b.C = C; b.stats = stats; b.gamma = gamma; b.beta = beta; b.running_mean = rm; b.running_var = rv;
+    b.nbt = nbt; b.eps = eps; b.momentum = momentum; b.act = act; b.training = training;
+    return b;
+}
+
+#define LR_BN_CHECK(name)                                                                        \
+    LR_CHECK_ARG(rows >= 0 && C > 0 && (C & 3) == 0, name ": need rows >= 0 and C %% 4 == 0");  \
+    LR_CHECK_ARG(act >= LR_ACT_NONE && act <= LR_ACT_HSIGMOID, name ": bad activation");        \
+    LR_CHECK_ARG(training ? stats != nullptr : (running_mean && running_var), name ": missing statistics"); \
+    if (rows == 0) return LR_OK
+
+extern "C" int lr_bn_act_fwd(const float* x, const double* stats, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var, long long* num_batches_tracked, float eps,
+                             float momentum, int act, int training, const float* residual, float* z,
+                             long long rows, int C, lr_stream_t stream) {
+    LR_BN_CHECK("lr_bn_act_fwd");
+    LR_CHECK_ARG(x && gamma && beta && z, "lr_bn_act_fwd: null pointer");
+    LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(z); LR_CHECK_ALIGN(residual);
+    int gx; const int rpb = rows_per_block_for(rows, C, &gx);
+    dim3 grid(gx, nn::cg_block_cols(C, bn::TH));
+    bn::bn_act_fwd_kernel<<<grid, bn::TH, 0, stream>>>(
+        make_bn(rows, C, stats, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, act, training),
+        x, residual, z, rpb);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("bn_act_fwd_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_bn_act_bwd(const float* x, const double* stats, const float* gamma, const float* beta,
+                             const float* running_mean, const float* running_var, float eps, int act, int training,
+                             const float* dz, double* sums /*[2C], zeroed by the caller*/, float* dx, float* dgamma,
+                             float* dbeta, long long rows, int C, lr_stream_t stream) {
+    LR_BN_CHECK("lr_bn_act_bwd");
+    LR_CHECK_ARG(x && gamma && beta && dz && sums && dx, "lr_bn_act_bwd: null pointer");
+    LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(dz); LR_CHECK_ALIGN(dx);
+    int gx; const int rpb = rows_per_block_for(rows, C, &gx);
+    dim3 grid(gx, nn::cg_block_cols(C, bn::TH));
+    const bn::Bn b = make_bn(rows, C, stats, gamma, beta, const_cast<float*>(running_mean),
+                             const_cast<float*>(running_var), nullptr, eps, 0.f, act, training);
+    bn::bn_act_bwd_reduce_kernel<<<grid, bn::TH, 2 * C * sizeof(float), stream>>>(b, x, dz, sums, rpb);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("bn_act_bwd_reduce_kernel");
+    bn::bn_act_bwd_apply_kernel<<<grid, bn::TH, 0, stream>>>(b, x, dz, sums, dx, dgamma, dbeta, rpb);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("bn_act_bwd_apply_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_frame_reduce(const float* a, const float* g, float* p, int F, int HW, int C, int mode,
+                               lr_stream_t stream) {
+    LR_CHECK_ARG(F >= 0 && HW > 0 && C > 0 && (C & 3) == 0, "lr_frame_reduce: bad shape");
+    LR_CHECK_ARG(mode == 0 || (mode == 1 && g), "lr_frame_reduce: bad mode");
+    if (F == 0) return LR_OK;
+    LR_CHECK_ARG(a && p, "lr_frame_reduce: null pointer");
+    LR_CHECK_ALIGN(a); LR_CHECK_ALIGN(g);
+    bn::frame_reduce_kernel<<<F, bn::TH, C * sizeof(float), stream>>>(a, g, p, HW, C, mode);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("frame_reduce_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_frame_scale(const float* a, const float* s, const float* dp, float* out, int F, int HW, int C,
+                              lr_stream_t stream) {
+    LR_CHECK_ARG(F >= 0 && HW > 0 && C > 0 && (C & 3) == 0, "lr_frame_scale: bad shape");
+    LR_CHECK_ARG((a && s) || dp, "lr_frame_scale: nothing to do");
+    if (F == 0) return LR_OK;
+    LR_CHECK_ARG(out, "lr_frame_scale: null pointer");
+    LR_CHECK_ALIGN(a); LR_CHECK_ALIGN(s); LR_CHECK_ALIGN(dp); LR_CHECK_ALIGN(out);
+    const long long rows = (long long)F * HW;
+    int gx; const int rpb = rows_per_block_for(rows, C, &gx);
+    dim3 grid(gx, nn::cg_block_cols(C, bn::TH));
+    bn::frame_scale_kernel<<<grid, bn::TH, 0, stream>>>(a, s, dp, out, rows, HW, C, 1.f / (float)HW, rpb);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("frame_scale_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_act_bwd(float* dy, const float* y, long long n, int act, lr_stream_t stream) {
+    LR_CHECK_ARG(n >= 0, "lr_act_bwd: negative size");
+    LR_CHECK_ARG(act == LR_ACT_RELU || act == LR_ACT_HSIGMOID || act == LR_ACT_NONE, "lr_act_bwd: activation has no output-form derivative");
+    if (n == 0 || act == LR_ACT_NONE) return LR_OK;
+    LR_CHECK_ARG(dy && y, "lr_act_bwd: null pointer");
+    long long g = (n + bn::TH - 1) / bn::TH;
+    const long long cap = (long long)lr::sm_count() * 16;
+    if (g > cap) g = cap;
+    bn::act_bwd_kernel<<<(unsigned)g, bn::TH, 0, stream>>>(dy, y, n, act);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("act_bwd_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_colsum(const float* dY, long long ld, long long M, int N, float* db, lr_stream_t stream) {
+    LR_CHECK_ARG(M >= 0 && N > 0, "lr_colsum: bad shape");
+    if (M == 0) return LR_OK;
+    LR_CHECK_ARG(dY && db, "lr_colsum: null pointer");
+    const int cols = N < bn::TH ? N : bn::TH;
+    const int rpp = bn::TH / cols;
+    long long rpb = (M + (long long)lr::sm_count() * 2 - 1) / ((long long)lr::sm_count() * 2);
+    rpb = ((rpb + rpp - 1) / rpp) * rpp;
+    if (rpb < rpp) rpb = rpp;
+    dim3 grid((unsigned)((M + rpb - 1) / rpb), 1);
+    bn::colsum_kernel<<<grid, bn::TH, 0, stream>>>(dY, ld, M, N, db, (int)rpb);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("colsum_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_copy2d(float* dst, long long ldd, const float* src, long long lds, int rows, int cols,
+                         lr_stream_t stream) {
+    LR_CHECK_ARG(rows >= 0 && cols >= 0, "lr_copy2d: negative shape");
+    if (rows == 0 || cols == 0) return LR_OK;
+    LR_CHECK_ARG(dst && src, "lr_copy2d: null pointer");
+    long long g = ((long long)rows * cols + bn::TH - 1) / bn::TH;
+    const long long cap = (long long)lr::sm_count() * 8;
+    if (g > cap) g = cap;
+    bn::copy2d_kernel<<<(unsigned)g, bn::TH, 0, stream>>>(dst, ldd, src, lds, rows, cols);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("copy2d_kernel");
+    return LR_OK;
+}

@@ -1,0 +1,424 @@
+// Direct convolutions of the MobileNetV3 trunk that are NOT GEMM-shaped (channels-last, fp32):
+//   stem   : 3x3 stride-2 conv 3 -> 16 reading the lip frames in the layout the caller has
+//            (uint8 (B,T,H,W,3) straight from the .npy, or float (B,3,T,H,W) as the reference's
+//            forward() receives it) -- the /255, permute(3,0,1,2) and TimeDistributed
+//            permute/contiguous/view of video/data_utils/dataset_loader.py:90,96 and
+//            audio_video/models/middle_fusion_fast.py:32-33 are folded into the addressing.
+//   dwconv : depthwise k x k (k = 3, 5; stride 1, 2), forward / dgrad / wgrad.
+// Every forward kernel also emits the per-channel sum and sum of squares of its raw output
+// (double atomics) so that train-mode BatchNorm needs no extra pass over the activation.
+#include "nn_common.cuh"
+
+namespace cv {
+
+constexpr int TH = 256;
+
+// ------------------------------------------------------------------------------------------ stem
+struct StemIn {
+    const void* x;
+    int is_u8;                       // 1: uint8 values scaled by `scale`; 0: float
+    long long sf, sc, sh, sw;        // element strides of frame / channel / row / column
+    float scale;
+    int F, H, W, Ho, Wo;
+};
+__device__ __forceinline__ float stem_load(const StemIn& in, int f, int c, int h, int w) {
+    const long long off = (long long)f * in.sf + (long long)c * in.sc + (long long)h * in.sh + (long long)w * in.sw;
+    return in.is_u8 ? float(static_cast<const unsigned char*>(in.x)[off]) * in.scale
+                    : static_cast<const float*>(in.x)[off] * in.scale;
+}
+// Frame index f = b*T + t maps to (b, t) strides through `sf` only when the (b, t) pair is
+// addressable with one stride; for the float (B,3,T,H,W) layout that is not the case, so the
+// caller passes T and the two strides and we resolve here.
+struct StemIn2 {
+    StemIn in; int T; long long sb, st;
+};
+__device__ __forceinline__ long long frame_base(const StemIn2& s, int f) {
+    const int b = f / s.T, t = f - b * s.T;
+    return (long long)b * s.sb + (long long)t * s.st;
+}
+__device__ __forceinline__ float stem_ld(const StemIn2& s, long long fb, int c, int h, int w) {
+    const long long off = fb + (long long)c * s.in.sc + (long long)h * s.in.sh + (long long)w * s.in.sw;
+    return s.in.is_u8 ? float(static_cast<const unsigned char*>(s.in.x)[off]) * s.in.scale
+                      : static_cast<const float*>(s.in.x)[off] * s.in.scale;
+}
+
+constexpr int SC = 16;               // stem output channels
+constexpr int ST = 27;               // 3 in-channels * 3 * 3 taps
+
+__global__ void __launch_bounds__(TH)
+stem_fwd_kernel(const StemIn2 s, const float* __restrict__ w /*[16][3][3][3]*/, float* __restrict__ y,
+                double* __restrict__ stats) {
+    __shared__ float ws[ST][SC];      // [ci*9 + kh*3 + kw][co]
+    __shared__ float ssum[SC], ssq[SC];
+    for (int i = threadIdx.x; i < ST * SC; i += TH) { const int co = i / ST, tp = i - co * ST; ws[tp][co] = w[i]; }
+    if (threadIdx.x < SC) { ssum[threadIdx.x] = 0.f; ssq[threadIdx.x] = 0.f; }
+    __syncthreads();
+    const int Ho = s.in.Ho, Wo = s.in.Wo, H = s.in.H, W = s.in.W;
+    const long long total = (long long)s.in.F * Ho * Wo;
+    float lsum[SC], lsq[SC];
+#pragma unroll
+    for (int c = 0; c < SC; ++c) { lsum[c] = 0.f; lsq[c] = 0.f; }
+    for (long long pix = (long long)blockIdx.x * TH + threadIdx.x; pix < total; pix += (long long)gridDim.x * TH) {
+        const int wo = int(pix % Wo);
+        const long long r = pix / Wo;
+        const int ho = int(r % Ho), f = int(r / Ho);
+        const long long fb = frame_base(s, f);
+        float acc[SC];
+#pragma unroll
+        for (int c = 0; c < SC; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const int hi = ho * 2 - 1 + kh;
+                if (hi < 0 || hi >= H) continue;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int wi = wo * 2 - 1 + kw;
+                    if (wi < 0 || wi >= W) continue;
+                    const float xv = stem_ld(s, fb, ci, hi, wi);
+                    const float* wr = ws[ci * 9 + kh * 3 + kw];
+#pragma unroll
+                    for (int c = 0; c < SC; ++c) acc[c] = fmaf(xv, wr[c], acc[c]);
+                }
+            }
+        float* o = y + pix * SC;
+#pragma unroll
+        for (int c = 0; c < SC; c += 4) nn::st4(o + c, make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]));
+#pragma unroll
+        for (int c = 0; c < SC; ++c) { lsum[c] += acc[c]; lsq[c] = fmaf(acc[c], acc[c], lsq[c]); }
+    }
+#pragma unroll
+    for (int c = 0; c < SC; ++c) {
+        const float a = lr::warp_sum(lsum[c]), b = lr::warp_sum(lsq[c]);
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&ssum[c], a); atomicAdd(&ssq[c], b); }
+    }
+    __syncthreads();
+    if (threadIdx.x < SC) {
+        nn::atomic_add_double(stats + threadIdx.x, (double)ssum[threadIdx.x]);
+        nn::atomic_add_double(stats + SC + threadIdx.x, (double)ssq[threadIdx.x]);
+    }
+}
+
+// dW[co][tap] = sum_pix dy[pix][co] * x[pix, tap].  Thread (co, tap-slot) owns outputs, the block
+// stages PT pixels of dy and of the im2col patch in shared memory; persistent over pixel tiles.
+constexpr int PT = 64;
+__global__ void __launch_bounds__(TH)
+stem_wgrad_kernel(const StemIn2 s, const float* __restrict__ dy, float* __restrict__ dw /*[16][27]*/) {
+    __shared__ float xs[PT][ST + 1];
+    __shared__ float ds[PT][SC + 1];
+    const int Ho = s.in.Ho, Wo = s.in.Wo, H = s.in.H, W = s.in.W;
+    const long long total = (long long)s.in.F * Ho * Wo;
+    // 432 outputs over 256 threads: thread t owns (co = t & 15, taps tp = t >> 4 and tp + 16 (< 27))
+    const int co = threadIdx.x & 15, tp0 = threadIdx.x >> 4, tp1 = tp0 + 16;
+    float a0 = 0.f, a1 = 0.f;
+    for (long long base = (long long)blockIdx.x * PT; base < total; base += (long long)gridDim.x * PT) {
+        const int np = (int)min((long long)PT, total - base);
+        for (int i = threadIdx.x; i < PT * ST; i += TH) {
+            const int pl = i / ST, tp = i - pl * ST;
+            float v = 0.f;
+            if (pl < np) {
+                const long long pix = base + pl;
+                const int wo = int(pix % Wo);
+                const long long r = pix / Wo;
+                const int ho = int(r % Ho), f = int(r / Ho);
+                const int ci = tp / 9, kh = (tp - ci * 9) / 3, kw = tp - ci * 9 - kh * 3;
+                const int hi = ho * 2 - 1 + kh, wi = wo * 2 - 1 + kw;
+                if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = stem_ld(s, frame_base(s, f), ci, hi, wi);
+            }
+            xs[pl][tp] = v;
+        }
+        for (int i = threadIdx.x; i < PT * SC; i += TH) {
+            const int pl = i >> 4, c = i & 15;
+            ds[pl][c] = pl < np ? dy[(base + pl) * SC + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int pl = 0; pl < PT; ++pl) {
+            const float d = ds[pl][co];
+            a0 = fmaf(d, xs[pl][tp0], a0);
+            if (tp1 < ST) a1 = fmaf(d, xs[pl][tp1], a1);
+        }
+        __syncthreads();
+    }
+    atomicAdd(&dw[co * ST + tp0], a0);
+    if (tp1 < ST) atomicAdd(&dw[co * ST + tp1], a1);
+}
+
+// ---------------------------------------------------------------------------------------- dwconv
+struct Dw {
+    int F, H, W, C, Ho, Wo, k, stride, pad;
+};
+
+// weights -> shared memory transposed to [tap][C] so that a thread's float4 is contiguous
+__device__ __forceinline__ void dw_stage_weights(const float* __restrict__ w, float* ws, int C, int kk) {
+    for (int i = threadIdx.x; i < C * kk; i += blockDim.x) { const int c = i / kk, tp = i - c * kk; ws[tp * C + c] = w[i]; }
+}
+
+template <int K>
+__global__ void __launch_bounds__(TH)
+dw_fwd_kernel(const Dw d, const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+              double* __restrict__ stats, int pix_per_block) {
+    extern __shared__ __align__(16) float smem[];
+    float* ws = smem;                                  // [K*K][C]
+    float* ssum = smem + K * K * d.C;                  // [C]
+    float* ssq = ssum + d.C;                           // [C]
+    dw_stage_weights(w, ws, d.C, K * K);
+    for (int i = threadIdx.x; i < 2 * d.C; i += blockDim.x) ssum[i] = 0.f;
+    __syncthreads();
+    const nn::CgMap map(d.C, blockIdx.y * blockDim.x);
+    const long long total = (long long)d.F * d.Ho * d.Wo;
+    const long long p0 = (long long)blockIdx.x * pix_per_block;
+    const long long p1 = min(total, p0 + pix_per_block);
+    float4 ls = make_float4(0.f, 0.f, 0.f, 0.f), lq = ls;
+    if (map.active) {
+        const int c = map.cg * 4;
+        for (long long pix = p0 + map.rlane; pix < p1; pix += map.rpp) {
+            const int wo = int(pix % d.Wo);
+            const long long r = pix / d.Wo;
+            const int ho = int(r % d.Ho), f = int(r / d.Ho);
+            const float* xf = x + (long long)f * d.H * d.W * d.C + c;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int kh = 0; kh < K; ++kh) {
+                const int hi = ho * d.stride - d.pad + kh;
+                if (hi < 0 || hi >= d.H) continue;
+#pragma unroll
+                for (int kw = 0; kw < K; ++kw) {
+                    const int wi = wo * d.stride - d.pad + kw;
+                    if (wi < 0 || wi >= d.W) continue;
+                    const float4 xv = nn::ld4(xf + ((long long)hi * d.W + wi) * d.C);
+                    const float4 wv = nn::ld4(ws + (kh * K + kw) * d.C + c);
+                    acc.x = fmaf(xv.x, wv.x, acc.x); acc.y = fmaf(xv.y, wv.y, acc.y);
+                    acc.z = fmaf(xv.z, wv.z, acc.z); acc.w = fmaf(xv.w, wv.w, acc.w);
+                }
+            }
+            nn::st4(y + pix * d.C + c, acc);
+            ls.x += acc.x; ls.y += acc.y; ls.z += acc.z; ls.w += acc.w;
+            lq.x = fmaf(acc.x, acc.x, lq.x); lq.y = fmaf(acc.y, acc.y, lq.y);
+            lq.z = fmaf(acc.z, acc.z, lq.z); lq.w = fmaf(acc.w, acc.w, lq.w);
+        }
+        atomicAdd(&ssum[c], ls.x); atomicAdd(&ssum[c + 1], ls.y); atomicAdd(&ssum[c + 2], ls.z); atomicAdd(&ssum[c + 3], ls.w);
+        atomicAdd(&ssq[c], lq.x); atomicAdd(&ssq[c + 1], lq.y); atomicAdd(&ssq[c + 2], lq.z); atomicAdd(&ssq[c + 3], lq.w);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < d.C; i += blockDim.x) {
+        nn::atomic_add_double(stats + i, (double)ssum[i]);
+        nn::atomic_add_double(stats + d.C + i, (double)ssq[i]);
+    }
+}
+
+// dx[f,hi,wi,c] = sum_{kh,kw : (hi+pad-kh) % s == 0} dy[f,(hi+pad-kh)/s,(wi+pad-kw)/s,c] * w[c,kh,kw]
+template <int K>
+__global__ void __launch_bounds__(TH)
+dw_dgrad_kernel(const Dw d, const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+                int pix_per_block) {
+    extern __shared__ __align__(16) float smem[];
+    float* ws = smem;
+    dw_stage_weights(w, ws, d.C, K * K);
+    __syncthreads();
+    const nn::CgMap map(d.C, blockIdx.y * blockDim.x);
+    const long long total = (long long)d.F * d.H * d.W;
+    const long long p0 = (long long)blockIdx.x * pix_per_block;
+    const long long p1 = min(total, p0 + pix_per_block);
+    if (!map.active) return;
+    const int c = map.cg * 4;
+    for (long long pix = p0 + map.rlane; pix < p1; pix += map.rpp) {
+        const int wi = int(pix % d.W);
+        const long long r = pix / d.W;
+        const int hi = int(r % d.H), f = int(r / d.H);
+        const float* df = dy + (long long)f * d.Ho * d.Wo * d.C + c;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int kh = 0; kh < K; ++kh) {
+            const int hn = hi + d.pad - kh;
+            if (hn < 0 || hn % d.stride != 0) continue;
+            const int ho = hn / d.stride;
+            if (ho >= d.Ho) continue;
+#pragma unroll
+            for (int kw = 0; kw < K; ++kw) {
+                const int wn = wi + d.pad - kw;
+                if (wn < 0 || wn % d.stride != 0) continue;
+                const int wo = wn / d.stride;
+                if (wo >= d.Wo) continue;
+                const float4 g = nn::ld4(df + ((long long)ho * d.Wo + wo) * d.C);
+                const float4 wv = nn::ld4(ws + (kh * K + kw) * d.C + c);
+                acc.x = fmaf(g.x, wv.x, acc.x); acc.y = fmaf(g.y, wv.y, acc.y);
+                acc.z = fmaf(g.z, wv.z, acc.z); acc.w = fmaf(g.w, wv.w, acc.w);
+            }
+        }
+        nn::st4(dx + pix * d.C + c, acc);
+    }
+}
+
+// dw[c,kh,kw] = sum_{f,ho,wo} dy[f,ho,wo,c] * x[f,ho*s-pad+kh,wo*s-pad+kw,c]
+// thread = one channel (coalesced across the warp) and one pixel lane; K*K register accumulators;
+// persistent over pixel tiles, one shared-memory + one global atomic round at the end.
+template <int K>
+__global__ void __launch_bounds__(TH)
+dw_wgrad_kernel(const Dw d, const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw) {
+    extern __shared__ __align__(16) float smem[];      // [cw][K*K]
+    const int cbase = blockIdx.y * TH;
+    const int cw = min(d.C - cbase, TH);
+    const int rpp = TH / cw;
+    const int c = cbase + threadIdx.x % cw, rl = threadIdx.x / cw;
+    for (int i = threadIdx.x; i < cw * K * K; i += TH) smem[i] = 0.f;
+    __syncthreads();
+    float acc[K * K];
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) acc[i] = 0.f;
+    const long long total = (long long)d.F * d.Ho * d.Wo;
+    if (rl < rpp) {
+        for (long long pix = (long long)blockIdx.x * rpp + rl; pix < total; pix += (long long)gridDim.x * rpp) {
+            const int wo = int(pix % d.Wo);
+            const long long r = pix / d.Wo;
+            const int ho = int(r % d.Ho), f = int(r / d.Ho);
+            const float g = dy[pix * d.C + c];
+            const float* xf = x + (long long)f * d.H * d.W * d.C + c;
+#pragma unroll
+            for (int kh = 0; kh < K; ++kh) {
+                const int hi = ho * d.stride - d.pad + kh;
+                if (hi < 0 || hi >= d.H) continue;
+#pragma unroll
+                for (int kw = 0; kw < K; ++kw) {
+                    const int wi = wo * d.stride - d.pad + kw;
+                    if (wi < 0 || wi >= d.W) continue;
+                    acc[kh * K + kw] = fmaf(g, xf[((long long)hi * d.W + wi) * d.C], acc[kh * K + kw]);
+                }
+            }
+        }
+        float* sm = smem + (c - cbase) * K * K;
+#pragma unroll
+        for (int i = 0; i < K * K; ++i) atomicAdd(&sm[i], acc[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cw * K * K; i += TH) atomicAdd(&dw[cbase * K * K + i], smem[i]);
+}
+
+}  // namespace cv
+
+// ------------------------------------------------------------------------------------------ C ABI
+static int make_stem(cv::StemIn2& s, const void* x, int is_u8, int B, int T, int H, int W, long long sb,
+                     long long st, long long sc, long long sh, long long sw, float scale) {
+    s.in.x = x; s.in.is_u8 = is_u8; s.in.sf = 0; s.in.sc = sc; s.in.sh = sh; s.in.sw = sw; s.in.scale = scale;
+    s.in.F = B * T; s.in.H = H; s.in.W = W; s.in.Ho = (H + 2 - 3) / 2 + 1; s.in.Wo = (W + 2 - 3) / 2 + 1;
+    s.T = T; s.sb = sb; s.st = st;
+    return 0;
+}
+
+extern "C" int lr_stem_conv_fwd(const void* x, int is_u8, int B, int T, int H, int W, long long sb, long long st,
+                                long long sc, long long sh, long long sw, float scale, const float* w, float* y,
+                                double* stats, lr_stream_t stream) {
+    LR_CHECK_ARG(B >= 0 && T > 0 && H > 0 && W > 0, "lr_stem_conv_fwd: bad shape");
+    if (B == 0) return LR_OK;
+    LR_CHECK_ARG(x && w && y && stats, "lr_stem_conv_fwd: null pointer");
+    LR_CHECK_ALIGN(y);
+    cv::StemIn2 s; make_stem(s, x, is_u8, B, T, H, W, sb, st, sc, sh, sw, scale);
+    const long long total = (long long)s.in.F * s.in.Ho * s.in.Wo;
+    const long long want = (total + cv::TH - 1) / cv::TH;
+    const int grid = (int)(want < (long long)lr::sm_count() * 8 ? want : (long long)lr::sm_count() * 8);
+    cv::stem_fwd_kernel<<<grid, cv::TH, 0, stream>>>(s, w, y, stats);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("stem_fwd_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_stem_conv_wgrad(const void* x, int is_u8, int B, int T, int H, int W, long long sb, long long st,
+                                  long long sc, long long sh, long long sw, float scale, const float* dy, float* dw,
+                                  lr_stream_t stream) {
+    LR_CHECK_ARG(B >= 0 && T > 0 && H > 0 && W > 0, "lr_stem_conv_wgrad: bad shape");
+    if (B == 0) return LR_OK;
+    LR_CHECK_ARG(x && dy && dw, "lr_stem_conv_wgrad: null pointer");
+    cv::StemIn2 s; make_stem(s, x, is_u8, B, T, H, W, sb, st, sc, sh, sw, scale);
+    const long long total = (long long)s.in.F * s.in.Ho * s.in.Wo;
+    const long long want = (total + cv::PT - 1) / cv::PT;
+    const int grid = (int)(want < (long long)lr::sm_count() * 4 ? want : (long long)lr::sm_count() * 4);
+    cv::stem_wgrad_kernel<<<grid, cv::TH, 0, stream>>>(s, dy, dw);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("stem_wgrad_kernel");
+    return LR_OK;
+}
+
+static int make_dw(cv::Dw& d, int F, int H, int W, int C, int k, int stride) {
+    d.F = F; d.H = H; d.W = W; d.C = C; d.k = k; d.stride = stride; d.pad = k / 2;
+    d.Ho = (H + 2 * d.pad - k) / stride + 1; d.Wo = (W + 2 * d.pad - k) / stride + 1;
+    return 0;
+}
+#define LR_DW_CHECK(name)                                                                              \
+    LR_CHECK_ARG(F >= 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, name ": bad shape (C %% 4 != 0?)"); \
+    LR_CHECK_ARG(k == 3 || k == 5, name ": kernel size %d not in {3,5}", k);                          \
+    LR_CHECK_ARG(stride == 1 || stride == 2, name ": stride %d not in {1,2}", stride);                \
+    if (F == 0) return LR_OK
+
+static int dw_pix_per_block(long long total, int C) {
+    const int rpp = cv::TH / ((C >> 2) < cv::TH ? (C >> 2) : cv::TH);
+    long long ppb = (total + (long long)lr::sm_count() * 8 - 1) / ((long long)lr::sm_count() * 8);
+    ppb = ((ppb + rpp - 1) / rpp) * rpp;
+    if (ppb < rpp) ppb = rpp;
+    return (int)ppb;
+}
+
+template <typename Kern>
+static cudaError_t dw_smem_attr(Kern kern, size_t bytes) {
+    return bytes > 48 * 1024 ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
+                             : cudaSuccess;
+}
+
+extern "C" int lr_dwconv_fwd(const float* x, const float* w, float* y, double* stats, int F, int H, int W, int C,
+                             int k, int stride, lr_stream_t stream) {
+    LR_DW_CHECK("lr_dwconv_fwd");
+    LR_CHECK_ARG(x && w && y && stats, "lr_dwconv_fwd: null pointer");
+    LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(y);
+    cv::Dw d; make_dw(d, F, H, W, C, k, stride);
+    const long long total = (long long)F * d.Ho * d.Wo;
+    const int ppb = dw_pix_per_block(total, C);
+    dim3 grid((unsigned)((total + ppb - 1) / ppb), nn::cg_block_cols(C, cv::TH));
+    const size_t smem = (size_t)(k * k + 2) * C * sizeof(float);
+    cudaError_t e = k == 3 ? dw_smem_attr(cv::dw_fwd_kernel<3>, smem) : dw_smem_attr(cv::dw_fwd_kernel<5>, smem);
+    if (e != cudaSuccess) return lr::fail(LR_ECUDA, "lr_dwconv_fwd smem: %s", cudaGetErrorString(e));
+    if (k == 3) cv::dw_fwd_kernel<3><<<grid, cv::TH, smem, stream>>>(d, x, w, y, stats, ppb);
+    else cv::dw_fwd_kernel<5><<<grid, cv::TH, smem, stream>>>(d, x, w, y, stats, ppb);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("dw_fwd_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_dwconv_dgrad(const float* dy, const float* w, float* dx, int F, int H, int W, int C, int k,
+                               int stride, lr_stream_t stream) {
+    LR_DW_CHECK("lr_dwconv_dgrad");
+    LR_CHECK_ARG(dy && w && dx, "lr_dwconv_dgrad: null pointer");
+    LR_CHECK_ALIGN(dy); LR_CHECK_ALIGN(dx);
+    cv::Dw d; make_dw(d, F, H, W, C, k, stride);
+    const long long total = (long long)F * H * W;
+    const int ppb = dw_pix_per_block(total, C);
+    dim3 grid((unsigned)((total + ppb - 1) / ppb), nn::cg_block_cols(C, cv::TH));
+    const size_t smem = (size_t)(k * k) * C * sizeof(float);
+    cudaError_t e = k == 3 ? dw_smem_attr(cv::dw_dgrad_kernel<3>, smem) : dw_smem_attr(cv::dw_dgrad_kernel<5>, smem);
+    if (e != cudaSuccess) return lr::fail(LR_ECUDA, "lr_dwconv_dgrad smem: %s", cudaGetErrorString(e));
+    if (k == 3) cv::dw_dgrad_kernel<3><<<grid, cv::TH, smem, stream>>>(d, dy, w, dx, ppb);
+    else cv::dw_dgrad_kernel<5><<<grid, cv::TH, smem, stream>>>(d, dy, w, dx, ppb);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("dw_dgrad_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_dwconv_wgrad(const float* dy, const float* x, float* dw, int F, int H, int W, int C, int k,
+                               int stride, lr_stream_t stream) {
+    LR_DW_CHECK("lr_dwconv_wgrad");
+    LR_CHECK_ARG(dy && x && dw, "lr_dwconv_wgrad: null pointer");
+    cv::Dw d; make_dw(d, F, H, W, C, k, stride);
+    const long long total = (long long)F * d.Ho * d.Wo;
+    const int ycols = (C + cv::TH - 1) / cv::TH;
+    const int cw = C < cv::TH ? C : cv::TH;
+    const int rpp = cv::TH / cw;
+    long long gx = (total + rpp - 1) / rpp;
+    const long long cap = (long long)lr::sm_count() * 4;
+    if (gx > cap) gx = cap;
+    dim3 grid((unsigned)gx, ycols);
+    const size_t smem = (size_t)cw * k * k * sizeof(float);
+    if (k == 3) cv::dw_wgrad_kernel<3><<<grid, cv::TH, smem, stream>>>(d, dy, x, dw);
+    else cv::dw_wgrad_kernel<5><<<grid, cv::TH, smem, stream>>>(d, dy, x, dw);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("dw_wgrad_kernel");
+    return LR_OK;
+}

@@ -1,0 +1,62 @@
+// Device helpers shared by the trunk / head kernels: activations, vector access, and the
+// "fixed channel group per thread" mapping used by every [rows, C] channels-last kernel.
+#pragma once
+#include "common.cuh"
+
+namespace nn {
+
+// LR_ACT_* in include/lipread_b200.h
+__device__ __forceinline__ float act_fwd(float u, int act) {
+    switch (act) {
+        case LR_ACT_RELU: return fmaxf(u, 0.f);
+        case LR_ACT_HSWISH: return u * fminf(fmaxf(u + 3.f, 0.f), 6.f) * (1.f / 6.f);
+        case LR_ACT_HSIGMOID: return fminf(fmaxf(u + 3.f, 0.f), 6.f) * (1.f / 6.f);
+        default: return u;
+    }
+}
+// d act(u) / du evaluated at the pre-activation u (torch: hardswish_backward, hardsigmoid_backward,
+// threshold_backward conventions at the kinks).
+__device__ __forceinline__ float act_grad(float u, int act) {
+    switch (act) {
+        case LR_ACT_RELU: return u > 0.f ? 1.f : 0.f;
+        case LR_ACT_HSWISH: return u < -3.f ? 0.f : (u <= 3.f ? u * (1.f / 3.f) + 0.5f : 1.f);
+        case LR_ACT_HSIGMOID: return (u > -3.f && u < 3.f) ? (1.f / 6.f) : 0.f;
+        default: return 1.f;
+    }
+}
+// derivative expressed through the OUTPUT y = act(u) (only for monotone acts where that is possible)
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+    switch (act) {
+        case LR_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+        case LR_ACT_HSIGMOID: return (y > 0.f && y < 1.f) ? (1.f / 6.f) : 0.f;
+        default: return 1.f;
+    }
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// Channel-group mapping for a row-major [rows, C] tensor with C % 4 == 0: a thread owns ONE group of
+// 4 consecutive channels (so per-channel parameters live in registers) and strides over rows.
+// Consecutive threads touch consecutive float4s, so every warp access is fully coalesced.
+struct CgMap {
+    int ncg;        // channel groups per row = C / 4
+    int cg;         // this thread's group (valid if active)
+    int rlane;      // this thread's row lane
+    int rpp;        // rows per pass of the block
+    bool active;
+    __device__ __forceinline__ CgMap(int C, int cg0 /*first group handled by this block column*/) {
+        ncg = C >> 2;
+        const int w = min(ncg - cg0, (int)blockDim.x);     // groups handled by this block column
+        rpp = blockDim.x / w;
+        cg = cg0 + threadIdx.x % w;
+        rlane = threadIdx.x / w;
+        active = rlane < rpp;
+    }
+};
+// number of block columns needed so that every channel group is owned by some thread
+inline int cg_block_cols(int C, int threads) { return ((C >> 2) + threads - 1) / threads; }
+
+__device__ __forceinline__ void atomic_add_double(double* p, double v) { atomicAdd(p, v); }
+
+}  // namespace nn

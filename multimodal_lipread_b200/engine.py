@@ -1,0 +1,312 @@
+"""Execution engine of the B200 audio-visual path: static launch plans over preallocated HBM buffers.
+
+A *plan* is built once per (model, batch shape, train/eval) and is nothing but two flat lists of C-ABI
+kernel launches (forward, backward) with every pointer already resolved, so a step is a tight loop of
+ctypes calls -- or, after CUDA-graph capture, a single graph launch.  There is no autograd tape and no
+tracing compiler: the backward schedule is written out by hand next to each forward op.
+
+Data layout in HBM (all fp32, channels-last):
+  frames      the caller's own layout, uint8 (B,T,H,W,3) or float (B,3,T,H,W); read in place by the stem
+  activations [F*H*W, C] row-major per layer (F = B*T frames), one value buffer + one gradient buffer
+  BN stats    one float64 arena: per BatchNorm [2C] forward sums + [2C] backward sums, zeroed once per step
+  parameters  ONE flat fp32 buffer (module parameters are views into it) + flat gradient + Adam m, v
+
+Reference structure reproduced: torchvision MobileNetV3-small `features` + avgpool
+(audio_video/models/middle_fusion_fast.py:15-17,34), nn.LSTM with an out[:, -1] head (:18,35-36), the audio
+conv/fc branch (:8-13,28-30), the classifier (:20-25,38-39), CrossEntropyLoss + Adam (audio_video/train.py:129-130).
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import lib, ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_HSIGMOID
+
+_ACT_OF = {nn.ReLU: ACT_RELU, nn.Hardswish: ACT_HSWISH, nn.Hardsigmoid: ACT_HSIGMOID, nn.Identity: ACT_NONE}
+
+
+def _act_code(mod):
+    for k, v in _ACT_OF.items():
+        if isinstance(mod, k):
+            return v
+    raise NotImplementedError(f"activation {type(mod).__name__} has no lipread_b200 kernel")
+
+
+class OpList:
+    """A flat list of (C function, argument tuple); run() appends the stream and checks the status."""
+
+    def __init__(self):
+        self.ops = []
+
+    def add(self, name, *args):
+        self.ops.append((getattr(lib, name), tuple(a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args), name))
+
+    def run(self, stream):
+        for fn, args, name in self.ops:
+            rc = fn(*args, stream)
+            if rc != 0:
+                raise _lib.LipreadError(f"{name} failed ({rc}): {lib.lr_last_error().decode()}")
+
+    def __len__(self):
+        return len(self.ops)
+
+
+def _ksplit(M, N, K, sms, min_k=256):
+    tiles = ((M + 63) // 64) * ((N + 63) // 64)
+    want = max(1, (2 * sms) // tiles)
+    return max(1, min(want, K // min_k if K >= min_k else 1))
+
+
+class FlatParams:
+    """All parameters of a module in ONE flat fp32 buffer (+ gradient, Adam moments); the module's Parameters
+    become views into it, so state_dict()/load_state_dict() keep working with the reference's key names."""
+
+    def __init__(self, module, device):
+        self.module = module
+        self.params = [p for p in module.parameters()]
+        self.device = torch.device(device)
+        offs, n = [], 0
+        for p in self.params:
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4                    # keep every tensor 16-byte aligned
+        self.offsets, self.numel = offs, n
+        self.flat = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.m = None
+        self.v = None
+        self.adam_state = None
+        for p, o in zip(self.params, offs):
+            view = self.flat[o:o + p.numel()].view(p.shape)
+            view.copy_(p.detach().to(self.device, torch.float32))
+            p.data = view
+        self._ptrs = [p.data_ptr() for p in self.params]
+
+    def intact(self):
+        return all(p.data_ptr() == q for p, q in zip(self.params, self._ptrs))
+
+    def g(self, p):
+        """Gradient view of parameter p inside the flat gradient buffer."""
+        for q, o in zip(self.params, self.offsets):
+            if q is p:
+                return self.grad[o:o + p.numel()].view(p.shape)
+        raise KeyError("parameter not owned by this FlatParams")
+
+    def init_adam(self, lr):
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.adam_state = torch.tensor([0.0, 0.0, 0.0, float(lr)], dtype=torch.float32, device=self.device)
+
+
+class T2:
+    """A [rows, C] channels-last activation (value + gradient buffer) with its frame geometry."""
+
+    def __init__(self, plan, F, H, W, C, need_grad=True):
+        self.F, self.H, self.W, self.C = F, H, W, C
+        self.rows = F * H * W
+        self.val = plan.alloc(self.rows * C)
+        self.grad = plan.alloc(self.rows * C) if (need_grad and plan.with_backward) else None
+
+
+class Plan:
+    """Launch plan for one model at one batch shape."""
+
+    def __init__(self, flat, device, training, with_backward):
+        self.flat, self.dev, self.training, self.with_backward = flat, torch.device(device), training, with_backward
+        self.fwd, self.bwd_rev = OpList(), []          # bwd_rev: groups appended in forward order, run reversed
+        self.bufs = []
+        self.sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        self._stat_reqs = []
+        self.stats = None
+
+    # ---- memory
+    def alloc(self, n, dtype=torch.float32):
+        t = torch.empty(max(int(n), 1), dtype=dtype, device=self.dev)
+        self.bufs.append(t)
+        return t
+
+    def stat_slot(self, C):
+        """Reserve [2C] forward + [2C] backward float64 sums; resolved to pointers by finalize()."""
+        slot = {"C": C}
+        self._stat_reqs.append(slot)
+        return slot
+
+    def finalize(self):
+        total = sum(4 * s["C"] for s in self._stat_reqs)
+        self.stats = torch.zeros(max(total, 1), dtype=torch.float64, device=self.dev)
+        self.bufs.append(self.stats)
+        off = 0
+        base = self.stats.data_ptr()
+        for s in self._stat_reqs:
+            s["fwd"] = base + 8 * off
+            s["bwd"] = base + 8 * (off + 2 * s["C"])
+            off += 4 * s["C"]
+        for ops in [self.fwd] + [g for g in self.bwd_rev]:
+            ops.ops = [(fn, tuple(a() if callable(a) else a for a in args), name) for fn, args, name in ops.ops]
+        self.bwd = OpList()
+        for g in reversed(self.bwd_rev):
+            self.bwd.ops.extend(g.ops)
+
+    def bgroup(self):
+        g = OpList()
+        self.bwd_rev.append(g)
+        return g
+
+    # ---- op emitters ----------------------------------------------------------------------------------
+    def gemm(self, ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias=0, act=ACT_NONE, R=0, ldr=0, stats=0, ksplit=1):
+        ops.add("lr_gemm", A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias, act, R, ldr, stats, ksplit)
+
+    def linear(self, x, lda, M, w, b, out, ldc, act=ACT_NONE, stats=0, ksplit=1):
+        N, K = w.shape[0], w[0].numel()
+        self.gemm(self.fwd, x, lda, 0, w, K, 0, out, ldc, M, N, K, bias=(b if b is not None else 0), act=act,
+                  stats=stats, ksplit=ksplit)
+
+    def linear_bwd(self, g, x, lda, M, w, b, dy, ldy, dx=None, ldx=0, dx_residual=0, ldr=0):
+        """dw += dy^T x, db += colsum(dy), dx = dy w (+ residual).  Ops are appended to backward group g."""
+        N, K = w.shape[0], w[0].numel()
+        dw = self.flat.g(w)
+        ks = _ksplit(N, K, M, self.sms)
+        if ks > 1:
+            self.gemm(g, dy, ldy, 1, x, lda, 1, dw, K, N, K, M, ksplit=ks)
+        else:
+            self.gemm(g, dy, ldy, 1, x, lda, 1, dw, K, N, K, M, R=dw, ldr=K)
+        if b is not None:
+            g.add("lr_colsum", dy, ldy, M, N, self.flat.g(b))
+        if dx is not None:
+            self.gemm(g, dy, ldy, 0, w, K, 1, dx, ldx, M, K, N, R=dx_residual, ldr=ldr)
+
+    def bn_act(self, x, bn, act, out, residual=None):
+        """out.val = act(bn(x.val)) (+ residual.val); backward: x.grad from out.grad (residual.grad is out.grad)."""
+        slot = x.stat_slot
+        st = (lambda s=slot: s["fwd"]) if self.training else 0
+        self.fwd.add("lr_bn_act_fwd", x.val, st, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                     bn.num_batches_tracked, float(bn.eps), float(bn.momentum), act, int(self.training),
+                     residual.val if residual is not None else 0, out.val, x.rows, x.C)
+        if self.with_backward:
+            g = self.bgroup()
+            g.add("lr_bn_act_bwd", x.val, st, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.eps), act,
+                  int(self.training), out.grad, (lambda s=slot: s["bwd"]), x.grad, self.flat.g(bn.weight),
+                  self.flat.g(bn.bias), x.rows, x.C)
+
+    def pw_conv(self, x, conv, F, H, W):
+        """1x1 convolution as a GEMM on [rows, Cin]; returns the raw output tensor (with BN statistics slot)."""
+        Cout, Cin = conv.out_channels, conv.in_channels
+        y = T2(self, F, H, W, Cout)
+        y.stat_slot = self.stat_slot(Cout)
+        st = (lambda s=y.stat_slot: s["fwd"]) if self.training else 0
+        self.gemm(self.fwd, x.val, Cin, 0, conv.weight, Cin, 0, y.val, Cout, x.rows, Cout, Cin, stats=st)
+        return y
+
+    def dw_conv(self, x, conv):
+        C, k, s = conv.in_channels, conv.kernel_size[0], conv.stride[0]
+        Ho = (x.H + 2 * (k // 2) - k) // s + 1
+        Wo = (x.W + 2 * (k // 2) - k) // s + 1
+        y = T2(self, x.F, Ho, Wo, C)
+        y.stat_slot = self.stat_slot(C)
+        st = (lambda sl=y.stat_slot: sl["fwd"]) if self.training else self.dummy_stats()
+        self.fwd.add("lr_dwconv_fwd", x.val, conv.weight, y.val, st, x.F, x.H, x.W, C, k, s)
+        if self.with_backward:
+            g = self.bgroup()
+            g.add("lr_dwconv_wgrad", y.grad, x.val, self.flat.g(conv.weight), x.F, x.H, x.W, C, k, s)
+            g.add("lr_dwconv_dgrad", y.grad, conv.weight, x.grad, x.F, x.H, x.W, C, k, s)
+        return y
+
+    def dummy_stats(self):
+        if not hasattr(self, "_dummy"):
+            self._dummy = self.alloc(4096, torch.float64)
+        return self._dummy
+
+    # ---- MobileNetV3 -----------------------------------------------------------------------------------
+    def mbv3_features(self, feats, frames, layout, scale, B, T, H, W):
+        """torchvision `features` Sequential on B*T frames read in the caller's layout -> last activation T2."""
+        stem = feats[0]
+        conv, bn, act = stem[0], stem[1], _act_code(stem[2])
+        assert conv.kernel_size == (3, 3) and conv.stride == (2, 2) and conv.out_channels == 16 and conv.in_channels == 3
+        F = B * T
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        raw = T2(self, F, Ho, Wo, 16)
+        raw.stat_slot = self.stat_slot(16)
+        st = (lambda s=raw.stat_slot: s["fwd"]) if self.training else self.dummy_stats()
+        self.fwd.add("lr_stem_conv_fwd", frames, *layout, float(scale), conv.weight, raw.val, st)
+        if self.with_backward:
+            g = self.bgroup()
+            g.add("lr_stem_conv_wgrad", frames, *layout, float(scale), raw.grad, self.flat.g(conv.weight))
+        cur = T2(self, F, Ho, Wo, 16)
+        self.bn_act(raw, bn, act, cur)
+        for blk in feats[1:]:
+            if hasattr(blk, "block"):
+                cur = self.inverted_residual(blk, cur)
+            else:
+                conv, bn, act = blk[0], blk[1], _act_code(blk[2])
+                assert conv.kernel_size == (1, 1)
+                raw = self.pw_conv(cur, conv, cur.F, cur.H, cur.W)
+                if self.with_backward:
+                    self.linear_bwd(self.bgroup(), cur.val, conv.in_channels, cur.rows, conv.weight, None, raw.grad,
+                                    conv.out_channels, dx=cur.grad, ldx=conv.in_channels)
+                out = T2(self, cur.F, cur.H, cur.W, conv.out_channels)
+                self.bn_act(raw, bn, act, out)
+                cur = out
+        return cur
+
+    def inverted_residual(self, blk, x):
+        """torchvision InvertedResidual: [1x1 expand+BN+act] -> depthwise+BN+act -> [SE] -> 1x1 project+BN (+x)."""
+        layers = list(blk.block)
+        use_res = bool(blk.use_res_connect)
+        cur, deferred = x, []
+        for li, layer in enumerate(layers):
+            last = li == len(layers) - 1
+            if type(layer).__name__ == "SqueezeExcitation":
+                cur = self.squeeze_excite(layer, cur)
+                continue
+            conv, bn = layer[0], layer[1]
+            act = _act_code(layer[2]) if len(layer) > 2 else ACT_NONE
+            if conv.groups == 1:
+                assert conv.kernel_size == (1, 1)
+                raw = self.pw_conv(cur, conv, cur.F, cur.H, cur.W)
+                if self.with_backward:
+                    # Backward groups run in reverse registration order, so the conv's group is registered here
+                    # (before its BatchNorm's) and filled in once the block output -- whose gradient the residual
+                    # branch adds to the block input's -- exists.
+                    deferred.append((self.bgroup(), cur, conv, raw, (cur is x) and use_res))
+            else:
+                assert conv.groups == conv.in_channels
+                if (cur is x) and use_res:
+                    raise NotImplementedError("residual block without an expansion conv")
+                raw = self.dw_conv(cur, conv)
+            out = T2(self, raw.F, raw.H, raw.W, raw.C)
+            self.bn_act(raw, bn, act, out, residual=x if (last and use_res) else None)
+            cur = out
+        for g, inp, conv, raw, add_res in deferred:
+            Cout, Cin = conv.out_channels, conv.in_channels
+            self.linear_bwd(g, inp.val, Cin, inp.rows, conv.weight, None, raw.grad, Cout, dx=inp.grad, ldx=Cin,
+                            dx_residual=(cur.grad if add_res else 0), ldr=Cin)
+        return cur
+
+    def squeeze_excite(self, se, a):
+        """SqueezeExcitation: b = a * hardsigmoid(fc2(relu(fc1(mean_hw(a)))))."""
+        F, HW, C = a.F, a.H * a.W, a.C
+        Cs = se.fc1.out_channels
+        p, h1, s = self.alloc(F * C), self.alloc(F * Cs), self.alloc(F * C)
+        out = T2(self, a.F, a.H, a.W, C)
+        self.fwd.add("lr_frame_reduce", a.val, 0, p, F, HW, C, 0)
+        self.linear(p, C, F, se.fc1.weight, se.fc1.bias, h1, Cs, act=_act_code(se.activation))
+        self.linear(h1, Cs, F, se.fc2.weight, se.fc2.bias, s, C, act=_act_code(se.scale_activation))
+        self.fwd.add("lr_frame_scale", a.val, s, 0, out.val, F, HW, C)
+        if self.with_backward:
+            ds, dh1, dp = self.alloc(F * C), self.alloc(F * Cs), self.alloc(F * C)
+            g = self.bgroup()
+            g.add("lr_frame_reduce", out.grad, a.val, ds, F, HW, C, 1)
+            g.add("lr_act_bwd", ds, s, F * C, _act_code(se.scale_activation))
+            self.linear_bwd(g, h1, Cs, F, se.fc2.weight, se.fc2.bias, ds, C, dx=dh1, ldx=Cs)
+            g.add("lr_act_bwd", dh1, h1, F * Cs, _act_code(se.activation))
+            self.linear_bwd(g, p, C, F, se.fc1.weight, se.fc1.bias, dh1, Cs, dx=dp, ldx=C)
+            g.add("lr_frame_scale", out.grad, s, dp, a.grad, F, HW, C)
+        return out
+
+    def avgpool(self, a):
+        """AdaptiveAvgPool2d(1) + flatten: [F, HW, C] -> feat [F, C] (value, gradient)."""
+        F, HW, C = a.F, a.H * a.W, a.C
+        feat, dfeat = self.alloc(F * C), (self.alloc(F * C) if self.with_backward else None)
+        self.fwd.add("lr_frame_reduce", a.val, 0, feat, F, HW, C, 0)
+        if self.with_backward:
+            g = self.bgroup()
+            g.add("lr_frame_scale", 0, 0, dfeat, a.grad, F, HW, C)
+        return feat, dfeat

@@ -1,0 +1,344 @@
+"""Per-kernel parity on the GPU, through the C ABI, against the torch CPU ops the reference dispatches to
+(nn.Conv2d / BatchNorm2d / LSTM / Linear / CrossEntropyLoss / Adam in fp32).  Tolerances are fp32 round-off:
+the kernels compute in fp32 with a different summation order than MKL/oneDNN."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as Fn
+
+pytestmark = pytest.mark.gpu
+
+ACTS = {0: lambda u: u, 1: Fn.relu, 2: Fn.hardswish, 3: Fn.hardsigmoid}
+
+
+@pytest.fixture(scope="module")
+def K(cuda_device):
+    from multimodal_lipread_b200 import kernels
+    return kernels
+
+
+def _close(a, b, rtol=1e-4, atol=None):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    scale = b.abs().max().item() + 1e-30
+    atol = rtol * scale if atol is None else atol
+    err = (a - b).abs().max().item()
+    assert err <= atol, f"max err {err:.3e} > {atol:.3e} (scale {scale:.3e})"
+
+
+def _cl(x):   # NCHW -> channels-last rows [F*H*W, C]
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("M,N,K_,at,bt", [(300, 72, 16, 0, 0), (129, 40, 96, 0, 1), (88, 24, 1000, 1, 1),
+                                          (64, 64, 64, 0, 0), (7, 5, 3, 0, 0), (33, 130, 50, 1, 0)])
+def test_gemm_layouts(K, M, N, K_, at, bt):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K_, generator=g)
+    B = torch.randn(N, K_, generator=g)
+    ref = A @ B.t()
+    Ad = (A.t().contiguous() if at else A).cuda()
+    Bd = (B.t().contiguous() if bt else B).cuda()
+    C = torch.empty(M, N, device="cuda")
+    K.gemm(Ad, M if at else K_, at, Bd, N if bt else K_, bt, C, N, M, N, K_)
+    _close(C, ref)
+
+
+def test_gemm_epilogues_and_splitk(K):
+    g = torch.Generator().manual_seed(3)
+    M, N, Kd = 500, 88, 24
+    A, B, bias, R = torch.randn(M, Kd, generator=g), torch.randn(N, Kd, generator=g), torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    for act in (0, 1, 3):
+        C = torch.empty(M, N, device="cuda")
+        stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+        K.gemm(A.cuda(), Kd, 0, B.cuda(), Kd, 0, C, N, M, N, Kd, bias=bias.cuda(), act=act, R=R.cuda(), ldr=N, stats=stats)
+        ref = ACTS[act](A @ B.t() + bias) + R
+        _close(C, ref)
+        _close(stats[:N], ref.double().sum(0), rtol=1e-5)
+        _close(stats[N:], (ref.double() ** 2).sum(0), rtol=1e-5)
+    # accumulate (R aliases C) and strided C
+    Cbig = torch.randn(M, 2 * N, generator=g).cuda()
+    base = Cbig.clone()
+    view = Cbig[:, N:]
+    K.gemm(A.cuda(), Kd, 0, B.cuda(), Kd, 0, view, 2 * N, M, N, Kd, R=view, ldr=2 * N)
+    _close(Cbig[:, N:], base[:, N:].cpu() + A @ B.t())
+    assert torch.equal(Cbig[:, :N], base[:, :N])
+    # split-K: wgrad-shaped (long reduction) accumulating atomically onto an existing value
+    Mr = 5000
+    dY, X = torch.randn(Mr, 40, generator=g), torch.randn(Mr, 96, generator=g)
+    dW0 = torch.randn(40, 96, generator=g)
+    dW = dW0.clone().cuda()
+    K.gemm(dY.cuda(), 40, 1, X.cuda(), 96, 1, dW, 96, 40, 96, Mr, ksplit=13)
+    _close(dW, dW0 + dY.t() @ X)
+    # split-K with bias (audio_fc-shaped)
+    x, w, b = torch.randn(8, 3000, generator=g), torch.randn(128, 3000, generator=g), torch.randn(128, generator=g)
+    out = torch.zeros(8, 128, device="cuda")
+    K.linear_fwd(x.cuda(), w.cuda(), out, bias=b.cuda(), ksplit=7)
+    _close(out, x @ w.t() + b)
+
+
+@pytest.mark.parametrize("u8,size", [(True, 44), (False, 44), (True, 30)])
+def test_stem_conv(K, u8, size):
+    from multimodal_lipread_b200 import synthetic
+    B, T = 2, 5
+    lips = synthetic.make_lips_u8(B, size=size)[:, :T].contiguous()            # (B,T,H,W,3) u8
+    video = (lips.float() / 255.0).permute(0, 4, 1, 2, 3).contiguous()        # (B,3,T,H,W) f32 (reference input)
+    conv = nn.Conv2d(3, 16, 3, 2, 1, bias=False)
+    frames = video.permute(0, 2, 1, 3, 4).reshape(B * T, 3, size, size)
+    ref = conv(frames)
+    Ho = ref.shape[2]
+    if u8:
+        x = lips.cuda()
+        layout = (1, B, T, size, size, T * size * size * 3, size * size * 3, 1, size * 3, 3)
+        scale = 1.0 / 255.0
+    else:
+        x = video.cuda()
+        layout = (0, B, T, size, size, 3 * T * size * size, size * size, T * size * size, size, 1)
+        scale = 1.0
+    y = torch.empty(B * T, Ho, Ho, 16, device="cuda")
+    stats = torch.zeros(32, dtype=torch.float64, device="cuda")
+    K.stem_conv_fwd(x, layout, conv.weight.detach().cuda(), y, stats, scale)
+    _close(y, _cl(ref), rtol=2e-5)
+    _close(stats[:16], ref.double().sum((0, 2, 3)), rtol=1e-5)
+    _close(stats[16:], (ref.double() ** 2).sum((0, 2, 3)), rtol=1e-5)
+    dy = torch.randn_like(ref)
+    ref.backward(dy)
+    dw = torch.zeros(16, 3, 3, 3, device="cuda")
+    K.stem_conv_wgrad(x, layout, _cl(dy).cuda(), dw, scale)
+    _close(dw, conv.weight.grad)
+
+
+@pytest.mark.parametrize("C,k,s,H", [(16, 3, 2, 22), (72, 3, 2, 11), (88, 3, 1, 6), (96, 5, 2, 6), (240, 5, 1, 3),
+                                     (576, 5, 1, 2), (288, 5, 2, 3)])
+def test_dwconv(K, C, k, s, H):
+    F = 6
+    g = torch.Generator().manual_seed(C + k)
+    conv = nn.Conv2d(C, C, k, s, k // 2, groups=C, bias=False)
+    x = torch.randn(F, C, H, H, generator=g, requires_grad=True)
+    ref = conv(x)
+    Ho = ref.shape[2]
+    xd = _cl(x.detach()).cuda()
+    w = conv.weight.detach().cuda()
+    y = torch.empty(F, Ho, Ho, C, device="cuda")
+    stats = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    K.dwconv_fwd(xd, w, y, stats, F, H, H, C, k, s)
+    _close(y, _cl(ref), rtol=2e-5)
+    _close(stats[:C], ref.double().sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
+    _close(stats[C:], (ref.double() ** 2).sum((0, 2, 3)), rtol=1e-5)
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy)
+    dyd = _cl(dy).cuda()
+    dx = torch.empty(F, H, H, C, device="cuda")
+    K.dwconv_dgrad(dyd, w, dx, F, H, H, C, k, s)
+    _close(dx, _cl(x.grad), rtol=2e-5)
+    dw = torch.zeros_like(w)
+    K.dwconv_wgrad(dyd, xd, dw, F, H, H, C, k, s)
+    _close(dw, conv.weight.grad, rtol=5e-5)
+
+
+@pytest.mark.parametrize("C,act,res,training", [(16, 2, False, True), (72, 1, False, True), (24, 0, True, True),
+                                                (576, 2, False, True), (40, 0, True, False), (88, 1, False, False)])
+def test_bn_act(K, C, act, res, training):
+    F, H = 5, 7
+    g = torch.Generator().manual_seed(C)
+    bn = nn.BatchNorm2d(C, eps=1e-3, momentum=0.01)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(C, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(C, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(C, generator=g) + 0.5)
+    bn.train(training)
+    x = (torch.randn(F, C, H, H, generator=g) * 2 + 0.3).requires_grad_(True)
+    r = torch.randn(F, C, H, H, generator=g, requires_grad=True) if res else None
+    import copy
+    bnd = copy.deepcopy(bn).cuda()
+    z_ref = ACTS[act](bn(x))
+    if res:
+        z_ref = z_ref + r
+    rows = F * H * H
+    xd = _cl(x.detach()).cuda()
+    x2 = xd.view(rows, C).double()
+    stats = torch.stack([x2.sum(0), (x2 ** 2).sum(0)]).reshape(-1).contiguous()
+    z = torch.empty(rows, C, device="cuda")
+    K.bn_act_fwd(xd, stats if training else None, bnd, act, training, z, rows, C,
+                 residual=_cl(r.detach()).cuda() if res else None)
+    _close(z.view(F, H, H, C), _cl(z_ref), rtol=2e-5)
+    _close(bnd.running_mean, bn.running_mean, rtol=1e-5)
+    _close(bnd.running_var, bn.running_var, rtol=1e-5)
+    assert int(bnd.num_batches_tracked) == int(bn.num_batches_tracked)
+    dz = torch.randn(F, C, H, H, generator=g)
+    z_ref.backward(dz)
+    sums = torch.zeros(2 * C, dtype=torch.float64, device="cuda")
+    dx = torch.empty(rows, C, device="cuda")
+    dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    K.bn_act_bwd(xd, stats if training else None, bnd, act, training, _cl(dz).cuda(), sums, dx, dgamma, dbeta, rows, C)
+    _close(dx.view(F, H, H, C), _cl(x.grad), rtol=1e-4)
+    _close(dgamma, bn.weight.grad, rtol=1e-4)
+    _close(dbeta, bn.bias.grad, rtol=1e-4)
+
+
+def test_frame_ops_and_small_kernels(K):
+    g = torch.Generator().manual_seed(1)
+    F, HW, C = 7, 9, 72
+    a, gt = torch.randn(F, HW, C, generator=g), torch.randn(F, HW, C, generator=g)
+    s, dp = torch.rand(F, C, generator=g), torch.randn(F, C, generator=g)
+    p = torch.empty(F, C, device="cuda")
+    K.frame_reduce(a.cuda(), None, p, F, HW, C, 0)
+    _close(p, a.mean(1))
+    K.frame_reduce(a.cuda(), gt.cuda(), p, F, HW, C, 1)
+    _close(p, (a * gt).sum(1))
+    out = torch.empty(F, HW, C, device="cuda")
+    K.frame_scale(a.cuda(), s.cuda(), None, out, F, HW, C)
+    _close(out, a * s[:, None, :])
+    K.frame_scale(a.cuda(), s.cuda(), dp.cuda(), out, F, HW, C)
+    _close(out, a * s[:, None, :] + dp[:, None, :] / HW)
+    K.frame_scale(None, None, dp.cuda(), out, F, HW, C)
+    _close(out, (dp[:, None, :] / HW).expand(F, HW, C))
+    y = torch.randn(1000, generator=g)
+    for act in (1, 3):
+        yo = ACTS[act](y)
+        dy = torch.randn(1000, generator=g)
+        d = dy.clone().cuda()
+        K.act_bwd(d, yo.cuda(), 1000, act)
+        yy = y.clone().requires_grad_(True)
+        ACTS[act](yy).backward(dy)
+        _close(d, yy.grad)
+    dY = torch.randn(777, 300, generator=g)
+    db = torch.ones(300, device="cuda")
+    K.colsum(dY.cuda(), 300, 777, 300, db)
+    _close(db, 1 + dY.sum(0))
+    src = torch.randn(10, 50, generator=g).cuda()
+    dst = torch.zeros(10, 30, device="cuda")
+    K.copy2d(dst[:, 5:], 30, src[:, 20:], 50, 10, 20)
+    assert torch.equal(dst[:, 5:25], src[:, 20:40]) and dst[:, :5].abs().sum() == 0 and dst[:, 25:].abs().sum() == 0
+
+
+@pytest.mark.parametrize("H,I,B,T", [(128, 576, 6, 29), (32, 20, 5, 4)])
+def test_lstm_direction_kernels(K, H, I, B, T):
+    """Both directions of a bidirectional nn.LSTM layer, full sequence with external gradients at every t."""
+    torch.manual_seed(H)
+    lstm = nn.LSTM(I, H, 1, batch_first=True, bidirectional=True)
+    x = torch.randn(B, T, I, requires_grad=True)
+    out, _ = lstm(x)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    xd = x.detach().cuda()
+    for d, sfx in enumerate(("", "_reverse")):
+        wih, whh = getattr(lstm, "weight_ih_l0" + sfx).detach().cuda(), getattr(lstm, "weight_hh_l0" + sfx).detach().cuda()
+        bih, bhh = getattr(lstm, "bias_ih_l0" + sfx).detach().cuda(), getattr(lstm, "bias_hh_l0" + sfx).detach().cuda()
+        xproj = torch.empty(B * T, 4 * H, device="cuda")
+        K.linear_fwd(xd.view(B * T, I), wih, xproj, bias=bih)
+        o = torch.zeros(B, T, 2 * H, device="cuda")
+        gates, cst, hprev = torch.empty(B, T, 4 * H, device="cuda"), torch.empty(B, T, H, device="cuda"), torch.empty(B, T, H, device="cuda")
+        K.lstm_fwd(xproj, 4 * H, bhh, whh, o[:, :, d * H:], 2 * H, gates, cst, hprev, B, T, H, T, d)
+        _close(o[:, :, d * H:(d + 1) * H], out[:, :, d * H:(d + 1) * H], rtol=2e-5)
+        dg = torch.zeros(B, T, 4 * H, device="cuda")
+        dod = dout.contiguous().cuda()          # nn.LSTM(batch_first) hands back a transposed view
+        K.lstm_bwd(dod[:, :, d * H:], 2 * H, -1, gates, cst, whh, dg, B, T, H, T, d)
+        dwih, dwhh = torch.zeros_like(wih), torch.zeros_like(whh)
+        K.linear_wgrad(dg.view(B * T, 4 * H), xd.view(B * T, I), dwih)
+        K.linear_wgrad(dg.view(B * T, 4 * H), hprev.view(B * T, H), dwhh)
+        db = torch.zeros(4 * H, device="cuda")
+        K.colsum(dg, 4 * H, B * T, 4 * H, db)
+        _close(dwih, getattr(lstm, "weight_ih_l0" + sfx).grad, rtol=1e-4)
+        _close(dwhh, getattr(lstm, "weight_hh_l0" + sfx).grad, rtol=1e-4)
+        _close(db, getattr(lstm, "bias_ih_l0" + sfx).grad, rtol=1e-4)
+        dx = torch.empty(B * T, I, device="cuda")
+        K.linear_dgrad(dg.view(B * T, 4 * H), wih, dx)
+        if d == 0:
+            dx_total = dx.clone()
+        else:
+            dx_total += dx
+    _close(dx_total.view(B, T, I), x.grad, rtol=1e-4)
+
+
+def test_lstm_last_step_only(K):
+    """out[:, -1] head (middle_fusion_fast.py:36): forward direction with a gradient at t = T-1 only, and the
+    reverse direction reduced to its first step."""
+    torch.manual_seed(5)
+    H, I, B, T = 128, 576, 5, 29
+    lstm = nn.LSTM(I, H, 1, batch_first=True, bidirectional=True)
+    x = torch.randn(B, T, I, requires_grad=True)
+    out, _ = lstm(x)
+    last = out[:, -1]
+    dlast = torch.randn(last.shape)
+    last.backward(dlast)
+    xd, dl = x.detach().cuda(), dlast.cuda()
+    P = {n: p.detach().cuda() for n, p in lstm.named_parameters()}
+    fused = torch.zeros(B, 2 * H, device="cuda")
+    # reverse direction: one step on x[:, T-1]
+    xr = torch.empty(B, 4 * H, device="cuda")
+    K.linear_fwd(xd[:, T - 1], P["weight_ih_l0_reverse"], xr, bias=P["bias_ih_l0_reverse"], M=B, lda=T * I)
+    gr, cr = torch.empty(B, 1, 4 * H, device="cuda"), torch.empty(B, 1, H, device="cuda")
+    K.lstm_fwd(xr, 4 * H, P["bias_hh_l0_reverse"], P["weight_hh_l0_reverse"], fused[:, H:], 2 * H, gr, cr, None, B, 1, H, 1, 1)
+    _close(fused[:, H:], last[:, H:], rtol=2e-5)
+    dgr = torch.empty(B, 1, 4 * H, device="cuda")
+    K.lstm_bwd(dl[:, H:], 2 * H, 0, gr, cr, P["weight_hh_l0_reverse"], dgr, B, 1, H, 1, 1)
+    dwih_r = torch.zeros_like(P["weight_ih_l0_reverse"])
+    K.linear_wgrad(dgr.view(B, 4 * H), xd[:, T - 1], dwih_r, M=B, ldx=T * I)
+    _close(dwih_r, lstm.weight_ih_l0_reverse.grad, rtol=1e-4)
+    assert lstm.weight_hh_l0_reverse.grad.abs().max() == 0
+    # forward direction: all steps, gradient only at the last
+    xp = torch.empty(B * T, 4 * H, device="cuda")
+    K.linear_fwd(xd.view(B * T, I), P["weight_ih_l0"], xp, bias=P["bias_ih_l0"])
+    hs = torch.empty(B, T, H, device="cuda")
+    gf, cf, hp = torch.empty(B, T, 4 * H, device="cuda"), torch.empty(B, T, H, device="cuda"), torch.empty(B, T, H, device="cuda")
+    K.lstm_fwd(xp, 4 * H, P["bias_hh_l0"], P["weight_hh_l0"], hs, H, gf, cf, hp, B, T, H, T, 0)
+    K.copy2d(fused, 2 * H, hs[:, T - 1], T * H, B, H)
+    _close(fused[:, :H], last[:, :H], rtol=2e-5)
+    dgf = torch.empty(B, T, 4 * H, device="cuda")
+    K.lstm_bwd(dl, 2 * H, T - 1, gf, cf, P["weight_hh_l0"], dgf, B, T, H, T, 0)
+    dx = torch.empty(B * T, I, device="cuda")
+    K.linear_dgrad(dgf.view(B * T, 4 * H), P["weight_ih_l0"], dx)
+    K.linear_dgrad(dgr.view(B, 4 * H), P["weight_ih_l0_reverse"], dx.view(B, T, I)[:, T - 1], M=B, ldx=T * I, accumulate=True)
+    _close(dx.view(B, T, I), x.grad, rtol=1e-4)
+    dwhh = torch.zeros_like(P["weight_hh_l0"])
+    K.linear_wgrad(dgf.view(B * T, 4 * H), hp.view(B * T, H), dwhh)
+    _close(dwhh, lstm.weight_hh_l0.grad, rtol=1e-4)
+
+
+def test_audio_conv_ce_adam(K):
+    torch.manual_seed(2)
+    B = 3
+    conv = nn.Conv2d(1, 16, 3, padding=1)
+    mel = torch.randn(B, 80, 117)
+    a_ref = Fn.max_pool2d(Fn.relu(conv(mel.unsqueeze(1))), 2).flatten(1)
+    out = torch.zeros(B, 37120 + 8, device="cuda")
+    arg = torch.empty(B * 37120, dtype=torch.uint8, device="cuda")
+    K.audio_conv_fwd(mel.cuda(), conv.weight.detach().cuda(), conv.bias.detach().cuda(), out, 37128, arg, B, 80, 117)
+    _close(out[:, :37120], a_ref, rtol=2e-5)
+    dA = torch.randn_like(a_ref)
+    a_ref.backward(dA)
+    dw, db = torch.zeros(16, 1, 3, 3, device="cuda"), torch.zeros(16, device="cuda")
+    K.audio_conv_bwd(mel.cuda(), dA.cuda(), 37120, arg, dw, db, B, 80, 117)
+    _close(dw, conv.weight.grad, rtol=1e-4)
+    _close(db, conv.bias.grad, rtol=1e-4)
+    # cross entropy
+    for C in (4, 40, 500):
+        logits = torch.randn(9, C, requires_grad=True)
+        labels = torch.randint(0, C, (9,))
+        loss_ref = Fn.cross_entropy(logits, labels)
+        loss_ref.backward()
+        loss = torch.zeros(1, device="cuda")
+        dl = torch.empty(9, C, device="cuda")
+        correct = torch.zeros(1, dtype=torch.int32, device="cuda")
+        K.ce_loss(logits.detach().cuda(), labels.cuda(), loss, dl, correct, 9, C, 1.0 / 9)
+        _close(loss, loss_ref.reshape(1), rtol=1e-5)
+        _close(dl, logits.grad, rtol=1e-4)
+        assert int(correct) == int((logits.argmax(1) == labels).sum())
+    # Adam, three steps, with and without coupled weight decay
+    from multimodal_lipread_b200 import _lib
+    for wd in (0.0, 1e-4):
+        p = torch.randn(1000, requires_grad=True)
+        opt = torch.optim.Adam([p], lr=3e-4, weight_decay=wd)
+        pd = p.detach().clone().cuda()
+        m, v = torch.zeros(1000, device="cuda"), torch.zeros(1000, device="cuda")
+        state = torch.tensor([0.0, 0.0, 0.0, 3e-4], device="cuda")
+        assert _lib.lib.lr_adam_state_bytes() == 16
+        for i in range(3):
+            gr = torch.randn(1000)
+            p.grad = gr.clone()
+            opt.step()
+            K.adam_step(pd, (gr * 4).cuda(), m, v, state, 1000, 0.9, 0.999, 1e-8, wd, 0.25)
+        _close(pd, p, rtol=1e-6)
+        assert float(state[0]) == 3.0

@@ -1,0 +1,175 @@
+"""Whole-model parity of MidFusionFast on the GPU against the oracle (oracle/av_models.py, itself pinned to the
+reference's module by tests/golden/midfusion_golden.npz) on identical seeded inputs and weights.
+
+Tolerances (fp32 kernels vs fp32 torch CPU, different summation orders, 50+ layers deep with train-mode
+BatchNorm): logits / loss 1e-4 relative; every parameter gradient max|d| <= 2e-3 * max|ref| (norm-wise);
+argmax identical; weights after one Adam step within 2e-3 * lr (Adam's first step is lr * sign-like, so it
+amplifies round-off in tiny gradients)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.av_models import MidFusionFastOracle
+from oracle.frontend import AudioProcessorPort, lips_u8_to_model_input
+
+pytestmark = pytest.mark.gpu
+
+C = 40
+
+
+def _inputs(B, size, T=29):
+    from multimodal_lipread_b200 import synthetic
+    wav = synthetic.make_waveforms(B, pad_fraction=0.5)
+    lips = synthetic.make_lips_u8(B, size=size)[:, :T].contiguous()
+    labels = synthetic.make_labels(B, C)
+    mel = AudioProcessorPort().batch_frontend_loop(wav)
+    return wav, mel, lips, labels
+
+
+def _pair(seed=0):
+    from multimodal_lipread_b200.audio_video_models import MidFusionFast
+    torch.manual_seed(seed)
+    ref = MidFusionFastOracle(C)
+    torch.manual_seed(seed)
+    ours = MidFusionFast(C)
+    sd_ref, sd = ref.state_dict(), ours.state_dict()
+    assert list(sd_ref.keys()) == list(sd.keys())
+    for k in sd:                                        # same construction order => same seeded init
+        assert torch.equal(sd_ref[k], sd[k]), k
+    return ref, ours.cuda()
+
+
+def _rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-30)
+
+
+GRAD_FLOOR = 1e-7   # gradients that are exactly zero in exact arithmetic (a BatchNorm bias feeding conv -> train-mode
+                    # BatchNorm, W_hh of the one-step reverse LSTM) are ~1e-9 round-off noise in BOTH implementations
+
+
+def _grad_err(a, b):
+    """max|a-b| relative to max|b|, with an absolute floor for gradients that are pure round-off noise."""
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return (a - b).abs().max().item() / (b.abs().max().item() + GRAD_FLOOR / 2e-3)
+
+
+@pytest.mark.parametrize("size,B", [(44, 4), (88, 2)])
+def test_train_step_matches_oracle(cuda_device, size, B):
+    ref, ours = _pair()
+    wav, mel, lips, labels = _inputs(B, size)
+    ref.train()
+    ours.train()
+    opt = torch.optim.Adam(ref.parameters(), lr=3e-4)
+    opt.zero_grad()
+    logits_ref = ref(mel, lips_u8_to_model_input(lips))
+    loss_ref = torch.nn.functional.cross_entropy(logits_ref, labels)
+    loss_ref.backward()
+    gref = {n: p.grad.clone() for n, p in ref.named_parameters()}
+    opt.step()
+
+    ours.configure_optimizer(lr=3e-4)
+    w0 = {n: p.detach().clone() for n, p in ours.named_parameters()}
+    loss, logits = ours.train_step(mel.cuda(), lips.cuda(), labels.cuda(), use_graph=False)
+    torch.cuda.synchronize()
+    assert _rel(logits, logits_ref) <= 1e-4, _rel(logits, logits_ref)
+    assert abs(loss.item() - loss_ref.item()) <= 1e-4 * abs(loss_ref.item())
+    assert torch.equal(logits.argmax(1).cpu(), logits_ref.argmax(1))
+    flat = ours._flat
+    worst = {}
+    for n, p in ours.named_parameters():
+        worst[n] = _grad_err(flat.g(p), gref[n])
+    bad = {n: e for n, e in worst.items() if e > 2e-3}
+    assert not bad, bad
+    # one Adam step
+    for (n, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+        step_ref = (q.detach() - w0[n].cpu())
+        step = (p.detach().cpu() - w0[n].cpu())
+        assert (step - step_ref).abs().max().item() <= 0.05 * 3e-4 + 1e-7, n
+    # BatchNorm running statistics and counters follow torch's update rule
+    sd_ref, sd = ref.state_dict(), ours.state_dict()
+    for k in sd:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            assert _rel(sd[k], sd_ref[k]) <= 1e-4, k
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(sd_ref[k]) == 1, k
+
+
+def test_golden_vectors_of_the_reference(cuda_device, golden_dir):
+    """Outputs recorded from the reference's own MidFusionFast (tests/golden/make_golden.py)."""
+    mg = np.load(os.path.join(golden_dir, "midfusion_golden.npz"))
+    for size in (44, 88):
+        _, ours = _pair()
+        ours.train()
+        wav, mel, lips, labels = _inputs(2, size)
+        ours.configure_optimizer(lr=3e-4)
+        loss, logits = ours.train_step(mel.cuda(), lips.cuda(), labels.cuda(), use_graph=False)
+        assert _rel(logits, torch.from_numpy(mg[f"logits_{size}"])) <= 1e-4
+        assert abs(loss.item() - float(mg[f"loss_{size}"])) <= 1e-4
+        names = list(mg["param_names"])
+        flat = ours._flat
+        gn = np.array([flat.g(p).double().norm().item() for _, p in ours.named_parameters()])
+        assert [n for n, _ in ours.named_parameters()] == names
+        np.testing.assert_allclose(gn, mg[f"grad_norm_{size}"], rtol=2e-3, atol=1e-6)
+        sd = ours.state_dict()
+        assert _rel(sd["video_cnn.features.0.1.running_mean"], torch.from_numpy(mg[f"rm_stem_{size}"])) <= 1e-4
+        assert _rel(sd["video_cnn.features.12.1.running_var"], torch.from_numpy(mg[f"rv_last_{size}"])) <= 1e-4
+        ours.eval()
+        with torch.no_grad():
+            out = ours(mel.cuda(), lips_u8_to_model_input(lips).cuda())
+        # eval logits were recorded AFTER the reference's Adam step and BN update: same here
+        assert _rel(out, torch.from_numpy(mg[f"logits_eval_{size}"])) <= 2e-3
+
+
+def test_module_surface_forward_backward_and_raw_inputs(cuda_device):
+    """Drop-in use: model(audio, video) -> logits with torch autograd + torch.optim, float (B,3,T,H,W) video as the
+    reference's DataLoader delivers it; and the raw-input path (waveform + uint8 frames) gives the same logits."""
+    ref, ours = _pair(seed=1)
+    B, size = 3, 44
+    wav, mel, lips, labels = _inputs(B, size)
+    video = lips_u8_to_model_input(lips)
+    ref.train(); ours.train()
+    out_ref = ref(mel, video)
+    torch.nn.functional.cross_entropy(out_ref, labels).backward()
+    out = ours(mel.cuda(), video.cuda())
+    assert out.shape == (B, C) and out.requires_grad
+    loss = torch.nn.functional.cross_entropy(out, labels.cuda())
+    loss.backward()
+    assert _rel(out, out_ref) <= 1e-4
+    for (n, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+        assert _grad_err(p.grad, q.grad) <= 2e-3, n
+    # raw inputs: waveform through the fused log-mel kernel, uint8 frames read in place
+    _, ours2 = _pair(seed=1)
+    ours2.train()
+    ours2.configure_optimizer(lr=0.0)
+    _, logits_raw = ours2.train_step(wav.cuda(), lips.cuda(), labels.cuda(), use_graph=False)
+    assert _rel(logits_raw, out_ref) <= 2e-4
+    # eval mode (running statistics), no grad
+    ref.eval(); ours.eval()
+    with torch.no_grad():
+        assert _rel(ours(mel.cuda(), video.cuda()), ref(mel, video)) <= 1e-4
+    # state_dict round trip with the reference's key names
+    sd = {k: v.cpu() for k, v in ours.state_dict().items()}
+    ref.load_state_dict(sd)
+    with pytest.raises(Exception):
+        ours(mel, video)                                   # CPU tensors: no CPU path
+
+
+def test_cuda_graph_step_equals_eager_and_trains(cuda_device):
+    _, a = _pair(seed=2)
+    _, b = _pair(seed=2)
+    B, size = 4, 44
+    wav, mel, lips, labels = _inputs(B, size)
+    a.train(); b.train()
+    a.configure_optimizer(lr=1e-3); b.configure_optimizer(lr=1e-3)
+    losses = []
+    for i in range(4):
+        la, _ = a.train_step(wav.cuda(), lips.cuda(), labels.cuda(), use_graph=False)
+        lb, _ = b.train_step(wav.cuda(), lips.cuda(), labels.cuda(), use_graph=True)
+        assert abs(la.item() - lb.item()) <= 2e-4 * abs(la.item()), i
+        losses.append(lb.item())
+    assert losses[-1] < losses[0]                          # the same batch repeated: the loss must fall
+    assert int(b.state_dict()["video_cnn.features.0.1.num_batches_tracked"]) == 4
+    assert float(b._flat.adam_state[0]) == 4.0
