@@ -90,13 +90,14 @@ int lr_gemm(const float* A, long long lda, int a_trans, const float* B, long lon
             long long ldc, int M, int N, int K, const float* bias, int act, const float* R, long long ldr,
             double* stats, int ksplit, lr_stream_t stream);
 
-/* Tensor-core variant of the "NT" GEMM (a_trans = b_trans = 0): C[M,N] = act(A[M,K].B[N,K]^T + bias) + R with
- * TF32 products and fp32 accumulation (tcgen05.mma kind::tf32, operands fetched by TMA from the fp32 matrices
- * where they live, accumulator in TMEM).  Same epilogue as lr_gemm (bias, act, residual, double column
- * statistics).  lda and ldb must be multiples of 4 floats, A and B 16-byte aligned.  Used for the 1x1
- * convolutions of the trunk (forward, and dgrad against a transposed weight copy). */
-int lr_gemm_tf32(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int M, int N,
-                 int K, const float* bias, int act, const float* R, long long ldr, double* stats, lr_stream_t stream);
+/* Tensor-core variant of lr_gemm (same layout flags and epilogue): TF32 products with fp32 accumulation
+ * (tcgen05.mma kind::tf32; operands fetched by TMA from the fp32 matrices where they live, K-major or MN-major
+ * with the 128-byte swizzle; accumulator in TMEM).  lda and ldb must be multiples of 4 floats, A and B 16-byte
+ * aligned.  ksplit > 1 splits the reduction over CTAs and adds the partial tiles into C atomically (wgrad).
+ * Used for the 1x1 convolutions of the trunk: forward (NT), dgrad (NN) and wgrad (TN). */
+int lr_gemm_tf32(const float* A, long long lda, int a_trans, const float* B, long long ldb, int b_trans, float* C,
+                 long long ldc, int M, int N, int K, const float* bias, int act, const float* R, long long ldr,
+                 double* stats, int ksplit, lr_stream_t stream);
 
 /* MobileNetV3 stem: Conv2d(3,16,3,stride=2,padding=1,bias=False) on frames addressed in the caller's own
  * layout: element (b, t, c, h, w) at x[b*sb + t*st + c*sc + h*sh + w*sw] (uint8 if is_u8 else float), times

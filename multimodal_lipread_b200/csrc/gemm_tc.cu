@@ -27,6 +27,8 @@ constexpr int A_STAGE_BYTES = BM * BK * 4;     // 16 KB
 
 struct P {
     int M, N, K, BN, stages;
+    int kchunk;          // reduce-dimension elements handled by one CTA (multiple of BK); gridDim.z CTAs split K
+    int atomic_out;      // 1: C += tile with red.global.add (split-K wgrad); bias / act / residual / stats unused
     float* C; long long ldc;
     const float* bias; const float* R; long long ldr;
     double* stats;
@@ -67,9 +69,19 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
 }
-// instruction descriptor, kind::tf32: D = F32, A = B = TF32, both K-major, M = 128, N = bn
-__device__ __forceinline__ uint32_t make_idesc_tf32(int bn) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// MN-major operand.  For 32-bit (tf32) operands the only MN-major shared-memory layout the tensor core accepts
+// is the 128-byte swizzle with a 32-byte base (layout type 1, CUTLASS Layout_MN_SW128_32B_Atom; TMA writes it
+// with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): the tile is stored as chunks of 32 MN-contiguous floats; inside a
+// chunk the 32 reduce-rows sit at a 128 B pitch, the swizzle atom is 4 rows (SBO = 512 B between 4-row groups),
+// chunks are 4096 B apart (= LBO).
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+           (1ull << 46) | (1ull << 61);
+}
+// instruction descriptor, kind::tf32: D = F32, A = B = TF32, M = 128, N = bn; bit 15 / 16: A / B is MN-major
+__device__ __forceinline__ uint32_t make_idesc_tf32(int bn, bool a_mn, bool b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
+           ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -139,6 +151,7 @@ __device__ __forceinline__ int colsum16_col(int lane) {
     return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const P p) {
     extern __shared__ uint8_t smem_raw[];
@@ -148,8 +161,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.BN;
-    const int num_kb = (p.K + BK - 1) / BK;
-    const uint32_t b_stage_bytes = (uint32_t)p.BN * BK * 4;
+    const int kbeg = blockIdx.z * p.kchunk;
+    const int kend = min(p.K, kbeg + p.kchunk);
+    const int num_kb = (kend - kbeg + BK - 1) / BK;
+    const int b_chunks = (p.BN + 31) / 32;
+    const uint32_t b_stage_bytes = B_MN ? (uint32_t)b_chunks * 4096u : (uint32_t)p.BN * BK * 4;
     const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
     const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;        // 1024 B alignment for SWIZZLE_128B
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[MAX_STAGES]);
@@ -181,23 +197,37 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 const uint32_t a_dst = tiles + s * stage_bytes, b_dst = a_dst + A_STAGE_BYTES;
                 mbar_expect_tx(full0 + 8 * s, stage_bytes);
-                tma_load_2d(a_dst, &tmA, full0 + 8 * s, kb * BK, m0);
-                tma_load_2d(b_dst, &tmB, full0 + 8 * s, kb * BK, n0);
+                const int k0 = kbeg + kb * BK;
+                if (A_MN) {
+#pragma unroll
+                    for (int c = 0; c < BM / 32; ++c) tma_load_2d(a_dst + c * 4096, &tmA, full0 + 8 * s, m0 + c * 32, k0);
+                } else {
+                    tma_load_2d(a_dst, &tmA, full0 + 8 * s, k0, m0);
+                }
+                if (B_MN) {
+                    for (int c = 0; c < b_chunks; ++c) tma_load_2d(b_dst + c * 4096, &tmB, full0 + 8 * s, n0 + c * 32, k0);
+                } else {
+                    tma_load_2d(b_dst, &tmB, full0 + 8 * s, k0, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(p.BN);
+            const uint32_t idesc = make_idesc_tf32(p.BN, A_MN, B_MN);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % p.stages;
                 const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
                 mbar_wait(full0 + 8 * s, ph);
                 fence_after();
                 const uint32_t a_src = tiles + s * stage_bytes, b_src = a_src + A_STAGE_BYTES;
-                const uint64_t adesc = make_desc_k_sw128(a_src), bdesc = make_desc_k_sw128(b_src);
+                const uint64_t adesc = A_MN ? make_desc_mn_sw128(a_src) : make_desc_k_sw128(a_src);
+                const uint64_t bdesc = B_MN ? make_desc_mn_sw128(b_src) : make_desc_k_sw128(b_src);
+                // one MMA consumes 8 reduce-elements: K-major: 32 bytes along the swizzled row (2 address units);
+                // MN-major: one 8-row group = 1024 bytes (64 address units)
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k)        // 8 tf32 = 32 bytes = 2 descriptor address units per MMA
-                    mma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < BK / 8; ++k)
+                    mma_tf32(tmem_d, adesc + (A_MN ? 64 : 2) * k, bdesc + (B_MN ? 64 : 2) * k, idesc,
+                             (kb > 0 || k > 0) ? 1u : 0u);
                 mma_commit(empty0 + 8 * s);
             }
             mma_commit(tmem_full);
@@ -217,6 +247,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float v[16];
             tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             const bool full16 = n + 15 < p.N;
+            if (p.atomic_out) {
+                if (row_ok && num_kb > 0) {
+                    float* cr = p.C + (long long)row * p.ldc + n;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (n + j < p.N) atomicAdd(cr + j, v[j]);
+                }
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
                 float x = v[j];
@@ -292,7 +330,8 @@ static EncodeTiledFn encode_fn() {
 }
 
 // row-major fp32 matrix [rows][cols] (ld floats) -> tensor map with a {32 floats, box_rows} box, 128 B swizzle
-static int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+static int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows,
+                    bool mn_major = false) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return lr::fail(LR_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -300,7 +339,8 @@ static int make_map(CUtensorMap* map, const float* base, long long rows, long lo
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return lr::fail(LR_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return LR_OK;
@@ -308,36 +348,54 @@ static int make_map(CUtensorMap* map, const float* base, long long rows, long lo
 
 }  // namespace tc
 
-extern "C" int lr_gemm_tf32(const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
-                            int M, int N, int K, const float* bias, int act, const float* R, long long ldr,
-                            double* stats, lr_stream_t stream) {
+extern "C" int lr_gemm_tf32(const float* A, long long lda, int a_trans, const float* B, long long ldb, int b_trans,
+                            float* C, long long ldc, int M, int N, int K, const float* bias, int act, const float* R,
+                            long long ldr, double* stats, int ksplit, lr_stream_t stream) {
     LR_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "lr_gemm_tf32: bad dimension");
     if (M == 0 || N == 0) return LR_OK;
     LR_CHECK_ARG(A && B && C, "lr_gemm_tf32: null pointer");
     LR_CHECK_ARG(act >= LR_ACT_NONE && act <= LR_ACT_HSIGMOID, "lr_gemm_tf32: bad activation %d", act);
     LR_CHECK_ARG((lda & 3) == 0 && (ldb & 3) == 0, "lr_gemm_tf32: lda / ldb must be multiples of 4 floats (TMA 16-byte stride)");
+    LR_CHECK_ARG(ksplit >= 1, "lr_gemm_tf32: ksplit must be >= 1");
+    LR_CHECK_ARG(ksplit == 1 || (act == LR_ACT_NONE && !R && !stats && !bias),
+                 "lr_gemm_tf32: split-K accumulates atomically and cannot fuse bias / act / residual / stats");
     LR_CHECK_ALIGN(A); LR_CHECK_ALIGN(B);
     const int ntile = (N + 255) / 256;
     int bn = (N + ntile - 1) / ntile;
     bn = (bn + 15) / 16 * 16;
     tc::P p;
     p.M = M; p.N = N; p.K = K; p.BN = bn; p.C = C; p.ldc = ldc; p.bias = bias; p.R = R; p.ldr = ldr; p.stats = stats; p.act = act;
-    const int num_kb = (K + tc::BK - 1) / tc::BK;
+    int kchunk = (K + ksplit - 1) / ksplit;
+    kchunk = (kchunk + tc::BK - 1) / tc::BK * tc::BK;
+    const int nz = (K + kchunk - 1) / kchunk;
+    p.kchunk = kchunk;
+    p.atomic_out = ksplit > 1 ? 1 : 0;
+    const int num_kb = kchunk / tc::BK;
     p.stages = num_kb < tc::MAX_STAGES ? num_kb : tc::MAX_STAGES;
     CUtensorMap ma, mb;
-    int rc = tc::make_map(&ma, A, M, K, lda, tc::BM);
+    int rc = a_trans ? tc::make_map(&ma, A, K, M, lda, 32, true) : tc::make_map(&ma, A, M, K, lda, tc::BM);
     if (rc) return rc;
-    rc = tc::make_map(&mb, B, N, K, ldb, bn);
+    rc = b_trans ? tc::make_map(&mb, B, K, N, ldb, 32, true) : tc::make_map(&mb, B, N, K, ldb, bn);
     if (rc) return rc;
-    const size_t smem = (size_t)p.stages * (tc::A_STAGE_BYTES + (size_t)bn * tc::BK * 4) + 1024;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const size_t b_stage = b_trans ? (size_t)((bn + 31) / 32) * 4096 : (size_t)bn * tc::BK * 4;
+    const size_t smem = (size_t)p.stages * (tc::A_STAGE_BYTES + b_stage) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc::gemm_tf32_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tf32_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tf32_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tf32_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return lr::fail(LR_ECUDA, "lr_gemm_tf32 smem: %s", cudaGetErrorString(e));
-        configured = 200 * 1024;
+        configured = true;
     }
-    dim3 grid((unsigned)((M + tc::BM - 1) / tc::BM), (unsigned)((N + bn - 1) / bn));
-    tc::gemm_tf32_kernel<<<grid, tc::THREADS, smem, stream>>>(ma, mb, p);
+    dim3 grid((unsigned)((M + tc::BM - 1) / tc::BM), (unsigned)((N + bn - 1) / bn), (unsigned)nz);
+    if (a_trans) {
+        if (b_trans) tc::gemm_tf32_kernel<true, true><<<grid, tc::THREADS, smem, stream>>>(ma, mb, p);
+        else tc::gemm_tf32_kernel<true, false><<<grid, tc::THREADS, smem, stream>>>(ma, mb, p);
+    } else {
+        if (b_trans) tc::gemm_tf32_kernel<false, true><<<grid, tc::THREADS, smem, stream>>>(ma, mb, p);
+        else tc::gemm_tf32_kernel<false, false><<<grid, tc::THREADS, smem, stream>>>(ma, mb, p);
+    }
     lr::count_launch();
     LR_CHECK_LAUNCH("gemm_tf32_kernel");
     return LR_OK;

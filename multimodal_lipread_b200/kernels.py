@@ -132,6 +132,8 @@ def copy2d(dst, ldd, src, lds, rows, cols):
     check(lib.lr_copy2d(_p(dst), ldd, _p(src), lds, rows, cols, _s()))
 
 
-def gemm_tf32(A, lda, B, ldb, C, ldc, M, N, K, bias=None, act=ACT_NONE, R=None, ldr=0, stats=None):
-    """Tensor-core NT GEMM (TF32 products, fp32 accumulate): C = act(A[M,K] @ B[N,K]^T + bias) + R."""
-    check(lib.lr_gemm_tf32(_p(A), lda, _p(B), ldb, _p(C), ldc, M, N, K, _p(bias), act, _p(R), ldr, _p(stats), _s()))
+def gemm_tf32(A, lda, a_trans, B, ldb, b_trans, C, ldc, M, N, K, bias=None, act=ACT_NONE, R=None, ldr=0, stats=None,
+              ksplit=1):
+    """Tensor-core GEMM (TF32 products, fp32 accumulate), same layout flags / epilogue as gemm()."""
+    check(lib.lr_gemm_tf32(_p(A), lda, a_trans, _p(B), ldb, b_trans, _p(C), ldc, M, N, K, _p(bias), act, _p(R), ldr,
+                           _p(stats), ksplit, _s()))

@@ -18,7 +18,7 @@ def test_gemm_tf32_shapes(cuda_device, M, N, K):
     ref = A.double() @ B.double().t()
     C = torch.full((M, N), float("nan"), device="cuda")
     stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
-    Kn.gemm_tf32(A.cuda(), K, B.cuda(), K, C, N, M, N, K, stats=stats)
+    Kn.gemm_tf32(A.cuda(), K, 0, B.cuda(), K, 0, C, N, M, N, K, stats=stats)
     torch.cuda.synchronize()
     assert torch.isfinite(C).all()
     err = (C.cpu().double() - ref).abs().max().item()
@@ -36,9 +36,40 @@ def test_gemm_tf32_epilogue_and_strides(cuda_device):
     bias, R = torch.randn(N, generator=g), torch.randn(M, N + 4, generator=g)
     Cbig = torch.zeros(M, N + 12, device="cuda")
     for act, fn in ((0, lambda u: u), (1, torch.relu), (2, torch.nn.functional.hardswish)):
-        Kn.gemm_tf32(A.cuda(), K + 8, B.cuda(), K, Cbig[:, 4:], N + 12, M, N, K, bias=bias.cuda(), act=act,
+        Kn.gemm_tf32(A.cuda(), K + 8, 0, B.cuda(), K, 0, Cbig[:, 4:], N + 12, M, N, K, bias=bias.cuda(), act=act,
                      R=R.cuda(), ldr=N + 4)
         ref = fn(A[:, :K].double() @ B.double().t() + bias.double()) + R[:, :N].double()
         err = (Cbig[:, 4:4 + N].cpu().double() - ref).abs().max().item()
         assert err <= 2e-3 * ref.abs().max().item(), (act, err)
         assert Cbig[:, :4].abs().sum().item() == 0 and Cbig[:, 4 + N:].abs().sum().item() == 0
+
+
+# dgrad shapes: dX[M, Cin] = dY[M, Cout] @ W[Cout, Cin]  (B stored [K][N]: MN-major operand)
+@pytest.mark.parametrize("M,Cout,Cin", [(4000, 72, 16), (1000, 24, 72), (300, 576, 96), (333, 96, 576), (2000, 288, 48),
+                                        (129, 16, 16), (640, 40, 240), (500, 88, 24)])
+def test_gemm_tf32_dgrad_layout(cuda_device, M, Cout, Cin):
+    from multimodal_lipread_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(M + Cout)
+    dY, W, R = torch.randn(M, Cout, generator=g), torch.randn(Cout, Cin, generator=g), torch.randn(M, Cin, generator=g)
+    ref = dY.double() @ W.double() + R.double()
+    dX = torch.full((M, Cin), float("nan"), device="cuda")
+    Kn.gemm_tf32(dY.cuda(), Cout, 0, W.cuda(), Cin, 1, dX, Cin, M, Cin, Cout, R=R.cuda(), ldr=Cin)
+    err = (dX.cpu().double() - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+# wgrad shapes: dW[Cout, Cin] += dY[M, Cout]^T @ X[M, Cin]  (both operands MN-major, split over the M rows)
+@pytest.mark.parametrize("M,Cout,Cin,ks", [(40000, 72, 16, 37), (9000, 24, 72, 8), (3000, 576, 96, 5), (3333, 96, 576, 3),
+                                           (2000, 288, 48, 1), (129, 16, 16, 1), (5000, 40, 240, 11), (70, 88, 24, 2)])
+def test_gemm_tf32_wgrad_layout(cuda_device, M, Cout, Cin, ks):
+    from multimodal_lipread_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(M + Cin)
+    dY, X, W0 = torch.randn(M, Cout, generator=g), torch.randn(M, Cin, generator=g), torch.randn(Cout, Cin, generator=g)
+    ref = W0.double() + dY.double().t() @ X.double()
+    dW = W0.clone().cuda()
+    if ks > 1:
+        Kn.gemm_tf32(dY.cuda(), Cout, 1, X.cuda(), Cin, 1, dW, Cin, Cout, Cin, M, ksplit=ks)
+    else:
+        Kn.gemm_tf32(dY.cuda(), Cout, 1, X.cuda(), Cin, 1, dW, Cin, Cout, Cin, M, R=dW, ldr=Cin)
+    err = (dW.cpu().double() - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
