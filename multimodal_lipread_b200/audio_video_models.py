@@ -43,7 +43,7 @@ class MidFusionPlan(engine.Plan):
     """Launch plan of MidFusionFast at one batch shape."""
 
     def __init__(self, model, flat, key, device, training, with_backward, from_wav):
-        super().__init__(flat, device, training, with_backward)
+        super().__init__(flat, device, training, with_backward, precision=model.precision)
         kind, B, T, H, W = key[:5]
         self.B, self.T, self.num_classes = B, T, model.num_classes
         self.from_wav = from_wav
@@ -189,10 +189,13 @@ class _PlanFn(torch.autograd.Function):
 class MidFusionFast(nn.Module):
     """audio_video/models/middle_fusion_fast.py:5-39."""
 
-    def __init__(self, num_classes, config=None, pretrained_state_dict=None):
+    def __init__(self, num_classes, config=None, pretrained_state_dict=None, precision=None):
         super().__init__()
         config = config or _Cfg()
         self.num_classes = num_classes
+        # "tf32": trunk GEMMs on the tensor cores (TF32 products, fp32 accumulate; >= the bf16 the north star
+        # allows); "fp32": every kernel in fp32 SIMT arithmetic (strict parity with the reference's fp32 path)
+        self.precision = precision or config.get("precision.compute", "tf32")
         # construction order == the reference's, so a seeded init draws identical values
         self.audio_cnn = nn.Sequential(
             nn.Conv2d(config.get("dataset.audio_channels", 1), 16, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2))
@@ -240,7 +243,7 @@ class MidFusionFast(nn.Module):
             raise _lib.LipreadError("multimodal_lipread_b200 models run on CUDA only (no CPU path)")
         flat = self._ensure_flat(dev)
         layout, _ = _video_layout(video)
-        key = layout[:5] + (bool(training), bool(with_backward), bool(from_wav))
+        key = layout[:5] + (bool(training), bool(with_backward), bool(from_wav), self.precision)
         plan = self._plans.get(key)
         if plan is None:
             plan = MidFusionPlan(self, flat, key, dev, training, with_backward, from_wav)

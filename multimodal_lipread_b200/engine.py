@@ -109,8 +109,13 @@ class T2:
 class Plan:
     """Launch plan for one model at one batch shape."""
 
-    def __init__(self, flat, device, training, with_backward):
+    def __init__(self, flat, device, training, with_backward, precision="tf32"):
+        """precision: "tf32" -- the GEMMs with enough rows run on the tensor cores (tcgen05, TF32 products, fp32
+        accumulate); "fp32" -- every GEMM on the fp32 SIMT kernel (strict-parity mode)."""
+        if precision not in ("tf32", "fp32"):
+            raise ValueError(f"precision must be 'tf32' or 'fp32', got {precision!r}")
         self.flat, self.dev, self.training, self.with_backward = flat, torch.device(device), training, with_backward
+        self.tc = precision == "tf32"
         self.fwd, self.bwd_rev = OpList(), []          # bwd_rev: groups appended in forward order, run reversed
         self.bufs = []
         self.sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
@@ -154,24 +159,50 @@ class Plan:
     def gemm(self, ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias=0, act=ACT_NONE, R=0, ldr=0, stats=0, ksplit=1):
         ops.add("lr_gemm", A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias, act, R, ldr, stats, ksplit)
 
+    def use_tc(self, M, N, K, lda, ldb):
+        """Tensor-core path for GEMMs that stream many rows (1x1 convs, SE / LSTM projections over all frames);
+        tiny GEMMs (head, per-clip vectors) stay on the SIMT kernel.  TMA needs 16-byte row pitches."""
+        return self.tc and lda % 4 == 0 and ldb % 4 == 0 and max(M, K) >= 512
+
+    def gemm_auto(self, ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias=0, act=ACT_NONE, R=0, ldr=0, stats=0,
+                  split_ok=False):
+        """Emit one GEMM, choosing the tcgen05 kernel when it pays; split_ok: the caller accumulates into a
+        pre-initialised C, so the reduction may be split over CTAs with atomic adds."""
+        if self.use_tc(M, N, K, lda, ldb):
+            ks = 1
+            if split_ok:
+                bn_tiles = ((M + 127) // 128) * ((N + 255) // 256)
+                ks = max(1, min((K + 255) // 256, (2 * self.sms) // bn_tiles))
+            if ks > 1:
+                ops.add("lr_gemm_tf32", A, lda, at, B, ldb, bt, C, ldc, M, N, K, 0, ACT_NONE, 0, 0, 0, ks)
+            else:
+                ops.add("lr_gemm_tf32", A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias, act, (C if split_ok else R),
+                        (ldc if split_ok else ldr), stats, 1)
+            return
+        ks = _ksplit(M, N, K, self.sms) if split_ok else 1
+        if ks > 1:
+            self.gemm(ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, ksplit=ks)
+        else:
+            self.gemm(ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias=bias, act=act, R=(C if split_ok else R),
+                      ldr=(ldc if split_ok else ldr), stats=stats)
+
     def linear(self, x, lda, M, w, b, out, ldc, act=ACT_NONE, stats=0, ksplit=1):
         N, K = w.shape[0], w[0].numel()
-        self.gemm(self.fwd, x, lda, 0, w, K, 0, out, ldc, M, N, K, bias=(b if b is not None else 0), act=act,
-                  stats=stats, ksplit=ksplit)
+        if ksplit > 1:
+            self.gemm(self.fwd, x, lda, 0, w, K, 0, out, ldc, M, N, K, bias=(b if b is not None else 0), ksplit=ksplit)
+        else:
+            self.gemm_auto(self.fwd, x, lda, 0, w, K, 0, out, ldc, M, N, K, bias=(b if b is not None else 0), act=act,
+                           stats=stats)
 
     def linear_bwd(self, g, x, lda, M, w, b, dy, ldy, dx=None, ldx=0, dx_residual=0, ldr=0):
         """dw += dy^T x, db += colsum(dy), dx = dy w (+ residual).  Ops are appended to backward group g."""
         N, K = w.shape[0], w[0].numel()
         dw = self.flat.g(w)
-        ks = _ksplit(N, K, M, self.sms)
-        if ks > 1:
-            self.gemm(g, dy, ldy, 1, x, lda, 1, dw, K, N, K, M, ksplit=ks)
-        else:
-            self.gemm(g, dy, ldy, 1, x, lda, 1, dw, K, N, K, M, R=dw, ldr=K)
+        self.gemm_auto(g, dy, ldy, 1, x, lda, 1, dw, K, N, K, M, split_ok=True)       # dw += dy^T x
         if b is not None:
             g.add("lr_colsum", dy, ldy, M, N, self.flat.g(b))
         if dx is not None:
-            self.gemm(g, dy, ldy, 0, w, K, 1, dx, ldx, M, K, N, R=dx_residual, ldr=ldr)
+            self.gemm_auto(g, dy, ldy, 0, w, K, 1, dx, ldx, M, K, N, R=dx_residual, ldr=ldr)
 
     def bn_act(self, x, bn, act, out, residual=None):
         """out.val = act(bn(x.val)) (+ residual.val); backward: x.grad from out.grad (residual.grad is out.grad)."""
@@ -192,7 +223,7 @@ class Plan:
         y = T2(self, F, H, W, Cout)
         y.stat_slot = self.stat_slot(Cout)
         st = (lambda s=y.stat_slot: s["fwd"]) if self.training else 0
-        self.gemm(self.fwd, x.val, Cin, 0, conv.weight, Cin, 0, y.val, Cout, x.rows, Cout, Cin, stats=st)
+        self.gemm_auto(self.fwd, x.val, Cin, 0, conv.weight, Cin, 0, y.val, Cout, x.rows, Cout, Cin, stats=st)
         return y
 
     def dw_conv(self, x, conv):

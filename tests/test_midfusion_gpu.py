@@ -28,12 +28,12 @@ def _inputs(B, size, T=29):
     return wav, mel, lips, labels
 
 
-def _pair(seed=0):
+def _pair(seed=0, precision="fp32"):
     from multimodal_lipread_b200.audio_video_models import MidFusionFast
     torch.manual_seed(seed)
     ref = MidFusionFastOracle(C)
     torch.manual_seed(seed)
-    ours = MidFusionFast(C)
+    ours = MidFusionFast(C, precision=precision)
     sd_ref, sd = ref.state_dict(), ours.state_dict()
     assert list(sd_ref.keys()) == list(sd.keys())
     for k in sd:                                        # same construction order => same seeded init
@@ -71,7 +71,7 @@ def test_train_step_matches_oracle(cuda_device, size, B):
     opt.step()
 
     ours.configure_optimizer(lr=3e-4)
-    w0 = {n: p.detach().clone() for n, p in ours.named_parameters()}
+    w0 = {n: p.detach().clone() for n, p in ours.named_parameters()}          # on the GPU
     loss, logits = ours.train_step(mel.cuda(), lips.cuda(), labels.cuda(), use_graph=False)
     torch.cuda.synchronize()
     assert _rel(logits, logits_ref) <= 1e-4, _rel(logits, logits_ref)
@@ -83,18 +83,24 @@ def test_train_step_matches_oracle(cuda_device, size, B):
         worst[n] = _grad_err(flat.g(p), gref[n])
     bad = {n: e for n, e in worst.items() if e > 2e-3}
     assert not bad, bad
-    # one Adam step
+    # one Adam step: torch.optim.Adam applied to the initial weights with OUR gradient must land on our new weights
+    # (comparing against the step taken with the reference's gradient would amplify round-off: Adam's first step
+    # is lr * g / (|g| + eps), i.e. sign-like, and flips for noise-level gradient elements)
+    mine = [w0[n].clone().requires_grad_(True) for n, _ in ours.named_parameters()]
+    chk = torch.optim.Adam(mine, lr=3e-4)
+    for t, (n, p) in zip(mine, ours.named_parameters()):
+        t.grad = flat.g(p).detach().clone()
+    chk.step()
+    for t, (n, p) in zip(mine, ours.named_parameters()):
+        assert (t.detach() - p.detach()).abs().max().item() <= 2e-7 + 1e-5 * 3e-4, n
     for (n, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
-        if gref[n].abs().max().item() < 1e-6:
-            continue          # zero-in-exact-arithmetic gradient: Adam turns the round-off noise into +-lr steps
-        step_ref = (q.detach() - w0[n].cpu())
-        step = (p.detach().cpu() - w0[n].cpu())
-        assert (step - step_ref).abs().max().item() <= 0.05 * 3e-4 + 1e-7, n
+        assert (p.detach().cpu() - q.detach()).abs().max().item() <= 2 * 3e-4 + 1e-7, n     # both moved by <= lr
     # BatchNorm running statistics and counters follow torch's update rule
     sd_ref, sd = ref.state_dict(), ours.state_dict()
     for k in sd:
         if k.endswith("running_mean") or k.endswith("running_var"):
-            assert _rel(sd[k], sd_ref[k]) <= 1e-4, k
+            # absolute floor: the mean of a conv fed by a batch-normalised (zero-mean) input is ~1e-10 round-off
+            assert (sd[k].cpu() - sd_ref[k]).abs().max().item() <= 1e-4 * sd_ref[k].abs().max().item() + 1e-7, k
         if k.endswith("num_batches_tracked"):
             assert int(sd[k]) == int(sd_ref[k]) == 1, k
 
@@ -175,3 +181,45 @@ def test_cuda_graph_step_equals_eager_and_trains(cuda_device):
     assert losses[-1] < losses[0]                          # the same batch repeated: the loss must fall
     assert int(b.state_dict()["video_cnn.features.0.1.num_batches_tracked"]) == 4
     assert float(b._flat.adam_state[0]) == 4.0
+
+
+def test_tf32_tensor_core_mode_within_bf16_tolerance(cuda_device):
+    """precision="tf32": the trunk GEMMs run on tcgen05 with TF32 products (10-bit mantissa, fp32 accumulate).
+
+    Stated tolerance (north star: "logits/grads within a stated bf16 tolerance, argmax identical"): the bf16
+    tolerance is MEASURED, not guessed -- it is the deviation of the reference's own model run under
+    torch.autocast(bfloat16) from its fp32 run on the same inputs and weights (logits ~2e-2 norm-wise, parameter
+    gradients: median ~14 %, worst ~90 % norm-wise per tensor, because tiny gradients formed by cancellation are
+    chaotic under any reduced-precision forward).  The TF32 mode must be at least as close to the fp32 reference
+    as that on every count, and at least 5x closer on the logits; argmax must be identical."""
+    import statistics
+    ref, ours = _pair(precision="tf32")
+    torch.manual_seed(0)
+    low = MidFusionFastOracle(C).train()
+    B, size = 4, 88
+    wav, mel, lips, labels = _inputs(B, size)
+    video = lips_u8_to_model_input(lips)
+    ref.train(); ours.train()
+    logits_ref = ref(mel, video)
+    loss_ref = torch.nn.functional.cross_entropy(logits_ref, labels)
+    loss_ref.backward()
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        logits_bf16 = low(mel, video)
+        loss_bf16 = torch.nn.functional.cross_entropy(logits_bf16.float(), labels)
+    loss_bf16.backward()
+    bf16_logits = _rel(logits_bf16.float(), logits_ref)
+    bf16_grads = [_grad_err(q.grad, p.grad) for p, q in zip(ref.parameters(), low.parameters())]
+
+    ours.configure_optimizer(lr=3e-4)
+    loss, logits = ours.train_step(mel.cuda(), lips.cuda(), labels.cuda(), use_graph=False)
+    e_logits = _rel(logits, logits_ref)
+    e_loss = abs(loss.item() - loss_ref.item()) / abs(loss_ref.item())
+    flat = ours._flat
+    e_grads = [_grad_err(flat.g(p), q.grad) for p, q in zip(ours.parameters(), ref.parameters())]
+    print(f"tf32 mode: logits {e_logits:.2e} (bf16 ref {bf16_logits:.2e}) loss {e_loss:.2e} "
+          f"grads median {statistics.median(e_grads):.2e} worst {max(e_grads):.2e} "
+          f"(bf16 ref median {statistics.median(bf16_grads):.2e} worst {max(bf16_grads):.2e})")
+    assert e_logits <= min(5e-3, bf16_logits / 5) and e_loss <= 1e-3
+    assert statistics.median(e_grads) <= statistics.median(bf16_grads)
+    assert max(e_grads) <= max(bf16_grads)
+    assert torch.equal(logits.argmax(1).cpu(), logits_ref.argmax(1))
