@@ -93,6 +93,12 @@ def cpu_reference(workload, cfg, steps, warmup, budget_s=25.0):
     import torch
     from multimodal_lipread_b200 import synthetic
     from oracle.frontend import AudioProcessorPort, lips_u8_to_model_input
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use all the host threads it can
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(max(torch.get_num_threads(), avail))
     cores = torch.get_num_threads()
     ap = AudioProcessorPort()
     if workload == "logmel":
@@ -135,6 +141,17 @@ def cpu_reference(workload, cfg, steps, warmup, budget_s=25.0):
 
 # ------------------------------------------------------------------------------------------------
 def main():
+    # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO; stdout must carry ONE JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    # ... and anything else a library writes to fd 1 goes to stderr: the JSON line is written to the saved fd
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     ap_ = argparse.ArgumentParser()
     ap_.add_argument("--gpus", type=int, default=1)
     ap_.add_argument("--steps", type=int, default=20)
@@ -180,7 +197,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -257,7 +274,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, ms, sample, cores = cpu_reference(workload, cfg, steps=3, warmup=1)
             line["cpu_baseline"] = {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

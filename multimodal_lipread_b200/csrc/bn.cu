@@ -70,15 +70,27 @@ bn_act_fwd_kernel(const Bn b, const float* __restrict__ x, const float* __restri
     const Coef k = coef4(b, c);
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = min(b.rows, r0 + rows_per_block);
-    for (long long r = r0 + map.rlane; r < r1; r += map.rpp) {
-        const float4 v = nn::ld4(x + r * b.C + c);
-        float4 o;
-        o.x = nn::act_fwd(fmaf(v.x, k.scale.x, k.shift.x), b.act);
-        o.y = nn::act_fwd(fmaf(v.y, k.scale.y, k.shift.y), b.act);
-        o.z = nn::act_fwd(fmaf(v.z, k.scale.z, k.shift.z), b.act);
-        o.w = nn::act_fwd(fmaf(v.w, k.scale.w, k.shift.w), b.act);
-        if (res) { const float4 q = nn::ld4(res + r * b.C + c); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
-        nn::st4(z + r * b.C + c, o);
+    constexpr int U = 4;                       // independent rows in flight per thread (memory-level parallelism)
+    const long long step = map.rpp;
+    for (long long r = r0 + map.rlane; r < r1; r += U * step) {
+        float4 v[U], q[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) if (r + u * step < r1) v[u] = nn::ld4(x + (r + u * step) * b.C + c);
+        if (res) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) if (r + u * step < r1) q[u] = nn::ld4(res + (r + u * step) * b.C + c);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (r + u * step >= r1) break;
+            float4 o;
+            o.x = nn::act_fwd(fmaf(v[u].x, k.scale.x, k.shift.x), b.act);
+            o.y = nn::act_fwd(fmaf(v[u].y, k.scale.y, k.shift.y), b.act);
+            o.z = nn::act_fwd(fmaf(v[u].z, k.scale.z, k.shift.z), b.act);
+            o.w = nn::act_fwd(fmaf(v[u].w, k.scale.w, k.shift.w), b.act);
+            if (res) { o.x += q[u].x; o.y += q[u].y; o.z += q[u].z; o.w += q[u].w; }
+            nn::st4(z + (r + u * step) * b.C + c, o);
+        }
     }
 }
 
@@ -96,18 +108,27 @@ bn_act_bwd_reduce_kernel(const Bn b, const float* __restrict__ x, const float* _
         const long long r0 = (long long)blockIdx.x * rows_per_block;
         const long long r1 = min(b.rows, r0 + rows_per_block);
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-        for (long long r = r0 + map.rlane; r < r1; r += map.rpp) {
-            const float4 v = nn::ld4(x + r * b.C + c);
-            const float4 g = nn::ld4(dz + r * b.C + c);
-            const float d0 = g.x * nn::act_grad(fmaf(v.x, k.scale.x, k.shift.x), b.act);
-            const float d1 = g.y * nn::act_grad(fmaf(v.y, k.scale.y, k.shift.y), b.act);
-            const float d2 = g.z * nn::act_grad(fmaf(v.z, k.scale.z, k.shift.z), b.act);
-            const float d3 = g.w * nn::act_grad(fmaf(v.w, k.scale.w, k.shift.w), b.act);
-            s1.x += d0; s1.y += d1; s1.z += d2; s1.w += d3;
-            s2.x = fmaf(d0, (v.x - k.mean.x) * k.invstd.x, s2.x);
-            s2.y = fmaf(d1, (v.y - k.mean.y) * k.invstd.y, s2.y);
-            s2.z = fmaf(d2, (v.z - k.mean.z) * k.invstd.z, s2.z);
-            s2.w = fmaf(d3, (v.w - k.mean.w) * k.invstd.w, s2.w);
+        constexpr int U = 4;
+        const long long step = map.rpp;
+        for (long long r = r0 + map.rlane; r < r1; r += U * step) {
+            float4 vv[U], gg[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (r + u * step < r1) { vv[u] = nn::ld4(x + (r + u * step) * b.C + c); gg[u] = nn::ld4(dz + (r + u * step) * b.C + c); }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (r + u * step >= r1) break;
+                const float4 v = vv[u], g = gg[u];
+                const float d0 = g.x * nn::act_grad(fmaf(v.x, k.scale.x, k.shift.x), b.act);
+                const float d1 = g.y * nn::act_grad(fmaf(v.y, k.scale.y, k.shift.y), b.act);
+                const float d2 = g.z * nn::act_grad(fmaf(v.z, k.scale.z, k.shift.z), b.act);
+                const float d3 = g.w * nn::act_grad(fmaf(v.w, k.scale.w, k.shift.w), b.act);
+                s1.x += d0; s1.y += d1; s1.z += d2; s1.w += d3;
+                s2.x = fmaf(d0, (v.x - k.mean.x) * k.invstd.x, s2.x);
+                s2.y = fmaf(d1, (v.y - k.mean.y) * k.invstd.y, s2.y);
+                s2.z = fmaf(d2, (v.z - k.mean.z) * k.invstd.z, s2.z);
+                s2.w = fmaf(d3, (v.w - k.mean.w) * k.invstd.w, s2.w);
+            }
         }
         atomicAdd(&sh[c], s1.x); atomicAdd(&sh[c + 1], s1.y); atomicAdd(&sh[c + 2], s1.z); atomicAdd(&sh[c + 3], s1.w);
         atomicAdd(&sh[b.C + c], s2.x); atomicAdd(&sh[b.C + c + 1], s2.y);
@@ -141,15 +162,25 @@ bn_act_bwd_apply_kernel(const Bn b, const float* __restrict__ x, const float* __
                          (float)(sums[b.C + c + 2] * inv_n), (float)(sums[b.C + c + 3] * inv_n)};
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = min(b.rows, r0 + rows_per_block);
-    for (long long r = r0 + map.rlane; r < r1; r += map.rpp) {
-        const float4 v = nn::ld4(x + r * b.C + c);
-        const float4 g = nn::ld4(dz + r * b.C + c);
+    constexpr int U = 4;
+    const long long step = map.rpp;
+    for (long long rb = r0 + map.rlane; rb < r1; rb += U * step) {
+      float4 vv[U], gg[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+          if (rb + u * step < r1) { vv[u] = nn::ld4(x + (rb + u * step) * b.C + c); gg[u] = nn::ld4(dz + (rb + u * step) * b.C + c); }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long r = rb + u * step;
+        if (r >= r1) break;
+        const float4 v = vv[u], g = gg[u];
         float4 o;
         o.x = k.scale.x * (g.x * nn::act_grad(fmaf(v.x, k.scale.x, k.shift.x), b.act) - m1[0] - (v.x - k.mean.x) * k.invstd.x * m2[0]);
         o.y = k.scale.y * (g.y * nn::act_grad(fmaf(v.y, k.scale.y, k.shift.y), b.act) - m1[1] - (v.y - k.mean.y) * k.invstd.y * m2[1]);
         o.z = k.scale.z * (g.z * nn::act_grad(fmaf(v.z, k.scale.z, k.shift.z), b.act) - m1[2] - (v.z - k.mean.z) * k.invstd.z * m2[2]);
         o.w = k.scale.w * (g.w * nn::act_grad(fmaf(v.w, k.scale.w, k.shift.w), b.act) - m1[3] - (v.w - k.mean.w) * k.invstd.w * m2[3]);
         nn::st4(dx + r * b.C + c, o);
+      }
     }
 }
 

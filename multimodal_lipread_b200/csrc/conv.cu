@@ -4,7 +4,7 @@
 //            forward() receives it) -- the /255, permute(3,0,1,2) and TimeDistributed
 //            permute/contiguous/view of video/data_utils/dataset_loader.py:90,96 and
 //            audio_video/models/middle_fusion_fast.py:32-33 are folded into the addressing.
-//   dwconv : depthwise k x k (k = 3, 5; stride 1, 2), forward / dgrad / wgrad.
+// (the depthwise convolutions live in dwconv.cu)
 // Every forward kernel also emits the per-channel sum and sum of squares of its raw output
 // (double atomics) so that train-mode BatchNorm needs no extra pass over the activation.
 #include "nn_common.cuh"
@@ -145,156 +145,6 @@ stem_wgrad_kernel(const StemIn2 s, const float* __restrict__ dy, float* __restri
     if (tp1 < ST) atomicAdd(&dw[co * ST + tp1], a1);
 }
 
-// ---------------------------------------------------------------------------------------- dwconv
-struct Dw {
-    int F, H, W, C, Ho, Wo, k, stride, pad;
-};
-
-// weights -> shared memory transposed to [tap][C] so that a thread's float4 is contiguous
-__device__ __forceinline__ void dw_stage_weights(const float* __restrict__ w, float* ws, int C, int kk) {
-    for (int i = threadIdx.x; i < C * kk; i += blockDim.x) { const int c = i / kk, tp = i - c * kk; ws[tp * C + c] = w[i]; }
-}
-
-template <int K>
-__global__ void __launch_bounds__(TH)
-dw_fwd_kernel(const Dw d, const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
-              double* __restrict__ stats, int pix_per_block) {
-    extern __shared__ __align__(16) float smem[];
-    float* ws = smem;                                  // [K*K][C]
-    float* ssum = smem + K * K * d.C;                  // [C]
-    float* ssq = ssum + d.C;                           // [C]
-    dw_stage_weights(w, ws, d.C, K * K);
-    for (int i = threadIdx.x; i < 2 * d.C; i += blockDim.x) ssum[i] = 0.f;
-    __syncthreads();
-    const nn::CgMap map(d.C, blockIdx.y * blockDim.x);
-    const long long total = (long long)d.F * d.Ho * d.Wo;
-    const long long p0 = (long long)blockIdx.x * pix_per_block;
-    const long long p1 = min(total, p0 + pix_per_block);
-    float4 ls = make_float4(0.f, 0.f, 0.f, 0.f), lq = ls;
-    if (map.active) {
-        const int c = map.cg * 4;
-        for (long long pix = p0 + map.rlane; pix < p1; pix += map.rpp) {
-            const int wo = int(pix % d.Wo);
-            const long long r = pix / d.Wo;
-            const int ho = int(r % d.Ho), f = int(r / d.Ho);
-            const float* xf = x + (long long)f * d.H * d.W * d.C + c;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int kh = 0; kh < K; ++kh) {
-                const int hi = ho * d.stride - d.pad + kh;
-                if (hi < 0 || hi >= d.H) continue;
-#pragma unroll
-                for (int kw = 0; kw < K; ++kw) {
-                    const int wi = wo * d.stride - d.pad + kw;
-                    if (wi < 0 || wi >= d.W) continue;
-                    const float4 xv = nn::ld4(xf + ((long long)hi * d.W + wi) * d.C);
-                    const float4 wv = nn::ld4(ws + (kh * K + kw) * d.C + c);
-                    acc.x = fmaf(xv.x, wv.x, acc.x); acc.y = fmaf(xv.y, wv.y, acc.y);
-                    acc.z = fmaf(xv.z, wv.z, acc.z); acc.w = fmaf(xv.w, wv.w, acc.w);
-                }
-            }
-            nn::st4(y + pix * d.C + c, acc);
-            ls.x += acc.x; ls.y += acc.y; ls.z += acc.z; ls.w += acc.w;
-            lq.x = fmaf(acc.x, acc.x, lq.x); lq.y = fmaf(acc.y, acc.y, lq.y);
-            lq.z = fmaf(acc.z, acc.z, lq.z); lq.w = fmaf(acc.w, acc.w, lq.w);
-        }
-        atomicAdd(&ssum[c], ls.x); atomicAdd(&ssum[c + 1], ls.y); atomicAdd(&ssum[c + 2], ls.z); atomicAdd(&ssum[c + 3], ls.w);
-        atomicAdd(&ssq[c], lq.x); atomicAdd(&ssq[c + 1], lq.y); atomicAdd(&ssq[c + 2], lq.z); atomicAdd(&ssq[c + 3], lq.w);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < d.C; i += blockDim.x) {
-        nn::atomic_add_double(stats + i, (double)ssum[i]);
-        nn::atomic_add_double(stats + d.C + i, (double)ssq[i]);
-    }
-}
-
-// dx[f,hi,wi,c] = sum_{kh,kw : (hi+pad-kh) % s == 0} dy[f,(hi+pad-kh)/s,(wi+pad-kw)/s,c] * w[c,kh,kw]
-template <int K>
-__global__ void __launch_bounds__(TH)
-dw_dgrad_kernel(const Dw d, const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
-                int pix_per_block) {
-    extern __shared__ __align__(16) float smem[];
-    float* ws = smem;
-    dw_stage_weights(w, ws, d.C, K * K);
-    __syncthreads();
-    const nn::CgMap map(d.C, blockIdx.y * blockDim.x);
-    const long long total = (long long)d.F * d.H * d.W;
-    const long long p0 = (long long)blockIdx.x * pix_per_block;
-    const long long p1 = min(total, p0 + pix_per_block);
-    if (!map.active) return;
-    const int c = map.cg * 4;
-    for (long long pix = p0 + map.rlane; pix < p1; pix += map.rpp) {
-        const int wi = int(pix % d.W);
-        const long long r = pix / d.W;
-        const int hi = int(r % d.H), f = int(r / d.H);
-        const float* df = dy + (long long)f * d.Ho * d.Wo * d.C + c;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int kh = 0; kh < K; ++kh) {
-            const int hn = hi + d.pad - kh;
-            if (hn < 0 || hn % d.stride != 0) continue;
-            const int ho = hn / d.stride;
-            if (ho >= d.Ho) continue;
-#pragma unroll
-            for (int kw = 0; kw < K; ++kw) {
-                const int wn = wi + d.pad - kw;
-                if (wn < 0 || wn % d.stride != 0) continue;
-                const int wo = wn / d.stride;
-                if (wo >= d.Wo) continue;
-                const float4 g = nn::ld4(df + ((long long)ho * d.Wo + wo) * d.C);
-                const float4 wv = nn::ld4(ws + (kh * K + kw) * d.C + c);
-                acc.x = fmaf(g.x, wv.x, acc.x); acc.y = fmaf(g.y, wv.y, acc.y);
-                acc.z = fmaf(g.z, wv.z, acc.z); acc.w = fmaf(g.w, wv.w, acc.w);
-            }
-        }
-        nn::st4(dx + pix * d.C + c, acc);
-    }
-}
-
-// dw[c,kh,kw] = sum_{f,ho,wo} dy[f,ho,wo,c] * x[f,ho*s-pad+kh,wo*s-pad+kw,c]
-// thread = one channel (coalesced across the warp) and one pixel lane; K*K register accumulators;
-// persistent over pixel tiles, one shared-memory + one global atomic round at the end.
-template <int K>
-__global__ void __launch_bounds__(TH)
-dw_wgrad_kernel(const Dw d, const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw) {
-    extern __shared__ __align__(16) float smem[];      // [cw][K*K]
-    const int cbase = blockIdx.y * TH;
-    const int cw = min(d.C - cbase, TH);
-    const int rpp = TH / cw;
-    const int c = cbase + threadIdx.x % cw, rl = threadIdx.x / cw;
-    for (int i = threadIdx.x; i < cw * K * K; i += TH) smem[i] = 0.f;
-    __syncthreads();
-    float acc[K * K];
-#pragma unroll
-    for (int i = 0; i < K * K; ++i) acc[i] = 0.f;
-    const long long total = (long long)d.F * d.Ho * d.Wo;
-    if (rl < rpp) {
-        for (long long pix = (long long)blockIdx.x * rpp + rl; pix < total; pix += (long long)gridDim.x * rpp) {
-            const int wo = int(pix % d.Wo);
-            const long long r = pix / d.Wo;
-            const int ho = int(r % d.Ho), f = int(r / d.Ho);
-            const float g = dy[pix * d.C + c];
-            const float* xf = x + (long long)f * d.H * d.W * d.C + c;
-#pragma unroll
-            for (int kh = 0; kh < K; ++kh) {
-                const int hi = ho * d.stride - d.pad + kh;
-                if (hi < 0 || hi >= d.H) continue;
-#pragma unroll
-                for (int kw = 0; kw < K; ++kw) {
-                    const int wi = wo * d.stride - d.pad + kw;
-                    if (wi < 0 || wi >= d.W) continue;
-                    acc[kh * K + kw] = fmaf(g, xf[((long long)hi * d.W + wi) * d.C], acc[kh * K + kw]);
-                }
-            }
-        }
-        float* sm = smem + (c - cbase) * K * K;
-#pragma unroll
-        for (int i = 0; i < K * K; ++i) atomicAdd(&sm[i], acc[i]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < cw * K * K; i += TH) atomicAdd(&dw[cbase * K * K + i], smem[i]);
-}
-
 }  // namespace cv
 
 // ------------------------------------------------------------------------------------------ C ABI
@@ -336,89 +186,5 @@ extern "C" int lr_stem_conv_wgrad(const void* x, int is_u8, int B, int T, int H,
     cv::stem_wgrad_kernel<<<grid, cv::TH, 0, stream>>>(s, dy, dw);
     lr::count_launch();
     LR_CHECK_LAUNCH("stem_wgrad_kernel");
-    return LR_OK;
-}
-
-static int make_dw(cv::Dw& d, int F, int H, int W, int C, int k, int stride) {
-    d.F = F; d.H = H; d.W = W; d.C = C; d.k = k; d.stride = stride; d.pad = k / 2;
-    d.Ho = (H + 2 * d.pad - k) / stride + 1; d.Wo = (W + 2 * d.pad - k) / stride + 1;
-    return 0;
-}
-#define LR_DW_CHECK(name)                                                                              \
-    LR_CHECK_ARG(F >= 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, name ": bad shape (C %% 4 != 0?)"); \
-    LR_CHECK_ARG(k == 3 || k == 5, name ": kernel size %d not in {3,5}", k);                          \
-    LR_CHECK_ARG(stride == 1 || stride == 2, name ": stride %d not in {1,2}", stride);                \
-    if (F == 0) return LR_OK
-
-static int dw_pix_per_block(long long total, int C) {
-    const int rpp = cv::TH / ((C >> 2) < cv::TH ? (C >> 2) : cv::TH);
-    long long ppb = (total + (long long)lr::sm_count() * 8 - 1) / ((long long)lr::sm_count() * 8);
-    ppb = ((ppb + rpp - 1) / rpp) * rpp;
-    if (ppb < rpp) ppb = rpp;
-    return (int)ppb;
-}
-
-template <typename Kern>
-static cudaError_t dw_smem_attr(Kern kern, size_t bytes) {
-    return bytes > 48 * 1024 ? cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)
-                             : cudaSuccess;
-}
-
-extern "C" int lr_dwconv_fwd(const float* x, const float* w, float* y, double* stats, int F, int H, int W, int C,
-                             int k, int stride, lr_stream_t stream) {
-    LR_DW_CHECK("lr_dwconv_fwd");
-    LR_CHECK_ARG(x && w && y && stats, "lr_dwconv_fwd: null pointer");
-    LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(y);
-    cv::Dw d; make_dw(d, F, H, W, C, k, stride);
-    const long long total = (long long)F * d.Ho * d.Wo;
-    const int ppb = dw_pix_per_block(total, C);
-    dim3 grid((unsigned)((total + ppb - 1) / ppb), nn::cg_block_cols(C, cv::TH));
-    const size_t smem = (size_t)(k * k + 2) * C * sizeof(float);
-    cudaError_t e = k == 3 ? dw_smem_attr(cv::dw_fwd_kernel<3>, smem) : dw_smem_attr(cv::dw_fwd_kernel<5>, smem);
-    if (e != cudaSuccess) return lr::fail(LR_ECUDA, "lr_dwconv_fwd smem: %s", cudaGetErrorString(e));
-    if (k == 3) cv::dw_fwd_kernel<3><<<grid, cv::TH, smem, stream>>>(d, x, w, y, stats, ppb);
-    else cv::dw_fwd_kernel<5><<<grid, cv::TH, smem, stream>>>(d, x, w, y, stats, ppb);
-    lr::count_launch();
-    LR_CHECK_LAUNCH("dw_fwd_kernel");
-    return LR_OK;
-}
-
-extern "C" int lr_dwconv_dgrad(const float* dy, const float* w, float* dx, int F, int H, int W, int C, int k,
-                               int stride, lr_stream_t stream) {
-    LR_DW_CHECK("lr_dwconv_dgrad");
-    LR_CHECK_ARG(dy && w && dx, "lr_dwconv_dgrad: null pointer");
-    LR_CHECK_ALIGN(dy); LR_CHECK_ALIGN(dx);
-    cv::Dw d; make_dw(d, F, H, W, C, k, stride);
-    const long long total = (long long)F * H * W;
-    const int ppb = dw_pix_per_block(total, C);
-    dim3 grid((unsigned)((total + ppb - 1) / ppb), nn::cg_block_cols(C, cv::TH));
-    const size_t smem = (size_t)(k * k) * C * sizeof(float);
-    cudaError_t e = k == 3 ? dw_smem_attr(cv::dw_dgrad_kernel<3>, smem) : dw_smem_attr(cv::dw_dgrad_kernel<5>, smem);
-    if (e != cudaSuccess) return lr::fail(LR_ECUDA, "lr_dwconv_dgrad smem: %s", cudaGetErrorString(e));
-    if (k == 3) cv::dw_dgrad_kernel<3><<<grid, cv::TH, smem, stream>>>(d, dy, w, dx, ppb);
-    else cv::dw_dgrad_kernel<5><<<grid, cv::TH, smem, stream>>>(d, dy, w, dx, ppb);
-    lr::count_launch();
-    LR_CHECK_LAUNCH("dw_dgrad_kernel");
-    return LR_OK;
-}
-
-extern "C" int lr_dwconv_wgrad(const float* dy, const float* x, float* dw, int F, int H, int W, int C, int k,
-                               int stride, lr_stream_t stream) {
-    LR_DW_CHECK("lr_dwconv_wgrad");
-    LR_CHECK_ARG(dy && x && dw, "lr_dwconv_wgrad: null pointer");
-    cv::Dw d; make_dw(d, F, H, W, C, k, stride);
-    const long long total = (long long)F * d.Ho * d.Wo;
-    const int ycols = (C + cv::TH - 1) / cv::TH;
-    const int cw = C < cv::TH ? C : cv::TH;
-    const int rpp = cv::TH / cw;
-    long long gx = (total + rpp - 1) / rpp;
-    const long long cap = (long long)lr::sm_count() * 4;
-    if (gx > cap) gx = cap;
-    dim3 grid((unsigned)gx, ycols);
-    const size_t smem = (size_t)cw * k * k * sizeof(float);
-    if (k == 3) cv::dw_wgrad_kernel<3><<<grid, cv::TH, smem, stream>>>(d, dy, x, dw);
-    else cv::dw_wgrad_kernel<5><<<grid, cv::TH, smem, stream>>>(d, dy, x, dw);
-    lr::count_launch();
-    LR_CHECK_LAUNCH("dw_wgrad_kernel");
     return LR_OK;
 }
