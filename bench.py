@@ -162,6 +162,7 @@ def main():
     ap_.add_argument("--size", type=int, default=88, help="lip frame height = width (88 benchmark, 44 reference)")
     ap_.add_argument("--classes", type=int, default=40)
     ap_.add_argument("--no-cpu-baseline", action="store_true")
+    ap_.add_argument("--dump-ops", default=None, help="write the per-op device times of one step (JSON) to this file")
     args = ap_.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -271,6 +272,9 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": wl.roofline(kernel_ms, ms_step, peaks)}
         line.update(wl.extra())
+        if args.dump_ops and getattr(wl, "op_rows", None):
+            with open(args.dump_ops, "w") as f:
+                json.dump(wl.op_rows, f, indent=0)
         if world == 1 and not args.no_cpu_baseline:
             v, ms, sample, cores = cpu_reference(workload, cfg, steps=3, warmup=1)
             line["cpu_baseline"] = {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample}

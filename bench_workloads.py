@@ -148,15 +148,38 @@ class AvTrainWorkload:
         torch.cuda.current_stream().synchronize()
         return self.loss_host
 
+    def profile_ops(self):
+        """Per-op device time of one train step (eager launches, CUDA events on the launching stream)."""
+        from multimodal_lipread_b200 import engine
+        plan = next(p for p in self.model._plans.values() if p.with_backward)
+        st = torch.cuda.current_stream()
+        rows = []
+        for phase, ops in (("pre", plan.pre), ("fwd", plan.fwd), ("ce", plan.ce), ("pre_bwd", plan.pre_bwd), ("bwd", plan.bwd)):
+            for name, args, ms in ops.profile(st, reps=5):
+                rows.append({"phase": phase, "op": name, "ms": ms, "bytes": engine.op_algorithmic_bytes(name, args),
+                             "shape": [a for a in args if isinstance(a, int) and 0 < a < (1 << 31)][-6:]})
+        return rows
+
     def roofline(self, kernel_ms, ms_step, peaks):
-        # whole-step view: algorithmic minimum HBM traffic of the step is not well defined for a 300-kernel
-        # step, so the step-level figure reported is fp32 FLOP throughput of the model math (3x forward)
+        """Dominant kernel = the single launch with the largest device time in the step; achieved = its
+        algorithmic bytes / its CUDA-event duration (eager pass after the timed region, same buffers)."""
+        rows = self.profile_ops()
+        self.op_rows = rows
+        total = sum(r["ms"] for r in rows)
+        cand = [r for r in rows if r["bytes"]]
+        top = max(cand, key=lambda r: r["ms"])
+        achieved = top["bytes"] / 1e9 / (top["ms"] / 1e3)
+        by_op = {}
+        for r in rows:
+            by_op[r["op"]] = by_op.get(r["op"], 0.0) + r["ms"]
         size = self.cfg["size"]
         fwd_gflop = 0.630 if size == 88 else 0.256           # SURVEY.md 8(a) a16, per clip
-        tf = 3 * fwd_gflop * self.batch / (ms_step / 1e3) / 1e3
-        return {"kernel": "whole train step (see profiles/ for the per-kernel launch list)", "bound": "hbm",
-                "achieved": None, "peak": peaks["hbm"], "unit": "GB/s", "frac": None, "traffic": None,
-                "peak_source": peaks["src"], "step_model_tflops": tf}
+        return {"kernel": f"{top['op']} {top['shape']} ({top['phase']})", "bound": "hbm", "achieved": achieved,
+                "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None,
+                "peak_source": peaks["src"], "kernel_ms": top["ms"], "kernel_share_of_step": top["ms"] / total,
+                "eager_step_ms_sum_of_kernels": total,
+                "time_by_op_ms": {k: round(v, 4) for k, v in sorted(by_op.items(), key=lambda kv: -kv[1])},
+                "step_model_tflops": 3 * fwd_gflop * self.batch / (ms_step / 1e3) / 1e3}
 
     def extra(self):
         return {"final_loss": float(self.last_loss.item()) if self.last_loss is not None else None,

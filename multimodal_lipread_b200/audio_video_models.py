@@ -84,7 +84,7 @@ class MidFusionPlan(engine.Plan):
             g = self.bgroup()
             self.linear_bwd(g, a_pool, KA, B, m.audio_fc.weight, m.audio_fc.bias, dfused, FD, dx=d_pool, ldx=KA)
             g.add("lr_audio_conv_bwd", self.mel, d_pool, KA, a_arg, flat.g(conv.weight), flat.g(conv.bias), B, N_MELS,
-                  N_FRAMES_OUT)
+                  N_FRAMES_OUT, leaf=True)
 
         # ---- video trunk: MobileNetV3-small features + avgpool -> feat [B*T, 576]
         last = self.mbv3_features(m.video_cnn.features, self.video, layout, scale, B, T, H, W)
@@ -117,7 +117,7 @@ class MidFusionPlan(engine.Plan):
             self.linear_bwd(g, feat, I, F, L.weight_ih_l0, L.bias_ih_l0, dg_f, G4, dx=dfeat, ldx=I)
             # reverse direction (one step from the zero state: W_hh_reverse gets no gradient)
             g.add("lr_lstm_bwd", dfused_r, FD, 0, gates_r, c_r, L.weight_hh_l0_reverse, dg_r, B, 1, HL, 1, 1)
-            g.add("lr_colsum", dg_r, G4, B, G4, flat.g(L.bias_hh_l0_reverse))
+            g.add("lr_colsum", dg_r, G4, B, G4, flat.g(L.bias_hh_l0_reverse), leaf=True)
             dfeat_last = dfeat.data_ptr() + 4 * (T - 1) * I
             self.linear_bwd(g, feat_last, T * I, B, L.weight_ih_l0_reverse, L.bias_ih_l0_reverse, dg_r, G4,
                             dx=dfeat_last, ldx=T * I, dx_residual=dfeat_last, ldr=T * I)
@@ -154,9 +154,14 @@ class MidFusionPlan(engine.Plan):
         self.pre.run(stream)
         self.fwd.run(stream)
 
-    def run_backward(self, stream):
+    def run_backward(self, stream, forked=None):
+        """forked = (main, side) torch streams: weight-gradient kernels run on `side` concurrently with the
+        dgrad chain (used under CUDA-graph capture, where it becomes a parallel branch of the graph)."""
         self.pre_bwd.run(stream)
-        self.bwd.run(stream)
+        if forked is None:
+            self.bwd.run(stream)
+        else:
+            self.bwd.run_forked(*forked)
 
     def n_launches(self):
         return len(self.fwd) + len(self.bwd) + 1
@@ -281,10 +286,10 @@ class MidFusionFast(nn.Module):
         plan.labels.copy_(labels, non_blocking=True)
         o = self._opt
 
-        def compute(stream):
+        def compute(stream, forked=None):
             plan.run_forward(stream)
             plan.ce.run(stream)
-            plan.run_backward(stream)
+            plan.run_backward(stream, forked)
 
         def update(stream):
             _lib.check(lib.lr_adam_step(flat.flat.data_ptr(), flat.grad.data_ptr(), flat.m.data_ptr(), flat.v.data_ptr(),
@@ -319,10 +324,12 @@ class MidFusionFast(nn.Module):
         torch.cuda.synchronize()
         g0 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g0):
-            s = torch.cuda.current_stream().cuda_stream
-            compute(s)
+            main = torch.cuda.current_stream()
+            if not hasattr(self, "_side"):
+                self._side = torch.cuda.Stream()
+            compute(main.cuda_stream, forked=(main, self._side))
             if not split:
-                update(s)
+                update(main.cuda_stream)
         if not split:
             return (g0,)
         g1 = torch.cuda.CUDAGraph()

@@ -37,17 +37,80 @@ class OpList:
     def __init__(self):
         self.ops = []
 
-    def add(self, name, *args):
-        self.ops.append((getattr(lib, name), tuple(a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args), name))
+    def add(self, name, *args, leaf=False):
+        """leaf=True marks an op whose output nobody reads before the optimizer (weight / bias gradients): such
+        ops may run on a side stream concurrently with the dgrad chain (run_forked)."""
+        self.ops.append((getattr(lib, name), tuple(a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args), name, leaf))
 
     def run(self, stream):
-        for fn, args, name in self.ops:
+        for fn, args, name, _ in self.ops:
             rc = fn(*args, stream)
             if rc != 0:
                 raise _lib.LipreadError(f"{name} failed ({rc}): {lib.lr_last_error().decode()}")
 
+    def run_forked(self, main, side):
+        """Same launches, but leaf ops go to `side` (a torch.cuda.Stream) behind an event recorded on `main`
+        (their inputs are ready there), and `main` joins `side` at the end.  Under CUDA-graph capture this turns
+        the weight-gradient kernels into parallel branches of the graph."""
+        ms, ss = main.cuda_stream, side.cuda_stream
+        forked = False
+        for fn, args, name, leaf in self.ops:
+            if leaf:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                rc = fn(*args, ss)
+                forked = True
+            else:
+                rc = fn(*args, ms)
+            if rc != 0:
+                raise _lib.LipreadError(f"{name} failed ({rc}): {lib.lr_last_error().decode()}")
+        if forked:
+            main.wait_stream(side)
+
     def __len__(self):
         return len(self.ops)
+
+    def profile(self, stream_obj, reps=5):
+        """Eager launches with a CUDA-event pair around every op on the launching stream; returns
+        [(name, args, mean ms)] in launch order (used by bench.py for the per-kernel roofline)."""
+        s = stream_obj.cuda_stream
+        acc = [0.0] * len(self.ops)
+        for _ in range(reps):
+            evs = []
+            for fn, args, name, _ in self.ops:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream_obj)
+                rc = fn(*args, s)
+                b.record(stream_obj)
+                if rc != 0:
+                    raise _lib.LipreadError(f"{name} failed ({rc}): {lib.lr_last_error().decode()}")
+                evs.append((a, b))
+            stream_obj.synchronize()
+            for i, (a, b) in enumerate(evs):
+                acc[i] += a.elapsed_time(b)
+        return [(name, args, t / reps) for (fn, args, name, _), t in zip(self.ops, acc)]
+
+
+def op_algorithmic_bytes(name, args):
+    """Algorithmic HBM bytes of one launch (every operand read once, every result written once, fp32)."""
+    if name in ("lr_gemm", "lr_gemm_tf32"):
+        M, N, K = args[8], args[9], args[10]
+        extra = M * N if args[13] else 0                 # residual / accumulate operand
+        return 4 * (M * K + N * K + M * N + extra)
+    if name == "lr_bn_act_fwd":
+        rows, C = args[-2], args[-1]
+        return 4 * rows * C * (3 if args[-4] else 2)
+    if name == "lr_bn_act_bwd":
+        rows, C = args[-2], args[-1]
+        return 4 * rows * C * 3                          # x, dz in; dx out (the two passes re-read x and dz)
+    if name in ("lr_dwconv_fwd", "lr_dwconv_dgrad", "lr_dwconv_wgrad"):
+        F, H, W, C, k, st = args[-6:]
+        Ho, Wo = (H + 2 * (k // 2) - k) // st + 1, (W + 2 * (k // 2) - k) // st + 1
+        return 4 * F * C * (H * W + Ho * Wo)
+    if name in ("lr_frame_reduce", "lr_frame_scale"):
+        return None
+    return None
 
 
 def _ksplit(M, N, K, sms, min_k=256):
@@ -145,7 +208,7 @@ class Plan:
             s["bwd"] = base + 8 * (off + 2 * s["C"])
             off += 4 * s["C"]
         for ops in [self.fwd] + [g for g in self.bwd_rev]:
-            ops.ops = [(fn, tuple(a() if callable(a) else a for a in args), name) for fn, args, name in ops.ops]
+            ops.ops = [(fn, tuple(a() if callable(a) else a for a in args), name, leaf) for fn, args, name, leaf in ops.ops]
         self.bwd = OpList()
         for g in reversed(self.bwd_rev):
             self.bwd.ops.extend(g.ops)
@@ -156,8 +219,9 @@ class Plan:
         return g
 
     # ---- op emitters ----------------------------------------------------------------------------------
-    def gemm(self, ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias=0, act=ACT_NONE, R=0, ldr=0, stats=0, ksplit=1):
-        ops.add("lr_gemm", A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias, act, R, ldr, stats, ksplit)
+    def gemm(self, ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias=0, act=ACT_NONE, R=0, ldr=0, stats=0, ksplit=1,
+             leaf=False):
+        ops.add("lr_gemm", A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias, act, R, ldr, stats, ksplit, leaf=leaf)
 
     def use_tc(self, M, N, K, lda, ldb):
         """Tensor-core path for GEMMs that stream many rows (1x1 convs, SE / LSTM projections over all frames);
@@ -174,17 +238,17 @@ class Plan:
                 bn_tiles = ((M + 127) // 128) * ((N + 255) // 256)
                 ks = max(1, min((K + 255) // 256, (2 * self.sms) // bn_tiles))
             if ks > 1:
-                ops.add("lr_gemm_tf32", A, lda, at, B, ldb, bt, C, ldc, M, N, K, 0, ACT_NONE, 0, 0, 0, ks)
+                ops.add("lr_gemm_tf32", A, lda, at, B, ldb, bt, C, ldc, M, N, K, 0, ACT_NONE, 0, 0, 0, ks, leaf=split_ok)
             else:
                 ops.add("lr_gemm_tf32", A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias, act, (C if split_ok else R),
-                        (ldc if split_ok else ldr), stats, 1)
+                        (ldc if split_ok else ldr), stats, 1, leaf=split_ok)
             return
         ks = _ksplit(M, N, K, self.sms) if split_ok else 1
         if ks > 1:
-            self.gemm(ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, ksplit=ks)
+            self.gemm(ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, ksplit=ks, leaf=split_ok)
         else:
             self.gemm(ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias=bias, act=act, R=(C if split_ok else R),
-                      ldr=(ldc if split_ok else ldr), stats=stats)
+                      ldr=(ldc if split_ok else ldr), stats=stats, leaf=split_ok)
 
     def linear(self, x, lda, M, w, b, out, ldc, act=ACT_NONE, stats=0, ksplit=1):
         N, K = w.shape[0], w[0].numel()
@@ -200,7 +264,7 @@ class Plan:
         dw = self.flat.g(w)
         self.gemm_auto(g, dy, ldy, 1, x, lda, 1, dw, K, N, K, M, split_ok=True)       # dw += dy^T x
         if b is not None:
-            g.add("lr_colsum", dy, ldy, M, N, self.flat.g(b))
+            g.add("lr_colsum", dy, ldy, M, N, self.flat.g(b), leaf=True)
         if dx is not None:
             self.gemm_auto(g, dy, ldy, 0, w, K, 1, dx, ldx, M, K, N, R=dx_residual, ldr=ldr)
 
@@ -236,7 +300,7 @@ class Plan:
         self.fwd.add("lr_dwconv_fwd", x.val, conv.weight, y.val, st, x.F, x.H, x.W, C, k, s)
         if self.with_backward:
             g = self.bgroup()
-            g.add("lr_dwconv_wgrad", y.grad, x.val, self.flat.g(conv.weight), x.F, x.H, x.W, C, k, s)
+            g.add("lr_dwconv_wgrad", y.grad, x.val, self.flat.g(conv.weight), x.F, x.H, x.W, C, k, s, leaf=True)
             g.add("lr_dwconv_dgrad", y.grad, conv.weight, x.grad, x.F, x.H, x.W, C, k, s)
         return y
 
@@ -259,7 +323,7 @@ class Plan:
         self.fwd.add("lr_stem_conv_fwd", frames, *layout, float(scale), conv.weight, raw.val, st)
         if self.with_backward:
             g = self.bgroup()
-            g.add("lr_stem_conv_wgrad", frames, *layout, float(scale), raw.grad, self.flat.g(conv.weight))
+            g.add("lr_stem_conv_wgrad", frames, *layout, float(scale), raw.grad, self.flat.g(conv.weight), leaf=True)
         cur = T2(self, F, Ho, Wo, 16)
         self.bn_act(raw, bn, act, cur)
         for blk in feats[1:]:
