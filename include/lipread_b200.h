@@ -34,7 +34,7 @@ enum {
     LR_ENOSPC = -4   /* caller-provided workspace / plan buffer too small */
 };
 
-#define LR_ABI_VERSION 1
+#define LR_ABI_VERSION 2
 
 int lr_version(void);
 const char* lr_last_error(void);
@@ -79,7 +79,7 @@ int lr_normalize_fwd(const float* x, float* out, int B, int n, lr_stream_t strea
  * row-major [rows = F*H*W, C] matrix, so the 1x1 convolutions of torchvision's MobileNetV3 / the SE and
  * classifier linears / nn.LSTM's projections are all lr_gemm calls on it.
  * ------------------------------------------------------------------------------------------ */
-enum { LR_ACT_NONE = 0, LR_ACT_RELU = 1, LR_ACT_HSWISH = 2, LR_ACT_HSIGMOID = 3 };
+enum { LR_ACT_NONE = 0, LR_ACT_RELU = 1, LR_ACT_HSWISH = 2, LR_ACT_HSIGMOID = 3, LR_ACT_RELU6 = 4 };
 
 /* C[M,N] = act(A.B + bias) + R, optional per-column sum / sum-of-squares into double stats[2N]
  * (train-mode BatchNorm statistics of a conv output), optional split-K with atomic accumulation.
@@ -123,16 +123,20 @@ int lr_dwconv_wgrad(const float* dy, const float* x, float* dw, int F, int H, in
 /* nn.BatchNorm2d (+ activation, + residual add) on [rows, C].  training != 0: batch statistics from
  * `stats` (double[2C] sum / sum of squares over the rows), running_mean / running_var / num_batches_tracked
  * updated exactly as torch does (unbiased variance, momentum); training == 0: running statistics.
- * z = act(bn(x)) + residual. */
+ * res_pre == 0: z = act(bn(x)) + residual   (torchvision InvertedResidual: the projection has no activation)
+ * res_pre != 0: z = act(bn(x) + residual)   (torchvision BasicBlock: out += identity; out = relu(out)) */
 int lr_bn_act_fwd(const float* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
                   float* running_var, long long* num_batches_tracked, float eps, float momentum, int act,
-                  int training, const float* residual, float* z, long long rows, int C, lr_stream_t stream);
+                  int training, const float* residual, int res_pre, float* z, long long rows, int C,
+                  lr_stream_t stream);
 /* dx from dz (gradient of z); dgamma / dbeta accumulated into; sums: double[2C] scratch zeroed by the caller.
- * The residual branch's gradient is dz itself. */
+ * z_out == NULL: the activation derivative is evaluated at bn(x) and the residual branch's gradient is dz itself.
+ * z_out != NULL (res_pre blocks, ReLU / ReLU6 only): the derivative is taken through the forward output z_out;
+ * the masked gradient dz * act'(z) -- which is also the identity branch's gradient -- is written to dres if given. */
 int lr_bn_act_bwd(const float* x, const double* stats, const float* gamma, const float* beta,
                   const float* running_mean, const float* running_var, float eps, int act, int training,
-                  const float* dz, double* sums, float* dx, float* dgamma, float* dbeta, long long rows, int C,
-                  lr_stream_t stream);
+                  const float* dz, const float* z_out, float* dres, double* sums, float* dx, float* dgamma,
+                  float* dbeta, long long rows, int C, lr_stream_t stream);
 
 /* Per-frame reductions over the HW pixels of [F, HW, C]:  mode 0: p = mean(a)  (AdaptiveAvgPool2d(1), SE squeeze);
  * mode 1: p = sum(a * g)  (gradient of the SE gate). */
@@ -141,10 +145,47 @@ int lr_frame_reduce(const float* a, const float* g, float* p, int F, int HW, int
  * SE excitation forward, SE backward, average-pool backward. */
 int lr_frame_scale(const float* a, const float* s, const float* dp, float* out, int F, int HW, int C,
                    lr_stream_t stream);
-/* dy *= act'(.) expressed through the activation OUTPUT y (ReLU, hard-sigmoid), in place. */
+/* y = act(x) element-wise (x == y allowed). */
+int lr_act_fwd(const float* x, float* y, long long n, int act, lr_stream_t stream);
+/* dy *= act'(.) expressed through the activation OUTPUT y (ReLU, ReLU6, hard-sigmoid), in place. */
 int lr_act_bwd(float* dy, const float* y, long long n, int act, lr_stream_t stream);
 /* db[n] += sum_m dY[m*ld + n]  (bias gradients) */
 int lr_colsum(const float* dY, long long ld, long long M, int N, float* db, lr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense k x k convolutions (groups == 1) as GEMMs on an explicit patch matrix: torchvision resnet18
+ * (video/models/resnet_lstm.py:79-110, audio/models/resnet_model.py:12-17), AudioEncoder
+ * (audio_video/models/early_fusion.py:21-35), the mobilenet_v2 stem.
+ *
+ * lr_im2col gathers col[(f,hd,wd)][c*kh*kw + r*kw + s] (row pitch ldk, tail columns zeroed) from a source whose
+ * element (f, c, h, w) lies at x[(f/T)*sb + (f%T)*st + c*sc + h*sh + w*sw] (uint8 if is_u8, times `scale`), so the
+ * lip frames are read in the caller's layout exactly as lr_stem_conv_fwd does.
+ *   transposed == 0 (forward / wgrad operand): source pixel (hd*stride - pad + r, wd*stride - pad + s);
+ *                    the column order equals torch's weight layout [Cout][Cin][kh][kw], so y = col . W^T.
+ *   transposed != 0 (dgrad operand, source = dy): source pixel ((hd + pad - r)/stride, (wd + pad - s)/stride) when
+ *                    both divide exactly; dx = colT . Wt^T with Wt from lr_weight_transpose.
+ * Out-of-range taps contribute 0. */
+int lr_im2col(const void* x, int is_u8, float scale, int F, int T, long long sb, long long st, long long sc,
+              long long sh, long long sw, int Hs, int Ws, int C, int kh, int kw, int stride, int pad, int transposed,
+              int Hd, int Wd, float* col, long long ldk, lr_stream_t stream);
+/* wt[c][k*kk + rs] (row pitch ldt) = w[k][c][rs]: the dgrad weight of a dense convolution. */
+int lr_weight_transpose(const float* w, float* wt, int Cout, int Cin, int kk, long long ldt, lr_stream_t stream);
+
+/* nn.MaxPool2d(k, stride, pad) on [F,H,W,C] -> [F,Ho,Wo,C]; arg: uint8 window position of the first maximum
+ * (torch's tie rule), saved for the backward.  The backward is a gather (no atomics). */
+int lr_maxpool_fwd(const float* x, float* y, unsigned char* arg, int F, int H, int W, int C, int k, int stride,
+                   int pad, lr_stream_t stream);
+int lr_maxpool_bwd(const float* dy, const unsigned char* arg, float* dx, int F, int H, int W, int C, int k,
+                   int stride, int pad, lr_stream_t stream);
+
+/* nn.Dropout(p) in training mode: y = keep ? x / (1 - p) : 0 with keep drawn from a counter-based generator keyed by
+ * (seed, *step, element index); *step is a device counter advanced once per train step by lr_rng_tick, so a
+ * replayed CUDA graph draws fresh masks.  (The reference draws from torch's Philox stream; masks are statistically,
+ * not bitwise, equivalent -- parity tests run with p = 0) */
+int lr_dropout_fwd(const float* x, float* y, unsigned char* mask, long long n, float p, unsigned long long seed,
+                   const long long* step, lr_stream_t stream);
+int lr_dropout_bwd(const float* dy, const unsigned char* mask, float* dx, long long n, float p, lr_stream_t stream);
+int lr_rng_tick(long long* step, lr_stream_t stream);
 
 /* One direction of one nn.LSTM layer over `nsteps` <= T steps of its walk (forward: t = 0.., reverse: t = T-1..).
  * xproj: [B*T, 4H] = x W_ih^T + b_ih + b_hh (one lr_gemm); out rows (b*T+t) with stride ldo; gates / cst / hprev
@@ -168,6 +209,14 @@ int lr_audio_conv_fwd(const float* x, const float* w, const float* bias, float* 
                       unsigned char* arg, int B, int H, int W, lr_stream_t stream);
 int lr_audio_conv_bwd(const float* x, const float* dA, long long lda, const unsigned char* arg, float* dw, float* db,
                       int B, int H, int W, lr_stream_t stream);
+
+/* AttentionFusion of the late triple-fusion model (audio_cues_video/models/late_fusion_mobile.py:6-19) around its
+ * attn MLP (two lr_gemm calls): weights = softmax(scores[B,S], dim=1); fused[b,:] = sum_s weights[b,s] stacked[b,s,:].
+ * Backward: dstacked = weights * dfused (the MLP's own backward then accumulates onto it), dscores through the softmax. */
+int lr_attn_fuse_fwd(const float* stacked, const float* scores, float* weights, float* fused, int B, int S, int C,
+                     lr_stream_t stream);
+int lr_attn_fuse_bwd(const float* stacked, const float* weights, const float* dfused, float* dstacked, float* dscores,
+                     int B, int S, int C, lr_stream_t stream);
 
 /* nn.CrossEntropyLoss(mean) forward + gradient (audio_video/train.py:129,65): loss += mean CE (caller zeroes),
  * dlogits = (softmax - onehot) * inv_n (may be NULL), correct += #(argmax == label) (may be NULL). */

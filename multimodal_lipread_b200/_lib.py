@@ -53,7 +53,7 @@ def parse_header(path=HEADER_PATH):
 SIGNATURES = parse_header()
 
 LR_LOGMEL_FRONTEND, LR_LOGMEL_RAW = 0, 1
-ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_HSIGMOID = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_HSIGMOID, ACT_RELU6 = 0, 1, 2, 3, 4
 
 
 def _bind():

@@ -51,7 +51,7 @@ __device__ __forceinline__ Coef coef4(const Bn& b, int c) {
 // z = act(x * scale + shift) (+ residual).  Block (0,0) also performs the running-statistics update.
 __global__ void __launch_bounds__(TH)
 bn_act_fwd_kernel(const Bn b, const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ z,
-                  int rows_per_block) {
+                  int rows_per_block, int res_pre) {
     const nn::CgMap map(b.C, blockIdx.y * blockDim.x);
     if (b.training && b.running_mean && blockIdx.x == 0 && blockIdx.y == 0) {
         for (int c = threadIdx.x; c < b.C; c += blockDim.x) {
@@ -84,20 +84,35 @@ bn_act_fwd_kernel(const Bn b, const float* __restrict__ x, const float* __restri
         for (int u = 0; u < U; ++u) {
             if (r + u * step >= r1) break;
             float4 o;
-            o.x = nn::act_fwd(fmaf(v[u].x, k.scale.x, k.shift.x), b.act);
-            o.y = nn::act_fwd(fmaf(v[u].y, k.scale.y, k.shift.y), b.act);
-            o.z = nn::act_fwd(fmaf(v[u].z, k.scale.z, k.shift.z), b.act);
-            o.w = nn::act_fwd(fmaf(v[u].w, k.scale.w, k.shift.w), b.act);
-            if (res) { o.x += q[u].x; o.y += q[u].y; o.z += q[u].z; o.w += q[u].w; }
+            if (res && res_pre) {               // ResNet BasicBlock: act(bn(x) + identity)
+                o.x = nn::act_fwd(fmaf(v[u].x, k.scale.x, k.shift.x) + q[u].x, b.act);
+                o.y = nn::act_fwd(fmaf(v[u].y, k.scale.y, k.shift.y) + q[u].y, b.act);
+                o.z = nn::act_fwd(fmaf(v[u].z, k.scale.z, k.shift.z) + q[u].z, b.act);
+                o.w = nn::act_fwd(fmaf(v[u].w, k.scale.w, k.shift.w) + q[u].w, b.act);
+            } else {
+                o.x = nn::act_fwd(fmaf(v[u].x, k.scale.x, k.shift.x), b.act);
+                o.y = nn::act_fwd(fmaf(v[u].y, k.scale.y, k.shift.y), b.act);
+                o.z = nn::act_fwd(fmaf(v[u].z, k.scale.z, k.shift.z), b.act);
+                o.w = nn::act_fwd(fmaf(v[u].w, k.scale.w, k.shift.w), b.act);
+                if (res) { o.x += q[u].x; o.y += q[u].y; o.z += q[u].z; o.w += q[u].w; }
+            }
             nn::st4(z + (r + u * step) * b.C + c, o);
         }
     }
 }
 
+// dz masked by the activation derivative expressed through the forward OUTPUT z (pre-activation residual blocks,
+// where u + residual is not recomputable from x alone)
+__device__ __forceinline__ float4 mask_by_out(float4 g, const float4 z, int act) {
+    g.x *= nn::act_grad_from_out(z.x, act); g.y *= nn::act_grad_from_out(z.y, act);
+    g.z *= nn::act_grad_from_out(z.z, act); g.w *= nn::act_grad_from_out(z.w, act);
+    return g;
+}
+
 // backward pass 1: dy = dz * act'(u), u = x*scale + shift;  sums[c] += dy, sums[C+c] += dy * xhat
 __global__ void __launch_bounds__(TH)
 bn_act_bwd_reduce_kernel(const Bn b, const float* __restrict__ x, const float* __restrict__ dz,
-                         double* __restrict__ sums, int rows_per_block) {
+                         const float* __restrict__ zo, double* __restrict__ sums, int rows_per_block) {
     extern __shared__ float sh[];                       // [2C]
     for (int i = threadIdx.x; i < 2 * b.C; i += blockDim.x) sh[i] = 0.f;
     __syncthreads();
@@ -114,15 +129,19 @@ bn_act_bwd_reduce_kernel(const Bn b, const float* __restrict__ x, const float* _
             float4 vv[U], gg[U];
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (r + u * step < r1) { vv[u] = nn::ld4(x + (r + u * step) * b.C + c); gg[u] = nn::ld4(dz + (r + u * step) * b.C + c); }
+                if (r + u * step < r1) {
+                    vv[u] = nn::ld4(x + (r + u * step) * b.C + c); gg[u] = nn::ld4(dz + (r + u * step) * b.C + c);
+                    if (zo) gg[u] = mask_by_out(gg[u], nn::ld4(zo + (r + u * step) * b.C + c), b.act);
+                }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (r + u * step >= r1) break;
                 const float4 v = vv[u], g = gg[u];
-                const float d0 = g.x * nn::act_grad(fmaf(v.x, k.scale.x, k.shift.x), b.act);
-                const float d1 = g.y * nn::act_grad(fmaf(v.y, k.scale.y, k.shift.y), b.act);
-                const float d2 = g.z * nn::act_grad(fmaf(v.z, k.scale.z, k.shift.z), b.act);
-                const float d3 = g.w * nn::act_grad(fmaf(v.w, k.scale.w, k.shift.w), b.act);
+                const int ga = zo ? LR_ACT_NONE : b.act;
+                const float d0 = g.x * nn::act_grad(fmaf(v.x, k.scale.x, k.shift.x), ga);
+                const float d1 = g.y * nn::act_grad(fmaf(v.y, k.scale.y, k.shift.y), ga);
+                const float d2 = g.z * nn::act_grad(fmaf(v.z, k.scale.z, k.shift.z), ga);
+                const float d3 = g.w * nn::act_grad(fmaf(v.w, k.scale.w, k.shift.w), ga);
                 s1.x += d0; s1.y += d1; s1.z += d2; s1.w += d3;
                 s2.x = fmaf(d0, (v.x - k.mean.x) * k.invstd.x, s2.x);
                 s2.y = fmaf(d1, (v.y - k.mean.y) * k.invstd.y, s2.y);
@@ -143,6 +162,7 @@ bn_act_bwd_reduce_kernel(const Bn b, const float* __restrict__ x, const float* _
 // block (0,0) writes dgamma += sum(dy*xhat), dbeta += sum(dy).
 __global__ void __launch_bounds__(TH)
 bn_act_bwd_apply_kernel(const Bn b, const float* __restrict__ x, const float* __restrict__ dz,
+                        const float* __restrict__ zo, float* __restrict__ dres,
                         const double* __restrict__ sums, float* __restrict__ dx, float* __restrict__ dgamma,
                         float* __restrict__ dbeta, int rows_per_block) {
     if (blockIdx.x == 0 && blockIdx.y == 0 && dgamma) {
@@ -168,17 +188,24 @@ bn_act_bwd_apply_kernel(const Bn b, const float* __restrict__ x, const float* __
       float4 vv[U], gg[U];
 #pragma unroll
       for (int u = 0; u < U; ++u)
-          if (rb + u * step < r1) { vv[u] = nn::ld4(x + (rb + u * step) * b.C + c); gg[u] = nn::ld4(dz + (rb + u * step) * b.C + c); }
+          if (rb + u * step < r1) {
+              vv[u] = nn::ld4(x + (rb + u * step) * b.C + c); gg[u] = nn::ld4(dz + (rb + u * step) * b.C + c);
+              if (zo) {
+                  gg[u] = mask_by_out(gg[u], nn::ld4(zo + (rb + u * step) * b.C + c), b.act);
+                  if (dres) nn::st4(dres + (rb + u * step) * b.C + c, gg[u]);     // gradient of the identity branch
+              }
+          }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long r = rb + u * step;
         if (r >= r1) break;
         const float4 v = vv[u], g = gg[u];
+        const int ga = zo ? LR_ACT_NONE : b.act;
         float4 o;
-        o.x = k.scale.x * (g.x * nn::act_grad(fmaf(v.x, k.scale.x, k.shift.x), b.act) - m1[0] - (v.x - k.mean.x) * k.invstd.x * m2[0]);
-        o.y = k.scale.y * (g.y * nn::act_grad(fmaf(v.y, k.scale.y, k.shift.y), b.act) - m1[1] - (v.y - k.mean.y) * k.invstd.y * m2[1]);
-        o.z = k.scale.z * (g.z * nn::act_grad(fmaf(v.z, k.scale.z, k.shift.z), b.act) - m1[2] - (v.z - k.mean.z) * k.invstd.z * m2[2]);
-        o.w = k.scale.w * (g.w * nn::act_grad(fmaf(v.w, k.scale.w, k.shift.w), b.act) - m1[3] - (v.w - k.mean.w) * k.invstd.w * m2[3]);
+        o.x = k.scale.x * (g.x * nn::act_grad(fmaf(v.x, k.scale.x, k.shift.x), ga) - m1[0] - (v.x - k.mean.x) * k.invstd.x * m2[0]);
+        o.y = k.scale.y * (g.y * nn::act_grad(fmaf(v.y, k.scale.y, k.shift.y), ga) - m1[1] - (v.y - k.mean.y) * k.invstd.y * m2[1]);
+        o.z = k.scale.z * (g.z * nn::act_grad(fmaf(v.z, k.scale.z, k.shift.z), ga) - m1[2] - (v.z - k.mean.z) * k.invstd.z * m2[2]);
+        o.w = k.scale.w * (g.w * nn::act_grad(fmaf(v.w, k.scale.w, k.shift.w), ga) - m1[3] - (v.w - k.mean.w) * k.invstd.w * m2[3]);
         nn::st4(dx + r * b.C + c, o);
       }
     }
@@ -246,6 +273,13 @@ act_bwd_kernel(float* __restrict__ dy, const float* __restrict__ y, long long n,
         dy[i] *= nn::act_grad_from_out(y[i], act);
 }
 
+// y = act(x) (stand-alone activation, e.g. the ReLU between nn.LSTM and the classifier in video/models/resnet_lstm.py:152)
+__global__ void __launch_bounds__(TH)
+act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, int act) {
+    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < n; i += (long long)gridDim.x * TH)
+        y[i] = nn::act_fwd(x[i], act);
+}
+
 // db[n] += sum_m dY[m, n]   (row stride ld)
 __global__ void __launch_bounds__(TH)
 colsum_kernel(const float* __restrict__ dY, long long ld, long long M, int N, float* __restrict__ db,
@@ -297,13 +331,13 @@ static bn::Bn make_bn(long long rows, int C, const double* stats, const float* g
 
 #define LR_BN_CHECK(name)                                                                        \
     LR_CHECK_ARG(rows >= 0 && C > 0 && (C & 3) == 0, name ": need rows >= 0 and C %% 4 == 0");  \
-    LR_CHECK_ARG(act >= LR_ACT_NONE && act <= LR_ACT_HSIGMOID, name ": bad activation");        \
+    LR_CHECK_ARG(act >= LR_ACT_NONE && act <= LR_ACT_RELU6, name ": bad activation");        \
     LR_CHECK_ARG(training ? stats != nullptr : (running_mean && running_var), name ": missing statistics"); \
     if (rows == 0) return LR_OK
 
 extern "C" int lr_bn_act_fwd(const float* x, const double* stats, const float* gamma, const float* beta,
                              float* running_mean, float* running_var, long long* num_batches_tracked, float eps,
-                             float momentum, int act, int training, const float* residual, float* z,
+                             float momentum, int act, int training, const float* residual, int res_pre, float* z,
                              long long rows, int C, lr_stream_t stream) {
     LR_BN_CHECK("lr_bn_act_fwd");
     LR_CHECK_ARG(x && gamma && beta && z, "lr_bn_act_fwd: null pointer");
@@ -312,7 +346,7 @@ extern "C" int lr_bn_act_fwd(const float* x, const double* stats, const float* g
     dim3 grid(gx, nn::cg_block_cols(C, bn::TH));
     bn::bn_act_fwd_kernel<<<grid, bn::TH, 0, stream>>>(
         make_bn(rows, C, stats, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, act, training),
-        x, residual, z, rpb);
+        x, residual, z, rpb, res_pre);
     lr::count_launch();
     LR_CHECK_LAUNCH("bn_act_fwd_kernel");
     return LR_OK;
@@ -320,19 +354,21 @@ extern "C" int lr_bn_act_fwd(const float* x, const double* stats, const float* g
 
 extern "C" int lr_bn_act_bwd(const float* x, const double* stats, const float* gamma, const float* beta,
                              const float* running_mean, const float* running_var, float eps, int act, int training,
-                             const float* dz, double* sums /*[2C], zeroed by the caller*/, float* dx, float* dgamma,
-                             float* dbeta, long long rows, int C, lr_stream_t stream) {
+                             const float* dz, const float* z_out, float* dres, double* sums /*[2C], zeroed by the caller*/,
+                             float* dx, float* dgamma, float* dbeta, long long rows, int C, lr_stream_t stream) {
     LR_BN_CHECK("lr_bn_act_bwd");
     LR_CHECK_ARG(x && gamma && beta && dz && sums && dx, "lr_bn_act_bwd: null pointer");
-    LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(dz); LR_CHECK_ALIGN(dx);
+    LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(dz); LR_CHECK_ALIGN(dx); LR_CHECK_ALIGN(z_out); LR_CHECK_ALIGN(dres);
+    LR_CHECK_ARG(!z_out || act == LR_ACT_RELU || act == LR_ACT_RELU6 || act == LR_ACT_NONE,
+                 "lr_bn_act_bwd: output-form derivative exists for ReLU / ReLU6 only");
     int gx; const int rpb = rows_per_block_for(rows, C, &gx);
     dim3 grid(gx, nn::cg_block_cols(C, bn::TH));
     const bn::Bn b = make_bn(rows, C, stats, gamma, beta, const_cast<float*>(running_mean),
                              const_cast<float*>(running_var), nullptr, eps, 0.f, act, training);
-    bn::bn_act_bwd_reduce_kernel<<<grid, bn::TH, 2 * C * sizeof(float), stream>>>(b, x, dz, sums, rpb);
+    bn::bn_act_bwd_reduce_kernel<<<grid, bn::TH, 2 * C * sizeof(float), stream>>>(b, x, dz, z_out, sums, rpb);
     lr::count_launch();
     LR_CHECK_LAUNCH("bn_act_bwd_reduce_kernel");
-    bn::bn_act_bwd_apply_kernel<<<grid, bn::TH, 0, stream>>>(b, x, dz, sums, dx, dgamma, dbeta, rpb);
+    bn::bn_act_bwd_apply_kernel<<<grid, bn::TH, 0, stream>>>(b, x, dz, z_out, dres, sums, dx, dgamma, dbeta, rpb);
     lr::count_launch();
     LR_CHECK_LAUNCH("bn_act_bwd_apply_kernel");
     return LR_OK;
@@ -369,7 +405,7 @@ extern "C" int lr_frame_scale(const float* a, const float* s, const float* dp, f
 
 extern "C" int lr_act_bwd(float* dy, const float* y, long long n, int act, lr_stream_t stream) {
     LR_CHECK_ARG(n >= 0, "lr_act_bwd: negative size");
-    LR_CHECK_ARG(act == LR_ACT_RELU || act == LR_ACT_HSIGMOID || act == LR_ACT_NONE, "lr_act_bwd: activation has no output-form derivative");
+    LR_CHECK_ARG(act == LR_ACT_RELU || act == LR_ACT_HSIGMOID || act == LR_ACT_RELU6 || act == LR_ACT_NONE, "lr_act_bwd: activation has no output-form derivative");
     if (n == 0 || act == LR_ACT_NONE) return LR_OK;
     LR_CHECK_ARG(dy && y, "lr_act_bwd: null pointer");
     long long g = (n + bn::TH - 1) / bn::TH;
@@ -378,6 +414,20 @@ extern "C" int lr_act_bwd(float* dy, const float* y, long long n, int act, lr_st
     bn::act_bwd_kernel<<<(unsigned)g, bn::TH, 0, stream>>>(dy, y, n, act);
     lr::count_launch();
     LR_CHECK_LAUNCH("act_bwd_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_act_fwd(const float* x, float* y, long long n, int act, lr_stream_t stream) {
+    LR_CHECK_ARG(n >= 0, "lr_act_fwd: negative size");
+    LR_CHECK_ARG(act >= LR_ACT_NONE && act <= LR_ACT_RELU6, "lr_act_fwd: bad activation");
+    if (n == 0) return LR_OK;
+    LR_CHECK_ARG(x && y, "lr_act_fwd: null pointer");
+    long long g = (n + bn::TH - 1) / bn::TH;
+    const long long cap = (long long)lr::sm_count() * 16;
+    if (g > cap) g = cap;
+    bn::act_fwd_kernel<<<(unsigned)g, bn::TH, 0, stream>>>(x, y, n, act);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("act_fwd_kernel");
     return LR_OK;
 }
 

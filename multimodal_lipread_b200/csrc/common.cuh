@@ -38,6 +38,13 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 void count_launch(int n = 1);
 int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
 
+// uint8 pixel -> float.  The reference divides (`lip_regions.astype(np.float32) / 255.0`,
+// video/data_utils/dataset_loader.py:90): x / 255 and x * (1/255) differ in the last bit for some x, so the
+// canonical scale 1/255 is applied as a true division; any other scale is a multiplication.
+__device__ __forceinline__ float u8_scaled(unsigned char v, float scale) {
+    return scale == (1.f / 255.f) ? __fdiv_rn((float)v, 255.f) : (float)v * scale;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -23,7 +23,7 @@ struct StemIn {
 };
 __device__ __forceinline__ float stem_load(const StemIn& in, int f, int c, int h, int w) {
     const long long off = (long long)f * in.sf + (long long)c * in.sc + (long long)h * in.sh + (long long)w * in.sw;
-    return in.is_u8 ? float(static_cast<const unsigned char*>(in.x)[off]) * in.scale
+    return in.is_u8 ? lr::u8_scaled(static_cast<const unsigned char*>(in.x)[off], in.scale)
                     : static_cast<const float*>(in.x)[off] * in.scale;
 }
 // Frame index f = b*T + t maps to (b, t) strides through `sf` only when the (b, t) pair is
@@ -38,7 +38,7 @@ __device__ __forceinline__ long long frame_base(const StemIn2& s, int f) {
 }
 __device__ __forceinline__ float stem_ld(const StemIn2& s, long long fb, int c, int h, int w) {
     const long long off = fb + (long long)c * s.in.sc + (long long)h * s.in.sh + (long long)w * s.in.sw;
-    return s.in.is_u8 ? float(static_cast<const unsigned char*>(s.in.x)[off]) * s.in.scale
+    return s.in.is_u8 ? lr::u8_scaled(static_cast<const unsigned char*>(s.in.x)[off], s.in.scale)
                       : static_cast<const float*>(s.in.x)[off] * s.in.scale;
 }
 

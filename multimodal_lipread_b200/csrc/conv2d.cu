@@ -1,0 +1,286 @@
+// Dense (groups == 1) k x k convolutions as GEMMs on an explicit patch matrix, plus the pooling / dropout
+// kernels of the ResNet-18 trunk and the early-fusion audio encoder (channels-last fp32).
+//
+//   forward   col = im2col(x)            [F*Ho*Wo, Cin*kh*kw]   (column order (c, r, s) == torch's weight layout,
+//             y   = col . W^T            lr_gemm_tf32 (tcgen05) with W[Cout][Cin*kh*kw] used as it lies in HBM)
+//   wgrad     dW += dy^T . col           (same col, kept from the forward)
+//   dgrad     colT = im2col_T(dy)        [F*H*W, Cout*kh*kw]: the gather form of the transposed convolution
+//             dx   = colT . Wt^T         with Wt[Cin][Cout*kh*kw] = W transposed over its first two dims
+// Reference call sites: torchvision resnet18 (video/models/resnet_lstm.py:79-110, audio/models/resnet_model.py:12-17,
+// audio_cues_video/models/late_fusion_mobile.py:57-66), AudioEncoder (audio_video/models/early_fusion.py:21-35),
+// torchvision mobilenet_v2 stem (audio_cues_video/models/late_fusion_mobile.py:33-40).
+#include "nn_common.cuh"
+
+namespace c2 {
+
+constexpr int TH = 256;
+
+struct Src {
+    const void* x;
+    int is_u8; float scale;
+    int T; long long sb, st, sc, sh, sw;     // element (f, c, h, w) at (f/T)*sb + (f%T)*st + c*sc + h*sh + w*sw
+    int Hs, Ws, C;                           // source frame geometry
+};
+struct Geo {
+    int Hd, Wd;                              // destination rows run over (f, hd, wd)
+    int kh, kw, stride, pad, transposed;
+    int K, ldk;                              // K = C*kh*kw valid columns, ldk = row pitch (multiple of 4), tail zeroed
+};
+
+__device__ __forceinline__ float src_ld(const Src& s, long long fb, int c, int h, int w) {
+    const long long off = fb + (long long)c * s.sc + (long long)h * s.sh + (long long)w * s.sw;
+    return s.is_u8 ? lr::u8_scaled(static_cast<const unsigned char*>(s.x)[off], s.scale)
+                   : static_cast<const float*>(s.x)[off] * s.scale;
+}
+
+// one thread -> 4 consecutive columns of one row (coalesced float4 store; the gathers hit L1)
+__global__ void __launch_bounds__(TH)
+im2col_kernel(const Src s, const Geo g, float* __restrict__ col, long long rows) {
+    const int q4 = g.ldk >> 2;
+    const long long total = rows * q4;
+    const int kk = g.kh * g.kw;
+    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < total; i += (long long)gridDim.x * TH) {
+        const long long row = i / q4;
+        const int k0 = int(i - row * q4) * 4;
+        const int wd = int(row % g.Wd);
+        const long long t = row / g.Wd;
+        const int hd = int(t % g.Hd), f = int(t / g.Hd);
+        const long long fb = (long long)(f / s.T) * s.sb + (long long)(f % s.T) * s.st;
+        int c = k0 / kk, rs = k0 - c * kk;
+        int r = rs / g.kw, q = rs - r * g.kw;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float val = 0.f;
+            if (k0 + j < g.K) {
+                int hs, ws; bool ok;
+                if (!g.transposed) {
+                    hs = hd * g.stride - g.pad + r; ws = wd * g.stride - g.pad + q;
+                    ok = hs >= 0 && hs < s.Hs && ws >= 0 && ws < s.Ws;
+                } else {
+                    const int hn = hd + g.pad - r, wn = wd + g.pad - q;
+                    hs = hn / g.stride; ws = wn / g.stride;
+                    ok = hn >= 0 && wn >= 0 && hs * g.stride == hn && ws * g.stride == wn && hs < s.Hs && ws < s.Ws;
+                }
+                if (ok) val = src_ld(s, fb, c, hs, ws);
+            }
+            v[j] = val;
+            if (++q == g.kw) { q = 0; if (++r == g.kh) { r = 0; ++c; } }
+        }
+        nn::st4(col + row * g.ldk + k0, make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
+
+// wt[c][k][rs] = w[k][c][rs]  (row pitch of wt = ldt >= Cout*kk, tail zeroed by the caller once)
+__global__ void __launch_bounds__(TH)
+weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin, int kk, long long ldt) {
+    const long long n = (long long)Cout * Cin * kk;
+    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < n; i += (long long)gridDim.x * TH) {
+        const int rs = int(i % kk);
+        const long long t = i / kk;
+        const int k = int(t % Cout), c = int(t / Cout);
+        wt[(long long)c * ldt + (long long)k * kk + rs] = w[((long long)k * Cin + c) * kk + rs];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ max pooling
+// y[f,ho,wo,c] = max over the window (padding = -inf), arg = r*k + s of the FIRST maximum in scan order
+// (torch.nn.MaxPool2d tie rule: `val > maxval`).
+__global__ void __launch_bounds__(TH)
+maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned char* __restrict__ arg, int F, int H,
+                   int W, int C, int k, int stride, int pad, int Ho, int Wo) {
+    const int c4n = C >> 2;
+    const long long total = (long long)F * Ho * Wo * c4n;
+    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < total; i += (long long)gridDim.x * TH) {
+        const int c = int(i % c4n) * 4;
+        long long t = i / c4n;
+        const int wo = int(t % Wo); t /= Wo;
+        const int ho = int(t % Ho), f = int(t / Ho);
+        float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        unsigned char a[4] = {0, 0, 0, 0};
+        for (int r = 0; r < k; ++r) {
+            const int h = ho * stride - pad + r;
+            if (h < 0 || h >= H) continue;
+            for (int s = 0; s < k; ++s) {
+                const int w = wo * stride - pad + s;
+                if (w < 0 || w >= W) continue;
+                const float4 v = nn::ld4(x + (((long long)f * H + h) * W + w) * C + c);
+                const unsigned char code = (unsigned char)(r * k + s);
+                if (v.x > m[0] || v.x != v.x) { m[0] = v.x; a[0] = code; }
+                if (v.y > m[1] || v.y != v.y) { m[1] = v.y; a[1] = code; }
+                if (v.z > m[2] || v.z != v.z) { m[2] = v.z; a[2] = code; }
+                if (v.w > m[3] || v.w != v.w) { m[3] = v.w; a[3] = code; }
+            }
+        }
+        const long long o = (((long long)f * Ho + ho) * Wo + wo) * C + c;
+        nn::st4(y + o, make_float4(m[0], m[1], m[2], m[3]));
+        *reinterpret_cast<uchar4*>(arg + o) = make_uchar4(a[0], a[1], a[2], a[3]);
+    }
+}
+
+// dx[f,h,w,c] = sum of dy over the windows whose saved arg-max is (h, w)   (gather form: no atomics)
+__global__ void __launch_bounds__(TH)
+maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ arg, float* __restrict__ dx, int F,
+                   int H, int W, int C, int k, int stride, int pad, int Ho, int Wo) {
+    const int c4n = C >> 2;
+    const long long total = (long long)F * H * W * c4n;
+    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < total; i += (long long)gridDim.x * TH) {
+        const int c = int(i % c4n) * 4;
+        long long t = i / c4n;
+        const int w = int(t % W); t /= W;
+        const int h = int(t % H), f = int(t / H);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int ho_lo = max(0, (h + pad - k + stride) / stride), ho_hi = min(Ho - 1, (h + pad) / stride);
+        const int wo_lo = max(0, (w + pad - k + stride) / stride), wo_hi = min(Wo - 1, (w + pad) / stride);
+        for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+            const int r = h + pad - ho * stride;
+            if (r < 0 || r >= k) continue;
+            for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+                const int s = w + pad - wo * stride;
+                if (s < 0 || s >= k) continue;
+                const long long o = (((long long)f * Ho + ho) * Wo + wo) * C + c;
+                const uchar4 a = *reinterpret_cast<const uchar4*>(arg + o);
+                const float4 g = nn::ld4(dy + o);
+                const unsigned char code = (unsigned char)(r * k + s);
+                if (a.x == code) acc.x += g.x;
+                if (a.y == code) acc.y += g.y;
+                if (a.z == code) acc.z += g.z;
+                if (a.w == code) acc.w += g.w;
+            }
+        }
+        nn::st4(dx + (((long long)f * H + h) * W + w) * C + c, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ dropout
+// Counter-based generator: keep(i) = hash(seed, step, i) >= p.  `step` lives on the device and is advanced by
+// lr_rng_tick once per training step, so a captured CUDA graph draws a fresh mask on every replay.
+__device__ __forceinline__ uint32_t mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return (uint32_t)((x ^ (x >> 31)) >> 32);
+}
+__global__ void __launch_bounds__(TH)
+dropout_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned char* __restrict__ mask, long long n,
+                   float p, unsigned long long seed, const long long* __restrict__ step) {
+    const unsigned long long base = seed * 0xD1342543DE82EF95ull + (unsigned long long)(*step) * 0xA0761D6478BD642Full;
+    const float inv_keep = 1.f / (1.f - p);
+    const uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
+    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < n; i += (long long)gridDim.x * TH) {
+        const bool keep = mix64(base + (unsigned long long)i) >= thr;
+        mask[i] = keep ? 1 : 0;
+        y[i] = keep ? x[i] * inv_keep : 0.f;
+    }
+}
+__global__ void __launch_bounds__(TH)
+dropout_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ mask, float* __restrict__ dx,
+                   long long n, float inv_keep) {
+    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < n; i += (long long)gridDim.x * TH)
+        dx[i] = mask[i] ? dy[i] * inv_keep : 0.f;
+}
+__global__ void rng_tick_kernel(long long* step) { *step += 1; }
+
+static unsigned grid_for(long long work) {
+    long long g = (work + TH - 1) / TH;
+    const long long cap = (long long)lr::sm_count() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+}  // namespace c2
+
+extern "C" int lr_im2col(const void* x, int is_u8, float scale, int F, int T, long long sb, long long st, long long sc,
+                         long long sh, long long sw, int Hs, int Ws, int C, int kh, int kw, int stride, int pad,
+                         int transposed, int Hd, int Wd, float* col, long long ldk, lr_stream_t stream) {
+    LR_CHECK_ARG(F >= 0 && T > 0 && Hs > 0 && Ws > 0 && C > 0 && Hd > 0 && Wd > 0, "lr_im2col: bad shape");
+    LR_CHECK_ARG(kh > 0 && kw > 0 && stride > 0 && pad >= 0, "lr_im2col: bad window");
+    const long long K = (long long)C * kh * kw;
+    LR_CHECK_ARG(ldk >= K && (ldk & 3) == 0, "lr_im2col: ldk must be >= C*kh*kw and a multiple of 4");
+    if (F == 0) return LR_OK;
+    LR_CHECK_ARG(x && col, "lr_im2col: null pointer");
+    LR_CHECK_ALIGN(col);
+    c2::Src s;
+    s.x = x; s.is_u8 = is_u8; s.scale = scale; s.T = T; s.sb = sb; s.st = st; s.sc = sc; s.sh = sh; s.sw = sw;
+    s.Hs = Hs; s.Ws = Ws; s.C = C;
+    c2::Geo g;
+    g.Hd = Hd; g.Wd = Wd; g.kh = kh; g.kw = kw; g.stride = stride; g.pad = pad; g.transposed = transposed;
+    g.K = (int)K; g.ldk = (int)ldk;
+    const long long rows = (long long)F * Hd * Wd;
+    c2::im2col_kernel<<<c2::grid_for(rows * (ldk >> 2)), c2::TH, 0, stream>>>(s, g, col, rows);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("im2col_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_weight_transpose(const float* w, float* wt, int Cout, int Cin, int kk, long long ldt,
+                                   lr_stream_t stream) {
+    LR_CHECK_ARG(Cout > 0 && Cin > 0 && kk > 0 && ldt >= (long long)Cout * kk, "lr_weight_transpose: bad shape");
+    LR_CHECK_ARG(w && wt, "lr_weight_transpose: null pointer");
+    c2::weight_transpose_kernel<<<c2::grid_for((long long)Cout * Cin * kk), c2::TH, 0, stream>>>(w, wt, Cout, Cin, kk, ldt);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("weight_transpose_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_maxpool_fwd(const float* x, float* y, unsigned char* arg, int F, int H, int W, int C, int k,
+                              int stride, int pad, lr_stream_t stream) {
+    LR_CHECK_ARG(F >= 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, "lr_maxpool_fwd: bad shape (C %% 4 != 0?)");
+    LR_CHECK_ARG(k > 0 && k <= 15 && stride > 0 && pad >= 0 && 2 * pad <= k, "lr_maxpool_fwd: bad window");
+    if (F == 0) return LR_OK;
+    LR_CHECK_ARG(x && y && arg, "lr_maxpool_fwd: null pointer");
+    LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(y);
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    LR_CHECK_ARG(Ho > 0 && Wo > 0, "lr_maxpool_fwd: window larger than the input");
+    c2::maxpool_fwd_kernel<<<c2::grid_for((long long)F * Ho * Wo * (C >> 2)), c2::TH, 0, stream>>>(
+        x, y, arg, F, H, W, C, k, stride, pad, Ho, Wo);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("maxpool_fwd_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_maxpool_bwd(const float* dy, const unsigned char* arg, float* dx, int F, int H, int W, int C, int k,
+                              int stride, int pad, lr_stream_t stream) {
+    LR_CHECK_ARG(F >= 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, "lr_maxpool_bwd: bad shape");
+    LR_CHECK_ARG(k > 0 && k <= 15 && stride > 0 && pad >= 0 && 2 * pad <= k, "lr_maxpool_bwd: bad window");
+    if (F == 0) return LR_OK;
+    LR_CHECK_ARG(dy && arg && dx, "lr_maxpool_bwd: null pointer");
+    LR_CHECK_ALIGN(dy); LR_CHECK_ALIGN(dx);
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    c2::maxpool_bwd_kernel<<<c2::grid_for((long long)F * H * W * (C >> 2)), c2::TH, 0, stream>>>(
+        dy, arg, dx, F, H, W, C, k, stride, pad, Ho, Wo);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("maxpool_bwd_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_dropout_fwd(const float* x, float* y, unsigned char* mask, long long n, float p,
+                              unsigned long long seed, const long long* step, lr_stream_t stream) {
+    LR_CHECK_ARG(n >= 0 && p >= 0.f && p < 1.f, "lr_dropout_fwd: need n >= 0 and 0 <= p < 1");
+    if (n == 0) return LR_OK;
+    LR_CHECK_ARG(x && y && mask && step, "lr_dropout_fwd: null pointer");
+    c2::dropout_fwd_kernel<<<c2::grid_for(n), c2::TH, 0, stream>>>(x, y, mask, n, p, seed, step);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("dropout_fwd_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_dropout_bwd(const float* dy, const unsigned char* mask, float* dx, long long n, float p,
+                              lr_stream_t stream) {
+    LR_CHECK_ARG(n >= 0 && p >= 0.f && p < 1.f, "lr_dropout_bwd: need n >= 0 and 0 <= p < 1");
+    if (n == 0) return LR_OK;
+    LR_CHECK_ARG(dy && mask && dx, "lr_dropout_bwd: null pointer");
+    c2::dropout_bwd_kernel<<<c2::grid_for(n), c2::TH, 0, stream>>>(dy, mask, dx, n, 1.f / (1.f - p));
+    lr::count_launch();
+    LR_CHECK_LAUNCH("dropout_bwd_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_rng_tick(long long* step, lr_stream_t stream) {
+    LR_CHECK_ARG(step, "lr_rng_tick: null pointer");
+    c2::rng_tick_kernel<<<1, 1, 0, stream>>>(step);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("rng_tick_kernel");
+    return LR_OK;
+}

@@ -179,7 +179,7 @@ extern "C" int lr_gemm(const float* A, long long lda, int a_trans, const float* 
     LR_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "lr_gemm: negative dimension");
     if (M == 0 || N == 0) return LR_OK;
     LR_CHECK_ARG(A && B && C, "lr_gemm: null pointer");
-    LR_CHECK_ARG(act >= LR_ACT_NONE && act <= LR_ACT_HSIGMOID, "lr_gemm: bad activation %d", act);
+    LR_CHECK_ARG(act >= LR_ACT_NONE && act <= LR_ACT_RELU6, "lr_gemm: bad activation %d", act);
     LR_CHECK_ARG(ksplit >= 1, "lr_gemm: ksplit must be >= 1");
     LR_CHECK_ARG(ksplit == 1 || (act == LR_ACT_NONE && !R && !stats),
                  "lr_gemm: split-K accumulates atomically and cannot fuse act / residual / stats");

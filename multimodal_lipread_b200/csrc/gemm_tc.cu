@@ -354,7 +354,7 @@ extern "C" int lr_gemm_tf32(const float* A, long long lda, int a_trans, const fl
     LR_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "lr_gemm_tf32: bad dimension");
     if (M == 0 || N == 0) return LR_OK;
     LR_CHECK_ARG(A && B && C, "lr_gemm_tf32: null pointer");
-    LR_CHECK_ARG(act >= LR_ACT_NONE && act <= LR_ACT_HSIGMOID, "lr_gemm_tf32: bad activation %d", act);
+    LR_CHECK_ARG(act >= LR_ACT_NONE && act <= LR_ACT_RELU6, "lr_gemm_tf32: bad activation %d", act);
     LR_CHECK_ARG((lda & 3) == 0 && (ldb & 3) == 0, "lr_gemm_tf32: lda / ldb must be multiples of 4 floats (TMA 16-byte stride)");
     LR_CHECK_ARG(ksplit >= 1, "lr_gemm_tf32: ksplit must be >= 1");
     LR_CHECK_ARG(ksplit == 1 || (act == LR_ACT_NONE && !R && !stats && !bias),

@@ -11,6 +11,7 @@ __device__ __forceinline__ float act_fwd(float u, int act) {
         case LR_ACT_RELU: return fmaxf(u, 0.f);
         case LR_ACT_HSWISH: return u * fminf(fmaxf(u + 3.f, 0.f), 6.f) * (1.f / 6.f);
         case LR_ACT_HSIGMOID: return fminf(fmaxf(u + 3.f, 0.f), 6.f) * (1.f / 6.f);
+        case LR_ACT_RELU6: return fminf(fmaxf(u, 0.f), 6.f);
         default: return u;
     }
 }
@@ -21,6 +22,7 @@ __device__ __forceinline__ float act_grad(float u, int act) {
         case LR_ACT_RELU: return u > 0.f ? 1.f : 0.f;
         case LR_ACT_HSWISH: return u < -3.f ? 0.f : (u <= 3.f ? u * (1.f / 3.f) + 0.5f : 1.f);
         case LR_ACT_HSIGMOID: return (u > -3.f && u < 3.f) ? (1.f / 6.f) : 0.f;
+        case LR_ACT_RELU6: return (u > 0.f && u < 6.f) ? 1.f : 0.f;
         default: return 1.f;
     }
 }
@@ -29,6 +31,7 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act) {
     switch (act) {
         case LR_ACT_RELU: return y > 0.f ? 1.f : 0.f;
         case LR_ACT_HSIGMOID: return (y > 0.f && y < 1.f) ? (1.f / 6.f) : 0.f;
+        case LR_ACT_RELU6: return (y > 0.f && y < 6.f) ? 1.f : 0.f;
         default: return 1.f;
     }
 }

@@ -19,9 +19,10 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import lib, ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_HSIGMOID
+from ._lib import lib, ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_HSIGMOID, ACT_RELU6
 
-_ACT_OF = {nn.ReLU: ACT_RELU, nn.Hardswish: ACT_HSWISH, nn.Hardsigmoid: ACT_HSIGMOID, nn.Identity: ACT_NONE}
+_ACT_OF = {nn.ReLU: ACT_RELU, nn.Hardswish: ACT_HSWISH, nn.Hardsigmoid: ACT_HSIGMOID, nn.ReLU6: ACT_RELU6,
+           nn.Identity: ACT_NONE}
 
 
 def _act_code(mod):
@@ -184,6 +185,10 @@ class Plan:
         self.sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
         self._stat_reqs = []
         self.stats = None
+        self._ws_floats = 0                            # shared scratch (dgrad patch matrices), sized at finalize()
+        self._ws = None
+        self.rng_step = None                           # device counter behind the dropout masks
+        self._n_dropout = 0
 
     # ---- memory
     def alloc(self, n, dtype=torch.float32):
@@ -207,6 +212,8 @@ class Plan:
             s["fwd"] = base + 8 * off
             s["bwd"] = base + 8 * (off + 2 * s["C"])
             off += 4 * s["C"]
+        if self._ws_floats:
+            self._ws = self.alloc(self._ws_floats)
         for ops in [self.fwd] + [g for g in self.bwd_rev]:
             ops.ops = [(fn, tuple(a() if callable(a) else a for a in args), name, leaf) for fn, args, name, leaf in ops.ops]
         self.bwd = OpList()
@@ -217,6 +224,12 @@ class Plan:
         g = OpList()
         self.bwd_rev.append(g)
         return g
+
+    def workspace(self, n_floats):
+        """A scratch buffer shared by every op that asks (used and consumed within one backward group on the
+        main stream); returns a thunk resolved by finalize()."""
+        self._ws_floats = max(self._ws_floats, int(n_floats))
+        return lambda: self._ws.data_ptr()
 
     # ---- op emitters ----------------------------------------------------------------------------------
     def gemm(self, ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias=0, act=ACT_NONE, R=0, ldr=0, stats=0, ksplit=1,
@@ -268,18 +281,21 @@ class Plan:
         if dx is not None:
             self.gemm_auto(g, dy, ldy, 0, w, K, 1, dx, ldx, M, K, N, R=dx_residual, ldr=ldr)
 
-    def bn_act(self, x, bn, act, out, residual=None):
-        """out.val = act(bn(x.val)) (+ residual.val); backward: x.grad from out.grad (residual.grad is out.grad)."""
+    def bn_act(self, x, bn, act, out, residual=None, res_pre=False, dres=None):
+        """out.val = act(bn(x.val)) (+ residual.val); backward: x.grad from out.grad (residual.grad is out.grad).
+        res_pre (ResNet BasicBlock): out.val = act(bn(x.val) + residual.val); the backward takes the derivative
+        through out.val and writes the masked gradient (= the identity branch's gradient) to `dres`."""
         slot = x.stat_slot
         st = (lambda s=slot: s["fwd"]) if self.training else 0
+        momentum = 0.1 if bn.momentum is None else float(bn.momentum)
         self.fwd.add("lr_bn_act_fwd", x.val, st, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                     bn.num_batches_tracked, float(bn.eps), float(bn.momentum), act, int(self.training),
-                     residual.val if residual is not None else 0, out.val, x.rows, x.C)
+                     bn.num_batches_tracked, float(bn.eps), momentum, act, int(self.training),
+                     residual.val if residual is not None else 0, int(res_pre), out.val, x.rows, x.C)
         if self.with_backward:
             g = self.bgroup()
             g.add("lr_bn_act_bwd", x.val, st, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.eps), act,
-                  int(self.training), out.grad, (lambda s=slot: s["bwd"]), x.grad, self.flat.g(bn.weight),
-                  self.flat.g(bn.bias), x.rows, x.C)
+                  int(self.training), out.grad, (out.val if res_pre else 0), (dres if dres is not None else 0),
+                  (lambda s=slot: s["bwd"]), x.grad, self.flat.g(bn.weight), self.flat.g(bn.bias), x.rows, x.C)
 
     def pw_conv(self, x, conv, F, H, W):
         """1x1 convolution as a GEMM on [rows, Cin]; returns the raw output tensor (with BN statistics slot)."""
@@ -330,29 +346,38 @@ class Plan:
             if hasattr(blk, "block"):
                 cur = self.inverted_residual(blk, cur)
             else:
-                conv, bn, act = blk[0], blk[1], _act_code(blk[2])
-                assert conv.kernel_size == (1, 1)
-                raw = self.pw_conv(cur, conv, cur.F, cur.H, cur.W)
-                if self.with_backward:
-                    self.linear_bwd(self.bgroup(), cur.val, conv.in_channels, cur.rows, conv.weight, None, raw.grad,
-                                    conv.out_channels, dx=cur.grad, ldx=conv.in_channels)
-                out = T2(self, cur.F, cur.H, cur.W, conv.out_channels)
-                self.bn_act(raw, bn, act, out)
-                cur = out
+                cur = self.pw_bn_act(cur, blk[0], blk[1], _act_code(blk[2]))
         return cur
+
+    @staticmethod
+    def _ir_layers(blk):
+        """torchvision InvertedResidual (MobileNetV3: blk.block, MobileNetV2: blk.conv) -> [("conv", conv, bn, act) |
+        ("se", module)], use_res."""
+        out = []
+        mods = list(blk.block) if hasattr(blk, "block") else list(blk.conv)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if type(m).__name__ == "SqueezeExcitation":
+                out.append(("se", m))
+            elif isinstance(m, nn.Conv2d):                       # MobileNetV2 tail: bare Conv2d followed by BatchNorm2d
+                out.append(("conv", m, mods[i + 1], ACT_NONE))
+                i += 1
+            else:                                                # Conv2dNormActivation
+                out.append(("conv", m[0], m[1], _act_code(m[2]) if len(m) > 2 else ACT_NONE))
+            i += 1
+        return out, bool(blk.use_res_connect)
 
     def inverted_residual(self, blk, x):
         """torchvision InvertedResidual: [1x1 expand+BN+act] -> depthwise+BN+act -> [SE] -> 1x1 project+BN (+x)."""
-        layers = list(blk.block)
-        use_res = bool(blk.use_res_connect)
+        layers, use_res = self._ir_layers(blk)
         cur, deferred = x, []
         for li, layer in enumerate(layers):
             last = li == len(layers) - 1
-            if type(layer).__name__ == "SqueezeExcitation":
-                cur = self.squeeze_excite(layer, cur)
+            if layer[0] == "se":
+                cur = self.squeeze_excite(layer[1], cur)
                 continue
-            conv, bn = layer[0], layer[1]
-            act = _act_code(layer[2]) if len(layer) > 2 else ACT_NONE
+            _, conv, bn, act = layer
             if conv.groups == 1:
                 assert conv.kernel_size == (1, 1)
                 raw = self.pw_conv(cur, conv, cur.F, cur.H, cur.W)
@@ -373,6 +398,35 @@ class Plan:
             Cout, Cin = conv.out_channels, conv.in_channels
             self.linear_bwd(g, inp.val, Cin, inp.rows, conv.weight, None, raw.grad, Cout, dx=inp.grad, ldx=Cin,
                             dx_residual=(cur.grad if add_res else 0), ldr=Cin)
+        return cur
+
+    def pw_bn_act(self, cur, conv, bn, act):
+        """Stand-alone 1x1 Conv2dNormActivation (the last `features` stage of MobileNetV2 / V3)."""
+        assert conv.kernel_size == (1, 1) and conv.groups == 1
+        raw = self.pw_conv(cur, conv, cur.F, cur.H, cur.W)
+        if self.with_backward:
+            self.linear_bwd(self.bgroup(), cur.val, conv.in_channels, cur.rows, conv.weight, None, raw.grad,
+                            conv.out_channels, dx=cur.grad, ldx=conv.in_channels)
+        out = T2(self, cur.F, cur.H, cur.W, conv.out_channels)
+        self.bn_act(raw, bn, act, out)
+        return out
+
+    def mbv2_features(self, feats, frames):
+        """torchvision mobilenet_v2 `features` on frames = (tensor, layout, scale) -> last activation T2
+        (audio_cues_video/models/late_fusion_mobile.py:33-40, video/models/mobilenet_lstm.py:29-39)."""
+        stem = feats[0]
+        raw = self.dense_conv(None, stem[0], frames=frames)
+        if self.with_backward:
+            self.dense_conv_bwd(raw)
+        cur = T2(self, raw.F, raw.H, raw.W, raw.C)
+        self.bn_act(raw, stem[1], _act_code(stem[2]), cur)
+        self.trace = [cur]
+        for blk in feats[1:]:
+            if hasattr(blk, "conv"):
+                cur = self.inverted_residual(blk, cur)
+            else:
+                cur = self.pw_bn_act(cur, blk[0], blk[1], _act_code(blk[2]))
+            self.trace.append(cur)
         return cur
 
     def squeeze_excite(self, se, a):
@@ -405,3 +459,226 @@ class Plan:
             g = self.bgroup()
             g.add("lr_frame_scale", 0, 0, dfeat, a.grad, F, HW, C)
         return feat, dfeat
+
+    # ---- dense convolutions (ResNet-18, AudioEncoder, MobileNetV2 stem) ----------------------------------
+    def dense_conv(self, x, conv, frames=None, need_dx=True):
+        """nn.Conv2d with groups == 1 on a channels-last T2 (or, for a stem, on the raw frames in the caller's
+        layout: frames = (tensor, (is_u8, B, T, H, W, sb, st, sc, sh, sw), scale)) as im2col + GEMM.  Returns the
+        raw output T2 (BatchNorm statistic slot attached).  The backward group is reserved here (its position fixes
+        when it runs) and filled by dense_conv_bwd once the caller knows what accumulates into x.grad."""
+        Cout, Cin = conv.out_channels, conv.in_channels
+        kh, kw = conv.kernel_size
+        st_, pd = conv.stride[0], conv.padding[0]
+        assert conv.groups == 1 and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
+        assert conv.dilation == (1, 1)
+        if frames is not None:
+            ft, (is_u8, B, T, Hs, Ws, sb, stt, sc, sh, sw), scale = frames
+            F = B * T
+            src = (int(is_u8), float(scale), F, T, sb, stt, sc, sh, sw)
+            xptr = ft
+            need_dx = False
+        else:
+            F, Hs, Ws = x.F, x.H, x.W
+            src = (0, 1.0, F, 1, Hs * Ws * Cin, 0, 1, Ws * Cin, Cin)
+            xptr = x.val
+        Ho, Wo = (Hs + 2 * pd - kh) // st_ + 1, (Ws + 2 * pd - kw) // st_ + 1
+        rows = F * Ho * Wo
+        K = Cin * kh * kw
+        pointwise = frames is None and kh == 1 and kw == 1 and st_ == 1 and pd == 0 and Cin % 4 == 0
+        ldk = K if pointwise else (K + 3) // 4 * 4
+        if pointwise:
+            col = xptr
+        else:
+            col = self.alloc(rows * ldk)
+            self.fwd.add("lr_im2col", xptr, *src, Hs, Ws, Cin, kh, kw, st_, pd, 0, Ho, Wo, col, ldk)
+        if ldk != K:
+            wmat = self.alloc(Cout * ldk)
+            wmat.zero_()
+            self.fwd.add("lr_copy2d", wmat, ldk, conv.weight, K, Cout, K)
+        else:
+            wmat = conv.weight
+        y = T2(self, F, Ho, Wo, Cout)
+        y.stat_slot = self.stat_slot(Cout)
+        stt_ = (lambda s=y.stat_slot: s["fwd"]) if self.training else 0
+        self.gemm_auto(self.fwd, col, ldk, 0, wmat, ldk, 0, y.val, Cout, rows, Cout, ldk,
+                       bias=(conv.bias if conv.bias is not None else 0), stats=stt_)
+        if self.with_backward:
+            g = self.bgroup()
+            y._conv_bwd = (g, x, conv, col, ldk, wmat, src, (F, Hs, Ws, Ho, Wo), need_dx and frames is None)
+        return y
+
+    def dense_conv_bwd(self, y, dx_residual=0):
+        """Emit the backward of a dense_conv output y (after everything that writes y.grad has been registered):
+        dW += dy^T col, db += colsum(dy), x.grad = im2col_T(dy) . Wt^T (+ dx_residual)."""
+        g, x, conv, col, ldk, wmat, src, (F, Hs, Ws, Ho, Wo), need_dx = y._conv_bwd
+        Cout, Cin = conv.out_channels, conv.in_channels
+        kh, kw = conv.kernel_size
+        st_, pd = conv.stride[0], conv.padding[0]
+        K = Cin * kh * kw
+        rows = F * Ho * Wo
+        dw = self.flat.g(conv.weight)
+        if ldk != K:
+            dwp = self.alloc(Cout * ldk)
+            g.add("lr_memset", dwp, Cout * ldk * 4, leaf=True)
+            self.gemm_auto(g, y.grad, Cout, 1, col, ldk, 1, dwp, ldk, Cout, ldk, rows, split_ok=True)
+            g.add("lr_copy2d", dw, K, dwp, ldk, Cout, K, leaf=True)
+        else:
+            self.gemm_auto(g, y.grad, Cout, 1, col, ldk, 1, dw, ldk, Cout, ldk, rows, split_ok=True)
+        if conv.bias is not None:
+            g.add("lr_colsum", y.grad, Cout, rows, Cout, self.flat.g(conv.bias), leaf=True)
+        if not need_dx:
+            return
+        rows_in = F * Hs * Ws
+        if kh == 1 and kw == 1 and st_ == 1 and pd == 0:
+            self.gemm_auto(g, y.grad, Cout, 0, conv.weight, Cin, 1, x.grad, Cin, rows_in, Cin, Cout, R=dx_residual, ldr=Cin)
+            return
+        Kt = Cout * kh * kw
+        ldt = (Kt + 3) // 4 * 4
+        wt = self.alloc(Cin * ldt)
+        wt.zero_()
+        g.add("lr_weight_transpose", conv.weight, wt, Cout, Cin, kh * kw, ldt)
+        colT = self.workspace(rows_in * ldt)
+        dsrc = (0, 1.0, F, 1, Ho * Wo * Cout, 0, 1, Wo * Cout, Cout)
+        g.add("lr_im2col", y.grad, *dsrc, Ho, Wo, Cout, kh, kw, st_, pd, 1, Hs, Ws, colT, ldt)
+        self.gemm_auto(g, colT, ldt, 0, wt, ldt, 0, x.grad, Cin, rows_in, Cin, ldt, R=dx_residual, ldr=Cin)
+
+    def maxpool(self, x, k, stride, pad):
+        Ho, Wo = (x.H + 2 * pad - k) // stride + 1, (x.W + 2 * pad - k) // stride + 1
+        y = T2(self, x.F, Ho, Wo, x.C)
+        arg = self.alloc(y.rows * x.C, torch.uint8)
+        self.fwd.add("lr_maxpool_fwd", x.val, y.val, arg, x.F, x.H, x.W, x.C, k, stride, pad)
+        if self.with_backward:
+            self.bgroup().add("lr_maxpool_bwd", y.grad, arg, x.grad, x.F, x.H, x.W, x.C, k, stride, pad)
+        return y
+
+    def dropout(self, x, dx, n, p):
+        """nn.Dropout(p) on a flat buffer of n floats (training plans only; identity otherwise).
+        Returns (y, dy): dy is the buffer the consumer's backward must write."""
+        if not self.training or p <= 0.0:
+            return x, dx
+        if self.rng_step is None:
+            self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            self.bufs.append(self.rng_step)
+        self._n_dropout += 1
+        y, mask = self.alloc(n), self.alloc(n, torch.uint8)
+        self.fwd.add("lr_dropout_fwd", x, y, mask, n, float(p), 0x5EED0000 + self._n_dropout, self.rng_step)
+        dy = None
+        if self.with_backward:
+            dy = self.alloc(n)
+            if dx is not None:
+                self.bgroup().add("lr_dropout_bwd", dy, mask, dx, n, float(p))
+        return y, dy
+
+    # ---- nn.LSTM (batch_first, bidirectional) with an out[:, -1] head -------------------------------------
+    def bilstm_last(self, x, dx, I, B, T, lstm, out, ldo, dout):
+        """x: [B*T, I] features (dx: its gradient buffer, written here).  Writes out[b, 0:2H] (row stride ldo) =
+        lstm(x)[:, -1]: all layers below the top run both directions over the whole sequence; the top layer runs
+        its forward direction over T steps and its reverse direction for ONE step.
+        dout: gradient of that row (same stride), read by the backward."""
+        assert lstm.bidirectional and lstm.batch_first
+        H, L = lstm.hidden_size, lstm.num_layers
+        F, G4 = B * T, 4 * H
+        p_drop = float(lstm.dropout)
+
+        def par(name, layer, rev):
+            return getattr(lstm, f"{name}_l{layer}{'_reverse' if rev else ''}")
+
+        cur, dcur, Icur = x, dx, I
+        for l in range(L - 1):
+            seq = self.alloc(F * 2 * H)
+            dseq = self.alloc(F * 2 * H) if self.with_backward else None
+            saved = []
+            for rev in (0, 1):
+                xp, gates, cst, hp = self.alloc(F * G4), self.alloc(F * G4), self.alloc(F * H), self.alloc(F * H)
+                self.linear(cur, Icur, F, par("weight_ih", l, rev), par("bias_ih", l, rev), xp, G4)
+                self.fwd.add("lr_lstm_fwd", xp, G4, par("bias_hh", l, rev), par("weight_hh", l, rev),
+                             seq.data_ptr() + 4 * H * rev, 2 * H, gates, cst, hp, B, T, H, T, rev)
+                saved.append((gates, cst, hp))
+            if self.with_backward:
+                g = self.bgroup()
+                for rev in (0, 1):
+                    gates, cst, hp = saved[rev]
+                    dg = self.alloc(F * G4)
+                    g.add("lr_lstm_bwd", dseq.data_ptr() + 4 * H * rev, 2 * H, -1, gates, cst, par("weight_hh", l, rev), dg,
+                          B, T, H, T, rev)
+                    self.linear_bwd(g, hp, H, F, par("weight_hh", l, rev), par("bias_hh", l, rev), dg, G4)
+                    self.linear_bwd(g, cur, Icur, F, par("weight_ih", l, rev), par("bias_ih", l, rev), dg, G4,
+                                    dx=dcur, ldx=Icur, dx_residual=(dcur if rev else 0), ldr=Icur)
+            cur, dcur = self.dropout(seq, dseq, F * 2 * H, p_drop)
+            Icur = 2 * H
+        # ---- top layer
+        l = L - 1
+        xp_f, hs_f = self.alloc(F * G4), self.alloc(F * H)
+        gates_f, c_f, hp_f = self.alloc(F * G4), self.alloc(F * H), self.alloc(F * H)
+        self.linear(cur, Icur, F, par("weight_ih", l, 0), par("bias_ih", l, 0), xp_f, G4)
+        self.fwd.add("lr_lstm_fwd", xp_f, G4, par("bias_hh", l, 0), par("weight_hh", l, 0), hs_f, H, gates_f, c_f, hp_f,
+                     B, T, H, T, 0)
+        optr = out if isinstance(out, int) else out.data_ptr()
+        self.fwd.add("lr_copy2d", optr, ldo, hs_f.data_ptr() + 4 * (T - 1) * H, T * H, B, H)
+        xp_r, gates_r, c_r = self.alloc(B * G4), self.alloc(B * G4), self.alloc(B * H)
+        cur_last = (cur if isinstance(cur, int) else cur.data_ptr()) + 4 * (T - 1) * Icur
+        self.linear(cur_last, T * Icur, B, par("weight_ih", l, 1), par("bias_ih", l, 1), xp_r, G4)
+        self.fwd.add("lr_lstm_fwd", xp_r, G4, par("bias_hh", l, 1), par("weight_hh", l, 1), optr + 4 * H, ldo, gates_r, c_r, 0,
+                     B, 1, H, 1, 1)
+        if self.with_backward:
+            dptr = dout if isinstance(dout, int) else dout.data_ptr()
+            dg_f, dg_r = self.alloc(F * G4), self.alloc(B * G4)
+            g = self.bgroup()
+            g.add("lr_lstm_bwd", dptr, ldo, T - 1, gates_f, c_f, par("weight_hh", l, 0), dg_f, B, T, H, T, 0)
+            self.linear_bwd(g, hp_f, H, F, par("weight_hh", l, 0), par("bias_hh", l, 0), dg_f, G4)
+            self.linear_bwd(g, cur, Icur, F, par("weight_ih", l, 0), par("bias_ih", l, 0), dg_f, G4, dx=dcur, ldx=Icur)
+            # reverse direction: one step from the zero state (W_hh_reverse gets no gradient)
+            g.add("lr_lstm_bwd", dptr + 4 * H, ldo, 0, gates_r, c_r, par("weight_hh", l, 1), dg_r, B, 1, H, 1, 1)
+            g.add("lr_colsum", dg_r, G4, B, G4, self.flat.g(par("bias_hh", l, 1)), leaf=True)
+            dcur_last = (dcur if isinstance(dcur, int) else dcur.data_ptr()) + 4 * (T - 1) * Icur
+            self.linear_bwd(g, cur_last, T * Icur, B, par("weight_ih", l, 1), par("bias_ih", l, 1), dg_r, G4,
+                            dx=dcur_last, ldx=T * Icur, dx_residual=dcur_last, ldr=T * Icur)
+
+    # ---- torchvision ResNet (BasicBlock) -------------------------------------------------------------------
+    def resnet_features(self, net, frames, need_input_grad=False):
+        """torchvision resnet18/34 children()[:-2] (conv1, bn1, relu, maxpool, layer1..4) on frames given as
+        (tensor, layout, scale) -> last activation T2.  video/models/resnet_lstm.py:90-93,
+        audio/models/resnet_model.py:12-17."""
+        raw = self.dense_conv(None, net.conv1, frames=frames)
+        if self.with_backward:
+            self.dense_conv_bwd(raw)
+        a = T2(self, raw.F, raw.H, raw.W, raw.C)
+        self.bn_act(raw, net.bn1, ACT_RELU, a)
+        mp = net.maxpool
+        k = mp.kernel_size if isinstance(mp.kernel_size, int) else mp.kernel_size[0]
+        s_ = mp.stride if isinstance(mp.stride, int) else mp.stride[0]
+        p_ = mp.padding if isinstance(mp.padding, int) else mp.padding[0]
+        cur = self.maxpool(a, k, s_, p_)
+        for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
+            for blk in layer:
+                cur = self.basic_block(blk, cur)
+        return cur
+
+    def basic_block(self, blk, x):
+        """torchvision BasicBlock: relu(bn2(conv2(relu(bn1(conv1(x))))) + identity), identity = x or
+        bn_d(conv_d(x)) when the shape changes."""
+        if type(blk).__name__ != "BasicBlock":
+            raise NotImplementedError(f"{type(blk).__name__} blocks (resnet50) have no lipread_b200 plan yet")
+        ident, dmask = x, None
+        ds_raw = None
+        # Backward groups run in reverse registration order: bn2, conv2, bn1, conv1, [bn_d, conv_d].  conv1 writes
+        # x.grad (plus the identity gradient when there is no downsample); conv_d then accumulates onto it.
+        if blk.downsample is not None:
+            dconv, dbn = blk.downsample[0], blk.downsample[1]
+            ds_raw = self.dense_conv(x, dconv)
+            ident = T2(self, ds_raw.F, ds_raw.H, ds_raw.W, ds_raw.C)
+            self.bn_act(ds_raw, dbn, ACT_NONE, ident)
+        raw1 = self.dense_conv(x, blk.conv1)
+        h1 = T2(self, raw1.F, raw1.H, raw1.W, raw1.C)
+        self.bn_act(raw1, blk.bn1, ACT_RELU, h1)
+        raw2 = self.dense_conv(h1, blk.conv2)
+        out = T2(self, raw2.F, raw2.H, raw2.W, raw2.C)
+        if self.with_backward:
+            dmask = ident.grad if ds_raw is not None else self.alloc(out.rows * out.C)
+        self.bn_act(raw2, blk.bn2, ACT_RELU, out, residual=ident, res_pre=True, dres=dmask)
+        if self.with_backward:
+            self.dense_conv_bwd(raw2)
+            self.dense_conv_bwd(raw1, dx_residual=(0 if ds_raw is not None else dmask))
+            if ds_raw is not None:
+                self.dense_conv_bwd(ds_raw, dx_residual=x.grad)
+        return out

@@ -3,7 +3,7 @@ tensors (torch is used for device memory and the current stream only), passes ra
 liblipread_b200.so and returns nothing: outputs are caller-allocated, as the ABI requires."""
 import torch
 
-from ._lib import lib, check, ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_HSIGMOID  # noqa: F401
+from ._lib import lib, check, ACT_NONE, ACT_RELU, ACT_HSWISH, ACT_HSIGMOID, ACT_RELU6  # noqa: F401
 
 
 def _p(t):
@@ -75,15 +75,50 @@ def dwconv_wgrad(dy, x, dw, F, H, W, C, k, stride):
     check(lib.lr_dwconv_wgrad(_p(dy), _p(x), _p(dw), F, H, W, C, k, stride, _s()))
 
 
-def bn_act_fwd(x, stats, bn, act, training, z, rows, C, residual=None):
+def bn_act_fwd(x, stats, bn, act, training, z, rows, C, residual=None, res_pre=False):
     check(lib.lr_bn_act_fwd(_p(x), _p(stats), _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var),
-                            _p(bn.num_batches_tracked), bn.eps, bn.momentum, act, int(training), _p(residual), _p(z),
-                            rows, C, _s()))
+                            _p(bn.num_batches_tracked), bn.eps, bn.momentum, act, int(training), _p(residual),
+                            int(res_pre), _p(z), rows, C, _s()))
 
 
-def bn_act_bwd(x, stats, bn, act, training, dz, sums, dx, dgamma, dbeta, rows, C):
+def bn_act_bwd(x, stats, bn, act, training, dz, sums, dx, dgamma, dbeta, rows, C, z_out=None, dres=None):
     check(lib.lr_bn_act_bwd(_p(x), _p(stats), _p(bn.weight), _p(bn.bias), _p(bn.running_mean), _p(bn.running_var),
-                            bn.eps, act, int(training), _p(dz), _p(sums), _p(dx), _p(dgamma), _p(dbeta), rows, C, _s()))
+                            bn.eps, act, int(training), _p(dz), _p(z_out), _p(dres), _p(sums), _p(dx), _p(dgamma),
+                            _p(dbeta), rows, C, _s()))
+
+
+def nhwc_layout(F, H, W, C):
+    """(is_u8, scale, F, T, sb, st, sc, sh, sw) of a channels-last float activation [F,H,W,C] for lr_im2col."""
+    return (0, 1.0, F, 1, H * W * C, 0, 1, W * C, C)
+
+
+def im2col(x, src, Hs, Ws, C, kh, kw, stride, pad, transposed, Hd, Wd, col, ldk):
+    """src = (is_u8, scale, F, T, sb, st, sc, sh, sw)."""
+    check(lib.lr_im2col(_p(x), *src, Hs, Ws, C, kh, kw, stride, pad, int(transposed), Hd, Wd, _p(col), ldk, _s()))
+
+
+def weight_transpose(w, wt, Cout, Cin, kk, ldt):
+    check(lib.lr_weight_transpose(_p(w), _p(wt), Cout, Cin, kk, ldt, _s()))
+
+
+def maxpool_fwd(x, y, arg, F, H, W, C, k, stride, pad):
+    check(lib.lr_maxpool_fwd(_p(x), _p(y), _p(arg), F, H, W, C, k, stride, pad, _s()))
+
+
+def maxpool_bwd(dy, arg, dx, F, H, W, C, k, stride, pad):
+    check(lib.lr_maxpool_bwd(_p(dy), _p(arg), _p(dx), F, H, W, C, k, stride, pad, _s()))
+
+
+def dropout_fwd(x, y, mask, n, p, seed, step):
+    check(lib.lr_dropout_fwd(_p(x), _p(y), _p(mask), n, p, seed, _p(step), _s()))
+
+
+def dropout_bwd(dy, mask, dx, n, p):
+    check(lib.lr_dropout_bwd(_p(dy), _p(mask), _p(dx), n, p, _s()))
+
+
+def rng_tick(step):
+    check(lib.lr_rng_tick(_p(step), _s()))
 
 
 def frame_reduce(a, g, p, F, HW, C, mode):

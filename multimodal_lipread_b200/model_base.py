@@ -1,0 +1,382 @@
+"""Shared plumbing of every lipread_b200 model: flat parameters, launch plans keyed by input shape, the autograd
+bridge behind the reference's `model(*inputs) -> logits` call, and the fused train step
+(zero_grad -> forward -> CrossEntropyLoss -> backward -> [allreduce] -> Adam: audio_video/train.py:61-67,
+video/train.py:93-104, audio/train.py:67-78, audio_cues_video/train.py:60-72) replayed as a CUDA graph.
+
+A concrete model keeps the reference's sub-modules as parameter containers (so seeded initialisation and
+`state_dict` keys are interchangeable with the reference) and provides a plan class whose constructor writes the
+launch lists.  The torch forward() of the sub-modules is never called; there is no CPU path."""
+import torch
+import torch.nn as nn
+
+from . import _lib, engine
+from ._lib import lib
+
+N_MELS, N_FRAMES_OUT, N_SAMPLES = 80, 117, 20000
+
+
+class Cfg:
+    """Stand-in for the reference's Config objects: anything with .get("dotted.key", default)."""
+
+    def __init__(self, values=None):
+        self.values = values or {}
+
+    def get(self, key, default=None):
+        if key in self.values:
+            return self.values[key]
+        cur = self.values
+        for part in key.split("."):
+            if not isinstance(cur, dict) or part not in cur:
+                return default
+            cur = cur[part]
+        return cur
+
+
+def video_layout(video):
+    """(kind, B, T, H, W, sb, st, sc, sh, sw), scale of lip frames in the caller's own layout:
+    uint8 (B,T,H,W,3) as the .npy files hold them (video/data_utils/dataset_loader.py:87-96) or float32
+    (B,3,T,H,W) as the reference's forward() receives them."""
+    if video.dtype == torch.uint8:
+        if video.dim() != 5 or video.shape[-1] != 3:
+            raise ValueError(f"uint8 lip frames must be (B, T, H, W, 3), got {tuple(video.shape)}")
+        B, T, H, W, _ = video.shape
+        sb, st, sh, sw, sc = video.stride()
+        return (1, B, T, H, W, sb, st, sc, sh, sw), 1.0 / 255.0
+    if video.dtype != torch.float32:
+        raise ValueError(f"lip frames must be uint8 (B,T,H,W,3) or float32 (B,3,T,H,W), got {video.dtype}")
+    if video.dim() != 5 or video.shape[1] != 3:
+        raise ValueError(f"float lip frames must be (B, 3, T, H, W), got {tuple(video.shape)}")
+    B, _, T, H, W = video.shape
+    sb, sc, st, sh, sw = video.stride()
+    return (0, B, T, H, W, sb, st, sc, sh, sw), 1.0
+
+
+class ModelPlan(engine.Plan):
+    """Launch plan of one model at one input shape.  Sub-classes write the launch lists in build()."""
+
+    def __init__(self, model, flat, spec, device, training, with_backward):
+        super().__init__(flat, device, training, with_backward, precision=model.precision)
+        self.model, self.spec = model, spec
+        self.B = spec["B"]
+        self.num_classes = model.num_classes
+        self.inputs = {}                               # name -> static device tensor the caller copies into
+        self.build(model, spec)
+        self._finish()
+
+    # -- static inputs ------------------------------------------------------------------------------------
+    def video_input(self):
+        kind, B, T, H, W = self.spec["video"]
+        if kind == 1:
+            v = torch.empty(B, T, H, W, 3, dtype=torch.uint8, device=self.dev)
+        else:
+            v = torch.empty(B, 3, T, H, W, dtype=torch.float32, device=self.dev)
+        self.inputs["video"] = v
+        self.bufs.append(v)
+        layout, scale = video_layout(v)
+        return v, layout, scale
+
+    def audio_input(self):
+        """(B,80,117) log-mel buffer; when the plan takes raw waveforms the log-mel kernel fills it first."""
+        B = self.B
+        mel = torch.empty(B, N_MELS, N_FRAMES_OUT, dtype=torch.float32, device=self.dev)
+        self.bufs.append(mel)
+        self.mel = mel
+        if self.spec.get("from_wav"):
+            wav = torch.empty(B, N_SAMPLES, dtype=torch.float32, device=self.dev)
+            self.bufs.append(wav)
+            self.inputs["audio"] = wav
+            self.fwd.add("lr_logmel_fwd", wav, self.model.logmel_plan(self.dev), mel, B, N_FRAMES_OUT, 0)
+        else:
+            self.inputs["audio"] = mel
+        return mel
+
+    def vector_input(self, name, dim):
+        v = torch.empty(self.B, dim, dtype=torch.float32, device=self.dev)
+        self.inputs[name] = v
+        self.bufs.append(v)
+        return v
+
+    # -- head --------------------------------------------------------------------------------------------
+    def mlp(self, x, dx, B, layers):
+        """nn.Sequential of Linear / ReLU / Dropout on a [B, D] buffer -> (out, dout) of the last Linear."""
+        cur, dcur, dim = x, dx, None
+        mods = list(layers)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Linear):
+                act = engine.ACT_NONE
+                if i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
+                    act = engine.ACT_RELU
+                    i += 1
+                out = self.alloc(B * m.out_features)
+                dout = self.alloc(B * m.out_features) if self.with_backward else None
+                self.linear(cur, m.in_features, B, m.weight, m.bias, out, m.out_features, act=act)
+                if self.with_backward:
+                    g = self.bgroup()
+                    if act != engine.ACT_NONE:
+                        g.add("lr_act_bwd", dout, out, B * m.out_features, act)
+                    self.linear_bwd(g, cur, m.in_features, B, m.weight, m.bias, dout, m.out_features,
+                                    dx=dcur, ldx=m.in_features)
+                cur, dcur, dim = out, dout, m.out_features
+            elif isinstance(m, nn.Dropout):
+                if dim is None:
+                    raise NotImplementedError("Dropout before the first Linear of a head")
+                cur, dcur = self.dropout(cur, dcur, B * dim, m.p)
+            elif isinstance(m, (nn.Identity,)):
+                pass
+            else:
+                raise NotImplementedError(f"{type(m).__name__} in a classifier head")
+            i += 1
+        return cur, dcur
+
+    def linear_bn_act(self, x, dx, B, fc, bn, act):
+        """nn.Linear -> nn.BatchNorm1d -> activation on a [B, K] buffer: the GEMM epilogue emits the batch statistics,
+        one lr_bn_act pass applies them.  Returns (value, gradient) buffers of the activation output."""
+        D, K = fc.out_features, fc.in_features
+        raw = engine.T2(self, B, 1, 1, D)
+        raw.stat_slot = self.stat_slot(D)
+        st = (lambda s=raw.stat_slot: s["fwd"]) if self.training else 0
+        self.gemm_auto(self.fwd, x, K, 0, fc.weight, K, 0, raw.val, D, B, D, K, bias=(fc.bias if fc.bias is not None else 0),
+                       stats=st)
+        if self.with_backward:
+            self.linear_bwd(self.bgroup(), x, K, B, fc.weight, fc.bias, raw.grad, D, dx=dx, ldx=K)
+        h = engine.T2(self, B, 1, 1, D)
+        self.bn_act(raw, bn, act, h)
+        return h.val, h.grad
+
+    def set_logits(self, logits, dlogits):
+        self.logits = logits.view(self.B, self.num_classes)
+        self.dlogits = dlogits.view(self.B, self.num_classes) if dlogits is not None else None
+
+    def _finish(self):
+        B, C = self.B, self.num_classes
+        self.labels = torch.zeros(B, dtype=torch.int64, device=self.dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.correct = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.bufs += [self.labels, self.loss, self.correct]
+        self.finalize()
+        # per-step zeroing: BN statistic arena and (for the backward) the flat gradient
+        self.pre = engine.OpList()
+        self.pre.add("lr_memset", self.stats, self.stats.numel() * 8)
+        if self.rng_step is not None:
+            self.pre.add("lr_rng_tick", self.rng_step)
+        self.pre_bwd = engine.OpList()
+        if self.with_backward:
+            self.pre_bwd.add("lr_memset", self.flat.grad, self.flat.grad.numel() * 4)
+        self.ce = engine.OpList()
+        self.ce.add("lr_memset", self.loss, 4)
+        self.ce.add("lr_memset", self.correct, 4)
+        self.ce.add("lr_ce_loss", self.logits, self.labels, self.loss, self.dlogits if self.with_backward else 0,
+                    self.correct, B, C, 1.0 / B)
+
+    # -- execution ---------------------------------------------------------------------------------------
+    def run_forward(self, stream):
+        self.pre.run(stream)
+        self.fwd.run(stream)
+
+    def run_backward(self, stream, forked=None):
+        """forked = (main, side) torch streams: weight-gradient kernels run on `side` concurrently with the
+        dgrad chain (used under CUDA-graph capture, where it becomes a parallel branch of the graph)."""
+        self.pre_bwd.run(stream)
+        if forked is None:
+            self.bwd.run(stream)
+        else:
+            self.bwd.run_forked(*forked)
+
+    def n_launches(self):
+        return len(self.fwd) + len(self.bwd) + 1
+
+
+class _PlanFn(torch.autograd.Function):
+    """autograd bridge for the drop-in `model(*inputs)` -> logits call: the backward runs the plan's
+    hand-written backward schedule and hands the parameter gradients to autograd."""
+
+    @staticmethod
+    def forward(ctx, model, need_backward, n_in, *args):
+        inputs, _params = args[:n_in], args[n_in:]
+        named = dict(zip(model.INPUTS, inputs))
+        plan = model._plan_for(named, training=model.training, with_backward=need_backward)
+        for name, t in named.items():
+            buf = plan.inputs[name]
+            buf.copy_(t.reshape(buf.shape))
+        plan.run_forward(torch.cuda.current_stream().cuda_stream)
+        ctx.plan, ctx.model, ctx.n_in = plan, model, n_in
+        return plan.logits.clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        plan, model = ctx.plan, ctx.model
+        if not plan.with_backward:
+            raise RuntimeError("forward ran without gradient buffers (torch.no_grad)")
+        plan.dlogits.copy_(dlogits)
+        plan.run_backward(torch.cuda.current_stream().cuda_stream)
+        flat = model._flat
+        return (None, None, None) + (None,) * ctx.n_in + tuple(flat.g(p).clone() for p in flat.params)
+
+
+class PlanModel(nn.Module):
+    """Base class: sub-classes set INPUTS (forward argument names, in order), PLAN (a ModelPlan sub-class) and
+    build the reference's sub-modules in __init__ (after calling _init_base)."""
+
+    INPUTS = ("audio", "video")
+    PLAN = None
+    DEFAULT_LR = 3e-4
+    DEFAULT_WD = 0.0
+
+    def _init_base(self, num_classes, config, precision):
+        self.num_classes = num_classes
+        # "tf32": GEMM-shaped work on the tensor cores (tcgen05, TF32 products, fp32 accumulate; >= the bf16 the
+        # north star allows); "fp32": every kernel in fp32 SIMT arithmetic (strict parity with the reference)
+        self.precision = precision or config.get("precision.compute", "tf32")
+        self._flat = None
+        self._plans = {}
+        self._logmel = {}
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def _ensure_flat(self, device):
+        if self._flat is None or not self._flat.intact() or self._flat.device != torch.device(device):
+            old = self._flat
+            self._flat = engine.FlatParams(self, device)
+            for b in self.buffers():
+                if b.device != self._flat.device:
+                    b.data = b.data.to(self._flat.device)
+            self._plans.clear()
+            self._graphs.clear()
+            if old is not None and old.m is not None and old.numel == self._flat.numel and old.device == self._flat.device:
+                self._flat.m, self._flat.v, self._flat.adam_state = old.m, old.v, old.adam_state
+        return self._flat
+
+    def logmel_plan(self, device):
+        from .audio_processor import AudioProcessor
+        key = str(device)
+        if key not in self._logmel:
+            self._logmel[key] = AudioProcessor(device=device)
+        return self._logmel[key].plan
+
+    def _spec_of(self, named):
+        """Hashable description of the input shapes (the plan key)."""
+        spec = {}
+        dev = None
+        for name, t in named.items():
+            if t.device.type != "cuda":
+                raise _lib.LipreadError("multimodal_lipread_b200 models run on CUDA tensors only (no CPU path)")
+            dev = t.device if dev is None else dev
+            if t.device != dev:
+                raise _lib.LipreadError("all inputs must live on the same CUDA device")
+            if name == "video":
+                layout, _ = video_layout(t)
+                spec["video"] = layout[:5]
+                spec["B"] = layout[1]
+            elif name == "audio":
+                spec["from_wav"] = t.dim() == 2 and t.shape[1] == N_SAMPLES
+                if not spec["from_wav"] and t.numel() != t.shape[0] * N_MELS * N_FRAMES_OUT:
+                    raise ValueError(f"audio must be (B,80,117) log-mel or (B,20000) waveform, got {tuple(t.shape)}")
+                spec.setdefault("B", t.shape[0])
+            else:
+                spec[name] = tuple(t.shape[1:])
+                spec.setdefault("B", t.shape[0])
+        return spec, dev
+
+    def _plan_for(self, named, training, with_backward):
+        spec, dev = self._spec_of(named)
+        flat = self._ensure_flat(dev)
+        key = (tuple(sorted((k, v) for k, v in spec.items())), bool(training), bool(with_backward), self.precision)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self.PLAN(self, flat, spec, dev, training, with_backward)
+            self._plans[key] = plan
+        return plan
+
+    # ------------------------------------------------------------------ reference surface
+    def forward(self, *inputs):
+        if len(inputs) != len(self.INPUTS):
+            raise TypeError(f"{type(self).__name__}.forward takes {self.INPUTS}, got {len(inputs)} tensors")
+        for t in inputs:
+            if t.device.type != "cuda":
+                raise _lib.LipreadError("multimodal_lipread_b200 models run on CUDA tensors only (no CPU path)")
+        flat = self._ensure_flat(inputs[0].device)
+        return _PlanFn.apply(self, torch.is_grad_enabled(), len(inputs), *inputs, *flat.params)
+
+    # ------------------------------------------------------------------ fused training step
+    def configure_optimizer(self, lr=None, betas=(0.9, 0.999), eps=1e-8, weight_decay=None):
+        """torch.optim.Adam as the reference's train scripts build it; state lives next to the flat parameters."""
+        lr = self.DEFAULT_LR if lr is None else lr
+        weight_decay = self.DEFAULT_WD if weight_decay is None else weight_decay
+        self._opt = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        if self._flat is not None:
+            self._flat.init_adam(lr)
+
+    def train_step(self, *inputs_and_labels, grad_allreduce=None, world=1, use_graph=True):
+        """One training iteration entirely in lipread_b200 kernels:
+        [log-mel if the audio input is a raw (B,20000) waveform] -> forward -> CE -> backward -> [allreduce] -> Adam.
+        Call as train_step(*inputs, labels).  Returns (loss, logits) device tensors owned by the plan (no host sync)."""
+        if not hasattr(self, "_opt"):
+            self.configure_optimizer()
+        *inputs, labels = inputs_and_labels
+        named = dict(zip(self.INPUTS, inputs))
+        plan = self._plan_for(named, training=True, with_backward=True)
+        flat = self._flat
+        if flat.m is None:
+            flat.init_adam(self._opt["lr"])
+        for name, t in named.items():
+            buf = plan.inputs[name]
+            buf.copy_(t.reshape(buf.shape), non_blocking=True)
+        plan.labels.copy_(labels, non_blocking=True)
+        o = self._opt
+
+        def compute(stream, forked=None):
+            plan.run_forward(stream)
+            plan.ce.run(stream)
+            plan.run_backward(stream, forked)
+
+        def update(stream):
+            _lib.check(lib.lr_adam_step(flat.flat.data_ptr(), flat.grad.data_ptr(), flat.m.data_ptr(), flat.v.data_ptr(),
+                                        flat.adam_state.data_ptr(), flat.numel, o["betas"][0], o["betas"][1], o["eps"],
+                                        o["weight_decay"], 1.0 / world, stream))
+
+        if not use_graph or not getattr(plan, "warm", False):
+            # eager launches; the first step of every plan runs this way, which also serves as the warm-up
+            # (function attributes, lazy module loading) that must happen outside graph capture
+            s = torch.cuda.current_stream().cuda_stream
+            n0 = _lib.launch_count()
+            compute(s)
+            if grad_allreduce is not None:
+                grad_allreduce(flat.grad)
+            update(s)
+            plan.warm = True
+            plan.kernel_launches = _lib.launch_count() - n0
+            return plan.loss, plan.logits
+        gkey = (id(plan), grad_allreduce is not None)
+        graphs = self._graphs.get(gkey)
+        if graphs is None:
+            graphs = self._capture(compute, update, split=grad_allreduce is not None)
+            self._graphs[gkey] = graphs
+        graphs[0].replay()
+        if grad_allreduce is not None:
+            grad_allreduce(flat.grad)
+            graphs[1].replay()
+        return plan.loss, plan.logits
+
+    def _capture(self, compute, update, split):
+        """CUDA-graph capture of the step (one graph, or compute / update split around the NCCL allreduce)."""
+        torch.cuda.synchronize()
+        g0 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g0):
+            main = torch.cuda.current_stream()
+            if not hasattr(self, "_side"):
+                self._side = torch.cuda.Stream()
+            compute(main.cuda_stream, forked=(main, self._side))
+            if not split:
+                update(main.cuda_stream)
+        if not split:
+            return (g0,)
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            update(torch.cuda.current_stream().cuda_stream)
+        return (g0, g1)
+
+    def launches_per_step(self):
+        """Kernels of this library launched by one train_step (counted by the library during the eager step)."""
+        return max((getattr(p, "kernel_launches", 0) for p in self._plans.values()), default=0)

@@ -1,0 +1,94 @@
+"""Video-only lip readers behind the reference's nn.Module surface (video/models/*.py).
+
+  ResNet2DBiLSTM / create_model      video/models/resnet_lstm.py:56-177   (model.name == "resnet_lstm")
+
+Sub-modules are parameter containers only (same names, construction order and `state_dict` keys as the reference,
+including the CNN appearing twice -- `cnn_features.*` and `time_distributed_cnn.module.0.*` share tensors);
+arithmetic runs through the launch plans of engine.py."""
+import types
+
+import torch.nn as nn
+from torchvision.models import resnet18, resnet34
+
+from ._lib import ACT_RELU
+from .model_base import Cfg, ModelPlan, PlanModel
+
+
+class TimeDistributed(nn.Module):
+    """Parameter container mirroring video/models/resnet_lstm.py:15-53 (its reshape is folded into the stem's addressing)."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+
+def _resnet_view(seq):
+    """children()[:-2] Sequential -> object with the attribute names Plan.resnet_features expects."""
+    return types.SimpleNamespace(conv1=seq[0], bn1=seq[1], maxpool=seq[3], layer1=seq[4], layer2=seq[5],
+                                 layer3=seq[6], layer4=seq[7])
+
+
+class ResNetLstmPlan(ModelPlan):
+    def build(self, m, spec):
+        B, wb = self.B, self.with_backward
+        video, layout, scale = self.video_input()
+        T = layout[2]
+        last = self.resnet_features(_resnet_view(m.cnn_features), (video, layout, scale))
+        feat, dfeat = self.avgpool(last)
+        D = 2 * m.bilstm.hidden_size
+        seq_last = self.alloc(B * D)
+        h = self.alloc(B * D)
+        dh = self.alloc(B * D) if wb else None
+        # dh is turned into the gradient of x[:, -1] in place by the ReLU backward below, which runs first
+        self.bilstm_last(feat, dfeat, last.C, B, T, m.bilstm, seq_last, D, dh if wb else 0)
+        # x[:, -1] -> ReLU -> Dropout -> fc   (resnet_lstm.py:151-154)
+        self.fwd.add("lr_act_fwd", seq_last, h, B * D, ACT_RELU)
+        if wb:
+            self.bgroup().add("lr_act_bwd", dh, h, B * D, ACT_RELU)
+        p = m.dropout.p if isinstance(m.dropout, nn.Dropout) else 0.0
+        hd, dhd = self.dropout(h, dh, B * D, p)
+        logits = self.alloc(B * self.num_classes)
+        dlogits = self.alloc(B * self.num_classes) if wb else None
+        self.linear(hd, D, B, m.fc.weight, m.fc.bias, logits, self.num_classes)
+        if wb:
+            self.linear_bwd(self.bgroup(), hd, D, B, m.fc.weight, m.fc.bias, dlogits, self.num_classes, dx=dhd, ldx=D)
+        self.set_logits(logits, dlogits)
+
+
+class ResNet2DBiLSTM(PlanModel):
+    """video/models/resnet_lstm.py:56-156.  forward(x (B,3,T,H,W) f32 [or uint8 (B,T,H,W,3)]) -> (B, num_classes)."""
+    INPUTS = ("video",)
+    PLAN = ResNetLstmPlan
+    DEFAULT_LR = 5e-5            # video/config/visual_config.yaml:25
+    DEFAULT_WD = 1e-5            # video/train.py:210
+
+    def __init__(self, num_classes, config=None, pretrained_state_dict=None, precision=None):
+        super().__init__()
+        config = config or Cfg()
+        self._init_base(num_classes, config, precision)
+        resnet_version = config.get("model.resnet_version", 18)
+        feature_dim = config.get("model.feature_dim", 1024)
+        dropout = config.get("model.dropout", 0.5)
+        if resnet_version == 18:
+            base = resnet18(weights=None)
+        elif resnet_version == 34:
+            base = resnet34(weights=None)
+        else:
+            raise ValueError(f"Unsupported ResNet version: {resnet_version}")
+        if pretrained_state_dict is not None:
+            base.load_state_dict(pretrained_state_dict)
+        base.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)      # re-initialised (:90)
+        self.cnn_features = nn.Sequential(*list(base.children())[:-2])
+        self.global_pool = nn.AdaptiveAvgPool2d((1, 1))
+        cnn_output_dim = 512
+        self.time_distributed_cnn = TimeDistributed(nn.Sequential(self.cnn_features, self.global_pool, nn.Flatten()))
+        self.bilstm = nn.LSTM(input_size=cnn_output_dim, hidden_size=feature_dim // 2, num_layers=2, bidirectional=True,
+                              batch_first=True, dropout=dropout if dropout > 0 else 0)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout) if dropout > 0 else nn.Identity()
+        self.fc = nn.Linear(feature_dim, num_classes)
+
+
+def create_model(num_classes, config=None):
+    """video/models/resnet_lstm.py:165-177."""
+    return ResNet2DBiLSTM(num_classes, config)

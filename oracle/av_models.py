@@ -9,13 +9,17 @@ there is no network for the ImageNet checkpoint:
 
   MidFusionFastOracle      audio_video/models/middle_fusion_fast.py:5-39
   EarlyFusionMobileNetOracle  audio_video/models/early_fusion.py:14-110  (dropout p passed in)
+  EarlyFusionResNetOracle     audio_video/models/ef_cnn_lstm_resnet.py:14-127
+  ResNet2DBiLSTMOracle        video/models/resnet_lstm.py:56-156
+  AudioResNetOracle           audio/models/resnet_model.py:5-39
+  LateFusionMobileOracle      audio_cues_video/models/late_fusion_mobile.py:6-107
 
 ``tests/golden/make_golden.py`` imports the *real* reference modules in the build container and
 records their outputs; ``tests/test_oracle_golden.py`` pins these restatements to them.
 """
 import torch
 import torch.nn as nn
-from torchvision.models import mobilenet_v3_small
+from torchvision.models import mobilenet_v2, mobilenet_v3_small, resnet18
 
 
 class DictConfig:
@@ -111,6 +115,154 @@ class EarlyFusionMobileNetOracle(nn.Module):
         a = self.audio_encoder(audio.unsqueeze(1))
         v = self.video_encoder(video)
         return self.classifier(torch.cat([a, v], dim=1))
+
+
+class EarlyFusionResNetOracle(EarlyFusionMobileNetOracle):
+    """ef_cnn_lstm_resnet.py:14-127: the same composition with a ResNet-18 video trunk (fc = Identity)."""
+
+    class _Video(nn.Module):
+        def __init__(self, config, dropout):
+            super().__init__()
+            hid = config.get("video.lstm_hidden", 256)
+            base = resnet18(weights=None)
+            base.fc = nn.Identity()
+            self.cnn = base
+            self.lstm = nn.LSTM(512, hid, 2, batch_first=True, bidirectional=True, dropout=dropout)
+            self.output_dim = 2 * hid
+
+        def forward(self, x):
+            frames, b, t = _frames(x)
+            seq, _ = self.lstm(self.cnn(frames).view(b, t, -1))
+            return seq[:, -1]
+
+
+class _TimeDistributed(nn.Module):
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, x):
+        frames, b, t = _frames(x)
+        return self.module(frames).view(b, t, -1)
+
+
+class ResNet2DBiLSTMOracle(nn.Module):
+    """video/models/resnet_lstm.py:56-156 (resnet_version 18): conv1 re-initialised, CNN registered twice
+    (cnn_features / time_distributed_cnn.module.0), 2-layer BiLSTM(512, feature_dim/2), x[:, -1] -> ReLU -> Dropout -> fc."""
+
+    def __init__(self, num_classes, config=None):
+        super().__init__()
+        config = config or DictConfig()
+        feature_dim = config.get("model.feature_dim", 1024)
+        dropout = config.get("model.dropout", 0.5)
+        base = resnet18(weights=None)
+        base.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.cnn_features = nn.Sequential(*list(base.children())[:-2])
+        self.global_pool = nn.AdaptiveAvgPool2d((1, 1))
+        self.time_distributed_cnn = _TimeDistributed(nn.Sequential(self.cnn_features, self.global_pool, nn.Flatten()))
+        self.bilstm = nn.LSTM(512, feature_dim // 2, num_layers=2, bidirectional=True, batch_first=True,
+                              dropout=dropout if dropout > 0 else 0)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout) if dropout > 0 else nn.Identity()
+        self.fc = nn.Linear(feature_dim, num_classes)
+
+    def forward(self, x):
+        x, _ = self.bilstm(self.time_distributed_cnn(x))
+        return self.fc(self.dropout(self.relu(x[:, -1, :])))
+
+
+class AudioResNetOracle(nn.Module):
+    """audio/models/resnet_model.py:5-39: resnet18 with a 1-channel conv1 and fc = Linear-BN1d-ReLU-Dropout-Linear."""
+
+    def __init__(self, num_classes=40, dropout_rate=0.5, use_batchnorm=True):
+        super().__init__()
+        self.use_bn = use_batchnorm
+        self.resnet = resnet18(weights=None)
+        self.resnet.conv1 = nn.Conv2d(1, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        layers = [nn.Linear(self.resnet.fc.in_features, 512)]
+        if use_batchnorm:
+            layers.append(nn.BatchNorm1d(512))
+        layers.extend([nn.ReLU(), nn.Dropout(dropout_rate), nn.Linear(512, num_classes)])
+        self.resnet.fc = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.resnet(x.unsqueeze(1))
+
+
+class LateFusionMobileOracle(nn.Module):
+    """audio_cues_video/models/late_fusion_mobile.py:84-107 (pretrained=False): ResNet-18 audio encoder, cue MLP with
+    BatchNorm1d, MobileNetV2 + 2-layer BiLSTM video encoder, per-modality classifiers, attention fusion of the logits."""
+
+    class _Attn(nn.Module):
+        def __init__(self, dim):
+            super().__init__()
+            self.attn = nn.Sequential(nn.Linear(dim, dim // 2), nn.ReLU(), nn.Linear(dim // 2, 1))
+
+        def forward(self, feats):
+            stacked = torch.stack(feats, dim=1)
+            weights = torch.softmax(self.attn(stacked).squeeze(-1), dim=1)
+            return (stacked * weights.unsqueeze(-1)).sum(dim=1), weights
+
+    class _Video(nn.Module):
+        def __init__(self, feature_dim, dropout):
+            super().__init__()
+            base = mobilenet_v2(weights=None)
+            base.classifier = nn.Identity()
+            self.cnn = nn.Sequential(base.features, nn.AdaptiveAvgPool2d(1), nn.Flatten())
+            self.td = _TimeDistributed(self.cnn)
+            self.lstm = nn.LSTM(1280, feature_dim // 2, num_layers=2, bidirectional=True, batch_first=True, dropout=dropout)
+            self.output_dim = feature_dim
+
+        def forward(self, x):
+            x, _ = self.lstm(self.td(x))
+            return x[:, -1, :]
+
+    class _Audio(nn.Module):
+        def __init__(self):
+            super().__init__()
+            net = resnet18(weights=None)
+            net.conv1 = nn.Conv2d(1, 64, 7, 2, 3, bias=False)
+            net.fc = nn.Identity()
+            self.enc = net
+
+        def forward(self, x):
+            return self.enc(x.unsqueeze(1))
+
+    class _Cue(nn.Module):
+        def __init__(self, input_dim):
+            super().__init__()
+            self.net = nn.Sequential(nn.Linear(input_dim, 256), nn.BatchNorm1d(256), nn.ReLU(), nn.Linear(256, 256))
+
+        def forward(self, x):
+            return self.net(x)
+
+    def __init__(self, num_classes, cue_dim=768, vdim=256, lstm_dropout=0.3):
+        super().__init__()
+        self.audio = self._Audio()
+        self.cue = self._Cue(cue_dim)
+        self.video = self._Video(vdim, lstm_dropout)
+        self.afc = nn.Linear(512, num_classes)
+        self.cfc = nn.Linear(256, num_classes)
+        self.vfc = nn.Linear(vdim, num_classes)
+        self.attn = self._Attn(num_classes)
+
+    def forward(self, mel, cue, lip):
+        a = self.afc(self.audio(mel))
+        c = self.cfc(self.cue(cue))
+        v = self.vfc(self.video(lip))
+        fused, _ = self.attn([a, c, v])
+        return fused
+
+
+def train_step_generic(model, optimizer, inputs, labels):
+    """zero_grad, forward, CrossEntropyLoss(mean), backward, step -- the loop body shared by audio/train.py:67-78,
+    video/train.py:93-104, audio_video/train.py:61-67, audio_cues_video/train.py:60-72."""
+    optimizer.zero_grad()
+    logits = model(*inputs)
+    loss = nn.functional.cross_entropy(logits, labels)
+    loss.backward()
+    optimizer.step()
+    return logits.detach(), float(loss.item())
 
 
 def train_step(model, optimizer, audio, video, labels):

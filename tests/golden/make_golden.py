@@ -2,7 +2,7 @@
 
 Run in the build container only (needs /root/reference, read-only):
     python tests/golden/make_golden.py
-Writes tests/golden/logmel_golden.npz and tests/golden/midfusion_golden.npz.
+Writes tests/golden/logmel_golden.npz, tests/golden/midfusion_golden.npz and tests/golden/models_golden.npz.
 
 Recipe: stub the unused top-level imports `librosa` / `pydub`, make the
 ImageNet weight download a no-op (seeded random init instead), and load one reference
@@ -128,9 +128,88 @@ def golden_midfusion():
     np.savez_compressed(os.path.join(HERE, "midfusion_golden.npz"), **out)
 
 
+class DCfg:
+    def __init__(self, d):
+        self.d = d
+
+    def get(self, key, default=None):
+        return self.d.get(key, default)
+
+
+def golden_models():
+    """Configs 1, 2, 4: the reference's own AudioResNet / ResNet2DBiLSTM / EarlyFusionAVMobileNet with dropout set to 0
+    (the only change: p is a constructor argument / module attribute), one train step each."""
+    out = {}
+    apm = load_ref("audio_video", "utils.audio_processor").AudioProcessor()
+
+    def data(B, size, T, C):
+        wav = synthetic.make_waveforms(B, pad_fraction=0.5)
+        mel = torch.stack([apm.normalize_spectrogram(apm.compute_melspectrogram(w))[:80, :117].float() for w in wav])
+        lips = synthetic.make_lips_u8(B, size=size)[:, :T].contiguous()
+        video = (lips.float() / 255.0).permute(0, 4, 1, 2, 3).contiguous()
+        return mel, video, synthetic.make_labels(B, C)
+
+    def record(name, model, inputs, labels, lr, wd, B, T, size):
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
+        opt.zero_grad()
+        logits = model(*inputs)
+        loss = torch.nn.CrossEntropyLoss()(logits, labels)
+        loss.backward()
+        out[f"{name}_logits"] = logits.detach().numpy()
+        out[f"{name}_loss"] = np.array(loss.item())
+        out[f"{name}_grad_norm"] = np.array([p.grad.double().norm().item() for _, p in model.named_parameters()])
+        out[f"{name}_wsum_before"] = np.array([p.detach().double().sum().item() for _, p in model.named_parameters()])
+        opt.step()
+        out[f"{name}_wsum_after"] = np.array([p.detach().double().sum().item() for _, p in model.named_parameters()])
+        out[f"{name}_param_names"] = np.array([n for n, _ in model.named_parameters()])
+        out[f"{name}_state_keys"] = np.array(list(model.state_dict().keys()))
+        out[f"{name}_B"], out[f"{name}_T"], out[f"{name}_size"] = np.array(B), np.array(T), np.array(size)
+        print(name, "loss", loss.item(), "n_params", sum(p.numel() for p in model.parameters()))
+
+    # config 4: audio_video early_fusion_mobilenet (lr 3e-4, av_config.yaml:23)
+    B, T, size, C = 3, 8, 44, 40
+    mod = load_ref("audio_video", "models.early_fusion")
+    torch.manual_seed(0)
+    model = mod.create_early_fusion_mobilenet_model(C, Cfg())
+    model.video_encoder.lstm.dropout = 0.0
+    model.classifier[2].p = 0.0
+    mel, video, labels = data(B, size, T, C)
+    record("early_fusion_mobilenet", model, (mel, video), labels, 3e-4, 0.0, B, T, size)
+
+    # config 2: video resnet_lstm (lr 5e-5, weight_decay 1e-5: visual_config.yaml:25, video/train.py:210)
+    B, T, size, C = 2, 5, 44, 40
+    mod = load_ref("video", "models.resnet_lstm")
+    torch.manual_seed(0)
+    model = mod.ResNet2DBiLSTM(C, DCfg({"model.dropout": 0.0}))
+    mel, video, labels = data(B, size, T, C)
+    record("video_resnet_lstm", model, (video,), labels, 5e-5, 1e-5, B, T, size)
+
+    # config 1: audio-only resnet (lr 5e-4, weight_decay 1e-4: audio_config.yaml:20-21)
+    B, C = 4, 8
+    mod = load_ref("audio", "models.resnet_model")
+    torch.manual_seed(0)
+    model = mod.AudioResNet(num_classes=C, dropout_rate=0.0)
+    mel, video, labels = data(B, 44, 1, C)
+    record("audio_resnet", model, (mel,), labels, 5e-4, 1e-4, B, 1, 44)
+    # config 5: audio_cues_video late_fusion_mobile (lr 1e-5, acv_config.yaml:14), pretrained=False as its own
+    # constructor allows (late_fusion_mobile.py:86)
+    B, T, size, C = 3, 6, 44, 40
+    mod = load_ref("audio_cues_video", "models.late_fusion_mobile")
+    torch.manual_seed(0)
+    model = mod.MultimodalAttentionLate(C, cue_dim=768, video_cfg=None, pretrained=False)
+    model.video.lstm.dropout = 0.0
+    mel, video, labels = data(B, size, T, C)
+    cue = synthetic.make_cues(B)
+    record("acv_late_fusion_mobile", model, (mel, cue, video), labels, 1e-5, 0.0, B, T, size)
+    np.savez_compressed(os.path.join(HERE, "models_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     _stub_unused_imports()
     _offline_weights()
     torch.set_num_threads(8)
-    golden_logmel()
-    golden_midfusion()
+    if "--models-only" not in sys.argv:
+        golden_logmel()
+        golden_midfusion()
+    golden_models()

@@ -103,3 +103,47 @@ def test_midfusion_oracle_matches_reference(mg, size):
     model.eval()
     with torch.no_grad():
         np.testing.assert_allclose(model(mel, video).numpy(), mg[f"logits_eval_{size}"], rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# configs 1, 2, 4: oracle ports pinned to the reference's own AudioResNet / ResNet2DBiLSTM / EarlyFusionAVMobileNet
+# ---------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def models_golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "models_golden.npz"))
+
+
+@pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile"])
+def test_model_oracles_match_reference(models_golden, name):
+    from oracle import av_models as O
+    g = models_golden
+    B, T, size = int(g[f"{name}_B"]), int(g[f"{name}_T"]), int(g[f"{name}_size"])
+    C = 8 if name == "audio_resnet" else 40
+    torch.manual_seed(0)
+    if name == "early_fusion_mobilenet":
+        model, lr, wd = O.EarlyFusionMobileNetOracle(C, lstm_dropout=0.0, head_dropout=0.0), 3e-4, 0.0
+    elif name == "video_resnet_lstm":
+        model, lr, wd = O.ResNet2DBiLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}})), 5e-5, 1e-5
+    elif name == "acv_late_fusion_mobile":
+        model, lr, wd = O.LateFusionMobileOracle(C, lstm_dropout=0.0), 1e-5, 0.0
+    else:
+        model, lr, wd = O.AudioResNetOracle(C, dropout_rate=0.0), 5e-4, 1e-4
+    model.train()
+    assert [n for n, _ in model.named_parameters()] == list(g[f"{name}_param_names"])
+    assert list(model.state_dict().keys()) == list(g[f"{name}_state_keys"])
+    wsum0 = np.array([p.detach().double().sum().item() for p in model.parameters()])
+    np.testing.assert_allclose(wsum0, g[f"{name}_wsum_before"], rtol=0, atol=0)     # same seeded init
+    wav = synthetic.make_waveforms(B, pad_fraction=0.5)
+    mel = AudioProcessorPort().batch_frontend_loop(wav)
+    video = lips_u8_to_model_input(synthetic.make_lips_u8(B, size=size)[:, :T].contiguous())
+    labels = synthetic.make_labels(B, C)
+    inputs = {"early_fusion_mobilenet": (mel, video), "video_resnet_lstm": (video,), "audio_resnet": (mel,),
+              "acv_late_fusion_mobile": (mel, synthetic.make_cues(B), video)}[name]
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
+    logits, loss = O.train_step_generic(model, opt, inputs, labels)
+    np.testing.assert_allclose(logits.numpy(), g[f"{name}_logits"], rtol=1e-5, atol=1e-6)
+    assert abs(loss - float(g[f"{name}_loss"])) < 1e-6
+    gnorm = np.array([p.grad.double().norm().item() for p in model.parameters()])
+    np.testing.assert_allclose(gnorm, g[f"{name}_grad_norm"], rtol=1e-4, atol=1e-7)
+    wsum1 = np.array([p.detach().double().sum().item() for p in model.parameters()])
+    np.testing.assert_allclose(wsum1, g[f"{name}_wsum_after"], rtol=1e-5, atol=1e-4)
