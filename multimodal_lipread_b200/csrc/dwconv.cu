@@ -389,14 +389,19 @@ static dim3 persistent_grid(const Geo& d, int ctas_per_sm) {
     return dim3((unsigned)gx, chunks);
 }
 
-template <typename Kern>
-static cudaError_t set_smem(Kern kern, size_t bytes) {
-    return bytes > 40 * 1024 ?   /* static + dynamic shared memory must stay under 48 KB without the opt-in */ cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) : cudaSuccess;
-}
+// The opt-in dynamic shared-memory limit is raised ONCE per kernel instantiation to a fixed ceiling, never to the
+// size of the current launch: a later, smaller launch must not lower the limit under launches already captured in
+// a CUDA graph (tools that re-launch graph kernel nodes one by one -- ncu -- use the function's current limit).
+constexpr int SMEM_CEILING = 160 * 1024;
 
 #define DW_LAUNCH(KERNEL, K_, S_, WS_, ...)                                              \
     do {                                                                                 \
-        err = set_smem(KERNEL<K_, S_, WS_>, smem);                                       \
+        static bool configured = false;                                                  \
+        if (!configured) {                                                               \
+            err = cudaFuncSetAttribute(KERNEL<K_, S_, WS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CEILING); \
+            configured = err == cudaSuccess;                                             \
+        }                                                                                \
+        if (err == cudaSuccess && smem > (size_t)SMEM_CEILING) err = cudaErrorInvalidValue; \
         if (err == cudaSuccess) KERNEL<K_, S_, WS_><<<grid, TH, smem, stream>>>(__VA_ARGS__); \
     } while (0)
 #define DW_DISPATCH_WS(KERNEL, K_, S_, ...)                                              \

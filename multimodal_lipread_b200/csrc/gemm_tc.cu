@@ -12,11 +12,13 @@
 //   warp 0      TMA producer (one elected lane), 128 x 32-float A box + BN x 32-float B box per stage
 //   warp 1      TMEM allocation + MMA issue (one lane): 4 x tcgen05.mma (K = 8 each) per stage, tcgen05.commit
 //               hands the stage back to the producer and finally signals the epilogue
-//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 16 columns at a time -> bias / activation / residual -> row-major
-//               float4 stores; per-column sum / sum of squares (train-mode BatchNorm statistics) reduced with a
-//               transpose-reduce shuffle network, shared-memory float atomics, one double atomic per column/CTA
+//   warps 2..5  epilogue: tcgen05.ld 32 lanes x 16 columns at a time -> bias / activation -> a per-warp shared-memory
+//               slab (transpose) -> contiguous row segments to HBM (+ residual), 512 bytes per store instruction;
+//               per-column sum / sum of squares (train-mode BatchNorm statistics) read column-wise from the slab,
+//               shared-memory float atomics, one double atomic per column and CTA
 // Several CTAs are co-resident per SM (smem <= 2/SM for BN <= 96), so one CTA's epilogue overlaps another's loads.
 #include <cuda.h>
+#include <cstring>
 
 #include "nn_common.cuh"
 
@@ -24,16 +26,28 @@ namespace tc {
 
 constexpr int BM = 128, BK = 32, MAX_STAGES = 4, THREADS = 192;
 constexpr int A_STAGE_BYTES = BM * BK * 4;     // 16 KB
+constexpr int EPI_PW = 64, EPI_PITCH = EPI_PW + 4;                    // epilogue panel width / slab pitch (floats)
+constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;                    // four 32-row slabs
 
 struct P {
     int M, N, K, BN, stages;
     int kchunk;          // reduce-dimension elements handled by one CTA (multiple of BK); gridDim.z CTAs split K
     int atomic_out;      // 1: C += tile with red.global.add (split-K wgrad); bias / act / residual / stats unused
+    int tma_out;         // 1: tiles leave through TMA (store, or reduce-add when accum_out) from swizzled 32x32 boxes
+    int accum_out;       // tma_out only: C += tile (split-K, or an accumulating call whose R aliases C)
     float* C; long long ldc;
     const float* bias; const float* R; long long ldr;
     double* stats;
     int act;
+#ifdef LR_TRACE
+    long long* trace;    // [gridDim.x][32] clock64 stamps (debug builds only: scratch/gemm_trace.cu)
+#endif
 };
+#ifdef LR_TRACE
+#define LR_STAMP(i) do { p.trace[(long long)blockIdx.x * 32 + (i)] = clock64(); } while (0)
+#else
+#define LR_STAMP(i) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -60,8 +74,35 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
 
 // shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows at a 128 B pitch, 8-row groups
 // 1024 B apart (SBO), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
@@ -104,60 +145,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// column sums of a 32 (lanes) x 16 (values) tile: afterwards every lane holds the full 32-lane sum of column
-// ((lane>>1) & 15) -- 16 shuffles instead of 80.
-__device__ __forceinline__ float colsum16(const float* v, int lane) {
-    float a[8];
-    {
-        const bool hi = lane & 16;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float send = hi ? v[i] : v[i + 8];
-            const float keep = hi ? v[i + 8] : v[i];
-            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-    }
-    float b[4];
-    {
-        const bool hi = lane & 8;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float send = hi ? a[i] : a[i + 4];
-            const float keep = hi ? a[i + 4] : a[i];
-            b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    float c[2];
-    {
-        const bool hi = lane & 4;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float send = hi ? b[i] : b[i + 2];
-            const float keep = hi ? b[i + 2] : b[i];
-            c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-    }
-    float d;
-    {
-        const bool hi = lane & 2;
-        const float send = hi ? c[0] : c[1];
-        const float keep = hi ? c[1] : c[0];
-        d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    return d + __shfl_xor_sync(0xffffffffu, d, 1);
-}
-// column index held by `lane` after colsum16
-__device__ __forceinline__ int colsum16_col(int lane) {
-    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-}
-
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const P p) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const P p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 1];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float s_sum[256], s_sq[256];
+    __shared__ __align__(16) float s_sum[256], s_sq[256], s_bias[256];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.BN;
@@ -171,9 +166,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[MAX_STAGES]);
     const uint32_t tmem_full = smem_u32(&bars[2 * MAX_STAGES]);
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)p.BN) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)((p.BN + 31) & ~31)) tmem_cols <<= 1;     // the epilogue reads 32 columns at a time
 
-    for (int i = threadIdx.x; i < 256; i += THREADS) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
+    if (threadIdx.x == 0) LR_STAMP(0);
+    for (int i = threadIdx.x; i < 256; i += THREADS) {
+        s_sum[i] = 0.f; s_sq[i] = 0.f;
+        s_bias[i] = (p.bias && i < p.BN && blockIdx.y * p.BN + i < p.N) ? p.bias[blockIdx.y * p.BN + i] : 0.f;
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         mbar_init(tmem_full, 1);
@@ -188,6 +187,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     fence_after();
     const uint32_t tmem_d = tmem_base_slot;
+    if (threadIdx.x == 0) LR_STAMP(1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -195,6 +195,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int s = kb % p.stages;
                 const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                if (kb < 6) LR_STAMP(2 + kb);
                 const uint32_t a_dst = tiles + s * stage_bytes, b_dst = a_dst + A_STAGE_BYTES;
                 mbar_expect_tx(full0 + 8 * s, stage_bytes);
                 const int k0 = kbeg + kb * BK;
@@ -218,6 +219,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int s = kb % p.stages;
                 const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
                 mbar_wait(full0 + 8 * s, ph);
+                if (kb < 6) LR_STAMP(8 + kb);
                 fence_after();
                 const uint32_t a_src = tiles + s * stage_bytes, b_src = a_src + A_STAGE_BYTES;
                 const uint64_t adesc = A_MN ? make_desc_mn_sw128(a_src) : make_desc_k_sw128(a_src);
@@ -231,69 +233,169 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mma_commit(empty0 + 8 * s);
             }
             mma_commit(tmem_full);
+            LR_STAMP(14);
         }
     } else {
-        // ---------------- epilogue: warp w owns TMEM lanes 32*(w & 3) .. +31 == tile rows
+        // ---------------- epilogue: warp w owns TMEM lanes 32*(w & 3) .. +31 == tile rows.
+        // A thread reads ITS row from TMEM, so storing straight to HBM would write 32 different rows per
+        // instruction (16 bytes of 32 cache lines: the store unit serialises them -- measured 3-5k cycles per 16
+        // columns).  Instead each warp transposes through a private shared-memory slab (32 rows x 64 columns, pitch
+        // 68 floats: conflict-free both ways) and then writes whole contiguous row segments, 512 bytes per
+        // instruction.  The slabs reuse the pipeline buffers, which are idle once the last MMA has completed.
         const int q = warp & 3;
-        const int row = m0 + q * 32 + lane;
-        const bool row_ok = row < p.M;
+        const int row0 = m0 + q * 32;
+        const int rv = max(0, min(32, p.M - row0));                         // valid rows of this warp's slab
+        float* slab = reinterpret_cast<float*>(smem_raw + (tiles - smem_u32(smem_raw))) + q * 32 * EPI_PITCH;
         mbar_wait(tmem_full, 0);
+        if (threadIdx.x == 64) LR_STAMP(15);
         fence_after();
         const bool vec_c = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         const bool vec_r = p.R && ((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
-            const int n = n0 + c0;
-            if (n >= p.N) break;                         // warp-uniform
-            float v[16];
-            tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            const bool full16 = n + 15 < p.N;
-            if (p.atomic_out) {
-                if (row_ok && num_kb > 0) {
-                    float* cr = p.C + (long long)row * p.ldc + n;
+        if (p.tma_out) {
+            // ---- TMA epilogue: 32 rows x 32 columns at a time through a 128-byte-swizzled box (row r, 16-byte chunk
+            // c stored at chunk c ^ (r & 7): the row-per-lane writes and the column-per-lane statistic reads are both
+            // bank-conflict free); one lane hands the box to TMA, which clips rows >= M / columns >= N and either
+            // stores or reduce-adds it.  Two boxes per warp are in flight.
+            const uint32_t stg0 = tiles + (uint32_t)q * 8192u;
+            uint8_t* stg0_g = smem_raw + (stg0 - smem_u32(smem_raw));
+            int nbox = 0;
+            const bool do_out = num_kb > 0 || !p.accum_out;
+            const int plain_out = (p.atomic_out || (p.bias == nullptr && p.act == LR_ACT_NONE)) ? 1 : 0;
+            for (int c0 = 0; c0 < p.BN; c0 += 32, ++nbox) {
+                const int n = n0 + c0;
+                if (n >= p.N) break;                                         // warp-uniform
+                const uint32_t buf = (uint32_t)(nbox & 1) * 4096u;
+                if (threadIdx.x == 64 && nbox == 1) LR_STAMP(19);
+                if (nbox >= 2) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }
+                uint8_t* rowp = stg0_g + buf + lane * 128;
+                {
+                    float v[32];
+                    tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                    if (threadIdx.x == 64 && nbox == 1) LR_STAMP(20);
+                    if (plain_out == 0) {                                    // bias and / or activation (uniform branch)
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (n + j < p.N) atomicAdd(cr + j, v[j]);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bq = *reinterpret_cast<const float4*>(&s_bias[c0 + j]);
+                            v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
+                        }
+                        switch (p.act) {                                      // hoisted: one branch per box, not per element
+                            case LR_ACT_RELU:
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                                break;
+                            case LR_ACT_NONE: break;
+                            default:
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = nn::act_fwd(v[j], p.act);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
-                continue;
-            }
+                if (threadIdx.x == 64 && nbox == 1) LR_STAMP(21);
+                fence_proxy_async();
+                if (threadIdx.x == 64 && nbox == 1) LR_STAMP(22);
+                __syncwarp();
+                if (lane == 0 && do_out) {
+                    if (p.accum_out) tma_reduce_add_2d(&tmC, stg0 + buf, n, row0);
+                    else tma_store_2d(&tmC, stg0 + buf, n, row0);
+                    bulk_commit();
+                }
+                if (threadIdx.x == 64 && nbox == 1) LR_STAMP(23);
+                if (p.stats && n + lane < p.N) {
+                    const uint8_t* colp = stg0_g + buf + (lane & 3) * 4;
+                    float a = 0.f, b = 0.f;
+                    if (rv == 32) {
+                        // the 8 rows of a swizzle period hit 8 different 16-byte chunks: their offsets are loop constants
+                        float a1 = 0.f, b1 = 0.f, a2 = 0.f, b2 = 0.f, a3 = 0.f, b3 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float x = v[j];
-                if (p.bias && n + j < p.N) x += p.bias[n + j];
-                v[j] = nn::act_fwd(x, p.act);
+                        for (int r = 0; r < 32; r += 4) {
+                            const float x0 = *reinterpret_cast<const float*>(colp + r * 128 + (((lane >> 2) ^ (r & 7)) << 4));
+                            const float x1 = *reinterpret_cast<const float*>(colp + (r + 1) * 128 + (((lane >> 2) ^ ((r + 1) & 7)) << 4));
+                            const float x2 = *reinterpret_cast<const float*>(colp + (r + 2) * 128 + (((lane >> 2) ^ ((r + 2) & 7)) << 4));
+                            const float x3 = *reinterpret_cast<const float*>(colp + (r + 3) * 128 + (((lane >> 2) ^ ((r + 3) & 7)) << 4));
+                            a += x0; b = fmaf(x0, x0, b); a1 += x1; b1 = fmaf(x1, x1, b1);
+                            a2 += x2; b2 = fmaf(x2, x2, b2); a3 += x3; b3 = fmaf(x3, x3, b3);
+                        }
+                        a = (a + a1) + (a2 + a3); b = (b + b1) + (b2 + b3);
+                    } else {
+                        for (int r = 0; r < rv; ++r) {
+                            const float x = *reinterpret_cast<const float*>(colp + r * 128 + (((lane >> 2) ^ (r & 7)) << 4));
+                            a += x; b = fmaf(x, x, b);
+                        }
+                    }
+                    atomicAdd(&s_sum[c0 + lane], a);
+                    atomicAdd(&s_sq[c0 + lane], b);
+                }
+                if (threadIdx.x == 64 && nbox == 1) LR_STAMP(24);
             }
-            if (p.R && row_ok) {
-                const float* rr = p.R + (long long)row * p.ldr + n;
-                if (vec_r && full16) {
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+        } else
+        for (int p0 = 0; p0 < p.BN; p0 += EPI_PW) {
+            const int nbase = n0 + p0;
+            if (nbase >= p.N) break;                                         // warp-uniform
+            const int pwv = min(min(EPI_PW, p.BN - p0), p.N - nbase);        // valid columns of this panel
+            // ---- TMEM -> registers (bias, activation) -> slab[row = lane][col]
+            for (int c0 = 0; c0 < pwv; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(p0 + c0), v);
+                if (!p.atomic_out) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) { const float4 t = nn::ld4(rr + j); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+                    for (int j = 0; j < 16; ++j) v[j] = nn::act_fwd(v[j] + s_bias[p0 + c0 + j], p.act);
+                }
+                float* dst = slab + lane * EPI_PITCH + c0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            __syncwarp();
+            // ---- slab -> HBM in contiguous row segments (+ residual); the final value goes back to the slab for the statistics
+            if (num_kb > 0 || !p.atomic_out) {
+                if (vec_c && (pwv & 3) == 0 && (!p.R || vec_r)) {
+                    const int nv = pwv >> 2, total = rv * nv;
+                    for (int idx = lane; idx < total; idx += 32) {
+                        const int r = idx / nv, c4 = (idx - r * nv) * 4;
+                        float4 x = *reinterpret_cast<const float4*>(slab + r * EPI_PITCH + c4);
+                        float* cp = p.C + (long long)(row0 + r) * p.ldc + nbase + c4;
+                        if (p.atomic_out) { atomicAdd(reinterpret_cast<float4*>(cp), x); continue; }
+                        if (p.R) {
+                            const float4 t = nn::ld4(p.R + (long long)(row0 + r) * p.ldr + nbase + c4);
+                            x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+                            if (p.stats) *reinterpret_cast<float4*>(slab + r * EPI_PITCH + c4) = x;
+                        }
+                        nn::st4(cp, x);
+                    }
                 } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += rr[j];
+                    const int total = rv * pwv;
+                    for (int idx = lane; idx < total; idx += 32) {
+                        const int r = idx / pwv, c = idx - r * pwv;
+                        float x = slab[r * EPI_PITCH + c];
+                        float* cp = p.C + (long long)(row0 + r) * p.ldc + nbase + c;
+                        if (p.atomic_out) { atomicAdd(cp, x); continue; }
+                        if (p.R) {
+                            x += p.R[(long long)(row0 + r) * p.ldr + nbase + c];
+                            if (p.stats) slab[r * EPI_PITCH + c] = x;
+                        }
+                        *cp = x;
+                    }
                 }
             }
-            if (row_ok) {
-                float* cr = p.C + (long long)row * p.ldc + n;
-                if (vec_c && full16) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) nn::st4(cr + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) if (n + j < p.N) cr[j] = v[j];
-                }
-            }
+            // ---- per-column sum / sum of squares over this warp's valid rows (train-mode BatchNorm statistics)
             if (p.stats) {
-                float sq[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) { if (!row_ok) v[j] = 0.f; sq[j] = v[j] * v[j]; }
-                const float cs = colsum16(v, lane), cq = colsum16(sq, lane);
-                if ((lane & 1) == 0) {
-                    const int col = c0 + colsum16_col(lane);
-                    atomicAdd(&s_sum[col], cs);
-                    atomicAdd(&s_sq[col], cq);
+                __syncwarp();
+                for (int c = lane; c < pwv; c += 32) {
+                    float a = 0.f, b = 0.f;
+                    for (int r = 0; r < rv; ++r) { const float x = slab[r * EPI_PITCH + c]; a += x; b = fmaf(x, x, b); }
+                    atomicAdd(&s_sum[p0 + c], a);
+                    atomicAdd(&s_sq[p0 + c], b);
                 }
             }
+            __syncwarp();
         }
         fence_before();
+        if (threadIdx.x == 64) LR_STAMP(16);
         if (p.stats) {
             asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps only
             const int col = threadIdx.x - 64;
@@ -307,7 +409,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     }
+    if (threadIdx.x == 64) LR_STAMP(17);
     __syncthreads();
+    if (threadIdx.x == 0) LR_STAMP(18);
     if (warp == 1) {
         fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
@@ -363,6 +467,7 @@ extern "C" int lr_gemm_tf32(const float* A, long long lda, int a_trans, const fl
     const int ntile = (N + 255) / 256;
     int bn = (N + ntile - 1) / ntile;
     bn = (bn + 15) / 16 * 16;
+    if (ntile > 1) bn = (bn + 31) / 32 * 32;      // 32-column output boxes must not straddle two CTAs' tiles
     tc::P p;
     p.M = M; p.N = N; p.K = K; p.BN = bn; p.C = C; p.ldc = ldc; p.bias = bias; p.R = R; p.ldr = ldr; p.stats = stats; p.act = act;
     int kchunk = (K + ksplit - 1) / ksplit;
@@ -370,15 +475,33 @@ extern "C" int lr_gemm_tf32(const float* A, long long lda, int a_trans, const fl
     const int nz = (K + kchunk - 1) / kchunk;
     p.kchunk = kchunk;
     p.atomic_out = ksplit > 1 ? 1 : 0;
+#ifdef LR_TRACE
+    extern long long* g_lr_trace;
+    p.trace = g_lr_trace;
+#endif
     const int num_kb = kchunk / tc::BK;
     p.stages = num_kb < tc::MAX_STAGES ? num_kb : tc::MAX_STAGES;
-    CUtensorMap ma, mb;
+    // Output path: TMA store / reduce-add whenever C is TMA-addressable (16-byte aligned rows) and the residual
+    // is absent or IS C (then the call accumulates: reduce-add); otherwise the shared-memory slab path.
+    const bool c_tma_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+    const bool r_is_c = R == C && ldr == ldc;
+    p.tma_out = (c_tma_ok && (R == nullptr || (r_is_c && !stats && act == LR_ACT_NONE && !bias))) ? 1 : 0;
+    p.accum_out = (p.atomic_out || (R != nullptr && r_is_c)) ? 1 : 0;
+    CUtensorMap ma, mb, mc;
+    if (p.tma_out) {
+        int rcc = tc::make_map(&mc, C, M, N, ldc, 32);
+        if (rcc) return rcc;
+    } else {
+        memset(&mc, 0, sizeof(mc));
+    }
     int rc = a_trans ? tc::make_map(&ma, A, K, M, lda, 32, true) : tc::make_map(&ma, A, M, K, lda, tc::BM);
     if (rc) return rc;
     rc = b_trans ? tc::make_map(&mb, B, K, N, ldb, 32, true) : tc::make_map(&mb, B, N, K, ldb, bn);
     if (rc) return rc;
     const size_t b_stage = b_trans ? (size_t)((bn + 31) / 32) * 4096 : (size_t)bn * tc::BK * 4;
-    const size_t smem = (size_t)p.stages * (tc::A_STAGE_BYTES + b_stage) + 1024;
+    size_t smem = (size_t)p.stages * (tc::A_STAGE_BYTES + b_stage);
+    if (smem < (size_t)tc::EPI_BYTES) smem = tc::EPI_BYTES;           // the epilogue slabs reuse the pipeline buffers
+    smem += 1024;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc::gemm_tf32_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -390,11 +513,11 @@ extern "C" int lr_gemm_tf32(const float* A, long long lda, int a_trans, const fl
     }
     dim3 grid((unsigned)((M + tc::BM - 1) / tc::BM), (unsigned)((N + bn - 1) / bn), (unsigned)nz);
     if (a_trans) {
-        if (b_trans) tc::gemm_tf32_kernel<true, true><<<grid, tc::THREADS, smem, stream>>>(ma, mb, p);
-        else tc::gemm_tf32_kernel<true, false><<<grid, tc::THREADS, smem, stream>>>(ma, mb, p);
+        if (b_trans) tc::gemm_tf32_kernel<true, true><<<grid, tc::THREADS, smem, stream>>>(ma, mb, mc, p);
+        else tc::gemm_tf32_kernel<true, false><<<grid, tc::THREADS, smem, stream>>>(ma, mb, mc, p);
     } else {
-        if (b_trans) tc::gemm_tf32_kernel<false, true><<<grid, tc::THREADS, smem, stream>>>(ma, mb, p);
-        else tc::gemm_tf32_kernel<false, false><<<grid, tc::THREADS, smem, stream>>>(ma, mb, p);
+        if (b_trans) tc::gemm_tf32_kernel<false, true><<<grid, tc::THREADS, smem, stream>>>(ma, mb, mc, p);
+        else tc::gemm_tf32_kernel<false, false><<<grid, tc::THREADS, smem, stream>>>(ma, mb, mc, p);
     }
     lr::count_launch();
     LR_CHECK_LAUNCH("gemm_tf32_kernel");

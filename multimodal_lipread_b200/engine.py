@@ -93,6 +93,39 @@ class OpList:
         return [(name, args, t / reps) for (fn, args, name, _), t in zip(self.ops, acc)]
 
 
+def profile_ops_graph(ops, reps=20, flush=None):
+    """Device time of every op of an OpList measured without host launch overhead: each op is captured `reps`
+    times back to back into its own CUDA graph and the replay is timed with CUDA events (mean per launch, the
+    ~2 us launch-to-launch gap of graph kernel nodes included).  `flush`: optional callable run (untimed) before each
+    replay, e.g. an L2 flush.  Returns [(name, args, ms per launch)]."""
+    out = []
+    s = torch.cuda.Stream()
+    for fn, args, name, _ in ops.ops:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(s):
+            rc = fn(*args, s.cuda_stream)                      # warm (lazy module load / attributes) outside capture
+            if rc != 0:
+                raise _lib.LipreadError(f"{name} failed ({rc}): {lib.lr_last_error().decode()}")
+            s.synchronize()
+            with torch.cuda.graph(g, stream=s):
+                for _ in range(reps):
+                    fn(*args, s.cuda_stream)
+            best = None
+            for _ in range(3):
+                if flush is not None:
+                    flush()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(s)
+                g.replay()
+                b.record(s)
+                s.synchronize()
+                t = a.elapsed_time(b) / reps
+                best = t if best is None else min(best, t)
+        out.append((name, args, best))
+        del g
+    return out
+
+
 def op_algorithmic_bytes(name, args):
     """Algorithmic HBM bytes of one launch (every operand read once, every result written once, fp32)."""
     if name in ("lr_gemm", "lr_gemm_tf32"):

@@ -6,6 +6,8 @@ video/train.py:93-104, audio/train.py:67-78, audio_cues_video/train.py:60-72) re
 A concrete model keeps the reference's sub-modules as parameter containers (so seeded initialisation and
 `state_dict` keys are interchangeable with the reference) and provides a plan class whose constructor writes the
 launch lists.  The torch forward() of the sub-modules is never called; there is no CPU path."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -367,7 +369,10 @@ class PlanModel(nn.Module):
             main = torch.cuda.current_stream()
             if not hasattr(self, "_side"):
                 self._side = torch.cuda.Stream()
-            compute(main.cuda_stream, forked=(main, self._side))
+            # LIPREAD_SERIAL_GRAPH=1: one linear chain of kernel nodes (what the ncu launch lists are taken from);
+            # default: weight-gradient kernels as parallel branches of the graph
+            serial = os.environ.get("LIPREAD_SERIAL_GRAPH", "0") == "1"
+            compute(main.cuda_stream, forked=None if serial else (main, self._side))
             if not split:
                 update(main.cuda_stream)
         if not split:

@@ -109,7 +109,7 @@ def test_stem_conv(K, u8, size):
 
 
 @pytest.mark.parametrize("C,k,s,H", [(16, 3, 2, 22), (72, 3, 2, 11), (88, 3, 1, 6), (96, 5, 2, 6), (240, 5, 1, 3),
-                                     (576, 5, 1, 2), (288, 5, 2, 3),
+                                     (576, 5, 1, 2), (288, 5, 2, 3), (96, 5, 2, 22),
                                      # torchvision mobilenet_v2 (3x3 only) at 44 / 88 px lip frames
                                      (32, 3, 1, 22), (96, 3, 2, 22), (144, 3, 1, 11), (144, 3, 2, 11), (192, 3, 1, 6),
                                      (192, 3, 2, 6), (384, 3, 1, 3), (576, 3, 2, 3), (960, 3, 1, 2), (32, 3, 1, 44),
