@@ -1,12 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- headline measurement of the B200 audio-visual hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload av_train|logmel] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload av_train|logmel|<model>] [--impl reference]
 
 One "step" = one pass of the hot path over one per-GPU batch of synthetic GLips-shaped clips:
   av_train : log-mel frontend -> MidFusionFast forward -> CE -> backward -> (allreduce) -> Adam
              (audio_video/train.py:61-67 + audio_video/data_utils/dataset_av.py:58-71)
   logmel   : the log-mel frontend alone (audio/utils/audio_processor.py:48-64 + crop)
+  early_fusion_mobilenet | early_fusion_resnet | video_resnet_lstm | audio_resnet | acv_late_fusion_mobile :
+             the same train step for the other configs of BASELINE.json (not the headline line)
 `value` is device-timed with inputs resident in HBM; `e2e` goes through the public API from pinned HOST
 buffers with the H2D copies and a D2H read of the result inside the timed region.
 `--impl reference` times the reference's CPU implementation (oracle port: the reference's own
@@ -109,20 +111,40 @@ def cpu_reference(workload, cfg, steps, warmup, budget_s=25.0):
         unit_per_step, scale = n, LOGMEL_BYTES_PER_CLIP / 1e9
         sample = f"{n} clips per step, per-clip AudioProcessor loop (dataset_av.py:58-66 semantics)"
     else:
-        from oracle.av_models import MidFusionFastOracle, train_step
+        from oracle import av_models as O
+        kind = cfg.get("model", "mid_fusion_fast")
         n = cfg["cpu_batch"]
+        C = cfg["num_classes"]
         torch.manual_seed(0)
-        model = MidFusionFastOracle(cfg["num_classes"]).train()
-        opt = torch.optim.Adam(model.parameters(), lr=3e-4)
+        lr, wd = 3e-4, 0.0
+        if kind == "mid_fusion_fast":
+            model, names = O.MidFusionFastOracle(C), ("audio", "video")
+        elif kind == "early_fusion_mobilenet":
+            model, names = O.EarlyFusionMobileNetOracle(C), ("audio", "video")
+        elif kind == "early_fusion_resnet":
+            model, names = O.EarlyFusionResNetOracle(C), ("audio", "video")
+        elif kind == "video_resnet_lstm":
+            model, names, lr, wd = O.ResNet2DBiLSTMOracle(C), ("video",), 5e-5, 1e-5
+        elif kind == "audio_resnet":
+            model, names, lr, wd = O.AudioResNetOracle(C), ("audio",), 5e-4, 1e-4
+        else:
+            model, names, lr = O.LateFusionMobileOracle(C), ("audio", "cue", "video"), 1e-5
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
         wav = synthetic.make_waveforms(n, seed=1)
         lips = synthetic.make_lips_u8(n, size=cfg["size"], grayscale=cfg["grayscale"])
-        labels = synthetic.make_labels(n, cfg["num_classes"])
+        cue = synthetic.make_cues(n)
+        labels = synthetic.make_labels(n, C)
         def step():
-            mel = ap.batch_frontend_loop(wav)
-            train_step(model, opt, mel, lips_u8_to_model_input(lips), labels)
+            feed = {"cue": cue}
+            if "audio" in names:
+                feed["audio"] = ap.batch_frontend_loop(wav)
+            if "video" in names:
+                feed["video"] = lips_u8_to_model_input(lips)
+            O.train_step_generic(model, opt, tuple(feed[k] for k in names), labels)
         unit_per_step, scale = n, 1.0
-        sample = (f"{n} clips per step: per-clip log-mel + MidFusionFast fwd/CE/bwd/Adam in fp32 torch CPU "
-                  f"(audio_video/train.py:61-67), lips {cfg['size']}x{cfg['size']}")
+        sample = (f"{n} clips per step: per-clip log-mel + {type(model).__name__} fwd/CE/bwd/Adam in fp32 torch CPU "
+                  f"(the reference's train loop body), lips {cfg['size']}x{cfg['size']}")
     t_budget = time.perf_counter()
     for _ in range(warmup):
         step()
@@ -157,7 +179,9 @@ def main():
     ap_.add_argument("--steps", type=int, default=20)
     ap_.add_argument("--warmup", type=int, default=5)
     ap_.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap_.add_argument("--workload", default=None, choices=["av_train", "logmel"])
+    TRAIN_MODELS = ["early_fusion_mobilenet", "early_fusion_resnet", "video_resnet_lstm", "audio_resnet",
+                    "acv_late_fusion_mobile"]
+    ap_.add_argument("--workload", default=None, choices=["av_train", "logmel"] + TRAIN_MODELS)
     ap_.add_argument("--batch", type=int, default=None, help="clips per GPU per step")
     ap_.add_argument("--size", type=int, default=88, help="lip frame height = width (88 benchmark, 44 reference)")
     ap_.add_argument("--classes", type=int, default=40)
@@ -178,14 +202,20 @@ def main():
                   "clips_per_gpu_per_step": batch, "algorithmic_bytes_per_clip": LOGMEL_BYTES_PER_CLIP,
                   "l2": "inputs larger than L2 (batch * 80 kB >> 126 MB)"}
     else:
-        metric, unit = "av_midfusion_train_clips_per_sec", "clips/s"
+        kind = "mid_fusion_fast" if workload == "av_train" else workload
+        names = {"mid_fusion_fast": "audio_video middle_fusion_fast", "early_fusion_mobilenet": "audio_video early_fusion_mobilenet",
+                 "early_fusion_resnet": "audio_video early_fusion_resnet", "video_resnet_lstm": "video resnet_lstm",
+                 "audio_resnet": "audio resnet", "acv_late_fusion_mobile": "audio_cues_video late_fusion_mobile"}
+        metric = "av_midfusion_train_clips_per_sec" if workload == "av_train" else f"{workload}_train_clips_per_sec"
+        unit = "clips/s"
         batch = args.batch or 32
-        config = {"workload": f"audio_video middle_fusion_fast train step, GLips_{args.classes} shape "
+        config = {"workload": f"{names[kind]} train step, GLips_{args.classes} shape "
                               f"(29x{args.size}x{args.size} lips, 1.25 s 16 kHz audio)",
                   "batch_per_gpu": batch, "global_batch": batch * world, "num_classes": args.classes,
                   "lip_size": args.size, "grayscale_replicated": True, "parallelism": f"dp{world}",
                   "l2": "ring of input batches larger than L2"}
-    cfg = {"num_classes": args.classes, "size": args.size, "grayscale": True, "cpu_batch": min(batch, 32)}
+    cfg = {"num_classes": args.classes, "size": args.size, "grayscale": True, "cpu_batch": min(batch, 32),
+           "model": "mid_fusion_fast" if workload in ("av_train", "logmel") else workload}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":

@@ -80,29 +80,74 @@ class LogmelWorkload:
         return {"clips_per_sec": None}
 
 
+def _build_model(kind, num_classes):
+    """(model, input names) of a train workload; dropout keeps the reference's rates (it is part of the step)."""
+    if kind == "mid_fusion_fast":
+        from multimodal_lipread_b200.audio_video_models import MidFusionFast
+        return MidFusionFast(num_classes), ("audio", "video")
+    if kind == "early_fusion_mobilenet":
+        from multimodal_lipread_b200.audio_video_models import EarlyFusionAVMobileNet
+        return EarlyFusionAVMobileNet(num_classes), ("audio", "video")
+    if kind == "early_fusion_resnet":
+        from multimodal_lipread_b200.audio_video_models import EarlyFusionAV
+        return EarlyFusionAV(num_classes), ("audio", "video")
+    if kind == "video_resnet_lstm":
+        from multimodal_lipread_b200.video_models import ResNet2DBiLSTM
+        return ResNet2DBiLSTM(num_classes), ("video",)
+    if kind == "audio_resnet":
+        from multimodal_lipread_b200.audio_models import AudioResNet
+        return AudioResNet(num_classes), ("audio",)
+    if kind == "acv_late_fusion_mobile":
+        from multimodal_lipread_b200.audio_cues_video_models import MultimodalAttentionLate
+        return MultimodalAttentionLate(num_classes), ("audio", "cue", "video")
+    raise ValueError(f"unknown train workload {kind!r}")
+
+
+# forward GFLOP per clip at 44 / 88 px (SURVEY.md 8(a) a16, analytic 2*MAC counts of the reference modules)
+FWD_GFLOP = {"mid_fusion_fast": (0.256, 0.630), "early_fusion_mobilenet": (0.569, 0.944),
+             "early_fusion_resnet": (5.79, 17.99), "video_resnet_lstm": (6.04, 18.24), "audio_resnet": (0.72, 0.72),
+             "acv_late_fusion_mobile": (1.75, 3.81)}
+
+
+def flush_l2(dev, _buf={}):
+    """Overwrite a 512 MB buffer (4x the 126 MB L2) so that the next kernel starts cold."""
+    if dev not in _buf:
+        _buf[dev] = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    _buf[dev].zero_()
+
+
 class AvTrainWorkload:
-    """audio_video middle_fusion_fast train step on synthetic GLips-shaped clips (audio_video/train.py:61-67):
-    log-mel -> forward -> CE -> backward -> (NCCL allreduce) -> Adam, all in lipread_b200 kernels."""
+    """One train step of a lipread_b200 model on synthetic GLips-shaped clips (audio_video/train.py:61-67 and its
+    video / audio / audio_cues_video siblings): [log-mel ->] forward -> CE -> backward -> (NCCL allreduce) -> Adam,
+    all in lipread_b200 kernels.  The headline workload is audio_video middle_fusion_fast."""
     dtype = "f32"
 
     def __init__(self, dev, batch, cfg, rank, world):
         import torch.distributed as dist
-        from multimodal_lipread_b200.audio_video_models import MidFusionFast
         self.dev, self.batch, self.world, self.cfg = dev, batch, world, cfg
+        self.kind = cfg.get("model", "mid_fusion_fast")
         torch.manual_seed(0)                                   # identical replicas on every rank
-        self.model = MidFusionFast(cfg["num_classes"]).to(dev).train()
-        self.model.configure_optimizer(lr=3e-4)
+        model, self.names = _build_model(self.kind, cfg["num_classes"])
+        self.model = model.to(dev).train()
+        self.model.configure_optimizer()
         # a ring of distinct input batches larger than L2 (126 MB), resident in HBM
         per_batch = batch * (20000 * 4 + 29 * cfg["size"] * cfg["size"] * 3)
         self.ring = max(2, min(64, (160 * 1024 * 1024) // per_batch + 1))
         g = 1000 + rank
         self.host = []
         for i in range(self.ring):
-            wav = synthetic.make_waveforms(batch, seed=g * 100 + i).pin_memory()
-            lips = synthetic.make_lips_u8(batch, size=cfg["size"], seed=g * 100 + 50 + i, grayscale=cfg["grayscale"]).pin_memory()
-            lab = synthetic.make_labels(batch, cfg["num_classes"], seed=g * 100 + 77 + i).pin_memory()
-            self.host.append((wav, lips, lab))
-        self.devb = [(w.to(dev), l.to(dev), y.to(dev)) for w, l, y in self.host]
+            t = []
+            for n in self.names:
+                if n == "audio":
+                    t.append(synthetic.make_waveforms(batch, seed=g * 100 + i).pin_memory())
+                elif n == "video":
+                    t.append(synthetic.make_lips_u8(batch, size=cfg["size"], seed=g * 100 + 50 + i,
+                                                    grayscale=cfg["grayscale"]).pin_memory())
+                else:
+                    t.append(synthetic.make_cues(batch, seed=g * 100 + 30 + i).pin_memory())
+            t.append(synthetic.make_labels(batch, cfg["num_classes"], seed=g * 100 + 77 + i).pin_memory())
+            self.host.append(tuple(t))
+        self.devb = [tuple(x.to(dev) for x in t) for t in self.host]
         self.stage = tuple(torch.empty_like(t) for t in self.devb[0])
         self.i = 0
         self.loss_host = torch.zeros(1).pin_memory()
@@ -128,20 +173,20 @@ class AvTrainWorkload:
     def kernel_ms(self):
         return None
 
-    def _step(self, wav, lips, lab):
-        loss, _ = self.model.train_step(wav, lips, lab, grad_allreduce=self.allreduce, world=self.world)
+    def _step(self, *tensors):
+        loss, _ = self.model.train_step(*tensors, grad_allreduce=self.allreduce, world=self.world)
         self.last_loss = loss
         return loss
 
     def step_device(self):
-        w, l, y = self.devb[self.i % self.ring]
+        t = self.devb[self.i % self.ring]
         self.i += 1
-        return self._step(w, l, y)
+        return self._step(*t)
 
     def step_e2e(self):
-        w, l, y = self.host[self.i % self.ring]
+        t = self.host[self.i % self.ring]
         self.i += 1
-        for dst, src in zip(self.stage, (w, l, y)):
+        for dst, src in zip(self.stage, t):
             dst.copy_(src, non_blocking=True)
         loss = self._step(*self.stage)
         self.loss_host.copy_(loss, non_blocking=True)
@@ -149,20 +194,23 @@ class AvTrainWorkload:
         return self.loss_host
 
     def profile_ops(self):
-        """Per-op device time of one train step (eager launches, CUDA events on the launching stream)."""
+        """Device time of every kernel of one train step, each replayed alone from its own CUDA graph after an L2
+        flush (CUDA events on the launching stream, best of 3): no host launch overhead, cold cache like in the step."""
         from multimodal_lipread_b200 import engine
         plan = next(p for p in self.model._plans.values() if p.with_backward)
-        st = torch.cuda.current_stream()
         rows = []
-        for phase, ops in (("pre", plan.pre), ("fwd", plan.fwd), ("ce", plan.ce), ("pre_bwd", plan.pre_bwd), ("bwd", plan.bwd)):
-            for name, args, ms in ops.profile(st, reps=5):
+        for phase, ops in (("fwd", plan.fwd), ("bwd", plan.bwd)):
+            for name, args, ms in engine.profile_ops_graph(ops, reps=1, flush=lambda: flush_l2(self.dev)):
                 rows.append({"phase": phase, "op": name, "ms": ms, "bytes": engine.op_algorithmic_bytes(name, args),
                              "shape": [a for a in args if isinstance(a, int) and 0 < a < (1 << 31)][-6:]})
         return rows
 
     def roofline(self, kernel_ms, ms_step, peaks):
-        """Dominant kernel = the single launch with the largest device time in the step; achieved = its
-        algorithmic bytes / its CUDA-event duration (eager pass after the timed region, same buffers)."""
+        """Dominant kernel = the HBM-streaming launch with the largest device time in the step; achieved = its
+        algorithmic bytes / its CUDA-event duration.  `traffic` = dram bytes of that launch from the committed
+        ncu --set full capture (profiles/r1_traffic.json), when there is one for this kernel and shape."""
+        import json
+        import os
         rows = self.profile_ops()
         self.op_rows = rows
         total = sum(r["ms"] for r in rows)
@@ -172,12 +220,19 @@ class AvTrainWorkload:
         by_op = {}
         for r in rows:
             by_op[r["op"]] = by_op.get(r["op"], 0.0) + r["ms"]
-        size = self.cfg["size"]
-        fwd_gflop = 0.630 if size == 88 else 0.256           # SURVEY.md 8(a) a16, per clip
-        return {"kernel": f"{top['op']} {top['shape']} ({top['phase']})", "bound": "hbm", "achieved": achieved,
-                "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None,
+        label = f"{top['op']} {top['shape']} ({top['phase']})"
+        traffic = None
+        tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(label)
+        f44, f88 = FWD_GFLOP[self.kind]
+        fwd_gflop = f88 if self.cfg["size"] == 88 else f44
+        slowest = max(rows, key=lambda r: r["ms"])
+        return {"kernel": label, "bound": "hbm", "achieved": achieved,
+                "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": traffic,
                 "peak_source": peaks["src"], "kernel_ms": top["ms"], "kernel_share_of_step": top["ms"] / total,
-                "eager_step_ms_sum_of_kernels": total,
+                "step_ms_sum_of_kernels_cold": total,
+                "slowest_launch": f"{slowest['op']} {slowest['shape']} ({slowest['phase']}): {slowest['ms'] * 1e3:.0f} us",
                 "time_by_op_ms": {k: round(v, 4) for k, v in sorted(by_op.items(), key=lambda kv: -kv[1])},
                 "step_model_tflops": 3 * fwd_gflop * self.batch / (ms_step / 1e3) / 1e3}
 

@@ -353,30 +353,52 @@ class PlanModel(nn.Module):
         gkey = (id(plan), grad_allreduce is not None)
         graphs = self._graphs.get(gkey)
         if graphs is None:
-            graphs = self._capture(compute, update, split=grad_allreduce is not None)
+            graphs = self._capture(compute, update, grad_allreduce, flat)
             self._graphs[gkey] = graphs
         graphs[0].replay()
-        if grad_allreduce is not None:
+        if len(graphs) > 1:                                  # split capture: the collective runs between two graphs
             grad_allreduce(flat.grad)
             graphs[1].replay()
         return plan.loss, plan.logits
 
-    def _capture(self, compute, update, split):
-        """CUDA-graph capture of the step (one graph, or compute / update split around the NCCL allreduce)."""
-        torch.cuda.synchronize()
-        g0 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g0):
+    def _capture(self, compute, update, grad_allreduce, flat):
+        """CUDA-graph capture of the step.  Single GPU: one graph.  Data parallel: the NCCL allreduce of the flat
+        gradient is captured INSIDE the same graph (compute -> allreduce -> Adam: one launch per step, no host
+        round trip between backward and optimizer); if the collective cannot be captured the step falls back to two
+        graphs with the collective launched between them."""
+        main_serial = os.environ.get("LIPREAD_SERIAL_GRAPH", "0") == "1"
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream()
+
+        def body(with_update, with_allreduce):
             main = torch.cuda.current_stream()
-            if not hasattr(self, "_side"):
-                self._side = torch.cuda.Stream()
             # LIPREAD_SERIAL_GRAPH=1: one linear chain of kernel nodes (what the ncu launch lists are taken from);
             # default: weight-gradient kernels as parallel branches of the graph
-            serial = os.environ.get("LIPREAD_SERIAL_GRAPH", "0") == "1"
-            compute(main.cuda_stream, forked=None if serial else (main, self._side))
-            if not split:
+            compute(main.cuda_stream, forked=None if main_serial else (main, self._side))
+            if with_allreduce:
+                grad_allreduce(flat.grad)
+            if with_update:
                 update(main.cuda_stream)
-        if not split:
+
+        torch.cuda.synchronize()
+        if grad_allreduce is None:
+            g0 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g0):
+                body(True, False)
             return (g0,)
+        if os.environ.get("LIPREAD_ALLREDUCE_IN_GRAPH", "1") == "1":
+            try:
+                g0 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g0):
+                    body(True, True)
+                return (g0,)
+            except Exception as e:                           # collective not capturable on this stack: split
+                import warnings
+                warnings.warn(f"allreduce could not be captured into the step graph ({e}); using two graphs")
+                torch.cuda.synchronize()
+        g0 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g0):
+            body(False, False)
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):
             update(torch.cuda.current_stream().cuda_stream)

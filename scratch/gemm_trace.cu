@@ -11,13 +11,14 @@ int main(int argc, char** argv) {
     const int with_stats = argc > 4 ? atoi(argv[4]) : 0, with_bias = argc > 5 ? atoi(argv[5]) : 0;
     float *A, *B, *C, *bias; double* stats;
     cudaMalloc(&A, (size_t)M * K * 4); cudaMalloc(&B, (size_t)N * K * 4); cudaMalloc(&C, (size_t)M * N * 4);
-    cudaMalloc(&bias, N * 4); cudaMalloc(&stats, 2 * N * 8);
-    cudaMemset(A, 0, (size_t)M * K * 4); cudaMemset(B, 0, (size_t)N * K * 4); cudaMemset(bias, 0, N * 4); cudaMemset(stats, 0, 2 * N * 8);
+    cudaMalloc(&bias, N * 4); cudaMalloc(&stats, (64 * N + 2) * 8);
+    cudaMemset(A, 0, (size_t)M * K * 4); cudaMemset(B, 0, (size_t)N * K * 4); cudaMemset(bias, 0, N * 4); cudaMemset(stats, 0, (64 * N + 2) * 8);
     const int gx = (M + 127) / 128;
     cudaMalloc(&g_lr_trace, (size_t)gx * 32 * 8);
     cudaMemset(g_lr_trace, 0, (size_t)gx * 32 * 8);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int it = 0; it < 3; ++it) {
+        cudaMemset(stats, 0, (64 * N + 2) * 8);
         cudaEventRecord(e0);
         int rc = lr_gemm_tf32(A, K, 0, B, K, 0, C, N, M, N, K, with_bias ? bias : nullptr, with_bias ? 1 : 0, nullptr, 0,
                               with_stats ? stats : nullptr, 1, 0);
