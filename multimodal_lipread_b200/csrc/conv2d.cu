@@ -71,6 +71,37 @@ im2col_kernel(const Src s, const Geo g, float* __restrict__ col, long long rows)
     }
 }
 
+// Fast path of the stems on raw uint8 lip frames (3 channels, 3x3 window, any stride / padding): one thread per
+// output pixel reads its 3 x 3 x 3 byte patch (L1 serves the overlap with the neighbours) and writes its whole
+// 28-float row (7 coalesced float4 stores) -- no per-element index arithmetic.
+__global__ void __launch_bounds__(TH)
+im2col_u8c3_3x3_kernel(const Src s, const Geo g, float* __restrict__ col, long long rows) {
+    const unsigned char* xb = static_cast<const unsigned char*>(s.x);
+    for (long long row = (long long)blockIdx.x * TH + threadIdx.x; row < rows; row += (long long)gridDim.x * TH) {
+        const int wd = int(row % g.Wd);
+        const long long t = row / g.Wd;
+        const int hd = int(t % g.Hd), f = int(t / g.Hd);
+        const long long fb = (long long)(f / s.T) * s.sb + (long long)(f % s.T) * s.st;
+        float v[28];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int hs = hd * g.stride - g.pad + r;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int ws = wd * g.stride - g.pad + q;
+                const bool ok = hs >= 0 && hs < s.Hs && ws >= 0 && ws < s.Ws;
+                const unsigned char* px = xb + fb + (long long)hs * s.sh + (long long)ws * s.sw;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[c * 9 + r * 3 + q] = ok ? lr::u8_scaled(px[c * s.sc], s.scale) : 0.f;
+            }
+        }
+        v[27] = 0.f;
+        float* o = col + row * g.ldk;
+#pragma unroll
+        for (int j = 0; j < 28; j += 4) nn::st4(o + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+    }
+}
+
 // wt[c][k][rs] = w[k][c][rs]  (row pitch of wt = ldt >= Cout*kk, tail zeroed by the caller once)
 __global__ void __launch_bounds__(TH)
 weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin, int kk, long long ldt) {
@@ -208,7 +239,10 @@ extern "C" int lr_im2col(const void* x, int is_u8, float scale, int F, int T, lo
     g.Hd = Hd; g.Wd = Wd; g.kh = kh; g.kw = kw; g.stride = stride; g.pad = pad; g.transposed = transposed;
     g.K = (int)K; g.ldk = (int)ldk;
     const long long rows = (long long)F * Hd * Wd;
-    c2::im2col_kernel<<<c2::grid_for(rows * (ldk >> 2)), c2::TH, 0, stream>>>(s, g, col, rows);
+    if (is_u8 && C == 3 && kh == 3 && kw == 3 && !transposed && ldk == 28)
+        c2::im2col_u8c3_3x3_kernel<<<c2::grid_for(rows), c2::TH, 0, stream>>>(s, g, col, rows);
+    else
+        c2::im2col_kernel<<<c2::grid_for(rows * (ldk >> 2)), c2::TH, 0, stream>>>(s, g, col, rows);
     lr::count_launch();
     LR_CHECK_LAUNCH("im2col_kernel");
     return LR_OK;

@@ -10,6 +10,7 @@
 // prefix of its walk only: a head that reads out[:, -1] needs the reverse direction's FIRST step
 // (t = T-1) and nothing else.
 #include "nn_common.cuh"
+#include <cstdlib>
 
 namespace ls {
 
@@ -159,6 +160,286 @@ lstm_bwd_kernel(const Bwd p) {
 
 }  // namespace ls
 
+// =====================================================================================================================
+// Cluster version of the recurrence (thread-block clusters + distributed shared memory, sm_90+/sm_100a).
+//
+// The one-CTA-per-4-rows kernels above re-read the whole W_hh (4H x H floats: 256 KB at H = 128) from L2 on every step
+// and are latency bound (12 us per step).  Here a cluster of NC = 8 CTAs owns BG = 32 batch rows; CTA c owns the
+// hidden units [c*U, (c+1)*U), U = H / 8, i.e. the 4U gate rows {i,f,g,o} x U, whose W_hh slice (4U x H floats: 32 KB at
+// H = 128, 128 KB at H = 256) stays in its shared memory for all T steps.  Per step a CTA computes the gates of its
+// units for all 32 rows from h_{t-1} (a full [32][H] copy in its own shared memory), updates c / h for its units and
+// pushes its slice of h_t into the h buffer of all 8 CTAs through distributed shared memory; one cluster barrier per
+// step (the h buffer is double buffered).  The backward kernel does the transposed product the same way: every CTA
+// forms the partial W_hh^T dgates sum over its gate rows for all H columns and scatters column slices to their
+// owners (a reduce-scatter over DSMEM), two part buffers, one cluster barrier per step.
+namespace lsc {
+
+constexpr int NC = 8;          // CTAs per cluster (portable maximum)
+constexpr int BG = 32;         // batch rows per cluster
+constexpr int TH = 256;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_rank(const void* smem_ptr, unsigned rank) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// thread t: unit u = t % U, row group rg = t / U (TH / U groups of RPT = BG * U / TH rows)
+template <int H>
+__global__ void __launch_bounds__(TH)
+lstm_fwd_cluster_kernel(const ls::Fwd p) {
+    constexpr int U = H / NC;                 // hidden units per CTA
+    constexpr int NRG = TH / U;               // row groups
+    constexpr int RPT = BG / NRG;             // rows per thread
+    constexpr int HP = H + 4;                 // h row pitch (floats): rows land on different banks
+    static_assert(BG % NRG == 0 && RPT >= 1, "bad thread mapping");
+    extern __shared__ __align__(16) float sm[];
+    float* Wt = sm;                           // [H][U][4]   Wt[k][u][g] = whh[(g*H + c*U + u)*H + k]
+    float* hb = Wt + H * U * 4;               // [2][BG][HP]
+    const unsigned c = cluster_ctarank();
+    const int b0 = (blockIdx.x / NC) * BG;
+    const int u = threadIdx.x % U, rg = threadIdx.x / U;
+    for (int i = threadIdx.x; i < 4 * U * H; i += TH) {
+        const int k = i % H, ju = i / H;                       // ju = g*U + uu: coalesced reads of the row
+        const int g = ju / U, uu = ju - g * U;
+        Wt[(k * U + uu) * 4 + g] = p.whh[(long long)(g * H + c * U + uu) * H + k];
+    }
+    for (int i = threadIdx.x; i < 2 * BG * HP; i += TH) hb[i] = 0.f;
+    float bias[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) bias[g] = p.bhh ? p.bhh[g * H + c * U + u] : 0.f;
+    float cst[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) cst[r] = 0.f;
+    uint32_t remote[NC];
+#pragma unroll
+    for (int d = 0; d < NC; ++d) remote[d] = map_to_rank(hb, d);
+    cluster_sync();                           // every CTA's buffers are initialised before anyone writes into them
+    for (int s = 0; s < p.nsteps; ++s) {
+        const int t = p.reverse ? p.T - 1 - s : s;
+        const float* hcur = hb + (s & 1) * BG * HP;
+        float acc[RPT][4], xp[RPT][4];          // xp: issued now, consumed after the recurrent product (latency hidden)
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int b = b0 + rg * RPT + r;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                xp[r][g] = b < p.B ? p.xproj[((long long)b * p.T + t) * p.ldx + g * H + c * U + u] + bias[g] : 0.f;
+                acc[r][g] = 0.f;
+            }
+        }
+        if (s > 0) {                          // h_0 = 0: the first step has no recurrent term
+#pragma unroll 2
+            for (int k = 0; k < H; k += 4) {
+                float4 w[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4*>(Wt + ((k + kk) * U + u) * 4);
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    const float4 h = *reinterpret_cast<const float4*>(hcur + (rg * RPT + r) * HP + k);
+                    const float hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        acc[r][0] = fmaf(w[kk].x, hv[kk], acc[r][0]); acc[r][1] = fmaf(w[kk].y, hv[kk], acc[r][1]);
+                        acc[r][2] = fmaf(w[kk].z, hv[kk], acc[r][2]); acc[r][3] = fmaf(w[kk].w, hv[kk], acc[r][3]);
+                    }
+                }
+            }
+        }
+        const int nxt = ((s + 1) & 1) * BG * HP;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int rl = rg * RPT + r, b = b0 + rl;
+            const float ig = sigmoidf_(acc[r][0] + xp[r][0]), fg = sigmoidf_(acc[r][1] + xp[r][1]);
+            const float gg = tanhf(acc[r][2] + xp[r][2]), og = sigmoidf_(acc[r][3] + xp[r][3]);
+            const float cn = fg * cst[r] + ig * gg;
+            const float hn = og * tanhf(cn);
+            const int col = c * U + u;
+            if (b < p.B) {
+                const long long row = (long long)b * p.T + t;
+                if (p.gates) { float* gp = p.gates + row * 4 * H; gp[col] = ig; gp[H + col] = fg; gp[2 * H + col] = gg; gp[3 * H + col] = og; }
+                if (p.cst) p.cst[row * H + col] = cn;
+                if (p.hprev) p.hprev[row * H + col] = hcur[rl * HP + col];
+                p.out[row * p.ldo + col] = hn;
+            }
+            cst[r] = cn;
+            const uint32_t off = (uint32_t)(nxt + rl * HP + col) * 4u;
+#pragma unroll
+            for (int d = 0; d < NC; ++d) st_cluster(remote[d] + off, hn);
+        }
+        cluster_sync();
+    }
+}
+
+// BPTT with the same partition.  Per step: local dgates for the CTA's units, partial dh_prev[r][k] = sum over the
+// CTA's 4U gate rows of dg[r][j] * whh[j][k] for ALL k, scattered to the owner of column k.
+template <int H>
+__global__ void __launch_bounds__(TH)
+lstm_bwd_cluster_kernel(const ls::Bwd p) {
+    constexpr int U = H / NC;
+    constexpr int NRG = TH / U;
+    constexpr int RPT = BG / NRG;
+    constexpr int GP = 4 * U + 4;             // dg row pitch
+    constexpr int KPT = H / 32;               // columns per thread in the transposed product (32 column lanes)
+    constexpr int NRG2 = TH / 32;             // row groups of the transposed product
+    constexpr int RPT2 = BG / NRG2;
+    extern __shared__ __align__(16) float sm[];
+    float* Ws = sm;                           // [4U][H]    Ws[g*U+uu][k] = whh[(g*H + c*U + uu)*H + k]
+    float* dg = Ws + 4 * U * H;               // [BG][GP]   this step's gate gradients of the CTA's units
+    float* part = dg + BG * GP;               // [2][NC][BG][U]  partial dh of MY units from every CTA
+    const unsigned c = cluster_ctarank();
+    const int b0 = (blockIdx.x / NC) * BG;
+    const int u = threadIdx.x % U, rg = threadIdx.x / U;
+    for (int i = threadIdx.x; i < 4 * U * H; i += TH) {
+        const int k = i % H, ju = i / H;
+        const int g = ju / U, uu = ju - g * U;
+        Ws[ju * H + k] = p.whh[(long long)(g * H + c * U + uu) * H + k];
+    }
+    for (int i = threadIdx.x; i < 2 * NC * BG * U; i += TH) part[i] = 0.f;
+    float dc[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) dc[r] = 0.f;
+    uint32_t remote[NC];
+#pragma unroll
+    for (int d = 0; d < NC; ++d) remote[d] = map_to_rank(part, d);
+    const int kl = threadIdx.x % 32, rg2 = threadIdx.x / 32;
+    cluster_sync();
+    for (int s = p.nsteps - 1; s >= 0; --s) {
+        const int t = p.reverse ? p.T - 1 - s : s;
+        const int tprev = p.reverse ? t + 1 : t - 1;
+        const int par = s & 1;
+        // ---- gate gradients of my units: dh = sum of the 8 partials scattered to me in the previous iteration
+        const float* pin = part + par * NC * BG * U;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int rl = rg * RPT + r, b = b0 + rl;
+            const int col = c * U + u;
+            float pi = 0.f, pf = 0.f, pg = 0.f, po = 0.f;
+            if (b < p.B) {
+                float dht = 0.f;
+                if (s < p.nsteps - 1) {
+#pragma unroll
+                    for (int d = 0; d < NC; ++d) dht += pin[(d * BG + rl) * U + u];
+                }
+                const long long row = (long long)b * p.T + t;
+                if (p.dout) {
+                    if (p.dout_step < 0) dht += p.dout[row * p.ldo + col];
+                    else if (t == p.dout_step) dht += p.dout[(long long)b * p.ldo + col];
+                }
+                const float* gq = p.gates + row * 4 * H;
+                const float ig = gq[col], fg = gq[H + col], gg = gq[2 * H + col], og = gq[3 * H + col];
+                const float cc = p.cst[row * H + col];
+                const float cprev = s > 0 ? p.cst[((long long)b * p.T + tprev) * H + col] : 0.f;
+                const float tc = tanhf(cc);
+                const float dct = dc[r] + dht * og * (1.f - tc * tc);
+                pi = dct * gg * ig * (1.f - ig); pf = dct * cprev * fg * (1.f - fg);
+                pg = dct * ig * (1.f - gg * gg); po = dht * tc * og * (1.f - og);
+                float* o = p.dgates + row * 4 * H;
+                o[col] = pi; o[H + col] = pf; o[2 * H + col] = pg; o[3 * H + col] = po;
+                dc[r] = dct * fg;
+            }
+            float* d = dg + rl * GP;
+            d[u] = pi; d[U + u] = pf; d[2 * U + u] = pg; d[3 * U + u] = po;
+        }
+        __syncthreads();
+        if (s > 0) {
+            // ---- partial[r][k] = sum_j dg[r][j] * Ws[j][k]; thread: columns kl + 32*i, rows rg2*RPT2 ..
+            float acc[RPT2][KPT];
+#pragma unroll
+            for (int r = 0; r < RPT2; ++r)
+#pragma unroll
+                for (int i = 0; i < KPT; ++i) acc[r][i] = 0.f;
+            for (int j = 0; j < 4 * U; j += 4) {
+                float w[4][KPT];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                    for (int i = 0; i < KPT; ++i) w[jj][i] = Ws[(j + jj) * H + kl + 32 * i];
+#pragma unroll
+                for (int r = 0; r < RPT2; ++r) {
+                    const float4 g4 = *reinterpret_cast<const float4*>(dg + (rg2 * RPT2 + r) * GP + j);
+                    const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                        for (int i = 0; i < KPT; ++i) acc[r][i] = fmaf(gv[jj], w[jj][i], acc[r][i]);
+                }
+            }
+            // scatter: column k belongs to CTA k / U; it lands in that CTA's part[(s-1)&1][src = c][r][k % U]
+            const int npar = (s - 1) & 1;
+#pragma unroll
+            for (int i = 0; i < KPT; ++i) {
+                const int k = kl + 32 * i;
+                const int dst = k / U, ku = k - dst * U;
+#pragma unroll
+                for (int r = 0; r < RPT2; ++r) {
+                    const int rl = rg2 * RPT2 + r;
+                    st_cluster(remote[dst] + (uint32_t)(((npar * NC + (int)c) * BG + rl) * U + ku) * 4u, acc[r][i]);
+                }
+            }
+        }
+        cluster_sync();
+    }
+}
+
+template <typename Kern>
+static int launch_cluster(Kern kern, int clusters, size_t smem, lr_stream_t stream, const void* arg, const char* name,
+                          void (*launcher)(Kern, cudaLaunchConfig_t*, const void*)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return lr::fail(LR_ECUDA, "%s smem: %s", name, cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * NC));
+    cfg.blockDim = dim3(TH);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    launcher(kern, &cfg, arg);
+    return LR_OK;
+}
+
+template <int H> static size_t fwd_smem() { return (size_t)(H * (H / NC) * 4 + 2 * BG * (H + 4)) * sizeof(float); }
+template <int H> static size_t bwd_smem() {
+    return (size_t)(4 * (H / NC) * H + BG * (4 * (H / NC) + 4) + 2 * NC * BG * (H / NC)) * sizeof(float);
+}
+
+template <int H>
+static int run_fwd(const ls::Fwd& p, lr_stream_t stream) {
+    auto k = lstm_fwd_cluster_kernel<H>;
+    return launch_cluster(k, (p.B + BG - 1) / BG, fwd_smem<H>(), stream, &p, "lstm_fwd_cluster_kernel",
+                          +[](decltype(k) kk, cudaLaunchConfig_t* cfg, const void* a) {
+                              cudaLaunchKernelEx(cfg, kk, *static_cast<const ls::Fwd*>(a));
+                          });
+}
+template <int H>
+static int run_bwd(const ls::Bwd& p, lr_stream_t stream) {
+    auto k = lstm_bwd_cluster_kernel<H>;
+    return launch_cluster(k, (p.B + BG - 1) / BG, bwd_smem<H>(), stream, &p, "lstm_bwd_cluster_kernel",
+                          +[](decltype(k) kk, cudaLaunchConfig_t* cfg, const void* a) {
+                              cudaLaunchKernelEx(cfg, kk, *static_cast<const ls::Bwd*>(a));
+                          });
+}
+
+}  // namespace lsc
+
+// LIPREAD_LSTM=simple selects the one-CTA-per-4-rows kernels (debugging / A-B timing); read once.
+static bool lr_lstm_use_cluster() {
+    static const bool v = [] { const char* e = getenv("LIPREAD_LSTM"); return !(e && e[0] == 's'); }();
+    return v;
+}
+
 extern "C" int lr_lstm_fwd(const float* xproj, long long ldx, const float* bhh, const float* whh, float* out, long long ldo,
                            float* gates, float* cst, float* hprev, int B, int T, int H, int nsteps, int reverse,
                            lr_stream_t stream) {
@@ -170,6 +451,14 @@ extern "C" int lr_lstm_fwd(const float* xproj, long long ldx, const float* bhh, 
     ls::Fwd p;
     p.xproj = xproj; p.ldx = ldx; p.bhh = bhh; p.whh = whh; p.out = out; p.ldo = ldo; p.gates = gates; p.cst = cst; p.hprev = hprev;
     p.B = B; p.T = T; p.H = H; p.nsteps = nsteps; p.reverse = reverse;
+    // more than one step of a long walk: the cluster kernel keeps W_hh in shared memory (H = 128 / 256)
+    if (nsteps > 1 && (H == 128 || H == 256) && lr_lstm_use_cluster()) {
+        const int rc = H == 128 ? lsc::run_fwd<128>(p, stream) : lsc::run_fwd<256>(p, stream);
+        if (rc) return rc;
+        lr::count_launch();
+        LR_CHECK_LAUNCH("lstm_fwd_cluster_kernel");
+        return LR_OK;
+    }
     const size_t smem = (size_t)(2 * ls::R * H + ls::R * 4 * H) * sizeof(float);
     LR_CHECK_ARG(smem <= 200 * 1024, "lr_lstm_fwd: hidden size %d too large", H);
     static size_t configured = 0;
@@ -194,6 +483,13 @@ extern "C" int lr_lstm_bwd(const float* dout, long long ldo, int dout_step, cons
     ls::Bwd p;
     p.dout = dout; p.ldo = ldo; p.gates = gates; p.cst = cst; p.whh = whh; p.dgates = dgates;
     p.B = B; p.T = T; p.H = H; p.nsteps = nsteps; p.reverse = reverse; p.dout_step = dout_step;
+    if (nsteps > 1 && (H == 128 || H == 256) && lr_lstm_use_cluster()) {
+        const int rc = H == 128 ? lsc::run_bwd<128>(p, stream) : lsc::run_bwd<256>(p, stream);
+        if (rc) return rc;
+        lr::count_launch();
+        LR_CHECK_LAUNCH("lstm_bwd_cluster_kernel");
+        return LR_OK;
+    }
     const size_t smem = (size_t)(2 * ls::R * H + 2 * ls::R * 4 * H) * sizeof(float);
     LR_CHECK_ARG(smem <= 200 * 1024, "lr_lstm_bwd: hidden size %d too large", H);
     static size_t configured = 0;
@@ -208,3 +504,4 @@ extern "C" int lr_lstm_bwd(const float* dout, long long ldo, int dout_step, cons
     LR_CHECK_LAUNCH("lstm_bwd_kernel");
     return LR_OK;
 }
+

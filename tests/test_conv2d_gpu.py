@@ -54,12 +54,14 @@ def test_im2col_conv_fwd_dgrad_wgrad(cuda_device, Cin, Cout, k, stride, pad, H, 
     torch.testing.assert_close(dx.cpu().view(F, H, W, Cin), _cl(x.grad), rtol=1e-4, atol=2e-4)
 
 
-def test_im2col_reads_uint8_frames_in_place(cuda_device):
-    """The stem reads (B,T,H,W,3) uint8 frames with /255 and the TimeDistributed reshape folded into the addressing."""
+@pytest.mark.parametrize("k,stride,pad", [(7, 2, 3), (3, 2, 1), (3, 1, 1)])
+def test_im2col_reads_uint8_frames_in_place(cuda_device, k, stride, pad):
+    """The stem reads (B,T,H,W,3) uint8 frames with /255 and the TimeDistributed reshape folded into the addressing
+    (3x3 windows take the one-thread-per-pixel fast path)."""
     from multimodal_lipread_b200 import kernels as K
     from multimodal_lipread_b200.model_base import video_layout
     torch.manual_seed(0)
-    B, T, H, W, k, stride, pad = 2, 3, 10, 12, 7, 2, 3
+    B, T, H, W = 2, 3, 10, 12
     lips = torch.randint(0, 256, (B, T, H, W, 3), dtype=torch.uint8)
     x = (lips.float() / 255.0).permute(0, 1, 4, 2, 3).reshape(B * T, 3, H, W)
     ref = Fn.unfold(x, k, padding=pad, stride=stride)                       # [F, 3*k*k, L]

@@ -217,7 +217,7 @@ def test_frame_ops_and_small_kernels(K):
     assert torch.equal(dst[:, 5:25], src[:, 20:40]) and dst[:, :5].abs().sum() == 0 and dst[:, 25:].abs().sum() == 0
 
 
-@pytest.mark.parametrize("H,I,B,T", [(128, 576, 6, 29), (32, 20, 5, 4)])
+@pytest.mark.parametrize("H,I,B,T", [(128, 576, 6, 29), (32, 20, 5, 4), (256, 64, 33, 7), (128, 48, 32, 5), (512, 32, 3, 4)])
 def test_lstm_direction_kernels(K, H, I, B, T):
     """Both directions of a bidirectional nn.LSTM layer, full sequence with external gradients at every t."""
     torch.manual_seed(H)

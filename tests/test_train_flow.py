@@ -1,0 +1,52 @@
+"""Host-side train flow (no GPU): config loading, model-name dispatch and its error behaviour mirror the reference's
+train scripts (audio_video/train.py:112-127, video/train.py:189-204, audio/train.py:118-134,
+audio_cues_video/train.py:144-155, config/config.py:33-34)."""
+import pytest
+import torch
+
+
+def test_config_dotted_get_and_missing_file(tmp_path):
+    from multimodal_lipread_b200.train import Config
+    p = tmp_path / "av_config.yaml"
+    p.write_text("dataset:\n  num_classes: 40\n  audio_input_size: 117\nmodel:\n  name: middle_fusion_fast\ntraining:\n  learning_rate: 0.0003\n")
+    c = Config(str(p))
+    assert c.get("dataset.num_classes") == 40 and c.get("model.name") == "middle_fusion_fast"
+    assert c.get("model.audio_feature_dim", 128) == 128 and c.get("nope.deeper") is None
+    with pytest.raises(FileNotFoundError):
+        Config(str(tmp_path / "missing.yaml"))
+
+
+def test_model_name_dispatch_and_errors():
+    from multimodal_lipread_b200 import train as T
+    from multimodal_lipread_b200.model_base import Cfg
+    cfg = Cfg()
+    m = T.create_av_model("middle_fusion_fast", 40, cfg)
+    assert type(m).__name__ == "MidFusionFast" and len(m.state_dict()) == 256
+    assert type(T.create_av_model("early_fusion_mobilenet", 40, cfg)).__name__ == "EarlyFusionAVMobileNet"
+    assert type(T.create_av_model("early_fusion_resnet", 40, cfg)).__name__ == "EarlyFusionAV"
+    assert type(T.create_video_model("resnet_lstm", 40, cfg)).__name__ == "ResNet2DBiLSTM"
+    assert type(T.create_audio_model("resnet", 8)).__name__ == "AudioResNet"
+    assert type(T.create_acv_model("late_fusion_mobile", 40)).__name__ == "MultimodalAttentionLate"
+    with pytest.raises(ValueError, match="Unknown model name"):
+        T.create_av_model("not_a_model", 40, cfg)
+    with pytest.raises(ValueError, match="Invalid model name"):
+        T.create_audio_model("not_a_model", 8)
+    for name in ("late_fusion_fast", "middle_fusion_mobilenet"):
+        with pytest.raises(NotImplementedError):
+            T.create_av_model(name, 40, cfg)             # a reference name without a plan fails loudly
+
+
+def test_models_refuse_cpu_tensors():
+    from multimodal_lipread_b200 import train as T
+    from multimodal_lipread_b200.model_base import Cfg
+    m = T.create_av_model("middle_fusion_fast", 8, Cfg())
+    with pytest.raises(Exception):
+        m(torch.zeros(1, 80, 117), torch.zeros(1, 3, 4, 44, 44))
+
+
+def test_default_batch_adapters():
+    from multimodal_lipread_b200.train import default_batch_to_inputs
+    a, b, c = torch.zeros(2, 80, 117), torch.zeros(2, 3, 29, 44, 44), torch.zeros(2, dtype=torch.int64)
+    assert default_batch_to_inputs((a, b, c))[0] == (a, b)
+    ins, lab = default_batch_to_inputs({"lip_regions": b, "label": c})
+    assert ins == (b,) and lab is c
