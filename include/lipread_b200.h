@@ -218,6 +218,17 @@ int lr_attn_fuse_fwd(const float* stacked, const float* scores, float* weights, 
 int lr_attn_fuse_bwd(const float* stacked, const float* weights, const float* dfused, float* dstacked, float* dscores,
                      int B, int S, int C, lr_stream_t stream);
 
+/* Learnable scalar late fusion (audio_video/models/late_fusion.py:82,92; late_fusion_fast.py:34,58):
+ * out = alpha * a + (1 - alpha) * v on n floats; backward: da, dv and dalpha += sum (a - v) * dout. */
+int lr_alpha_fuse_fwd(const float* a, const float* v, const float* alpha, float* out, long long n, lr_stream_t stream);
+int lr_alpha_fuse_bwd(const float* a, const float* v, const float* alpha, const float* dout, float* da, float* dv,
+                      float* dalpha, long long n, lr_stream_t stream);
+/* Channel-major flatten of a channels-last activation -- `x.view(B, -1)` on an NCHW tensor
+ * (audio_video/models/middle_fusion.py:29): to_nchw != 0: y[b*ldy + c*HW + p] = x[(b*HW + p)*C + c]; to_nchw == 0:
+ * the inverse copy (gradient path).  Neither pointer is const: the direction flag picks the destination. */
+int lr_flatten_nchw(float* x_nhwc, float* y_nchw, long long ldy, int B, int HW, int C, int to_nchw,
+                    lr_stream_t stream);
+
 /* nn.CrossEntropyLoss(mean) forward + gradient (audio_video/train.py:129,65): loss += mean CE (caller zeroes),
  * dlogits = (softmax - onehot) * inv_n (may be NULL), correct += #(argmax == label) (may be NULL). */
 int lr_ce_loss(const float* logits, const long long* labels, float* loss, float* dlogits, int* correct, int B, int C,

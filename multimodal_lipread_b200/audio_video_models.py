@@ -113,33 +113,52 @@ class AudioEncoder(nn.Module):
         self.output_dim = feature_dim
 
 
-def audio_encoder_plan(plan, enc, mel, B, out, ldo, dout):
-    """AudioEncoder forward/backward on mel (B,80,117) viewed as a 1-channel NHWC image; writes out[b, 0:D]."""
-    if enc.cnn[0].in_channels != 1:
-        raise ValueError("AudioEncoder plan handles dataset.audio_channels == 1 (the reference default)")
-    mods = list(enc.cnn)
+def audio_cnn_plan(plan, cnn, mel, B):
+    """nn.Sequential of Conv2d(3x3, padding 1) [+ BatchNorm2d] + ReLU, MaxPool2d(2), AdaptiveAvgPool2d(1) on the mel
+    (B,80,117) viewed as a 1-channel NHWC image.  Returns ("pooled", feat, dfeat, C) after an AdaptiveAvgPool2d or
+    ("map", T2) when the Sequential ends on a feature map."""
+    mods = list(cnn)
+    if mods[0].in_channels != 1:
+        raise ValueError("audio CNN plans handle dataset.audio_channels == 1 (the reference default)")
     # (B,80,117) contiguous == NHWC with C = 1
     frames = (mel, (0, B, 1, N_MELS, N_FRAMES_OUT, N_MELS * N_FRAMES_OUT, 0, 0, N_FRAMES_OUT, 1), 1.0)
-    cur = None
+    cur, pooled = None, None
     i = 0
     while i < len(mods):
         m = mods[i]
         if isinstance(m, nn.Conv2d):
-            raw = plan.dense_conv(cur, m, frames=frames if cur is None else None)
-            if plan.with_backward:
-                plan.dense_conv_bwd(raw)
-            a = engine.T2(plan, raw.F, raw.H, raw.W, raw.C)
-            plan.bn_act(raw, mods[i + 1], ACT_RELU, a)
-            cur = a
-            i += 3
+            has_bn = isinstance(mods[i + 1], nn.BatchNorm2d)
+            if has_bn:
+                raw = plan.dense_conv(cur, m, frames=frames if cur is None else None)
+                if plan.with_backward:
+                    plan.dense_conv_bwd(raw)
+                a = engine.T2(plan, raw.F, raw.H, raw.W, raw.C)
+                plan.bn_act(raw, mods[i + 1], ACT_RELU, a)
+                cur = a
+                i += 3                                       # conv, bn, relu
+            else:
+                assert isinstance(mods[i + 1], nn.ReLU)
+                cur = plan.dense_conv(cur, m, frames=frames if cur is None else None, act=ACT_RELU, with_stats=False)
+                if plan.with_backward:
+                    plan.dense_conv_bwd(cur)
+                i += 2                                       # conv, relu
         elif isinstance(m, nn.MaxPool2d):
             cur = plan.maxpool(cur, 2, 2, 0)
             i += 1
         elif isinstance(m, nn.AdaptiveAvgPool2d):
-            pooled, dpooled = plan.avgpool(cur)
+            pooled = plan.avgpool(cur)
             i += 1
         else:
             raise NotImplementedError(type(m).__name__)
+    if pooled is not None:
+        return "pooled", pooled[0], pooled[1], cur.C
+    return "map", cur
+
+
+def audio_encoder_plan(plan, enc, mel, B, out, ldo, dout):
+    """AudioEncoder* (cnn + fc) forward/backward; writes out[b, 0:D] (row stride ldo)."""
+    kind, pooled, dpooled, _ = audio_cnn_plan(plan, enc.cnn, mel, B)
+    assert kind == "pooled"
     fc = enc.fc
     plan.linear(pooled, fc.in_features, B, fc.weight, fc.bias, out, ldo)
     if plan.with_backward:
@@ -232,3 +251,227 @@ def create_early_fusion_mobilenet_model(num_classes, config=None):
 def create_early_fusion_resnet_model(num_classes, config=None):
     """audio_video/models/ef_cnn_lstm_resnet.py:132-133."""
     return EarlyFusionAV(num_classes, config)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The remaining audio_video models (all MobileNetV3-small video trunks, single-layer BiLSTM)
+# ------------------------------------------------------------------------------------------------------------
+def _mbv3_lstm(config, hidden_default, pretrained_state_dict=None):
+    base = mobilenet_v3_small(weights=None)
+    if pretrained_state_dict is not None:
+        base.load_state_dict(pretrained_state_dict)
+    base.classifier = nn.Identity()
+    hid = config.get("video.lstm_hidden", hidden_default)
+    return base, nn.LSTM(input_size=576, hidden_size=hid, num_layers=1, batch_first=True, bidirectional=True), hid
+
+
+class _VideoEncoderLstm(nn.Module):
+    """VideoEncoderLate / VideoEncoderMid / VideoEncoderFast parameter container (cnn, lstm)."""
+
+    def __init__(self, config, hidden_default):
+        super().__init__()
+        self.cnn, self.lstm, hid = _mbv3_lstm(config, hidden_default)
+        self.output_dim = hid * 2
+
+
+class AudioEncoderLate(nn.Module):
+    """late_fusion.py:10-34."""
+
+    def __init__(self, config):
+        super().__init__()
+        cin = config.get("dataset.audio_channels", 1)
+        self.cnn = nn.Sequential(nn.Conv2d(cin, 32, 3, padding=1), nn.BatchNorm2d(32), nn.ReLU(), nn.MaxPool2d(2),
+                                 nn.Conv2d(32, 64, 3, padding=1), nn.BatchNorm2d(64), nn.ReLU(), nn.AdaptiveAvgPool2d((1, 1)))
+        self.fc = nn.Linear(64, config.get("model.audio_feature_dim", 256))
+        self.output_dim = config.get("model.audio_feature_dim", 256)
+
+
+class AudioEncoderMid(nn.Module):
+    """middle_fusion.py:11-30: ends on the (64, 20, 29) feature map, flattened channel-major."""
+
+    def __init__(self, config):
+        super().__init__()
+        cin = config.get("dataset.audio_channels", 1)
+        self.cnn = nn.Sequential(nn.Conv2d(cin, 32, kernel_size=3, padding=1), nn.BatchNorm2d(32), nn.ReLU(), nn.MaxPool2d(2),
+                                 nn.Conv2d(32, 64, kernel_size=3, padding=1), nn.BatchNorm2d(64), nn.ReLU(), nn.MaxPool2d(2))
+        self.output_dim = 64 * 20 * 29
+
+
+class AudioEncoderFast(nn.Module):
+    """early_fusion_fast.py:6-25."""
+
+    def __init__(self, config):
+        super().__init__()
+        cin = config.get("dataset.audio_channels", 1)
+        self.cnn = nn.Sequential(nn.Conv2d(cin, 16, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2),
+                                 nn.Conv2d(16, 32, 3, padding=1), nn.ReLU(), nn.AdaptiveAvgPool2d((1, 1)))
+        self.fc = nn.Linear(32, config.get("model.audio_feature_dim", 128))
+        self.output_dim = config.get("model.audio_feature_dim", 128)
+
+
+class _AlphaLatePlan(ModelPlan):
+    """fused = alpha * audio_logits + (1 - alpha) * video_logits (late_fusion.py:88-93, late_fusion_fast.py:36-59)."""
+
+    def build(self, m, spec):
+        B, wb, C = self.B, self.with_backward, self.num_classes
+        video, layout, scale = self.video_input()
+        T, H, W = layout[2], layout[3], layout[4]
+        mel = self.audio_input()
+        cnn, fc, acls, vcnn, vlstm, vcls = m._parts()
+        DA = fc.out_features
+        a_feat = self.alloc(B * DA)
+        da_feat = self.alloc(B * DA) if wb else None
+        kind, pooled, dpooled, _ = audio_cnn_plan(self, cnn, mel, B)
+        self.linear(pooled, fc.in_features, B, fc.weight, fc.bias, a_feat, DA)
+        if wb:
+            self.linear_bwd(self.bgroup(), pooled, fc.in_features, B, fc.weight, fc.bias, da_feat, DA, dx=dpooled,
+                            ldx=fc.in_features)
+        a_log = self.alloc(B * C)
+        da_log = self.alloc(B * C) if wb else None
+        self.linear(a_feat, DA, B, acls.weight, acls.bias, a_log, C)
+        if wb:
+            self.linear_bwd(self.bgroup(), a_feat, DA, B, acls.weight, acls.bias, da_log, C, dx=da_feat, ldx=DA)
+        last = self.mbv3_features(vcnn.features, video, layout, scale, B, T, H, W)
+        feat, dfeat = self.avgpool(last)
+        DV = 2 * vlstm.hidden_size
+        v_feat = self.alloc(B * DV)
+        dv_feat = self.alloc(B * DV) if wb else None
+        self.bilstm_hn(feat, dfeat, last.C, B, T, vlstm, v_feat, DV, dv_feat if wb else 0)
+        v_log = self.alloc(B * C)
+        dv_log = self.alloc(B * C) if wb else None
+        self.linear(v_feat, DV, B, vcls.weight, vcls.bias, v_log, C)
+        if wb:
+            self.linear_bwd(self.bgroup(), v_feat, DV, B, vcls.weight, vcls.bias, dv_log, C, dx=dv_feat, ldx=DV)
+        fused = self.alloc(B * C)
+        dfused = self.alloc(B * C) if wb else None
+        self.fwd.add("lr_alpha_fuse_fwd", a_log, v_log, m.alpha, fused, B * C)
+        if wb:
+            self.bgroup().add("lr_alpha_fuse_bwd", a_log, v_log, m.alpha, dfused, da_log, dv_log, self.flat.g(m.alpha), B * C)
+        self.set_logits(fused, dfused)
+
+
+class LateFusionAVMobileNet(PlanModel):
+    """audio_video/models/late_fusion.py:70-93."""
+    PLAN = _AlphaLatePlan
+
+    def __init__(self, num_classes, config=None, precision=None):
+        super().__init__()
+        config = config or Cfg()
+        self._init_base(num_classes, config, precision)
+        self.audio_encoder = AudioEncoderLate(config)
+        self.video_encoder = _VideoEncoderLstm(config, 256)
+        self.audio_classifier = nn.Linear(self.audio_encoder.output_dim, num_classes)
+        self.video_classifier = nn.Linear(self.video_encoder.output_dim, num_classes)
+        self.alpha = nn.Parameter(torch.tensor(0.5))
+
+    def _parts(self):
+        return (self.audio_encoder.cnn, self.audio_encoder.fc, self.audio_classifier, self.video_encoder.cnn,
+                self.video_encoder.lstm, self.video_classifier)
+
+
+class LateFusionFast(PlanModel):
+    """audio_video/models/late_fusion_fast.py:5-59."""
+    PLAN = _AlphaLatePlan
+
+    def __init__(self, num_classes, config=None, precision=None):
+        super().__init__()
+        config = config or Cfg()
+        self._init_base(num_classes, config, precision)
+        cin = config.get("dataset.audio_channels", 1)
+        self.audio_cnn = nn.Sequential(nn.Conv2d(cin, 16, 3, padding=1), nn.ReLU(), nn.AdaptiveAvgPool2d((1, 1)))
+        self.audio_fc = nn.Linear(16, config.get("model.audio_feature_dim", 128))
+        self.audio_classifier = nn.Linear(config.get("model.audio_feature_dim", 128), num_classes)
+        base = mobilenet_v3_small(weights=None)
+        base.classifier = nn.Identity()
+        self.video_cnn = base
+        self.video_lstm = nn.LSTM(input_size=576, hidden_size=128, num_layers=1, batch_first=True, bidirectional=True)
+        self.video_classifier = nn.Linear(128 * 2, num_classes)
+        self.alpha = nn.Parameter(torch.tensor(0.5))
+
+    def _parts(self):
+        return self.audio_cnn, self.audio_fc, self.audio_classifier, self.video_cnn, self.video_lstm, self.video_classifier
+
+
+class _ConcatFusionPlan(ModelPlan):
+    """fused = [audio features | video features] -> classifier (middle_fusion.py:72-85, early_fusion_fast.py:63-76)."""
+
+    def build(self, m, spec):
+        B, wb = self.B, self.with_backward
+        video, layout, scale = self.video_input()
+        T, H, W = layout[2], layout[3], layout[4]
+        mel = self.audio_input()
+        ae, ve = m.audio_encoder, m.video_encoder
+        DA, DV = ae.output_dim, ve.output_dim
+        FD = DA + DV
+        fused = self.alloc(B * FD)
+        dfused = self.alloc(B * FD) if wb else None
+        if hasattr(ae, "fc"):
+            audio_encoder_plan(self, ae, mel, B, fused, FD, dfused)
+        else:
+            kind, fmap = audio_cnn_plan(self, ae.cnn, mel, B)
+            assert kind == "map" and fmap.H * fmap.W * fmap.C == DA
+            # x.view(B, -1) of the NCHW map: channel-major flatten straight into the fused row
+            self.fwd.add("lr_flatten_nchw", fmap.val, fused, FD, B, fmap.H * fmap.W, fmap.C, 1)
+            if wb:
+                self.bgroup().add("lr_flatten_nchw", fmap.grad, dfused, FD, B, fmap.H * fmap.W, fmap.C, 0)
+        last = self.mbv3_features(ve.cnn.features, video, layout, scale, B, T, H, W)
+        feat, dfeat = self.avgpool(last)
+        vptr = fused.data_ptr() + 4 * DA
+        dvptr = (dfused.data_ptr() + 4 * DA) if wb else 0
+        if m.head == "hn":
+            self.bilstm_hn(feat, dfeat, last.C, B, T, ve.lstm, vptr, FD, dvptr)
+        else:
+            self.bilstm_last(feat, dfeat, last.C, B, T, ve.lstm, vptr, FD, dvptr)
+        logits, dlogits = self.mlp(fused, dfused, B, m.classifier)
+        self.set_logits(logits, dlogits)
+
+
+class MidFusionAVMobileNet(PlanModel):
+    """audio_video/models/middle_fusion.py:66-85 (video head: feats[:, -1])."""
+    PLAN = _ConcatFusionPlan
+    head = "last"
+
+    def __init__(self, num_classes, config=None, precision=None):
+        super().__init__()
+        config = config or Cfg()
+        self._init_base(num_classes, config, precision)
+        self.audio_encoder = AudioEncoderMid(config)
+        self.video_encoder = _VideoEncoderLstm(config, 256)
+        fusion_dim = self.audio_encoder.output_dim + self.video_encoder.output_dim
+        self.classifier = nn.Sequential(nn.Linear(fusion_dim, 512), nn.ReLU(),
+                                        nn.Dropout(config.get("model.classifier_dropout", 0.3)), nn.Linear(512, num_classes))
+
+
+class EarlyFusionFast(PlanModel):
+    """audio_video/models/early_fusion_fast.py:57-76 (video head: cat(h_n[0], h_n[1]))."""
+    PLAN = _ConcatFusionPlan
+    head = "hn"
+
+    def __init__(self, num_classes, config=None, precision=None):
+        super().__init__()
+        config = config or Cfg()
+        self._init_base(num_classes, config, precision)
+        self.audio_encoder = AudioEncoderFast(config)
+        self.video_encoder = _VideoEncoderLstm(config, 128)
+        fusion_dim = self.audio_encoder.output_dim + self.video_encoder.output_dim
+        self.classifier = nn.Sequential(nn.Linear(fusion_dim, 256), nn.ReLU(), nn.Linear(256, num_classes))
+
+
+def create_late_fusion_mobilenet_model(num_classes, config=None):
+    """audio_video/models/late_fusion.py:98-99."""
+    return LateFusionAVMobileNet(num_classes, config)
+
+
+def create_mid_fusion_mobilenet_model(num_classes, config=None):
+    """audio_video/models/middle_fusion.py:91-92."""
+    return MidFusionAVMobileNet(num_classes, config)
+
+
+def create_early_fusion_fast(num_classes, config=None):
+    """audio_video/models/early_fusion_fast.py:79-80."""
+    return EarlyFusionFast(num_classes, config)
+
+
+def create_late_fusion_fast(num_classes, config=None):
+    """audio_video/models/late_fusion_fast.py:62-63."""
+    return LateFusionFast(num_classes, config)

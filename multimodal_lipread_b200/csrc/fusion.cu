@@ -86,3 +86,103 @@ extern "C" int lr_attn_fuse_bwd(const float* stacked, const float* weights, cons
     LR_CHECK_LAUNCH("attn_fuse_bwd_kernel");
     return LR_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Learnable scalar late fusion (audio_video/models/late_fusion.py:82,92, late_fusion_fast.py:34,58):
+//   fused = alpha * a + (1 - alpha) * v
+// and the channel-major flatten of a channels-last activation (x.view(B, -1) on an NCHW tensor,
+// audio_video/models/middle_fusion.py:29): y[b, c*HW + p] = x[b, p, c].
+namespace fu {
+
+__global__ void __launch_bounds__(256)
+alpha_fuse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ v, const float* __restrict__ alpha,
+                      float* __restrict__ out, long long n) {
+    const float al = *alpha;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        out[i] = al * a[i] + (1.f - al) * v[i];
+}
+
+// one block: da = alpha * dout, dv = (1 - alpha) * dout, dalpha += sum (a - v) * dout
+__global__ void __launch_bounds__(256)
+alpha_fuse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ v, const float* __restrict__ alpha,
+                      const float* __restrict__ dout, float* __restrict__ da, float* __restrict__ dv,
+                      float* __restrict__ dalpha, long long n) {
+    __shared__ float red[8];
+    const float al = *alpha;
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < n; i += 256) {
+        const float g = dout[i];
+        da[i] = al * g;
+        dv[i] = (1.f - al) * g;
+        s = fmaf(a[i] - v[i], g, s);
+    }
+    s = lr::warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        *dalpha += t;
+    }
+}
+
+// to_nchw != 0: y[b*ldy + c*HW + p] = x[(b*HW + p)*C + c];  else the inverse (x[(b*HW + p)*C + c] = y[b*ldy + c*HW + p])
+__global__ void __launch_bounds__(256)
+flatten_kernel(float* __restrict__ x, float* __restrict__ y, long long ldy, int B, int HW, int C, int to_nchw) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    float* xb = x + (long long)b * HW * C;
+    float* yb = y + (long long)b * ldy;
+    if (to_nchw) {
+        for (int i = ty; i < 32; i += 8)
+            if (p0 + i < HW && c0 + tx < C) tile[i][tx] = xb[(long long)(p0 + i) * C + c0 + tx];
+        __syncthreads();
+        for (int i = ty; i < 32; i += 8)
+            if (c0 + i < C && p0 + tx < HW) yb[(long long)(c0 + i) * HW + p0 + tx] = tile[tx][i];
+    } else {
+        for (int i = ty; i < 32; i += 8)
+            if (c0 + i < C && p0 + tx < HW) tile[tx][i] = yb[(long long)(c0 + i) * HW + p0 + tx];
+        __syncthreads();
+        for (int i = ty; i < 32; i += 8)
+            if (p0 + i < HW && c0 + tx < C) xb[(long long)(p0 + i) * C + c0 + tx] = tile[i][tx];
+    }
+}
+
+}  // namespace fu
+
+extern "C" int lr_alpha_fuse_fwd(const float* a, const float* v, const float* alpha, float* out, long long n,
+                                 lr_stream_t stream) {
+    LR_CHECK_ARG(n >= 0, "lr_alpha_fuse_fwd: negative size");
+    if (n == 0) return LR_OK;
+    LR_CHECK_ARG(a && v && alpha && out, "lr_alpha_fuse_fwd: null pointer");
+    long long g = (n + 255) / 256;
+    if (g > 1024) g = 1024;
+    fu::alpha_fuse_fwd_kernel<<<(unsigned)g, 256, 0, stream>>>(a, v, alpha, out, n);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("alpha_fuse_fwd_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_alpha_fuse_bwd(const float* a, const float* v, const float* alpha, const float* dout, float* da,
+                                 float* dv, float* dalpha, long long n, lr_stream_t stream) {
+    LR_CHECK_ARG(n >= 0, "lr_alpha_fuse_bwd: negative size");
+    if (n == 0) return LR_OK;
+    LR_CHECK_ARG(a && v && alpha && dout && da && dv && dalpha, "lr_alpha_fuse_bwd: null pointer");
+    fu::alpha_fuse_bwd_kernel<<<1, 256, 0, stream>>>(a, v, alpha, dout, da, dv, dalpha, n);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("alpha_fuse_bwd_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_flatten_nchw(float* x_nhwc, float* y_nchw, long long ldy, int B, int HW, int C, int to_nchw,
+                               lr_stream_t stream) {
+    LR_CHECK_ARG(B >= 0 && HW > 0 && C > 0 && ldy >= (long long)HW * C, "lr_flatten_nchw: bad shape");
+    if (B == 0) return LR_OK;
+    LR_CHECK_ARG(x_nhwc && y_nchw, "lr_flatten_nchw: null pointer");
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
+    fu::flatten_kernel<<<grid, 256, 0, stream>>>(x_nhwc, y_nchw, ldy, B, HW, C, to_nchw);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("flatten_kernel");
+    return LR_OK;
+}

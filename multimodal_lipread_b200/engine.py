@@ -503,7 +503,7 @@ class Plan:
         return feat, dfeat
 
     # ---- dense convolutions (ResNet-18, AudioEncoder, MobileNetV2 stem) ----------------------------------
-    def dense_conv(self, x, conv, frames=None, need_dx=True):
+    def dense_conv(self, x, conv, frames=None, need_dx=True, act=ACT_NONE, with_stats=True):
         """nn.Conv2d with groups == 1 on a channels-last T2 (or, for a stem, on the raw frames in the caller's
         layout: frames = (tensor, (is_u8, B, T, H, W, sb, st, sc, sh, sw), scale)) as im2col + GEMM.  Returns the
         raw output T2 (BatchNorm statistic slot attached).  The backward group is reserved here (its position fixes
@@ -540,10 +540,13 @@ class Plan:
         else:
             wmat = conv.weight
         y = T2(self, F, Ho, Wo, Cout)
-        y.stat_slot = self.stat_slot(Cout)
-        stt_ = (lambda s=y.stat_slot: s["fwd"]) if self.training else 0
+        stt_ = 0
+        if with_stats:
+            y.stat_slot = self.stat_slot(Cout)
+            stt_ = (lambda s=y.stat_slot: s["fwd"]) if self.training else 0
+        y._act = act
         self.gemm_auto(self.fwd, col, ldk, 0, wmat, ldk, 0, y.val, Cout, rows, Cout, ldk,
-                       bias=(conv.bias if conv.bias is not None else 0), stats=stt_)
+                       bias=(conv.bias if conv.bias is not None else 0), act=act, stats=stt_)
         if self.with_backward:
             g = self.bgroup()
             y._conv_bwd = (g, x, conv, col, ldk, wmat, src, (F, Hs, Ws, Ho, Wo), need_dx and frames is None)
@@ -559,6 +562,8 @@ class Plan:
         K = Cin * kh * kw
         rows = F * Ho * Wo
         dw = self.flat.g(conv.weight)
+        if getattr(y, "_act", ACT_NONE) != ACT_NONE:          # fused activation: dy *= act'(y) first
+            g.add("lr_act_bwd", y.grad, y.val, rows * Cout, y._act)
         if ldk != K:
             dwp = self.alloc(Cout * ldk)
             g.add("lr_memset", dwp, Cout * ldk * 4, leaf=True)
@@ -675,6 +680,39 @@ class Plan:
             dcur_last = (dcur if isinstance(dcur, int) else dcur.data_ptr()) + 4 * (T - 1) * Icur
             self.linear_bwd(g, cur_last, T * Icur, B, par("weight_ih", l, 1), par("bias_ih", l, 1), dg_r, G4,
                             dx=dcur_last, ldx=T * Icur, dx_residual=dcur_last, ldr=T * Icur)
+
+    def bilstm_hn(self, x, dx, I, B, T, lstm, out, ldo, dout):
+        """Single-layer bidirectional nn.LSTM whose head is cat(h_n[0], h_n[1]) (audio_video/models/late_fusion.py:61-62,
+        early_fusion_fast.py:53-54): BOTH directions walk all T steps; h_n[0] = forward output at t = T-1, h_n[1] =
+        reverse output at t = 0.  Writes out[b, 0:2H] (row stride ldo); dout is the gradient of that row."""
+        assert lstm.bidirectional and lstm.batch_first and lstm.num_layers == 1
+        H = lstm.hidden_size
+        F, G4 = B * T, 4 * H
+
+        def par(name, rev):
+            return getattr(lstm, f"{name}_l0{'_reverse' if rev else ''}")
+
+        optr = out if isinstance(out, int) else out.data_ptr()
+        saved = []
+        for rev in (0, 1):
+            xp, hs = self.alloc(F * G4), self.alloc(F * H)
+            gates, cst, hp = self.alloc(F * G4), self.alloc(F * H), self.alloc(F * H)
+            self.linear(x, I, F, par("weight_ih", rev), par("bias_ih", rev), xp, G4)
+            self.fwd.add("lr_lstm_fwd", xp, G4, par("bias_hh", rev), par("weight_hh", rev), hs, H, gates, cst, hp,
+                         B, T, H, T, rev)
+            t_final = 0 if rev else T - 1
+            self.fwd.add("lr_copy2d", optr + 4 * H * rev, ldo, hs.data_ptr() + 4 * t_final * H, T * H, B, H)
+            saved.append((gates, cst, hp, t_final))
+        if self.with_backward:
+            dptr = dout if isinstance(dout, int) else dout.data_ptr()
+            g = self.bgroup()
+            for rev in (0, 1):
+                gates, cst, hp, t_final = saved[rev]
+                dg = self.alloc(F * G4)
+                g.add("lr_lstm_bwd", dptr + 4 * H * rev, ldo, t_final, gates, cst, par("weight_hh", rev), dg, B, T, H, T, rev)
+                self.linear_bwd(g, hp, H, F, par("weight_hh", rev), par("bias_hh", rev), dg, G4)
+                self.linear_bwd(g, x, I, F, par("weight_ih", rev), par("bias_ih", rev), dg, G4, dx=dx, ldx=I,
+                                dx_residual=(dx if rev else 0), ldr=I)
 
     # ---- torchvision ResNet (BasicBlock) -------------------------------------------------------------------
     def resnet_features(self, net, frames, need_input_grad=False):

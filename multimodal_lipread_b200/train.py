@@ -53,8 +53,14 @@ def create_av_model(model_name, num_classes, config):
         return M.create_early_fusion_mobilenet_model(num_classes, config)
     if model_name == "middle_fusion_fast":
         return M.create_mid_fusion_fast(num_classes, config)
-    if model_name in AV_MODELS:
-        _no_plan(model_name)
+    if model_name == "late_fusion_mobilenet":
+        return M.create_late_fusion_mobilenet_model(num_classes, config)
+    if model_name == "middle_fusion_mobilenet":
+        return M.create_mid_fusion_mobilenet_model(num_classes, config)
+    if model_name == "early_fusion_fast":
+        return M.create_early_fusion_fast(num_classes, config)
+    if model_name == "late_fusion_fast":
+        return M.create_late_fusion_fast(num_classes, config)
     raise ValueError(f"Unknown model name: {model_name}")
 
 

@@ -13,6 +13,10 @@ there is no network for the ImageNet checkpoint:
   ResNet2DBiLSTMOracle        video/models/resnet_lstm.py:56-156
   AudioResNetOracle           audio/models/resnet_model.py:5-39
   LateFusionMobileOracle      audio_cues_video/models/late_fusion_mobile.py:6-107
+  LateFusionAVMobileNetOracle audio_video/models/late_fusion.py:10-93
+  MidFusionAVMobileNetOracle  audio_video/models/middle_fusion.py:11-85
+  EarlyFusionFastOracle       audio_video/models/early_fusion_fast.py:6-76
+  LateFusionFastOracle        audio_video/models/late_fusion_fast.py:5-59
 
 ``tests/golden/make_golden.py`` imports the *real* reference modules in the build container and
 records their outputs; ``tests/test_oracle_golden.py`` pins these restatements to them.
@@ -252,6 +256,125 @@ class LateFusionMobileOracle(nn.Module):
         v = self.vfc(self.video(lip))
         fused, _ = self.attn([a, c, v])
         return fused
+
+
+class _VideoLstm(nn.Module):
+    """MobileNetV3-small + single-layer BiLSTM video encoder; head "hn": cat(h_n[0], h_n[1]) (late_fusion.py:54-62,
+    early_fusion_fast.py:44-54); head "last": out[:, -1] (middle_fusion.py:50-57)."""
+
+    def __init__(self, hidden, head):
+        super().__init__()
+        self.cnn = _trunk()
+        self.lstm = nn.LSTM(576, hidden, 1, batch_first=True, bidirectional=True)
+        self.output_dim, self.head = 2 * hidden, head
+
+    def forward(self, x):
+        frames, b, t = _frames(x)
+        seq, (h_n, _) = self.lstm(self.cnn(frames).view(b, t, -1))
+        return torch.cat([h_n[0], h_n[1]], dim=1) if self.head == "hn" else seq[:, -1]
+
+
+class _AudioCnnFc(nn.Module):
+    def __init__(self, cnn, fc_in, dim):
+        super().__init__()
+        self.cnn = cnn
+        self.fc = nn.Linear(fc_in, dim)
+        self.output_dim = dim
+
+    def forward(self, x):
+        if x.dim() == 3:
+            x = x.unsqueeze(1)
+        return self.fc(self.cnn(x).flatten(1))
+
+
+class LateFusionAVMobileNetOracle(nn.Module):
+    """audio_video/models/late_fusion.py:10-93."""
+
+    def __init__(self, num_classes, config=None):
+        super().__init__()
+        config = config or DictConfig()
+        cin = config.get("dataset.audio_channels", 1)
+        cnn = nn.Sequential(nn.Conv2d(cin, 32, 3, padding=1), nn.BatchNorm2d(32), nn.ReLU(), nn.MaxPool2d(2),
+                            nn.Conv2d(32, 64, 3, padding=1), nn.BatchNorm2d(64), nn.ReLU(), nn.AdaptiveAvgPool2d((1, 1)))
+        self.audio_encoder = _AudioCnnFc(cnn, 64, config.get("model.audio_feature_dim", 256))
+        self.video_encoder = _VideoLstm(config.get("video.lstm_hidden", 256), "hn")
+        self.audio_classifier = nn.Linear(self.audio_encoder.output_dim, num_classes)
+        self.video_classifier = nn.Linear(self.video_encoder.output_dim, num_classes)
+        self.alpha = nn.Parameter(torch.tensor(0.5))
+
+    def forward(self, audio, video):
+        a = self.audio_classifier(self.audio_encoder(audio))
+        v = self.video_classifier(self.video_encoder(video))
+        return self.alpha * a + (1 - self.alpha) * v
+
+
+class MidFusionAVMobileNetOracle(nn.Module):
+    """audio_video/models/middle_fusion.py:11-85 (head dropout passed in; the audio map is flattened channel-major)."""
+
+    class _Audio(nn.Module):
+        def __init__(self, cin):
+            super().__init__()
+            self.cnn = nn.Sequential(nn.Conv2d(cin, 32, kernel_size=3, padding=1), nn.BatchNorm2d(32), nn.ReLU(), nn.MaxPool2d(2),
+                                     nn.Conv2d(32, 64, kernel_size=3, padding=1), nn.BatchNorm2d(64), nn.ReLU(), nn.MaxPool2d(2))
+            self.output_dim = 64 * 20 * 29
+
+        def forward(self, x):
+            return self.cnn(x).flatten(1)
+
+    def __init__(self, num_classes, config=None, head_dropout=0.3):
+        super().__init__()
+        config = config or DictConfig()
+        self.audio_encoder = self._Audio(config.get("dataset.audio_channels", 1))
+        self.video_encoder = _VideoLstm(config.get("video.lstm_hidden", 256), "last")
+        dim = self.audio_encoder.output_dim + self.video_encoder.output_dim
+        self.classifier = nn.Sequential(nn.Linear(dim, 512), nn.ReLU(), nn.Dropout(head_dropout), nn.Linear(512, num_classes))
+
+    def forward(self, audio, video):
+        return self.classifier(torch.cat([self.audio_encoder(audio.unsqueeze(1)), self.video_encoder(video)], dim=1))
+
+
+class EarlyFusionFastOracle(nn.Module):
+    """audio_video/models/early_fusion_fast.py:6-76."""
+
+    def __init__(self, num_classes, config=None):
+        super().__init__()
+        config = config or DictConfig()
+        cin = config.get("dataset.audio_channels", 1)
+        cnn = nn.Sequential(nn.Conv2d(cin, 16, 3, padding=1), nn.ReLU(), nn.MaxPool2d(2),
+                            nn.Conv2d(16, 32, 3, padding=1), nn.ReLU(), nn.AdaptiveAvgPool2d((1, 1)))
+        self.audio_encoder = _AudioCnnFc(cnn, 32, config.get("model.audio_feature_dim", 128))
+        self.video_encoder = _VideoLstm(config.get("video.lstm_hidden", 128), "hn")
+        dim = self.audio_encoder.output_dim + self.video_encoder.output_dim
+        self.classifier = nn.Sequential(nn.Linear(dim, 256), nn.ReLU(), nn.Linear(256, num_classes))
+
+    def forward(self, audio, video):
+        return self.classifier(torch.cat([self.audio_encoder(audio), self.video_encoder(video)], dim=1))
+
+
+class LateFusionFastOracle(nn.Module):
+    """audio_video/models/late_fusion_fast.py:5-59."""
+
+    def __init__(self, num_classes, config=None):
+        super().__init__()
+        config = config or DictConfig()
+        cin = config.get("dataset.audio_channels", 1)
+        dim = config.get("model.audio_feature_dim", 128)
+        self.audio_cnn = nn.Sequential(nn.Conv2d(cin, 16, 3, padding=1), nn.ReLU(), nn.AdaptiveAvgPool2d((1, 1)))
+        self.audio_fc = nn.Linear(16, dim)
+        self.audio_classifier = nn.Linear(dim, num_classes)
+        self.video_cnn = _trunk()
+        self.video_lstm = nn.LSTM(576, 128, 1, batch_first=True, bidirectional=True)
+        self.video_classifier = nn.Linear(256, num_classes)
+        self.alpha = nn.Parameter(torch.tensor(0.5))
+
+    def forward(self, audio, video):
+        if audio.dim() == 3:
+            audio = audio.unsqueeze(1)
+        a = self.audio_classifier(self.audio_fc(self.audio_cnn(audio).flatten(1)))
+        frames, b, t = _frames(video)
+        _, (h_n, _) = self.video_lstm(self.video_cnn(frames).view(b, t, -1))
+        v = self.video_classifier(torch.cat([h_n[0], h_n[1]], dim=1))
+        return self.alpha * a + (1 - self.alpha) * v
 
 
 def train_step_generic(model, optimizer, inputs, labels):

@@ -202,6 +202,19 @@ def golden_models():
     mel, video, labels = data(B, size, T, C)
     cue = synthetic.make_cues(B)
     record("acv_late_fusion_mobile", model, (mel, cue, video), labels, 1e-5, 0.0, B, T, size)
+    # the remaining audio_video models (av_config.yaml:10), lr 3e-4
+    B, T, size, C = 3, 8, 44, 40
+    for name, module, factory, drop in (("late_fusion_mobilenet", "models.late_fusion", "create_late_fusion_mobilenet_model", False),
+                                        ("middle_fusion_mobilenet", "models.middle_fusion", "create_mid_fusion_mobilenet_model", True),
+                                        ("early_fusion_fast", "models.early_fusion_fast", "create_early_fusion_fast", False),
+                                        ("late_fusion_fast", "models.late_fusion_fast", "create_late_fusion_fast", False)):
+        mod = load_ref("audio_video", module)
+        torch.manual_seed(0)
+        model = getattr(mod, factory)(C, Cfg())
+        if drop:
+            model.classifier[2].p = 0.0
+        mel, video, labels = data(B, size, T, C)
+        record(name, model, (mel, video), labels, 3e-4, 0.0, B, T, size)
     np.savez_compressed(os.path.join(HERE, "models_golden.npz"), **out)
 
 

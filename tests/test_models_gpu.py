@@ -18,8 +18,15 @@ pytestmark = pytest.mark.gpu
 
 # A bias added right before a train-mode BatchNorm has an exactly-zero gradient in exact arithmetic: both
 # implementations produce only summation round-off there (~1e-7 .. 1e-6), so those are checked for smallness.
-ZERO_GRAD = ("audio_encoder.cnn.0.bias", "audio_encoder.cnn.4.bias", "audio_encoder.cnn.8.bias", "resnet.fc.0.bias",
-             "cue.net.0.bias")
+ZERO_GRAD_BN = ("audio_encoder.cnn.0.bias", "audio_encoder.cnn.4.bias", "audio_encoder.cnn.8.bias", "resnet.fc.0.bias",
+                "cue.net.0.bias")
+ZERO_GRAD = ZERO_GRAD_BN
+
+
+def _set_zero_grad(name):
+    """early_fusion_fast's audio convs have no BatchNorm behind them: their bias gradients are real."""
+    global ZERO_GRAD
+    ZERO_GRAD = () if name in ("early_fusion_fast", "late_fusion_fast") else ZERO_GRAD_BN
 NO_DROP = {"video.lstm_dropout": 0.0, "model.classifier_dropout": 0.0, "model.dropout": 0.0}
 GRAD_FLOOR = 1e-7
 
@@ -98,6 +105,7 @@ def _case(name, precision="fp32"):
     from multimodal_lipread_b200 import audio_cues_video_models as ACV, audio_models, audio_video_models as AV, video_models
     from multimodal_lipread_b200.model_base import Cfg
     cfg = Cfg(NO_DROP)
+    _set_zero_grad(name)
     C = 8 if name == "audio_resnet" else 40
     torch.manual_seed(0)
     if name == "early_fusion_mobilenet":
@@ -110,6 +118,14 @@ def _case(name, precision="fp32"):
         ref = O.AudioResNetOracle(C, dropout_rate=0.0)
     elif name == "acv_late_fusion_mobile":
         ref = O.LateFusionMobileOracle(C, lstm_dropout=0.0)
+    elif name == "late_fusion_mobilenet":
+        ref = O.LateFusionAVMobileNetOracle(C)
+    elif name == "middle_fusion_mobilenet":
+        ref = O.MidFusionAVMobileNetOracle(C, head_dropout=0.0)
+    elif name == "early_fusion_fast":
+        ref = O.EarlyFusionFastOracle(C)
+    elif name == "late_fusion_fast":
+        ref = O.LateFusionFastOracle(C)
     torch.manual_seed(0)
     if name == "early_fusion_mobilenet":
         ours = AV.EarlyFusionAVMobileNet(C, cfg, precision=precision)
@@ -121,6 +137,14 @@ def _case(name, precision="fp32"):
         ours = audio_models.AudioResNet(C, dropout_rate=0.0, precision=precision)
     elif name == "acv_late_fusion_mobile":
         ours = ACV.MultimodalAttentionLate(C, lstm_dropout=0.0, precision=precision)
+    elif name == "late_fusion_mobilenet":
+        ours = AV.LateFusionAVMobileNet(C, cfg, precision=precision)
+    elif name == "middle_fusion_mobilenet":
+        ours = AV.MidFusionAVMobileNet(C, cfg, precision=precision)
+    elif name == "early_fusion_fast":
+        ours = AV.EarlyFusionFast(C, cfg, precision=precision)
+    elif name == "late_fusion_fast":
+        ours = AV.LateFusionFast(C, cfg, precision=precision)
     sd_ref, sd = ref.state_dict(), ours.state_dict()
     assert list(sd_ref.keys()) == list(sd.keys())
     for k in sd:
@@ -130,7 +154,7 @@ def _case(name, precision="fp32"):
 
 def _inputs_for(name, mel, lips):
     video = lips_u8_to_model_input(lips)
-    if name.startswith("early_fusion"):
+    if name.startswith("early_fusion") or name in ("late_fusion_mobilenet", "middle_fusion_mobilenet", "late_fusion_fast"):
         return (mel, video), (mel.cuda(), lips.cuda())
     if name == "video_resnet_lstm":
         return (video,), (lips.cuda(),)
@@ -151,6 +175,10 @@ def _inputs_for(name, mel, lips):
     ("video_resnet_lstm", 2, 3, 88),
     ("audio_resnet", 4, 1, 44),
     ("acv_late_fusion_mobile", 3, 6, 44),
+    ("late_fusion_mobilenet", 3, 8, 44),
+    ("middle_fusion_mobilenet", 3, 8, 44),
+    ("early_fusion_fast", 3, 8, 44),
+    ("late_fusion_fast", 3, 8, 44),
 ])
 def test_train_step_matches_oracle(cuda_device, name, B, T, size):
     ref, ours, C = _case(name)
@@ -202,7 +230,8 @@ def test_train_step_matches_oracle(cuda_device, name, B, T, size):
     assert _rel(out, out_ref) <= 5e-3, _rel(out, out_ref)          # weights moved by the two (slightly different) Adam steps
 
 
-@pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile"])
+@pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile",
+                                  "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast"])
 def test_golden_vectors_of_the_reference(cuda_device, golden_dir, name):
     """Outputs recorded from the reference's own modules (tests/golden/make_golden.py, dropout set to 0)."""
     mg = np.load(os.path.join(golden_dir, "models_golden.npz"))

@@ -31,9 +31,11 @@ def test_model_name_dispatch_and_errors():
         T.create_av_model("not_a_model", 40, cfg)
     with pytest.raises(ValueError, match="Invalid model name"):
         T.create_audio_model("not_a_model", 8)
-    for name in ("late_fusion_fast", "middle_fusion_mobilenet"):
+    for name in T.AV_MODELS:                             # every audio_video model name of av_config.yaml:10 has a plan
+        assert T.create_av_model(name, 40, cfg).num_classes == 40
+    for name in ("vgg_lstm", "resnet_trans"):
         with pytest.raises(NotImplementedError):
-            T.create_av_model(name, 40, cfg)             # a reference name without a plan fails loudly
+            T.create_video_model(name, 40, cfg)          # a reference name without a plan fails loudly
 
 
 def test_models_refuse_cpu_tensors():
