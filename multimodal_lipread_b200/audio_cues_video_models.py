@@ -1,6 +1,7 @@
 """Audio + cue + video triple-fusion models behind the reference's nn.Module surface (audio_cues_video/models/*.py).
 
-  MultimodalAttentionLate      audio_cues_video/models/late_fusion_mobile.py:6-107   (train.model_name == "late_fusion_mobile")
+  MultimodalAttentionLate        audio_cues_video/models/late_fusion_mobile.py:6-107   (train.model_name == "late_fusion_mobile")
+  MultimodalAttentionLateResNet  audio_cues_video/models/late_fusion_resnet.py:6-99    (train.model_name == "late_fusion_resnet")
 
 forward(mel (B,80,117), cue (B,768), lip (B,3,T,H,W) [or uint8 (B,T,H,W,3)]) -> (B, num_classes).
 Sub-modules are parameter containers (reference names / construction order / state_dict keys)."""
@@ -93,7 +94,9 @@ class LateFusionPlan(ModelPlan):
                             net[3].out_features, dx=dh, ldx=net[3].in_features)
         head(c_out, c_dout, m.cfc, 1)
         # ---- video: MobileNetV2 + 2-layer BiLSTM, out[:, -1] -> vfc
-        v_last = self.mbv2_features(m.video.cnn[0], (video, layout, scale))
+        trunk = m.video.cnn[0]
+        v_last = (self.resnet_features(trunk, (video, layout, scale)) if hasattr(trunk, "conv1")
+                  else self.mbv2_features(trunk, (video, layout, scale)))
         v_feat, v_dfeat = self.avgpool(v_last)
         D = m.video.output_dim
         v_out = self.alloc(B * D)
@@ -140,4 +143,40 @@ class MultimodalAttentionLate(PlanModel):
         self.afc = nn.Linear(512, num_classes)
         self.cfc = nn.Linear(256, num_classes)
         self.vfc = nn.Linear(vdim, num_classes)
+        self.attn = AttentionFusion(num_classes)
+
+
+class ResNetLSTM(nn.Module):
+    """late_fusion_resnet.py:31-46: resnet18 (fc = Identity, pretrained conv1 kept) + 2-layer BiLSTM."""
+
+    def __init__(self, feature_dim=256, pretrained_state_dict=None, dropout=0.3):
+        super().__init__()
+        resnet = resnet18(weights=None)
+        if pretrained_state_dict is not None:
+            resnet.load_state_dict(pretrained_state_dict)
+        resnet.fc = nn.Identity()
+        self.cnn = nn.Sequential(resnet)
+        self.td = TimeDistributed(self.cnn)
+        self.lstm = nn.LSTM(512, feature_dim // 2, num_layers=2, bidirectional=True, batch_first=True, dropout=dropout)
+        self.output_dim = feature_dim
+
+
+class MultimodalAttentionLateResNet(PlanModel):
+    """audio_cues_video/models/late_fusion_resnet.py:76-99 (parameter order afc, vfc, cfc as in the reference)."""
+    INPUTS = ("audio", "cue", "video")
+    PLAN = LateFusionPlan
+    DEFAULT_LR = 1e-5
+
+    def __init__(self, num_classes, cue_dim=768, video_cfg=None, pretrained=False, precision=None, lstm_dropout=0.3):
+        super().__init__()
+        if pretrained:
+            raise ValueError("no network here: pass ImageNet weights through the sub-modules' pretrained_state_dict")
+        self._init_base(num_classes, type("C", (), {"get": staticmethod(lambda k, d=None: d)})(), precision)
+        self.audio = AudioEncoder()
+        self.cue = CueEncoder(cue_dim)
+        vdim = int(video_cfg.get("model", {}).get("feature_dim", 256)) if video_cfg else 256
+        self.video = ResNetLSTM(vdim, dropout=lstm_dropout)
+        self.afc = nn.Linear(512, num_classes)
+        self.vfc = nn.Linear(vdim, num_classes)
+        self.cfc = nn.Linear(256, num_classes)
         self.attn = AttentionFusion(num_classes)

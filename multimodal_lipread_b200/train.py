@@ -69,6 +69,8 @@ def create_video_model(model_name, num_classes, config):
     from . import video_models as M
     if model_name == "resnet_lstm":
         return M.ResNet2DBiLSTM(num_classes=num_classes, config=config)
+    if model_name == "mobilenet_lstm":
+        return M.MobileNetLSTM(num_classes=num_classes, config=config)
     if model_name in VIDEO_MODELS:
         _no_plan(model_name)
     raise ValueError(f"Unknown model: {model_name}")
@@ -89,6 +91,8 @@ def create_acv_model(model_name, num_classes, cue_dim=768, video_cfg=None):
     from . import audio_cues_video_models as M
     if model_name == "late_fusion_mobile":
         return M.MultimodalAttentionLate(num_classes, cue_dim=cue_dim, video_cfg=video_cfg, pretrained=False)
+    if model_name == "late_fusion_resnet":
+        return M.MultimodalAttentionLateResNet(num_classes, cue_dim=cue_dim, video_cfg=video_cfg, pretrained=False)
     if model_name in ACV_MODELS:
         _no_plan(model_name)
     raise ValueError(f"Unknown model name: {model_name}")

@@ -1,6 +1,7 @@
 """Video-only lip readers behind the reference's nn.Module surface (video/models/*.py).
 
   ResNet2DBiLSTM / create_model      video/models/resnet_lstm.py:56-177   (model.name == "resnet_lstm")
+  MobileNetLSTM                      video/models/mobilenet_lstm.py:18-72  (model.name == "mobilenet_lstm")
 
 Sub-modules are parameter containers only (same names, construction order and `state_dict` keys as the reference,
 including the CNN appearing twice -- `cnn_features.*` and `time_distributed_cnn.module.0.*` share tensors);
@@ -8,7 +9,7 @@ arithmetic runs through the launch plans of engine.py."""
 import types
 
 import torch.nn as nn
-from torchvision.models import resnet18, resnet34
+from torchvision.models import mobilenet_v2, resnet18, resnet34
 
 from ._lib import ACT_RELU
 from .model_base import Cfg, ModelPlan, PlanModel
@@ -33,19 +34,24 @@ class ResNetLstmPlan(ModelPlan):
         B, wb = self.B, self.with_backward
         video, layout, scale = self.video_input()
         T = layout[2]
-        last = self.resnet_features(_resnet_view(m.cnn_features), (video, layout, scale))
+        if hasattr(m, "cnn_features"):
+            last = self.resnet_features(_resnet_view(m.cnn_features), (video, layout, scale))
+            lstm, drop = m.bilstm, m.dropout
+        else:
+            last = self.mbv2_features(m.cnn[0], (video, layout, scale))
+            lstm, drop = m.lstm, m.drop
         feat, dfeat = self.avgpool(last)
-        D = 2 * m.bilstm.hidden_size
+        D = 2 * lstm.hidden_size
         seq_last = self.alloc(B * D)
         h = self.alloc(B * D)
         dh = self.alloc(B * D) if wb else None
         # dh is turned into the gradient of x[:, -1] in place by the ReLU backward below, which runs first
-        self.bilstm_last(feat, dfeat, last.C, B, T, m.bilstm, seq_last, D, dh if wb else 0)
+        self.bilstm_last(feat, dfeat, last.C, B, T, lstm, seq_last, D, dh if wb else 0)
         # x[:, -1] -> ReLU -> Dropout -> fc   (resnet_lstm.py:151-154)
         self.fwd.add("lr_act_fwd", seq_last, h, B * D, ACT_RELU)
         if wb:
             self.bgroup().add("lr_act_bwd", dh, h, B * D, ACT_RELU)
-        p = m.dropout.p if isinstance(m.dropout, nn.Dropout) else 0.0
+        p = drop.p if isinstance(drop, nn.Dropout) else 0.0
         hd, dhd = self.dropout(h, dh, B * D, p)
         logits = self.alloc(B * self.num_classes)
         dlogits = self.alloc(B * self.num_classes) if wb else None
@@ -86,6 +92,32 @@ class ResNet2DBiLSTM(PlanModel):
                               batch_first=True, dropout=dropout if dropout > 0 else 0)
         self.relu = nn.ReLU()
         self.dropout = nn.Dropout(dropout) if dropout > 0 else nn.Identity()
+        self.fc = nn.Linear(feature_dim, num_classes)
+
+
+class MobileNetLSTM(PlanModel):
+    """video/models/mobilenet_lstm.py:18-68: MobileNetV2 features + avgpool, 2-layer BiLSTM, x[:, -1] -> ReLU -> Dropout -> fc."""
+    INPUTS = ("video",)
+    PLAN = ResNetLstmPlan
+    DEFAULT_LR = 5e-5
+    DEFAULT_WD = 1e-5
+
+    def __init__(self, num_classes, config=None, pretrained_state_dict=None, precision=None):
+        super().__init__()
+        config = config or Cfg()
+        self._init_base(num_classes, config, precision)
+        feature_dim = config.get("model.feature_dim", 256)
+        dropout = config.get("model.dropout", 0.3)
+        base = mobilenet_v2(weights=None)
+        if pretrained_state_dict is not None:
+            base.load_state_dict(pretrained_state_dict)
+        base.classifier = nn.Identity()
+        self.cnn = nn.Sequential(base.features, nn.AdaptiveAvgPool2d((1, 1)), nn.Flatten())
+        self.td = TimeDistributed(self.cnn)
+        self.lstm = nn.LSTM(input_size=1280, hidden_size=feature_dim // 2, num_layers=2, bidirectional=True,
+                            batch_first=True, dropout=dropout)
+        self.relu = nn.ReLU()
+        self.drop = nn.Dropout(dropout)
         self.fc = nn.Linear(feature_dim, num_classes)
 
 

@@ -13,6 +13,8 @@ there is no network for the ImageNet checkpoint:
   ResNet2DBiLSTMOracle        video/models/resnet_lstm.py:56-156
   AudioResNetOracle           audio/models/resnet_model.py:5-39
   LateFusionMobileOracle      audio_cues_video/models/late_fusion_mobile.py:6-107
+  LateFusionResNetOracle      audio_cues_video/models/late_fusion_resnet.py:6-99
+  MobileNetLSTMOracle         video/models/mobilenet_lstm.py:18-68
   LateFusionAVMobileNetOracle audio_video/models/late_fusion.py:10-93
   MidFusionAVMobileNetOracle  audio_video/models/middle_fusion.py:11-85
   EarlyFusionFastOracle       audio_video/models/early_fusion_fast.py:6-76
@@ -256,6 +258,57 @@ class LateFusionMobileOracle(nn.Module):
         v = self.vfc(self.video(lip))
         fused, _ = self.attn([a, c, v])
         return fused
+
+
+class LateFusionResNetOracle(LateFusionMobileOracle):
+    """audio_cues_video/models/late_fusion_resnet.py:76-99: the same composition with a ResNet-18 video trunk
+    (nn.Sequential(resnet), fc = Identity) and the heads registered in the order afc, vfc, cfc."""
+
+    class _Video(nn.Module):
+        def __init__(self, feature_dim, dropout):
+            super().__init__()
+            resnet = resnet18(weights=None)
+            resnet.fc = nn.Identity()
+            self.cnn = nn.Sequential(resnet)
+            self.td = _TimeDistributed(self.cnn)
+            self.lstm = nn.LSTM(512, feature_dim // 2, num_layers=2, bidirectional=True, batch_first=True, dropout=dropout)
+            self.output_dim = feature_dim
+
+        def forward(self, x):
+            x, _ = self.lstm(self.td(x))
+            return x[:, -1, :]
+
+    def __init__(self, num_classes, cue_dim=768, vdim=256, lstm_dropout=0.3):
+        nn.Module.__init__(self)
+        self.audio = self._Audio()
+        self.cue = self._Cue(cue_dim)
+        self.video = self._Video(vdim, lstm_dropout)
+        self.afc = nn.Linear(512, num_classes)
+        self.vfc = nn.Linear(vdim, num_classes)
+        self.cfc = nn.Linear(256, num_classes)
+        self.attn = self._Attn(num_classes)
+
+
+class MobileNetLSTMOracle(nn.Module):
+    """video/models/mobilenet_lstm.py:18-68."""
+
+    def __init__(self, num_classes, config=None):
+        super().__init__()
+        config = config or DictConfig()
+        feature_dim = config.get("model.feature_dim", 256)
+        dropout = config.get("model.dropout", 0.3)
+        base = mobilenet_v2(weights=None)
+        base.classifier = nn.Identity()
+        self.cnn = nn.Sequential(base.features, nn.AdaptiveAvgPool2d((1, 1)), nn.Flatten())
+        self.td = _TimeDistributed(self.cnn)
+        self.lstm = nn.LSTM(1280, feature_dim // 2, num_layers=2, bidirectional=True, batch_first=True, dropout=dropout)
+        self.relu = nn.ReLU()
+        self.drop = nn.Dropout(dropout)
+        self.fc = nn.Linear(feature_dim, num_classes)
+
+    def forward(self, x):
+        x, _ = self.lstm(self.td(x))
+        return self.fc(self.drop(self.relu(x[:, -1, :])))
 
 
 class _VideoLstm(nn.Module):

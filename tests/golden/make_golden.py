@@ -202,6 +202,18 @@ def golden_models():
     mel, video, labels = data(B, size, T, C)
     cue = synthetic.make_cues(B)
     record("acv_late_fusion_mobile", model, (mel, cue, video), labels, 1e-5, 0.0, B, T, size)
+    # video mobilenet_lstm (dropout 0 through its own config key) and audio_cues_video late_fusion_resnet
+    B, T, size, C = 3, 6, 44, 40
+    mod = load_ref("video", "models.mobilenet_lstm")
+    torch.manual_seed(0)
+    model = mod.MobileNetLSTM(C, DCfg({"model.dropout": 0.0}))
+    mel, video, labels = data(B, size, T, C)
+    record("video_mobilenet_lstm", model, (video,), labels, 5e-5, 1e-5, B, T, size)
+    mod = load_ref("audio_cues_video", "models.late_fusion_resnet")
+    torch.manual_seed(0)
+    model = mod.MultimodalAttentionLateResNet(C, cue_dim=768, video_cfg=None, pretrained=False)
+    model.video.lstm.dropout = 0.0
+    record("acv_late_fusion_resnet", model, (mel, synthetic.make_cues(B), video), labels, 1e-5, 0.0, B, T, size)
     # the remaining audio_video models (av_config.yaml:10), lr 3e-4
     B, T, size, C = 3, 8, 44, 40
     for name, module, factory, drop in (("late_fusion_mobilenet", "models.late_fusion", "create_late_fusion_mobilenet_model", False),

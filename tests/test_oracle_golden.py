@@ -113,8 +113,8 @@ def models_golden(golden_dir):
     return np.load(os.path.join(golden_dir, "models_golden.npz"))
 
 
-@pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile",
-                                  "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast"])
+@pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
+                                  "acv_late_fusion_resnet", "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast"])
 def test_model_oracles_match_reference(models_golden, name):
     from oracle import av_models as O
     g = models_golden
@@ -127,6 +127,10 @@ def test_model_oracles_match_reference(models_golden, name):
         model, lr, wd = O.ResNet2DBiLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}})), 5e-5, 1e-5
     elif name == "acv_late_fusion_mobile":
         model, lr, wd = O.LateFusionMobileOracle(C, lstm_dropout=0.0), 1e-5, 0.0
+    elif name == "video_mobilenet_lstm":
+        model, lr, wd = O.MobileNetLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}})), 5e-5, 1e-5
+    elif name == "acv_late_fusion_resnet":
+        model, lr, wd = O.LateFusionResNetOracle(C, lstm_dropout=0.0), 1e-5, 0.0
     elif name == "late_fusion_mobilenet":
         model, lr, wd = O.LateFusionAVMobileNetOracle(C), 3e-4, 0.0
     elif name == "middle_fusion_mobilenet":
@@ -146,8 +150,9 @@ def test_model_oracles_match_reference(models_golden, name):
     mel = AudioProcessorPort().batch_frontend_loop(wav)
     video = lips_u8_to_model_input(synthetic.make_lips_u8(B, size=size)[:, :T].contiguous())
     labels = synthetic.make_labels(B, C)
-    inputs = {"video_resnet_lstm": (video,), "audio_resnet": (mel,),
-              "acv_late_fusion_mobile": (mel, synthetic.make_cues(B), video)}.get(name, (mel, video))
+    inputs = {"video_resnet_lstm": (video,), "video_mobilenet_lstm": (video,), "audio_resnet": (mel,),
+              "acv_late_fusion_mobile": (mel, synthetic.make_cues(B), video),
+              "acv_late_fusion_resnet": (mel, synthetic.make_cues(B), video)}.get(name, (mel, video))
     opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
     logits, loss = O.train_step_generic(model, opt, inputs, labels)
     np.testing.assert_allclose(logits.numpy(), g[f"{name}_logits"], rtol=1e-5, atol=1e-6)
