@@ -168,6 +168,14 @@ int lr_colsum(const float* dY, long long ld, long long M, int N, float* db, lr_s
 int lr_im2col(const void* x, int is_u8, float scale, int F, int T, long long sb, long long st, long long sc,
               long long sh, long long sw, int Hs, int Ws, int C, int kh, int kw, int stride, int pad, int transposed,
               int Hd, int Wd, float* col, long long ldk, lr_stream_t stream);
+/* Tap-major variant for channels-last float activations with C % 4 == 0 (every ResNet convolution but the stem):
+ * col[(f,hd,wd)][(r*kw + s)*C + c], a shifted float4 copy that is coalesced on both sides.  The matching weight
+ * layouts come from lr_weight_tap: mode 0: wp[k][rs][c] = w[k][c][rs] (forward / wgrad operand), mode 1:
+ * wp[c][rs][k] = w[k][c][rs] (dgrad operand), mode 2: w[k][c][rs] = wp[k][rs][c] (weight gradient back to torch's
+ * layout). */
+int lr_im2col_tap(const float* x, int F, int Hs, int Ws, int C, int kh, int kw, int stride, int pad, int transposed,
+                  int Hd, int Wd, float* col, lr_stream_t stream);
+int lr_weight_tap(const float* src, float* dst, int Cout, int Cin, int kk, int mode, lr_stream_t stream);
 /* wt[c][k*kk + rs] (row pitch ldt) = w[k][c][rs]: the dgrad weight of a dense convolution. */
 int lr_weight_transpose(const float* w, float* wt, int Cout, int Cin, int kk, long long ldt, lr_stream_t stream);
 

@@ -102,6 +102,59 @@ im2col_u8c3_3x3_kernel(const Src s, const Geo g, float* __restrict__ col, long l
     }
 }
 
+// Tap-major patch matrix of a channels-last float activation with C % 4 == 0:
+//   col[(f,hd,wd)][(r*kw + s)*C + c] = x[f, hs, ws, c]   (0 outside the image)
+// A thread moves one float4 of channels: the gather is a shifted, fully coalesced copy (both sides), which is what
+// lets the ResNet trunk's patch matrices be written at HBM speed.  transposed: the dgrad operand (see lr_im2col).
+__global__ void __launch_bounds__(TH)
+im2col_tap_kernel(const float* __restrict__ x, const Geo g, int Hs, int Ws, int C, float* __restrict__ col, long long rows) {
+    const int c4n = C >> 2, kk = g.kh * g.kw;
+    const long long per_row = (long long)kk * c4n;
+    const long long total = rows * per_row;
+    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < total; i += (long long)gridDim.x * TH) {
+        const long long row = i / per_row;
+        const int rem = int(i - row * per_row);
+        const int tap = rem / c4n, c = (rem - tap * c4n) * 4;
+        const int r = tap / g.kw, q = tap - r * g.kw;
+        const int wd = int(row % g.Wd);
+        const long long t = row / g.Wd;
+        const int hd = int(t % g.Hd), f = int(t / g.Hd);
+        int hs, ws; bool ok;
+        if (!g.transposed) {
+            hs = hd * g.stride - g.pad + r; ws = wd * g.stride - g.pad + q;
+            ok = hs >= 0 && hs < Hs && ws >= 0 && ws < Ws;
+        } else {
+            const int hn = hd + g.pad - r, wn = wd + g.pad - q;
+            hs = hn / g.stride; ws = wn / g.stride;
+            ok = hn >= 0 && wn >= 0 && hs * g.stride == hn && ws * g.stride == wn && hs < Hs && ws < Ws;
+        }
+        const float4 v = ok ? nn::ld4(x + (((long long)f * Hs + hs) * Ws + ws) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        nn::st4(col + row * g.ldk + (long long)tap * C + c, v);
+    }
+}
+
+// Weight layouts of the tap-major patch matrix (kk = kh*kw taps):
+//   mode 0: wp[k][rs][c]  = w[k][c][rs]    forward / wgrad operand   [Cout][kk*Cin]
+//   mode 1: wp[c][rs][k]  = w[k][c][rs]    dgrad operand             [Cin][kk*Cout]
+//   mode 2: w[k][c][rs]   = wp[k][rs][c]   weight gradient back to torch's layout (overwrites w)
+__global__ void __launch_bounds__(TH)
+weight_tap_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin, int kk, int mode) {
+    const long long n = (long long)Cout * Cin * kk;
+    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < n; i += (long long)gridDim.x * TH) {
+        // i enumerates the DESTINATION contiguously
+        if (mode == 0) {
+            const int c = int(i % Cin); const long long t = i / Cin; const int rs = int(t % kk), k = int(t / kk);
+            dst[i] = src[((long long)k * Cin + c) * kk + rs];
+        } else if (mode == 1) {
+            const int k = int(i % Cout); const long long t = i / Cout; const int rs = int(t % kk), c = int(t / kk);
+            dst[i] = src[((long long)k * Cin + c) * kk + rs];
+        } else {
+            const int rs = int(i % kk); const long long t = i / kk; const int c = int(t % Cin), k = int(t / Cin);
+            dst[i] = src[((long long)k * kk + rs) * Cin + c];
+        }
+    }
+}
+
 // wt[c][k][rs] = w[k][c][rs]  (row pitch of wt = ldt >= Cout*kk, tail zeroed by the caller once)
 __global__ void __launch_bounds__(TH)
 weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin, int kk, long long ldt) {
@@ -245,6 +298,32 @@ extern "C" int lr_im2col(const void* x, int is_u8, float scale, int F, int T, lo
         c2::im2col_kernel<<<c2::grid_for(rows * (ldk >> 2)), c2::TH, 0, stream>>>(s, g, col, rows);
     lr::count_launch();
     LR_CHECK_LAUNCH("im2col_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_im2col_tap(const float* x, int F, int Hs, int Ws, int C, int kh, int kw, int stride, int pad,
+                             int transposed, int Hd, int Wd, float* col, lr_stream_t stream) {
+    LR_CHECK_ARG(F >= 0 && Hs > 0 && Ws > 0 && C > 0 && (C & 3) == 0 && Hd > 0 && Wd > 0, "lr_im2col_tap: bad shape (C %% 4 != 0?)");
+    LR_CHECK_ARG(kh > 0 && kw > 0 && stride > 0 && pad >= 0, "lr_im2col_tap: bad window");
+    if (F == 0) return LR_OK;
+    LR_CHECK_ARG(x && col, "lr_im2col_tap: null pointer");
+    LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(col);
+    c2::Geo g;
+    g.Hd = Hd; g.Wd = Wd; g.kh = kh; g.kw = kw; g.stride = stride; g.pad = pad; g.transposed = transposed;
+    g.K = C * kh * kw; g.ldk = g.K;
+    const long long rows = (long long)F * Hd * Wd;
+    c2::im2col_tap_kernel<<<c2::grid_for(rows * kh * kw * (C >> 2)), c2::TH, 0, stream>>>(x, g, Hs, Ws, C, col, rows);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("im2col_tap_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_weight_tap(const float* src, float* dst, int Cout, int Cin, int kk, int mode, lr_stream_t stream) {
+    LR_CHECK_ARG(Cout > 0 && Cin > 0 && kk > 0 && mode >= 0 && mode <= 2, "lr_weight_tap: bad argument");
+    LR_CHECK_ARG(src && dst, "lr_weight_tap: null pointer");
+    c2::weight_tap_kernel<<<c2::grid_for((long long)Cout * Cin * kk), c2::TH, 0, stream>>>(src, dst, Cout, Cin, kk, mode);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("weight_tap_kernel");
     return LR_OK;
 }
 

@@ -10,6 +10,7 @@
 // prefix of its walk only: a head that reads out[:, -1] needs the reverse direction's FIRST step
 // (t = T-1) and nothing else.
 #include "nn_common.cuh"
+#include <cooperative_groups.h>
 #include <cstdlib>
 
 namespace ls {
@@ -434,6 +435,219 @@ static int run_bwd(const ls::Bwd& p, lr_stream_t stream) {
 
 }  // namespace lsc
 
+// =====================================================================================================================
+// Grid-cooperative version for hidden sizes whose W_hh (4H x H floats: 4 MB at H = 512) does not fit the shared
+// memory of one 8-CTA cluster: NC = H / 16 CTAs per group of 32 batch rows, CTA c owns 16 hidden units and keeps its
+// W_hh slice (64 gate rows x H: 128 KB at H = 512) in shared memory for the whole walk.  h_t is exchanged through the
+// `out` tensor itself (it is the next step's input and lives in L2), dgates through the `dgates` tensor; one
+// cooperative grid barrier per step.  Launched with cudaLaunchAttributeCooperative (all CTAs co-resident).
+namespace lsg {
+
+constexpr int U = 16, BG = 32, TH = 256, NRG = TH / U, RPT = BG / NRG;   // 16 units x 16 row groups of 2 rows
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(TH)
+lstm_fwd_coop_kernel(const ls::Fwd p) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    extern __shared__ __align__(16) float sm[];
+    const int H = p.H, HP = H + 4, NC = H / U;
+    float* Wt = sm;                                   // [H][U][4]
+    float* hb = Wt + (size_t)H * U * 4;               // [BG][HP]  h_{t-1}
+    const int c = blockIdx.x % NC, b0 = (blockIdx.x / NC) * BG;
+    const int u = threadIdx.x % U, rg = threadIdx.x / U;
+    for (int i = threadIdx.x; i < 4 * U * H; i += TH) {
+        const int k = i % H, ju = i / H;
+        const int g = ju / U, uu = ju - g * U;
+        Wt[(k * U + uu) * 4 + g] = p.whh[(long long)(g * H + c * U + uu) * H + k];
+    }
+    float bias[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) bias[g] = p.bhh ? p.bhh[g * H + c * U + u] : 0.f;
+    float cst[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) cst[r] = 0.f;
+    const int col = c * U + u;
+    for (int s = 0; s < p.nsteps; ++s) {
+        const int t = p.reverse ? p.T - 1 - s : s;
+        const int tprev = p.reverse ? t + 1 : t - 1;
+        // h_{t-1}: the whole [BG][H] block from `out` (written by all CTAs of the group in the previous step)
+        for (int i = threadIdx.x; i < BG * (H / 4); i += TH) {
+            const int r = i / (H / 4), k4 = (i - r * (H / 4)) * 4;
+            const int b = b0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s > 0 && b < p.B) {
+                const float* src = p.out + ((long long)b * p.T + tprev) * p.ldo + k4;
+                v = make_float4(__ldcg(src), __ldcg(src + 1), __ldcg(src + 2), __ldcg(src + 3));
+            }
+            *reinterpret_cast<float4*>(hb + r * HP + k4) = v;
+        }
+        float acc[RPT][4], xp[RPT][4];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int b = b0 + rg * RPT + r;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                xp[r][g] = b < p.B ? p.xproj[((long long)b * p.T + t) * p.ldx + g * H + col] + bias[g] : 0.f;
+                acc[r][g] = 0.f;
+            }
+        }
+        __syncthreads();
+        if (s > 0) {
+#pragma unroll 2
+            for (int k = 0; k < H; k += 4) {
+                float4 w[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4*>(Wt + ((k + kk) * U + u) * 4);
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    const float4 h = *reinterpret_cast<const float4*>(hb + (rg * RPT + r) * HP + k);
+                    const float hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        acc[r][0] = fmaf(w[kk].x, hv[kk], acc[r][0]); acc[r][1] = fmaf(w[kk].y, hv[kk], acc[r][1]);
+                        acc[r][2] = fmaf(w[kk].z, hv[kk], acc[r][2]); acc[r][3] = fmaf(w[kk].w, hv[kk], acc[r][3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int rl = rg * RPT + r, b = b0 + rl;
+            const float ig = sigmoidf_(acc[r][0] + xp[r][0]), fg = sigmoidf_(acc[r][1] + xp[r][1]);
+            const float gg = tanhf(acc[r][2] + xp[r][2]), og = sigmoidf_(acc[r][3] + xp[r][3]);
+            const float cn = fg * cst[r] + ig * gg;
+            const float hn = og * tanhf(cn);
+            if (b < p.B) {
+                const long long row = (long long)b * p.T + t;
+                if (p.gates) { float* gp = p.gates + row * 4 * H; gp[col] = ig; gp[H + col] = fg; gp[2 * H + col] = gg; gp[3 * H + col] = og; }
+                if (p.cst) p.cst[row * H + col] = cn;
+                if (p.hprev) p.hprev[row * H + col] = hb[rl * HP + col];
+                p.out[row * p.ldo + col] = hn;
+            }
+            cst[r] = cn;
+        }
+        __threadfence();
+        grid.sync();                                  // also protects hb against the next step's refill
+    }
+}
+
+__global__ void __launch_bounds__(TH)
+lstm_bwd_coop_kernel(const ls::Bwd p) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    extern __shared__ __align__(16) float sm[];
+    const int H = p.H, G = 4 * H, NC = H / U;
+    constexpr int JC = 256;                           // dgates columns staged per chunk
+    constexpr int JP = JC + 4;
+    float* Wc = sm;                                   // [4H][U]   Wc[j][u'] = whh[j*H + c*U + u']
+    float* dgs = Wc + (size_t)G * U;                  // [BG][JP]  a chunk of this step's dgates (all units)
+    float* dhs = dgs + BG * JP;                       // [BG][U]   dh of my units for the next visited step
+    const int c = blockIdx.x % NC, b0 = (blockIdx.x / NC) * BG;
+    const int u = threadIdx.x % U, rg = threadIdx.x / U;
+    for (int i = threadIdx.x; i < G * U; i += TH) {
+        const int uu = i % U, j = i / U;
+        Wc[i] = p.whh[(long long)j * H + c * U + uu];
+    }
+    for (int i = threadIdx.x; i < BG * U; i += TH) dhs[i] = 0.f;
+    float dc[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) dc[r] = 0.f;
+    const int col = c * U + u;
+    __syncthreads();
+    for (int s = p.nsteps - 1; s >= 0; --s) {
+        const int t = p.reverse ? p.T - 1 - s : s;
+        const int tprev = p.reverse ? t + 1 : t - 1;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int rl = rg * RPT + r, b = b0 + rl;
+            if (b < p.B) {
+                float dht = dhs[rl * U + u];
+                const long long row = (long long)b * p.T + t;
+                if (p.dout) {
+                    if (p.dout_step < 0) dht += p.dout[row * p.ldo + col];
+                    else if (t == p.dout_step) dht += p.dout[(long long)b * p.ldo + col];
+                }
+                const float* gq = p.gates + row * G;
+                const float ig = gq[col], fg = gq[H + col], gg = gq[2 * H + col], og = gq[3 * H + col];
+                const float cc = p.cst[row * H + col];
+                const float cprev = s > 0 ? p.cst[((long long)b * p.T + tprev) * H + col] : 0.f;
+                const float tc = tanhf(cc);
+                const float dct = dc[r] + dht * og * (1.f - tc * tc);
+                float* o = p.dgates + row * G;
+                o[col] = dct * gg * ig * (1.f - ig);
+                o[H + col] = dct * cprev * fg * (1.f - fg);
+                o[2 * H + col] = dct * ig * (1.f - gg * gg);
+                o[3 * H + col] = dht * tc * og * (1.f - og);
+                dc[r] = dct * fg;
+            }
+        }
+        __threadfence();
+        grid.sync();
+        if (s > 0) {
+            // dh_prev[r][u] = sum_j dgates[r, t, j] * whh[j][col] over ALL 4H gate rows, staged JC columns at a time
+            float acc[RPT];
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) acc[r] = 0.f;
+            for (int j0 = 0; j0 < G; j0 += JC) {
+                __syncthreads();
+                for (int i = threadIdx.x; i < BG * (JC / 4); i += TH) {
+                    const int r = i / (JC / 4), j4 = (i - r * (JC / 4)) * 4;
+                    const int b = b0 + r;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b < p.B) {
+                        const float* src = p.dgates + ((long long)b * p.T + t) * G + j0 + j4;
+                        v = make_float4(__ldcg(src), __ldcg(src + 1), __ldcg(src + 2), __ldcg(src + 3));
+                    }
+                    *reinterpret_cast<float4*>(dgs + r * JP + j4) = v;
+                }
+                __syncthreads();
+#pragma unroll 4
+                for (int j = 0; j < JC; j += 4) {
+                    float w[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) w[jj] = Wc[(size_t)(j0 + j + jj) * U + u];
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        const float4 g4 = *reinterpret_cast<const float4*>(dgs + (rg * RPT + r) * JP + j);
+                        acc[r] = fmaf(g4.x, w[0], acc[r]); acc[r] = fmaf(g4.y, w[1], acc[r]);
+                        acc[r] = fmaf(g4.z, w[2], acc[r]); acc[r] = fmaf(g4.w, w[3], acc[r]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) dhs[(rg * RPT + r) * U + u] = acc[r];      // read back by the same thread
+        }
+    }
+}
+
+static size_t fwd_smem(int H) { return ((size_t)H * U * 4 + (size_t)BG * (H + 4)) * sizeof(float); }
+static size_t bwd_smem(int H) { return ((size_t)4 * H * U + (size_t)BG * (256 + 4) + (size_t)BG * U) * sizeof(float); }
+static bool usable(int H, int B) {
+    // shared memory fits and every CTA of the cooperative grid can be resident at once (one CTA per SM)
+    return H % U == 0 && H >= 64 && fwd_smem(H) <= 220 * 1024 && bwd_smem(H) <= 220 * 1024 &&
+           (long long)(H / U) * ((B + BG - 1) / BG) <= lr::sm_count();
+}
+
+template <typename Kern, typename Arg>
+static int launch(Kern kern, int ctas, size_t smem, lr_stream_t stream, const Arg& arg, const char* name) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return lr::fail(LR_ECUDA, "%s smem: %s", name, cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(TH);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, arg);
+    if (e != cudaSuccess) return lr::fail(LR_ECUDA, "%s launch: %s", name, cudaGetErrorString(e));
+    return LR_OK;
+}
+
+}  // namespace lsg
+
 // LIPREAD_LSTM=simple selects the one-CTA-per-4-rows kernels (debugging / A-B timing); read once.
 static bool lr_lstm_use_cluster() {
     static const bool v = [] { const char* e = getenv("LIPREAD_LSTM"); return !(e && e[0] == 's'); }();
@@ -457,6 +671,14 @@ extern "C" int lr_lstm_fwd(const float* xproj, long long ldx, const float* bhh, 
         if (rc) return rc;
         lr::count_launch();
         LR_CHECK_LAUNCH("lstm_fwd_cluster_kernel");
+        return LR_OK;
+    }
+    if (nsteps > 1 && H > 256 && lsg::usable(H, B) && lr_lstm_use_cluster()) {
+        const int rc = lsg::launch(lsg::lstm_fwd_coop_kernel, (H / lsg::U) * ((B + lsg::BG - 1) / lsg::BG), lsg::fwd_smem(H),
+                                   stream, p, "lstm_fwd_coop_kernel");
+        if (rc) return rc;
+        lr::count_launch();
+        LR_CHECK_LAUNCH("lstm_fwd_coop_kernel");
         return LR_OK;
     }
     const size_t smem = (size_t)(2 * ls::R * H + ls::R * 4 * H) * sizeof(float);
@@ -488,6 +710,14 @@ extern "C" int lr_lstm_bwd(const float* dout, long long ldo, int dout_step, cons
         if (rc) return rc;
         lr::count_launch();
         LR_CHECK_LAUNCH("lstm_bwd_cluster_kernel");
+        return LR_OK;
+    }
+    if (nsteps > 1 && H > 256 && lsg::usable(H, B) && lr_lstm_use_cluster()) {
+        const int rc = lsg::launch(lsg::lstm_bwd_coop_kernel, (H / lsg::U) * ((B + lsg::BG - 1) / lsg::BG), lsg::bwd_smem(H),
+                                   stream, p, "lstm_bwd_coop_kernel");
+        if (rc) return rc;
+        lr::count_launch();
+        LR_CHECK_LAUNCH("lstm_bwd_coop_kernel");
         return LR_OK;
     }
     const size_t smem = (size_t)(2 * ls::R * H + 2 * ls::R * 4 * H) * sizeof(float);

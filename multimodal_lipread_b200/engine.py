@@ -527,13 +527,21 @@ class Plan:
         rows = F * Ho * Wo
         K = Cin * kh * kw
         pointwise = frames is None and kh == 1 and kw == 1 and st_ == 1 and pd == 0 and Cin % 4 == 0
-        ldk = K if pointwise else (K + 3) // 4 * 4
+        # tap-major patch matrix (shifted float4 copies) for channels-last inputs; torch-order gather for the stems
+        tap = frames is None and not pointwise and Cin % 4 == 0 and Cout % 4 == 0
+        ldk = K if (pointwise or tap) else (K + 3) // 4 * 4
         if pointwise:
             col = xptr
+        elif tap:
+            col = self.alloc(rows * K)
+            self.fwd.add("lr_im2col_tap", xptr, F, Hs, Ws, Cin, kh, kw, st_, pd, 0, Ho, Wo, col)
         else:
             col = self.alloc(rows * ldk)
             self.fwd.add("lr_im2col", xptr, *src, Hs, Ws, Cin, kh, kw, st_, pd, 0, Ho, Wo, col, ldk)
-        if ldk != K:
+        if tap:
+            wmat = self.alloc(Cout * K)
+            self.fwd.add("lr_weight_tap", conv.weight, wmat, Cout, Cin, kh * kw, 0)
+        elif ldk != K:
             wmat = self.alloc(Cout * ldk)
             wmat.zero_()
             self.fwd.add("lr_copy2d", wmat, ldk, conv.weight, K, Cout, K)
@@ -549,13 +557,13 @@ class Plan:
                        bias=(conv.bias if conv.bias is not None else 0), act=act, stats=stt_)
         if self.with_backward:
             g = self.bgroup()
-            y._conv_bwd = (g, x, conv, col, ldk, wmat, src, (F, Hs, Ws, Ho, Wo), need_dx and frames is None)
+            y._conv_bwd = (g, x, conv, col, ldk, wmat, src, (F, Hs, Ws, Ho, Wo), need_dx and frames is None, tap)
         return y
 
     def dense_conv_bwd(self, y, dx_residual=0):
         """Emit the backward of a dense_conv output y (after everything that writes y.grad has been registered):
         dW += dy^T col, db += colsum(dy), x.grad = im2col_T(dy) . Wt^T (+ dx_residual)."""
-        g, x, conv, col, ldk, wmat, src, (F, Hs, Ws, Ho, Wo), need_dx = y._conv_bwd
+        g, x, conv, col, ldk, wmat, src, (F, Hs, Ws, Ho, Wo), need_dx, tap = y._conv_bwd
         Cout, Cin = conv.out_channels, conv.in_channels
         kh, kw = conv.kernel_size
         st_, pd = conv.stride[0], conv.padding[0]
@@ -564,7 +572,12 @@ class Plan:
         dw = self.flat.g(conv.weight)
         if getattr(y, "_act", ACT_NONE) != ACT_NONE:          # fused activation: dy *= act'(y) first
             g.add("lr_act_bwd", y.grad, y.val, rows * Cout, y._act)
-        if ldk != K:
+        if tap:
+            dwp = self.alloc(Cout * K)                              # gradient in the tap-major layout, then back to torch's
+            g.add("lr_memset", dwp, Cout * K * 4, leaf=True)
+            self.gemm_auto(g, y.grad, Cout, 1, col, K, 1, dwp, K, Cout, K, rows, split_ok=True)
+            g.add("lr_weight_tap", dwp, dw, Cout, Cin, kh * kw, 2, leaf=True)
+        elif ldk != K:
             dwp = self.alloc(Cout * ldk)
             g.add("lr_memset", dwp, Cout * ldk * 4, leaf=True)
             self.gemm_auto(g, y.grad, Cout, 1, col, ldk, 1, dwp, ldk, Cout, ldk, rows, split_ok=True)
@@ -580,6 +593,13 @@ class Plan:
             self.gemm_auto(g, y.grad, Cout, 0, conv.weight, Cin, 1, x.grad, Cin, rows_in, Cin, Cout, R=dx_residual, ldr=Cin)
             return
         Kt = Cout * kh * kw
+        if tap:
+            wt = self.alloc(Cin * Kt)
+            g.add("lr_weight_tap", conv.weight, wt, Cout, Cin, kh * kw, 1)
+            colT = self.workspace(rows_in * Kt)
+            g.add("lr_im2col_tap", y.grad, F, Ho, Wo, Cout, kh, kw, st_, pd, 1, Hs, Ws, colT)
+            self.gemm_auto(g, colT, Kt, 0, wt, Kt, 0, x.grad, Cin, rows_in, Cin, Kt, R=dx_residual, ldr=Cin)
+            return
         ldt = (Kt + 3) // 4 * 4
         wt = self.alloc(Cin * ldt)
         wt.zero_()
