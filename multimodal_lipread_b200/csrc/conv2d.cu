@@ -108,28 +108,29 @@ im2col_u8c3_3x3_kernel(const Src s, const Geo g, float* __restrict__ col, long l
 // lets the ResNet trunk's patch matrices be written at HBM speed.  transposed: the dgrad operand (see lr_im2col).
 __global__ void __launch_bounds__(TH)
 im2col_tap_kernel(const float* __restrict__ x, const Geo g, int Hs, int Ws, int C, float* __restrict__ col, long long rows) {
-    const int c4n = C >> 2, kk = g.kh * g.kw;
-    const long long per_row = (long long)kk * c4n;
-    const long long total = rows * per_row;
+    // one thread = one (row, 4-channel group): the pixel decode is done once and reused for all kh*kw taps
+    const int c4n = C >> 2;
+    const long long total = rows * c4n;
     for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < total; i += (long long)gridDim.x * TH) {
-        const long long row = i / per_row;
-        const int rem = int(i - row * per_row);
-        const int tap = rem / c4n, c = (rem - tap * c4n) * 4;
-        const int r = tap / g.kw, q = tap - r * g.kw;
+        const long long row = i / c4n;
+        const int c = int(i - row * c4n) * 4;
         const int wd = int(row % g.Wd);
         const long long t = row / g.Wd;
         const int hd = int(t % g.Hd), f = int(t / g.Hd);
-        int hs, ws; bool ok;
-        if (!g.transposed) {
-            hs = hd * g.stride - g.pad + r; ws = wd * g.stride - g.pad + q;
-            ok = hs >= 0 && hs < Hs && ws >= 0 && ws < Ws;
-        } else {
-            const int hn = hd + g.pad - r, wn = wd + g.pad - q;
-            hs = hn / g.stride; ws = wn / g.stride;
-            ok = hn >= 0 && wn >= 0 && hs * g.stride == hn && ws * g.stride == wn && hs < Hs && ws < Ws;
+        const float* xf = x + (long long)f * Hs * Ws * C + c;
+        float* o = col + row * g.ldk + c;
+        for (int r = 0; r < g.kh; ++r) {
+            int hs; bool okh;
+            if (!g.transposed) { hs = hd * g.stride - g.pad + r; okh = hs >= 0 && hs < Hs; }
+            else { const int hn = hd + g.pad - r; hs = hn / g.stride; okh = hn >= 0 && hs * g.stride == hn && hs < Hs; }
+            for (int q = 0; q < g.kw; ++q) {
+                int ws; bool ok;
+                if (!g.transposed) { ws = wd * g.stride - g.pad + q; ok = okh && ws >= 0 && ws < Ws; }
+                else { const int wn = wd + g.pad - q; ws = wn / g.stride; ok = okh && wn >= 0 && ws * g.stride == wn && ws < Ws; }
+                const float4 v = ok ? nn::ld4(xf + ((long long)hs * Ws + ws) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+                nn::st4(o + (long long)(r * g.kw + q) * C, v);
+            }
         }
-        const float4 v = ok ? nn::ld4(x + (((long long)f * Hs + hs) * Ws + ws) * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        nn::st4(col + row * g.ldk + (long long)tap * C + c, v);
     }
 }
 
@@ -312,7 +313,7 @@ extern "C" int lr_im2col_tap(const float* x, int F, int Hs, int Ws, int C, int k
     g.Hd = Hd; g.Wd = Wd; g.kh = kh; g.kw = kw; g.stride = stride; g.pad = pad; g.transposed = transposed;
     g.K = C * kh * kw; g.ldk = g.K;
     const long long rows = (long long)F * Hd * Wd;
-    c2::im2col_tap_kernel<<<c2::grid_for(rows * kh * kw * (C >> 2)), c2::TH, 0, stream>>>(x, g, Hs, Ws, C, col, rows);
+    c2::im2col_tap_kernel<<<c2::grid_for(rows * (C >> 2)), c2::TH, 0, stream>>>(x, g, Hs, Ws, C, col, rows);
     lr::count_launch();
     LR_CHECK_LAUNCH("im2col_tap_kernel");
     return LR_OK;

@@ -172,3 +172,11 @@ def gemm_tf32(A, lda, a_trans, B, ldb, b_trans, C, ldc, M, N, K, bias=None, act=
     """Tensor-core GEMM (TF32 products, fp32 accumulate), same layout flags / epilogue as gemm()."""
     check(lib.lr_gemm_tf32(_p(A), lda, a_trans, _p(B), ldb, b_trans, _p(C), ldc, M, N, K, _p(bias), act, _p(R), ldr,
                            _p(stats), ksplit, _s()))
+
+
+def im2col_tap(x, F, Hs, Ws, C, kh, kw, stride, pad, transposed, Hd, Wd, col):
+    check(lib.lr_im2col_tap(_p(x), F, Hs, Ws, C, kh, kw, stride, pad, int(transposed), Hd, Wd, _p(col), _s()))
+
+
+def weight_tap(src, dst, Cout, Cin, kk, mode):
+    check(lib.lr_weight_tap(_p(src), _p(dst), Cout, Cin, kk, mode, _s()))

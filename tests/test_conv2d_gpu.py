@@ -165,3 +165,42 @@ def test_relu6_and_act_fwd(cuda_device):
     dy = torch.ones_like(x)
     K.act_bwd(dy, y, x.numel(), K.ACT_RELU6)
     assert torch.equal(dy, ((y > 0) & (y < 6)).float())
+
+
+@pytest.mark.parametrize("Cin,Cout,k,stride,pad,H,W", [(8, 16, 3, 1, 1, 9, 7), (8, 12, 3, 2, 1, 11, 10), (16, 8, 1, 2, 0, 9, 9),
+                                                        (64, 64, 3, 1, 1, 11, 11), (32, 64, 3, 2, 1, 6, 6)])
+def test_tap_major_conv_fwd_dgrad_wgrad(cuda_device, Cin, Cout, k, stride, pad, H, W):
+    """The ResNet path: tap-major patch matrix (lr_im2col_tap) with the weight layouts of lr_weight_tap."""
+    from multimodal_lipread_b200 import kernels as K
+    torch.manual_seed(0)
+    F = 3
+    x = torch.randn(F, Cin, H, W, requires_grad=True)
+    w = torch.randn(Cout, Cin, k, k, requires_grad=True)
+    y = Fn.conv2d(x, w, stride=stride, padding=pad)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    Ho, Wo = y.shape[2], y.shape[3]
+    Kd, kk = Cin * k * k, k * k
+    xd, wd_ = _cl(x.detach()).cuda(), w.detach().cuda().contiguous()
+    col = torch.full((F * Ho * Wo, Kd), 7.0, device="cuda")
+    K.im2col_tap(xd, F, H, W, Cin, k, k, stride, pad, False, Ho, Wo, col)
+    wp = torch.empty(Cout, Kd, device="cuda")
+    K.weight_tap(wd_, wp, Cout, Cin, kk, 0)
+    assert torch.equal(wp.cpu().view(Cout, kk, Cin), w.detach().reshape(Cout, Cin, kk).permute(0, 2, 1))
+    yd = torch.empty(F * Ho * Wo, Cout, device="cuda")
+    K.gemm(col, Kd, 0, wp, Kd, 0, yd, Cout, F * Ho * Wo, Cout, Kd)
+    torch.testing.assert_close(yd.cpu().view(F, Ho, Wo, Cout), _cl(y.detach()), rtol=1e-4, atol=1e-4)
+    dyd = _cl(dy).cuda().view(F * Ho * Wo, Cout)
+    dwp = torch.zeros(Cout, Kd, device="cuda")
+    K.gemm(dyd, Cout, 1, col, Kd, 1, dwp, Kd, Cout, Kd, F * Ho * Wo, R=dwp, ldr=Kd)
+    dw = torch.empty(Cout, Cin, k, k, device="cuda")
+    K.weight_tap(dwp, dw, Cout, Cin, kk, 2)
+    torch.testing.assert_close(dw.cpu(), w.grad, rtol=1e-4, atol=3e-4)
+    Kt = Cout * kk
+    wt = torch.empty(Cin, Kt, device="cuda")
+    K.weight_tap(wd_, wt, Cout, Cin, kk, 1)
+    colT = torch.empty(F * H * W, Kt, device="cuda")
+    K.im2col_tap(dyd, F, Ho, Wo, Cout, k, k, stride, pad, True, H, W, colT)
+    dx = torch.empty(F * H * W, Cin, device="cuda")
+    K.gemm(colT, Kt, 0, wt, Kt, 0, dx, Cin, F * H * W, Cin, Kt)
+    torch.testing.assert_close(dx.cpu().view(F, H, W, Cin), _cl(x.grad), rtol=1e-4, atol=3e-4)
