@@ -51,8 +51,8 @@ __device__ __forceinline__ Coef coef4(const Bn& b, int c) {
 // z = act(x * scale + shift) (+ residual).  Block (0,0) also performs the running-statistics update.
 __global__ void __launch_bounds__(TH, 4)
 bn_act_fwd_kernel(const Bn b, const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ z,
-                  int rows_per_block, int res_pre) {
-    const nn::CgMap map(b.C, blockIdx.y * blockDim.x);
+                  int rows_per_block, int res_pre, int gw) {
+    const nn::CgMap map(b.C, blockIdx.y * gw, gw);
     if (b.training && b.running_mean && blockIdx.x == 0 && blockIdx.y == 0) {
         for (int c = threadIdx.x; c < b.C; c += blockDim.x) {
             const double n = (double)b.rows;
@@ -112,11 +112,12 @@ __device__ __forceinline__ float4 mask_by_out(float4 g, const float4 z, int act)
 // backward pass 1: dy = dz * act'(u), u = x*scale + shift;  sums[c] += dy, sums[C+c] += dy * xhat
 __global__ void __launch_bounds__(TH, 3)
 bn_act_bwd_reduce_kernel(const Bn b, const float* __restrict__ x, const float* __restrict__ dz,
-                         const float* __restrict__ zo, double* __restrict__ sums, int rows_per_block) {
-    extern __shared__ float sh[];                       // [2C]
-    for (int i = threadIdx.x; i < 2 * b.C; i += blockDim.x) sh[i] = 0.f;
+                         const float* __restrict__ zo, double* __restrict__ sums, int rows_per_block, int gw) {
+    extern __shared__ float sh[];                       // [2C] (only this block column's channels are touched)
+    const int c_lo = blockIdx.y * gw * 4, c_hi = min(b.C, c_lo + gw * 4);
+    for (int i = c_lo + threadIdx.x; i < c_hi; i += blockDim.x) { sh[i] = 0.f; sh[b.C + i] = 0.f; }
     __syncthreads();
-    const nn::CgMap map(b.C, blockIdx.y * blockDim.x);
+    const nn::CgMap map(b.C, blockIdx.y * gw, gw);
     if (map.active) {
         const int c = map.cg * 4;
         const Coef k = coef4(b, c);
@@ -154,7 +155,10 @@ bn_act_bwd_reduce_kernel(const Bn b, const float* __restrict__ x, const float* _
         atomicAdd(&sh[b.C + c + 2], s2.z); atomicAdd(&sh[b.C + c + 3], s2.w);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * b.C; i += blockDim.x) nn::atomic_add_double(sums + i, (double)sh[i]);
+    for (int i = c_lo + threadIdx.x; i < c_hi; i += blockDim.x) {
+        nn::atomic_add_double(sums + i, (double)sh[i]);
+        nn::atomic_add_double(sums + b.C + i, (double)sh[b.C + i]);
+    }
 }
 
 // backward pass 2: dx = gamma*invstd * (dy - mean(dy) - xhat * mean(dy*xhat))   (training)
@@ -164,14 +168,14 @@ __global__ void __launch_bounds__(TH, 3)
 bn_act_bwd_apply_kernel(const Bn b, const float* __restrict__ x, const float* __restrict__ dz,
                         const float* __restrict__ zo, float* __restrict__ dres,
                         const double* __restrict__ sums, float* __restrict__ dx, float* __restrict__ dgamma,
-                        float* __restrict__ dbeta, int rows_per_block) {
+                        float* __restrict__ dbeta, int rows_per_block, int gw) {
     if (blockIdx.x == 0 && blockIdx.y == 0 && dgamma) {
         for (int c = threadIdx.x; c < b.C; c += blockDim.x) {
             dbeta[c] += (float)sums[c];
             dgamma[c] += (float)sums[b.C + c];
         }
     }
-    const nn::CgMap map(b.C, blockIdx.y * blockDim.x);
+    const nn::CgMap map(b.C, blockIdx.y * gw, gw);
     if (!map.active) return;
     const int c = map.cg * 4;
     // dx = scale * (dy - mean(dy) - xhat * mean(dy * xhat)) with xhat = (x - mean) * invstd, folded into per-channel
@@ -255,8 +259,8 @@ frame_reduce_kernel(const float* __restrict__ a, const float* __restrict__ g, fl
 //   avg-pool backward     : a = null, dp = gradient of the pooled value
 __global__ void __launch_bounds__(TH)
 frame_scale_kernel(const float* __restrict__ a, const float* __restrict__ s, const float* __restrict__ dp,
-                   float* __restrict__ out, long long rows, int HW, int C, float inv_hw, int rows_per_block) {
-    const nn::CgMap map(C, blockIdx.y * blockDim.x);
+                   float* __restrict__ out, long long rows, int HW, int C, float inv_hw, int rows_per_block, int gw) {
+    const nn::CgMap map(C, blockIdx.y * gw, gw);
     if (!map.active) return;
     const int c = map.cg * 4;
     const long long r0 = (long long)blockIdx.x * rows_per_block;
@@ -320,14 +324,19 @@ copy2d_kernel(float* __restrict__ dst, long long ldd, const float* __restrict__ 
 }  // namespace bn
 
 // ------------------------------------------------------------------------------------------ C ABI
-static int rows_per_block_for(long long rows, int C, int* grid_x) {
+// grid of the streaming [rows, C] kernels: block columns of gw channel groups (grid.y) x row ranges (grid.x), about
+// 8 blocks per SM in total, every block at least 4 passes of its row lanes deep
+static int rows_per_block_for(long long rows, int C, dim3* grid, int* gw_out) {
     const int ncg = C >> 2;
-    const int w = ncg < bn::TH ? ncg : bn::TH;
-    const int rpp = bn::TH / w;
-    long long rpb = (rows + (long long)lr::sm_count() * 8 - 1) / ((long long)lr::sm_count() * 8);
+    const int gw = nn::cg_col_width(C);
+    const int ncols = (ncg + gw - 1) / gw;
+    const int rpp = bn::TH / gw;                                  // row lanes of a full-width column
+    long long want = ((long long)lr::sm_count() * 8 + ncols - 1) / ncols;
+    long long rpb = (rows + want - 1) / want;
+    if (rpb < 4LL * rpp) rpb = 4LL * rpp;
     rpb = ((rpb + rpp - 1) / rpp) * rpp;
-    if (rpb < rpp) rpb = rpp;
-    *grid_x = (int)((rows + rpb - 1) / rpb);
+    *grid = dim3((unsigned)((rows + rpb - 1) / rpb), (unsigned)ncols);
+    *gw_out = gw;
     return (int)rpb;
 }
 
@@ -352,11 +361,10 @@ extern "C" int lr_bn_act_fwd(const float* x, const double* stats, const float* g
     LR_BN_CHECK("lr_bn_act_fwd");
     LR_CHECK_ARG(x && gamma && beta && z, "lr_bn_act_fwd: null pointer");
     LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(z); LR_CHECK_ALIGN(residual);
-    int gx; const int rpb = rows_per_block_for(rows, C, &gx);
-    dim3 grid(gx, nn::cg_block_cols(C, bn::TH));
+    dim3 grid; int gw; const int rpb = rows_per_block_for(rows, C, &grid, &gw);
     bn::bn_act_fwd_kernel<<<grid, bn::TH, 0, stream>>>(
         make_bn(rows, C, stats, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, act, training),
-        x, residual, z, rpb, res_pre);
+        x, residual, z, rpb, res_pre, gw);
     lr::count_launch();
     LR_CHECK_LAUNCH("bn_act_fwd_kernel");
     return LR_OK;
@@ -371,14 +379,13 @@ extern "C" int lr_bn_act_bwd(const float* x, const double* stats, const float* g
     LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(dz); LR_CHECK_ALIGN(dx); LR_CHECK_ALIGN(z_out); LR_CHECK_ALIGN(dres);
     LR_CHECK_ARG(!z_out || act == LR_ACT_RELU || act == LR_ACT_RELU6 || act == LR_ACT_NONE,
                  "lr_bn_act_bwd: output-form derivative exists for ReLU / ReLU6 only");
-    int gx; const int rpb = rows_per_block_for(rows, C, &gx);
-    dim3 grid(gx, nn::cg_block_cols(C, bn::TH));
+    dim3 grid; int gw; const int rpb = rows_per_block_for(rows, C, &grid, &gw);
     const bn::Bn b = make_bn(rows, C, stats, gamma, beta, const_cast<float*>(running_mean),
                              const_cast<float*>(running_var), nullptr, eps, 0.f, act, training);
-    bn::bn_act_bwd_reduce_kernel<<<grid, bn::TH, 2 * C * sizeof(float), stream>>>(b, x, dz, z_out, sums, rpb);
+    bn::bn_act_bwd_reduce_kernel<<<grid, bn::TH, 2 * C * sizeof(float), stream>>>(b, x, dz, z_out, sums, rpb, gw);
     lr::count_launch();
     LR_CHECK_LAUNCH("bn_act_bwd_reduce_kernel");
-    bn::bn_act_bwd_apply_kernel<<<grid, bn::TH, 0, stream>>>(b, x, dz, z_out, dres, sums, dx, dgamma, dbeta, rpb);
+    bn::bn_act_bwd_apply_kernel<<<grid, bn::TH, 0, stream>>>(b, x, dz, z_out, dres, sums, dx, dgamma, dbeta, rpb, gw);
     lr::count_launch();
     LR_CHECK_LAUNCH("bn_act_bwd_apply_kernel");
     return LR_OK;
@@ -405,9 +412,8 @@ extern "C" int lr_frame_scale(const float* a, const float* s, const float* dp, f
     LR_CHECK_ARG(out, "lr_frame_scale: null pointer");
     LR_CHECK_ALIGN(a); LR_CHECK_ALIGN(s); LR_CHECK_ALIGN(dp); LR_CHECK_ALIGN(out);
     const long long rows = (long long)F * HW;
-    int gx; const int rpb = rows_per_block_for(rows, C, &gx);
-    dim3 grid(gx, nn::cg_block_cols(C, bn::TH));
-    bn::frame_scale_kernel<<<grid, bn::TH, 0, stream>>>(a, s, dp, out, rows, HW, C, 1.f / (float)HW, rpb);
+    dim3 grid; int gw; const int rpb = rows_per_block_for(rows, C, &grid, &gw);
+    bn::frame_scale_kernel<<<grid, bn::TH, 0, stream>>>(a, s, dp, out, rows, HW, C, 1.f / (float)HW, rpb, gw);
     lr::count_launch();
     LR_CHECK_LAUNCH("frame_scale_kernel");
     return LR_OK;

@@ -48,9 +48,12 @@ struct CgMap {
     int rlane;      // this thread's row lane
     int rpp;        // rows per pass of the block
     bool active;
-    __device__ __forceinline__ CgMap(int C, int cg0 /*first group handled by this block column*/) {
+    // maxw: channel groups per block column (0: as many as the block has threads).  A narrow column (32 groups = 128
+    // channels) keeps all threads busy for wide layers (row lanes = threads / width) and shrinks the per-block
+    // statistic atomics to the column's channels.
+    __device__ __forceinline__ CgMap(int C, int cg0 /*first group handled by this block column*/, int maxw = 0) {
         ncg = C >> 2;
-        const int w = min(ncg - cg0, (int)blockDim.x);     // groups handled by this block column
+        const int w = min(ncg - cg0, maxw > 0 ? maxw : (int)blockDim.x);     // groups handled by this block column
         rpp = blockDim.x / w;
         cg = cg0 + threadIdx.x % w;
         rlane = threadIdx.x / w;
@@ -59,6 +62,8 @@ struct CgMap {
 };
 // number of block columns needed so that every channel group is owned by some thread
 inline int cg_block_cols(int C, int threads) { return ((C >> 2) + threads - 1) / threads; }
+// column width (in channel groups) of the streaming [rows, C] kernels: the whole row up to 32 groups, else 32
+inline int cg_col_width(int C) { const int ncg = C >> 2; return ncg <= 32 ? ncg : 32; }
 
 __device__ __forceinline__ void atomic_add_double(double* p, double v) { atomicAdd(p, v); }
 
