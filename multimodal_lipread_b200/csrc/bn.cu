@@ -24,14 +24,16 @@ struct Bn {
 // per-thread BN coefficients of the thread's 4 channels
 struct Coef { float4 scale, shift, mean, invstd; };
 
-__device__ __forceinline__ void coef1(const Bn& b, int c, float& scale, float& shift, float& mean, float& invstd) {
+// Mean and variance come from the double sums (the subtraction E[x^2] - E[x]^2 needs the precision); everything after
+// that is float like the tensor itself: the per-thread prologue must stay cheap next to a main loop of a few rows
+// (a double division or square root is a ~100-instruction sequence).
+__device__ __forceinline__ void coef1(const Bn& b, int c, double inv_n, float& scale, float& shift, float& mean, float& invstd) {
     if (b.training) {
-        const double n = (double)b.rows;
-        const double m = b.stats[c] / n;
-        double var = b.stats[b.C + c] / n - m * m;
+        const double m = b.stats[c] * inv_n;
+        double var = b.stats[b.C + c] * inv_n - m * m;
         if (var < 0.0) var = 0.0;
         mean = (float)m;
-        invstd = (float)(1.0 / sqrt(var + (double)b.eps));
+        invstd = 1.0f / sqrtf((float)var + b.eps);
     } else {
         mean = b.running_mean[c];
         invstd = 1.0f / sqrtf(b.running_var[c] + b.eps);
@@ -41,10 +43,11 @@ __device__ __forceinline__ void coef1(const Bn& b, int c, float& scale, float& s
 }
 __device__ __forceinline__ Coef coef4(const Bn& b, int c) {
     Coef k;
-    coef1(b, c, k.scale.x, k.shift.x, k.mean.x, k.invstd.x);
-    coef1(b, c + 1, k.scale.y, k.shift.y, k.mean.y, k.invstd.y);
-    coef1(b, c + 2, k.scale.z, k.shift.z, k.mean.z, k.invstd.z);
-    coef1(b, c + 3, k.scale.w, k.shift.w, k.mean.w, k.invstd.w);
+    const double inv_n = 1.0 / (double)b.rows;
+    coef1(b, c, inv_n, k.scale.x, k.shift.x, k.mean.x, k.invstd.x);
+    coef1(b, c + 1, inv_n, k.scale.y, k.shift.y, k.mean.y, k.invstd.y);
+    coef1(b, c + 2, inv_n, k.scale.z, k.shift.z, k.mean.z, k.invstd.z);
+    coef1(b, c + 3, inv_n, k.scale.w, k.shift.w, k.mean.w, k.invstd.w);
     return k;
 }
 

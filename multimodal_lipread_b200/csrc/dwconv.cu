@@ -9,6 +9,7 @@
 // that a one-output-per-thread mapping hits.  Reads are conflict-free (32 lanes = 32 consecutive channels).
 // The forward kernel also emits the per-channel sum / sum of squares (train-mode BatchNorm statistics).
 #include "nn_common.cuh"
+#include "dwconv_small.cuh"
 
 namespace dw {
 
@@ -430,6 +431,11 @@ extern "C" int lr_dwconv_fwd(const float* x, const float* w, float* y, double* s
     LR_DW_CHECK("lr_dwconv_fwd");
     LR_CHECK_ARG(x && w && y, "lr_dwconv_fwd: null pointer");
     LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(y);
+    if (dws::dispatch(0, x, w, y, stats, F, H, W, C, k, stride, stream)) {
+        lr::count_launch();
+        LR_CHECK_LAUNCH("dws::fwd_kernel");
+        return LR_OK;
+    }
     const int Wo = (W + 2 * (k / 2) - k) / stride + 1;
     const int ws = pick_ws(Wo, false);
     const Geo d = make_geo(F, H, W, C, k, stride, 0, ws);
@@ -453,6 +459,11 @@ extern "C" int lr_dwconv_dgrad(const float* dy, const float* w, float* dx, int F
     LR_DW_CHECK("lr_dwconv_dgrad");
     LR_CHECK_ARG(dy && w && dx, "lr_dwconv_dgrad: null pointer");
     LR_CHECK_ALIGN(dy); LR_CHECK_ALIGN(dx);
+    if (dws::dispatch(1, dy, w, dx, nullptr, F, H, W, C, k, stride, stream)) {
+        lr::count_launch();
+        LR_CHECK_LAUNCH("dws::dgrad_kernel");
+        return LR_OK;
+    }
     const int ws = pick_ws(W, stride == 2);
     const Geo d = make_geo(F, H, W, C, k, stride, 2, ws);
     LR_CHECK_ARG(d.rows_t * d.cols_t <= MAX_PIX, "lr_dwconv: image row of %d pixels is too wide for the staged tile", W);
@@ -475,6 +486,11 @@ extern "C" int lr_dwconv_wgrad(const float* dy, const float* x, float* dwt, int 
     LR_DW_CHECK("lr_dwconv_wgrad");
     LR_CHECK_ARG(dy && x && dwt, "lr_dwconv_wgrad: null pointer");
     LR_CHECK_ALIGN(dy); LR_CHECK_ALIGN(x);
+    if (dws::dispatch(2, dy, x, dwt, nullptr, F, H, W, C, k, stride, stream)) {
+        lr::count_launch();
+        LR_CHECK_LAUNCH("dws::wgrad_kernel");
+        return LR_OK;
+    }
     const int Wo = (W + 2 * (k / 2) - k) / stride + 1;
     const int ws = pick_ws(Wo, false);
     const Geo d = make_geo(F, H, W, C, k, stride, 1, ws);

@@ -113,9 +113,11 @@ def test_stem_conv(K, u8, size):
                                      # torchvision mobilenet_v2 (3x3 only) at 44 / 88 px lip frames
                                      (32, 3, 1, 22), (96, 3, 2, 22), (144, 3, 1, 11), (144, 3, 2, 11), (192, 3, 1, 6),
                                      (192, 3, 2, 6), (384, 3, 1, 3), (576, 3, 2, 3), (960, 3, 1, 2), (32, 3, 1, 44),
-                                     (96, 3, 2, 44), (144, 3, 1, 22), (960, 3, 1, 3), (576, 3, 2, 6)])
+                                     (96, 3, 2, 44), (144, 3, 1, 22), (960, 3, 1, 3), (576, 3, 2, 6),
+                                     # small-image kernels (dwconv_small.cuh): whole map per thread
+                                     (240, 5, 1, 6), (120, 5, 1, 6), (288, 5, 2, 6), (576, 5, 1, 3), (72, 5, 2, 3), (40, 3, 1, 6)])
 def test_dwconv(K, C, k, s, H):
-    F = 6
+    F = 6 if C != 120 else 37
     g = torch.Generator().manual_seed(C + k)
     conv = nn.Conv2d(C, C, k, s, k // 2, groups=C, bias=False)
     x = torch.randn(F, C, H, H, generator=g, requires_grad=True)
