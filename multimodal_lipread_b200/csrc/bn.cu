@@ -328,13 +328,14 @@ copy2d_kernel(float* __restrict__ dst, long long ldd, const float* __restrict__ 
 
 // ------------------------------------------------------------------------------------------ C ABI
 // grid of the streaming [rows, C] kernels: block columns of gw channel groups (grid.y) x row ranges (grid.x), about
-// 8 blocks per SM in total, every block at least 4 passes of its row lanes deep
-static int rows_per_block_for(long long rows, int C, dim3* grid, int* gw_out) {
+// 3 blocks per SM in total (= what fits at once: one wave, each thread streams many rows so that the coefficient
+// prologue and the statistic atomics are amortised), every block at least 4 passes of its row lanes deep
+static int rows_per_block_for(long long rows, int C, dim3* grid, int* gw_out, int blocks_per_sm = 3) {
     const int ncg = C >> 2;
     const int gw = nn::cg_col_width(C);
     const int ncols = (ncg + gw - 1) / gw;
     const int rpp = bn::TH / gw;                                  // row lanes of a full-width column
-    long long want = ((long long)lr::sm_count() * 8 + ncols - 1) / ncols;
+    long long want = ((long long)lr::sm_count() * blocks_per_sm + ncols - 1) / ncols;
     long long rpb = (rows + want - 1) / want;
     if (rpb < 4LL * rpp) rpb = 4LL * rpp;
     rpb = ((rpb + rpp - 1) / rpp) * rpp;
@@ -415,7 +416,7 @@ extern "C" int lr_frame_scale(const float* a, const float* s, const float* dp, f
     LR_CHECK_ARG(out, "lr_frame_scale: null pointer");
     LR_CHECK_ALIGN(a); LR_CHECK_ALIGN(s); LR_CHECK_ALIGN(dp); LR_CHECK_ALIGN(out);
     const long long rows = (long long)F * HW;
-    dim3 grid; int gw; const int rpb = rows_per_block_for(rows, C, &grid, &gw);
+    dim3 grid; int gw; const int rpb = rows_per_block_for(rows, C, &grid, &gw, 8);
     bn::frame_scale_kernel<<<grid, bn::TH, 0, stream>>>(a, s, dp, out, rows, HW, C, 1.f / (float)HW, rpb, gw);
     lr::count_launch();
     LR_CHECK_LAUNCH("frame_scale_kernel");

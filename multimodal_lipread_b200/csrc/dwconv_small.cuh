@@ -157,9 +157,10 @@ wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* _
     }
 }
 
-inline dim3 grid_for(int F, int C) {
+// blocks_per_sm: 4 for the streaming kernels; 1 for wgrad, whose every block ends in C/64 * K*K atomics
+inline dim3 grid_for(int F, int C, int blocks_per_sm = 4) {
     const int chunks = (C + CW - 1) / CW;
-    int gx = (lr::sm_count() * 4 + chunks - 1) / chunks;
+    int gx = (lr::sm_count() * blocks_per_sm + chunks - 1) / chunks;
     const int maxgx = (F + FL - 1) / FL;
     if (gx > maxgx) gx = maxgx;
     if (gx < 1) gx = 1;
@@ -169,7 +170,7 @@ inline dim3 grid_for(int F, int C) {
 // mode 0 fwd (a = x, b = w, out = y, stats), 1 dgrad (a = dy, b = w, out = dx), 2 wgrad (a = dy, b = x, out = dw)
 template <int H, int K, int S>
 inline void launch(int mode, const float* a, const float* b, float* out, double* stats, int F, int C, cudaStream_t st) {
-    const dim3 grid = grid_for(F, C);
+    const dim3 grid = grid_for(F, C, mode == 2 ? 1 : 4);
     if (mode == 0) fwd_kernel<H, K, S><<<grid, TH, 0, st>>>(a, b, out, stats, F, C);
     else if (mode == 1) dgrad_kernel<H, K, S><<<grid, TH, 0, st>>>(a, b, out, F, C);
     else wgrad_kernel<H, K, S><<<grid, TH, 0, st>>>(a, b, out, F, C);
