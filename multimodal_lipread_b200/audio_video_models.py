@@ -29,29 +29,25 @@ class MidFusionPlan(ModelPlan):
         flat, with_backward = self.flat, self.with_backward
         video, layout, scale = self.video_input()
         T, H, W = layout[2], layout[3], layout[4]
-        mel = self.audio_input()
-
-        # ---- audio branch: conv+relu+pool -> [B,37120] -> audio_fc -> fused[:, 0:FA]
         FA = m.audio_fc.out_features
         HL = m.video_lstm.hidden_size
         FD = FA + 2 * HL
         self.fused = self.alloc(B * FD)
         dfused = self.alloc(B * FD) if with_backward else None
         KA = m.audio_fc.in_features
-        a_pool = self.alloc(B * KA)
-        a_arg = self.alloc(B * KA, torch.uint8)
-        conv = m.audio_cnn[0]
-        self.fwd.add("lr_audio_conv_fwd", mel, conv.weight, conv.bias, a_pool, KA, a_arg, B, N_MELS, N_FRAMES_OUT)
         ks = engine._ksplit(B, FA, KA, self.sms)
         if ks > 1:
             self.fwd.add("lr_memset", self.fused, B * FD * 4)          # split-K accumulates onto zeros
-        self.linear(a_pool, KA, B, m.audio_fc.weight, m.audio_fc.bias, self.fused, FD, ksplit=ks)
-        if with_backward:
-            d_pool = self.alloc(B * KA)
-            g = self.bgroup()
-            self.linear_bwd(g, a_pool, KA, B, m.audio_fc.weight, m.audio_fc.bias, dfused, FD, dx=d_pool, ldx=KA)
-            g.add("lr_audio_conv_bwd", mel, d_pool, KA, a_arg, flat.g(conv.weight), flat.g(conv.bias), B, N_MELS,
-                  N_FRAMES_OUT, leaf=True)
+
+        # ---- audio branch (independent of the video trunk: its own branch of the step graph):
+        #      [log-mel ->] conv+relu+pool -> [B,37120] -> audio_fc -> fused[:, 0:FA]
+        with self.fwd.side_branch():
+            mel = self.audio_input()
+            a_pool = self.alloc(B * KA)
+            a_arg = self.alloc(B * KA, torch.uint8)
+            conv = m.audio_cnn[0]
+            self.fwd.add("lr_audio_conv_fwd", mel, conv.weight, conv.bias, a_pool, KA, a_arg, B, N_MELS, N_FRAMES_OUT)
+            self.linear(a_pool, KA, B, m.audio_fc.weight, m.audio_fc.bias, self.fused, FD, ksplit=ks)
 
         # ---- video trunk: MobileNetV3-small features + avgpool -> feat [B*T, 576]
         last = self.mbv3_features(m.video_cnn.features, video, layout, scale, B, T, H, W)
@@ -59,6 +55,16 @@ class MidFusionPlan(ModelPlan):
         # ---- BiLSTM with an out[:, -1] head, written straight into the fusion row (no torch.cat)
         self.bilstm_last(feat, dfeat, last.C, B, T, m.video_lstm, self.fused.data_ptr() + 4 * FA, FD,
                          (dfused.data_ptr() + 4 * FA) if with_backward else 0)
+        if with_backward:
+            # the audio branch's backward is registered HERE so that it runs right after the classifier's (groups run in
+            # reverse registration order), all of it on the side branch, next to the LSTM / trunk backward
+            d_pool = self.alloc(B * KA)
+            g = self.bgroup()
+            with g.side_branch():
+                self.linear_bwd(g, a_pool, KA, B, m.audio_fc.weight, m.audio_fc.bias, dfused, FD, dx=d_pool, ldx=KA)
+                g.add("lr_audio_conv_bwd", mel, d_pool, KA, a_arg, flat.g(conv.weight), flat.g(conv.bias), B, N_MELS,
+                      N_FRAMES_OUT)
+        self.fwd.join()
         # ---- classifier: Linear(FD,256)+ReLU -> Linear(256,C)
         logits, dlogits = self.mlp(self.fused, dfused, B, m.classifier)
         self.set_logits(logits, dlogits)
@@ -174,12 +180,13 @@ class EarlyFusionPlan(ModelPlan):
         wb = self.with_backward
         video, layout, scale = self.video_input()
         T, H, W = layout[2], layout[3], layout[4]
-        mel = self.audio_input()
         DA, DV = m.audio_encoder.output_dim, m.video_encoder.output_dim
         FD = DA + DV
         self.fused = self.alloc(B * FD)
         dfused = self.alloc(B * FD) if wb else None
-        audio_encoder_plan(self, m.audio_encoder, mel, B, self.fused, FD, dfused)
+        with self.fwd.side_branch():                       # the audio encoder is independent of the video trunk
+            mel = self.audio_input()
+            audio_encoder_plan(self, m.audio_encoder, mel, B, self.fused, FD, dfused)
         ve = m.video_encoder
         if m.backbone == "mobilenet_v3_small":
             last = self.mbv3_features(ve.cnn.features, video, layout, scale, B, T, H, W)
@@ -188,6 +195,7 @@ class EarlyFusionPlan(ModelPlan):
         feat, dfeat = self.avgpool(last)
         self.bilstm_last(feat, dfeat, last.C, B, T, ve.lstm, self.fused.data_ptr() + 4 * DA, FD,
                          (dfused.data_ptr() + 4 * DA) if wb else 0)
+        self.fwd.join()
         logits, dlogits = self.mlp(self.fused, dfused, B, m.classifier)
         self.set_logits(logits, dlogits)
 

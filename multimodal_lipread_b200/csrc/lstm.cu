@@ -468,6 +468,7 @@ lstm_fwd_coop_kernel(const ls::Fwd p) {
 #pragma unroll
     for (int r = 0; r < RPT; ++r) cst[r] = 0.f;
     const int col = c * U + u;
+    const bool vec_out = (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
     for (int s = 0; s < p.nsteps; ++s) {
         const int t = p.reverse ? p.T - 1 - s : s;
         const int tprev = p.reverse ? t + 1 : t - 1;
@@ -478,7 +479,8 @@ lstm_fwd_coop_kernel(const ls::Fwd p) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (s > 0 && b < p.B) {
                 const float* src = p.out + ((long long)b * p.T + tprev) * p.ldo + k4;
-                v = make_float4(__ldcg(src), __ldcg(src + 1), __ldcg(src + 2), __ldcg(src + 3));
+                v = vec_out ? __ldcg(reinterpret_cast<const float4*>(src))
+                            : make_float4(__ldcg(src), __ldcg(src + 1), __ldcg(src + 2), __ldcg(src + 3));
             }
             *reinterpret_cast<float4*>(hb + r * HP + k4) = v;
         }
@@ -588,19 +590,31 @@ lstm_bwd_coop_kernel(const ls::Bwd p) {
             float acc[RPT];
 #pragma unroll
             for (int r = 0; r < RPT; ++r) acc[r] = 0.f;
-            for (int j0 = 0; j0 < G; j0 += JC) {
-                __syncthreads();
-                for (int i = threadIdx.x; i < BG * (JC / 4); i += TH) {
+            // chunks of JC columns are double buffered through registers: the next chunk's L2 loads are in flight
+            // while the current one is multiplied
+            constexpr int PF = BG * (JC / 4) / TH;                        // float4 per thread and chunk (8)
+            float4 pre[PF];
+            auto fetch = [&](int j0) {
+#pragma unroll
+                for (int q = 0; q < PF; ++q) {
+                    const int i = threadIdx.x + q * TH;
                     const int r = i / (JC / 4), j4 = (i - r * (JC / 4)) * 4;
                     const int b = b0 + r;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (b < p.B) {
-                        const float* src = p.dgates + ((long long)b * p.T + t) * G + j0 + j4;
-                        v = make_float4(__ldcg(src), __ldcg(src + 1), __ldcg(src + 2), __ldcg(src + 3));
-                    }
-                    *reinterpret_cast<float4*>(dgs + r * JP + j4) = v;
+                    pre[q] = b < p.B ? __ldcg(reinterpret_cast<const float4*>(p.dgates + ((long long)b * p.T + t) * G + j0 + j4))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            fetch(0);
+            for (int j0 = 0; j0 < G; j0 += JC) {
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < PF; ++q) {
+                    const int i = threadIdx.x + q * TH;
+                    const int r = i / (JC / 4), j4 = (i - r * (JC / 4)) * 4;
+                    *reinterpret_cast<float4*>(dgs + r * JP + j4) = pre[q];
                 }
                 __syncthreads();
+                if (j0 + JC < G) fetch(j0 + JC);
 #pragma unroll 4
                 for (int j = 0; j < JC; j += 4) {
                     float w[4];

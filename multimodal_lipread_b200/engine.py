@@ -39,14 +39,38 @@ class OpList:
 
     def __init__(self):
         self.ops = []
+        self._branch = False
 
     def add(self, name, *args, leaf=False):
-        """leaf=True marks an op whose output nobody reads before the optimizer (weight / bias gradients): such
-        ops may run on a side stream concurrently with the dgrad chain (run_forked)."""
-        self.ops.append((getattr(lib, name), tuple(a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args), name, leaf))
+        """leaf=True marks an op whose output nobody reads before the next join (weight / bias gradients: the end of
+        the backward): such ops may run on a side stream concurrently with the main chain (run_forked)."""
+        self.ops.append((getattr(lib, name), tuple(a.data_ptr() if isinstance(a, torch.Tensor) else a for a in args), name,
+                         leaf or self._branch))
+
+    def side_branch(self):
+        """Context manager: every op added inside belongs to an independent branch (e.g. the audio encoder next to the
+        video trunk) and is marked leaf; `join()` marks where the main chain needs the branch's results."""
+        ops = self
+
+        class _Ctx:
+            def __enter__(self):
+                ops._branch = True
+
+            def __exit__(self, *exc):
+                ops._branch = False
+        return _Ctx()
+
+    def join(self):
+        self.ops.append((None, (), "__join__", False))
+
+    def kernels(self):
+        """The launches proper (join markers excluded)."""
+        return [op for op in self.ops if op[0] is not None]
 
     def run(self, stream):
         for fn, args, name, _ in self.ops:
+            if fn is None:
+                continue
             rc = fn(*args, stream)
             if rc != 0:
                 raise _lib.LipreadError(f"{name} failed ({rc}): {lib.lr_last_error().decode()}")
@@ -58,6 +82,11 @@ class OpList:
         ms, ss = main.cuda_stream, side.cuda_stream
         forked = False
         for fn, args, name, leaf in self.ops:
+            if fn is None:                                 # join: the main chain needs everything the side branch produced
+                if forked:
+                    main.wait_stream(side)
+                    forked = False
+                continue
             if leaf:
                 ev = torch.cuda.Event()
                 ev.record(main)
@@ -72,16 +101,16 @@ class OpList:
             main.wait_stream(side)
 
     def __len__(self):
-        return len(self.ops)
+        return len(self.kernels())
 
     def profile(self, stream_obj, reps=5):
         """Eager launches with a CUDA-event pair around every op on the launching stream; returns
         [(name, args, mean ms)] in launch order (used by bench.py for the per-kernel roofline)."""
         s = stream_obj.cuda_stream
-        acc = [0.0] * len(self.ops)
+        acc = [0.0] * len(self.kernels())
         for _ in range(reps):
             evs = []
-            for fn, args, name, _ in self.ops:
+            for fn, args, name, _ in self.kernels():
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(stream_obj)
                 rc = fn(*args, s)
@@ -92,7 +121,7 @@ class OpList:
             stream_obj.synchronize()
             for i, (a, b) in enumerate(evs):
                 acc[i] += a.elapsed_time(b)
-        return [(name, args, t / reps) for (fn, args, name, _), t in zip(self.ops, acc)]
+        return [(name, args, t / reps) for (fn, args, name, _), t in zip(self.kernels(), acc)]
 
 
 def profile_ops_graph(ops, reps=20, flush=None):
@@ -102,7 +131,7 @@ def profile_ops_graph(ops, reps=20, flush=None):
     replay, e.g. an L2 flush.  Returns [(name, args, ms per launch)]."""
     out = []
     s = torch.cuda.Stream()
-    for fn, args, name, _ in ops.ops:
+    for fn, args, name, _ in ops.kernels():
         g = torch.cuda.CUDAGraph()
         with torch.cuda.stream(s):
             rc = fn(*args, s.cuda_stream)                      # warm (lazy module load / attributes) outside capture

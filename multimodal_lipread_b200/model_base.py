@@ -173,9 +173,13 @@ class ModelPlan(engine.Plan):
                     self.correct, B, C, 1.0 / B)
 
     # -- execution ---------------------------------------------------------------------------------------
-    def run_forward(self, stream):
+    def run_forward(self, stream, forked=None):
+        """forked = (main, side) torch streams: ops of an independent branch (OpList.side_branch) run on `side`."""
         self.pre.run(stream)
-        self.fwd.run(stream)
+        if forked is None:
+            self.fwd.run(stream)
+        else:
+            self.fwd.run_forked(*forked)
 
     def run_backward(self, stream, forked=None):
         """forked = (main, side) torch streams: weight-gradient kernels run on `side` concurrently with the
@@ -329,7 +333,7 @@ class PlanModel(nn.Module):
         o = self._opt
 
         def compute(stream, forked=None):
-            plan.run_forward(stream)
+            plan.run_forward(stream, forked)
             plan.ce.run(stream)
             plan.run_backward(stream, forked)
 
