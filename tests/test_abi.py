@@ -24,7 +24,8 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_version_and_host_only_calls():
     from multimodal_lipread_b200 import _lib
-    assert _lib.lib.lr_version() == 1
+    header = open(os.path.join(ROOT, "include", "lipread_b200.h")).read()
+    assert _lib.lib.lr_version() == int(re.search(r"#define\s+LR_ABI_VERSION\s+(\d+)", header).group(1)) >= 2
     assert _lib.lib.lr_logmel_plan_bytes() % 16 == 0 and _lib.lib.lr_logmel_plan_bytes() > 9000
     assert _lib.launch_count() >= 0
 
