@@ -1,17 +1,54 @@
 """Audio-only classifiers behind the reference's nn.Module surface (audio/models/*.py).
 
-  AudioResNet      audio/models/resnet_model.py:5-39   (model.name == "resnet": BASELINE config 1)
+  AudioResNet          audio/models/resnet_model.py:5-39        (model.name == "resnet": BASELINE config 1)
+  AudioResNetLSTM      audio/models/resnet_lstm_model.py:5-59   (model.name == "resnet_lstm")
+  VGGAudioClassifier   audio/models/vgg_model.py:5-58           (model.name == "vgg")
 
 forward(spec (B,80,117) f32 log-mel) -> (B, num_classes); with a raw (B,20000) waveform the fused log-mel kernel
 runs first.  Sub-modules are parameter containers (reference names / construction order / state_dict keys)."""
 import types
 
 import torch.nn as nn
-from torchvision.models import resnet18
+from torchvision.models import resnet18, vgg11_bn, vgg13_bn, vgg16_bn, vgg19_bn
 
 from . import engine
 from ._lib import ACT_NONE, ACT_RELU
 from .model_base import ModelPlan, PlanModel, N_MELS, N_FRAMES_OUT
+
+
+def bn_head(plan, feat, dfeat, B, head):
+    """Linear -> [BatchNorm1d] -> ReLU -> Dropout -> Linear (resnet_model.py:19-33, resnet_lstm_model.py:32-44,
+    vgg_model.py:20-32).  Returns (logits, dlogits) buffers."""
+    wb = plan.with_backward
+    fc1 = head[0]
+    D = fc1.out_features
+    i = 1
+    if isinstance(head[i], nn.BatchNorm1d):
+        cur, dcur = plan.linear_bn_act(feat, dfeat, B, fc1, head[i], ACT_RELU)
+        i += 2                                           # BatchNorm1d, ReLU
+    else:
+        cur = plan.alloc(B * D)
+        dcur = plan.alloc(B * D) if wb else None
+        plan.linear(feat, fc1.in_features, B, fc1.weight, fc1.bias, cur, D, act=ACT_RELU)
+        if wb:
+            g = plan.bgroup()
+            g.add("lr_act_bwd", dcur, cur, B * D, ACT_RELU)
+            plan.linear_bwd(g, feat, fc1.in_features, B, fc1.weight, fc1.bias, dcur, D, dx=dfeat, ldx=fc1.in_features)
+        i += 1                                           # ReLU
+    drop, fc2 = head[i], head[i + 1]
+    cur, dcur = plan.dropout(cur, dcur, B * D, drop.p)
+    C = fc2.out_features
+    logits = plan.alloc(B * C)
+    dlogits = plan.alloc(B * C) if wb else None
+    plan.linear(cur, D, B, fc2.weight, fc2.bias, logits, C, act=ACT_NONE)
+    if wb:
+        plan.linear_bwd(plan.bgroup(), cur, D, B, fc2.weight, fc2.bias, dlogits, C, dx=dcur, ldx=D)
+    return logits, dlogits
+
+
+def _mel_frames(mel, B):
+    # x.unsqueeze(1): (B,1,80,117) NCHW with one channel == NHWC with C = 1
+    return (mel, (0, B, 1, N_MELS, N_FRAMES_OUT, N_MELS * N_FRAMES_OUT, 0, 0, N_FRAMES_OUT, 1), 1.0)
 
 
 class AudioResNetPlan(ModelPlan):
@@ -23,29 +60,7 @@ class AudioResNetPlan(ModelPlan):
         frames = (mel, (0, B, 1, N_MELS, N_FRAMES_OUT, N_MELS * N_FRAMES_OUT, 0, 0, N_FRAMES_OUT, 1), 1.0)
         last = self.resnet_features(net, frames)
         feat, dfeat = self.avgpool(last)
-        head = list(net.fc)
-        fc1 = head[0]
-        D = fc1.out_features
-        i = 1
-        if isinstance(head[i], nn.BatchNorm1d):
-            cur, dcur = self.linear_bn_act(feat, dfeat, B, fc1, head[i], ACT_RELU)
-            i += 2                                           # BatchNorm1d, ReLU
-        else:
-            cur = self.alloc(B * D)
-            dcur = self.alloc(B * D) if wb else None
-            self.linear(feat, fc1.in_features, B, fc1.weight, fc1.bias, cur, D, act=ACT_RELU)
-            if wb:
-                g = self.bgroup()
-                g.add("lr_act_bwd", dcur, cur, B * D, ACT_RELU)
-                self.linear_bwd(g, feat, fc1.in_features, B, fc1.weight, fc1.bias, dcur, D, dx=dfeat, ldx=fc1.in_features)
-            i += 1                                           # ReLU
-        drop, fc2 = head[i], head[i + 1]
-        cur, dcur = self.dropout(cur, dcur, B * D, drop.p)
-        logits = self.alloc(B * self.num_classes)
-        dlogits = self.alloc(B * self.num_classes) if wb else None
-        self.linear(cur, D, B, fc2.weight, fc2.bias, logits, self.num_classes, act=ACT_NONE)
-        if wb:
-            self.linear_bwd(self.bgroup(), cur, D, B, fc2.weight, fc2.bias, dlogits, self.num_classes, dx=dcur, ldx=D)
+        logits, dlogits = bn_head(self, feat, dfeat, B, list(net.fc))
         self.set_logits(logits, dlogits)
 
 
@@ -72,8 +87,101 @@ class AudioResNet(PlanModel):
         self.resnet.fc = nn.Sequential(*layers)
 
 
+class AudioResNetLstmPlan(ModelPlan):
+    def build(self, m, spec):
+        B, wb = self.B, self.with_backward
+        mel = self.audio_input()
+        last = self.resnet_features(m.resnet, _mel_frames(mel, B))
+        feat, dfeat = self.avgpool(last)
+        # features.unsqueeze(1): a sequence of length 1 through the 2-layer BiLSTM, lstm_out[:, -1, :]
+        D = 2 * m.lstm.hidden_size
+        seq = self.alloc(B * D)
+        dseq = self.alloc(B * D) if wb else None
+        self.bilstm_last(feat, dfeat, last.C, B, 1, m.lstm, seq, D, dseq if wb else 0)
+        logits, dlogits = bn_head(self, seq, dseq, B, list(m.classifier))
+        self.set_logits(logits, dlogits)
+
+
+class AudioResNetLSTM(PlanModel):
+    """audio/models/resnet_lstm_model.py:5-59."""
+    INPUTS = ("audio",)
+    PLAN = AudioResNetLstmPlan
+    DEFAULT_LR = 5e-4
+    DEFAULT_WD = 1e-4
+
+    def __init__(self, num_classes=40, lstm_hidden=128, lstm_layers=2, dropout_rate=0.3, use_batchnorm=True,
+                 pretrained_state_dict=None, precision=None):
+        super().__init__()
+        self._init_base(num_classes, types.SimpleNamespace(get=lambda k, d=None: d), precision)
+        self.use_bn = use_batchnorm
+        self.resnet = resnet18(weights=None)
+        if pretrained_state_dict is not None:
+            self.resnet.load_state_dict(pretrained_state_dict)
+        self.resnet.conv1 = nn.Conv2d(1, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.resnet.fc = nn.Identity()
+        self.lstm = nn.LSTM(input_size=512, hidden_size=lstm_hidden, num_layers=lstm_layers, bidirectional=True,
+                            batch_first=True)
+        layers = [nn.Linear(2 * lstm_hidden, 256)]
+        if use_batchnorm:
+            layers.append(nn.BatchNorm1d(256))
+        layers.extend([nn.ReLU(), nn.Dropout(dropout_rate), nn.Linear(256, num_classes)])
+        self.classifier = nn.Sequential(*layers)
+
+
+class VGGAudioPlan(ModelPlan):
+    def build(self, m, spec):
+        B, wb = self.B, self.with_backward
+        mel = self.audio_input()
+        kind, fmap = self.cnn_sequential(list(m.vgg.features), _mel_frames(mel, B))
+        assert kind == "map"
+        osz = m.adaptive_pool.output_size
+        if (fmap.H, fmap.W) != tuple(osz):
+            raise NotImplementedError(f"AdaptiveAvgPool2d{tuple(osz)} on a {fmap.H}x{fmap.W} map")
+        # torch.flatten(x, 1) of the NCHW map: channel-major
+        K = fmap.H * fmap.W * fmap.C
+        flat_in = self.alloc(B * K)
+        dflat = self.alloc(B * K) if wb else None
+        self.fwd.add("lr_flatten_nchw", fmap.val, flat_in, K, B, fmap.H * fmap.W, fmap.C, 1)
+        if wb:
+            self.bgroup().add("lr_flatten_nchw", fmap.grad, dflat, K, B, fmap.H * fmap.W, fmap.C, 0)
+        logits, dlogits = bn_head(self, flat_in, dflat, B, list(m.vgg.classifier))
+        self.set_logits(logits, dlogits)
+
+
+class VGGAudioClassifier(PlanModel):
+    """audio/models/vgg_model.py:5-58 (torchvision vgg{11,13,16,19}_bn features with a 1-channel first conv)."""
+    INPUTS = ("audio",)
+    PLAN = VGGAudioPlan
+    DEFAULT_LR = 5e-4
+    DEFAULT_WD = 1e-4
+
+    def __init__(self, num_classes=40, version=11, dropout_rate=0.5, use_batchnorm=True, pretrained_state_dict=None,
+                 precision=None):
+        super().__init__()
+        self._init_base(num_classes, types.SimpleNamespace(get=lambda k, d=None: d), precision)
+        self.use_bn = use_batchnorm
+        ctor = {11: vgg11_bn, 13: vgg13_bn, 16: vgg16_bn, 19: vgg19_bn}.get(version)
+        if ctor is None:
+            raise ValueError(f"Invalid VGG version: {version}")
+        # init_weights=False: what torchvision does when (as in the reference) pretrained weights are requested
+        self.vgg = ctor(weights=None, init_weights=False)
+        if pretrained_state_dict is not None:
+            self.vgg.load_state_dict(pretrained_state_dict)
+        self.vgg.features[0] = nn.Conv2d(1, 64, kernel_size=3, padding=1)
+        self.adaptive_pool = nn.AdaptiveAvgPool2d((2, 3))
+        layers = [nn.Linear(512 * 2 * 3, 256)]
+        if use_batchnorm:
+            layers.append(nn.BatchNorm1d(256))
+        layers.extend([nn.ReLU(), nn.Dropout(dropout_rate), nn.Linear(256, num_classes)])
+        self.vgg.classifier = nn.Sequential(*layers)
+
+
 def get_model(num_classes, input_size, model_name, version=None):
     """audio/train.py:118-134 (the variants with a lipread_b200 plan)."""
     if model_name == "resnet":
         return AudioResNet(num_classes=num_classes)
+    if model_name == "resnet_lstm":
+        return AudioResNetLSTM(num_classes=num_classes)
+    if model_name == "vgg":
+        return VGGAudioClassifier(num_classes=num_classes, version=version or 11)
     raise ValueError(f"Invalid model name: {model_name}")

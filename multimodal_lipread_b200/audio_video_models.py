@@ -120,45 +120,13 @@ class AudioEncoder(nn.Module):
 
 
 def audio_cnn_plan(plan, cnn, mel, B):
-    """nn.Sequential of Conv2d(3x3, padding 1) [+ BatchNorm2d] + ReLU, MaxPool2d(2), AdaptiveAvgPool2d(1) on the mel
-    (B,80,117) viewed as a 1-channel NHWC image.  Returns ("pooled", feat, dfeat, C) after an AdaptiveAvgPool2d or
-    ("map", T2) when the Sequential ends on a feature map."""
+    """An audio CNN Sequential on the mel (B,80,117) viewed as a 1-channel NHWC image (see Plan.cnn_sequential)."""
     mods = list(cnn)
     if mods[0].in_channels != 1:
         raise ValueError("audio CNN plans handle dataset.audio_channels == 1 (the reference default)")
     # (B,80,117) contiguous == NHWC with C = 1
     frames = (mel, (0, B, 1, N_MELS, N_FRAMES_OUT, N_MELS * N_FRAMES_OUT, 0, 0, N_FRAMES_OUT, 1), 1.0)
-    cur, pooled = None, None
-    i = 0
-    while i < len(mods):
-        m = mods[i]
-        if isinstance(m, nn.Conv2d):
-            has_bn = isinstance(mods[i + 1], nn.BatchNorm2d)
-            if has_bn:
-                raw = plan.dense_conv(cur, m, frames=frames if cur is None else None)
-                if plan.with_backward:
-                    plan.dense_conv_bwd(raw)
-                a = engine.T2(plan, raw.F, raw.H, raw.W, raw.C)
-                plan.bn_act(raw, mods[i + 1], ACT_RELU, a)
-                cur = a
-                i += 3                                       # conv, bn, relu
-            else:
-                assert isinstance(mods[i + 1], nn.ReLU)
-                cur = plan.dense_conv(cur, m, frames=frames if cur is None else None, act=ACT_RELU, with_stats=False)
-                if plan.with_backward:
-                    plan.dense_conv_bwd(cur)
-                i += 2                                       # conv, relu
-        elif isinstance(m, nn.MaxPool2d):
-            cur = plan.maxpool(cur, 2, 2, 0)
-            i += 1
-        elif isinstance(m, nn.AdaptiveAvgPool2d):
-            pooled = plan.avgpool(cur)
-            i += 1
-        else:
-            raise NotImplementedError(type(m).__name__)
-    if pooled is not None:
-        return "pooled", pooled[0], pooled[1], cur.C
-    return "map", cur
+    return plan.cnn_sequential(mods, frames)
 
 
 def audio_encoder_plan(plan, enc, mel, B, out, ldo, dout):

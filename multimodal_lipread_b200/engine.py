@@ -665,6 +665,51 @@ class Plan:
                 self.bgroup().add("lr_dropout_bwd", dy, mask, dx, n, float(p))
         return y, dy
 
+    def cnn_sequential(self, mods, frames):
+        """nn.Sequential of Conv2d(3x3, padding 1) [+ BatchNorm2d] + ReLU, MaxPool2d(2) and a closing
+        AdaptiveAvgPool2d on frames = (tensor, layout, scale): the audio encoders of audio_video/models/*.py, VGGLite
+        (video/models/vgg_lstm.py:21-41), torchvision vgg*_bn features (audio/models/vgg_model.py:11-13).
+        Returns ("pooled", feat, dfeat, C) after AdaptiveAvgPool2d(1) or ("map", T2) when it ends on a feature map."""
+        cur, pooled = None, None
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Conv2d):
+                has_bn = isinstance(mods[i + 1], nn.BatchNorm2d)
+                if has_bn:
+                    assert isinstance(mods[i + 2], nn.ReLU)
+                    raw = self.dense_conv(cur, m, frames=frames if cur is None else None)
+                    if self.with_backward:
+                        self.dense_conv_bwd(raw)
+                    a = T2(self, raw.F, raw.H, raw.W, raw.C)
+                    self.bn_act(raw, mods[i + 1], ACT_RELU, a)
+                    cur = a
+                    i += 3                                       # conv, bn, relu
+                else:
+                    assert isinstance(mods[i + 1], nn.ReLU)
+                    cur = self.dense_conv(cur, m, frames=frames if cur is None else None, act=ACT_RELU, with_stats=False)
+                    if self.with_backward:
+                        self.dense_conv_bwd(cur)
+                    i += 2                                       # conv, relu
+            elif isinstance(m, nn.MaxPool2d):
+                k = m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0]
+                st = m.stride if isinstance(m.stride, int) else m.stride[0]
+                pd = m.padding if isinstance(m.padding, int) else m.padding[0]
+                cur = self.maxpool(cur, k, st, pd)
+                i += 1
+            elif isinstance(m, nn.AdaptiveAvgPool2d):
+                osz = m.output_size if isinstance(m.output_size, tuple) else (m.output_size, m.output_size)
+                if tuple(osz) == (1, 1):
+                    pooled = self.avgpool(cur)
+                elif tuple(osz) != (cur.H, cur.W):
+                    raise NotImplementedError(f"AdaptiveAvgPool2d{tuple(osz)} on a {cur.H}x{cur.W} map")
+                i += 1                                           # output size == input size: identity
+            else:
+                raise NotImplementedError(type(m).__name__)
+        if pooled is not None:
+            return "pooled", pooled[0], pooled[1], cur.C
+        return "map", cur
+
     # ---- nn.LSTM (batch_first, bidirectional) with an out[:, -1] head -------------------------------------
     def bilstm_last(self, x, dx, I, B, T, lstm, out, ldo, dout):
         """x: [B*T, I] features (dx: its gradient buffer, written here).  Writes out[b, 0:2H] (row stride ldo) =

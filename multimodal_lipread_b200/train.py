@@ -71,6 +71,8 @@ def create_video_model(model_name, num_classes, config):
         return M.ResNet2DBiLSTM(num_classes=num_classes, config=config)
     if model_name == "mobilenet_lstm":
         return M.MobileNetLSTM(num_classes=num_classes, config=config)
+    if model_name == "vgg_lstm":
+        return M.VGGLSTM(num_classes=num_classes, config=config)
     if model_name in VIDEO_MODELS:
         _no_plan(model_name)
     raise ValueError(f"Unknown model: {model_name}")
@@ -81,6 +83,10 @@ def create_audio_model(model_name, num_classes, input_size=117, version=None):
     from . import audio_models as M
     if model_name == "resnet":
         return M.AudioResNet(num_classes=num_classes)
+    if model_name == "resnet_lstm":
+        return M.AudioResNetLSTM(num_classes=num_classes)
+    if model_name == "vgg":
+        return M.VGGAudioClassifier(num_classes=num_classes, version=version or 11)
     if model_name in AUDIO_MODELS:
         _no_plan(model_name)
     raise ValueError(f"Invalid model name: {model_name}")

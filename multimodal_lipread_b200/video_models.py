@@ -2,6 +2,7 @@
 
   ResNet2DBiLSTM / create_model      video/models/resnet_lstm.py:56-177   (model.name == "resnet_lstm")
   MobileNetLSTM                      video/models/mobilenet_lstm.py:18-72  (model.name == "mobilenet_lstm")
+  VGGLSTM                            video/models/vgg_lstm.py:14-92        (model.name == "vgg_lstm")
 
 Sub-modules are parameter containers only (same names, construction order and `state_dict` keys as the reference,
 including the CNN appearing twice -- `cnn_features.*` and `time_distributed_cnn.module.0.*` share tensors);
@@ -37,16 +38,23 @@ class ResNetLstmPlan(ModelPlan):
         if hasattr(m, "cnn_features"):
             last = self.resnet_features(_resnet_view(m.cnn_features), (video, layout, scale))
             lstm, drop = m.bilstm, m.dropout
+            feat, dfeat = self.avgpool(last)
+            feat_dim = last.C
+        elif isinstance(m, VGGLSTM):
+            kind, feat, dfeat, feat_dim = self.cnn_sequential(list(m.td.module.features), (video, layout, scale))
+            assert kind == "pooled"
+            lstm, drop = m.lstm, m.dropout
         else:
             last = self.mbv2_features(m.cnn[0], (video, layout, scale))
             lstm, drop = m.lstm, m.drop
-        feat, dfeat = self.avgpool(last)
+            feat, dfeat = self.avgpool(last)
+            feat_dim = last.C
         D = 2 * lstm.hidden_size
         seq_last = self.alloc(B * D)
         h = self.alloc(B * D)
         dh = self.alloc(B * D) if wb else None
         # dh is turned into the gradient of x[:, -1] in place by the ReLU backward below, which runs first
-        self.bilstm_last(feat, dfeat, last.C, B, T, lstm, seq_last, D, dh if wb else 0)
+        self.bilstm_last(feat, dfeat, feat_dim, B, T, lstm, seq_last, D, dh if wb else 0)
         # x[:, -1] -> ReLU -> Dropout -> fc   (resnet_lstm.py:151-154)
         self.fwd.add("lr_act_fwd", seq_last, h, B * D, ACT_RELU)
         if wb:
@@ -119,6 +127,41 @@ class MobileNetLSTM(PlanModel):
         self.relu = nn.ReLU()
         self.drop = nn.Dropout(dropout)
         self.fc = nn.Linear(feature_dim, num_classes)
+
+
+class VGGLite(nn.Module):
+    """video/models/vgg_lstm.py:16-45 (parameter container)."""
+
+    def __init__(self):
+        super().__init__()
+        self.features = nn.Sequential(
+            nn.Conv2d(3, 32, 3, padding=1), nn.ReLU(True), nn.Conv2d(32, 32, 3, padding=1), nn.ReLU(True), nn.MaxPool2d(2),
+            nn.Conv2d(32, 64, 3, padding=1), nn.ReLU(True), nn.Conv2d(64, 64, 3, padding=1), nn.ReLU(True), nn.MaxPool2d(2),
+            nn.Conv2d(64, 128, 3, padding=1), nn.ReLU(True), nn.AdaptiveAvgPool2d((1, 1)))
+
+
+class VGGLSTM(PlanModel):
+    """video/models/vgg_lstm.py:48-88: VGGLite per frame, 2-layer BiLSTM, x[:, -1] -> ReLU -> Dropout -> fc."""
+    INPUTS = ("video",)
+    PLAN = None                  # set below (the plan class is shared with the ResNet / MobileNet variants)
+    DEFAULT_LR = 5e-5
+    DEFAULT_WD = 1e-5
+
+    def __init__(self, num_classes, config=None, precision=None):
+        super().__init__()
+        config = config or Cfg()
+        self._init_base(num_classes, config, precision)
+        feature_dim = config.get("model.feature_dim", 256)
+        dropout = config.get("model.dropout", 0.5)
+        self.td = TimeDistributed(VGGLite())
+        self.lstm = nn.LSTM(input_size=128, hidden_size=feature_dim // 2, num_layers=2, bidirectional=True,
+                            batch_first=True, dropout=dropout)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+        self.fc = nn.Linear(feature_dim, num_classes)
+
+
+VGGLSTM.PLAN = ResNetLstmPlan
 
 
 def create_model(num_classes, config=None):

@@ -15,6 +15,9 @@ there is no network for the ImageNet checkpoint:
   LateFusionMobileOracle      audio_cues_video/models/late_fusion_mobile.py:6-107
   LateFusionResNetOracle      audio_cues_video/models/late_fusion_resnet.py:6-99
   MobileNetLSTMOracle         video/models/mobilenet_lstm.py:18-68
+  VGGLSTMOracle               video/models/vgg_lstm.py:14-88
+  AudioResNetLSTMOracle       audio/models/resnet_lstm_model.py:5-59
+  VGGAudioOracle              audio/models/vgg_model.py:5-58
   LateFusionAVMobileNetOracle audio_video/models/late_fusion.py:10-93
   MidFusionAVMobileNetOracle  audio_video/models/middle_fusion.py:11-85
   EarlyFusionFastOracle       audio_video/models/early_fusion_fast.py:6-76
@@ -25,7 +28,7 @@ records their outputs; ``tests/test_oracle_golden.py`` pins these restatements t
 """
 import torch
 import torch.nn as nn
-from torchvision.models import mobilenet_v2, mobilenet_v3_small, resnet18
+from torchvision.models import mobilenet_v2, mobilenet_v3_small, resnet18, vgg11_bn, vgg13_bn, vgg16_bn, vgg19_bn
 
 
 class DictConfig:
@@ -309,6 +312,77 @@ class MobileNetLSTMOracle(nn.Module):
     def forward(self, x):
         x, _ = self.lstm(self.td(x))
         return self.fc(self.drop(self.relu(x[:, -1, :])))
+
+
+class VGGLSTMOracle(nn.Module):
+    """video/models/vgg_lstm.py:14-88: VGGLite per frame (5 convs + ReLU, 2 max pools, global average), 2-layer BiLSTM."""
+
+    class _VGGLite(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.features = nn.Sequential(
+                nn.Conv2d(3, 32, 3, padding=1), nn.ReLU(True), nn.Conv2d(32, 32, 3, padding=1), nn.ReLU(True), nn.MaxPool2d(2),
+                nn.Conv2d(32, 64, 3, padding=1), nn.ReLU(True), nn.Conv2d(64, 64, 3, padding=1), nn.ReLU(True), nn.MaxPool2d(2),
+                nn.Conv2d(64, 128, 3, padding=1), nn.ReLU(True), nn.AdaptiveAvgPool2d((1, 1)))
+
+        def forward(self, x):
+            return self.features(x).flatten(1)
+
+    def __init__(self, num_classes, config=None):
+        super().__init__()
+        config = config or DictConfig()
+        feature_dim = config.get("model.feature_dim", 256)
+        dropout = config.get("model.dropout", 0.5)
+        self.td = _TimeDistributed(self._VGGLite())
+        self.lstm = nn.LSTM(128, feature_dim // 2, num_layers=2, bidirectional=True, batch_first=True, dropout=dropout)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+        self.fc = nn.Linear(feature_dim, num_classes)
+
+    def forward(self, x):
+        x, _ = self.lstm(self.td(x))
+        return self.fc(self.dropout(self.relu(x[:, -1, :])))
+
+
+class AudioResNetLSTMOracle(nn.Module):
+    """audio/models/resnet_lstm_model.py:5-59: ResNet-18 features as a length-1 sequence through a 2-layer BiLSTM."""
+
+    def __init__(self, num_classes=40, lstm_hidden=128, lstm_layers=2, dropout_rate=0.3, use_batchnorm=True):
+        super().__init__()
+        self.use_bn = use_batchnorm
+        self.resnet = resnet18(weights=None)
+        self.resnet.conv1 = nn.Conv2d(1, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.resnet.fc = nn.Identity()
+        self.lstm = nn.LSTM(512, lstm_hidden, num_layers=lstm_layers, bidirectional=True, batch_first=True)
+        layers = [nn.Linear(2 * lstm_hidden, 256)]
+        if use_batchnorm:
+            layers.append(nn.BatchNorm1d(256))
+        layers.extend([nn.ReLU(), nn.Dropout(dropout_rate), nn.Linear(256, num_classes)])
+        self.classifier = nn.Sequential(*layers)
+
+    def forward(self, x):
+        out, _ = self.lstm(self.resnet(x.unsqueeze(1)).unsqueeze(1))
+        return self.classifier(out[:, -1, :])
+
+
+class VGGAudioOracle(nn.Module):
+    """audio/models/vgg_model.py:5-58."""
+
+    def __init__(self, num_classes=40, version=11, dropout_rate=0.5, use_batchnorm=True):
+        super().__init__()
+        self.use_bn = use_batchnorm
+        self.vgg = {11: vgg11_bn, 13: vgg13_bn, 16: vgg16_bn, 19: vgg19_bn}[version](weights=None, init_weights=False)
+        self.vgg.features[0] = nn.Conv2d(1, 64, kernel_size=3, padding=1)
+        self.adaptive_pool = nn.AdaptiveAvgPool2d((2, 3))
+        layers = [nn.Linear(512 * 2 * 3, 256)]
+        if use_batchnorm:
+            layers.append(nn.BatchNorm1d(256))
+        layers.extend([nn.ReLU(), nn.Dropout(dropout_rate), nn.Linear(256, num_classes)])
+        self.vgg.classifier = nn.Sequential(*layers)
+
+    def forward(self, x):
+        x = self.adaptive_pool(self.vgg.features(x.unsqueeze(1)))
+        return self.vgg.classifier(torch.flatten(x, 1))
 
 
 class _VideoLstm(nn.Module):

@@ -214,6 +214,23 @@ def golden_models():
     model = mod.MultimodalAttentionLateResNet(C, cue_dim=768, video_cfg=None, pretrained=False)
     model.video.lstm.dropout = 0.0
     record("acv_late_fusion_resnet", model, (mel, synthetic.make_cues(B), video), labels, 1e-5, 0.0, B, T, size)
+    # video vgg_lstm, audio resnet_lstm (dropout is a constructor argument) and audio vgg (version 11)
+    B, T, size, C = 3, 6, 44, 40
+    mod = load_ref("video", "models.vgg_lstm")
+    torch.manual_seed(0)
+    model = mod.VGGLSTM(C, DCfg({"model.dropout": 0.0}))
+    mel, video, labels = data(B, size, T, C)
+    record("video_vgg_lstm", model, (video,), labels, 5e-5, 1e-5, B, T, size)
+    B, C = 4, 8
+    mel, video, labels = data(B, 44, 1, C)
+    mod = load_ref("audio", "models.resnet_lstm_model")
+    torch.manual_seed(0)
+    model = mod.AudioResNetLSTM(num_classes=C, dropout_rate=0.0)
+    record("audio_resnet_lstm", model, (mel,), labels, 5e-4, 1e-4, B, 1, 44)
+    mod = load_ref("audio", "models.vgg_model")
+    torch.manual_seed(0)
+    model = mod.VGGAudioClassifier(num_classes=C, version=11, dropout_rate=0.0)
+    record("audio_vgg", model, (mel,), labels, 5e-4, 1e-4, B, 1, 44)
     # the remaining audio_video models (av_config.yaml:10), lr 3e-4
     B, T, size, C = 3, 8, 44, 40
     for name, module, factory, drop in (("late_fusion_mobilenet", "models.late_fusion", "create_late_fusion_mobilenet_model", False),
