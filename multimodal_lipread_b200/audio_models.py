@@ -3,6 +3,7 @@
   AudioResNet          audio/models/resnet_model.py:5-39        (model.name == "resnet": BASELINE config 1)
   AudioResNetLSTM      audio/models/resnet_lstm_model.py:5-59   (model.name == "resnet_lstm")
   VGGAudioClassifier   audio/models/vgg_model.py:5-58           (model.name == "vgg")
+  VGGWithLSTMClassifier audio/models/vgg_lstm_model.py:5-75     (model.name == "vgg_lstm")
 
 forward(spec (B,80,117) f32 log-mel) -> (B, num_classes); with a raw (B,20000) waveform the fused log-mel kernel
 runs first.  Sub-modules are parameter containers (reference names / construction order / state_dict keys)."""
@@ -176,6 +177,58 @@ class VGGAudioClassifier(PlanModel):
         self.vgg.classifier = nn.Sequential(*layers)
 
 
+class VGGLstmAudioPlan(ModelPlan):
+    def build(self, m, spec):
+        B, wb = self.B, self.with_backward
+        mel = self.audio_input()
+        kind, fmap = self.cnn_sequential(list(m.vgg_features), _mel_frames(mel, B))
+        assert kind == "map"
+        # AdaptiveAvgPool2d((None, 1)) + squeeze + permute: mean over W per (clip, row) -> a sequence of H steps of C
+        # features; on the channels-last map that is a per-"frame" pooling with frames = (clip, row)
+        T = fmap.H
+        rows_view = engine.T2.__new__(engine.T2)
+        rows_view.F, rows_view.H, rows_view.W, rows_view.C = B * T, 1, fmap.W, fmap.C
+        rows_view.rows, rows_view.val, rows_view.grad = fmap.rows, fmap.val, fmap.grad
+        feat, dfeat = self.avgpool(rows_view)
+        D = 2 * m.lstm.hidden_size
+        seq = self.alloc(B * D)
+        dseq = self.alloc(B * D) if wb else None
+        self.bilstm_last(feat, dfeat, fmap.C, B, T, m.lstm, seq, D, dseq if wb else 0)
+        logits, dlogits = bn_head(self, seq, dseq, B, list(m.classifier))
+        self.set_logits(logits, dlogits)
+
+
+class VGGWithLSTMClassifier(PlanModel):
+    """audio/models/vgg_lstm_model.py:5-75."""
+    INPUTS = ("audio",)
+    PLAN = VGGLstmAudioPlan
+    DEFAULT_LR = 5e-4
+    DEFAULT_WD = 1e-4
+
+    def __init__(self, num_classes=40, lstm_hidden_size=128, lstm_layers=2, version=11, dropout_rate=0.3,
+                 use_batchnorm=True, pretrained_state_dict=None, precision=None):
+        super().__init__()
+        self._init_base(num_classes, types.SimpleNamespace(get=lambda k, d=None: d), precision)
+        self.use_bn = use_batchnorm
+        ctor = {11: vgg11_bn, 13: vgg13_bn, 16: vgg16_bn, 19: vgg19_bn}.get(version)
+        if ctor is None:
+            raise ValueError(f"Invalid VGG version: {version}")
+        vgg = ctor(weights=None, init_weights=False)
+        if pretrained_state_dict is not None:
+            vgg.load_state_dict(pretrained_state_dict)
+        vgg.features[0] = nn.Conv2d(1, 64, kernel_size=3, padding=1)
+        self.vgg_features = vgg.features
+        self.adaptive_pool = nn.AdaptiveAvgPool2d((None, 1))
+        self.cnn_output_dim = 512
+        self.lstm = nn.LSTM(input_size=512, hidden_size=lstm_hidden_size, num_layers=lstm_layers, bidirectional=True,
+                            batch_first=True)
+        layers = [nn.Linear(2 * lstm_hidden_size, 128)]
+        if use_batchnorm:
+            layers.append(nn.BatchNorm1d(128))
+        layers.extend([nn.ReLU(), nn.Dropout(dropout_rate), nn.Linear(128, num_classes)])
+        self.classifier = nn.Sequential(*layers)
+
+
 def get_model(num_classes, input_size, model_name, version=None):
     """audio/train.py:118-134 (the variants with a lipread_b200 plan)."""
     if model_name == "resnet":
@@ -184,4 +237,6 @@ def get_model(num_classes, input_size, model_name, version=None):
         return AudioResNetLSTM(num_classes=num_classes)
     if model_name == "vgg":
         return VGGAudioClassifier(num_classes=num_classes, version=version or 11)
+    if model_name == "vgg_lstm":
+        return VGGWithLSTMClassifier(num_classes=num_classes, version=version or 11)
     raise ValueError(f"Invalid model name: {model_name}")

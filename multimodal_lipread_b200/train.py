@@ -87,6 +87,8 @@ def create_audio_model(model_name, num_classes, input_size=117, version=None):
         return M.AudioResNetLSTM(num_classes=num_classes)
     if model_name == "vgg":
         return M.VGGAudioClassifier(num_classes=num_classes, version=version or 11)
+    if model_name == "vgg_lstm":
+        return M.VGGWithLSTMClassifier(num_classes=num_classes, version=version or 11)
     if model_name in AUDIO_MODELS:
         _no_plan(model_name)
     raise ValueError(f"Invalid model name: {model_name}")

@@ -18,6 +18,7 @@ there is no network for the ImageNet checkpoint:
   VGGLSTMOracle               video/models/vgg_lstm.py:14-88
   AudioResNetLSTMOracle       audio/models/resnet_lstm_model.py:5-59
   VGGAudioOracle              audio/models/vgg_model.py:5-58
+  VGGLstmAudioOracle          audio/models/vgg_lstm_model.py:5-75
   LateFusionAVMobileNetOracle audio_video/models/late_fusion.py:10-93
   MidFusionAVMobileNetOracle  audio_video/models/middle_fusion.py:11-85
   EarlyFusionFastOracle       audio_video/models/early_fusion_fast.py:6-76
@@ -383,6 +384,30 @@ class VGGAudioOracle(nn.Module):
     def forward(self, x):
         x = self.adaptive_pool(self.vgg.features(x.unsqueeze(1)))
         return self.vgg.classifier(torch.flatten(x, 1))
+
+
+class VGGLstmAudioOracle(nn.Module):
+    """audio/models/vgg_lstm_model.py:5-75: vgg features, mean over the width, the height as the LSTM's time axis."""
+
+    def __init__(self, num_classes=40, lstm_hidden_size=128, lstm_layers=2, version=11, dropout_rate=0.3, use_batchnorm=True):
+        super().__init__()
+        self.use_bn = use_batchnorm
+        vgg = {11: vgg11_bn, 13: vgg13_bn, 16: vgg16_bn, 19: vgg19_bn}[version](weights=None, init_weights=False)
+        vgg.features[0] = nn.Conv2d(1, 64, kernel_size=3, padding=1)
+        self.vgg_features = vgg.features
+        self.adaptive_pool = nn.AdaptiveAvgPool2d((None, 1))
+        self.cnn_output_dim = 512
+        self.lstm = nn.LSTM(512, lstm_hidden_size, num_layers=lstm_layers, bidirectional=True, batch_first=True)
+        layers = [nn.Linear(2 * lstm_hidden_size, 128)]
+        if use_batchnorm:
+            layers.append(nn.BatchNorm1d(128))
+        layers.extend([nn.ReLU(), nn.Dropout(dropout_rate), nn.Linear(128, num_classes)])
+        self.classifier = nn.Sequential(*layers)
+
+    def forward(self, x):
+        x = self.adaptive_pool(self.vgg_features(x.unsqueeze(1))).squeeze(-1).permute(0, 2, 1)
+        out, _ = self.lstm(x)
+        return self.classifier(out[:, -1, :])
 
 
 class _VideoLstm(nn.Module):

@@ -231,6 +231,10 @@ def golden_models():
     torch.manual_seed(0)
     model = mod.VGGAudioClassifier(num_classes=C, version=11, dropout_rate=0.0)
     record("audio_vgg", model, (mel,), labels, 5e-4, 1e-4, B, 1, 44)
+    mod = load_ref("audio", "models.vgg_lstm_model")
+    torch.manual_seed(0)
+    model = mod.VGGWithLSTMClassifier(num_classes=C, version=11, dropout_rate=0.0)
+    record("audio_vgg_lstm", model, (mel,), labels, 5e-4, 1e-4, B, 1, 44)
     # the remaining audio_video models (av_config.yaml:10), lr 3e-4
     B, T, size, C = 3, 8, 44, 40
     for name, module, factory, drop in (("late_fusion_mobilenet", "models.late_fusion", "create_late_fusion_mobilenet_model", False),

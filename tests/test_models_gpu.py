@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 # implementations produce only summation round-off there (~1e-7 .. 1e-6), so those are checked for smallness.
 ZERO_GRAD_BN = ("audio_encoder.cnn.0.bias", "audio_encoder.cnn.4.bias", "audio_encoder.cnn.8.bias", "resnet.fc.0.bias",
                 "cue.net.0.bias", "classifier.0.bias", "vgg.classifier.0.bias") + tuple(
-                    f"vgg.features.{i}.bias" for i in (0, 4, 8, 11, 15, 18, 22, 25))       # vgg11_bn conv biases (BN follows)
+                    f"{pre}.{i}.bias" for pre in ("vgg.features", "vgg_features") for i in (0, 4, 8, 11, 15, 18, 22, 25))       # vgg11_bn conv biases (BN follows)
 ZERO_GRAD = ZERO_GRAD_BN
 
 
@@ -139,6 +139,8 @@ def _case(name, precision="fp32"):
         ref = O.AudioResNetLSTMOracle(C, dropout_rate=0.0)
     elif name == "audio_vgg":
         ref = O.VGGAudioOracle(C, version=11, dropout_rate=0.0)
+    elif name == "audio_vgg_lstm":
+        ref = O.VGGLstmAudioOracle(C, version=11, dropout_rate=0.0)
     elif name == "video_mobilenet_lstm":
         ref = O.MobileNetLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
     elif name == "acv_late_fusion_resnet":
@@ -168,6 +170,8 @@ def _case(name, precision="fp32"):
         ours = audio_models.AudioResNetLSTM(C, dropout_rate=0.0, precision=precision)
     elif name == "audio_vgg":
         ours = audio_models.VGGAudioClassifier(C, version=11, dropout_rate=0.0, precision=precision)
+    elif name == "audio_vgg_lstm":
+        ours = audio_models.VGGWithLSTMClassifier(C, version=11, dropout_rate=0.0, precision=precision)
     elif name == "video_mobilenet_lstm":
         ours = video_models.MobileNetLSTM(C, cfg, precision=precision)
     elif name == "acv_late_fusion_resnet":
@@ -214,6 +218,7 @@ def _inputs_for(name, mel, lips):
     ("video_vgg_lstm", 3, 6, 44),
     ("audio_resnet_lstm", 4, 1, 44),
     ("audio_vgg", 4, 1, 44),
+    ("audio_vgg_lstm", 4, 1, 44),
     ("acv_late_fusion_resnet", 3, 6, 44),
     ("late_fusion_mobilenet", 3, 8, 44),
     ("middle_fusion_mobilenet", 3, 8, 44),
@@ -271,7 +276,7 @@ def test_train_step_matches_oracle(cuda_device, name, B, T, size):
 
 
 @pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
-                                  "acv_late_fusion_resnet", "video_vgg_lstm", "audio_resnet_lstm", "audio_vgg",
+                                  "acv_late_fusion_resnet", "video_vgg_lstm", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm",
                                   "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast"])
 def test_golden_vectors_of_the_reference(cuda_device, golden_dir, name):
     """Outputs recorded from the reference's own modules (tests/golden/make_golden.py, dropout set to 0)."""

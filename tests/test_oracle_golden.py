@@ -114,7 +114,7 @@ def models_golden(golden_dir):
 
 
 @pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
-                                  "acv_late_fusion_resnet", "video_vgg_lstm", "audio_resnet_lstm", "audio_vgg",
+                                  "acv_late_fusion_resnet", "video_vgg_lstm", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm",
                                   "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast"])
 def test_model_oracles_match_reference(models_golden, name):
     from oracle import av_models as O
@@ -134,6 +134,8 @@ def test_model_oracles_match_reference(models_golden, name):
         model, lr, wd = O.AudioResNetLSTMOracle(C, dropout_rate=0.0), 5e-4, 1e-4
     elif name == "audio_vgg":
         model, lr, wd = O.VGGAudioOracle(C, version=11, dropout_rate=0.0), 5e-4, 1e-4
+    elif name == "audio_vgg_lstm":
+        model, lr, wd = O.VGGLstmAudioOracle(C, version=11, dropout_rate=0.0), 5e-4, 1e-4
     elif name == "video_mobilenet_lstm":
         model, lr, wd = O.MobileNetLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}})), 5e-5, 1e-5
     elif name == "acv_late_fusion_resnet":
@@ -158,7 +160,7 @@ def test_model_oracles_match_reference(models_golden, name):
     video = lips_u8_to_model_input(synthetic.make_lips_u8(B, size=size)[:, :T].contiguous())
     labels = synthetic.make_labels(B, C)
     inputs = {"video_resnet_lstm": (video,), "video_mobilenet_lstm": (video,), "video_vgg_lstm": (video,),
-              "audio_resnet": (mel,), "audio_resnet_lstm": (mel,), "audio_vgg": (mel,),
+              "audio_resnet": (mel,), "audio_resnet_lstm": (mel,), "audio_vgg": (mel,), "audio_vgg_lstm": (mel,),
               "acv_late_fusion_mobile": (mel, synthetic.make_cues(B), video),
               "acv_late_fusion_resnet": (mel, synthetic.make_cues(B), video)}.get(name, (mel, video))
     opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)

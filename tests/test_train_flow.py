@@ -36,6 +36,7 @@ def test_model_name_dispatch_and_errors():
     assert type(T.create_video_model("vgg_lstm", 40, cfg)).__name__ == "VGGLSTM"
     assert type(T.create_audio_model("resnet_lstm", 8)).__name__ == "AudioResNetLSTM"
     assert type(T.create_audio_model("vgg", 8, version=11)).__name__ == "VGGAudioClassifier"
+    assert type(T.create_audio_model("vgg_lstm", 8, version=11)).__name__ == "VGGWithLSTMClassifier"
     for name in ("shufflenet_lstm", "resnet_trans"):
         with pytest.raises(NotImplementedError):
             T.create_video_model(name, 40, cfg)          # a reference name without a plan fails loudly
