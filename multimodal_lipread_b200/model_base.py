@@ -314,6 +314,16 @@ class PlanModel(nn.Module):
         if self._flat is not None:
             self._flat.init_adam(lr)
 
+    def set_lr(self, lr):
+        """Change the learning rate between steps (what optim.lr_scheduler.ReduceLROnPlateau does to the reference's
+        optimizer, video/train.py:213-215, audio/train.py:156): the rate lives in the device-side Adam state, so
+        captured step graphs pick it up on their next replay."""
+        if not hasattr(self, "_opt"):
+            self.configure_optimizer()
+        self._opt["lr"] = float(lr)
+        if self._flat is not None and self._flat.adam_state is not None:
+            self._flat.adam_state[3] = float(lr)
+
     def train_step(self, *inputs_and_labels, grad_allreduce=None, world=1, use_graph=True):
         """One training iteration entirely in lipread_b200 kernels:
         [log-mel if the audio input is a raw (B,20000) waveform] -> forward -> CE -> backward -> [allreduce] -> Adam.

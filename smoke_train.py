@@ -1,10 +1,11 @@
-"""One tiny train step of MidFusionFast on the GPU, checked against the oracle (called by __graft_entry__.smoke)."""
+"""One tiny train step of MidFusionFast on the GPU, checked against the oracle (called by __graft_entry__.smoke).
+Lives at the repo root, outside the product package: nothing under multimodal_lipread_b200/ may import oracle/."""
 import torch
 
 
 def run(dev):
-    from . import synthetic
-    from .audio_video_models import MidFusionFast
+    from multimodal_lipread_b200 import synthetic
+    from multimodal_lipread_b200.audio_video_models import MidFusionFast
     from oracle.av_models import MidFusionFastOracle          # checker only (smoke() is allowed to use the oracle)
     from oracle.frontend import AudioProcessorPort, lips_u8_to_model_input
     B, C, size, T = 2, 40, 44, 8

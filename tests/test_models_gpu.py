@@ -327,6 +327,14 @@ def test_module_surface_autograd_and_graph(cuda_device):
         l, _ = ours.train_step(lips.cuda(), labels.cuda(), use_graph=True)
         losses.append(l.item())
     assert losses[-1] < losses[0]
+    # a scheduler changes the rate between steps (ReduceLROnPlateau in video/train.py:213-215): the captured graph follows
+    ours.set_lr(0.0)
+    before = ours._flat.flat.clone()
+    ours.train_step(lips.cuda(), labels.cuda(), use_graph=True)
+    assert torch.equal(before, ours._flat.flat)
+    ours.set_lr(1e-3)
+    ours.train_step(lips.cuda(), labels.cuda(), use_graph=True)
+    assert not torch.equal(before, ours._flat.flat)
     with pytest.raises(Exception):
         ours(video)                                        # CPU tensors: no CPU path
 
