@@ -127,6 +127,7 @@ bn_act_bwd_reduce_kernel(const Bn b, const float* __restrict__ x, const float* _
         const long long r0 = (long long)blockIdx.x * rows_per_block;
         const long long r1 = min(b.rows, r0 + rows_per_block);
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+        const unsigned long long keep = nn::l2_policy_evict_last();     // the apply pass re-reads x and dz right away
         constexpr int U = 4;
         const long long step = map.rpp;
         for (long long r = r0 + map.rlane; r < r1; r += U * step) {
@@ -134,8 +135,8 @@ bn_act_bwd_reduce_kernel(const Bn b, const float* __restrict__ x, const float* _
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (r + u * step < r1) {
-                    vv[u] = nn::ld4(x + (r + u * step) * b.C + c); gg[u] = nn::ld4(dz + (r + u * step) * b.C + c);
-                    if (zo) gg[u] = mask_by_out(gg[u], nn::ld4(zo + (r + u * step) * b.C + c), b.act);
+                    vv[u] = nn::ld4_hint(x + (r + u * step) * b.C + c, keep); gg[u] = nn::ld4_hint(dz + (r + u * step) * b.C + c, keep);
+                    if (zo) gg[u] = mask_by_out(gg[u], nn::ld4_hint(zo + (r + u * step) * b.C + c, keep), b.act);
                 }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -199,6 +200,7 @@ bn_act_bwd_apply_kernel(const Bn b, const float* __restrict__ x, const float* __
     }
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = min(b.rows, r0 + rows_per_block);
+    const unsigned long long drop = nn::l2_policy_evict_first();       // last use of x and dz
     constexpr int U = 4;
     const long long step = map.rpp;
     for (long long rb = r0 + map.rlane; rb < r1; rb += U * step) {
@@ -206,9 +208,9 @@ bn_act_bwd_apply_kernel(const Bn b, const float* __restrict__ x, const float* __
 #pragma unroll
       for (int u = 0; u < U; ++u)
           if (rb + u * step < r1) {
-              vv[u] = nn::ld4(x + (rb + u * step) * b.C + c); gg[u] = nn::ld4(dz + (rb + u * step) * b.C + c);
+              vv[u] = nn::ld4_hint(x + (rb + u * step) * b.C + c, drop); gg[u] = nn::ld4_hint(dz + (rb + u * step) * b.C + c, drop);
               if (zo) {
-                  gg[u] = mask_by_out(gg[u], nn::ld4(zo + (rb + u * step) * b.C + c), b.act);
+                  gg[u] = mask_by_out(gg[u], nn::ld4_hint(zo + (rb + u * step) * b.C + c, drop), b.act);
                   if (dres) nn::st4(dres + (rb + u * step) * b.C + c, gg[u]);     // gradient of the identity branch
               }
           }

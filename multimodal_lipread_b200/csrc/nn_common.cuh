@@ -39,6 +39,25 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act) {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// L2 residency hints for two-pass kernels: the first pass loads with evict_last so that the second pass (the next
+// kernel) finds the tensor in the 126 MB L2 instead of HBM; the second pass loads with evict_first.
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ld4_hint(const float* p, unsigned long long pol) {
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+
 // Channel-group mapping for a row-major [rows, C] tensor with C % 4 == 0: a thread owns ONE group of
 // 4 consecutive channels (so per-channel parameters live in registers) and strides over rows.
 // Consecutive threads touch consecutive float4s, so every warp access is fully coalesced.
