@@ -310,7 +310,18 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample}
         emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        # Orderly multi-rank exit.  The step graphs hold captured NCCL kernels: they are released BEFORE the
+        # communicator goes away (destroying the process group under live graphs, or leaving both to interpreter
+        # teardown, hung the job after the JSON line had been printed), then every rank leaves through os._exit once
+        # all of them are past the last collective.
+        import gc
+        wl.model._graphs.clear() if hasattr(wl, "model") else None
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
