@@ -172,9 +172,10 @@ int lr_im2col(const void* x, int is_u8, float scale, int F, int T, long long sb,
  * col[(f,hd,wd)][(r*kw + s)*C + c], a shifted float4 copy that is coalesced on both sides.  The matching weight
  * layouts come from lr_weight_tap: mode 0: wp[k][rs][c] = w[k][c][rs] (forward / wgrad operand), mode 1:
  * wp[c][rs][k] = w[k][c][rs] (dgrad operand), mode 2: w[k][c][rs] = wp[k][rs][c] (weight gradient back to torch's
- * layout). */
-int lr_im2col_tap(const float* x, int F, int Hs, int Ws, int C, int kh, int kw, int stride, int pad, int transposed,
-                  int Hd, int Wd, float* col, lr_stream_t stream);
+ * layout).  pad_h / pad_w are separate so that nn.Conv1d(k, padding=p) over time (video/models/cnn.py:35-42) runs as a
+ * 1 x k window (kh = 1, pad_h = 0, pad_w = p) on a [B, 1, T, C] map. */
+int lr_im2col_tap(const float* x, int F, int Hs, int Ws, int C, int kh, int kw, int stride, int pad_h, int pad_w,
+                  int transposed, int Hd, int Wd, float* col, lr_stream_t stream);
 int lr_weight_tap(const float* src, float* dst, int Cout, int Cin, int kk, int mode, lr_stream_t stream);
 /* wt[c][k*kk + rs] (row pitch ldt) = w[k][c][rs]: the dgrad weight of a dense convolution. */
 int lr_weight_transpose(const float* w, float* wt, int Cout, int Cin, int kk, long long ldt, lr_stream_t stream);

@@ -4,6 +4,7 @@
   AudioResNetLSTM      audio/models/resnet_lstm_model.py:5-59   (model.name == "resnet_lstm")
   VGGAudioClassifier   audio/models/vgg_model.py:5-58           (model.name == "vgg")
   VGGWithLSTMClassifier audio/models/vgg_lstm_model.py:5-75     (model.name == "vgg_lstm")
+  LSTMResNet           audio/models/lstm_resnet_model.py:5-71   (model.name == "lstm_resnet")
 
 forward(spec (B,80,117) f32 log-mel) -> (B, num_classes); with a raw (B,20000) waveform the fused log-mel kernel
 runs first.  Sub-modules are parameter containers (reference names / construction order / state_dict keys)."""
@@ -186,10 +187,7 @@ class VGGLstmAudioPlan(ModelPlan):
         # AdaptiveAvgPool2d((None, 1)) + squeeze + permute: mean over W per (clip, row) -> a sequence of H steps of C
         # features; on the channels-last map that is a per-"frame" pooling with frames = (clip, row)
         T = fmap.H
-        rows_view = engine.T2.__new__(engine.T2)
-        rows_view.F, rows_view.H, rows_view.W, rows_view.C = B * T, 1, fmap.W, fmap.C
-        rows_view.rows, rows_view.val, rows_view.grad = fmap.rows, fmap.val, fmap.grad
-        feat, dfeat = self.avgpool(rows_view)
+        feat, dfeat = self.avgpool(engine.T2.of(B * T, 1, fmap.W, fmap.C, fmap.val, fmap.grad))
         D = 2 * m.lstm.hidden_size
         seq = self.alloc(B * D)
         dseq = self.alloc(B * D) if wb else None
@@ -229,6 +227,80 @@ class VGGWithLSTMClassifier(PlanModel):
         self.classifier = nn.Sequential(*layers)
 
 
+class LstmResNetPlan(ModelPlan):
+    def build(self, m, spec):
+        B, wb = self.B, self.with_backward
+        mel = self.audio_input()
+        I = m.initial_bilstm.input_size
+        if I != N_FRAMES_OUT:
+            raise ValueError(f"LSTMResNet input_size {I} != {N_FRAMES_OUT} mel frames")
+        # x.view(B*80, 117).unsqueeze(1): every mel row is a length-1 sequence through the 2-layer BiLSTM(117 -> 64)
+        Bq = B * N_MELS
+        D0 = 2 * m.initial_bilstm.hidden_size
+        img = self.alloc(Bq * D0)
+        dimg = self.alloc(Bq * D0) if wb else None
+        self.bilstm_last(mel, None, I, Bq, 1, m.initial_bilstm, img, D0, dimg if wb else 0)
+        # .view(B, 1, 80, 128): a computed 1-channel image; the stem needs its input gradient
+        x = engine.T2.of(B, N_MELS, D0, 1, img, dimg)
+        last = self.resnet_features(m.resnet, None, x=x)
+        feat, dfeat = self.avgpool(last)
+        head = list(m.fc)
+        if isinstance(head[1], nn.BatchNorm1d):
+            h, dh = self.linear_bn_act(feat, dfeat, B, head[0], head[1], ACT_RELU)
+            drop = head[3]
+        else:
+            Dh = head[0].out_features
+            h = self.alloc(B * Dh)
+            dh = self.alloc(B * Dh) if wb else None
+            self.linear(feat, head[0].in_features, B, head[0].weight, head[0].bias, h, Dh, act=ACT_RELU)
+            if wb:
+                g = self.bgroup()
+                g.add("lr_act_bwd", dh, h, B * Dh, ACT_RELU)
+                self.linear_bwd(g, feat, head[0].in_features, B, head[0].weight, head[0].bias, dh, Dh, dx=dfeat,
+                                ldx=head[0].in_features)
+            drop = head[2]
+        Dh = head[0].out_features
+        h, dh = self.dropout(h, dh, B * Dh, drop.p)
+        D1 = 2 * m.final_bilstm.hidden_size
+        seq = self.alloc(B * D1)
+        dseq = self.alloc(B * D1) if wb else None
+        self.bilstm_last(h, dh, Dh, B, 1, m.final_bilstm, seq, D1, dseq if wb else 0)
+        C = self.num_classes
+        logits = self.alloc(B * C)
+        dlogits = self.alloc(B * C) if wb else None
+        self.linear(seq, D1, B, m.classifier.weight, m.classifier.bias, logits, C)
+        if wb:
+            self.linear_bwd(self.bgroup(), seq, D1, B, m.classifier.weight, m.classifier.bias, dlogits, C, dx=dseq, ldx=D1)
+        self.set_logits(logits, dlogits)
+
+
+class LSTMResNet(PlanModel):
+    """audio/models/lstm_resnet_model.py:5-71."""
+    INPUTS = ("audio",)
+    PLAN = LstmResNetPlan
+    DEFAULT_LR = 5e-4
+    DEFAULT_WD = 1e-4
+
+    def __init__(self, num_classes=40, input_size=117, dropout_rate=0.3, use_batchnorm=True, pretrained_state_dict=None,
+                 precision=None):
+        super().__init__()
+        self._init_base(num_classes, types.SimpleNamespace(get=lambda k, d=None: d), precision)
+        self.use_bn = use_batchnorm
+        self.initial_bilstm = nn.LSTM(input_size=input_size, hidden_size=64, num_layers=2, bidirectional=True, batch_first=True)
+        self.resnet = resnet18(weights=None)
+        if pretrained_state_dict is not None:
+            self.resnet.load_state_dict(pretrained_state_dict)
+        self.resnet.conv1 = nn.Conv2d(1, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.resnet.fc = nn.Identity()
+        layers = [nn.Linear(512, 256)]
+        if use_batchnorm:
+            layers.append(nn.BatchNorm1d(256))
+        layers.extend([nn.ReLU(), nn.Dropout(dropout_rate)])
+        self.fc = nn.Sequential(*layers)
+        self.final_bilstm = nn.LSTM(input_size=256, hidden_size=128, num_layers=2, bidirectional=True, batch_first=True)
+        self.classifier = nn.Linear(2 * 128, num_classes)
+
+
 def get_model(num_classes, input_size, model_name, version=None):
     """audio/train.py:118-134 (the variants with a lipread_b200 plan)."""
     if model_name == "resnet":
@@ -239,4 +311,6 @@ def get_model(num_classes, input_size, model_name, version=None):
         return VGGAudioClassifier(num_classes=num_classes, version=version or 11)
     if model_name == "vgg_lstm":
         return VGGWithLSTMClassifier(num_classes=num_classes, version=version or 11)
+    if model_name == "lstm_resnet":
+        return LSTMResNet(num_classes=num_classes, input_size=input_size)
     raise ValueError(f"Invalid model name: {model_name}")

@@ -23,7 +23,8 @@ struct Src {
 };
 struct Geo {
     int Hd, Wd;                              // destination rows run over (f, hd, wd)
-    int kh, kw, stride, pad, transposed;
+    int kh, kw, stride, pad, transposed;     // pad: rows (and columns unless pad_w >= 0)
+    int pad_w;                               // column padding of the tap-major kernel (Conv1d as a 1 x k window)
     int K, ldk;                              // K = C*kh*kw valid columns, ldk = row pitch (multiple of 4), tail zeroed
 };
 
@@ -125,8 +126,8 @@ im2col_tap_kernel(const float* __restrict__ x, const Geo g, int Hs, int Ws, int 
             else { const int hn = hd + g.pad - r; hs = hn / g.stride; okh = hn >= 0 && hs * g.stride == hn && hs < Hs; }
             for (int q = 0; q < g.kw; ++q) {
                 int ws; bool ok;
-                if (!g.transposed) { ws = wd * g.stride - g.pad + q; ok = okh && ws >= 0 && ws < Ws; }
-                else { const int wn = wd + g.pad - q; ws = wn / g.stride; ok = okh && wn >= 0 && ws * g.stride == wn && ws < Ws; }
+                if (!g.transposed) { ws = wd * g.stride - g.pad_w + q; ok = okh && ws >= 0 && ws < Ws; }
+                else { const int wn = wd + g.pad_w - q; ws = wn / g.stride; ok = okh && wn >= 0 && ws * g.stride == wn && ws < Ws; }
                 const float4 v = ok ? nn::ld4(xf + ((long long)hs * Ws + ws) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
                 nn::st4(o + (long long)(r * g.kw + q) * C, v);
             }
@@ -291,6 +292,7 @@ extern "C" int lr_im2col(const void* x, int is_u8, float scale, int F, int T, lo
     s.Hs = Hs; s.Ws = Ws; s.C = C;
     c2::Geo g;
     g.Hd = Hd; g.Wd = Wd; g.kh = kh; g.kw = kw; g.stride = stride; g.pad = pad; g.transposed = transposed;
+    g.pad_w = pad;
     g.K = (int)K; g.ldk = (int)ldk;
     const long long rows = (long long)F * Hd * Wd;
     if (is_u8 && C == 3 && kh == 3 && kw == 3 && !transposed && ldk == 28)
@@ -302,15 +304,17 @@ extern "C" int lr_im2col(const void* x, int is_u8, float scale, int F, int T, lo
     return LR_OK;
 }
 
-extern "C" int lr_im2col_tap(const float* x, int F, int Hs, int Ws, int C, int kh, int kw, int stride, int pad,
-                             int transposed, int Hd, int Wd, float* col, lr_stream_t stream) {
+extern "C" int lr_im2col_tap(const float* x, int F, int Hs, int Ws, int C, int kh, int kw, int stride, int pad_h,
+                             int pad_w, int transposed, int Hd, int Wd, float* col, lr_stream_t stream) {
+    const int pad = pad_h;
     LR_CHECK_ARG(F >= 0 && Hs > 0 && Ws > 0 && C > 0 && (C & 3) == 0 && Hd > 0 && Wd > 0, "lr_im2col_tap: bad shape (C %% 4 != 0?)");
-    LR_CHECK_ARG(kh > 0 && kw > 0 && stride > 0 && pad >= 0, "lr_im2col_tap: bad window");
+    LR_CHECK_ARG(kh > 0 && kw > 0 && stride > 0 && pad_h >= 0 && pad_w >= 0, "lr_im2col_tap: bad window");
     if (F == 0) return LR_OK;
     LR_CHECK_ARG(x && col, "lr_im2col_tap: null pointer");
     LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(col);
     c2::Geo g;
     g.Hd = Hd; g.Wd = Wd; g.kh = kh; g.kw = kw; g.stride = stride; g.pad = pad; g.transposed = transposed;
+    g.pad_w = pad_w;
     g.K = C * kh * kw; g.ldk = g.K;
     const long long rows = (long long)F * Hd * Wd;
     c2::im2col_tap_kernel<<<c2::grid_for(rows * (C >> 2)), c2::TH, 0, stream>>>(x, g, Hs, Ws, C, col, rows);

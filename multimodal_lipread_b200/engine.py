@@ -178,6 +178,16 @@ def op_algorithmic_bytes(name, args):
     return None
 
 
+def _conv_geometry(conv):
+    """(kh, kw, stride, pad_h, pad_w) of an nn.Conv2d -- or of an nn.Conv1d seen as a 1 x k window over [B, 1, T, C]."""
+    assert conv.groups == 1
+    if isinstance(conv, nn.Conv1d):
+        assert conv.dilation == (1,)
+        return 1, conv.kernel_size[0], conv.stride[0], 0, conv.padding[0]
+    assert conv.stride[0] == conv.stride[1] and conv.dilation == (1, 1)
+    return conv.kernel_size[0], conv.kernel_size[1], conv.stride[0], conv.padding[0], conv.padding[1]
+
+
 def _ksplit(M, N, K, sms, min_k=256):
     tiles = ((M + 63) // 64) * ((N + 63) // 64)
     want = max(1, (2 * sms) // tiles)
@@ -232,6 +242,13 @@ class T2:
         self.rows = F * H * W
         self.val = plan.alloc(self.rows * C)
         self.grad = plan.alloc(self.rows * C) if (need_grad and plan.with_backward) else None
+
+    @classmethod
+    def of(cls, F, H, W, C, val, grad):
+        """A view of existing buffers under another frame geometry (e.g. [B*T, C] features as a [B, 1, T, C] map)."""
+        t = cls.__new__(cls)
+        t.F, t.H, t.W, t.C, t.rows, t.val, t.grad = F, H, W, C, F * H * W, val, grad
+        return t
 
 
 class Plan:
@@ -309,7 +326,7 @@ class Plan:
                   split_ok=False):
         """Emit one GEMM, choosing the tcgen05 kernel when it pays; split_ok: the caller accumulates into a
         pre-initialised C, so the reduction may be split over CTAs with atomic adds."""
-        if self.use_tc(M, N, K, lda, ldb):
+        if N >= 4 and self.use_tc(M, N, K, lda, ldb):
             ks = 1
             if split_ok:
                 bn_tiles = ((M + 127) // 128) * ((N + 255) // 256)
@@ -538,10 +555,7 @@ class Plan:
         raw output T2 (BatchNorm statistic slot attached).  The backward group is reserved here (its position fixes
         when it runs) and filled by dense_conv_bwd once the caller knows what accumulates into x.grad."""
         Cout, Cin = conv.out_channels, conv.in_channels
-        kh, kw = conv.kernel_size
-        st_, pd = conv.stride[0], conv.padding[0]
-        assert conv.groups == 1 and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
-        assert conv.dilation == (1, 1)
+        kh, kw, st_, pd, pw = _conv_geometry(conv)
         if frames is not None:
             ft, (is_u8, B, T, Hs, Ws, sb, stt, sc, sh, sw), scale = frames
             F = B * T
@@ -552,18 +566,19 @@ class Plan:
             F, Hs, Ws = x.F, x.H, x.W
             src = (0, 1.0, F, 1, Hs * Ws * Cin, 0, 1, Ws * Cin, Cin)
             xptr = x.val
-        Ho, Wo = (Hs + 2 * pd - kh) // st_ + 1, (Ws + 2 * pd - kw) // st_ + 1
+        Ho, Wo = (Hs + 2 * pd - kh) // st_ + 1, (Ws + 2 * pw - kw) // st_ + 1
         rows = F * Ho * Wo
         K = Cin * kh * kw
         pointwise = frames is None and kh == 1 and kw == 1 and st_ == 1 and pd == 0 and Cin % 4 == 0
         # tap-major patch matrix (shifted float4 copies) for channels-last inputs; torch-order gather for the stems
         tap = frames is None and not pointwise and Cin % 4 == 0 and Cout % 4 == 0
+        assert tap or pw == pd, "unequal paddings need the tap-major path (channels-last input, C % 4 == 0)"
         ldk = K if (pointwise or tap) else (K + 3) // 4 * 4
         if pointwise:
             col = xptr
         elif tap:
             col = self.alloc(rows * K)
-            self.fwd.add("lr_im2col_tap", xptr, F, Hs, Ws, Cin, kh, kw, st_, pd, 0, Ho, Wo, col)
+            self.fwd.add("lr_im2col_tap", xptr, F, Hs, Ws, Cin, kh, kw, st_, pd, pw, 0, Ho, Wo, col)
         else:
             col = self.alloc(rows * ldk)
             self.fwd.add("lr_im2col", xptr, *src, Hs, Ws, Cin, kh, kw, st_, pd, 0, Ho, Wo, col, ldk)
@@ -594,8 +609,7 @@ class Plan:
         dW += dy^T col, db += colsum(dy), x.grad = im2col_T(dy) . Wt^T (+ dx_residual)."""
         g, x, conv, col, ldk, wmat, src, (F, Hs, Ws, Ho, Wo), need_dx, tap = y._conv_bwd
         Cout, Cin = conv.out_channels, conv.in_channels
-        kh, kw = conv.kernel_size
-        st_, pd = conv.stride[0], conv.padding[0]
+        kh, kw, st_, pd, pw = _conv_geometry(conv)
         K = Cin * kh * kw
         rows = F * Ho * Wo
         dw = self.flat.g(conv.weight)
@@ -626,7 +640,7 @@ class Plan:
             wt = self.alloc(Cin * Kt)
             g.add("lr_weight_tap", conv.weight, wt, Cout, Cin, kh * kw, 1)
             colT = self.workspace(rows_in * Kt)
-            g.add("lr_im2col_tap", y.grad, F, Ho, Wo, Cout, kh, kw, st_, pd, 1, Hs, Ws, colT)
+            g.add("lr_im2col_tap", y.grad, F, Ho, Wo, Cout, kh, kw, st_, pd, pw, 1, Hs, Ws, colT)
             self.gemm_auto(g, colT, Kt, 0, wt, Kt, 0, x.grad, Cin, rows_in, Cin, Kt, R=dx_residual, ldr=Cin)
             return
         ldt = (Kt + 3) // 4 * 4
@@ -771,9 +785,12 @@ class Plan:
             # reverse direction: one step from the zero state (W_hh_reverse gets no gradient)
             g.add("lr_lstm_bwd", dptr + 4 * H, ldo, 0, gates_r, c_r, par("weight_hh", l, 1), dg_r, B, 1, H, 1, 1)
             g.add("lr_colsum", dg_r, G4, B, G4, self.flat.g(par("bias_hh", l, 1)), leaf=True)
-            dcur_last = (dcur if isinstance(dcur, int) else dcur.data_ptr()) + 4 * (T - 1) * Icur
-            self.linear_bwd(g, cur_last, T * Icur, B, par("weight_ih", l, 1), par("bias_ih", l, 1), dg_r, G4,
-                            dx=dcur_last, ldx=T * Icur, dx_residual=dcur_last, ldr=T * Icur)
+            if dcur is None:                                   # the sequence input needs no gradient (raw features)
+                self.linear_bwd(g, cur_last, T * Icur, B, par("weight_ih", l, 1), par("bias_ih", l, 1), dg_r, G4)
+            else:
+                dcur_last = (dcur if isinstance(dcur, int) else dcur.data_ptr()) + 4 * (T - 1) * Icur
+                self.linear_bwd(g, cur_last, T * Icur, B, par("weight_ih", l, 1), par("bias_ih", l, 1), dg_r, G4,
+                                dx=dcur_last, ldx=T * Icur, dx_residual=dcur_last, ldr=T * Icur)
 
     def bilstm_hn(self, x, dx, I, B, T, lstm, out, ldo, dout):
         """Single-layer bidirectional nn.LSTM whose head is cat(h_n[0], h_n[1]) (audio_video/models/late_fusion.py:61-62,
@@ -809,11 +826,12 @@ class Plan:
                                 dx_residual=(dx if rev else 0), ldr=I)
 
     # ---- torchvision ResNet (BasicBlock) -------------------------------------------------------------------
-    def resnet_features(self, net, frames, need_input_grad=False):
+    def resnet_features(self, net, frames, x=None):
         """torchvision resnet18/34 children()[:-2] (conv1, bn1, relu, maxpool, layer1..4) on frames given as
         (tensor, layout, scale) -> last activation T2.  video/models/resnet_lstm.py:90-93,
-        audio/models/resnet_model.py:12-17."""
-        raw = self.dense_conv(None, net.conv1, frames=frames)
+        audio/models/resnet_model.py:12-17.  x: a T2 input instead of raw frames when the image is itself computed and
+        needs a gradient (audio/models/lstm_resnet_model.py:47-49)."""
+        raw = self.dense_conv(x, net.conv1, frames=frames if x is None else None)
         if self.with_backward:
             self.dense_conv_bwd(raw)
         a = T2(self, raw.F, raw.H, raw.W, raw.C)

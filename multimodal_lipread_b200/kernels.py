@@ -174,8 +174,9 @@ def gemm_tf32(A, lda, a_trans, B, ldb, b_trans, C, ldc, M, N, K, bias=None, act=
                            _p(stats), ksplit, _s()))
 
 
-def im2col_tap(x, F, Hs, Ws, C, kh, kw, stride, pad, transposed, Hd, Wd, col):
-    check(lib.lr_im2col_tap(_p(x), F, Hs, Ws, C, kh, kw, stride, pad, int(transposed), Hd, Wd, _p(col), _s()))
+def im2col_tap(x, F, Hs, Ws, C, kh, kw, stride, pad, transposed, Hd, Wd, col, pad_w=None):
+    check(lib.lr_im2col_tap(_p(x), F, Hs, Ws, C, kh, kw, stride, pad, pad if pad_w is None else pad_w, int(transposed),
+                            Hd, Wd, _p(col), _s()))
 
 
 def weight_tap(src, dst, Cout, Cin, kk, mode):

@@ -3,6 +3,7 @@
   ResNet2DBiLSTM / create_model      video/models/resnet_lstm.py:56-177   (model.name == "resnet_lstm")
   MobileNetLSTM                      video/models/mobilenet_lstm.py:18-72  (model.name == "mobilenet_lstm")
   VGGLSTM                            video/models/vgg_lstm.py:14-92        (model.name == "vgg_lstm")
+  CNNOnly                            video/models/cnn.py:5-73              (model.name == "cnn")
 
 Sub-modules are parameter containers only (same names, construction order and `state_dict` keys as the reference,
 including the CNN appearing twice -- `cnn_features.*` and `time_distributed_cnn.module.0.*` share tensors);
@@ -12,6 +13,7 @@ import types
 import torch.nn as nn
 from torchvision.models import mobilenet_v2, resnet18, resnet34
 
+from . import engine
 from ._lib import ACT_RELU
 from .model_base import Cfg, ModelPlan, PlanModel
 
@@ -162,6 +164,59 @@ class VGGLSTM(PlanModel):
 
 
 VGGLSTM.PLAN = ResNetLstmPlan
+
+
+class CnnOnlyPlan(ModelPlan):
+    def build(self, m, spec):
+        B, wb = self.B, self.with_backward
+        video, layout, scale = self.video_input()
+        T = layout[2]
+        kind, feat, dfeat, C = self.cnn_sequential(list(m.frame_cnn), (video, layout, scale))
+        assert kind == "pooled"
+        # x.view(B, T, -1).permute(0, 2, 1) -> Conv1d over time: on the channels-last [B*T, C] features that is a 1 x 3
+        # window over a [B, 1, T, C] map (no permute), BatchNorm1d over the B*T rows
+        x = engine.T2.of(B, 1, T, C, feat, dfeat)
+        tc = list(m.temporal_conv)
+        for conv, bn in ((tc[0], tc[1]), (tc[3], tc[4])):
+            raw = self.dense_conv(x, conv)
+            if wb:
+                self.dense_conv_bwd(raw)
+            a = engine.T2(self, raw.F, raw.H, raw.W, raw.C)
+            self.bn_act(raw, bn, ACT_RELU, a)
+            x = a
+        pooled, dpooled = self.avgpool(x)                           # x.mean(dim=2): over time
+        hd, dhd = self.dropout(pooled, dpooled, B * x.C, m.dropout.p)
+        logits = self.alloc(B * self.num_classes)
+        dlogits = self.alloc(B * self.num_classes) if wb else None
+        self.linear(hd, x.C, B, m.fc.weight, m.fc.bias, logits, self.num_classes)
+        if wb:
+            self.linear_bwd(self.bgroup(), hd, x.C, B, m.fc.weight, m.fc.bias, dlogits, self.num_classes, dx=dhd, ldx=x.C)
+        self.set_logits(logits, dlogits)
+
+
+class CNNOnly(PlanModel):
+    """video/models/cnn.py:5-69: per-frame CNN, two Conv1d + BatchNorm1d + ReLU over time, mean over time, fc."""
+    INPUTS = ("video",)
+    PLAN = CnnOnlyPlan
+    DEFAULT_LR = 5e-5
+    DEFAULT_WD = 1e-5
+
+    def __init__(self, num_classes, config=None, precision=None):
+        super().__init__()
+        config = config or Cfg()
+        self._init_base(num_classes, config, precision)
+        self.frame_cnn = nn.Sequential(
+            nn.Conv2d(3, 32, kernel_size=3, stride=1, padding=1), nn.BatchNorm2d(32), nn.ReLU(inplace=True), nn.MaxPool2d(2),
+            nn.Conv2d(32, 64, kernel_size=3, stride=1, padding=1), nn.BatchNorm2d(64), nn.ReLU(inplace=True), nn.MaxPool2d(2),
+            nn.Conv2d(64, 128, kernel_size=3, stride=1, padding=1), nn.BatchNorm2d(128), nn.ReLU(inplace=True),
+            nn.AdaptiveAvgPool2d((1, 1)))
+        temporal_channels = config.get("model.temporal_channels", 128)
+        self.temporal_conv = nn.Sequential(
+            nn.Conv1d(128, temporal_channels, kernel_size=3, padding=1), nn.BatchNorm1d(temporal_channels), nn.ReLU(inplace=True),
+            nn.Conv1d(temporal_channels, temporal_channels, kernel_size=3, padding=1), nn.BatchNorm1d(temporal_channels),
+            nn.ReLU(inplace=True))
+        self.dropout = nn.Dropout(config.get("model.dropout", 0.3))
+        self.fc = nn.Linear(temporal_channels, num_classes)
 
 
 def create_model(num_classes, config=None):

@@ -16,9 +16,11 @@ there is no network for the ImageNet checkpoint:
   LateFusionResNetOracle      audio_cues_video/models/late_fusion_resnet.py:6-99
   MobileNetLSTMOracle         video/models/mobilenet_lstm.py:18-68
   VGGLSTMOracle               video/models/vgg_lstm.py:14-88
+  CNNOnlyOracle               video/models/cnn.py:5-69
   AudioResNetLSTMOracle       audio/models/resnet_lstm_model.py:5-59
   VGGAudioOracle              audio/models/vgg_model.py:5-58
   VGGLstmAudioOracle          audio/models/vgg_lstm_model.py:5-75
+  LSTMResNetOracle            audio/models/lstm_resnet_model.py:5-71
   LateFusionAVMobileNetOracle audio_video/models/late_fusion.py:10-93
   MidFusionAVMobileNetOracle  audio_video/models/middle_fusion.py:11-85
   EarlyFusionFastOracle       audio_video/models/early_fusion_fast.py:6-76
@@ -345,6 +347,30 @@ class VGGLSTMOracle(nn.Module):
         return self.fc(self.dropout(self.relu(x[:, -1, :])))
 
 
+class CNNOnlyOracle(nn.Module):
+    """video/models/cnn.py:5-69: per-frame CNN (3 x conv + BN + ReLU), two Conv1d + BatchNorm1d + ReLU over time, mean."""
+
+    def __init__(self, num_classes, config=None):
+        super().__init__()
+        config = config or DictConfig()
+        self.frame_cnn = nn.Sequential(
+            nn.Conv2d(3, 32, kernel_size=3, stride=1, padding=1), nn.BatchNorm2d(32), nn.ReLU(inplace=True), nn.MaxPool2d(2),
+            nn.Conv2d(32, 64, kernel_size=3, stride=1, padding=1), nn.BatchNorm2d(64), nn.ReLU(inplace=True), nn.MaxPool2d(2),
+            nn.Conv2d(64, 128, kernel_size=3, stride=1, padding=1), nn.BatchNorm2d(128), nn.ReLU(inplace=True),
+            nn.AdaptiveAvgPool2d((1, 1)))
+        tc = config.get("model.temporal_channels", 128)
+        self.temporal_conv = nn.Sequential(
+            nn.Conv1d(128, tc, kernel_size=3, padding=1), nn.BatchNorm1d(tc), nn.ReLU(inplace=True),
+            nn.Conv1d(tc, tc, kernel_size=3, padding=1), nn.BatchNorm1d(tc), nn.ReLU(inplace=True))
+        self.dropout = nn.Dropout(config.get("model.dropout", 0.3))
+        self.fc = nn.Linear(tc, num_classes)
+
+    def forward(self, x):
+        frames, b, t = _frames(x)
+        f = self.frame_cnn(frames).view(b, t, -1).permute(0, 2, 1)
+        return self.fc(self.dropout(self.temporal_conv(f).mean(dim=2)))
+
+
 class AudioResNetLSTMOracle(nn.Module):
     """audio/models/resnet_lstm_model.py:5-59: ResNet-18 features as a length-1 sequence through a 2-layer BiLSTM."""
 
@@ -407,6 +433,33 @@ class VGGLstmAudioOracle(nn.Module):
     def forward(self, x):
         x = self.adaptive_pool(self.vgg_features(x.unsqueeze(1))).squeeze(-1).permute(0, 2, 1)
         out, _ = self.lstm(x)
+        return self.classifier(out[:, -1, :])
+
+
+class LSTMResNetOracle(nn.Module):
+    """audio/models/lstm_resnet_model.py:5-71: every mel row through a BiLSTM as a length-1 sequence, the result as a
+    1-channel 80 x 128 image through ResNet-18, fc (+BN1d), a second length-1 BiLSTM, classifier."""
+
+    def __init__(self, num_classes=40, input_size=117, dropout_rate=0.3, use_batchnorm=True):
+        super().__init__()
+        self.use_bn = use_batchnorm
+        self.initial_bilstm = nn.LSTM(input_size, 64, num_layers=2, bidirectional=True, batch_first=True)
+        self.resnet = resnet18(weights=None)
+        self.resnet.conv1 = nn.Conv2d(1, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.resnet.fc = nn.Identity()
+        layers = [nn.Linear(512, 256)]
+        if use_batchnorm:
+            layers.append(nn.BatchNorm1d(256))
+        layers.extend([nn.ReLU(), nn.Dropout(dropout_rate)])
+        self.fc = nn.Sequential(*layers)
+        self.final_bilstm = nn.LSTM(256, 128, num_layers=2, bidirectional=True, batch_first=True)
+        self.classifier = nn.Linear(256, num_classes)
+
+    def forward(self, x):
+        b = x.size(0)
+        x1, _ = self.initial_bilstm(x.view(b * 80, 117).unsqueeze(1))
+        x1 = x1.squeeze(1).view(b, 1, 80, -1)
+        out, _ = self.final_bilstm(self.fc(self.resnet(x1)).unsqueeze(1))
         return self.classifier(out[:, -1, :])
 
 

@@ -221,6 +221,10 @@ def golden_models():
     model = mod.VGGLSTM(C, DCfg({"model.dropout": 0.0}))
     mel, video, labels = data(B, size, T, C)
     record("video_vgg_lstm", model, (video,), labels, 5e-5, 1e-5, B, T, size)
+    mod = load_ref("video", "models.cnn")
+    torch.manual_seed(0)
+    model = mod.CNNOnly(C, DCfg({"model.dropout": 0.0}))
+    record("video_cnn", model, (video,), labels, 5e-5, 1e-5, B, T, size)
     B, C = 4, 8
     mel, video, labels = data(B, 44, 1, C)
     mod = load_ref("audio", "models.resnet_lstm_model")
@@ -235,6 +239,10 @@ def golden_models():
     torch.manual_seed(0)
     model = mod.VGGWithLSTMClassifier(num_classes=C, version=11, dropout_rate=0.0)
     record("audio_vgg_lstm", model, (mel,), labels, 5e-4, 1e-4, B, 1, 44)
+    mod = load_ref("audio", "models.lstm_resnet_model")
+    torch.manual_seed(0)
+    model = mod.LSTMResNet(num_classes=C, input_size=117, dropout_rate=0.0)
+    record("audio_lstm_resnet", model, (mel,), labels, 5e-4, 1e-4, B, 1, 44)
     # the remaining audio_video models (av_config.yaml:10), lr 3e-4
     B, T, size, C = 3, 8, 44, 40
     for name, module, factory, drop in (("late_fusion_mobilenet", "models.late_fusion", "create_late_fusion_mobilenet_model", False),

@@ -19,7 +19,8 @@ pytestmark = pytest.mark.gpu
 # A bias added right before a train-mode BatchNorm has an exactly-zero gradient in exact arithmetic: both
 # implementations produce only summation round-off there (~1e-7 .. 1e-6), so those are checked for smallness.
 ZERO_GRAD_BN = ("audio_encoder.cnn.0.bias", "audio_encoder.cnn.4.bias", "audio_encoder.cnn.8.bias", "resnet.fc.0.bias",
-                "cue.net.0.bias", "classifier.0.bias", "vgg.classifier.0.bias") + tuple(
+                "cue.net.0.bias", "classifier.0.bias", "vgg.classifier.0.bias", "frame_cnn.0.bias", "frame_cnn.4.bias",
+                "frame_cnn.8.bias", "temporal_conv.0.bias", "temporal_conv.3.bias", "fc.0.bias") + tuple(
                     f"{pre}.{i}.bias" for pre in ("vgg.features", "vgg_features") for i in (0, 4, 8, 11, 15, 18, 22, 25))       # vgg11_bn conv biases (BN follows)
 ZERO_GRAD = ZERO_GRAD_BN
 
@@ -135,12 +136,16 @@ def _case(name, precision="fp32"):
         ref = O.LateFusionMobileOracle(C, lstm_dropout=0.0)
     elif name == "video_vgg_lstm":
         ref = O.VGGLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
+    elif name == "video_cnn":
+        ref = O.CNNOnlyOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
     elif name == "audio_resnet_lstm":
         ref = O.AudioResNetLSTMOracle(C, dropout_rate=0.0)
     elif name == "audio_vgg":
         ref = O.VGGAudioOracle(C, version=11, dropout_rate=0.0)
     elif name == "audio_vgg_lstm":
         ref = O.VGGLstmAudioOracle(C, version=11, dropout_rate=0.0)
+    elif name == "audio_lstm_resnet":
+        ref = O.LSTMResNetOracle(C, dropout_rate=0.0)
     elif name == "video_mobilenet_lstm":
         ref = O.MobileNetLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
     elif name == "acv_late_fusion_resnet":
@@ -166,12 +171,16 @@ def _case(name, precision="fp32"):
         ours = ACV.MultimodalAttentionLate(C, lstm_dropout=0.0, precision=precision)
     elif name == "video_vgg_lstm":
         ours = video_models.VGGLSTM(C, cfg, precision=precision)
+    elif name == "video_cnn":
+        ours = video_models.CNNOnly(C, cfg, precision=precision)
     elif name == "audio_resnet_lstm":
         ours = audio_models.AudioResNetLSTM(C, dropout_rate=0.0, precision=precision)
     elif name == "audio_vgg":
         ours = audio_models.VGGAudioClassifier(C, version=11, dropout_rate=0.0, precision=precision)
     elif name == "audio_vgg_lstm":
         ours = audio_models.VGGWithLSTMClassifier(C, version=11, dropout_rate=0.0, precision=precision)
+    elif name == "audio_lstm_resnet":
+        ours = audio_models.LSTMResNet(C, dropout_rate=0.0, precision=precision)
     elif name == "video_mobilenet_lstm":
         ours = video_models.MobileNetLSTM(C, cfg, precision=precision)
     elif name == "acv_late_fusion_resnet":
@@ -195,7 +204,7 @@ def _inputs_for(name, mel, lips):
     video = lips_u8_to_model_input(lips)
     if name.startswith("early_fusion") or name in ("late_fusion_mobilenet", "middle_fusion_mobilenet", "late_fusion_fast"):
         return (mel, video), (mel.cuda(), lips.cuda())
-    if name in ("video_resnet_lstm", "video_mobilenet_lstm", "video_vgg_lstm"):
+    if name in ("video_resnet_lstm", "video_mobilenet_lstm", "video_vgg_lstm", "video_cnn"):
         return (video,), (lips.cuda(),)
     if name in ("acv_late_fusion_mobile", "acv_late_fusion_resnet"):
         from multimodal_lipread_b200 import synthetic
@@ -216,9 +225,11 @@ def _inputs_for(name, mel, lips):
     ("acv_late_fusion_mobile", 3, 6, 44),
     ("video_mobilenet_lstm", 3, 6, 44),
     ("video_vgg_lstm", 3, 6, 44),
+    ("video_cnn", 3, 6, 44),
     ("audio_resnet_lstm", 4, 1, 44),
     ("audio_vgg", 4, 1, 44),
     ("audio_vgg_lstm", 4, 1, 44),
+    ("audio_lstm_resnet", 4, 1, 44),
     ("acv_late_fusion_resnet", 3, 6, 44),
     ("late_fusion_mobilenet", 3, 8, 44),
     ("middle_fusion_mobilenet", 3, 8, 44),
@@ -276,7 +287,7 @@ def test_train_step_matches_oracle(cuda_device, name, B, T, size):
 
 
 @pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
-                                  "acv_late_fusion_resnet", "video_vgg_lstm", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm",
+                                  "acv_late_fusion_resnet", "video_vgg_lstm", "video_cnn", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm", "audio_lstm_resnet",
                                   "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast"])
 def test_golden_vectors_of_the_reference(cuda_device, golden_dir, name):
     """Outputs recorded from the reference's own modules (tests/golden/make_golden.py, dropout set to 0)."""

@@ -114,7 +114,7 @@ def models_golden(golden_dir):
 
 
 @pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
-                                  "acv_late_fusion_resnet", "video_vgg_lstm", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm",
+                                  "acv_late_fusion_resnet", "video_vgg_lstm", "video_cnn", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm", "audio_lstm_resnet",
                                   "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast"])
 def test_model_oracles_match_reference(models_golden, name):
     from oracle import av_models as O
@@ -130,12 +130,16 @@ def test_model_oracles_match_reference(models_golden, name):
         model, lr, wd = O.LateFusionMobileOracle(C, lstm_dropout=0.0), 1e-5, 0.0
     elif name == "video_vgg_lstm":
         model, lr, wd = O.VGGLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}})), 5e-5, 1e-5
+    elif name == "video_cnn":
+        model, lr, wd = O.CNNOnlyOracle(C, O.DictConfig({"model": {"dropout": 0.0}})), 5e-5, 1e-5
     elif name == "audio_resnet_lstm":
         model, lr, wd = O.AudioResNetLSTMOracle(C, dropout_rate=0.0), 5e-4, 1e-4
     elif name == "audio_vgg":
         model, lr, wd = O.VGGAudioOracle(C, version=11, dropout_rate=0.0), 5e-4, 1e-4
     elif name == "audio_vgg_lstm":
         model, lr, wd = O.VGGLstmAudioOracle(C, version=11, dropout_rate=0.0), 5e-4, 1e-4
+    elif name == "audio_lstm_resnet":
+        model, lr, wd = O.LSTMResNetOracle(C, dropout_rate=0.0), 5e-4, 1e-4
     elif name == "video_mobilenet_lstm":
         model, lr, wd = O.MobileNetLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}})), 5e-5, 1e-5
     elif name == "acv_late_fusion_resnet":
@@ -159,8 +163,8 @@ def test_model_oracles_match_reference(models_golden, name):
     mel = AudioProcessorPort().batch_frontend_loop(wav)
     video = lips_u8_to_model_input(synthetic.make_lips_u8(B, size=size)[:, :T].contiguous())
     labels = synthetic.make_labels(B, C)
-    inputs = {"video_resnet_lstm": (video,), "video_mobilenet_lstm": (video,), "video_vgg_lstm": (video,),
-              "audio_resnet": (mel,), "audio_resnet_lstm": (mel,), "audio_vgg": (mel,), "audio_vgg_lstm": (mel,),
+    inputs = {"video_resnet_lstm": (video,), "video_mobilenet_lstm": (video,), "video_vgg_lstm": (video,), "video_cnn": (video,),
+              "audio_resnet": (mel,), "audio_resnet_lstm": (mel,), "audio_vgg": (mel,), "audio_vgg_lstm": (mel,), "audio_lstm_resnet": (mel,),
               "acv_late_fusion_mobile": (mel, synthetic.make_cues(B), video),
               "acv_late_fusion_resnet": (mel, synthetic.make_cues(B), video)}.get(name, (mel, video))
     opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)

@@ -34,9 +34,11 @@ def test_model_name_dispatch_and_errors():
     for name in T.AV_MODELS:                             # every audio_video model name of av_config.yaml:10 has a plan
         assert T.create_av_model(name, 40, cfg).num_classes == 40
     assert type(T.create_video_model("vgg_lstm", 40, cfg)).__name__ == "VGGLSTM"
+    assert type(T.create_video_model("cnn", 40, cfg)).__name__ == "CNNOnly"
     assert type(T.create_audio_model("resnet_lstm", 8)).__name__ == "AudioResNetLSTM"
     assert type(T.create_audio_model("vgg", 8, version=11)).__name__ == "VGGAudioClassifier"
     assert type(T.create_audio_model("vgg_lstm", 8, version=11)).__name__ == "VGGWithLSTMClassifier"
+    assert type(T.create_audio_model("lstm_resnet", 8, input_size=117)).__name__ == "LSTMResNet"
     for name in ("shufflenet_lstm", "resnet_trans"):
         with pytest.raises(NotImplementedError):
             T.create_video_model(name, 40, cfg)          # a reference name without a plan fails loudly
