@@ -302,6 +302,10 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": wl.roofline(kernel_ms, ms_step, peaks)}
         line.update(wl.extra())
+        if world == 1 and hasattr(wl, "files_e2e"):
+            fe = wl.files_e2e()
+            if fe:
+                line["files_e2e"] = fe
         if args.dump_ops and getattr(wl, "op_rows", None):
             with open(args.dump_ops, "w") as f:
                 json.dump(wl.op_rows, f, indent=0)

@@ -8,7 +8,8 @@
  *
  * Conventions
  *   - extern "C", plain pointers and sizes; no torch types.
- *   - Every pointer is DEVICE memory owned by the caller (including workspaces / plans).
+ *   - Every pointer is DEVICE memory owned by the caller (including workspaces / plans), except in the
+ *     lr_host_* readers of the input path, which take host pointers and make no CUDA calls.
  *   - Functions only enqueue work on `stream`; they never allocate, synchronise or throw.
  *   - Return LR_OK (0) or a negative LR_E* code; lr_last_error() gives a thread-local message.
  *   - Tensors are contiguous; base pointers must be 16-byte aligned (LR_EALIGN otherwise).
@@ -70,6 +71,35 @@ int lr_logmel_plan_init(const float* window /*[400]*/, const float* fb /*[201,80
 enum { LR_LOGMEL_FRONTEND = 0, LR_LOGMEL_RAW = 1 };
 int lr_logmel_fwd(const float* wav /*[B,20000]*/, const void* plan, float* out, int B, int n_out,
                   int mode, lr_stream_t stream);
+
+/* PCM ingestion in front of lr_logmel_fwd: B ragged clips of interleaved int16 PCM, packed in one buffer, become
+ * the fixed-length fp32 batch wav[B, target].  Clip b starts at pcm[offset[b]] and holds n_frames[b] sample frames
+ * of channels[b] channels (channels == NULL: mono).
+ *   wav[b, i] = i < min(n_frames[b], target) ? mean_c(scale * pcm[offset[b] + i*ch + c]) : 0
+ * replaces  audio/utils/audio_processor.py:29   integer PCM samples -> float, not rescaled (scale = 1)
+ *           audio/utils/audio_processor.py:37   samples.mean(dim=0) over channels (scale = 1/32768 for the
+ *                                               torchaudio.load branch, :31)
+ *           audio/utils/audio_processor.py:40-44 truncate to target_samples / right zero-pad
+ * Decoding the container (m4a -> PCM, pydub / ffmpeg, :26-28) stays on the host. */
+int lr_pcm_ingest(const short* pcm, const long long* offset /*[B]*/, const int* n_frames /*[B]*/,
+                  const int* channels /*[B] or NULL*/, float scale, float* wav /*[B,target]*/, int B, int target,
+                  lr_stream_t stream);
+
+/* Host-side batch readers of the input path (the ONLY entry points that take host pointers; no CUDA calls).
+ * A whole batch of `.npy` files is read by `n_threads` native threads straight into a ring slot of (pinned) host
+ * memory, from where one async copy takes it to the device; no arithmetic on the host.
+ *   replaces  video/data_utils/dataset_loader.py:90 / audio_video/data_utils/dataset_av.py:70   np.load per clip in
+ *             DataLoader workers (the astype(float32) / 255 and the permute are folded into the stem kernels)
+ * lr_host_read_npy_u8: file i must hold a C-order uint8 array of exactly shape[0..ndim); its payload lands at
+ *   dst + i * prod(shape).
+ * lr_host_read_npy_pcm16: file i holds little-endian int16 PCM, (n,) or (n, channels) interleaved; at most
+ *   target_frames sample frames land at dst + i * cap and meta[0][i] = i * cap (offset), meta[1][i] = frames kept,
+ *   meta[2][i] = channels (meta is [3][n]) -- the arguments of lr_pcm_ingest.
+ * Errors (LR_EINVAL, message names the first offending file): missing file, wrong dtype / order / shape, truncated. */
+int lr_host_read_npy_u8(const char* const* paths, int n, unsigned char* dst, const long long* shape, int ndim,
+                        int n_threads);
+int lr_host_read_npy_pcm16(const char* const* paths, int n, short* dst, long long cap, int target_frames,
+                           long long* meta, int n_threads);
 
 /* normalize_spectrogram alone on [B, n] rows: (x - mean)/(std_unbiased + 1e-9). */
 int lr_normalize_fwd(const float* x, float* out, int B, int n, lr_stream_t stream);

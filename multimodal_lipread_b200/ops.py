@@ -70,3 +70,28 @@ def normalize(x: torch.Tensor) -> torch.Tensor:
 @normalize.register_fake
 def _(x):
     return torch.empty_like(x)
+
+
+# ---------------------------------------------------------------- PCM ingestion (in front of K1)
+@torch.library.custom_op("lipread::pcm_ingest", mutates_args=(), device_types="cuda")
+def pcm_ingest(pcm: torch.Tensor, offset: torch.Tensor, n_frames: torch.Tensor, channels: torch.Tensor, scale: float,
+               target: int) -> torch.Tensor:
+    """Packed int16 PCM (ragged clips, interleaved channels) -> (B, target) f32: mono mean, truncate / right zero-pad
+    (audio/utils/audio_processor.py:29,37,40-44).  channels: int32 [B], or an empty tensor for all-mono."""
+    _need(pcm, torch.int16, "pcm")
+    _need(offset, torch.int64, "offset")
+    _need(n_frames, torch.int32, "n_frames")
+    B = offset.numel()
+    if n_frames.numel() != B or channels.numel() not in (0, B):
+        raise _lib.LipreadError("pcm_ingest: offset, n_frames and channels must have one entry per clip")
+    if channels.numel():
+        _need(channels, torch.int32, "channels")
+    wav = torch.empty(B, target, dtype=torch.float32, device=pcm.device)
+    check(lib.lr_pcm_ingest(_ptr(pcm), _ptr(offset), _ptr(n_frames), _ptr(channels) if channels.numel() else None,
+                            scale, _ptr(wav), B, target, _stream()))
+    return wav
+
+
+@pcm_ingest.register_fake
+def _(pcm, offset, n_frames, channels, scale, target):
+    return pcm.new_empty(offset.numel(), target, dtype=torch.float32)

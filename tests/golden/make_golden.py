@@ -2,7 +2,7 @@
 
 Run in the build container only (needs /root/reference, read-only):
     python tests/golden/make_golden.py
-Writes tests/golden/logmel_golden.npz, tests/golden/midfusion_golden.npz and tests/golden/models_golden.npz.
+Writes tests/golden/dataset_golden.npz, tests/golden/logmel_golden.npz, tests/golden/midfusion_golden.npz and tests/golden/models_golden.npz.
 
 Recipe: stub the unused top-level imports `librosa` / `pydub`, make the
 ImageNet weight download a no-op (seeded random init instead), and load one reference
@@ -259,11 +259,73 @@ def golden_models():
     np.savez_compressed(os.path.join(HERE, "models_golden.npz"), **out)
 
 
+def golden_dataset():
+    """The reference's own VisualDataset / GLipsMultimodalDataset over synthetic.write_dataset_tree: sample lists and
+    items.  The m4a decode (pydub + ffmpeg, absent here) is the one stubbed call: AudioSegment.from_file returns the
+    int16 samples the tree's audio files hold, so AudioProcessor.load_audio's own float conversion and pad / truncate
+    (audio_processor.py:29,37-44) run unmodified."""
+    import tempfile
+
+    class FakeSegment:
+        def __init__(self, a):
+            self.a = a
+
+        @classmethod
+        def from_file(cls, path, format=None):
+            return cls(np.load(path))
+
+        def set_frame_rate(self, r):
+            return self
+
+        def set_channels(self, c):
+            return self
+
+        def get_array_of_samples(self):
+            return self.a
+
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        root = os.path.join(tmp, "GLips_4")
+        synthetic.write_dataset_tree(root)
+        sys.modules["pydub"].AudioSegment = FakeSegment
+        mod = load_ref("audio_video", "data_utils.dataset_av")
+        sys.modules["utils.audio_processor"].AudioSegment = FakeSegment
+        for split in ("train", "val"):
+            ds = mod.GLipsMultimodalDataset(root, 117, split=split)
+            keys = []
+            for i in range(len(ds)):
+                mel, lips, label = ds[i]
+                rel = os.path.relpath(ds.samples[i]["video_path"], root + "_lip_regions")
+                key = os.path.splitext(rel)[0].split(os.sep, 1)[1].replace(os.sep, "/")
+                keys.append(key)
+                out[f"mel|{key}"] = mel.numpy()
+                out[f"lips|{key}"] = lips.numpy()
+                out[f"label|{key}"] = np.array(int(label))
+            out[f"keys_av|{split}"] = np.array(sorted(keys))
+            vds = mod.VisualDataset(root, root + "_lip_regions", split=split)
+            vkeys = []
+            for i in range(len(vds)):
+                item = vds[i]
+                rel = os.path.relpath(vds.samples[i][0], root + "_lip_regions")
+                key = os.path.splitext(rel)[0].split(os.sep, 1)[1].replace(os.sep, "/")
+                vkeys.append(key)
+                out[f"vlabel|{key}"] = np.array(int(item["label"]))
+                out[f"vsum|{key}"] = np.array(item["lip_regions"].double().sum().item())
+            out[f"keys_video|{split}"] = np.array(sorted(vkeys))
+            out[f"classes|{split}"] = np.array(vds.classes)
+    np.savez_compressed(os.path.join(HERE, "dataset_golden.npz"), **out)
+    print("dataset golden:", {k: v.tolist() for k, v in out.items() if k.startswith("keys_av")})
+
+
 if __name__ == "__main__":
     _stub_unused_imports()
     _offline_weights()
     torch.set_num_threads(8)
+    if "--dataset-only" in sys.argv:
+        golden_dataset()
+        sys.exit(0)
     if "--models-only" not in sys.argv:
+        golden_dataset()
         golden_logmel()
         golden_midfusion()
     golden_models()

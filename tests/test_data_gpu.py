@@ -1,0 +1,132 @@
+"""On-GPU input path, through the C ABI (lr_pcm_ingest -> lr_logmel_fwd, uint8 frames into the stem gather), against
+the golden items of the reference's own GLipsMultimodalDataset and against oracle/dataset.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from multimodal_lipread_b200 import data, synthetic
+from oracle import dataset as ods
+from oracle import logmel as olm
+
+pytestmark = pytest.mark.gpu
+
+
+def _key(video_path, root):
+    rel = os.path.relpath(video_path, root + "_lip_regions")
+    return os.path.splitext(rel)[0].split(os.sep, 1)[1].replace(os.sep, "/")
+
+
+def _decode(path):
+    a = np.load(path)
+    return a, 1, 1.0
+
+
+@pytest.mark.parametrize("case", ["mono_aligned", "mono_odd_offsets", "stereo", "mixed_channels", "scaled"])
+def test_pcm_ingest_is_bit_exact(cuda_device, case):
+    """Ragged lengths on both sides of 20 000, empty clips, offsets of any parity, 1-3 channels: equals
+    audio_processor.py:29,37-44 restated in oracle/dataset.py load_audio, bit for bit."""
+    from multimodal_lipread_b200 import ops
+    g = np.random.default_rng(5)
+    lens = [0, 1, 3, 19999, 20000, 20001, 26000, 12345, 7, 20003]
+    chans = {"mono_aligned": [1] * 10, "mono_odd_offsets": [1] * 10, "stereo": [2] * 10,
+             "mixed_channels": [1, 2, 3, 1, 2, 3, 1, 2, 3, 2], "scaled": [2, 1] * 5}[case]
+    scale = 1.0 / 32768.0 if case == "scaled" else 1.0
+    clips = [g.integers(-32768, 32768, size=(n, c), dtype=np.int16) for n, c in zip(lens, chans)]
+    parts, offs, pos = [], [], 0
+    for a in clips:
+        pad = (-pos) % 8 if case == "mono_aligned" else (1 if case == "mono_odd_offsets" else 0)
+        parts.append(np.zeros(pad, np.int16))
+        pos += pad
+        offs.append(pos)
+        parts.append(a.reshape(-1))
+        pos += a.size
+    packed = torch.from_numpy(np.concatenate(parts + [np.zeros(8, np.int16)])).to(cuda_device)
+    out = ops.pcm_ingest(packed, torch.tensor(offs, dtype=torch.int64, device=cuda_device),
+                         torch.tensor(lens, dtype=torch.int32, device=cuda_device),
+                         torch.tensor(chans, dtype=torch.int32, device=cuda_device), scale, 20000).cpu()
+    for b, a in enumerate(clips):
+        ref = ods.load_audio(a[:, 0] if a.shape[1] == 1 else a.T, scale)
+        assert torch.equal(out[b], ref), (case, b, (out[b] - ref).abs().max())
+    # all-mono shortcut (channels == NULL) and the empty batch
+    if case.startswith("mono"):
+        out2 = ops.pcm_ingest(packed, torch.tensor(offs, dtype=torch.int64, device=cuda_device),
+                              torch.tensor(lens, dtype=torch.int32, device=cuda_device),
+                              torch.empty(0, dtype=torch.int32, device=cuda_device), scale, 20000).cpu()
+        assert torch.equal(out2, out)
+    e = ops.pcm_ingest(packed, torch.empty(0, dtype=torch.int64, device=cuda_device),
+                       torch.empty(0, dtype=torch.int32, device=cuda_device),
+                       torch.empty(0, dtype=torch.int32, device=cuda_device), scale, 20000)
+    assert e.shape == (0, 20000)
+
+
+@pytest.mark.parametrize("batch_size,shuffle", [(4, False), (2, True), (16, False)])
+def test_loader_batches_match_the_reference_items(cuda_device, golden_dir, tmp_path, batch_size, shuffle):
+    golden = np.load(os.path.join(golden_dir, "dataset_golden.npz"))
+    root = str(tmp_path / "GLips_4")
+    synthetic.write_dataset_tree(root)
+    for split in ("train", "val"):
+        ds = data.GLipsMultimodalDataset(root, 117, split)
+        loader = data.DeviceBatchLoader(ds, batch_size, shuffle=shuffle, device=cuda_device, depth=2, workers=4, seed=11,
+                                        audio_decoder=_decode)
+        order = data.batch_indices(len(ds), batch_size, shuffle, False, torch.Generator().manual_seed(11))
+        seen = []
+        assert len(loader) == len(order)
+        for idxs, (mel, lips, labels) in zip(order, loader):
+            assert mel.is_cuda and lips.dtype == torch.uint8 and tuple(lips.shape) == (len(idxs), 5, 12, 12, 3)
+            mel_h, lips_h, lab_h = mel.cpu(), lips.cpu(), labels.cpu()       # copy out: the ring reuses the buffers
+            for j, i in enumerate(idxs):
+                k = _key(ds.samples[i]["video_path"], root)
+                seen.append(k)
+                ref = golden[f"mel|{k}"]                                    # the reference's own fp32 item
+                ref64 = olm.logmel_frontend(ods.load_audio(np.load(ds.samples[i]["audio_path"])).numpy()[None])[0]
+                noise = np.abs(ref - ref64).max()
+                assert np.abs(mel_h[j].numpy() - ref64).max() <= 1e-4 * np.abs(ref64).max()
+                assert np.abs(mel_h[j].numpy() - ref).max() <= 1e-4 * np.abs(ref).max() + noise
+                got = (lips_h[j].float() / 255.0).permute(3, 0, 1, 2)
+                assert np.array_equal(got.numpy(), golden[f"lips|{k}"])
+                assert int(lab_h[j]) == int(golden[f"label|{k}"])
+        assert sorted(seen) == golden[f"keys_av|{split}"].tolist()
+        loader.close()
+    vds = data.VisualDataset(root, root + "_lip_regions", "train")
+    vl = data.DeviceBatchLoader(vds, batch_size, device=cuda_device, workers=2)
+    n = 0
+    for batch in vl:
+        assert set(batch) == {"lip_regions", "label"}
+        for j in range(batch["label"].numel()):
+            k = _key(vds.samples[n][0], root)
+            assert int(batch["label"][j]) == int(golden[f"vlabel|{k}"])
+            assert (batch["lip_regions"][j].double() / 255.0).sum().item() == pytest.approx(float(golden[f"vsum|{k}"]), rel=1e-6)
+            n += 1
+    assert n == len(vds)
+    vl.close()
+
+
+def test_loader_feeds_the_train_step(cuda_device, tmp_path):
+    """Files -> pinned ring -> HBM -> MidFusionFast.train_step: the loss equals the oracle model's on the items the
+    oracle dataset (pinned to the reference's) yields for the same files."""
+    from multimodal_lipread_b200 import audio_video_models as M
+    from oracle import av_models as O
+    root = str(tmp_path / "GLips_4")
+    synthetic.write_dataset_tree(root, per_split={"train": 2}, T=6, size=44, missing_every=1000)
+    ds = data.GLipsMultimodalDataset(root, 117, "train")
+    assert len(ds) == 6
+    torch.manual_seed(0)
+    ref = O.MidFusionFastOracle(3).train()
+    ours = M.create_mid_fusion_fast(3, O.DictConfig()).to(cuda_device)
+    ours.load_state_dict(ref.state_dict())
+    ours.train()
+    ours.configure_optimizer(lr=3e-4)
+    loader = data.DeviceBatchLoader(ds, 6, device=cuda_device, audio_decoder=_decode)
+    n = 0
+    for mel, lips, labels in loader:
+        loss, logits = ours.train_step(mel, lips, labels)
+        items = [ods.getitem_multimodal(s, lambda p: np.load(p)) for s in ds.samples]
+        rlogits = ref(torch.stack([i[0] for i in items]), torch.stack([i[1] for i in items]))
+        rl = torch.nn.functional.cross_entropy(rlogits, torch.stack([i[2] for i in items]))
+        assert abs(float(loss) - float(rl)) < 5e-4 * max(1.0, abs(float(rl)))
+        assert (logits.cpu() - rlogits.detach()).abs().max() < 5e-3 * rlogits.abs().max()
+        n += 1
+    assert n == 1
+    loader.close()

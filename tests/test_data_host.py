@@ -1,0 +1,184 @@
+"""Host side of the on-GPU input path (multimodal_lipread_b200/data.py) and its oracle (oracle/dataset.py) against the
+golden items the reference's own GLipsMultimodalDataset / VisualDataset produced over the same synthetic tree
+(tests/golden/make_golden.py golden_dataset).  No GPU: sample lists, file readers, ring-slot staging."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from multimodal_lipread_b200 import data, synthetic
+from oracle import dataset as ods
+
+
+@pytest.fixture(scope="module")
+def tree(tmp_path_factory):
+    root = str(tmp_path_factory.mktemp("glips") / "GLips_4")
+    truth = synthetic.write_dataset_tree(root)
+    return root, truth
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "dataset_golden.npz"))
+
+
+def _key(video_path, root):
+    rel = os.path.relpath(video_path, root + "_lip_regions")
+    return os.path.splitext(rel)[0].split(os.sep, 1)[1].replace(os.sep, "/")
+
+
+def _decode(path):
+    return np.load(path)
+
+
+@pytest.mark.parametrize("split", ["train", "val"])
+def test_oracle_items_match_the_reference(tree, golden, split):
+    root, _ = tree
+    samples = ods.scan_multimodal(root, split)
+    assert sorted(_key(s["video_path"], root) for s in samples) == golden[f"keys_av|{split}"].tolist()
+    for s in samples:
+        k = _key(s["video_path"], root)
+        mel, lips, label = ods.getitem_multimodal(s, _decode)
+        assert int(label) == int(golden[f"label|{k}"])
+        assert np.array_equal(lips.numpy(), golden[f"lips|{k}"])
+        assert mel.shape == (80, 117) and np.abs(mel.numpy() - golden[f"mel|{k}"]).max() < 1e-5
+    classes, vis = ods.scan_visual(root, root + "_lip_regions", split)
+    assert classes == golden[f"classes|{split}"].tolist()
+    assert sorted(_key(p, root) for p, _ in vis) == golden[f"keys_video|{split}"].tolist()
+    for smp in vis:
+        item = ods.getitem_visual(smp)
+        k = _key(smp[0], root)
+        assert int(item["label"]) == int(golden[f"vlabel|{k}"])
+        assert item["lip_regions"].double().sum().item() == float(golden[f"vsum|{k}"])
+
+
+@pytest.mark.parametrize("split", ["train", "val", "test"])
+def test_sample_lists_equal_the_oracle_scan(tree, split):
+    root, _ = tree
+    vds = data.VisualDataset(root, root + "_lip_regions", split)
+    classes, vis = ods.scan_visual(root, root + "_lip_regions", split)
+    assert vds.classes == classes and vds.samples == vis and len(vds) == len(vis)
+    ds = data.GLipsMultimodalDataset(root, 117, split)
+    assert ds.samples == ods.scan_multimodal(root, split)
+    if split == "test":
+        assert len(ds) == 0
+
+
+def test_ring_slot_staging_is_byte_exact(tree):
+    root, truth = tree
+    ds = data.GLipsMultimodalDataset(root, 117, "train")
+    slot = data.HostSlot(len(ds), (5, 12, 12, 3), True, 2, pin=False)
+    for j in range(len(ds)):
+        scale = slot.stage_clip(j, *ds.paths(j), lambda p: (np.load(p), 1, 1.0))
+        assert scale == 1.0
+        pcm, lips, label = truth[_key(ds.samples[j]["video_path"], root)]
+        assert np.array_equal(slot.frames[j].numpy(), lips) and int(slot.labels[j]) == label
+        off, n, ch = (int(slot.meta[r, j]) for r in range(3))
+        assert off == j * slot.cap and off % 8 == 0 and ch == 1 and n == min(len(pcm), 20000)
+        assert np.array_equal(slot.pcm.view(-1).numpy()[off:off + n], pcm[:n])
+
+
+def test_native_batch_staging_equals_the_python_restatement(tree, tmp_path):
+    root, truth = tree
+    ds = data.GLipsMultimodalDataset(root, 117, "train")
+    items = [ds.paths(j) for j in range(len(ds))]
+    # the tree's audio files are .npy payloads under an .m4a name: give the native reader .npy names
+    for a, _, _ in items:
+        os.link(a, a[:-4] + ".npy") if not os.path.exists(a[:-4] + ".npy") else None
+    items = [(a[:-4] + ".npy", v, l) for a, v, l in items]
+    py = data.HostSlot(len(ds), (5, 12, 12, 3), True, 2, pin=False)
+    for j, it in enumerate(items):
+        py.stage_clip(j, *it, data.decode_pcm16)
+    for threads in (1, 4):
+        nat = data.HostSlot(len(ds), (5, 12, 12, 3), True, 2, pin=False)
+        nat.pcm.zero_(), py.pcm.mul_(1)
+        assert nat.stage_batch(items, data.decode_pcm16, threads) == 1.0 and nat.n == len(ds)
+        assert torch.equal(nat.frames, py.frames) and torch.equal(nat.labels, py.labels)
+        assert torch.equal(nat.meta, py.meta)
+        for j in range(len(ds)):
+            n = int(py.meta[1, j])
+            assert torch.equal(nat.pcm[j, :n], py.pcm[j, :n])
+    # a custom decoder keeps the per-clip path for the audio and the native path for the frames
+    nat = data.HostSlot(len(ds), (5, 12, 12, 3), True, 2, pin=False)
+    assert nat.stage_batch([ds.paths(j) for j in range(len(ds))], lambda p: (np.load(p), 1, 1.0), 2) == 1.0
+    assert torch.equal(nat.frames, py.frames) and torch.equal(nat.meta, py.meta)
+    # errors name the file
+    from multimodal_lipread_b200._lib import LipreadError
+    bad = list(items)
+    bad[2] = (bad[2][0], str(tmp_path / "missing.npy"), 0)
+    with pytest.raises(LipreadError, match="missing.npy"):
+        nat.stage_batch(bad, data.decode_pcm16, 3)
+    np.save(tmp_path / "float.npy", np.zeros((5, 12, 12, 3), np.float32))
+    bad[2] = (bad[2][0], str(tmp_path / "float.npy"), 0)
+    with pytest.raises(LipreadError, match="uint8"):
+        nat.stage_batch(bad, data.decode_pcm16, 3)
+    np.save(tmp_path / "shape.npy", np.zeros((5, 12, 13, 3), np.uint8))
+    bad[2] = (bad[2][0], str(tmp_path / "shape.npy"), 0)
+    with pytest.raises(LipreadError, match="batch shape"):
+        nat.stage_batch(bad, data.decode_pcm16, 3)
+    raw = open(items[0][1], "rb").read()
+    (tmp_path / "cut.npy").write_bytes(raw[:-7])
+    bad[2] = (bad[2][0], str(tmp_path / "cut.npy"), 0)
+    with pytest.raises(LipreadError, match="truncated"):
+        nat.stage_batch(bad, data.decode_pcm16, 3)
+    np.save(tmp_path / "stereo.npy", np.arange(60, dtype=np.int16).reshape(30, 2))
+    ok = [(str(tmp_path / "stereo.npy"), items[0][1], 1)]
+    assert nat.stage_batch(ok, data.decode_pcm16, 1) == 1.0
+    assert nat.meta[:, 0].tolist() == [0, 30, 2] and nat.pcm[0, :60].tolist() == list(range(60))
+
+
+def test_npy_reader_refuses_what_the_kernels_cannot_take(tmp_path):
+    good = np.arange(2 * 3 * 4 * 3, dtype=np.uint8).reshape(2, 3, 4, 3)
+    np.save(tmp_path / "a.npy", good)
+    dst = np.zeros_like(good)
+    assert data.read_npy_u8_into(str(tmp_path / "a.npy"), dst) == good.shape and np.array_equal(dst, good)
+    with pytest.raises(ValueError, match="differ from the batch shape"):
+        data.read_npy_u8_into(str(tmp_path / "a.npy"), np.zeros((2, 3, 4, 4), np.uint8))
+    np.save(tmp_path / "f.npy", good.astype(np.float32))
+    with pytest.raises(ValueError, match="uint8"):
+        data.read_npy_u8_into(str(tmp_path / "f.npy"), dst)
+    np.save(tmp_path / "t.npy", good)
+    raw = (tmp_path / "t.npy").read_bytes()
+    (tmp_path / "t.npy").write_bytes(raw[:-5])
+    with pytest.raises(ValueError, match="truncated"):
+        data.read_npy_u8_into(str(tmp_path / "t.npy"), dst)
+    (tmp_path / "x.npy").write_bytes(b"not numpy at all")
+    with pytest.raises(ValueError, match="not a .npy"):
+        data.read_npy_u8_into(str(tmp_path / "x.npy"), dst)
+
+
+def test_builtin_decoder(tmp_path):
+    import wave
+    pcm = (np.arange(3000) % 200 - 100).astype(np.int16)
+    st = np.stack([pcm, -pcm], axis=1)
+    with wave.open(str(tmp_path / "s.wav"), "wb") as w:
+        w.setnchannels(2), w.setsampwidth(2), w.setframerate(16000)
+        w.writeframes(st.tobytes())
+    a, ch, scale = data.decode_pcm16(str(tmp_path / "s.wav"))
+    assert ch == 2 and scale == 1.0 / 32768.0 and np.array_equal(a.reshape(-1, 2), st)
+    with wave.open(str(tmp_path / "r.wav"), "wb") as w:
+        w.setnchannels(1), w.setsampwidth(2), w.setframerate(8000)
+        w.writeframes(pcm.tobytes())
+    with pytest.raises(ValueError, match="resample"):
+        data.decode_pcm16(str(tmp_path / "r.wav"))
+    with pytest.raises(ValueError, match="audio_decoder"):
+        data.decode_pcm16(str(tmp_path / "clip.m4a"))
+    np.save(tmp_path / "p.npy", st)
+    a, ch, scale = data.decode_pcm16(str(tmp_path / "p.npy"))
+    assert ch == 2 and scale == 1.0 and np.array_equal(a, st.reshape(-1))
+
+
+def test_batch_order_and_loader_needs_the_gpu(tree):
+    g = torch.Generator().manual_seed(3)
+    b = data.batch_indices(10, 4, False, False, g)
+    assert b == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
+    assert data.batch_indices(10, 4, False, True, g) == [[0, 1, 2, 3], [4, 5, 6, 7]]
+    s = data.batch_indices(10, 4, True, False, torch.Generator().manual_seed(3))
+    assert sorted(sum(s, [])) == list(range(10)) and s == data.batch_indices(10, 4, True, False, torch.Generator().manual_seed(3))
+    root, _ = tree
+    ds = data.GLipsMultimodalDataset(root, 117, "train")
+    with pytest.raises(NotImplementedError):
+        data.DeviceBatchLoader(ds, 4, device="cpu")
+    with pytest.raises(RuntimeError, match="empty"):
+        data.DeviceBatchLoader(data.GLipsMultimodalDataset(root, 117, "test"), 4)
