@@ -229,9 +229,16 @@ class FlatParams:
         raise KeyError("parameter not owned by this FlatParams")
 
     def init_adam(self, lr):
-        self.m = torch.zeros_like(self.flat)
-        self.v = torch.zeros_like(self.flat)
-        self.adam_state = torch.tensor([0.0, 0.0, 0.0, float(lr)], dtype=torch.float32, device=self.device)
+        """Zero moments and step counter.  Buffers are reused when they exist: captured step graphs hold their
+        addresses."""
+        if self.m is None:
+            self.m = torch.zeros_like(self.flat)
+            self.v = torch.zeros_like(self.flat)
+            self.adam_state = torch.zeros(4, dtype=torch.float32, device=self.device)
+        else:
+            self.m.zero_()
+            self.v.zero_()
+        self.adam_state.copy_(torch.tensor([0.0, 0.0, 0.0, float(lr)]))
 
 
 class T2:

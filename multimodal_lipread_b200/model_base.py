@@ -311,6 +311,7 @@ class PlanModel(nn.Module):
         lr = self.DEFAULT_LR if lr is None else lr
         weight_decay = self.DEFAULT_WD if weight_decay is None else weight_decay
         self._opt = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        self._graphs.clear()                        # betas / eps / weight decay are launch arguments baked into graphs
         if self._flat is not None:
             self._flat.init_adam(lr)
 
@@ -323,6 +324,51 @@ class PlanModel(nn.Module):
         self._opt["lr"] = float(lr)
         if self._flat is not None and self._flat.adam_state is not None:
             self._flat.adam_state[3] = float(lr)
+
+    def optimizer_state_dict(self):
+        """The Adam state in the layout of torch.optim.Adam(model.parameters()).state_dict() -- what the reference
+        stores under "optimizer" in its checkpoints (video/train.py:246-251, audio_cues_video/train.py:178-183), so a
+        run can be resumed by either side.  Parameter indices follow model.parameters() order."""
+        if not hasattr(self, "_opt"):
+            self.configure_optimizer()
+        o, flat = self._opt, self._flat
+        n_params = len(list(self.parameters()))
+        state = {}
+        if flat is not None and flat.m is not None and float(flat.adam_state[0]) > 0:
+            step = float(flat.adam_state[0])
+            for i, (p, off) in enumerate(zip(flat.params, flat.offsets)):
+                state[i] = {"step": torch.tensor(step), "exp_avg": flat.m[off:off + p.numel()].view(p.shape).clone(),
+                            "exp_avg_sq": flat.v[off:off + p.numel()].view(p.shape).clone()}
+        group = {"lr": o["lr"], "betas": tuple(o["betas"]), "eps": o["eps"], "weight_decay": o["weight_decay"],
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "decoupled_weight_decay": False, "params": list(range(n_params))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd):
+        """Inverse of optimizer_state_dict; accepts a state_dict written by the reference's torch.optim.Adam."""
+        (group,) = sd["param_groups"]
+        if group.get("amsgrad") or group.get("maximize"):
+            raise ValueError("the Adam kernel implements the reference's plain Adam (no amsgrad / maximize)")
+        self.configure_optimizer(lr=group["lr"], betas=tuple(group["betas"]), eps=group["eps"],
+                                 weight_decay=group["weight_decay"])
+        if not sd["state"]:
+            return
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("move the model to its CUDA device (model.to(device)) before loading optimizer state")
+        flat = self._ensure_flat(dev)
+        if len(sd["state"]) != len(flat.params):
+            raise ValueError(f"optimizer state has {len(sd['state'])} entries, the model {len(flat.params)} parameters")
+        flat.init_adam(group["lr"])
+        steps = set()
+        for i, (p, off) in enumerate(zip(flat.params, flat.offsets)):
+            st = sd["state"][i]
+            flat.m[off:off + p.numel()].view(p.shape).copy_(st["exp_avg"])
+            flat.v[off:off + p.numel()].view(p.shape).copy_(st["exp_avg_sq"])
+            steps.add(float(st["step"]))
+        if len(steps) != 1:
+            raise ValueError("per-parameter step counts differ; the flat Adam state keeps one")
+        flat.adam_state[0] = steps.pop()
 
     def train_step(self, *inputs_and_labels, grad_allreduce=None, world=1, use_graph=True):
         """One training iteration entirely in lipread_b200 kernels:

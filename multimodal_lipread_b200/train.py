@@ -159,3 +159,149 @@ def default_batch_to_inputs(batch):
         return (batch["lip_regions"],), batch["label"]
     *inputs, labels = batch
     return tuple(inputs), labels
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Run bookkeeping around the epochs: log files, plateau schedule, checkpoints.  Formats are the reference's so that
+# downstream plotting and resume keep working after the switch.
+# ----------------------------------------------------------------------------------------------------------------
+LOG_HEADER = ["epoch", "train_loss", "train_acc", "val_loss", "val_acc", "test_loss", "test_acc"]
+
+
+def init_log_files(model_name, out_dir="./metrics"):
+    """<out_dir>/<model>_training_log.csv with the reference's header row and the .txt companion
+    (video/train.py:33-53, audio_video/train.py:21-33, audio_cues_video/train.py:25-35)."""
+    import csv
+    os.makedirs(out_dir, exist_ok=True)
+    csv_path = os.path.join(out_dir, f"{model_name}_training_log.csv")
+    txt_path = os.path.join(out_dir, f"{model_name}_training_log.txt")
+    if not os.path.exists(csv_path):
+        with open(csv_path, "w", newline="") as f:
+            csv.writer(f).writerow(LOG_HEADER)
+    if not os.path.exists(txt_path):
+        with open(txt_path, "w") as f:
+            f.write("Training Log\n\n")
+    return csv_path, txt_path
+
+
+def log_to_files(model_name, epoch, train_loss, train_acc, val_loss, val_acc, test_loss, test_acc, out_dir="./metrics"):
+    """One CSV row + one text block per epoch (audio_video/train.py:36-48)."""
+    import csv
+    with open(os.path.join(out_dir, f"{model_name}_training_log.csv"), "a", newline="") as f:
+        csv.writer(f).writerow([epoch, train_loss, train_acc, val_loss, val_acc, test_loss, test_acc])
+    with open(os.path.join(out_dir, f"{model_name}_training_log.txt"), "a") as f:
+        f.write(f"Epoch {epoch}\n"
+                f"  Train Loss: {train_loss:.4f}, Train Acc: {train_acc:.2f}%\n"
+                f"  Val Loss:   {val_loss:.4f}, Val Acc:   {val_acc:.2f}%\n"
+                f"  Test Loss:  {test_loss:.4f}, Test Acc:  {test_acc:.2f}%\n\n")
+
+
+def log_final_results(model_name, test_loss, test_acc, out_dir="./metrics"):
+    """audio_video/train.py:51-53."""
+    with open(os.path.join(out_dir, f"{model_name}_training_log.txt"), "a") as f:
+        f.write(f"Final Test Loss: {test_loss:.4f}, Final Test Acc: {test_acc:.2f}%\n")
+
+
+class ReduceLROnPlateau:
+    """optim.lr_scheduler.ReduceLROnPlateau as the reference configures it -- mode "max" on val_acc, factor 0.5,
+    patience 5 (video/train.py:213-215); mode "min" on val_loss (audio/train.py:156, patience 5;
+    audio_cues_video/train.py:163, patience 3) -- with torch's defaults for the rest (threshold 1e-4 relative,
+    cooldown 0, min_lr 0, eps 1e-8).  The new rate goes to the device-side Adam state through model.set_lr."""
+
+    def __init__(self, model, mode="min", factor=0.5, patience=5, threshold=1e-4, min_lr=0.0, eps=1e-8):
+        if mode not in ("min", "max"):
+            raise ValueError(f"mode {mode} is unknown!")
+        if factor >= 1.0:
+            raise ValueError("Factor should be < 1.0.")
+        self.model, self.mode, self.factor, self.patience = model, mode, factor, patience
+        self.threshold, self.min_lr, self.eps = threshold, min_lr, eps
+        self.best = float("inf") if mode == "min" else -float("inf")
+        self.num_bad_epochs = 0
+        self.last_epoch = 0
+
+    def is_better(self, a):
+        if self.mode == "min":
+            return a < self.best * (1.0 - self.threshold)
+        return a > self.best * (self.threshold + 1.0)
+
+    def step(self, metric):
+        current = float(metric)
+        self.last_epoch += 1
+        if self.is_better(current):
+            self.best, self.num_bad_epochs = current, 0
+        else:
+            self.num_bad_epochs += 1
+        if self.num_bad_epochs > self.patience:
+            old = self.model._opt["lr"]
+            new = max(old * self.factor, self.min_lr)
+            if old - new > self.eps:
+                self.model.set_lr(new)
+            self.num_bad_epochs = 0
+
+    def state_dict(self):
+        return {k: v for k, v in self.__dict__.items() if k != "model"}
+
+    def load_state_dict(self, sd):
+        self.__dict__.update(sd)
+
+
+def make_checkpoint(model, epoch, best_val_acc):
+    """video/train.py:246-251 / audio_cues_video/train.py:178-183: {"epoch": next epoch, "state_dict", "optimizer",
+    "best_val_acc"}; the optimizer entry has torch.optim.Adam's state_dict layout."""
+    return {"epoch": epoch + 1, "state_dict": model.state_dict(), "optimizer": model.optimizer_state_dict(),
+            "best_val_acc": best_val_acc}
+
+
+def resume(model, path):
+    """video/train.py:221-227 -> (start_epoch, best_val_acc).  Also reads audio/train.py:174-179 checkpoints
+    ({"model_state_dict", "optimizer_state_dict", "val_acc", "epoch"}) and bare state_dicts
+    (audio_video/train.py:150,153)."""
+    ckpt = torch.load(path, map_location="cpu")
+    if "state_dict" in ckpt:
+        model.load_state_dict(ckpt["state_dict"])
+        model.load_optimizer_state_dict(ckpt["optimizer"])
+        return ckpt["epoch"], ckpt["best_val_acc"]
+    if "model_state_dict" in ckpt:
+        model.load_state_dict(ckpt["model_state_dict"])
+        model.load_optimizer_state_dict(ckpt["optimizer_state_dict"])
+        return ckpt["epoch"] + 1, ckpt["val_acc"]
+    model.load_state_dict(ckpt)
+    return 1, 0.0
+
+
+def fit(model, model_name, loaders, device, epochs, save_dir, out_dir="./metrics", schedule=None, resume_from=None,
+        batch_to_inputs=None, log=print):
+    """The epoch loop of the reference's main(): train, validate, test every epoch, log, keep
+    `<model>_checkpoint.pth` and `model_best.pth`, reload the best weights for the final test and write
+    test_results.txt (video/train.py:232-283; audio_cues_video/train.py:166-207).
+    loaders = (train, val, test); schedule = None | ("max" | "min", patience) for ReduceLROnPlateau on
+    val_acc | val_loss.  Returns {"best_val_acc", "test_loss", "test_acc"}."""
+    train_loader, val_loader, test_loader = loaders
+    os.makedirs(save_dir, exist_ok=True)
+    init_log_files(model_name, out_dir)
+    sched = ReduceLROnPlateau(model, mode=schedule[0], factor=0.5, patience=schedule[1]) if schedule else None
+    start_epoch, best_val_acc = (1, 0.0) if not resume_from else resume(model, resume_from)
+    for epoch in range(start_epoch, epochs + 1):
+        train_loss, train_acc = train_epoch(model, train_loader, device, batch_to_inputs)
+        val_loss, val_acc = validate(model, val_loader, device, batch_to_inputs)
+        if sched:
+            sched.step(val_acc if sched.mode == "max" else val_loss)
+        test_loss, test_acc = validate(model, test_loader, device, batch_to_inputs)
+        log(f"Epoch {epoch}/{epochs}  Train Loss: {train_loss:.4f} | Train Acc: {train_acc:.2f}%  "
+            f"Val Loss: {val_loss:.4f} | Val Acc: {val_acc:.2f}%  Test Loss: {test_loss:.4f} | Test Acc: {test_acc:.2f}%")
+        log_to_files(model_name, epoch, train_loss, train_acc, val_loss, val_acc, test_loss, test_acc, out_dir)
+        is_best = val_acc > best_val_acc or not os.path.exists(os.path.join(save_dir, "model_best.pth"))
+        best_val_acc = max(best_val_acc, val_acc)
+        ckpt = make_checkpoint(model, epoch, best_val_acc)
+        torch.save(ckpt, os.path.join(save_dir, f"{model_name}_checkpoint.pth"))
+        if is_best:
+            torch.save(ckpt, os.path.join(save_dir, "model_best.pth"))
+    best = torch.load(os.path.join(save_dir, "model_best.pth"), map_location="cpu")
+    model.load_state_dict(best["state_dict"])
+    test_loss, test_acc = validate(model, test_loader, device, batch_to_inputs)
+    log_final_results(model_name, test_loss, test_acc, out_dir)
+    with open(os.path.join(save_dir, "test_results.txt"), "w") as f:
+        f.write(f"Final Test Loss: {test_loss:.4f}\n")
+        f.write(f"Final Test Acc: {test_acc:.2f}%\n")
+        f.write(f"Best Val Acc: {best_val_acc:.2f}%\n")
+    return {"best_val_acc": best_val_acc, "test_loss": test_loss, "test_acc": test_acc}

@@ -130,3 +130,58 @@ def test_loader_feeds_the_train_step(cuda_device, tmp_path):
         n += 1
     assert n == 1
     loader.close()
+
+
+def test_fit_run_checkpoints_logs_and_resume_interop(cuda_device, tmp_path):
+    """The reference's main() loop on files: per-epoch CSV rows, `<model>_checkpoint.pth` / `model_best.pth` in the
+    reference's dict format whose "optimizer" entry loads into torch.optim.Adam (and back), resume continues the
+    Adam state exactly."""
+    import csv
+    from multimodal_lipread_b200 import audio_video_models as M, train as T
+    from oracle import av_models as O
+    root = str(tmp_path / "GLips_4")
+    synthetic.write_dataset_tree(root, per_split={"train": 4, "val": 2, "test": 2}, T=6, size=44, missing_every=1000)
+    loaders = tuple(data.DeviceBatchLoader(data.GLipsMultimodalDataset(root, 117, s), 4, shuffle=(s == "train"),
+                                           device=cuda_device, audio_decoder=_decode) for s in ("train", "val", "test"))
+    torch.manual_seed(0)
+    model = M.create_mid_fusion_fast(3, O.DictConfig()).to(cuda_device)
+    model.configure_optimizer(lr=3e-4)
+    save_dir, out_dir = str(tmp_path / "ckpt"), str(tmp_path / "metrics")
+    res = T.fit(model, "middle_fusion_fast", loaders, cuda_device, 2, save_dir, out_dir, schedule=("max", 5), log=lambda s: None)
+    rows = list(csv.reader(open(os.path.join(out_dir, "middle_fusion_fast_training_log.csv"))))
+    assert rows[0] == T.LOG_HEADER and [r[0] for r in rows[1:]] == ["1", "2"]
+    assert all(np.isfinite(float(v)) for r in rows[1:] for v in r[1:])
+    assert 0.0 <= res["test_acc"] <= 100.0 and os.path.exists(os.path.join(save_dir, "test_results.txt"))
+    ck = torch.load(os.path.join(save_dir, "middle_fusion_fast_checkpoint.pth"), map_location="cpu")
+    assert set(ck) == {"epoch", "state_dict", "optimizer", "best_val_acc"} and ck["epoch"] == 3
+    # the reference side can resume from it: same keys, and torch's Adam accepts the optimizer entry
+    ref = O.MidFusionFastOracle(3)
+    ref.load_state_dict(ck["state_dict"])
+    opt = torch.optim.Adam(ref.parameters(), lr=1.0)
+    opt.load_state_dict(ck["optimizer"])
+    assert opt.param_groups[0]["lr"] == pytest.approx(3e-4) and len(opt.state) == len(list(ref.parameters()))
+    steps_done = 2 * len(loaders[0])
+    assert all(float(s["step"]) == steps_done for s in opt.state.values())
+    # ... take one step on the reference side, hand the state back, and take the same step here from the checkpoint
+    items = [ods.getitem_multimodal(s, lambda p: np.load(p)) for s in loaders[0].ds.samples[:4]]
+    mel, lips, lab = (torch.stack([i[k] for i in items]) for k in range(3))
+    ref.train()
+    torch.nn.functional.cross_entropy(ref(mel, lips), lab).backward()
+    opt.step()
+    torch.manual_seed(1)
+    again = M.create_mid_fusion_fast(3, O.DictConfig({"precision": {"compute": "fp32"}})).to(cuda_device)
+    start, best = T.resume(again, os.path.join(save_dir, "middle_fusion_fast_checkpoint.pth"))
+    assert start == 3 and best == ck["best_val_acc"]
+    again.train()
+    again.train_step(mel.to(cuda_device), lips.to(cuda_device), lab.to(cuda_device))
+    # one Adam step moves a weight by at most ~lr; both sides start from the same moments, so the step agrees to
+    # a small fraction of lr on average (single elements may sit on a ReLU kink: bounded by lr itself)
+    for (n, p), q in zip(ref.named_parameters(), again.parameters()):
+        d = (p.detach() - q.detach().cpu()).abs()
+        assert d.mean() <= 0.02 * 3e-4 and d.max() <= 1.01 * 3e-4, (n, d.mean(), d.max())
+    back = again.optimizer_state_dict()
+    assert float(back["state"][0]["step"]) == steps_done + 1
+    m_ref = opt.state_dict()["state"][0]["exp_avg"]
+    assert (back["state"][0]["exp_avg"].cpu() - m_ref).abs().max() <= 1e-3 * m_ref.abs().max() + 1e-7
+    for ld in loaders:
+        ld.close()

@@ -1,6 +1,8 @@
 """Host-side train flow (no GPU): config loading, model-name dispatch and its error behaviour mirror the reference's
 train scripts (audio_video/train.py:112-127, video/train.py:189-204, audio/train.py:118-134,
 audio_cues_video/train.py:144-155, config/config.py:33-34)."""
+import os
+
 import pytest
 import torch
 
@@ -58,3 +60,50 @@ def test_default_batch_adapters():
     assert default_batch_to_inputs((a, b, c))[0] == (a, b)
     ins, lab = default_batch_to_inputs({"lip_regions": b, "label": c})
     assert ins == (b,) and lab is c
+
+
+def test_plateau_schedule_follows_torch():
+    """ReduceLROnPlateau drives model.set_lr exactly as torch's scheduler drives the reference's optimizer
+    (video/train.py:213-215 mode max / patience 5; audio_cues_video/train.py:163 mode min / patience 3)."""
+    import torch
+    from multimodal_lipread_b200 import train as T
+
+    class Dummy:
+        def __init__(self, lr):
+            self._opt = {"lr": lr}
+
+        def set_lr(self, lr):
+            self._opt["lr"] = lr
+
+    g = torch.Generator().manual_seed(0)
+    for mode, patience in (("max", 5), ("min", 3), ("min", 0)):
+        metrics = (torch.rand(60, generator=g) * 0.2 + torch.linspace(0.5, 0.6, 60)).tolist()
+        metrics[20:40] = [metrics[19]] * 20                                   # a real plateau
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.Adam([p], lr=1e-3)
+        ref = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode=mode, factor=0.5, patience=patience)
+        ours_model = Dummy(1e-3)
+        ours = T.ReduceLROnPlateau(ours_model, mode=mode, factor=0.5, patience=patience)
+        for m in metrics:
+            ref.step(m)
+            ours.step(m)
+            assert ours_model._opt["lr"] == opt.param_groups[0]["lr"]
+            assert ours.num_bad_epochs == ref.num_bad_epochs and ours.best == ref.best
+        assert ours_model._opt["lr"] < 1e-3
+
+
+def test_log_files_have_the_reference_schema(tmp_path):
+    import csv
+    from multimodal_lipread_b200 import train as T
+    out = str(tmp_path / "metrics")
+    T.init_log_files("m", out)
+    T.log_to_files("m", 1, 2.5, 10.0, 2.25, 12.5, 2.0, 15.0, out)
+    T.init_log_files("m", out)                                               # a second run appends, never truncates
+    T.log_to_files("m", 2, 1.5, 30.0, 1.25, 32.5, 1.0, 35.0, out)
+    T.log_final_results("m", 1.0, 35.0, out)
+    rows = list(csv.reader(open(os.path.join(out, "m_training_log.csv"))))
+    assert rows[0] == ["epoch", "train_loss", "train_acc", "val_loss", "val_acc", "test_loss", "test_acc"]
+    assert rows[1] == ["1", "2.5", "10.0", "2.25", "12.5", "2.0", "15.0"] and len(rows) == 3
+    txt = open(os.path.join(out, "m_training_log.txt")).read()
+    assert txt.startswith("Training Log\n\nEpoch 1\n  Train Loss: 2.5000, Train Acc: 10.00%\n  Val Loss:   2.2500, Val Acc:   12.50%\n")
+    assert txt.endswith("Final Test Loss: 1.0000, Final Test Acc: 35.00%\n")
