@@ -15,6 +15,7 @@ Reference structure reproduced: torchvision MobileNetV3-small `features` + avgpo
 (audio_video/models/middle_fusion_fast.py:15-17,34), nn.LSTM with an out[:, -1] head (:18,35-36), the audio
 conv/fc branch (:8-13,28-30), the classifier (:20-25,38-39), CrossEntropyLoss + Adam (audio_video/train.py:129-130).
 """
+import contextlib
 import os
 
 import torch
@@ -407,6 +408,19 @@ class Plan:
             g.add("lr_dwconv_wgrad", y.grad, x.val, self.flat.g(conv.weight), x.F, x.H, x.W, C, k, s, leaf=True)
             g.add("lr_dwconv_dgrad", y.grad, conv.weight, x.grad, x.F, x.H, x.W, C, k, s)
         return y
+
+    @contextlib.contextmanager
+    def frozen(self, on=True):
+        """Emit a sub-network forward-only inside a training plan: a backbone whose parameters have
+        requires_grad=False and whose input needs no gradient (audio_cues_video/models/early_fusion_mobile.py:100-103,
+        131-133).  BatchNorm keeps its train-mode batch statistics and running-stat updates."""
+        old = self.with_backward
+        if on:
+            self.with_backward = False
+        try:
+            yield
+        finally:
+            self.with_backward = old
 
     def dummy_stats(self):
         if not hasattr(self, "_dummy"):

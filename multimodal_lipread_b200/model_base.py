@@ -310,6 +310,9 @@ class PlanModel(nn.Module):
         """torch.optim.Adam as the reference's train scripts build it; state lives next to the flat parameters."""
         lr = self.DEFAULT_LR if lr is None else lr
         weight_decay = self.DEFAULT_WD if weight_decay is None else weight_decay
+        if weight_decay and any(not p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("weight decay with frozen parameters: torch skips them, the flat Adam kernel would "
+                                      "decay them (the reference's frozen models train with weight_decay 0)")
         self._opt = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         self._graphs.clear()                        # betas / eps / weight decay are launch arguments baked into graphs
         if self._flat is not None:
@@ -337,6 +340,8 @@ class PlanModel(nn.Module):
         if flat is not None and flat.m is not None and float(flat.adam_state[0]) > 0:
             step = float(flat.adam_state[0])
             for i, (p, off) in enumerate(zip(flat.params, flat.offsets)):
+                if not p.requires_grad:
+                    continue                                   # torch keeps no state for parameters without gradients
                 state[i] = {"step": torch.tensor(step), "exp_avg": flat.m[off:off + p.numel()].view(p.shape).clone(),
                             "exp_avg_sq": flat.v[off:off + p.numel()].view(p.shape).clone()}
         group = {"lr": o["lr"], "betas": tuple(o["betas"]), "eps": o["eps"], "weight_decay": o["weight_decay"],
@@ -357,11 +362,14 @@ class PlanModel(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("move the model to its CUDA device (model.to(device)) before loading optimizer state")
         flat = self._ensure_flat(dev)
-        if len(sd["state"]) != len(flat.params):
-            raise ValueError(f"optimizer state has {len(sd['state'])} entries, the model {len(flat.params)} parameters")
+        n_live = sum(p.requires_grad for p in flat.params)
+        if len(sd["state"]) != n_live:
+            raise ValueError(f"optimizer state has {len(sd['state'])} entries, the model {n_live} trainable parameters")
         flat.init_adam(group["lr"])
         steps = set()
         for i, (p, off) in enumerate(zip(flat.params, flat.offsets)):
+            if not p.requires_grad:
+                continue
             st = sd["state"][i]
             flat.m[off:off + p.numel()].view(p.shape).copy_(st["exp_avg"])
             flat.v[off:off + p.numel()].view(p.shape).copy_(st["exp_avg_sq"])

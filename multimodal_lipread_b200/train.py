@@ -105,6 +105,11 @@ def create_acv_model(model_name, num_classes, cue_dim=768, video_cfg=None):
         return M.MultimodalAttentionLate(num_classes, cue_dim=cue_dim, video_cfg=video_cfg, pretrained=False)
     if model_name == "late_fusion_resnet":
         return M.MultimodalAttentionLateResNet(num_classes, cue_dim=cue_dim, video_cfg=video_cfg, pretrained=False)
+    cls = {"early_fusion_mobile": M.MultimodalAttentionEarly, "middle_fusion_mobile": M.MultimodalAttentionMiddle,
+           "early_fusion_resnet": M.MultimodalAttentionEarlyResNet,
+           "middle_fusion_resnet": M.MultimodalAttentionMiddleResNet}.get(model_name)
+    if cls is not None:
+        return cls(num_classes, cue_dim=cue_dim, video_cfg=video_cfg, pretrained=False)
     if model_name in ACV_MODELS:
         _no_plan(model_name)
     raise ValueError(f"Unknown model name: {model_name}")

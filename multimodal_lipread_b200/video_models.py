@@ -10,6 +10,7 @@ including the CNN appearing twice -- `cnn_features.*` and `time_distributed_cnn.
 arithmetic runs through the launch plans of engine.py."""
 import types
 
+import torch
 import torch.nn as nn
 from torchvision.models import mobilenet_v2, resnet18, resnet34
 
@@ -96,6 +97,11 @@ class ResNet2DBiLSTM(PlanModel):
         base.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)      # re-initialised (:90)
         self.cnn_features = nn.Sequential(*list(base.children())[:-2])
         self.global_pool = nn.AdaptiveAvgPool2d((1, 1))
+        # video/models/resnet_lstm.py:98-103 sizes the LSTM input with a dummy pass through the freshly built (train-mode)
+        # CNN: that pass moves every BatchNorm's running statistics once and sets num_batches_tracked to 1.  Reproduced
+        # at construction (host, once) so that state_dicts and eval-mode outputs agree with the reference's from step 0.
+        with torch.no_grad():
+            self.cnn_features(torch.zeros(1, 3, 44, 44))
         cnn_output_dim = 512
         self.time_distributed_cnn = TimeDistributed(nn.Sequential(self.cnn_features, self.global_pool, nn.Flatten()))
         self.bilstm = nn.LSTM(input_size=cnn_output_dim, hidden_size=feature_dim // 2, num_layers=2, bidirectional=True,

@@ -21,6 +21,7 @@ there is no network for the ImageNet checkpoint:
   VGGAudioOracle              audio/models/vgg_model.py:5-58
   VGGLstmAudioOracle          audio/models/vgg_lstm_model.py:5-75
   LSTMResNetOracle            audio/models/lstm_resnet_model.py:5-71
+  AttentionFusionACVOracle    audio_cues_video/models/{middle_fusion_mobile,middle_fusion_resnet,early_fusion_mobile,early_fusion_resnet}.py
   LateFusionAVMobileNetOracle audio_video/models/late_fusion.py:10-93
   MidFusionAVMobileNetOracle  audio_video/models/middle_fusion.py:11-85
   EarlyFusionFastOracle       audio_video/models/early_fusion_fast.py:6-76
@@ -171,6 +172,10 @@ class ResNet2DBiLSTMOracle(nn.Module):
         base.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
         self.cnn_features = nn.Sequential(*list(base.children())[:-2])
         self.global_pool = nn.AdaptiveAvgPool2d((1, 1))
+        # resnet_lstm.py:98-103: the LSTM input size is measured with a dummy pass through the freshly built CNN, which
+        # is in train mode -- every BatchNorm's running statistics move once and num_batches_tracked becomes 1
+        with torch.no_grad():
+            self.global_pool(self.cnn_features(torch.zeros(1, 3, 44, 44)))
         self.time_distributed_cnn = _TimeDistributed(nn.Sequential(self.cnn_features, self.global_pool, nn.Flatten()))
         self.bilstm = nn.LSTM(512, feature_dim // 2, num_layers=2, bidirectional=True, batch_first=True,
                               dropout=dropout if dropout > 0 else 0)
@@ -293,6 +298,117 @@ class LateFusionResNetOracle(LateFusionMobileOracle):
         self.vfc = nn.Linear(vdim, num_classes)
         self.cfc = nn.Linear(256, num_classes)
         self.attn = self._Attn(num_classes)
+
+
+class _SafeCheckpoint(nn.Module):
+    """early_fusion_mobile.py:62-72.  Recomputation never changes values, and it does not engage at all for a frozen
+    backbone whose input needs no gradient -- the only way the reference uses it."""
+
+    def __init__(self, module, enabled=True):
+        super().__init__()
+        self.module = module
+        self.enabled = bool(enabled)
+
+    def forward(self, x):
+        return self.module(x)
+
+
+class _TimeDistributedChunked(nn.Module):
+    """early_fusion_mobile.py:31-56: chunk_size time steps of every clip per CNN call."""
+
+    def __init__(self, module, chunk_size=4):
+        super().__init__()
+        self.module = module
+        self.chunk_size = int(chunk_size)
+
+    def forward(self, x):
+        B, C, T, H, W = x.shape
+        outs = []
+        for i in range(0, T, self.chunk_size):
+            frames = x[:, :, i:min(i + self.chunk_size, T)].permute(0, 2, 1, 3, 4).reshape(-1, C, H, W)
+            out = self.module(frames)
+            outs.append(out.view(B, out.size(0) // B, -1))
+        return torch.cat(outs, dim=1)
+
+
+class AttentionFusionACVOracle(nn.Module):
+    """The four early / middle audio+cue+video attention models of audio_cues_video/models/:
+      kind "middle_mobile"  middle_fusion_mobile.py:84-110    trainable encoders, 2-layer BiLSTM, cls with BatchNorm1d
+      kind "middle_resnet"  middle_fusion_resnet.py:164-191   frozen ResNet-18 encoders, chunked TimeDistributed
+      kind "early_mobile"   early_fusion_mobile.py:179-213    frozen audio ResNet-18 + MobileNetV2 features, cp, classifier
+      kind "early_resnet"   early_fusion_resnet.py:158-191    the same with a frozen ResNet-18 video trunk"""
+
+    def __init__(self, kind, num_classes, cue_dim=768, vdim=256, lstm_dropout=0.3, cue_dropout=0.3, head_dropout=0.4):
+        super().__init__()
+        self.kind = kind
+        frozen = kind != "middle_mobile"
+        early = kind.startswith("early")
+        # audio
+        net = resnet18(weights=None)
+        net.conv1 = nn.Conv2d(1, 64, 7, 2, 3, bias=False)
+        net.fc = nn.Identity()
+        self.audio = nn.Module()
+        if frozen:
+            for p in net.parameters():
+                p.requires_grad = False
+            setattr(self.audio, "encoder" if early else "enc", _SafeCheckpoint(net))
+        else:
+            self.audio.enc = net
+        # cue
+        self.cue = nn.Module()
+        if early:
+            self.cue.net = nn.Sequential(nn.Linear(cue_dim, 256), nn.BatchNorm1d(256), nn.ReLU(), nn.Dropout(cue_dropout),
+                                         nn.Linear(256, 256), nn.ReLU())
+        else:
+            self.cue.net = nn.Sequential(nn.Linear(cue_dim, 256), nn.BatchNorm1d(256), nn.ReLU(), nn.Linear(256, 256))
+        # video
+        self.video = nn.Module()
+        if kind.endswith("mobile"):
+            base = mobilenet_v2(weights=None)
+            base.classifier = nn.Identity()
+            seq = nn.Sequential(base.features, nn.AdaptiveAvgPool2d(1), nn.Flatten())
+            if frozen:
+                for p in base.features.parameters():
+                    p.requires_grad = False
+            width = 1280
+        else:
+            base = resnet18(weights=None)
+            base.fc = nn.Identity()
+            for p in base.parameters():
+                p.requires_grad = False
+            seq = nn.Sequential(base)
+            width = 512
+        if frozen:
+            self.video.cnn = _SafeCheckpoint(seq)
+            self.video.td = _TimeDistributedChunked(self.video.cnn, 4)
+            self.video.lstm = nn.LSTM(width, vdim // 2, num_layers=1, bidirectional=True, batch_first=True, dropout=0.0)
+        else:
+            self.video.cnn = seq
+            self.video.td = _TimeDistributed(seq)
+            self.video.lstm = nn.LSTM(width, vdim // 2, num_layers=2, bidirectional=True, batch_first=True, dropout=lstm_dropout)
+        self.ap = nn.Linear(512, 256)
+        self.vp = nn.Linear(vdim, 256)
+        if early:
+            self.cp = nn.Linear(256, 256)
+        self.attn = LateFusionMobileOracle._Attn(256)
+        if early:
+            self.classifier = nn.Sequential(nn.Linear(256, 256), nn.ReLU(), nn.Dropout(head_dropout), nn.Linear(256, num_classes))
+        elif kind == "middle_mobile":
+            self.cls = nn.Sequential(nn.Linear(256, 512), nn.BatchNorm1d(512), nn.ReLU(), nn.Dropout(head_dropout),
+                                     nn.Linear(512, num_classes))
+        else:
+            self.cls = nn.Sequential(nn.Linear(256, 512), nn.ReLU(), nn.Dropout(head_dropout), nn.Linear(512, num_classes))
+
+    def forward(self, mel, cue, lip):
+        enc = getattr(self.audio, "enc", None) or self.audio.encoder
+        a = self.ap(enc(mel.unsqueeze(1)))
+        c = self.cue.net(cue)
+        if hasattr(self, "cp"):
+            c = self.cp(c)
+        seq, _ = self.video.lstm(self.video.td(lip))
+        v = self.vp(seq[:, -1, :])
+        fused, _ = self.attn([a, c, v])
+        return (self.classifier if hasattr(self, "classifier") else self.cls)(fused)
 
 
 class MobileNetLSTMOracle(nn.Module):

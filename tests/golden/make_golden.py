@@ -158,12 +158,17 @@ def golden_models():
         loss.backward()
         out[f"{name}_logits"] = logits.detach().numpy()
         out[f"{name}_loss"] = np.array(loss.item())
-        out[f"{name}_grad_norm"] = np.array([p.grad.double().norm().item() for _, p in model.named_parameters()])
+        out[f"{name}_grad_norm"] = np.array([0.0 if p.grad is None else p.grad.double().norm().item()
+                                             for _, p in model.named_parameters()])
+        out[f"{name}_frozen"] = np.array([p.grad is None for _, p in model.named_parameters()])
         out[f"{name}_wsum_before"] = np.array([p.detach().double().sum().item() for _, p in model.named_parameters()])
         opt.step()
         out[f"{name}_wsum_after"] = np.array([p.detach().double().sum().item() for _, p in model.named_parameters()])
         out[f"{name}_param_names"] = np.array([n for n, _ in model.named_parameters()])
         out[f"{name}_state_keys"] = np.array(list(model.state_dict().keys()))
+        sd = model.state_dict()
+        out[f"{name}_nbt"] = np.array([int(v) for k, v in sd.items() if k.endswith("num_batches_tracked")])
+        out[f"{name}_running_mean_sum"] = np.array([v.double().sum().item() for k, v in sd.items() if k.endswith("running_mean")])
         out[f"{name}_B"], out[f"{name}_T"], out[f"{name}_size"] = np.array(B), np.array(T), np.array(size)
         print(name, "loss", loss.item(), "n_params", sum(p.numel() for p in model.parameters()))
 
@@ -214,6 +219,21 @@ def golden_models():
     model = mod.MultimodalAttentionLateResNet(C, cue_dim=768, video_cfg=None, pretrained=False)
     model.video.lstm.dropout = 0.0
     record("acv_late_fusion_resnet", model, (mel, synthetic.make_cues(B), video), labels, 1e-5, 0.0, B, T, size)
+    # audio_cues_video early / middle attention fusion; the early and middle-resnet variants freeze their backbones and
+    # feed the CNN 4 time steps at a time (T = 6: one chunk of 4 and one of 2)
+    cue = synthetic.make_cues(B)
+    for key, module, cls_name in (("middle_fusion_mobile", "models.middle_fusion_mobile", "MultimodalAttentionMiddle"),
+                                  ("middle_fusion_resnet", "models.middle_fusion_resnet", "MultimodalAttentionMiddleResNet"),
+                                  ("early_fusion_mobile", "models.early_fusion_mobile", "MultimodalAttentionEarly"),
+                                  ("early_fusion_resnet", "models.early_fusion_resnet", "MultimodalAttentionEarlyResNet")):
+        mod = load_ref("audio_cues_video", module)
+        torch.manual_seed(0)
+        model = getattr(mod, cls_name)(C, cue_dim=768, video_cfg=None, pretrained=False)
+        for m_ in model.modules():
+            if isinstance(m_, torch.nn.Dropout):
+                m_.p = 0.0
+        model.video.lstm.dropout = 0.0
+        record("acv_" + key, model, (mel, cue, video), labels, 1e-4, 0.0, B, T, size)
     # video vgg_lstm, audio resnet_lstm (dropout is a constructor argument) and audio vgg (version 11)
     B, T, size, C = 3, 6, 44, 40
     mod = load_ref("video", "models.vgg_lstm")

@@ -28,11 +28,13 @@ ZERO_GRAD = ZERO_GRAD_BN
 def _set_zero_grad(name):
     """early_fusion_fast's audio convs have no BatchNorm behind them: their bias gradients are real."""
     global ZERO_GRAD
-    no_bn = ("early_fusion_fast", "late_fusion_fast", "early_fusion_mobilenet", "early_fusion_resnet", "middle_fusion_mobilenet")
+    no_bn = ("early_fusion_fast", "late_fusion_fast", "early_fusion_mobilenet", "early_fusion_resnet", "middle_fusion_mobilenet",
+             "acv_early_fusion_mobile", "acv_early_fusion_resnet")
     # (those models' `classifier.0` is a plain Linear; their audio-encoder conv biases are listed by full name)
     ZERO_GRAD = tuple(n for n in ZERO_GRAD_BN if not (n == "classifier.0.bias" and name in no_bn))
     if name in ("early_fusion_fast", "late_fusion_fast"):
         ZERO_GRAD = ()
+ACV_ATTENTION = ("acv_middle_fusion_mobile", "acv_middle_fusion_resnet", "acv_early_fusion_mobile", "acv_early_fusion_resnet")
 NO_DROP = {"video.lstm_dropout": 0.0, "model.classifier_dropout": 0.0, "model.dropout": 0.0}
 GRAD_FLOOR = 1e-7
 
@@ -84,7 +86,7 @@ def _grad_check(named_ours, gref, tol, ref=None, ref_inputs=None, labels=None):
     for p in r64.parameters():
         p.grad = None
     torch.nn.functional.cross_entropy(r64(*[t.double() for t in ref_inputs]), labels).backward()
-    g64 = {n: p.grad for n, p in r64.named_parameters()}
+    g64 = {n: (p.grad if p.grad is not None else torch.zeros_like(p)) for n, p in r64.named_parameters()}
     ours64 = _errs(named_ours, g64, tol)
     ref64 = _errs([(n, gref[n]) for n, _ in named_ours], g64, tol)
     n_ours, n_ref = sum(e > tol for e in ours64.values()), sum(e > tol for e in ref64.values())
@@ -158,6 +160,8 @@ def _case(name, precision="fp32"):
         ref = O.EarlyFusionFastOracle(C)
     elif name == "late_fusion_fast":
         ref = O.LateFusionFastOracle(C)
+    elif name in ACV_ATTENTION:
+        ref = O.AttentionFusionACVOracle("_".join(name.split("_")[1::2]), C, lstm_dropout=0.0, cue_dropout=0.0, head_dropout=0.0)
     torch.manual_seed(0)
     if name == "early_fusion_mobilenet":
         ours = AV.EarlyFusionAVMobileNet(C, cfg, precision=precision)
@@ -193,6 +197,14 @@ def _case(name, precision="fp32"):
         ours = AV.EarlyFusionFast(C, cfg, precision=precision)
     elif name == "late_fusion_fast":
         ours = AV.LateFusionFast(C, cfg, precision=precision)
+    elif name == "acv_middle_fusion_mobile":
+        ours = ACV.MultimodalAttentionMiddle(C, lstm_dropout=0.0, head_dropout=0.0, precision=precision)
+    elif name == "acv_middle_fusion_resnet":
+        ours = ACV.MultimodalAttentionMiddleResNet(C, head_dropout=0.0, precision=precision)
+    elif name == "acv_early_fusion_mobile":
+        ours = ACV.MultimodalAttentionEarly(C, cue_dropout=0.0, head_dropout=0.0, precision=precision)
+    elif name == "acv_early_fusion_resnet":
+        ours = ACV.MultimodalAttentionEarlyResNet(C, cue_dropout=0.0, head_dropout=0.0, precision=precision)
     sd_ref, sd = ref.state_dict(), ours.state_dict()
     assert list(sd_ref.keys()) == list(sd.keys())
     for k in sd:
@@ -206,7 +218,7 @@ def _inputs_for(name, mel, lips):
         return (mel, video), (mel.cuda(), lips.cuda())
     if name in ("video_resnet_lstm", "video_mobilenet_lstm", "video_vgg_lstm", "video_cnn"):
         return (video,), (lips.cuda(),)
-    if name in ("acv_late_fusion_mobile", "acv_late_fusion_resnet"):
+    if name.startswith("acv_"):
         from multimodal_lipread_b200 import synthetic
         cue = synthetic.make_cues(mel.shape[0])
         return (mel, cue, video), (mel.cuda(), cue.cuda(), lips.cuda())
@@ -235,6 +247,10 @@ def _inputs_for(name, mel, lips):
     ("middle_fusion_mobilenet", 3, 8, 44),
     ("early_fusion_fast", 3, 8, 44),
     ("late_fusion_fast", 3, 8, 44),
+    ("acv_middle_fusion_mobile", 3, 6, 44),
+    ("acv_middle_fusion_resnet", 3, 6, 44),
+    ("acv_early_fusion_mobile", 3, 6, 44),
+    ("acv_early_fusion_resnet", 3, 7, 44),
 ])
 def test_train_step_matches_oracle(cuda_device, name, B, T, size):
     ref, ours, C = _case(name)
@@ -247,7 +263,9 @@ def test_train_step_matches_oracle(cuda_device, name, B, T, size):
     logits_ref = ref(*ref_in)
     loss_ref = torch.nn.functional.cross_entropy(logits_ref, labels)
     loss_ref.backward()
-    gref = {n: p.grad.clone() for n, p in ref.named_parameters()}
+    gref = {n: (p.grad.clone() if p.grad is not None else torch.zeros_like(p)) for n, p in ref.named_parameters()}
+    frozen = [n for n, p in ref.named_parameters() if p.grad is None]
+    assert frozen == [n for n, p in ours.named_parameters() if not p.requires_grad]
     opt.step()
 
     ours.configure_optimizer()
@@ -276,7 +294,7 @@ def test_train_step_matches_oracle(cuda_device, name, B, T, size):
         if k.endswith("running_mean") or k.endswith("running_var"):
             assert (sd[k].cpu() - sd_ref[k]).abs().max().item() <= 2e-4 * sd_ref[k].abs().max().item() + 1e-6, k
         if k.endswith("num_batches_tracked"):
-            assert int(sd[k]) == int(sd_ref[k]) == 1, k
+            assert int(sd[k]) == int(sd_ref[k]) >= 1, k            # > 1 under the chunked TimeDistributed
     # eval mode (running statistics) after the step
     ref.eval(); ours.eval()
     fwd_in = tuple(t if t.dtype != torch.uint8 else lips_u8_to_model_input(t.cpu()).cuda() for t in our_in)
@@ -288,7 +306,8 @@ def test_train_step_matches_oracle(cuda_device, name, B, T, size):
 
 @pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
                                   "acv_late_fusion_resnet", "video_vgg_lstm", "video_cnn", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm", "audio_lstm_resnet",
-                                  "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast"])
+                                  "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast",
+                                  "acv_middle_fusion_mobile", "acv_middle_fusion_resnet", "acv_early_fusion_mobile", "acv_early_fusion_resnet"])
 def test_golden_vectors_of_the_reference(cuda_device, golden_dir, name):
     """Outputs recorded from the reference's own modules (tests/golden/make_golden.py, dropout set to 0)."""
     mg = np.load(os.path.join(golden_dir, "models_golden.npz"))
@@ -312,7 +331,11 @@ def test_golden_vectors_of_the_reference(cuda_device, golden_dir, name):
     close = np.isclose(gn, ref_gn, rtol=3e-3, atol=3e-6)
     # MobileNetV2 at 18 frames: 41 % of the REFERENCE's own fp32 gradient tensors differ from its fp64 ones by
     # more than 3e-3 (scratch/cond_check4.py); the other models are well conditioned
-    frac = 0.5 if name in ("acv_late_fusion_mobile", "video_mobilenet_lstm") else 0.06
+    frac = 0.5 if name in ("acv_late_fusion_mobile", "video_mobilenet_lstm", "acv_middle_fusion_mobile") else 0.06
+    sd = ours.state_dict()
+    assert [int(v) for k, v in sd.items() if k.endswith("num_batches_tracked")] == mg[f"{name}_nbt"].tolist()
+    np.testing.assert_allclose([v.double().sum().item() for k, v in sd.items() if k.endswith("running_mean")],
+                               mg[f"{name}_running_mean_sum"], rtol=2e-3, atol=2e-4)
     assert close.sum() >= len(gn) - max(2, int(frac * len(gn))), (gn[~close], ref_gn[~close])
     np.testing.assert_allclose(gn, ref_gn, rtol=0.2, atol=3e-6)
 

@@ -115,7 +115,8 @@ def models_golden(golden_dir):
 
 @pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
                                   "acv_late_fusion_resnet", "video_vgg_lstm", "video_cnn", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm", "audio_lstm_resnet",
-                                  "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast"])
+                                  "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast",
+                                  "acv_middle_fusion_mobile", "acv_middle_fusion_resnet", "acv_early_fusion_mobile", "acv_early_fusion_resnet"])
 def test_model_oracles_match_reference(models_golden, name):
     from oracle import av_models as O
     g = models_golden
@@ -152,6 +153,9 @@ def test_model_oracles_match_reference(models_golden, name):
         model, lr, wd = O.EarlyFusionFastOracle(C), 3e-4, 0.0
     elif name == "late_fusion_fast":
         model, lr, wd = O.LateFusionFastOracle(C), 3e-4, 0.0
+    elif name in ("acv_middle_fusion_mobile", "acv_middle_fusion_resnet", "acv_early_fusion_mobile", "acv_early_fusion_resnet"):
+        kind = "_".join(name.split("_")[1::2])                       # acv_middle_fusion_mobile -> middle_mobile
+        model, lr, wd = O.AttentionFusionACVOracle(kind, C, lstm_dropout=0.0, cue_dropout=0.0, head_dropout=0.0), 1e-4, 0.0
     else:
         model, lr, wd = O.AudioResNetOracle(C, dropout_rate=0.0), 5e-4, 1e-4
     model.train()
@@ -167,11 +171,18 @@ def test_model_oracles_match_reference(models_golden, name):
               "audio_resnet": (mel,), "audio_resnet_lstm": (mel,), "audio_vgg": (mel,), "audio_vgg_lstm": (mel,), "audio_lstm_resnet": (mel,),
               "acv_late_fusion_mobile": (mel, synthetic.make_cues(B), video),
               "acv_late_fusion_resnet": (mel, synthetic.make_cues(B), video)}.get(name, (mel, video))
+    if name.startswith("acv_"):
+        inputs = (mel, synthetic.make_cues(B), video)
     opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
     logits, loss = O.train_step_generic(model, opt, inputs, labels)
     np.testing.assert_allclose(logits.numpy(), g[f"{name}_logits"], rtol=1e-5, atol=1e-6)
     assert abs(loss - float(g[f"{name}_loss"])) < 1e-6
-    gnorm = np.array([p.grad.double().norm().item() for p in model.parameters()])
+    gnorm = np.array([0.0 if p.grad is None else p.grad.double().norm().item() for p in model.parameters()])
     np.testing.assert_allclose(gnorm, g[f"{name}_grad_norm"], rtol=1e-4, atol=1e-7)
+    assert [p.grad is None for p in model.parameters()] == g[f"{name}_frozen"].tolist()      # frozen backbones stay frozen
+    sd = model.state_dict()
+    assert [int(v) for k, v in sd.items() if k.endswith("num_batches_tracked")] == g[f"{name}_nbt"].tolist()
+    np.testing.assert_allclose([v.double().sum().item() for k, v in sd.items() if k.endswith("running_mean")],
+                               g[f"{name}_running_mean_sum"], rtol=1e-4, atol=1e-5)
     wsum1 = np.array([p.detach().double().sum().item() for p in model.parameters()])
     np.testing.assert_allclose(wsum1, g[f"{name}_wsum_after"], rtol=1e-5, atol=1e-4)

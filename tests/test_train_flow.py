@@ -41,6 +41,16 @@ def test_model_name_dispatch_and_errors():
     assert type(T.create_audio_model("vgg", 8, version=11)).__name__ == "VGGAudioClassifier"
     assert type(T.create_audio_model("vgg_lstm", 8, version=11)).__name__ == "VGGWithLSTMClassifier"
     assert type(T.create_audio_model("lstm_resnet", 8, input_size=117)).__name__ == "LSTMResNet"
+    for name in T.ACV_MODELS:                            # every audio_cues_video name (train.py:144-155) has a plan
+        m = T.create_acv_model(name, 40)
+        assert m.num_classes == 40 and m.INPUTS == ("audio", "cue", "video")
+    frozen = T.create_acv_model("early_fusion_mobile", 40)
+    assert not any(p.requires_grad for p in frozen.audio.parameters())
+    assert not any(p.requires_grad for p in frozen.video.cnn.parameters()) and all(p.requires_grad for p in frozen.video.lstm.parameters())
+    with pytest.raises(NotImplementedError, match="frozen"):
+        frozen.configure_optimizer(lr=1e-4, weight_decay=1e-5)
+    with pytest.raises(ValueError, match="Unknown model name"):
+        T.create_acv_model("not_a_model", 40)
     for name in ("shufflenet_lstm", "resnet_trans"):
         with pytest.raises(NotImplementedError):
             T.create_video_model(name, 40, cfg)          # a reference name without a plan fails loudly
