@@ -249,9 +249,26 @@ int lr_audio_conv_fwd(const float* x, const float* w, const float* bias, float* 
 int lr_audio_conv_bwd(const float* x, const float* dA, long long lda, const unsigned char* arg, float* dw, float* db,
                       int B, int H, int W, lr_stream_t stream);
 
+/* nn.MultiheadAttention(embed_dim E, heads, batch_first) over the T time steps of each clip, around its in- and
+ * out-projections (two lr_gemm calls): qkv is the packed in-projection [B*T, 3E] (row stride ld; q | k | v, head h in
+ * columns h*d .. (h+1)*d of each section, d = E / heads), P [B, heads, T, T] the attention weights (saved for the
+ * backward), O [B*T, E] the concatenated heads.  T <= 64, d <= 128.
+ *   scores_fwd: P = softmax((q / sqrt(d)) k^T)            apply_fwd: O = P v     (nn.Dropout on P sits between them)
+ *   apply_bwd:  dP = dO v^T, dqkv[v section] = P^T dO     scores_bwd: dqkv[q | k sections] through the softmax
+ * replaces: video/models/resnet_attn.py:23-35,103 (TemporalAttention), the self-attention of
+ * nn.TransformerEncoderLayer (video/models/resnet_trans.py:96-103). */
+int lr_mha_scores_fwd(const float* qkv, long long ld, float* P, int B, int T, int E, int heads, lr_stream_t stream);
+int lr_mha_apply_fwd(const float* P, const float* qkv, long long ld, float* O, int B, int T, int E, int heads,
+                     lr_stream_t stream);
+int lr_mha_apply_bwd(const float* dO, const float* P, const float* qkv, long long ld, float* dP, float* dqkv, int B,
+                     int T, int E, int heads, lr_stream_t stream);
+int lr_mha_scores_bwd(const float* P, const float* dP, const float* qkv, long long ld, float* dqkv, int B, int T, int E,
+                      int heads, lr_stream_t stream);
+
 /* AttentionFusion of the late triple-fusion model (audio_cues_video/models/late_fusion_mobile.py:6-19) around its
  * attn MLP (two lr_gemm calls): weights = softmax(scores[B,S], dim=1); fused[b,:] = sum_s weights[b,s] stacked[b,s,:].
- * Backward: dstacked = weights * dfused (the MLP's own backward then accumulates onto it), dscores through the softmax. */
+ * Backward: dstacked = weights * dfused (the MLP's own backward then accumulates onto it), dscores through the softmax.
+ * Also the additive attention pooling over S time steps of audio/models/lstm_resnet_attn_model.py:5-14.  S <= 32. */
 int lr_attn_fuse_fwd(const float* stacked, const float* scores, float* weights, float* fused, int B, int S, int C,
                      lr_stream_t stream);
 int lr_attn_fuse_bwd(const float* stacked, const float* weights, const float* dfused, float* dstacked, float* dscores,

@@ -5,11 +5,13 @@
   VGGAudioClassifier   audio/models/vgg_model.py:5-58           (model.name == "vgg")
   VGGWithLSTMClassifier audio/models/vgg_lstm_model.py:5-75     (model.name == "vgg_lstm")
   LSTMResNet           audio/models/lstm_resnet_model.py:5-71   (model.name == "lstm_resnet")
+  DeepAudioNetWithAttention audio/models/lstm_resnet_attn_model.py:17-88 (model.name == "lstm_resnet_attn")
 
 forward(spec (B,80,117) f32 log-mel) -> (B, num_classes); with a raw (B,20000) waveform the fused log-mel kernel
 runs first.  Sub-modules are parameter containers (reference names / construction order / state_dict keys)."""
 import types
 
+import torch
 import torch.nn as nn
 from torchvision.models import resnet18, vgg11_bn, vgg13_bn, vgg16_bn, vgg19_bn
 
@@ -227,40 +229,48 @@ class VGGWithLSTMClassifier(PlanModel):
         self.classifier = nn.Sequential(*layers)
 
 
+def lstm_resnet_front(plan, m):
+    """mel rows -> initial_bilstm (length-1 sequences) -> 1-channel image -> ResNet-18 -> fc (+BN1d) -> ReLU -> Dropout:
+    the part audio/models/lstm_resnet_model.py:39-60, lstm_resnet_attn_model.py:61-75 and lstm_resnet_trans_model.py
+    share.  Returns (h, dh, width)."""
+    self, B, wb = plan, plan.B, plan.with_backward
+    mel = self.audio_input()
+    I = m.initial_bilstm.input_size
+    if I != N_FRAMES_OUT:
+        raise ValueError(f"LSTMResNet input_size {I} != {N_FRAMES_OUT} mel frames")
+    # x.view(B*80, 117).unsqueeze(1): every mel row is a length-1 sequence through the 2-layer BiLSTM(117 -> 64)
+    Bq = B * N_MELS
+    D0 = 2 * m.initial_bilstm.hidden_size
+    img = self.alloc(Bq * D0)
+    dimg = self.alloc(Bq * D0) if wb else None
+    self.bilstm_last(mel, None, I, Bq, 1, m.initial_bilstm, img, D0, dimg if wb else 0)
+    # .view(B, 1, 80, 128): a computed 1-channel image; the stem needs its input gradient
+    x = engine.T2.of(B, N_MELS, D0, 1, img, dimg)
+    last = self.resnet_features(m.resnet, None, x=x)
+    feat, dfeat = self.avgpool(last)
+    head = list(m.fc)
+    Dh = head[0].out_features
+    if isinstance(head[1], nn.BatchNorm1d):
+        h, dh = self.linear_bn_act(feat, dfeat, B, head[0], head[1], ACT_RELU)
+        drop = head[3]
+    else:
+        h = self.alloc(B * Dh)
+        dh = self.alloc(B * Dh) if wb else None
+        self.linear(feat, head[0].in_features, B, head[0].weight, head[0].bias, h, Dh, act=ACT_RELU)
+        if wb:
+            g = self.bgroup()
+            g.add("lr_act_bwd", dh, h, B * Dh, ACT_RELU)
+            self.linear_bwd(g, feat, head[0].in_features, B, head[0].weight, head[0].bias, dh, Dh, dx=dfeat,
+                            ldx=head[0].in_features)
+        drop = head[2]
+    h, dh = self.dropout(h, dh, B * Dh, drop.p)
+    return h, dh, Dh
+
+
 class LstmResNetPlan(ModelPlan):
     def build(self, m, spec):
         B, wb = self.B, self.with_backward
-        mel = self.audio_input()
-        I = m.initial_bilstm.input_size
-        if I != N_FRAMES_OUT:
-            raise ValueError(f"LSTMResNet input_size {I} != {N_FRAMES_OUT} mel frames")
-        # x.view(B*80, 117).unsqueeze(1): every mel row is a length-1 sequence through the 2-layer BiLSTM(117 -> 64)
-        Bq = B * N_MELS
-        D0 = 2 * m.initial_bilstm.hidden_size
-        img = self.alloc(Bq * D0)
-        dimg = self.alloc(Bq * D0) if wb else None
-        self.bilstm_last(mel, None, I, Bq, 1, m.initial_bilstm, img, D0, dimg if wb else 0)
-        # .view(B, 1, 80, 128): a computed 1-channel image; the stem needs its input gradient
-        x = engine.T2.of(B, N_MELS, D0, 1, img, dimg)
-        last = self.resnet_features(m.resnet, None, x=x)
-        feat, dfeat = self.avgpool(last)
-        head = list(m.fc)
-        if isinstance(head[1], nn.BatchNorm1d):
-            h, dh = self.linear_bn_act(feat, dfeat, B, head[0], head[1], ACT_RELU)
-            drop = head[3]
-        else:
-            Dh = head[0].out_features
-            h = self.alloc(B * Dh)
-            dh = self.alloc(B * Dh) if wb else None
-            self.linear(feat, head[0].in_features, B, head[0].weight, head[0].bias, h, Dh, act=ACT_RELU)
-            if wb:
-                g = self.bgroup()
-                g.add("lr_act_bwd", dh, h, B * Dh, ACT_RELU)
-                self.linear_bwd(g, feat, head[0].in_features, B, head[0].weight, head[0].bias, dh, Dh, dx=dfeat,
-                                ldx=head[0].in_features)
-            drop = head[2]
-        Dh = head[0].out_features
-        h, dh = self.dropout(h, dh, B * Dh, drop.p)
+        h, dh, Dh = lstm_resnet_front(self, m)
         D1 = 2 * m.final_bilstm.hidden_size
         seq = self.alloc(B * D1)
         dseq = self.alloc(B * D1) if wb else None
@@ -271,6 +281,45 @@ class LstmResNetPlan(ModelPlan):
         self.linear(seq, D1, B, m.classifier.weight, m.classifier.bias, logits, C)
         if wb:
             self.linear_bwd(self.bgroup(), seq, D1, B, m.classifier.weight, m.classifier.bias, dlogits, C, dx=dseq, ldx=D1)
+        self.set_logits(logits, dlogits)
+
+
+class LstmResNetAttnPlan(ModelPlan):
+    """audio/models/lstm_resnet_attn_model.py:61-88: the projection repeated over 10 steps, a full 2-layer BiLSTM over
+    them, additive attention pooling (Linear(256, 1) -> softmax over time -> weighted sum), classifier."""
+    STEPS = 10
+
+    def build(self, m, spec):
+        B, wb, T = self.B, self.with_backward, self.STEPS
+        h, dh, Dh = lstm_resnet_front(self, m)
+        # fc_out.unsqueeze(1).repeat(1, 10, 1)
+        xs = self.alloc(B * T * Dh)
+        dxs = self.alloc(B * T * Dh) if wb else None
+        for t in range(T):
+            self.fwd.add("lr_copy2d", xs.data_ptr() + 4 * t * Dh, T * Dh, h, Dh, B, Dh)
+        if wb:
+            ones = torch.ones(B * T * Dh, dtype=torch.float32, device=self.dev)
+            self.bufs.append(ones)
+            self.bgroup().add("lr_frame_reduce", dxs, ones, dh, B, T, Dh, 1)          # dh[b] = sum_t dxs[b, t]
+        seq, dseq = self.bilstm_seq(xs, dxs, Dh, B, T, m.final_bilstm)
+        D1 = 2 * m.final_bilstm.hidden_size
+        att = m.attention.attn
+        scores, weights = self.alloc(B * T), self.alloc(B * T)
+        pooled = self.alloc(B * D1)
+        dpooled = self.alloc(B * D1) if wb else None
+        self.linear(seq, D1, B * T, att.weight, att.bias, scores, 1)
+        self.fwd.add("lr_attn_fuse_fwd", seq, scores, weights, pooled, B, T, D1)
+        if wb:
+            dscores = self.alloc(B * T)
+            g = self.bgroup()
+            g.add("lr_attn_fuse_bwd", seq, weights, dpooled, dseq, dscores, B, T, D1)
+            self.linear_bwd(g, seq, D1, B * T, att.weight, att.bias, dscores, 1, dx=dseq, ldx=D1, dx_residual=dseq, ldr=D1)
+        C = self.num_classes
+        logits = self.alloc(B * C)
+        dlogits = self.alloc(B * C) if wb else None
+        self.linear(pooled, D1, B, m.classifier.weight, m.classifier.bias, logits, C)
+        if wb:
+            self.linear_bwd(self.bgroup(), pooled, D1, B, m.classifier.weight, m.classifier.bias, dlogits, C, dx=dpooled, ldx=D1)
         self.set_logits(logits, dlogits)
 
 
@@ -298,7 +347,27 @@ class LSTMResNet(PlanModel):
         layers.extend([nn.ReLU(), nn.Dropout(dropout_rate)])
         self.fc = nn.Sequential(*layers)
         self.final_bilstm = nn.LSTM(input_size=256, hidden_size=128, num_layers=2, bidirectional=True, batch_first=True)
+        self._tail(num_classes)
+
+    def _tail(self, num_classes):
         self.classifier = nn.Linear(2 * 128, num_classes)
+
+
+class Attention(nn.Module):
+    """lstm_resnet_attn_model.py:5-14 (parameters only)."""
+
+    def __init__(self, input_dim):
+        super().__init__()
+        self.attn = nn.Linear(input_dim, 1)
+
+
+class DeepAudioNetWithAttention(LSTMResNet):
+    """audio/models/lstm_resnet_attn_model.py:17-88 (model.name == "lstm_resnet_attn")."""
+    PLAN = LstmResNetAttnPlan
+
+    def _tail(self, num_classes):                            # construction order of the reference (:54-58)
+        self.attention = Attention(input_dim=256)
+        self.classifier = nn.Linear(256, num_classes)
 
 
 def get_model(num_classes, input_size, model_name, version=None):
@@ -313,4 +382,6 @@ def get_model(num_classes, input_size, model_name, version=None):
         return VGGWithLSTMClassifier(num_classes=num_classes, version=version or 11)
     if model_name == "lstm_resnet":
         return LSTMResNet(num_classes=num_classes, input_size=input_size)
+    if model_name == "lstm_resnet_attn":
+        return DeepAudioNetWithAttention(num_classes=num_classes, input_size=input_size)
     raise ValueError(f"Invalid model name: {model_name}")

@@ -7,7 +7,7 @@
 namespace fu {
 
 constexpr int TH = 128;
-constexpr int SMAX = 8;
+constexpr int SMAX = 32;   // modalities (3) or pooled time steps (10, audio/models/lstm_resnet_attn_model.py:78-84)
 
 __global__ void __launch_bounds__(TH)
 attn_fuse_fwd_kernel(const float* __restrict__ stacked, const float* __restrict__ scores, float* __restrict__ w,
@@ -67,7 +67,7 @@ attn_fuse_bwd_kernel(const float* __restrict__ stacked, const float* __restrict_
 
 extern "C" int lr_attn_fuse_fwd(const float* stacked, const float* scores, float* weights, float* fused, int B, int S,
                                 int C, lr_stream_t stream) {
-    LR_CHECK_ARG(B >= 0 && S > 0 && S <= fu::SMAX && C > 0, "lr_attn_fuse_fwd: need 1 <= S <= 8, C > 0");
+    LR_CHECK_ARG(B >= 0 && S > 0 && S <= fu::SMAX && C > 0, "lr_attn_fuse_fwd: need 1 <= S <= 32, C > 0");
     if (B == 0) return LR_OK;
     LR_CHECK_ARG(stacked && scores && weights && fused, "lr_attn_fuse_fwd: null pointer");
     fu::attn_fuse_fwd_kernel<<<B, fu::TH, 0, stream>>>(stacked, scores, weights, fused, S, C);
@@ -78,7 +78,7 @@ extern "C" int lr_attn_fuse_fwd(const float* stacked, const float* scores, float
 
 extern "C" int lr_attn_fuse_bwd(const float* stacked, const float* weights, const float* dfused, float* dstacked,
                                 float* dscores, int B, int S, int C, lr_stream_t stream) {
-    LR_CHECK_ARG(B >= 0 && S > 0 && S <= fu::SMAX && C > 0, "lr_attn_fuse_bwd: need 1 <= S <= 8, C > 0");
+    LR_CHECK_ARG(B >= 0 && S > 0 && S <= fu::SMAX && C > 0, "lr_attn_fuse_bwd: need 1 <= S <= 32, C > 0");
     if (B == 0) return LR_OK;
     LR_CHECK_ARG(stacked && weights && dfused && dstacked && dscores, "lr_attn_fuse_bwd: null pointer");
     fu::attn_fuse_bwd_kernel<<<B, fu::TH, 0, stream>>>(stacked, weights, dfused, dstacked, dscores, S, C);

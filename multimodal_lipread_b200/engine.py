@@ -761,25 +761,7 @@ class Plan:
 
         cur, dcur, Icur = x, dx, I
         for l in range(L - 1):
-            seq = self.alloc(F * 2 * H)
-            dseq = self.alloc(F * 2 * H) if self.with_backward else None
-            saved = []
-            for rev in (0, 1):
-                xp, gates, cst, hp = self.alloc(F * G4), self.alloc(F * G4), self.alloc(F * H), self.alloc(F * H)
-                self.linear(cur, Icur, F, par("weight_ih", l, rev), par("bias_ih", l, rev), xp, G4)
-                self.fwd.add("lr_lstm_fwd", xp, G4, par("bias_hh", l, rev), par("weight_hh", l, rev),
-                             seq.data_ptr() + 4 * H * rev, 2 * H, gates, cst, hp, B, T, H, T, rev)
-                saved.append((gates, cst, hp))
-            if self.with_backward:
-                g = self.bgroup()
-                for rev in (0, 1):
-                    gates, cst, hp = saved[rev]
-                    dg = self.alloc(F * G4)
-                    g.add("lr_lstm_bwd", dseq.data_ptr() + 4 * H * rev, 2 * H, -1, gates, cst, par("weight_hh", l, rev), dg,
-                          B, T, H, T, rev)
-                    self.linear_bwd(g, hp, H, F, par("weight_hh", l, rev), par("bias_hh", l, rev), dg, G4)
-                    self.linear_bwd(g, cur, Icur, F, par("weight_ih", l, rev), par("bias_ih", l, rev), dg, G4,
-                                    dx=dcur, ldx=Icur, dx_residual=(dcur if rev else 0), ldr=Icur)
+            seq, dseq = self._bilstm_full_layer(cur, dcur, Icur, B, T, lstm, l)
             cur, dcur = self.dropout(seq, dseq, F * 2 * H, p_drop)
             Icur = 2 * H
         # ---- top layer
@@ -813,6 +795,47 @@ class Plan:
                 self.linear_bwd(g, cur_last, T * Icur, B, par("weight_ih", l, 1), par("bias_ih", l, 1), dg_r, G4,
                                 dx=dcur_last, ldx=T * Icur, dx_residual=dcur_last, ldr=T * Icur)
 
+    def _bilstm_full_layer(self, cur, dcur, Icur, B, T, lstm, l):
+        """Layer l of a bidirectional nn.LSTM over the whole sequence, both directions -> (seq [B*T, 2H], dseq)."""
+        H = lstm.hidden_size
+        F, G4 = B * T, 4 * H
+
+        def par(name, rev):
+            return getattr(lstm, f"{name}_l{l}{'_reverse' if rev else ''}")
+        seq = self.alloc(F * 2 * H)
+        dseq = self.alloc(F * 2 * H) if self.with_backward else None
+        saved = []
+        for rev in (0, 1):
+            xp, gates, cst, hp = self.alloc(F * G4), self.alloc(F * G4), self.alloc(F * H), self.alloc(F * H)
+            self.linear(cur, Icur, F, par("weight_ih", rev), par("bias_ih", rev), xp, G4)
+            self.fwd.add("lr_lstm_fwd", xp, G4, par("bias_hh", rev), par("weight_hh", rev),
+                         seq.data_ptr() + 4 * H * rev, 2 * H, gates, cst, hp, B, T, H, T, rev)
+            saved.append((gates, cst, hp))
+        if self.with_backward:
+            g = self.bgroup()
+            for rev in (0, 1):
+                gates, cst, hp = saved[rev]
+                dg = self.alloc(F * G4)
+                g.add("lr_lstm_bwd", dseq.data_ptr() + 4 * H * rev, 2 * H, -1, gates, cst, par("weight_hh", rev), dg,
+                      B, T, H, T, rev)
+                self.linear_bwd(g, hp, H, F, par("weight_hh", rev), par("bias_hh", rev), dg, G4)
+                self.linear_bwd(g, cur, Icur, F, par("weight_ih", rev), par("bias_ih", rev), dg, G4,
+                                dx=dcur, ldx=Icur, dx_residual=(dcur if rev else 0), ldr=Icur)
+        return seq, dseq
+
+    def bilstm_seq(self, x, dx, I, B, T, lstm):
+        """Every layer of a bidirectional nn.LSTM over the whole sequence -> (out [B*T, 2H], dout): the heads that read
+        all time steps (audio/models/lstm_resnet_attn_model.py:78-81)."""
+        assert lstm.bidirectional and lstm.batch_first
+        H, L = lstm.hidden_size, lstm.num_layers
+        cur, dcur, Icur = x, dx, I
+        for l in range(L):
+            cur, dcur = self._bilstm_full_layer(cur, dcur, Icur, B, T, lstm, l)
+            if l < L - 1:
+                cur, dcur = self.dropout(cur, dcur, B * T * 2 * H, float(lstm.dropout))
+            Icur = 2 * H
+        return cur, dcur
+
     def bilstm_hn(self, x, dx, I, B, T, lstm, out, ldo, dout):
         """Single-layer bidirectional nn.LSTM whose head is cat(h_n[0], h_n[1]) (audio_video/models/late_fusion.py:61-62,
         early_fusion_fast.py:53-54): BOTH directions walk all T steps; h_n[0] = forward output at t = T-1, h_n[1] =
@@ -845,6 +868,38 @@ class Plan:
                 self.linear_bwd(g, hp, H, F, par("weight_hh", rev), par("bias_hh", rev), dg, G4)
                 self.linear_bwd(g, x, I, F, par("weight_ih", rev), par("bias_ih", rev), dg, G4, dx=dx, ldx=I,
                                 dx_residual=(dx if rev else 0), ldr=I)
+
+    # ---- nn.MultiheadAttention (self-attention over time) ---------------------------------------------------
+    def multihead_attention(self, x, dx, B, T, mha):
+        """nn.MultiheadAttention(embed_dim, heads, dropout, batch_first=True)(x, x, x)[0] on x [B*T, E] -> (out, dout).
+        In-projection GEMM -> lr_mha_scores_fwd -> [dropout on the weights] -> lr_mha_apply_fwd -> out-projection GEMM
+        (video/models/resnet_attn.py:23-35)."""
+        E, heads = mha.embed_dim, mha.num_heads
+        assert mha.batch_first and mha._qkv_same_embed_dim and mha.in_proj_bias is not None
+        F, wb = B * T, self.with_backward
+        qkv = self.alloc(F * 3 * E)
+        dqkv = self.alloc(F * 3 * E) if wb else None
+        self.linear(x, E, F, mha.in_proj_weight, mha.in_proj_bias, qkv, 3 * E)
+        if wb:
+            self.linear_bwd(self.bgroup(), x, E, F, mha.in_proj_weight, mha.in_proj_bias, dqkv, 3 * E, dx=dx, ldx=E)
+        n_p = B * heads * T * T
+        P = self.alloc(n_p)
+        dP = self.alloc(n_p) if wb else None
+        self.fwd.add("lr_mha_scores_fwd", qkv, 3 * E, P, B, T, E, heads)
+        if wb:
+            self.bgroup().add("lr_mha_scores_bwd", P, dP, qkv, 3 * E, dqkv, B, T, E, heads)
+        Pd, dPd = self.dropout(P, dP, n_p, float(mha.dropout))
+        O = self.alloc(F * E)
+        dO = self.alloc(F * E) if wb else None
+        self.fwd.add("lr_mha_apply_fwd", Pd, qkv, 3 * E, O, B, T, E, heads)
+        if wb:
+            self.bgroup().add("lr_mha_apply_bwd", dO, Pd, qkv, 3 * E, dPd, dqkv, B, T, E, heads)
+        out = self.alloc(F * E)
+        dout = self.alloc(F * E) if wb else None
+        self.linear(O, E, F, mha.out_proj.weight, mha.out_proj.bias, out, E)
+        if wb:
+            self.linear_bwd(self.bgroup(), O, E, F, mha.out_proj.weight, mha.out_proj.bias, dout, E, dx=dO, ldx=E)
+        return out, dout
 
     # ---- torchvision ResNet (BasicBlock) -------------------------------------------------------------------
     def resnet_features(self, net, frames, x=None):

@@ -72,6 +72,76 @@ class ResNetLstmPlan(ModelPlan):
         self.set_logits(logits, dlogits)
 
 
+class ResNetAttnPlan(ModelPlan):
+    """video/models/resnet_attn.py:95-111: per-frame ResNet features -> proj_in -> multi-head self-attention over time ->
+    mean over time -> ReLU -> Dropout -> fc."""
+
+    def build(self, m, spec):
+        B, wb = self.B, self.with_backward
+        video, layout, scale = self.video_input()
+        T = layout[2]
+        last = self.resnet_features(_resnet_view(m.cnn_features), (video, layout, scale))
+        feat, dfeat = self.avgpool(last)
+        E = m.proj_in.out_features
+        x = self.alloc(B * T * E)
+        dx = self.alloc(B * T * E) if wb else None
+        self.linear(feat, last.C, B * T, m.proj_in.weight, m.proj_in.bias, x, E)
+        if wb:
+            self.linear_bwd(self.bgroup(), feat, last.C, B * T, m.proj_in.weight, m.proj_in.bias, dx, E, dx=dfeat, ldx=last.C)
+        att, datt = self.multihead_attention(x, dx, B, T, m.attention.attn)
+        pooled, dpooled = self.avgpool(engine.T2.of(B, 1, T, E, att, datt))            # x.mean(dim=1)
+        h = self.alloc(B * E)
+        self.fwd.add("lr_act_fwd", pooled, h, B * E, ACT_RELU)
+        if wb:
+            self.bgroup().add("lr_act_bwd", dpooled, h, B * E, ACT_RELU)               # dpooled doubles as dh
+        hd, dhd = self.dropout(h, dpooled, B * E, m.dropout.p)
+        logits = self.alloc(B * self.num_classes)
+        dlogits = self.alloc(B * self.num_classes) if wb else None
+        self.linear(hd, E, B, m.fc.weight, m.fc.bias, logits, self.num_classes)
+        if wb:
+            self.linear_bwd(self.bgroup(), hd, E, B, m.fc.weight, m.fc.bias, dlogits, self.num_classes, dx=dhd, ldx=E)
+        self.set_logits(logits, dlogits)
+
+
+class TemporalAttention(nn.Module):
+    """resnet_attn.py:23-35 (parameter container)."""
+
+    def __init__(self, embed_dim, num_heads=4, dropout=0.1):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(embed_dim, num_heads, dropout=dropout, batch_first=True)
+
+
+class ResNet2DAttention(PlanModel):
+    """video/models/resnet_attn.py:38-111 (model.name == "resnet_attn")."""
+    INPUTS = ("video",)
+    PLAN = ResNetAttnPlan
+    DEFAULT_LR = 5e-5
+    DEFAULT_WD = 1e-5
+
+    def __init__(self, num_classes, config=None, pretrained_state_dict=None, precision=None):
+        super().__init__()
+        config = config or Cfg()
+        self._init_base(num_classes, config, precision)
+        base = resnet18(weights=None) if config.get("model.resnet_version", 18) == 18 else resnet34(weights=None)
+        if pretrained_state_dict is not None:
+            base.load_state_dict(pretrained_state_dict)
+        base.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.cnn_features = nn.Sequential(*list(base.children())[:-2])
+        self.global_pool = nn.AdaptiveAvgPool2d((1, 1))
+        with torch.no_grad():                                # :63-67, the same constructor-time pass as resnet_lstm.py
+            self.cnn_features(torch.zeros(1, 3, 44, 44))
+        cnn_output_dim = 512
+        self.time_cnn = TimeDistributed(nn.Sequential(self.cnn_features, self.global_pool, nn.Flatten()))
+        attn_dim = config.get("model.attention_dim", cnn_output_dim)
+        num_heads = config.get("model.num_heads", 4)
+        dropout = config.get("model.dropout", 0.3)
+        self.proj_in = nn.Linear(cnn_output_dim, attn_dim)
+        self.attention = TemporalAttention(attn_dim, num_heads=num_heads, dropout=dropout)
+        self.dropout = nn.Dropout(dropout)
+        self.relu = nn.ReLU()
+        self.fc = nn.Linear(attn_dim, num_classes)
+
+
 class ResNet2DBiLSTM(PlanModel):
     """video/models/resnet_lstm.py:56-156.  forward(x (B,3,T,H,W) f32 [or uint8 (B,T,H,W,3)]) -> (B, num_classes)."""
     INPUTS = ("video",)

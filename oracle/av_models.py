@@ -21,6 +21,8 @@ there is no network for the ImageNet checkpoint:
   VGGAudioOracle              audio/models/vgg_model.py:5-58
   VGGLstmAudioOracle          audio/models/vgg_lstm_model.py:5-75
   LSTMResNetOracle            audio/models/lstm_resnet_model.py:5-71
+  LSTMResNetAttnOracle        audio/models/lstm_resnet_attn_model.py:17-88
+  ResNet2DAttentionOracle     video/models/resnet_attn.py:38-111
   AttentionFusionACVOracle    audio_cues_video/models/{middle_fusion_mobile,middle_fusion_resnet,early_fusion_mobile,early_fusion_resnet}.py
   LateFusionAVMobileNetOracle audio_video/models/late_fusion.py:10-93
   MidFusionAVMobileNetOracle  audio_video/models/middle_fusion.py:11-85
@@ -186,6 +188,41 @@ class ResNet2DBiLSTMOracle(nn.Module):
     def forward(self, x):
         x, _ = self.bilstm(self.time_distributed_cnn(x))
         return self.fc(self.dropout(self.relu(x[:, -1, :])))
+
+
+class ResNet2DAttentionOracle(nn.Module):
+    """video/models/resnet_attn.py:38-111: ResNet-18 per frame (conv1 re-initialised, constructor-time dummy pass),
+    proj_in, nn.MultiheadAttention over time, mean over time, ReLU, Dropout, fc."""
+
+    class _TemporalAttention(nn.Module):
+        def __init__(self, embed_dim, num_heads, dropout):
+            super().__init__()
+            self.attn = nn.MultiheadAttention(embed_dim, num_heads, dropout=dropout, batch_first=True)
+
+        def forward(self, x):
+            return self.attn(x, x, x)[0]
+
+    def __init__(self, num_classes, config=None):
+        super().__init__()
+        config = config or DictConfig()
+        base = resnet18(weights=None)
+        base.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.cnn_features = nn.Sequential(*list(base.children())[:-2])
+        self.global_pool = nn.AdaptiveAvgPool2d((1, 1))
+        with torch.no_grad():                                              # :63-67
+            self.global_pool(self.cnn_features(torch.zeros(1, 3, 44, 44)))
+        self.time_cnn = _TimeDistributed(nn.Sequential(self.cnn_features, self.global_pool, nn.Flatten()))
+        attn_dim = config.get("model.attention_dim", 512)
+        dropout = config.get("model.dropout", 0.3)
+        self.proj_in = nn.Linear(512, attn_dim)
+        self.attention = self._TemporalAttention(attn_dim, config.get("model.num_heads", 4), dropout)
+        self.dropout = nn.Dropout(dropout)
+        self.relu = nn.ReLU()
+        self.fc = nn.Linear(attn_dim, num_classes)
+
+    def forward(self, x):
+        x = self.attention(self.proj_in(self.time_cnn(x))).mean(dim=1)
+        return self.fc(self.dropout(self.relu(x)))
 
 
 class AudioResNetOracle(nn.Module):
@@ -569,6 +606,9 @@ class LSTMResNetOracle(nn.Module):
         layers.extend([nn.ReLU(), nn.Dropout(dropout_rate)])
         self.fc = nn.Sequential(*layers)
         self.final_bilstm = nn.LSTM(256, 128, num_layers=2, bidirectional=True, batch_first=True)
+        self._tail(num_classes)
+
+    def _tail(self, num_classes):
         self.classifier = nn.Linear(256, num_classes)
 
     def forward(self, x):
@@ -577,6 +617,32 @@ class LSTMResNetOracle(nn.Module):
         x1 = x1.squeeze(1).view(b, 1, 80, -1)
         out, _ = self.final_bilstm(self.fc(self.resnet(x1)).unsqueeze(1))
         return self.classifier(out[:, -1, :])
+
+
+class LSTMResNetAttnOracle(LSTMResNetOracle):
+    """audio/models/lstm_resnet_attn_model.py:17-88: the fc output repeated over 10 steps, a full 2-layer BiLSTM,
+    additive attention pooling over the steps, classifier."""
+
+    class _Attention(nn.Module):
+        def __init__(self, input_dim):
+            super().__init__()
+            self.attn = nn.Linear(input_dim, 1)
+
+        def forward(self, x):
+            weights = torch.softmax(self.attn(x).squeeze(-1), dim=1)
+            return torch.sum(x * weights.unsqueeze(-1), dim=1), weights
+
+    def _tail(self, num_classes):                            # construction (= RNG) order of the reference: :54-58
+        self.attention = self._Attention(256)
+        self.classifier = nn.Linear(256, num_classes)
+
+    def forward(self, x):
+        b = x.size(0)
+        x1, _ = self.initial_bilstm(x.view(b * 80, 117).unsqueeze(1))
+        x1 = x1.squeeze(1).view(b, 1, 80, -1)
+        out, _ = self.final_bilstm(self.fc(self.resnet(x1)).unsqueeze(1).repeat(1, 10, 1))
+        pooled, _ = self.attention(out)
+        return self.classifier(pooled)
 
 
 class _VideoLstm(nn.Module):

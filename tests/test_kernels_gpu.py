@@ -348,3 +348,42 @@ def test_audio_conv_ce_adam(K):
             K.adam_step(pd, (gr * 4).cuda(), m, v, state, 1000, 0.9, 0.999, 1e-8, wd, 0.25)
         _close(pd, p, rtol=1e-6)
         assert float(state[0]) == 3.0
+
+
+@pytest.mark.parametrize("B,T,E,heads", [(3, 29, 512, 4), (2, 6, 256, 4), (1, 1, 64, 8), (2, 64, 128, 1), (2, 10, 256, 2)])
+def test_multihead_attention_kernels(K, B, T, E, heads):
+    """lr_mha_* against nn.MultiheadAttention's own forward / autograd (video/models/resnet_attn.py:23-35): attention
+    weights, concatenated heads and the gradient of the packed in-projection."""
+    from multimodal_lipread_b200._lib import lib, check
+    torch.manual_seed(T * 7 + E)
+    mha = nn.MultiheadAttention(E, heads, dropout=0.0, batch_first=True)
+    x = torch.randn(B, T, E)
+    qkv_ref = (x @ mha.in_proj_weight.T + mha.in_proj_bias).detach().requires_grad_(True)         # [B, T, 3E]
+    q, k, v = qkv_ref.chunk(3, dim=-1)
+    d = E // heads
+    split = lambda t: t.view(B, T, heads, d).transpose(1, 2)                                      # [B, h, T, d]
+    P_ref = torch.softmax((split(q) * (1.0 / d) ** 0.5) @ split(k).transpose(-1, -2), dim=-1)
+    O_ref = (P_ref @ split(v)).transpose(1, 2).reshape(B, T, E)
+    out_ref, w_ref = mha(x, x, x)                                                                 # the module's own answer
+    assert torch.allclose(out_ref, O_ref @ mha.out_proj.weight.T + mha.out_proj.bias, atol=1e-5)
+    assert torch.allclose(w_ref, P_ref.mean(dim=1), atol=1e-6)
+    dO_ref = torch.randn(B, T, E)
+    O_ref.backward(dO_ref)
+    dev = "cuda"
+    qkv = qkv_ref.detach().reshape(B * T, 3 * E).to(dev).contiguous()
+    P = torch.empty(B, heads, T, T, device=dev)
+    O = torch.empty(B * T, E, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    check(lib.lr_mha_scores_fwd(qkv.data_ptr(), 3 * E, P.data_ptr(), B, T, E, heads, s))
+    check(lib.lr_mha_apply_fwd(P.data_ptr(), qkv.data_ptr(), 3 * E, O.data_ptr(), B, T, E, heads, s))
+    _close(P.cpu(), P_ref.detach(), rtol=2e-5)
+    _close(O.cpu().view(B, T, E), O_ref.detach(), rtol=2e-5)
+    dO = dO_ref.reshape(B * T, E).to(dev).contiguous()
+    dP = torch.empty_like(P)
+    dqkv = torch.full_like(qkv, float("nan"))                       # every element must be written
+    check(lib.lr_mha_apply_bwd(dO.data_ptr(), P.data_ptr(), qkv.data_ptr(), 3 * E, dP.data_ptr(), dqkv.data_ptr(), B, T, E, heads, s))
+    check(lib.lr_mha_scores_bwd(P.data_ptr(), dP.data_ptr(), qkv.data_ptr(), 3 * E, dqkv.data_ptr(), B, T, E, heads, s))
+    _close(dqkv.cpu().view(B, T, 3 * E), qkv_ref.grad, rtol=5e-5)
+    # argument errors do not launch
+    assert lib.lr_mha_scores_fwd(qkv.data_ptr(), 3 * E, P.data_ptr(), B, 65, E, heads, s) == -1
+    assert lib.lr_mha_scores_fwd(qkv.data_ptr(), 3 * E, P.data_ptr(), B, T, E, 3 if E % 3 else 7, s) == -1

@@ -140,6 +140,8 @@ def _case(name, precision="fp32"):
         ref = O.VGGLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
     elif name == "video_cnn":
         ref = O.CNNOnlyOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
+    elif name == "video_resnet_attn":
+        ref = O.ResNet2DAttentionOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
     elif name == "audio_resnet_lstm":
         ref = O.AudioResNetLSTMOracle(C, dropout_rate=0.0)
     elif name == "audio_vgg":
@@ -148,6 +150,8 @@ def _case(name, precision="fp32"):
         ref = O.VGGLstmAudioOracle(C, version=11, dropout_rate=0.0)
     elif name == "audio_lstm_resnet":
         ref = O.LSTMResNetOracle(C, dropout_rate=0.0)
+    elif name == "audio_lstm_resnet_attn":
+        ref = O.LSTMResNetAttnOracle(C, dropout_rate=0.0)
     elif name == "video_mobilenet_lstm":
         ref = O.MobileNetLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
     elif name == "acv_late_fusion_resnet":
@@ -177,6 +181,8 @@ def _case(name, precision="fp32"):
         ours = video_models.VGGLSTM(C, cfg, precision=precision)
     elif name == "video_cnn":
         ours = video_models.CNNOnly(C, cfg, precision=precision)
+    elif name == "video_resnet_attn":
+        ours = video_models.ResNet2DAttention(C, cfg, precision=precision)
     elif name == "audio_resnet_lstm":
         ours = audio_models.AudioResNetLSTM(C, dropout_rate=0.0, precision=precision)
     elif name == "audio_vgg":
@@ -185,6 +191,8 @@ def _case(name, precision="fp32"):
         ours = audio_models.VGGWithLSTMClassifier(C, version=11, dropout_rate=0.0, precision=precision)
     elif name == "audio_lstm_resnet":
         ours = audio_models.LSTMResNet(C, dropout_rate=0.0, precision=precision)
+    elif name == "audio_lstm_resnet_attn":
+        ours = audio_models.DeepAudioNetWithAttention(C, dropout_rate=0.0, precision=precision)
     elif name == "video_mobilenet_lstm":
         ours = video_models.MobileNetLSTM(C, cfg, precision=precision)
     elif name == "acv_late_fusion_resnet":
@@ -216,7 +224,7 @@ def _inputs_for(name, mel, lips):
     video = lips_u8_to_model_input(lips)
     if name.startswith("early_fusion") or name in ("late_fusion_mobilenet", "middle_fusion_mobilenet", "late_fusion_fast"):
         return (mel, video), (mel.cuda(), lips.cuda())
-    if name in ("video_resnet_lstm", "video_mobilenet_lstm", "video_vgg_lstm", "video_cnn"):
+    if name.startswith("video_"):
         return (video,), (lips.cuda(),)
     if name.startswith("acv_"):
         from multimodal_lipread_b200 import synthetic
@@ -238,10 +246,12 @@ def _inputs_for(name, mel, lips):
     ("video_mobilenet_lstm", 3, 6, 44),
     ("video_vgg_lstm", 3, 6, 44),
     ("video_cnn", 3, 6, 44),
+    ("video_resnet_attn", 3, 6, 44),
     ("audio_resnet_lstm", 4, 1, 44),
     ("audio_vgg", 4, 1, 44),
     ("audio_vgg_lstm", 4, 1, 44),
     ("audio_lstm_resnet", 4, 1, 44),
+    ("audio_lstm_resnet_attn", 4, 1, 44),
     ("acv_late_fusion_resnet", 3, 6, 44),
     ("late_fusion_mobilenet", 3, 8, 44),
     ("middle_fusion_mobilenet", 3, 8, 44),
@@ -305,7 +315,7 @@ def test_train_step_matches_oracle(cuda_device, name, B, T, size):
 
 
 @pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
-                                  "acv_late_fusion_resnet", "video_vgg_lstm", "video_cnn", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm", "audio_lstm_resnet",
+                                  "acv_late_fusion_resnet", "video_vgg_lstm", "video_cnn", "video_resnet_attn", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm", "audio_lstm_resnet", "audio_lstm_resnet_attn",
                                   "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast",
                                   "acv_middle_fusion_mobile", "acv_middle_fusion_resnet", "acv_early_fusion_mobile", "acv_early_fusion_resnet"])
 def test_golden_vectors_of_the_reference(cuda_device, golden_dir, name):

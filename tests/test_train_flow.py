@@ -41,6 +41,7 @@ def test_model_name_dispatch_and_errors():
     assert type(T.create_audio_model("vgg", 8, version=11)).__name__ == "VGGAudioClassifier"
     assert type(T.create_audio_model("vgg_lstm", 8, version=11)).__name__ == "VGGWithLSTMClassifier"
     assert type(T.create_audio_model("lstm_resnet", 8, input_size=117)).__name__ == "LSTMResNet"
+    assert type(T.create_audio_model("lstm_resnet_attn", 8, input_size=117)).__name__ == "DeepAudioNetWithAttention"
     for name in T.ACV_MODELS:                            # every audio_cues_video name (train.py:144-155) has a plan
         m = T.create_acv_model(name, 40)
         assert m.num_classes == 40 and m.INPUTS == ("audio", "cue", "video")
