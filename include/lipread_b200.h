@@ -265,6 +265,20 @@ int lr_mha_apply_bwd(const float* dO, const float* P, const float* qkv, long lon
 int lr_mha_scores_bwd(const float* P, const float* dP, const float* qkv, long long ld, float* dqkv, int B, int T, int E,
                       int heads, lr_stream_t stream);
 
+/* nn.LayerNorm(D) over rows [rows, D] with the residual add of a post-norm nn.TransformerEncoderLayer fused in:
+ *   s = a + b (b == NULL: s = a);  y = (s - mean(s)) / sqrt(var(s) + eps) * gamma + beta.   D <= 1024.
+ * s [rows, D] and stats [rows, 2] = (mean, rstd) are saved for the backward, which writes ds (the gradient of both
+ * a and b) and ACCUMULATES dgamma / dbeta.
+ * replaces: norm1 / norm2 of nn.TransformerEncoderLayer (video/models/resnet_trans.py:96-103,
+ * audio/models/lstm_resnet_trans_model.py:52-58). */
+int lr_layernorm_fwd(const float* a, const float* b, const float* gamma, const float* beta, float eps, float* y, float* s,
+                     float* stats, int rows, int D, lr_stream_t stream);
+int lr_layernorm_bwd(const float* dy, const float* s, const float* stats, const float* gamma, float* ds, float* dgamma,
+                     float* dbeta, int rows, int D, lr_stream_t stream);
+/* out[f, t, c] = x[f, c] + r[t, c] (r == NULL: plain repeat): fc_out.unsqueeze(1).repeat(1, T, 1) + pe[:, :T]
+ * (audio/models/lstm_resnet_trans_model.py:91-94, lstm_resnet_attn_model.py:78). */
+int lr_add_bcast(const float* x, const float* r, float* out, int F, int T, int C, lr_stream_t stream);
+
 /* AttentionFusion of the late triple-fusion model (audio_cues_video/models/late_fusion_mobile.py:6-19) around its
  * attn MLP (two lr_gemm calls): weights = softmax(scores[B,S], dim=1); fused[b,:] = sum_s weights[b,s] stacked[b,s,:].
  * Backward: dstacked = weights * dfused (the MLP's own backward then accumulates onto it), dscores through the softmax.

@@ -6,6 +6,7 @@
   VGGWithLSTMClassifier audio/models/vgg_lstm_model.py:5-75     (model.name == "vgg_lstm")
   LSTMResNet           audio/models/lstm_resnet_model.py:5-71   (model.name == "lstm_resnet")
   DeepAudioNetWithAttention audio/models/lstm_resnet_attn_model.py:17-88 (model.name == "lstm_resnet_attn")
+  LSTMResNetWithTransformer audio/models/lstm_resnet_trans_model.py:22-104 (model.name == "lstm_resnet_trans")
 
 forward(spec (B,80,117) f32 log-mel) -> (B, num_classes); with a raw (B,20000) waveform the fused log-mel kernel
 runs first.  Sub-modules are parameter containers (reference names / construction order / state_dict keys)."""
@@ -295,8 +296,7 @@ class LstmResNetAttnPlan(ModelPlan):
         # fc_out.unsqueeze(1).repeat(1, 10, 1)
         xs = self.alloc(B * T * Dh)
         dxs = self.alloc(B * T * Dh) if wb else None
-        for t in range(T):
-            self.fwd.add("lr_copy2d", xs.data_ptr() + 4 * t * Dh, T * Dh, h, Dh, B, Dh)
+        self.fwd.add("lr_add_bcast", h, 0, xs, B, T, Dh)
         if wb:
             ones = torch.ones(B * T * Dh, dtype=torch.float32, device=self.dev)
             self.bufs.append(ones)
@@ -353,6 +353,80 @@ class LSTMResNet(PlanModel):
         self.classifier = nn.Linear(2 * 128, num_classes)
 
 
+class LstmResNetTransPlan(ModelPlan):
+    """audio/models/lstm_resnet_trans_model.py:88-104: the projection repeated over seq_len steps + positional encoding,
+    TransformerEncoder, mean over the steps, classifier."""
+
+    def build(self, m, spec):
+        B, wb, T = self.B, self.with_backward, m.seq_len
+        h, dh, E = lstm_resnet_front(self, m)
+        pe = m.pos_encoder.pe[0, :T]
+        xs = self.alloc(B * T * E)
+        dxs = self.alloc(B * T * E) if wb else None
+        self.fwd.add("lr_add_bcast", h, pe, xs, B, T, E)               # fc_out.unsqueeze(1).repeat(1, T, 1) + pe[:, :T]
+        if wb:
+            ones = torch.ones(B * T * E, dtype=torch.float32, device=self.dev)
+            self.bufs.append(ones)
+            self.bgroup().add("lr_frame_reduce", dxs, ones, dh, B, T, E, 1)             # dh[b] = sum_t dxs[b, t]
+        x, dx = xs, dxs
+        for layer in m.transformer.layers:
+            x, dx = self.transformer_encoder_layer(x, dx, B, T, layer)
+        pooled, dpooled = self.avgpool(engine.T2.of(B, 1, T, E, x, dx))                 # x_encoded.mean(dim=1)
+        C = self.num_classes
+        logits = self.alloc(B * C)
+        dlogits = self.alloc(B * C) if wb else None
+        self.linear(pooled, E, B, m.classifier.weight, m.classifier.bias, logits, C)
+        if wb:
+            self.linear_bwd(self.bgroup(), pooled, E, B, m.classifier.weight, m.classifier.bias, dlogits, C, dx=dpooled, ldx=E)
+        self.set_logits(logits, dlogits)
+
+
+class PositionalEncodingBuffer(nn.Module):
+    """lstm_resnet_trans_model.py:6-19: the table is a registered buffer (state_dict key `pos_encoder.pe`)."""
+
+    def __init__(self, dim, max_len=5000):
+        super().__init__()
+        import numpy as np
+        pe = torch.zeros(max_len, dim)
+        position = torch.arange(0, max_len).unsqueeze(1).float()
+        div_term = torch.exp(torch.arange(0, dim, 2).float() * (-np.log(10000.0) / dim))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe.unsqueeze(0))
+
+
+class LSTMResNetWithTransformer(PlanModel):
+    """audio/models/lstm_resnet_trans_model.py:22-104 (model.name == "lstm_resnet_trans")."""
+    INPUTS = ("audio",)
+    PLAN = LstmResNetTransPlan
+    DEFAULT_LR = 5e-4
+    DEFAULT_WD = 1e-4
+
+    def __init__(self, num_classes=40, input_size=117, transformer_dim=256, num_heads=4, num_layers=2, seq_len=10,
+                 dropout_rate=0.3, use_batchnorm=True, pretrained_state_dict=None, precision=None, encoder_dropout=0.1):
+        super().__init__()
+        self._init_base(num_classes, types.SimpleNamespace(get=lambda k, d=None: d), precision)
+        self.seq_len = seq_len
+        self.use_bn = use_batchnorm
+        self.initial_bilstm = nn.LSTM(input_size=input_size, hidden_size=64, num_layers=2, bidirectional=True, batch_first=True)
+        self.resnet = resnet18(weights=None)
+        if pretrained_state_dict is not None:
+            self.resnet.load_state_dict(pretrained_state_dict)
+        self.resnet.conv1 = nn.Conv2d(1, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.resnet.fc = nn.Identity()
+        layers = [nn.Linear(512, transformer_dim)]
+        if use_batchnorm:
+            layers.append(nn.BatchNorm1d(transformer_dim))
+        layers.extend([nn.ReLU(), nn.Dropout(dropout_rate)])
+        self.fc = nn.Sequential(*layers)
+        self.pos_encoder = PositionalEncodingBuffer(dim=transformer_dim, max_len=seq_len)
+        # nn.TransformerEncoderLayer's own default dropout (0.1) applies in the reference; encoder_dropout exposes it
+        encoder_layer = nn.TransformerEncoderLayer(d_model=transformer_dim, nhead=num_heads, batch_first=True,
+                                                   dropout=encoder_dropout)
+        self.transformer = nn.TransformerEncoder(encoder_layer, num_layers=num_layers)
+        self.classifier = nn.Linear(transformer_dim, num_classes)
+
+
 class Attention(nn.Module):
     """lstm_resnet_attn_model.py:5-14 (parameters only)."""
 
@@ -384,4 +458,6 @@ def get_model(num_classes, input_size, model_name, version=None):
         return LSTMResNet(num_classes=num_classes, input_size=input_size)
     if model_name == "lstm_resnet_attn":
         return DeepAudioNetWithAttention(num_classes=num_classes, input_size=input_size)
+    if model_name == "lstm_resnet_trans":
+        return LSTMResNetWithTransformer(num_classes=num_classes, input_size=input_size)
     raise ValueError(f"Invalid model name: {model_name}")

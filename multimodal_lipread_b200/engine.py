@@ -682,10 +682,13 @@ class Plan:
             self.bgroup().add("lr_maxpool_bwd", y.grad, arg, x.grad, x.F, x.H, x.W, x.C, k, stride, pad)
         return y
 
-    def dropout(self, x, dx, n, p):
+    def dropout_active(self, p):
+        return self.training and p > 0.0
+
+    def dropout(self, x, dx, n, p, dy=None):
         """nn.Dropout(p) on a flat buffer of n floats (training plans only; identity otherwise).
-        Returns (y, dy): dy is the buffer the consumer's backward must write."""
-        if not self.training or p <= 0.0:
+        Returns (y, dy): dy is the buffer the consumer's backward must write (allocated here unless given)."""
+        if not self.dropout_active(p):
             return x, dx
         if self.rng_step is None:
             self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.dev)
@@ -693,11 +696,12 @@ class Plan:
         self._n_dropout += 1
         y, mask = self.alloc(n), self.alloc(n, torch.uint8)
         self.fwd.add("lr_dropout_fwd", x, y, mask, n, float(p), 0x5EED0000 + self._n_dropout, self.rng_step)
-        dy = None
         if self.with_backward:
-            dy = self.alloc(n)
+            dy = self.alloc(n) if dy is None else dy
             if dx is not None:
                 self.bgroup().add("lr_dropout_bwd", dy, mask, dx, n, float(p))
+        else:
+            dy = None
         return y, dy
 
     def cnn_sequential(self, mods, frames):
@@ -870,7 +874,7 @@ class Plan:
                                 dx_residual=(dx if rev else 0), ldr=I)
 
     # ---- nn.MultiheadAttention (self-attention over time) ---------------------------------------------------
-    def multihead_attention(self, x, dx, B, T, mha):
+    def multihead_attention(self, x, dx, B, T, mha, dx_residual=0, dout=None):
         """nn.MultiheadAttention(embed_dim, heads, dropout, batch_first=True)(x, x, x)[0] on x [B*T, E] -> (out, dout).
         In-projection GEMM -> lr_mha_scores_fwd -> [dropout on the weights] -> lr_mha_apply_fwd -> out-projection GEMM
         (video/models/resnet_attn.py:23-35)."""
@@ -881,7 +885,8 @@ class Plan:
         dqkv = self.alloc(F * 3 * E) if wb else None
         self.linear(x, E, F, mha.in_proj_weight, mha.in_proj_bias, qkv, 3 * E)
         if wb:
-            self.linear_bwd(self.bgroup(), x, E, F, mha.in_proj_weight, mha.in_proj_bias, dqkv, 3 * E, dx=dx, ldx=E)
+            self.linear_bwd(self.bgroup(), x, E, F, mha.in_proj_weight, mha.in_proj_bias, dqkv, 3 * E, dx=dx, ldx=E,
+                            dx_residual=dx_residual, ldr=E)
         n_p = B * heads * T * T
         P = self.alloc(n_p)
         dP = self.alloc(n_p) if wb else None
@@ -895,11 +900,56 @@ class Plan:
         if wb:
             self.bgroup().add("lr_mha_apply_bwd", dO, Pd, qkv, 3 * E, dPd, dqkv, B, T, E, heads)
         out = self.alloc(F * E)
-        dout = self.alloc(F * E) if wb else None
+        dout = (self.alloc(F * E) if dout is None else dout) if wb else None
         self.linear(O, E, F, mha.out_proj.weight, mha.out_proj.bias, out, E)
         if wb:
             self.linear_bwd(self.bgroup(), O, E, F, mha.out_proj.weight, mha.out_proj.bias, dout, E, dx=dO, ldx=E)
         return out, dout
+
+    # ---- nn.TransformerEncoderLayer (post-norm, ReLU) ---------------------------------------------------------
+    def layer_norm(self, a, b, ln, rows, ds):
+        """y = LayerNorm(a + b); the backward writes the gradient of the sum (of a and of b alike) into `ds`."""
+        (D,) = ln.normalized_shape
+        y, sm, st = self.alloc(rows * D), self.alloc(rows * D), self.alloc(rows * 2)
+        dy = self.alloc(rows * D) if self.with_backward else None
+        self.fwd.add("lr_layernorm_fwd", a, (b if b is not None else 0), ln.weight, ln.bias, float(ln.eps), y, sm, st, rows, D)
+        if self.with_backward:
+            self.bgroup().add("lr_layernorm_bwd", dy, sm, st, ln.weight, ds, self.flat.g(ln.weight), self.flat.g(ln.bias), rows, D)
+        return y, dy
+
+    def transformer_encoder_layer(self, x, dx, B, T, layer):
+        """nn.TransformerEncoderLayer(batch_first=True, norm_first=False, activation=relu) on x [B*T, E]:
+             h = norm1(x + dropout1(self_attn(x)));  y = norm2(h + dropout2(linear2(dropout(relu(linear1(h))))))
+        (video/models/resnet_trans.py:96-103).  dx receives dL/dx.  Returns (y, dy)."""
+        if layer.norm_first or getattr(layer.activation, "__name__", "") != "relu":
+            raise NotImplementedError("only the post-norm ReLU TransformerEncoderLayer the reference builds")
+        E, Dff = layer.self_attn.embed_dim, layer.linear1.out_features
+        F, wb = B * T, self.with_backward
+        # -- self-attention block: ds1 is the gradient of (x + dropout1(sa)), shared by the residual and the branch
+        ds1 = self.alloc(F * E) if wb else None
+        p1 = float(layer.dropout1.p)
+        dsa = (self.alloc(F * E) if self.dropout_active(p1) else ds1) if wb else None
+        sa, _ = self.multihead_attention(x, dx, B, T, layer.self_attn, dx_residual=(ds1 if wb else 0), dout=dsa)
+        sa_d, _ = self.dropout(sa, dsa, F * E, p1, dy=ds1)
+        h, dh = self.layer_norm(x, sa_d, layer.norm1, F, ds1)
+        # -- feed-forward block: ds2 is the gradient of (h + dropout2(ff))
+        ds2 = self.alloc(F * E) if wb else None
+        f1 = self.alloc(F * Dff)
+        df1 = self.alloc(F * Dff) if wb else None
+        self.linear(h, E, F, layer.linear1.weight, layer.linear1.bias, f1, Dff, act=ACT_RELU)
+        if wb:
+            g = self.bgroup()
+            g.add("lr_act_bwd", df1, f1, F * Dff, ACT_RELU)
+            self.linear_bwd(g, h, E, F, layer.linear1.weight, layer.linear1.bias, df1, Dff, dx=dh, ldx=E, dx_residual=ds2, ldr=E)
+        f1d, df1d = self.dropout(f1, df1, F * Dff, float(layer.dropout.p))
+        p2 = float(layer.dropout2.p)
+        f2 = self.alloc(F * E)
+        df2 = (self.alloc(F * E) if self.dropout_active(p2) else ds2) if wb else None
+        self.linear(f1d, Dff, F, layer.linear2.weight, layer.linear2.bias, f2, E)
+        if wb:
+            self.linear_bwd(self.bgroup(), f1d, Dff, F, layer.linear2.weight, layer.linear2.bias, df2, E, dx=df1d, ldx=Dff)
+        f2d, _ = self.dropout(f2, df2, F * E, p2, dy=ds2)
+        return self.layer_norm(h, f2d, layer.norm2, F, ds2)
 
     # ---- torchvision ResNet (BasicBlock) -------------------------------------------------------------------
     def resnet_features(self, net, frames, x=None):

@@ -77,6 +77,8 @@ def create_video_model(model_name, num_classes, config):
         return M.CNNOnly(num_classes=num_classes, config=config)
     if model_name == "resnet_attn":
         return M.ResNet2DAttention(num_classes=num_classes, config=config)
+    if model_name == "resnet_trans":
+        return M.ResNet2DTransformer(num_classes=num_classes, config=config)
     if model_name in VIDEO_MODELS:
         _no_plan(model_name)
     raise ValueError(f"Unknown model: {model_name}")
@@ -97,6 +99,8 @@ def create_audio_model(model_name, num_classes, input_size=117, version=None):
         return M.LSTMResNet(num_classes=num_classes, input_size=input_size)
     if model_name == "lstm_resnet_attn":
         return M.DeepAudioNetWithAttention(num_classes=num_classes, input_size=input_size)
+    if model_name == "lstm_resnet_trans":
+        return M.LSTMResNetWithTransformer(num_classes=num_classes, input_size=input_size)
     if model_name in AUDIO_MODELS:
         _no_plan(model_name)
     raise ValueError(f"Invalid model name: {model_name}")

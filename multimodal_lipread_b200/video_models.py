@@ -103,6 +103,92 @@ class ResNetAttnPlan(ModelPlan):
         self.set_logits(logits, dlogits)
 
 
+class ResNetTransPlan(ModelPlan):
+    """video/models/resnet_trans.py:108-129: per-frame ResNet features -> proj_in -> + sinusoidal positions ->
+    TransformerEncoder -> mean over time -> ReLU -> Dropout -> fc."""
+
+    def build(self, m, spec):
+        B, wb = self.B, self.with_backward
+        video, layout, scale = self.video_input()
+        T = layout[2]
+        last = self.resnet_features(_resnet_view(m.cnn_features), (video, layout, scale))
+        feat, dfeat = self.avgpool(last)
+        E = m.proj_in.out_features
+        pe = m.pos_encoding.pe[0, :T].to(self.dev, torch.float32).repeat(B, 1).contiguous()      # [B*T, E] constant
+        self.bufs.append(pe)
+        x = self.alloc(B * T * E)
+        dx = self.alloc(B * T * E) if wb else None
+        # x = proj_in(feat) + pe: the positions ride the GEMM epilogue's residual
+        self.gemm_auto(self.fwd, feat, last.C, 0, m.proj_in.weight, last.C, 0, x, E, B * T, E, last.C, bias=m.proj_in.bias,
+                       R=pe, ldr=E)
+        if wb:
+            self.linear_bwd(self.bgroup(), feat, last.C, B * T, m.proj_in.weight, m.proj_in.bias, dx, E, dx=dfeat, ldx=last.C)
+        for layer in m.transformer.layers:
+            x, dx = self.transformer_encoder_layer(x, dx, B, T, layer)
+        if m.transformer.norm is not None:
+            raise NotImplementedError("final norm of nn.TransformerEncoder")
+        pooled, dpooled = self.avgpool(engine.T2.of(B, 1, T, E, x, dx))                          # x.mean(dim=1)
+        h = self.alloc(B * E)
+        self.fwd.add("lr_act_fwd", pooled, h, B * E, ACT_RELU)
+        if wb:
+            self.bgroup().add("lr_act_bwd", dpooled, h, B * E, ACT_RELU)
+        hd, dhd = self.dropout(h, dpooled, B * E, m.dropout.p)
+        logits = self.alloc(B * self.num_classes)
+        dlogits = self.alloc(B * self.num_classes) if wb else None
+        self.linear(hd, E, B, m.fc.weight, m.fc.bias, logits, self.num_classes)
+        if wb:
+            self.linear_bwd(self.bgroup(), hd, E, B, m.fc.weight, m.fc.bias, dlogits, self.num_classes, dx=dhd, ldx=E)
+        self.set_logits(logits, dlogits)
+
+
+class PositionalEncoding(nn.Module):
+    """resnet_trans.py:23-42: sinusoidal table kept as a plain attribute (not in the state_dict), as the reference has it."""
+
+    def __init__(self, d_model, max_len=200):
+        super().__init__()
+        pe = torch.zeros(max_len, d_model)
+        pos = torch.arange(0, max_len).unsqueeze(1)
+        div = torch.exp(torch.arange(0, d_model, 2) * (-torch.log(torch.tensor(10000.0)) / d_model))
+        pe[:, 0::2] = torch.sin(pos * div)
+        pe[:, 1::2] = torch.cos(pos * div)
+        self.pe = pe.unsqueeze(0)
+
+
+class ResNet2DTransformer(PlanModel):
+    """video/models/resnet_trans.py:45-129 (model.name == "resnet_trans")."""
+    INPUTS = ("video",)
+    PLAN = ResNetTransPlan
+    DEFAULT_LR = 5e-5
+    DEFAULT_WD = 1e-5
+
+    def __init__(self, num_classes, config=None, pretrained_state_dict=None, precision=None):
+        super().__init__()
+        config = config or Cfg()
+        self._init_base(num_classes, config, precision)
+        base = resnet18(weights=None) if config.get("model.resnet_version", 18) == 18 else resnet34(weights=None)
+        if pretrained_state_dict is not None:
+            base.load_state_dict(pretrained_state_dict)
+        base.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.cnn_features = nn.Sequential(*list(base.children())[:-2])
+        self.global_pool = nn.AdaptiveAvgPool2d((1, 1))
+        with torch.no_grad():                                # :69-73, constructor-time pass through the train-mode CNN
+            self.cnn_features(torch.zeros(1, 3, 44, 44))
+        cnn_out_dim = 512
+        self.time_cnn = TimeDistributed(nn.Sequential(self.cnn_features, self.global_pool, nn.Flatten()))
+        transformer_dim = config.get("model.transformer_dim", 256)
+        num_layers = config.get("model.num_layers", 2)
+        num_heads = config.get("model.num_heads", 4)
+        dropout = config.get("model.dropout", 0.2)
+        self.proj_in = nn.Linear(cnn_out_dim, transformer_dim)
+        self.pos_encoding = PositionalEncoding(transformer_dim)
+        encoder_layer = nn.TransformerEncoderLayer(d_model=transformer_dim, nhead=num_heads, dropout=dropout,
+                                                   batch_first=True, dim_feedforward=transformer_dim * 4)
+        self.transformer = nn.TransformerEncoder(encoder_layer, num_layers=num_layers)
+        self.dropout = nn.Dropout(dropout)
+        self.relu = nn.ReLU()
+        self.fc = nn.Linear(transformer_dim, num_classes)
+
+
 class TemporalAttention(nn.Module):
     """resnet_attn.py:23-35 (parameter container)."""
 

@@ -23,6 +23,8 @@ there is no network for the ImageNet checkpoint:
   LSTMResNetOracle            audio/models/lstm_resnet_model.py:5-71
   LSTMResNetAttnOracle        audio/models/lstm_resnet_attn_model.py:17-88
   ResNet2DAttentionOracle     video/models/resnet_attn.py:38-111
+  ResNet2DTransformerOracle   video/models/resnet_trans.py:45-129
+  LSTMResNetTransOracle       audio/models/lstm_resnet_trans_model.py:22-104
   AttentionFusionACVOracle    audio_cues_video/models/{middle_fusion_mobile,middle_fusion_resnet,early_fusion_mobile,early_fusion_resnet}.py
   LateFusionAVMobileNetOracle audio_video/models/late_fusion.py:10-93
   MidFusionAVMobileNetOracle  audio_video/models/middle_fusion.py:11-85
@@ -222,6 +224,43 @@ class ResNet2DAttentionOracle(nn.Module):
 
     def forward(self, x):
         x = self.attention(self.proj_in(self.time_cnn(x))).mean(dim=1)
+        return self.fc(self.dropout(self.relu(x)))
+
+
+class ResNet2DTransformerOracle(nn.Module):
+    """video/models/resnet_trans.py:45-129: ResNet-18 per frame, proj_in, sinusoidal positions, 2-layer post-norm
+    TransformerEncoder (dim_feedforward = 4 * dim), mean over time, ReLU, Dropout, fc."""
+
+    def __init__(self, num_classes, config=None):
+        super().__init__()
+        config = config or DictConfig()
+        base = resnet18(weights=None)
+        base.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.cnn_features = nn.Sequential(*list(base.children())[:-2])
+        self.global_pool = nn.AdaptiveAvgPool2d((1, 1))
+        with torch.no_grad():                                              # :69-73
+            self.global_pool(self.cnn_features(torch.zeros(1, 3, 44, 44)))
+        self.time_cnn = _TimeDistributed(nn.Sequential(self.cnn_features, self.global_pool, nn.Flatten()))
+        dim = config.get("model.transformer_dim", 256)
+        dropout = config.get("model.dropout", 0.2)
+        self.proj_in = nn.Linear(512, dim)
+        pe = torch.zeros(200, dim)
+        pos = torch.arange(0, 200).unsqueeze(1)
+        div = torch.exp(torch.arange(0, dim, 2) * (-torch.log(torch.tensor(10000.0)) / dim))
+        pe[:, 0::2] = torch.sin(pos * div)
+        pe[:, 1::2] = torch.cos(pos * div)
+        self.pos_encoding = nn.Module()
+        self.pos_encoding.pe = pe.unsqueeze(0)
+        layer = nn.TransformerEncoderLayer(d_model=dim, nhead=config.get("model.num_heads", 4), dropout=dropout,
+                                           batch_first=True, dim_feedforward=dim * 4)
+        self.transformer = nn.TransformerEncoder(layer, num_layers=config.get("model.num_layers", 2))
+        self.dropout = nn.Dropout(dropout)
+        self.relu = nn.ReLU()
+        self.fc = nn.Linear(dim, num_classes)
+
+    def forward(self, x):
+        x = self.proj_in(self.time_cnn(x))
+        x = self.transformer(x + self.pos_encoding.pe[:, :x.size(1), :]).mean(dim=1)
         return self.fc(self.dropout(self.relu(x)))
 
 
@@ -643,6 +682,47 @@ class LSTMResNetAttnOracle(LSTMResNetOracle):
         out, _ = self.final_bilstm(self.fc(self.resnet(x1)).unsqueeze(1).repeat(1, 10, 1))
         pooled, _ = self.attention(out)
         return self.classifier(pooled)
+
+
+class LSTMResNetTransOracle(nn.Module):
+    """audio/models/lstm_resnet_trans_model.py:22-104: LSTMResNet front with fc -> transformer_dim, the projection repeated
+    over seq_len steps + positional encoding (a registered buffer), 2-layer TransformerEncoder (torch defaults:
+    dim_feedforward 2048, dropout 0.1), mean over the steps, classifier."""
+
+    def __init__(self, num_classes=40, input_size=117, transformer_dim=256, num_heads=4, num_layers=2, seq_len=10,
+                 dropout_rate=0.3, use_batchnorm=True, encoder_dropout=0.1):
+        super().__init__()
+        import numpy as np
+        self.seq_len = seq_len
+        self.initial_bilstm = nn.LSTM(input_size, 64, num_layers=2, bidirectional=True, batch_first=True)
+        self.resnet = resnet18(weights=None)
+        self.resnet.conv1 = nn.Conv2d(1, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.resnet.fc = nn.Identity()
+        layers = [nn.Linear(512, transformer_dim)]
+        if use_batchnorm:
+            layers.append(nn.BatchNorm1d(transformer_dim))
+        layers.extend([nn.ReLU(), nn.Dropout(dropout_rate)])
+        self.fc = nn.Sequential(*layers)
+        pe = torch.zeros(seq_len, transformer_dim)
+        position = torch.arange(0, seq_len).unsqueeze(1).float()
+        div_term = torch.exp(torch.arange(0, transformer_dim, 2).float() * (-np.log(10000.0) / transformer_dim))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.pos_encoder = nn.Module()
+        self.pos_encoder.register_buffer("pe", pe.unsqueeze(0))
+        layer = nn.TransformerEncoderLayer(d_model=transformer_dim, nhead=num_heads, batch_first=True, dropout=encoder_dropout)
+        self.transformer = nn.TransformerEncoder(layer, num_layers=num_layers)
+        self.classifier = nn.Linear(transformer_dim, num_classes)
+
+    def forward(self, x):
+        b = x.size(0)
+        if x.dim() == 4:
+            x = x.squeeze(1)
+        x1, _ = self.initial_bilstm(x.view(b * x.shape[1], x.shape[2]).unsqueeze(1))
+        x1 = x1.squeeze(1).view(b, 1, 80, -1)
+        seq = self.fc(self.resnet(x1)).unsqueeze(1).repeat(1, self.seq_len, 1)
+        seq = seq + self.pos_encoder.pe[:, :seq.size(1)]
+        return self.classifier(self.transformer(seq).mean(dim=1))
 
 
 class _VideoLstm(nn.Module):

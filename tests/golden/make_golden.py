@@ -223,6 +223,10 @@ def golden_models():
     torch.manual_seed(0)
     model = mod.ResNet2DAttention(C, DCfg({"model.dropout": 0.0}))
     record("video_resnet_attn", model, (video,), labels, 5e-5, 1e-5, B, T, size)
+    mod = load_ref("video", "models.resnet_trans")
+    torch.manual_seed(0)
+    model = mod.ResNet2DTransformer(C, DCfg({"model.dropout": 0.0}))
+    record("video_resnet_trans", model, (video,), labels, 5e-5, 1e-5, B, T, size)
     # audio_cues_video early / middle attention fusion; the early and middle-resnet variants freeze their backbones and
     # feed the CNN 4 time steps at a time (T = 6: one chunk of 4 and one of 2)
     cue = synthetic.make_cues(B)
@@ -271,6 +275,15 @@ def golden_models():
     torch.manual_seed(0)
     model = mod.DeepAudioNetWithAttention(num_classes=C, input_size=117, dropout_rate=0.0)
     record("audio_lstm_resnet_attn", model, (mel,), labels, 5e-4, 1e-4, B, 1, 44)
+    mod = load_ref("audio", "models.lstm_resnet_trans_model")
+    torch.manual_seed(0)
+    model = mod.LSTMResNetWithTransformer(num_classes=C, input_size=117, dropout_rate=0.0)
+    for m_ in model.modules():                               # the encoder layers' own dropout (torch default 0.1)
+        if isinstance(m_, torch.nn.Dropout):
+            m_.p = 0.0
+        if isinstance(m_, torch.nn.MultiheadAttention):
+            m_.dropout = 0.0
+    record("audio_lstm_resnet_trans", model, (mel,), labels, 5e-4, 1e-4, B, 1, 44)
     # the remaining audio_video models (av_config.yaml:10), lr 3e-4
     B, T, size, C = 3, 8, 44, 40
     for name, module, factory, drop in (("late_fusion_mobilenet", "models.late_fusion", "create_late_fusion_mobilenet_model", False),

@@ -387,3 +387,48 @@ def test_multihead_attention_kernels(K, B, T, E, heads):
     # argument errors do not launch
     assert lib.lr_mha_scores_fwd(qkv.data_ptr(), 3 * E, P.data_ptr(), B, 65, E, heads, s) == -1
     assert lib.lr_mha_scores_fwd(qkv.data_ptr(), 3 * E, P.data_ptr(), B, T, E, 3 if E % 3 else 7, s) == -1
+
+
+@pytest.mark.parametrize("rows,D,residual", [(290, 256, True), (7, 1024, False), (33, 100, True), (1, 32, True)])
+def test_layernorm_residual_and_broadcast_add(K, rows, D, residual):
+    """lr_layernorm_fwd / _bwd against nn.LayerNorm(a + b) and its autograd (norm1 / norm2 of
+    nn.TransformerEncoderLayer, video/models/resnet_trans.py:96-103); lr_add_bcast against repeat + positional add."""
+    from multimodal_lipread_b200._lib import lib, check
+    torch.manual_seed(rows + D)
+    ln = nn.LayerNorm(D)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.5, 0.5)
+    a = torch.randn(rows, D, requires_grad=True)
+    b = torch.randn(rows, D, requires_grad=True) if residual else None
+    y_ref = ln(a + b if residual else a)
+    dy_ref = torch.randn(rows, D)
+    y_ref.backward(dy_ref)
+    dev, s = "cuda", torch.cuda.current_stream().cuda_stream
+    ad, bd = a.detach().to(dev), (b.detach().to(dev) if residual else None)
+    g, be = ln.weight.detach().to(dev), ln.bias.detach().to(dev)
+    y, sm, st = torch.empty(rows, D, device=dev), torch.empty(rows, D, device=dev), torch.empty(rows, 2, device=dev)
+    check(lib.lr_layernorm_fwd(ad.data_ptr(), bd.data_ptr() if residual else None, g.data_ptr(), be.data_ptr(), ln.eps,
+                               y.data_ptr(), sm.data_ptr(), st.data_ptr(), rows, D, s))
+    _close(y.cpu(), y_ref, rtol=2e-5)
+    ds = torch.full((rows, D), float("nan"), device=dev)
+    dg, db = torch.ones(D, device=dev), torch.ones(D, device=dev)          # accumulated onto
+    dyd = dy_ref.to(dev)
+    check(lib.lr_layernorm_bwd(dyd.data_ptr(), sm.data_ptr(), st.data_ptr(), g.data_ptr(), ds.data_ptr(),
+                               dg.data_ptr(), db.data_ptr(), rows, D, s))
+    _close(ds.cpu(), a.grad, rtol=5e-5)
+    if residual:
+        assert torch.equal(a.grad, b.grad)
+    _close(dg.cpu() - 1.0, ln.weight.grad, rtol=5e-5)
+    _close(db.cpu() - 1.0, ln.bias.grad, rtol=5e-5)
+    assert lib.lr_layernorm_fwd(ad.data_ptr(), None, g.data_ptr(), be.data_ptr(), ln.eps, y.data_ptr(), sm.data_ptr(),
+                                st.data_ptr(), rows, 1025, s) == -1
+    # broadcast add
+    F, T = 5, 10
+    x, r = torch.randn(F, D), torch.randn(T, D)
+    xd, rd = x.to(dev), r.to(dev)
+    out = torch.empty(F, T, D, device=dev)
+    check(lib.lr_add_bcast(xd.data_ptr(), rd.data_ptr(), out.data_ptr(), F, T, D, s))
+    assert torch.equal(out.cpu(), x.unsqueeze(1).repeat(1, T, 1) + r)
+    check(lib.lr_add_bcast(xd.data_ptr(), None, out.data_ptr(), F, T, D, s))
+    assert torch.equal(out.cpu(), x.unsqueeze(1).repeat(1, T, 1))

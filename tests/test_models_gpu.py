@@ -140,6 +140,10 @@ def _case(name, precision="fp32"):
         ref = O.VGGLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
     elif name == "video_cnn":
         ref = O.CNNOnlyOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
+    elif name == "video_resnet_trans":
+        ref = O.ResNet2DTransformerOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
+    elif name == "audio_lstm_resnet_trans":
+        ref = O.LSTMResNetTransOracle(C, dropout_rate=0.0, encoder_dropout=0.0)
     elif name == "video_resnet_attn":
         ref = O.ResNet2DAttentionOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
     elif name == "audio_resnet_lstm":
@@ -181,6 +185,10 @@ def _case(name, precision="fp32"):
         ours = video_models.VGGLSTM(C, cfg, precision=precision)
     elif name == "video_cnn":
         ours = video_models.CNNOnly(C, cfg, precision=precision)
+    elif name == "video_resnet_trans":
+        ours = video_models.ResNet2DTransformer(C, cfg, precision=precision)
+    elif name == "audio_lstm_resnet_trans":
+        ours = audio_models.LSTMResNetWithTransformer(C, dropout_rate=0.0, encoder_dropout=0.0, precision=precision)
     elif name == "video_resnet_attn":
         ours = video_models.ResNet2DAttention(C, cfg, precision=precision)
     elif name == "audio_resnet_lstm":
@@ -247,6 +255,8 @@ def _inputs_for(name, mel, lips):
     ("video_vgg_lstm", 3, 6, 44),
     ("video_cnn", 3, 6, 44),
     ("video_resnet_attn", 3, 6, 44),
+    ("video_resnet_trans", 3, 6, 44),
+    ("audio_lstm_resnet_trans", 4, 1, 44),
     ("audio_resnet_lstm", 4, 1, 44),
     ("audio_vgg", 4, 1, 44),
     ("audio_vgg_lstm", 4, 1, 44),
@@ -315,7 +325,7 @@ def test_train_step_matches_oracle(cuda_device, name, B, T, size):
 
 
 @pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
-                                  "acv_late_fusion_resnet", "video_vgg_lstm", "video_cnn", "video_resnet_attn", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm", "audio_lstm_resnet", "audio_lstm_resnet_attn",
+                                  "acv_late_fusion_resnet", "video_vgg_lstm", "video_cnn", "video_resnet_attn", "video_resnet_trans", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm", "audio_lstm_resnet", "audio_lstm_resnet_attn", "audio_lstm_resnet_trans",
                                   "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast",
                                   "acv_middle_fusion_mobile", "acv_middle_fusion_resnet", "acv_early_fusion_mobile", "acv_early_fusion_resnet"])
 def test_golden_vectors_of_the_reference(cuda_device, golden_dir, name):

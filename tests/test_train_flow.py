@@ -52,7 +52,11 @@ def test_model_name_dispatch_and_errors():
         frozen.configure_optimizer(lr=1e-4, weight_decay=1e-5)
     with pytest.raises(ValueError, match="Unknown model name"):
         T.create_acv_model("not_a_model", 40)
-    for name in ("shufflenet_lstm", "resnet_trans"):
+    assert type(T.create_video_model("resnet_attn", 40, cfg)).__name__ == "ResNet2DAttention"
+    assert type(T.create_video_model("resnet_trans", 40, cfg)).__name__ == "ResNet2DTransformer"
+    for name in T.AUDIO_MODELS:                          # every audio model name (audio/train.py:118-134) has a plan
+        assert T.create_audio_model(name, 8, input_size=117, version=11).num_classes == 8
+    for name in ("shufflenet_lstm",):
         with pytest.raises(NotImplementedError):
             T.create_video_model(name, 40, cfg)          # a reference name without a plan fails loudly
 
