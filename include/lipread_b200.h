@@ -249,6 +249,16 @@ int lr_audio_conv_fwd(const float* x, const float* w, const float* bias, float* 
 int lr_audio_conv_bwd(const float* x, const float* dA, long long lda, const unsigned char* arg, float* dw, float* db,
                       int B, int H, int W, lr_stream_t stream);
 
+/* ShuffleNetV2 unit tail: out[rows, 2*Ch] = channel_shuffle(cat(a, b), groups = 2), i.e. out[r, 2c] = a[r*lda + c],
+ * out[r, 2c+1] = b[r*ldb + c]  (a / b may be column slices: x.chunk(2, dim=1) leaves x1 where it is); the backward
+ * de-interleaves dout into da / db (written, same strides).
+ * replaces: torchvision.models.shufflenetv2 InvertedResidual.forward / channel_shuffle as used by
+ * video/models/shufflenet_lstm.py:37-55. */
+int lr_shuffle2_fwd(const float* a, long long lda, const float* b, long long ldb, float* out, long long rows, int Ch,
+                    lr_stream_t stream);
+int lr_shuffle2_bwd(const float* dout, float* da, long long lda, float* db, long long ldb, long long rows, int Ch,
+                    lr_stream_t stream);
+
 /* nn.MultiheadAttention(embed_dim E, heads, batch_first) over the T time steps of each clip, around its in- and
  * out-projections (two lr_gemm calls): qkv is the packed in-projection [B*T, 3E] (row stride ld; q | k | v, head h in
  * columns h*d .. (h+1)*d of each section, d = E / heads), P [B, heads, T, T] the attention weights (saved for the

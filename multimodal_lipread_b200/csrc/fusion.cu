@@ -186,3 +186,63 @@ extern "C" int lr_flatten_nchw(float* x_nhwc, float* y_nchw, long long ldy, int 
     LR_CHECK_LAUNCH("flatten_kernel");
     return LR_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// ShuffleNetV2 unit tail (torchvision shufflenetv2.py InvertedResidual.forward): out = channel_shuffle(cat(a, b), 2).
+// In channels-last rows that is an interleave: out[r, 2c] = a[r, c], out[r, 2c + 1] = b[r, c]; a and b may be column
+// slices of wider matrices (x.chunk(2, dim=1) leaves x1 in place), hence the row strides.
+namespace fu {
+
+__global__ void __launch_bounds__(256)
+shuffle2_fwd_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ b, long long ldb,
+                    float* __restrict__ out, long long rows, int Ch) {
+    const long long n = rows * Ch;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const long long r = i / Ch;
+        const int c = (int)(i - r * Ch);
+        reinterpret_cast<float2*>(out)[i] = make_float2(a[r * lda + c], b[r * ldb + c]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+shuffle2_bwd_kernel(const float* __restrict__ dout, float* __restrict__ da, long long lda, float* __restrict__ db,
+                    long long ldb, long long rows, int Ch) {
+    const long long n = rows * Ch;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const long long r = i / Ch;
+        const int c = (int)(i - r * Ch);
+        const float2 g = reinterpret_cast<const float2*>(dout)[i];
+        da[r * lda + c] = g.x;
+        db[r * ldb + c] = g.y;
+    }
+}
+
+}  // namespace fu
+
+extern "C" int lr_shuffle2_fwd(const float* a, long long lda, const float* b, long long ldb, float* out, long long rows,
+                               int Ch, lr_stream_t stream) {
+    LR_CHECK_ARG(rows >= 0 && Ch > 0 && lda >= Ch && ldb >= Ch, "lr_shuffle2_fwd: bad shape");
+    if (rows == 0) return LR_OK;
+    LR_CHECK_ARG(a && b && out, "lr_shuffle2_fwd: null pointer");
+    long long g = (rows * Ch + 255) / 256;
+    const long long cap = (long long)lr::sm_count() * 8;
+    if (g > cap) g = cap;
+    fu::shuffle2_fwd_kernel<<<(unsigned)g, 256, 0, stream>>>(a, lda, b, ldb, out, rows, Ch);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("shuffle2_fwd_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_shuffle2_bwd(const float* dout, float* da, long long lda, float* db, long long ldb, long long rows, int Ch,
+                               lr_stream_t stream) {
+    LR_CHECK_ARG(rows >= 0 && Ch > 0 && lda >= Ch && ldb >= Ch, "lr_shuffle2_bwd: bad shape");
+    if (rows == 0) return LR_OK;
+    LR_CHECK_ARG(dout && da && db, "lr_shuffle2_bwd: null pointer");
+    long long g = (rows * Ch + 255) / 256;
+    const long long cap = (long long)lr::sm_count() * 8;
+    if (g > cap) g = cap;
+    fu::shuffle2_bwd_kernel<<<(unsigned)g, 256, 0, stream>>>(dout, da, lda, db, ldb, rows, Ch);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("shuffle2_bwd_kernel");
+    return LR_OK;
+}

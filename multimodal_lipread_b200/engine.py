@@ -538,6 +538,76 @@ class Plan:
             self.trace.append(cur)
         return cur
 
+    # ---- torchvision ShuffleNetV2 -----------------------------------------------------------------------------
+    def _pw_strided(self, xval, lda, xgrad, ldg, x, conv, bn, act, accumulate=False):
+        """1x1 conv + BN + act whose input is a column slice (row stride lda) of a wider activation; its input gradient
+        goes to the matching slice of that activation's gradient (written, or accumulated when another branch wrote)."""
+        Cout, Cin = conv.out_channels, conv.in_channels
+        assert conv.kernel_size == (1, 1) and conv.groups == 1 and conv.bias is None
+        raw = T2(self, x.F, x.H, x.W, Cout)
+        raw.stat_slot = self.stat_slot(Cout)
+        st = (lambda sl=raw.stat_slot: sl["fwd"]) if self.training else 0
+        self.gemm_auto(self.fwd, xval, lda, 0, conv.weight, Cin, 0, raw.val, Cout, x.rows, Cout, Cin, stats=st)
+        if self.with_backward:
+            self.linear_bwd(self.bgroup(), xval, lda, x.rows, conv.weight, None, raw.grad, Cout, dx=xgrad, ldx=ldg,
+                            dx_residual=(xgrad if accumulate else 0), ldr=ldg)
+        out = T2(self, x.F, x.H, x.W, Cout)
+        self.bn_act(raw, bn, act, out)
+        return out
+
+    def _dw_bn(self, x, conv, bn):
+        raw = self.dw_conv(x, conv)
+        out = T2(self, raw.F, raw.H, raw.W, raw.C)
+        self.bn_act(raw, bn, ACT_NONE, out)
+        return out
+
+    def shuffle_unit(self, blk, x):
+        """torchvision shufflenetv2.InvertedResidual: stride 1: cat(x1, branch2(x2)); stride 2: cat(branch1(x),
+        branch2(x)); then channel_shuffle(., 2) (an interleave of the two halves in channels-last rows)."""
+        wb = self.with_backward
+        b2 = blk.branch2
+        if blk.stride == 1:
+            C = x.C
+            bf = C // 2
+            xg = (x.grad.data_ptr() + 4 * bf) if wb else None
+            h = self._pw_strided(x.val.data_ptr() + 4 * bf, C, xg, C, x, b2[0], b2[1], ACT_RELU)
+            h = self._dw_bn(h, b2[3], b2[4])
+            right = self.pw_bn_act(h, b2[5], b2[6], ACT_RELU)
+            out = T2(self, x.F, x.H, x.W, C)
+            self.fwd.add("lr_shuffle2_fwd", x.val, C, right.val, bf, out.val, x.rows, bf)
+            if wb:
+                self.bgroup().add("lr_shuffle2_bwd", out.grad, x.grad, C, right.grad, bf, x.rows, bf)
+            return out
+        # stride 2: branch2 is registered first so that, in the reversed backward, branch1's depthwise dgrad WRITES
+        # x.grad and branch2's first 1x1 conv then accumulates onto it
+        b1 = blk.branch1
+        h = self._pw_strided(x.val, x.C, x.grad, x.C, x, b2[0], b2[1], ACT_RELU, accumulate=True)
+        h = self._dw_bn(h, b2[3], b2[4])
+        right = self.pw_bn_act(h, b2[5], b2[6], ACT_RELU)
+        l = self._dw_bn(x, b1[0], b1[1])
+        left = self.pw_bn_act(l, b1[2], b1[3], ACT_RELU)
+        bf = left.C
+        out = T2(self, left.F, left.H, left.W, 2 * bf)
+        self.fwd.add("lr_shuffle2_fwd", left.val, bf, right.val, bf, out.val, left.rows, bf)
+        if wb:
+            self.bgroup().add("lr_shuffle2_bwd", out.grad, left.grad, bf, right.grad, bf, left.rows, bf)
+        return out
+
+    def shufflenet_features(self, seq, frames):
+        """Sequential(conv1, maxpool, stage2, stage3, stage4, conv5) of torchvision shufflenet_v2_x0_5 / x1_0 on
+        frames = (tensor, layout, scale) -> last activation T2 (video/models/shufflenet_lstm.py:47-55)."""
+        conv1, mp, stages, conv5 = seq[0], seq[1], (seq[2], seq[3], seq[4]), seq[5]
+        raw = self.dense_conv(None, conv1[0], frames=frames)
+        if self.with_backward:
+            self.dense_conv_bwd(raw)
+        cur = T2(self, raw.F, raw.H, raw.W, raw.C)
+        self.bn_act(raw, conv1[1], ACT_RELU, cur)
+        cur = self.maxpool(cur, mp.kernel_size, mp.stride, mp.padding)
+        for stage in stages:
+            for blk in stage:
+                cur = self.shuffle_unit(blk, cur)
+        return self.pw_bn_act(cur, conv5[0], conv5[1], ACT_RELU)
+
     def squeeze_excite(self, se, a):
         """SqueezeExcitation: b = a * hardsigmoid(fc2(relu(fc1(mean_hw(a)))))."""
         F, HW, C = a.F, a.H * a.W, a.C

@@ -7,8 +7,7 @@ body replaced by the fused `model.train_step`:
   audio_video/train.py:57-75 (train_epoch), :78-90 (validate), :112-127 (model selection)
   video/train.py:85-114, :189-204        audio/train.py:59-84, :118-134        audio_cues_video/train.py:52-81, :144-155
 
-Model names without a launch plan yet raise NotImplementedError (they are listed in DESIGN.md section 7), so a config
-that selects one fails loudly instead of silently running something else.  Datasets / DataLoaders stay the caller's
+Every model name of the four train scripts has a launch plan; an unknown name raises the reference's ValueError.  Datasets / DataLoaders stay the caller's
 (the reference's own classes work unchanged: their items are (mel, lips, label) tuples etc.)."""
 import os
 
@@ -77,6 +76,8 @@ def create_video_model(model_name, num_classes, config):
         return M.CNNOnly(num_classes=num_classes, config=config)
     if model_name == "resnet_attn":
         return M.ResNet2DAttention(num_classes=num_classes, config=config)
+    if model_name == "shufflenet_lstm":
+        return M.ShuffleNet2DBiLSTM(num_classes=num_classes, config=config)
     if model_name == "resnet_trans":
         return M.ResNet2DTransformer(num_classes=num_classes, config=config)
     if model_name in VIDEO_MODELS:

@@ -38,7 +38,12 @@ class ResNetLstmPlan(ModelPlan):
         B, wb = self.B, self.with_backward
         video, layout, scale = self.video_input()
         T = layout[2]
-        if hasattr(m, "cnn_features"):
+        if isinstance(m, ShuffleNet2DBiLSTM):
+            last = self.shufflenet_features(m.cnn_features, (video, layout, scale))
+            lstm, drop = m.lstm, m.dropout
+            feat, dfeat = self.avgpool(last)
+            feat_dim = last.C
+        elif hasattr(m, "cnn_features"):
             last = self.resnet_features(_resnet_view(m.cnn_features), (video, layout, scale))
             lstm, drop = m.bilstm, m.dropout
             feat, dfeat = self.avgpool(last)
@@ -70,6 +75,36 @@ class ResNetLstmPlan(ModelPlan):
         if wb:
             self.linear_bwd(self.bgroup(), hd, D, B, m.fc.weight, m.fc.bias, dlogits, self.num_classes, dx=dhd, ldx=D)
         self.set_logits(logits, dlogits)
+
+
+class ShuffleNet2DBiLSTM(PlanModel):
+    """video/models/shufflenet_lstm.py:27-109 (model.name == "shufflenet_lstm")."""
+    INPUTS = ("video",)
+    PLAN = None                 # ResNetLstmPlan, set below
+    DEFAULT_LR = 5e-5
+    DEFAULT_WD = 1e-5
+
+    def __init__(self, num_classes, config=None, pretrained_state_dict=None, precision=None):
+        super().__init__()
+        config = config or Cfg()
+        self._init_base(num_classes, config, precision)
+        from torchvision.models import shufflenet_v2_x0_5, shufflenet_v2_x1_0
+        version = config.get("model.shufflenet_version", "0.5x")
+        base = shufflenet_v2_x0_5(weights=None) if version == "0.5x" else shufflenet_v2_x1_0(weights=None)
+        if pretrained_state_dict is not None:
+            base.load_state_dict(pretrained_state_dict)
+        self.cnn_features = nn.Sequential(base.conv1, base.maxpool, base.stage2, base.stage3, base.stage4, base.conv5)
+        self.global_pool = nn.AdaptiveAvgPool2d((1, 1))
+        with torch.no_grad():                                # :60-64, constructor-time pass through the train-mode CNN
+            cnn_output_dim = self.global_pool(self.cnn_features(torch.zeros(1, 3, 44, 44))).view(-1).shape[0]
+        self.time_cnn = TimeDistributed(nn.Sequential(self.cnn_features, self.global_pool, nn.Flatten()))
+        feature_dim = config.get("model.feature_dim", 512)
+        dropout = config.get("model.dropout", 0.4)
+        self.lstm = nn.LSTM(input_size=cnn_output_dim, hidden_size=feature_dim // 2, num_layers=2, batch_first=True,
+                            bidirectional=True, dropout=dropout)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+        self.fc = nn.Linear(feature_dim, num_classes)
 
 
 class ResNetAttnPlan(ModelPlan):
@@ -384,3 +419,6 @@ class CNNOnly(PlanModel):
 def create_model(num_classes, config=None):
     """video/models/resnet_lstm.py:165-177."""
     return ResNet2DBiLSTM(num_classes, config)
+
+
+ShuffleNet2DBiLSTM.PLAN = ResNetLstmPlan

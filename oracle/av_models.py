@@ -24,6 +24,7 @@ there is no network for the ImageNet checkpoint:
   LSTMResNetAttnOracle        audio/models/lstm_resnet_attn_model.py:17-88
   ResNet2DAttentionOracle     video/models/resnet_attn.py:38-111
   ResNet2DTransformerOracle   video/models/resnet_trans.py:45-129
+  ShuffleNet2DBiLSTMOracle    video/models/shufflenet_lstm.py:27-109
   LSTMResNetTransOracle       audio/models/lstm_resnet_trans_model.py:22-104
   AttentionFusionACVOracle    audio_cues_video/models/{middle_fusion_mobile,middle_fusion_resnet,early_fusion_mobile,early_fusion_resnet}.py
   LateFusionAVMobileNetOracle audio_video/models/late_fusion.py:10-93
@@ -225,6 +226,33 @@ class ResNet2DAttentionOracle(nn.Module):
     def forward(self, x):
         x = self.attention(self.proj_in(self.time_cnn(x))).mean(dim=1)
         return self.fc(self.dropout(self.relu(x)))
+
+
+class ShuffleNet2DBiLSTMOracle(nn.Module):
+    """video/models/shufflenet_lstm.py:27-109: ShuffleNetV2 (0.5x) conv1 .. conv5 per frame (constructor-time dummy
+    pass), 2-layer BiLSTM, x[:, -1] -> ReLU -> Dropout -> fc."""
+
+    def __init__(self, num_classes, config=None):
+        super().__init__()
+        from torchvision.models import shufflenet_v2_x0_5, shufflenet_v2_x1_0
+        config = config or DictConfig()
+        version = config.get("model.shufflenet_version", "0.5x")
+        base = shufflenet_v2_x0_5(weights=None) if version == "0.5x" else shufflenet_v2_x1_0(weights=None)
+        self.cnn_features = nn.Sequential(base.conv1, base.maxpool, base.stage2, base.stage3, base.stage4, base.conv5)
+        self.global_pool = nn.AdaptiveAvgPool2d((1, 1))
+        with torch.no_grad():                                              # :60-64
+            dim = self.global_pool(self.cnn_features(torch.zeros(1, 3, 44, 44))).view(-1).shape[0]
+        self.time_cnn = _TimeDistributed(nn.Sequential(self.cnn_features, self.global_pool, nn.Flatten()))
+        feature_dim = config.get("model.feature_dim", 512)
+        dropout = config.get("model.dropout", 0.4)
+        self.lstm = nn.LSTM(dim, feature_dim // 2, num_layers=2, batch_first=True, bidirectional=True, dropout=dropout)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+        self.fc = nn.Linear(feature_dim, num_classes)
+
+    def forward(self, x):
+        x, _ = self.lstm(self.time_cnn(x))
+        return self.fc(self.dropout(self.relu(x[:, -1])))
 
 
 class ResNet2DTransformerOracle(nn.Module):

@@ -223,6 +223,10 @@ def golden_models():
     torch.manual_seed(0)
     model = mod.ResNet2DAttention(C, DCfg({"model.dropout": 0.0}))
     record("video_resnet_attn", model, (video,), labels, 5e-5, 1e-5, B, T, size)
+    mod = load_ref("video", "models.shufflenet_lstm")
+    torch.manual_seed(0)
+    model = mod.ShuffleNet2DBiLSTM(C, DCfg({"model.dropout": 0.0}))
+    record("video_shufflenet_lstm", model, (video,), labels, 5e-5, 1e-5, B, T, size)
     mod = load_ref("video", "models.resnet_trans")
     torch.manual_seed(0)
     model = mod.ResNet2DTransformer(C, DCfg({"model.dropout": 0.0}))

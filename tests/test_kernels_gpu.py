@@ -432,3 +432,27 @@ def test_layernorm_residual_and_broadcast_add(K, rows, D, residual):
     assert torch.equal(out.cpu(), x.unsqueeze(1).repeat(1, T, 1) + r)
     check(lib.lr_add_bcast(xd.data_ptr(), None, out.data_ptr(), F, T, D, s))
     assert torch.equal(out.cpu(), x.unsqueeze(1).repeat(1, T, 1))
+
+
+def test_channel_shuffle_interleave(K):
+    """lr_shuffle2_fwd / _bwd against torchvision's channel_shuffle(cat(x1, branch), 2) on an NCHW tensor, with x1 a
+    column slice left in place (x.chunk(2, dim=1))."""
+    from torchvision.models.shufflenetv2 import channel_shuffle
+    from multimodal_lipread_b200._lib import lib, check
+    torch.manual_seed(3)
+    F, H, W, C = 3, 5, 4, 48
+    bf = C // 2
+    x = torch.randn(F, C, H, W)
+    right = torch.randn(F, bf, H, W)
+    ref = channel_shuffle(torch.cat((x[:, :bf], right), dim=1), 2)
+    dev, s = "cuda", torch.cuda.current_stream().cuda_stream
+    xr, rr = _cl(x).reshape(-1, C).to(dev), _cl(right).reshape(-1, bf).to(dev)
+    out = torch.empty(F * H * W, C, device=dev)
+    check(lib.lr_shuffle2_fwd(xr.data_ptr(), C, rr.data_ptr(), bf, out.data_ptr(), F * H * W, bf, s))
+    assert torch.equal(out.cpu(), _cl(ref).reshape(-1, C))
+    dout = torch.randn(F * H * W, C, device=dev)
+    dx = torch.zeros(F * H * W, C, device=dev)
+    dr = torch.empty(F * H * W, bf, device=dev)
+    check(lib.lr_shuffle2_bwd(dout.data_ptr(), dx.data_ptr(), C, dr.data_ptr(), bf, F * H * W, bf, s))
+    assert torch.equal(dx[:, :bf].cpu(), dout[:, 0::2].cpu()) and torch.equal(dr.cpu(), dout[:, 1::2].cpu())
+    assert (dx[:, bf:] == 0).all()                                     # the other half belongs to branch2's 1x1 conv

@@ -140,6 +140,8 @@ def _case(name, precision="fp32"):
         ref = O.VGGLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
     elif name == "video_cnn":
         ref = O.CNNOnlyOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
+    elif name == "video_shufflenet_lstm":
+        ref = O.ShuffleNet2DBiLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
     elif name == "video_resnet_trans":
         ref = O.ResNet2DTransformerOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
     elif name == "audio_lstm_resnet_trans":
@@ -185,6 +187,8 @@ def _case(name, precision="fp32"):
         ours = video_models.VGGLSTM(C, cfg, precision=precision)
     elif name == "video_cnn":
         ours = video_models.CNNOnly(C, cfg, precision=precision)
+    elif name == "video_shufflenet_lstm":
+        ours = video_models.ShuffleNet2DBiLSTM(C, cfg, precision=precision)
     elif name == "video_resnet_trans":
         ours = video_models.ResNet2DTransformer(C, cfg, precision=precision)
     elif name == "audio_lstm_resnet_trans":
@@ -256,6 +260,9 @@ def _inputs_for(name, mel, lips):
     ("video_cnn", 3, 6, 44),
     ("video_resnet_attn", 3, 6, 44),
     ("video_resnet_trans", 3, 6, 44),
+    # ShuffleNetV2 ends on 2x2 maps at 44 px: with 18 frames its last BatchNorms see 72 values and the REFERENCE's own
+    # fp32 gradients differ from its fp64 ones by > 3e-3 on 40 of 186 tensors; 32 frames at 88 px are well conditioned
+    ("video_shufflenet_lstm", 4, 8, 88),
     ("audio_lstm_resnet_trans", 4, 1, 44),
     ("audio_resnet_lstm", 4, 1, 44),
     ("audio_vgg", 4, 1, 44),
@@ -325,7 +332,7 @@ def test_train_step_matches_oracle(cuda_device, name, B, T, size):
 
 
 @pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
-                                  "acv_late_fusion_resnet", "video_vgg_lstm", "video_cnn", "video_resnet_attn", "video_resnet_trans", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm", "audio_lstm_resnet", "audio_lstm_resnet_attn", "audio_lstm_resnet_trans",
+                                  "acv_late_fusion_resnet", "video_vgg_lstm", "video_cnn", "video_resnet_attn", "video_resnet_trans", "video_shufflenet_lstm", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm", "audio_lstm_resnet", "audio_lstm_resnet_attn", "audio_lstm_resnet_trans",
                                   "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast",
                                   "acv_middle_fusion_mobile", "acv_middle_fusion_resnet", "acv_early_fusion_mobile", "acv_early_fusion_resnet"])
 def test_golden_vectors_of_the_reference(cuda_device, golden_dir, name):
@@ -351,7 +358,7 @@ def test_golden_vectors_of_the_reference(cuda_device, golden_dir, name):
     close = np.isclose(gn, ref_gn, rtol=3e-3, atol=3e-6)
     # MobileNetV2 at 18 frames: 41 % of the REFERENCE's own fp32 gradient tensors differ from its fp64 ones by
     # more than 3e-3 (scratch/cond_check4.py); the other models are well conditioned
-    frac = 0.5 if name in ("acv_late_fusion_mobile", "video_mobilenet_lstm", "acv_middle_fusion_mobile") else 0.06
+    frac = 0.5 if name in ("acv_late_fusion_mobile", "video_mobilenet_lstm", "acv_middle_fusion_mobile", "video_shufflenet_lstm") else 0.06
     sd = ours.state_dict()
     assert [int(v) for k, v in sd.items() if k.endswith("num_batches_tracked")] == mg[f"{name}_nbt"].tolist()
     np.testing.assert_allclose([v.double().sum().item() for k, v in sd.items() if k.endswith("running_mean")],

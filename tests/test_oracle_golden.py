@@ -114,7 +114,7 @@ def models_golden(golden_dir):
 
 
 @pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
-                                  "acv_late_fusion_resnet", "video_vgg_lstm", "video_cnn", "video_resnet_attn", "video_resnet_trans", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm", "audio_lstm_resnet", "audio_lstm_resnet_attn", "audio_lstm_resnet_trans",
+                                  "acv_late_fusion_resnet", "video_vgg_lstm", "video_cnn", "video_resnet_attn", "video_resnet_trans", "video_shufflenet_lstm", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm", "audio_lstm_resnet", "audio_lstm_resnet_attn", "audio_lstm_resnet_trans",
                                   "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast",
                                   "acv_middle_fusion_mobile", "acv_middle_fusion_resnet", "acv_early_fusion_mobile", "acv_early_fusion_resnet"])
 def test_model_oracles_match_reference(models_golden, name):
@@ -133,6 +133,8 @@ def test_model_oracles_match_reference(models_golden, name):
         model, lr, wd = O.VGGLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}})), 5e-5, 1e-5
     elif name == "video_cnn":
         model, lr, wd = O.CNNOnlyOracle(C, O.DictConfig({"model": {"dropout": 0.0}})), 5e-5, 1e-5
+    elif name == "video_shufflenet_lstm":
+        model, lr, wd = O.ShuffleNet2DBiLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}})), 5e-5, 1e-5
     elif name == "video_resnet_trans":
         model, lr, wd = O.ResNet2DTransformerOracle(C, O.DictConfig({"model": {"dropout": 0.0}})), 5e-5, 1e-5
     elif name == "audio_lstm_resnet_trans":
@@ -175,7 +177,7 @@ def test_model_oracles_match_reference(models_golden, name):
     mel = AudioProcessorPort().batch_frontend_loop(wav)
     video = lips_u8_to_model_input(synthetic.make_lips_u8(B, size=size)[:, :T].contiguous())
     labels = synthetic.make_labels(B, C)
-    inputs = {"video_resnet_lstm": (video,), "video_mobilenet_lstm": (video,), "video_vgg_lstm": (video,), "video_cnn": (video,), "video_resnet_attn": (video,), "video_resnet_trans": (video,), "audio_lstm_resnet_trans": (mel,),
+    inputs = {"video_resnet_lstm": (video,), "video_mobilenet_lstm": (video,), "video_vgg_lstm": (video,), "video_cnn": (video,), "video_resnet_attn": (video,), "video_resnet_trans": (video,), "video_shufflenet_lstm": (video,), "audio_lstm_resnet_trans": (mel,),
               "audio_resnet": (mel,), "audio_resnet_lstm": (mel,), "audio_vgg": (mel,), "audio_vgg_lstm": (mel,), "audio_lstm_resnet": (mel,), "audio_lstm_resnet_attn": (mel,),
               "acv_late_fusion_mobile": (mel, synthetic.make_cues(B), video),
               "acv_late_fusion_resnet": (mel, synthetic.make_cues(B), video)}.get(name, (mel, video))

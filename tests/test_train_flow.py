@@ -56,9 +56,10 @@ def test_model_name_dispatch_and_errors():
     assert type(T.create_video_model("resnet_trans", 40, cfg)).__name__ == "ResNet2DTransformer"
     for name in T.AUDIO_MODELS:                          # every audio model name (audio/train.py:118-134) has a plan
         assert T.create_audio_model(name, 8, input_size=117, version=11).num_classes == 8
-    for name in ("shufflenet_lstm",):
-        with pytest.raises(NotImplementedError):
-            T.create_video_model(name, 40, cfg)          # a reference name without a plan fails loudly
+    for name in T.VIDEO_MODELS:                          # every video model name (video/train.py:189-204) has a plan
+        assert T.create_video_model(name, 40, cfg).num_classes == 40
+    with pytest.raises(ValueError, match="Unknown model"):
+        T.create_video_model("not_a_model", 40, cfg)
 
 
 def test_models_refuse_cpu_tensors():
