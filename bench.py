@@ -213,7 +213,8 @@ def main():
                               f"(29x{args.size}x{args.size} lips, 1.25 s 16 kHz audio)",
                   "batch_per_gpu": batch, "global_batch": batch * world, "num_classes": args.classes,
                   "lip_size": args.size, "grayscale_replicated": True, "parallelism": f"dp{world}",
-                  "l2": "ring of input batches larger than L2"}
+                  "l2": "ring of input batches larger than L2",
+                  "e2e_pipeline": "H2D of step i+1 (copy stream) overlaps step i; loss read back and host-synced every step"}
     cfg = {"num_classes": args.classes, "size": args.size, "grayscale": True, "cpu_batch": min(batch, 32),
            "model": "mid_fusion_fast" if workload in ("av_train", "logmel") else workload}
 

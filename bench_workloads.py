@@ -148,7 +148,11 @@ class AvTrainWorkload:
             t.append(synthetic.make_labels(batch, cfg["num_classes"], seed=g * 100 + 77 + i).pin_memory())
             self.host.append(tuple(t))
         self.devb = [tuple(x.to(dev) for x in t) for t in self.host]
-        self.stage = tuple(torch.empty_like(t) for t in self.devb[0])
+        # e2e: two staging sets; the next batch's H2D runs on a copy stream while the current step computes
+        self.stages = [tuple(torch.empty_like(t) for t in self.devb[0]) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.staged = [torch.cuda.Event() for _ in range(2)]
+        self.prefetched = None
         self.i = 0
         self.loss_host = torch.zeros(1).pin_memory()
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host[0])
@@ -183,14 +187,31 @@ class AvTrainWorkload:
         self.i += 1
         return self._step(*t)
 
+    def _prefetch(self, i):
+        """H2D of batch i from pinned host memory into staging set i % 2, on the copy stream."""
+        k = i % 2
+        with torch.cuda.stream(self.copy_stream):
+            for dst, src in zip(self.stages[k], self.host[i % self.ring]):
+                dst.copy_(src, non_blocking=True)
+            self.staged[k].record(self.copy_stream)
+        self.prefetched = i
+
     def step_e2e(self):
-        t = self.host[self.i % self.ring]
+        """One step from HOST buffers: every step's inputs cross PCIe from pinned memory and its loss is read back
+        (host sync) inside the timed region; the copy of step i+1 is issued before step i's loss is awaited, so it
+        overlaps the compute the way a prefetching loader (data.DeviceBatchLoader) does."""
+        i = self.i
         self.i += 1
-        for dst, src in zip(self.stage, t):
-            dst.copy_(src, non_blocking=True)
-        loss = self._step(*self.stage)
+        cur = torch.cuda.current_stream()
+        if self.prefetched != i:
+            self.copy_stream.wait_stream(cur)
+            self._prefetch(i)
+        cur.wait_event(self.staged[i % 2])
+        loss = self._step(*self.stages[i % 2])          # train_step copies the inputs into the plan's own buffers
+        self._prefetch(i + 1)                           # set (i+1) % 2 was last read by step i-1, host-synced below
+
         self.loss_host.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        cur.synchronize()
         return self.loss_host
 
     def files_e2e(self, n_batches=16, workers=4):
