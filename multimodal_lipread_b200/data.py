@@ -90,6 +90,124 @@ class GLipsMultimodalDataset:
         return s["audio_path"], s["video_path"], s["label"]
 
 
+class GLipsDataset:
+    """Sample list of the audio-only dataset (audio/data_utils/dataset.py:11-40, audio_cues_video/data_utils/
+    audio_data.py:11-37): classes = sorted sub-directories, one sample per `<class>/<split>/*<audio_ext>` in
+    os.listdir order.  The loader yields (mel, label)."""
+
+    def __init__(self, root_dir, input_size, split="train", transform=None, audio_ext=".m4a"):
+        if transform is not None:
+            raise NotImplementedError("host-side transforms are not part of the device input path")
+        self.root_dir, self.input_size, self.split = root_dir, input_size, split
+        self.input_size_audio = input_size
+        self.class_dir = os.path.join(root_dir, "lipread_files")
+        self.classes = sorted(e.name for e in os.scandir(self.class_dir) if e.is_dir())
+        self.class_to_idx = {c: i for i, c in enumerate(self.classes)}
+        self.samples = []
+        for word in self.classes:
+            word_dir = os.path.join(self.class_dir, word, split)
+            if os.path.exists(word_dir):
+                for f in os.listdir(word_dir):
+                    if f.endswith(audio_ext):
+                        self.samples.append({"audio_path": os.path.join(word_dir, f), "label": self.class_to_idx[word]})
+
+    def __len__(self):
+        return len(self.samples)
+
+    def paths(self, idx):
+        s = self.samples[idx]
+        return s["audio_path"], None, s["label"]
+
+
+class MultimodalTripleDataset:
+    """Sample list of audio_cues_video/data_utils/dataset.py:19-205: audio samples (the source of labels) strictly
+    aligned with cue descriptions and lip-region files by (word, sequence id "dddd-dddd", split); RuntimeError for
+    duplicate lip files and for an empty alignment, as the reference raises them.  Cue embeddings come from the
+    reference's own cache file `<cache_dir>/<cue_mode>_<md5 of the descriptions>.npz` when it exists, otherwise from
+    `embedder(list_of_descriptions) -> (n, dim) array` (SentenceTransformer.encode in the reference, :207-221; the
+    text encoder itself is outside the path).  The loader yields (mel, cue, lips, label) like collate_fn_triple (:279-284).
+    Known deviation: the reference divides a clip by 255 only `if arr.max() > 1.0` (:256-258); the device path always
+    divides uint8 frames, which differs for clips whose every pixel is 0 or 1."""
+
+    def __init__(self, root_dir, cue_root, lip_regions_root, input_size=117, split="train", cue_mode="emotion",
+                 cache_dir=".cache_cues", embedder=None, audio_ext=".m4a"):
+        import hashlib
+        import json
+        import pathlib
+        import re
+        sid_regex = re.compile(r"\d{4}-\d{4}")
+        self.split = split.lower()
+        self.cue_root, self.cue_mode, self.cache_dir = cue_root, cue_mode, cache_dir
+        self.audio_ds = GLipsDataset(root_dir, input_size, split=self.split, audio_ext=audio_ext)
+        self.input_size_audio = input_size
+        self.classes, self.class_to_idx = self.audio_ds.classes, self.audio_ds.class_to_idx
+        # cues (:72-97)
+        folder = os.path.join(cue_root, f"Descriptions_{cue_mode.capitalize()}")
+        self.cues = {}
+        for file in os.listdir(folder):
+            if self.split not in file.lower():
+                continue
+            with open(os.path.join(folder, file), "r") as f:
+                for entry in json.load(f):
+                    self.cues[(entry["word"], entry["sequence_id"], self.split)] = entry["description"]
+        # lip-region index (:102-144)
+        self.video_index = {}
+        for npy_file in pathlib.Path(lip_regions_root).rglob("*.npy"):
+            m = sid_regex.search(npy_file.name)
+            if not m:
+                continue
+            parts = [p.lower() for p in npy_file.parts]
+            if self.split not in parts:
+                continue
+            word = next((c for c in self.classes if c.lower() in parts), None)
+            if word is None:
+                continue
+            key = (word, m.group(), self.split)
+            if key in self.video_index:
+                raise RuntimeError(f"Duplicate video entries for {key}:\n  Existing: {self.video_index[key]}\n  New:      {npy_file}")
+            self.video_index[key] = str(npy_file)
+        # strict alignment (:150-205)
+        self.samples = []
+        for s in self.audio_ds.samples:
+            m = sid_regex.search(s["audio_path"])
+            if not m:
+                continue
+            word = self.classes[s["label"]]
+            key = (word, m.group(), self.split)
+            if key not in self.cues or key not in self.video_index:
+                continue
+            self.samples.append({"audio_path": s["audio_path"], "label": s["label"], "word": word, "sid": m.group(),
+                                 "desc": self.cues[key], "lip_path": self.video_index[key]})
+        if len(self.samples) == 0:
+            raise RuntimeError("No aligned samples were built. Check folder structure and naming!")
+        # embeddings (:207-221)
+        descs = sorted(set(s["desc"] for s in self.samples))
+        sig = hashlib.md5("".join(descs).encode()).hexdigest()
+        cache = os.path.join(cache_dir, f"{cue_mode}_{sig}.npz")
+        if os.path.exists(cache):
+            d = np.load(cache, allow_pickle=True)
+            self.desc2vec = dict(zip(d["desc"], d["emb"]))
+        elif embedder is not None:
+            emb = np.asarray(embedder(descs))
+            os.makedirs(cache_dir, exist_ok=True)
+            np.savez(cache, desc=descs, emb=emb)
+            self.desc2vec = dict(zip(descs, emb))
+        else:
+            raise FileNotFoundError(f"no cached cue embeddings at {cache} and no embedder given "
+                                    "(the reference computes them with sentence-transformers)")
+        self.cue_dim = int(np.asarray(next(iter(self.desc2vec.values()))).shape[0])
+
+    def __len__(self):
+        return len(self.samples)
+
+    def paths(self, idx):
+        s = self.samples[idx]
+        return s["audio_path"], s["lip_path"], s["label"]
+
+    def cue(self, idx):
+        return np.asarray(self.desc2vec[self.samples[idx]["desc"]], dtype=np.float32)
+
+
 # ---------------------------------------------------------------------------------------------- file readers
 def npy_header(f):
     """Parse a .npy header from an open binary file -> (dtype, fortran_order, shape); leaves f at the payload."""
@@ -151,11 +269,12 @@ class HostSlot:
     """One ring slot of host staging memory: frames uint8 [B,T,H,W,3], packed PCM int16 [B, cap] and per-clip
     metadata.  Pinned when CUDA is there (async H2D), plain memory otherwise (host-logic tests)."""
 
-    def __init__(self, batch, frame_shape, with_audio, max_channels, pin):
+    def __init__(self, batch, frame_shape, with_audio, max_channels, pin, cue_dim=0):
         def buf(shape, dtype):
             t = torch.empty(shape, dtype=dtype)
             return t.pin_memory() if pin else t
-        self.frames = buf((batch,) + tuple(frame_shape), torch.uint8)
+        self.frames = buf((batch,) + tuple(frame_shape), torch.uint8) if frame_shape is not None else None
+        self.cues = buf((batch, cue_dim), torch.float32) if cue_dim else None
         self.labels = buf((batch,), torch.int64)
         self.cap = (TARGET_SAMPLES * max_channels + 7) // 8 * 8          # 16-byte aligned clip starts
         self.with_audio = with_audio
@@ -175,9 +294,12 @@ class HostSlot:
 
         def c_paths(paths):
             return (ctypes.c_char_p * n)(*[os.fsencode(p) for p in paths])
-        shape = (ctypes.c_longlong * (self.frames.dim() - 1))(*self.frames.shape[1:])
-        check(lib.lr_host_read_npy_u8(c_paths([it[1] for it in items]), n, self.frames.data_ptr(), shape,
-                                      self.frames.dim() - 1, n_threads))
+        if self.frames is not None:
+            shape = (ctypes.c_longlong * (self.frames.dim() - 1))(*self.frames.shape[1:])
+            check(lib.lr_host_read_npy_u8(c_paths([it[1] for it in items]), n, self.frames.data_ptr(), shape,
+                                          self.frames.dim() - 1, n_threads))
+        if self.cues is not None:
+            self.cues[:n] = torch.from_numpy(np.stack([it[3] for it in items]))
         self.labels[:n] = torch.tensor([int(it[2]) for it in items], dtype=torch.int64)
         if not self.with_audio:
             return None
@@ -223,6 +345,8 @@ class DeviceBatchLoader:
     """DataLoader replacement for the reference's datasets whose batches arrive in HBM ready for the models:
       GLipsMultimodalDataset -> (mel (B,80,n_out) f32, lips (B,T,H,W,3) uint8, labels (B,) i64)   [dataset_av.py:77]
       VisualDataset          -> {"lip_regions": lips uint8, "label": labels}                      [dataset_loader.py:98-101]
+      GLipsDataset           -> (mel, labels)                                                      [audio/data_utils/dataset.py:52]
+      MultimodalTripleDataset -> (mel, cue (B,dim) f32, lips uint8, labels)     [audio_cues_video/data_utils/dataset.py:273-284]
     `depth` batches are in flight: worker threads fill pinned slots while the copy stream uploads the previous one
     and runs the audio kernels.  A yielded batch stays valid until `depth - 1` further batches have been taken."""
 
@@ -235,20 +359,26 @@ class DeviceBatchLoader:
         if self.device.type != "cuda":
             raise NotImplementedError("DeviceBatchLoader feeds the GPU path; there is no CPU frontend here")
         self.depth = max(2, int(depth))
-        self.with_audio = isinstance(dataset, GLipsMultimodalDataset)
+        a0, v0, _ = dataset.paths(0)
+        self.with_audio, self.with_video = a0 is not None, v0 is not None
+        self.cue_dim = int(getattr(dataset, "cue_dim", 0))
         self.n_out = int(dataset.input_size_audio) if self.with_audio else 0
         self.decoder = audio_decoder or decode_pcm16
         self.gen = torch.Generator().manual_seed(seed)
-        with open(dataset.paths(0)[1], "rb") as f:
-            dtype, fortran, self.frame_shape = npy_header(f)
-        if len(self.frame_shape) != 4 or self.frame_shape[3] != 3:
-            raise ValueError(f"lip regions must be (T, H, W, 3), got {self.frame_shape}")
+        self.frame_shape = None
+        if self.with_video:
+            with open(v0, "rb") as f:
+                dtype, fortran, self.frame_shape = npy_header(f)
+            if len(self.frame_shape) != 4 or self.frame_shape[3] != 3:
+                raise ValueError(f"lip regions must be (T, H, W, 3), got {self.frame_shape}")
         self.workers = int(workers)
         self.pool = ThreadPoolExecutor(max_workers=self.depth)        # one staging job per ring slot in flight
-        self.slots = [HostSlot(self.batch_size, self.frame_shape, self.with_audio, max_channels, pin=True)
+        self.slots = [HostSlot(self.batch_size, self.frame_shape, self.with_audio, max_channels, pin=True, cue_dim=self.cue_dim)
                       for _ in range(self.depth)]
         B = self.batch_size
-        self.dev = [dict(frames=torch.empty((B,) + self.frame_shape, dtype=torch.uint8, device=self.device),
+        self.dev = [dict(frames=(torch.empty((B,) + self.frame_shape, dtype=torch.uint8, device=self.device)
+                                 if self.with_video else None),
+                         cues=torch.empty(B, self.cue_dim, dtype=torch.float32, device=self.device) if self.cue_dim else None,
                          labels=torch.empty(B, dtype=torch.int64, device=self.device),
                          pcm=torch.empty(B, self.slots[0].cap, dtype=torch.int16, device=self.device) if self.with_audio else None,
                          meta=torch.empty(3, B, dtype=torch.int64, device=self.device) if self.with_audio else None,
@@ -263,7 +393,8 @@ class DeviceBatchLoader:
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
     def _stage(self, slot, idxs):
-        return self.pool.submit(slot.stage_batch, [self.ds.paths(i) for i in idxs], self.decoder, self.workers)
+        items = [self.ds.paths(i) + ((self.ds.cue(i),) if self.cue_dim else ()) for i in idxs]
+        return self.pool.submit(slot.stage_batch, items, self.decoder, self.workers)
 
     def _upload(self, k, futures):
         """Slot k: wait for its files, then (copy stream) H2D + pcm_ingest + log-mel; returns the device batch."""
@@ -275,7 +406,10 @@ class DeviceBatchLoader:
         dev["free"].record(cur)                      # consumer work enqueued so far may still read older batches
         self.copy_stream.wait_event(dev["free"])
         with torch.cuda.stream(self.copy_stream):
-            dev["frames"][:n].copy_(slot.frames[:n], non_blocking=True)
+            if self.with_video:
+                dev["frames"][:n].copy_(slot.frames[:n], non_blocking=True)
+            if self.cue_dim:
+                dev["cues"][:n].copy_(slot.cues[:n], non_blocking=True)
             dev["labels"][:n].copy_(slot.labels[:n], non_blocking=True)
             mel = None
             if self.with_audio:
@@ -287,11 +421,16 @@ class DeviceBatchLoader:
                 mel = ops.logmel(wav, self.ap.plan, self.n_out, 0)
             dev["ready"].record(self.copy_stream)
         cur.wait_event(dev["ready"])
-        frames, labels = dev["frames"][:n], dev["labels"][:n]
+        frames = dev["frames"][:n] if self.with_video else None
+        labels = dev["labels"][:n]
         if mel is not None:
             mel.record_stream(cur)                   # allocated on the copy stream, consumed on the caller's
-        if self.with_audio:
+        if self.cue_dim:
+            return mel, dev["cues"][:n], frames, labels
+        if self.with_audio and self.with_video:
             return mel, frames, labels
+        if self.with_audio:
+            return mel, labels
         return {"lip_regions": frames, "label": labels}
 
     def __iter__(self):

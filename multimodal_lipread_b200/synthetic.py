@@ -93,3 +93,57 @@ def write_dataset_tree(root, classes=("aufgaben", "besser", "danke"), per_split=
                 if has_lips and has_audio:
                     truth[f"{cname}/{split}/{base}"] = (pcm, lips, ci)
     return truth
+
+
+def write_triple_tree(root, classes=("aufgaben", "besser", "danke"), per_split=None, T=5, size=12, seed=131, audio_ext=".m4a"):
+    """A tiny tree for the audio + cue + video dataset (audio_cues_video/data_utils/dataset.py:19-205):
+      <root>/GLips/lipread_files/<word>/<split>/<word>_<sid>.m4a            int16 PCM (.npy payload, see write_dataset_tree)
+      <root>/lips/<word>/<split>/<word>_<sid>.npy                           uint8 (T, size, size, 3)
+      <root>/cues/Descriptions_Emotion/cues_<split>.json                    [{"word", "sequence_id", "description"}]
+    with sid = "dddd-dddd".  Some clips lack a cue, some a lip file, one audio file has no sequence id in its name.
+    Returns (glips_root, cue_root, lip_root)."""
+    import json
+    import os
+    import numpy as np
+    per_split = per_split or {"train": 5, "val": 2}
+    g = torch.Generator().manual_seed(seed)
+    glips, cue_root, lip_root = os.path.join(root, "GLips"), os.path.join(root, "cues"), os.path.join(root, "lips")
+    os.makedirs(os.path.join(cue_root, "Descriptions_Emotion"), exist_ok=True)
+    moods = ("calm", "tense", "happy", "tired", "angry")
+    k = 0
+    for split, n in per_split.items():
+        entries = []
+        for cname in sorted(classes):
+            adir = os.path.join(glips, "lipread_files", cname, split)
+            ldir = os.path.join(lip_root, cname, split)
+            os.makedirs(adir, exist_ok=True)
+            os.makedirs(ldir, exist_ok=True)
+            for i in range(n):
+                k += 1
+                sid = f"{1000 + k:04d}-{2000 + 7 * k:04d}"
+                base = f"{cname}_{sid}" if k % 7 else f"{cname}_nosid{k}"
+                pcm = torch.round(3000.0 * torch.randn(int(torch.randint(9000, 26000, (1,), generator=g)), generator=g))
+                with open(os.path.join(adir, base + audio_ext), "wb") as f:
+                    np.save(f, pcm.clamp(-32768, 32767).to(torch.int16).numpy())
+                if k % 5 != 0:
+                    np.save(os.path.join(ldir, base + ".npy"),
+                            torch.randint(0, 256, (T, size, size, 3), generator=g, dtype=torch.uint8).numpy())
+                if k % 4 != 0:
+                    entries.append({"word": cname, "sequence_id": sid,
+                                    "description": f"The speaker sounds {moods[k % len(moods)]} saying {cname}."})
+        with open(os.path.join(cue_root, "Descriptions_Emotion", f"cues_{split}.json"), "w") as f:
+            json.dump(entries, f)
+    return glips, cue_root, lip_root
+
+
+def fake_sentence_embedding(descs, dim=768):
+    """Deterministic stand-in for SentenceTransformer.encode (the embedder itself is out of scope): unit vectors
+    seeded by the text."""
+    import hashlib
+    import numpy as np
+    out = np.empty((len(descs), dim), dtype=np.float32)
+    for i, d in enumerate(descs):
+        rng = np.random.default_rng(int(hashlib.md5(d.encode()).hexdigest()[:8], 16))
+        v = rng.standard_normal(dim).astype(np.float32)
+        out[i] = v / np.linalg.norm(v)
+    return out

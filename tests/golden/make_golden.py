@@ -358,6 +358,37 @@ def golden_dataset():
                 out[f"vsum|{key}"] = np.array(item["lip_regions"].double().sum().item())
             out[f"keys_video|{split}"] = np.array(sorted(vkeys))
             out[f"classes|{split}"] = np.array(vds.classes)
+        # audio + cue + video: the reference's MultimodalTripleDataset with SentenceTransformer stubbed by the seeded
+        # fake embedder (the text encoder is outside the path) and the same fake m4a decode
+        st = types.ModuleType("sentence_transformers")
+
+        class FakeST:
+            def __init__(self, *a, **k):
+                pass
+
+            def encode(self, descs, show_progress_bar=False):
+                return synthetic.fake_sentence_embedding(list(descs))
+        st.SentenceTransformer = FakeST
+        sys.modules["sentence_transformers"] = st
+        glips, cue_root, lip_root = synthetic.write_triple_tree(os.path.join(tmp, "triple"))
+        load_ref("audio_cues_video", "utils.audio_processor")
+        sys.path.insert(0, os.path.join(REF, "audio_cues_video", "data_utils"))     # dataset.py does `from audio_data import`
+        tmod = importlib.import_module("data_utils.dataset")
+        sys.modules["utils.audio_processor"].AudioSegment = FakeSegment
+        for split in ("train", "val"):
+            ds = tmod.MultimodalTripleDataset(glips, cue_root, lip_root, 117, split=split,
+                                              cache_dir=os.path.join(tmp, "cache"))
+            keys = []
+            for i in range(len(ds)):
+                mel, cue, lip, label = ds[i]
+                key = f"{ds.samples[i]['word']}/{split}/{ds.samples[i]['sid']}"
+                keys.append(key)
+                out[f"tmel|{key}"], out[f"tcue|{key}"] = mel.numpy(), cue.numpy()
+                out[f"tlipsum|{key}"] = np.array(lip.double().sum().item())
+                out[f"tlabel|{key}"] = np.array(int(label))
+            out[f"keys_triple|{split}"] = np.array(sorted(keys))
+            batch = tmod.collate_fn_triple([ds[i] for i in range(min(2, len(ds)))])
+            out[f"collate_shapes|{split}"] = np.array([list(t.shape) + [0] * (5 - t.dim()) for t in batch])
     np.savez_compressed(os.path.join(HERE, "dataset_golden.npz"), **out)
     print("dataset golden:", {k: v.tolist() for k, v in out.items() if k.startswith("keys_av")})
 

@@ -125,7 +125,7 @@ def test_loader_feeds_the_train_step(cuda_device, tmp_path):
         items = [ods.getitem_multimodal(s, lambda p: np.load(p)) for s in ds.samples]
         rlogits = ref(torch.stack([i[0] for i in items]), torch.stack([i[1] for i in items]))
         rl = torch.nn.functional.cross_entropy(rlogits, torch.stack([i[2] for i in items]))
-        assert abs(float(loss) - float(rl)) < 5e-4 * max(1.0, abs(float(rl)))
+        assert abs(float(loss) - float(rl.detach())) < 5e-4 * max(1.0, abs(float(rl.detach())))
         assert (logits.cpu() - rlogits.detach()).abs().max() < 5e-3 * rlogits.abs().max()
         n += 1
     assert n == 1
@@ -185,3 +185,38 @@ def test_fit_run_checkpoints_logs_and_resume_interop(cuda_device, tmp_path):
     assert (back["state"][0]["exp_avg"].cpu() - m_ref).abs().max() <= 1e-3 * m_ref.abs().max() + 1e-7
     for ld in loaders:
         ld.close()
+
+
+def test_triple_and_audio_loaders_match_the_reference_items(cuda_device, golden_dir, tmp_path):
+    """(mel, cue, lips, label) batches of the audio + cue + video dataset and (mel, label) batches of the audio-only
+    one, against the items of the reference's own MultimodalTripleDataset (collate_fn_triple layout)."""
+    golden = np.load(os.path.join(golden_dir, "dataset_golden.npz"))
+    glips, cue_root, lip_root = synthetic.write_triple_tree(str(tmp_path / "triple"))
+    for split in ("train", "val"):
+        ds = data.MultimodalTripleDataset(glips, cue_root, lip_root, 117, split, cache_dir=str(tmp_path / "cache"),
+                                          embedder=synthetic.fake_sentence_embedding)
+        loader = data.DeviceBatchLoader(ds, 4, device=cuda_device, audio_decoder=_decode, workers=2)
+        i = 0
+        for mel, cue, lips, labels in loader:
+            assert cue.shape[1] == 768 and lips.dtype == torch.uint8 and mel.shape[1:] == (80, 117)
+            mel_h, cue_h, lips_h, lab_h = mel.cpu(), cue.cpu(), lips.cpu(), labels.cpu()
+            for j in range(lab_h.numel()):
+                s = ds.samples[i]
+                k = f"{s['word']}/{split}/{s['sid']}"
+                ref = golden[f"tmel|{k}"]
+                assert np.abs(mel_h[j].numpy() - ref).max() <= 2e-4 * np.abs(ref).max()
+                assert np.array_equal(cue_h[j].numpy(), golden[f"tcue|{k}"])
+                assert (lips_h[j].double() / 255.0).sum().item() == pytest.approx(float(golden[f"tlipsum|{k}"]), rel=1e-6)
+                assert int(lab_h[j]) == int(golden[f"tlabel|{k}"])
+                i += 1
+        assert i == len(ds) == len(golden[f"keys_triple|{split}"])
+        loader.close()
+    ads = data.GLipsDataset(glips, 117, "train")
+    n = 0
+    al = data.DeviceBatchLoader(ads, 8, device=cuda_device, audio_decoder=_decode)
+    for mel, labels in al:
+        assert mel.shape[1:] == (80, 117) and torch.isfinite(mel).all()
+        assert labels.tolist() == [s["label"] for s in ads.samples[n:n + labels.numel()]]
+        n += labels.numel()
+    assert n == len(ads)
+    al.close()

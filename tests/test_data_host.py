@@ -182,3 +182,53 @@ def test_batch_order_and_loader_needs_the_gpu(tree):
         data.DeviceBatchLoader(ds, 4, device="cpu")
     with pytest.raises(RuntimeError, match="empty"):
         data.DeviceBatchLoader(data.GLipsMultimodalDataset(root, 117, "test"), 4)
+
+
+@pytest.fixture(scope="module")
+def triple_tree(tmp_path_factory):
+    return synthetic.write_triple_tree(str(tmp_path_factory.mktemp("triple")))
+
+
+@pytest.mark.parametrize("split", ["train", "val"])
+def test_triple_dataset_alignment_and_items_match_the_reference(triple_tree, golden, tmp_path, split):
+    """audio + cue + video: sample alignment, cue vectors and items equal what the reference's
+    MultimodalTripleDataset produced (golden), for the oracle port and for data.MultimodalTripleDataset."""
+    glips, cue_root, lip_root = triple_tree
+    classes, aligned = ods.scan_triple(glips, cue_root, lip_root, split)
+    want = golden[f"keys_triple|{split}"].tolist()
+    assert sorted(f"{s['word']}/{split}/{s['sid']}" for s in aligned) == want
+    ds = data.MultimodalTripleDataset(glips, cue_root, lip_root, 117, split, cache_dir=str(tmp_path / "cache"),
+                                      embedder=synthetic.fake_sentence_embedding)
+    assert ds.samples == aligned and ds.classes == classes and ds.cue_dim == 768
+    for i, s in enumerate(aligned):
+        k = f"{s['word']}/{split}/{s['sid']}"
+        mel, cue, lip, label = ods.getitem_triple(s, ds.desc2vec, _decode)
+        assert np.abs(mel.numpy() - golden[f"tmel|{k}"]).max() < 1e-5
+        assert np.array_equal(cue.numpy(), golden[f"tcue|{k}"]) and np.array_equal(ds.cue(i), golden[f"tcue|{k}"])
+        assert lip.double().sum().item() == float(golden[f"tlipsum|{k}"]) and int(label) == int(golden[f"tlabel|{k}"])
+        assert ds.paths(i) == (s["audio_path"], s["lip_path"], s["label"])
+    # the second construction finds the cache the first one wrote (the reference's file name and layout)
+    again = data.MultimodalTripleDataset(glips, cue_root, lip_root, 117, split, cache_dir=str(tmp_path / "cache"))
+    assert all(np.array_equal(again.desc2vec[d], ds.desc2vec[d]) for d in ds.desc2vec)
+    with pytest.raises(FileNotFoundError, match="embedder"):
+        data.MultimodalTripleDataset(glips, cue_root, lip_root, 117, split, cache_dir=str(tmp_path / "empty"))
+
+
+def test_triple_dataset_error_conventions(triple_tree, tmp_path):
+    import shutil
+    glips, cue_root, lip_root = triple_tree
+    with pytest.raises(RuntimeError, match="No aligned samples"):
+        data.MultimodalTripleDataset(glips, cue_root, lip_root, 117, "test", embedder=synthetic.fake_sentence_embedding,
+                                     cache_dir=str(tmp_path / "c"))
+    dup = tmp_path / "lips"
+    shutil.copytree(lip_root, dup)
+    first = sorted((dup / "aufgaben" / "train").glob("*.npy"))[0]
+    other = dup / "extra" / "aufgaben" / "train"
+    other.mkdir(parents=True)
+    shutil.copy(first, other / first.name)
+    with pytest.raises(RuntimeError, match="Duplicate video entries"):
+        data.MultimodalTripleDataset(glips, cue_root, str(dup), 117, "train", embedder=synthetic.fake_sentence_embedding,
+                                     cache_dir=str(tmp_path / "c"))
+    classes, samples = ods.scan_audio(glips, "train")
+    ads = data.GLipsDataset(glips, 117, "train")
+    assert ads.classes == classes and ads.samples == samples and ads.paths(0)[1] is None
