@@ -452,3 +452,19 @@ class DeviceBatchLoader:
 
     def close(self):
         self.pool.shutdown(wait=True)
+
+
+def get_data_loaders(config_path, device="cuda", **loader_kw):
+    """video/data_utils/dataset_loader.py:129-186: (train, val, test) loaders over the lip regions next to
+    `dataset.root_dir` (`<root>_lip_regions`), batch size `training.batch_size` (default 4), only the train split
+    shuffled; FileNotFoundError when the preprocessed lip regions are missing (:144-148)."""
+    from .train import Config
+    config = Config(config_path)
+    dataset_path = config.get("dataset.root_dir")
+    lip_regions_dir = os.path.join(os.path.dirname(dataset_path), os.path.basename(dataset_path) + "_lip_regions")
+    if not os.path.exists(lip_regions_dir):
+        raise FileNotFoundError(f"Preprocessed lip regions not found at {lip_regions_dir}. "
+                                f"Run visual_preprocessing.py first.")
+    batch_size = config.get("training.batch_size", 4)
+    return tuple(DeviceBatchLoader(VisualDataset(dataset_path, lip_regions_dir, split=s), batch_size, shuffle=(s == "train"),
+                                   device=device, **loader_kw) for s in ("train", "val", "test"))

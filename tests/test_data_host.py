@@ -232,3 +232,14 @@ def test_triple_dataset_error_conventions(triple_tree, tmp_path):
     classes, samples = ods.scan_audio(glips, "train")
     ads = data.GLipsDataset(glips, 117, "train")
     assert ads.classes == classes and ads.samples == samples and ads.paths(0)[1] is None
+
+
+def test_get_data_loaders_error_convention(tmp_path):
+    """video/data_utils/dataset_loader.py:144-148: missing preprocessed lip regions -> FileNotFoundError."""
+    (tmp_path / "GLips_4" / "lipread_files").mkdir(parents=True)
+    cfg = tmp_path / "visual_config.yaml"
+    cfg.write_text(f"dataset:\n  root_dir: {tmp_path / 'GLips_4'}\ntraining:\n  batch_size: 8\n")
+    with pytest.raises(FileNotFoundError, match="Preprocessed lip regions not found"):
+        data.get_data_loaders(str(cfg))
+    with pytest.raises(FileNotFoundError, match="Config file not found"):
+        data.get_data_loaders(str(tmp_path / "nope.yaml"))
