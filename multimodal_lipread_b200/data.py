@@ -348,7 +348,9 @@ class DeviceBatchLoader:
       GLipsDataset           -> (mel, labels)                                                      [audio/data_utils/dataset.py:52]
       MultimodalTripleDataset -> (mel, cue (B,dim) f32, lips uint8, labels)     [audio_cues_video/data_utils/dataset.py:273-284]
     `depth` batches are in flight: worker threads fill pinned slots while the copy stream uploads the previous one
-    and runs the audio kernels.  A yielded batch stays valid until `depth - 1` further batches have been taken."""
+    and runs the audio kernels.  Contract: enqueue the work that reads a batch (e.g. model.train_step, which copies its
+    inputs first) BEFORE asking for the next batch; its ring buffers are reused `depth` batches later, ordered after
+    that work on the device."""
 
     def __init__(self, dataset, batch_size, shuffle=False, drop_last=False, device="cuda", depth=3, workers=8, seed=0,
                  audio_decoder=None, max_channels=2):
@@ -403,7 +405,10 @@ class DeviceBatchLoader:
         scale = futures.result()
         n = slot.n
         cur = torch.cuda.current_stream(self.device)
-        dev["free"].record(cur)                      # consumer work enqueued so far may still read older batches
+        # Whatever the consumer enqueued for the PREVIOUS batch is on its stream by now: mark that batch's slot as
+        # released there.  This slot's own release mark dates from depth - 1 requests ago, so the upload below overlaps
+        # the steps still running on the batches in between instead of queueing behind them.
+        self.dev[(k - 1) % self.depth]["free"].record(cur)
         self.copy_stream.wait_event(dev["free"])
         with torch.cuda.stream(self.copy_stream):
             if self.with_video:
