@@ -85,6 +85,11 @@ int lr_pcm_ingest(const short* pcm, const long long* offset /*[B]*/, const int* 
                   const int* channels /*[B] or NULL*/, float scale, float* wav /*[B,target]*/, int B, int target,
                   lr_stream_t stream);
 
+/* audio_cues_video/data_utils/dataset.py:256-258 scales a lip clip by 1/255 only `if arr.max() > 1.0`.  The stem
+ * kernels always divide uint8 frames by 255; this pass rewrites, in place, every clip of frames[n_clips][clip_bytes]
+ * whose maximum is exactly 1 as 0 / 255, so that it comes out as the 0.0 / 1.0 the reference feeds its model. */
+int lr_u8_unit_clips(unsigned char* frames, int n_clips, long long clip_bytes, lr_stream_t stream);
+
 /* Host-side batch readers of the input path (the ONLY entry points that take host pointers; no CUDA calls).
  * A whole batch of `.npy` files is read by `n_threads` native threads straight into a ring slot of (pinned) host
  * memory, from where one async copy takes it to the device; no arithmetic on the host.

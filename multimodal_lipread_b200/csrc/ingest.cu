@@ -45,7 +45,41 @@ __global__ void __launch_bounds__(TH) pcm_ingest_kernel(const short* __restrict_
     }
 }
 
+// audio_cues_video/data_utils/dataset.py:256-258 divides a clip by 255 only `if arr.max() > 1.0`: a uint8 clip whose
+// every pixel is 0 or 1 stays 0.0 / 1.0.  The stem kernels always divide uint8 by 255, so such a clip is rewritten
+// as 0 / 255 here (one CTA per clip: max over the clip, then the rewrite if max <= 1) and comes out identical.
+__global__ void __launch_bounds__(TH) u8_unit_clip_kernel(unsigned char* __restrict__ frames, long long clip_bytes) {
+    __shared__ unsigned int smax;
+    if (threadIdx.x == 0) smax = 0u;
+    __syncthreads();
+    unsigned char* clip = frames + (long long)blockIdx.x * clip_bytes;
+    const long long n16 = clip_bytes / 16;
+    unsigned int m = 0u;
+    const uint4* v = reinterpret_cast<const uint4*>(clip);
+    for (long long i = threadIdx.x; i < n16 && m <= 1u; i += TH) {
+        const uint4 q = v[i];
+        const unsigned int o = q.x | q.y | q.z | q.w;           // any byte > 1 sets a bit above bit 0 of some byte
+        if (o & 0xFEFEFEFEu) m = 2u; else if (o) m = 1u;
+    }
+    for (long long i = n16 * 16 + threadIdx.x; i < clip_bytes; i += TH) m = max(m, (unsigned int)clip[i]);
+    atomicMax(&smax, m);
+    __syncthreads();
+    if (smax != 1u) return;                                     // max > 1: divided as usual; max == 0: all zeros either way
+    for (long long i = threadIdx.x; i < clip_bytes; i += TH) clip[i] = clip[i] ? 255 : 0;
+}
+
 }  // namespace ing
+
+extern "C" int lr_u8_unit_clips(unsigned char* frames, int n_clips, long long clip_bytes, lr_stream_t stream) {
+    LR_CHECK_ARG(n_clips >= 0 && clip_bytes > 0 && clip_bytes % 16 == 0, "lr_u8_unit_clips: clip_bytes must be a positive multiple of 16");
+    if (n_clips == 0) return LR_OK;
+    LR_CHECK_ARG(frames, "lr_u8_unit_clips: null pointer");
+    LR_CHECK_ALIGN(frames);
+    ing::u8_unit_clip_kernel<<<n_clips, ing::TH, 0, stream>>>(frames, clip_bytes);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("u8_unit_clip_kernel");
+    return LR_OK;
+}
 
 extern "C" int lr_pcm_ingest(const short* pcm, const long long* offset, const int* n_frames, const int* channels,
                              float scale, float* wav, int B, int target, lr_stream_t stream) {

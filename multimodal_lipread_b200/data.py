@@ -126,8 +126,9 @@ class MultimodalTripleDataset:
     reference's own cache file `<cache_dir>/<cue_mode>_<md5 of the descriptions>.npz` when it exists, otherwise from
     `embedder(list_of_descriptions) -> (n, dim) array` (SentenceTransformer.encode in the reference, :207-221; the
     text encoder itself is outside the path).  The loader yields (mel, cue, lips, label) like collate_fn_triple (:279-284).
-    Known deviation: the reference divides a clip by 255 only `if arr.max() > 1.0` (:256-258); the device path always
-    divides uint8 frames, which differs for clips whose every pixel is 0 or 1."""
+    The reference divides a clip by 255 only `if arr.max() > 1.0` (:256-258): `unit_clip_rule` makes the loader run
+    lr_u8_unit_clips on every batch so that a clip of 0 / 1 pixels reaches the model as 0.0 / 1.0 here too."""
+    unit_clip_rule = True
 
     def __init__(self, root_dir, cue_root, lip_regions_root, input_size=117, split="train", cue_mode="emotion",
                  cache_dir=".cache_cues", embedder=None, audio_ext=".m4a"):
@@ -413,6 +414,12 @@ class DeviceBatchLoader:
         with torch.cuda.stream(self.copy_stream):
             if self.with_video:
                 dev["frames"][:n].copy_(slot.frames[:n], non_blocking=True)
+                if getattr(self.ds, "unit_clip_rule", False):
+                    from ._lib import lib, check
+                    clip_bytes = dev["frames"][0].numel()
+                    if clip_bytes % 16:
+                        raise ValueError("unit_clip_rule needs clips of a multiple of 16 bytes")
+                    check(lib.lr_u8_unit_clips(dev["frames"].data_ptr(), n, clip_bytes, self.copy_stream.cuda_stream))
             if self.cue_dim:
                 dev["cues"][:n].copy_(slot.cues[:n], non_blocking=True)
             dev["labels"][:n].copy_(slot.labels[:n], non_blocking=True)

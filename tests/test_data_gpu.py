@@ -220,3 +220,24 @@ def test_triple_and_audio_loaders_match_the_reference_items(cuda_device, golden_
         n += labels.numel()
     assert n == len(ads)
     al.close()
+
+
+def test_unit_clip_rule_matches_the_reference_division(cuda_device):
+    """dataset.py:256-258: `if arr.max() > 1.0: arr = arr / 255.0` -- clips of 0 / 1 pixels are NOT divided."""
+    from multimodal_lipread_b200._lib import lib, check
+    g = torch.Generator().manual_seed(1)
+    clips = torch.randint(0, 256, (5, 3, 8, 8, 3), generator=g, dtype=torch.uint8)
+    clips[1] = torch.randint(0, 2, clips[1].shape, generator=g, dtype=torch.uint8)       # max == 1
+    clips[2] = 0                                                                          # max == 0
+    clips[3] = torch.randint(0, 2, clips[3].shape, generator=g, dtype=torch.uint8)
+    clips[3, 2, 7, 7, 2] = 2                                                              # a single 2 in the tail
+    ref = []
+    for c in clips:
+        arr = c.numpy().astype(np.float32)
+        ref.append(torch.from_numpy(arr / 255.0 if arr.max() > 1.0 else arr))
+    d = clips.to(cuda_device)
+    check(lib.lr_u8_unit_clips(d.data_ptr(), 5, clips[0].numel(), torch.cuda.current_stream().cuda_stream))
+    ours = d.cpu().float() / 255.0
+    for j in range(5):
+        assert torch.equal(ours[j], ref[j]), j
+    assert lib.lr_u8_unit_clips(d.data_ptr(), 5, 100, None) == -1
