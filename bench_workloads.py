@@ -290,17 +290,25 @@ class AvTrainWorkload:
         rows = self.profile_ops()
         self.op_rows = rows
         total = sum(r["ms"] for r in rows)
-        cand = [r for r in rows if r["bytes"]]
-        top = max(cand, key=lambda r: r["ms"])
+        cand = sorted((r for r in rows if r["bytes"]), key=lambda r: -r["ms"])
+        lab = lambda r: f"{r['op']} {r['shape']} ({r['phase']})"
+        tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
+        captured = json.load(open(tp)) if os.path.exists(tp) else {}
+        # the two largest streaming launches of this step are within run-to-run noise of each other (~125 us): among
+        # launches within 5 % of the longest, the one with a committed ncu --set full capture is reported, so that the
+        # line is stable from run to run and carries its measured DRAM traffic; the runner-up is listed beside it
+        near = [r for r in cand if r["ms"] >= 0.95 * cand[0]["ms"]]
+        top = next((r for r in near if lab(r) in captured), cand[0])
+        runner = next((r for r in cand if r is not top), None)
         achieved = top["bytes"] / 1e9 / (top["ms"] / 1e3)
-        by_op = {}
+        by_op, by_bytes = {}, {}
         for r in rows:
             by_op[r["op"]] = by_op.get(r["op"], 0.0) + r["ms"]
-        label = f"{top['op']} {top['shape']} ({top['phase']})"
-        traffic = None
-        tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(label)
+            if r["bytes"]:
+                b = by_bytes.setdefault(r["op"], [0.0, 0.0, 0])
+                b[0] += r["bytes"]; b[1] += r["ms"]; b[2] += 1
+        label = lab(top)
+        traffic = captured.get(label)
         f44, f88 = FWD_GFLOP[self.kind]
         fwd_gflop = f88 if self.cfg["size"] == 88 else f44
         slowest = max(rows, key=lambda r: r["ms"])
@@ -309,7 +317,14 @@ class AvTrainWorkload:
                 "peak_source": peaks["src"], "kernel_ms": top["ms"], "kernel_share_of_step": top["ms"] / total,
                 "step_ms_sum_of_kernels_cold": total,
                 "slowest_launch": f"{slowest['op']} {slowest['shape']} ({slowest['phase']}): {slowest['ms'] * 1e3:.0f} us",
+                "runner_up": (None if runner is None else
+                              {"kernel": lab(runner), "kernel_ms": runner["ms"],
+                               "frac": runner["bytes"] / 1e9 / (runner["ms"] / 1e3) / peaks["hbm"]}),
                 "time_by_op_ms": {k: round(v, 4) for k, v in sorted(by_op.items(), key=lambda kv: -kv[1])},
+                # every launch of an op family: sum of algorithmic bytes / sum of cold device times, as a fraction of peak
+                "hbm_frac_by_op": {k: {"launches": v[2], "GBps": round(v[0] / 1e9 / (v[1] / 1e3), 1),
+                                       "frac": round(v[0] / 1e9 / (v[1] / 1e3) / peaks["hbm"], 3)}
+                                   for k, v in sorted(by_bytes.items(), key=lambda kv: -kv[1][1])},
                 "step_model_tflops": 3 * fwd_gflop * self.batch / (ms_step / 1e3) / 1e3}
 
     def extra(self):
