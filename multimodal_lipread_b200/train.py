@@ -128,10 +128,12 @@ def _to_dev(t, device):
     return t.to(device, non_blocking=True)
 
 
-def train_epoch(model, loader, device, batch_to_inputs=None):
+def train_epoch(model, loader, device, batch_to_inputs=None, per_sample_loss=False):
     """One epoch with the fused step.  Returns (mean of the per-batch mean losses, accuracy %) exactly as
-    audio_video/train.py:57-75 reports them (sum(batch_mean_loss) / len(loader)).  `batch_to_inputs(batch)` maps a
-    DataLoader batch to (inputs tuple, labels); the default handles the reference's tuple / dict items."""
+    audio_video/train.py:57-75, video/train.py:85-114 and audio/train.py:59-84 report them
+    (sum(batch_mean_loss) / len(loader)); per_sample_loss=True weights every batch by its size instead, as
+    audio_cues_video/train.py:52-81 does (sum(loss * n) / total).  `batch_to_inputs(batch)` maps a DataLoader batch
+    to (inputs tuple, labels); the default handles the reference's tuple / dict items."""
     model.train()
     loss_sum = torch.zeros((), device=device)
     correct = torch.zeros((), dtype=torch.int64, device=device)
@@ -141,16 +143,19 @@ def train_epoch(model, loader, device, batch_to_inputs=None):
         inputs = tuple(_to_dev(t, device) for t in inputs)
         labels = _to_dev(labels, device)
         loss, logits = model.train_step(*inputs, labels)
-        loss_sum += loss.reshape(())                         # device-side accumulation: no host sync per step
+        # device-side accumulation: no host sync per step
+        loss_sum += loss.reshape(()) * (labels.numel() if per_sample_loss else 1)
         correct += (logits.argmax(1) == labels).sum()
         total += labels.numel()
         n_batches += 1
-    return (loss_sum / max(n_batches, 1)).item(), 100.0 * correct.item() / max(total, 1)
+    denom = max(total, 1) if per_sample_loss else max(n_batches, 1)
+    return (loss_sum / denom).item(), 100.0 * correct.item() / max(total, 1)
 
 
 @torch.no_grad()
-def validate(model, loader, device, batch_to_inputs=None):
-    """audio_video/train.py:78-90: eval mode, mean CE per batch, accuracy %."""
+def validate(model, loader, device, batch_to_inputs=None, per_sample_loss=False):
+    """audio_video/train.py:78-90: eval mode, mean CE per batch, accuracy %  (per_sample_loss: the size-weighted mean
+    of audio_cues_video/train.py:52-81)."""
     model.eval()
     loss_sum, correct, total, n_batches = 0.0, 0, 0, 0
     for batch in loader:
@@ -158,11 +163,11 @@ def validate(model, loader, device, batch_to_inputs=None):
         inputs = tuple(_to_dev(t, device) for t in inputs)
         labels = _to_dev(labels, device)
         out = model(*inputs)
-        loss_sum += torch.nn.functional.cross_entropy(out, labels).item()
+        loss_sum += torch.nn.functional.cross_entropy(out, labels).item() * (labels.numel() if per_sample_loss else 1)
         correct += (out.argmax(1) == labels).sum().item()
         total += labels.numel()
         n_batches += 1
-    return loss_sum / max(n_batches, 1), 100.0 * correct / max(total, 1)
+    return loss_sum / (max(total, 1) if per_sample_loss else max(n_batches, 1)), 100.0 * correct / max(total, 1)
 
 
 def default_batch_to_inputs(batch):
@@ -284,7 +289,7 @@ def resume(model, path):
 
 
 def fit(model, model_name, loaders, device, epochs, save_dir, out_dir="./metrics", schedule=None, resume_from=None,
-        batch_to_inputs=None, log=print):
+        batch_to_inputs=None, log=print, per_sample_loss=False):
     """The epoch loop of the reference's main(): train, validate, test every epoch, log, keep
     `<model>_checkpoint.pth` and `model_best.pth`, reload the best weights for the final test and write
     test_results.txt (video/train.py:232-283; audio_cues_video/train.py:166-207).
@@ -296,11 +301,11 @@ def fit(model, model_name, loaders, device, epochs, save_dir, out_dir="./metrics
     sched = ReduceLROnPlateau(model, mode=schedule[0], factor=0.5, patience=schedule[1]) if schedule else None
     start_epoch, best_val_acc = (1, 0.0) if not resume_from else resume(model, resume_from)
     for epoch in range(start_epoch, epochs + 1):
-        train_loss, train_acc = train_epoch(model, train_loader, device, batch_to_inputs)
-        val_loss, val_acc = validate(model, val_loader, device, batch_to_inputs)
+        train_loss, train_acc = train_epoch(model, train_loader, device, batch_to_inputs, per_sample_loss)
+        val_loss, val_acc = validate(model, val_loader, device, batch_to_inputs, per_sample_loss)
         if sched:
             sched.step(val_acc if sched.mode == "max" else val_loss)
-        test_loss, test_acc = validate(model, test_loader, device, batch_to_inputs)
+        test_loss, test_acc = validate(model, test_loader, device, batch_to_inputs, per_sample_loss)
         log(f"Epoch {epoch}/{epochs}  Train Loss: {train_loss:.4f} | Train Acc: {train_acc:.2f}%  "
             f"Val Loss: {val_loss:.4f} | Val Acc: {val_acc:.2f}%  Test Loss: {test_loss:.4f} | Test Acc: {test_acc:.2f}%")
         log_to_files(model_name, epoch, train_loss, train_acc, val_loss, val_acc, test_loss, test_acc, out_dir)
@@ -312,7 +317,7 @@ def fit(model, model_name, loaders, device, epochs, save_dir, out_dir="./metrics
             torch.save(ckpt, os.path.join(save_dir, "model_best.pth"))
     best = torch.load(os.path.join(save_dir, "model_best.pth"), map_location="cpu")
     model.load_state_dict(best["state_dict"])
-    test_loss, test_acc = validate(model, test_loader, device, batch_to_inputs)
+    test_loss, test_acc = validate(model, test_loader, device, batch_to_inputs, per_sample_loss)
     log_final_results(model_name, test_loss, test_acc, out_dir)
     with open(os.path.join(save_dir, "test_results.txt"), "w") as f:
         f.write(f"Final Test Loss: {test_loss:.4f}\n")

@@ -123,3 +123,35 @@ def test_log_files_have_the_reference_schema(tmp_path):
     txt = open(os.path.join(out, "m_training_log.txt")).read()
     assert txt.startswith("Training Log\n\nEpoch 1\n  Train Loss: 2.5000, Train Acc: 10.00%\n  Val Loss:   2.2500, Val Acc:   12.50%\n")
     assert txt.endswith("Final Test Loss: 1.0000, Final Test Acc: 35.00%\n")
+
+
+def test_epoch_bookkeeping_follows_each_train_script():
+    """Loss / accuracy aggregation of the epoch loops with a ragged last batch: mean of batch means
+    (audio_video/train.py:57-75,78-90) vs size-weighted mean (audio_cues_video/train.py:52-81)."""
+    import torch
+    from multimodal_lipread_b200 import train as T
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.eye(4))
+
+        def forward(self, x):
+            return x @ self.w
+
+        def train_step(self, x, labels):
+            out = self(x)
+            return torch.nn.functional.cross_entropy(out, labels).detach().reshape(1), out.detach()
+
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.randn(n, 4, generator=g), torch.randint(0, 4, (n,), generator=g)) for n in (5, 5, 2)]
+    losses = [torch.nn.functional.cross_entropy(x, y).item() for x, y in batches]
+    correct = sum((x.argmax(1) == y).sum().item() for x, y in batches)
+    m = Stub()
+    for fn in (T.train_epoch, T.validate):
+        loss, acc = fn(m, batches, "cpu")
+        assert loss == pytest.approx(sum(losses) / 3, rel=1e-6) and acc == pytest.approx(100.0 * correct / 12)
+        loss, acc = fn(m, batches, "cpu", per_sample_loss=True)
+        assert loss == pytest.approx((5 * losses[0] + 5 * losses[1] + 2 * losses[2]) / 12, rel=1e-6)
+    dict_batches = [{"lip_regions": x, "label": y} for x, y in batches]                  # video/data_utils items
+    assert T.validate(m, dict_batches, "cpu")[0] == pytest.approx(sum(losses) / 3, rel=1e-6)
