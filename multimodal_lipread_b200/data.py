@@ -333,8 +333,15 @@ class HostSlot:
         return self._stage_audio(j, audio_path, audio_decoder)
 
 
-def batch_indices(n, batch_size, shuffle, drop_last, generator):
+def batch_indices(n, batch_size, shuffle, drop_last, generator, rank=0, world=1):
+    """Per-rank batches of sample indices.  world == 1: DataLoader order (randperm when shuffled, ragged last batch
+    unless drop_last).  world > 1: the same global order on every rank (same seed), cut into GLOBAL
+    batches of batch_size * world clips of which rank r takes clips [r * batch_size, (r + 1) * batch_size); a ragged
+    global tail is dropped so that every rank takes the same number of equal steps (the in-graph allreduce needs it)."""
     order = torch.randperm(n, generator=generator).tolist() if shuffle else list(range(n))
+    if world > 1:
+        G = batch_size * world
+        return [order[i + rank * batch_size:i + (rank + 1) * batch_size] for i in range(0, n - G + 1, G)]
     out = [order[i:i + batch_size] for i in range(0, n, batch_size)]
     if drop_last and out and len(out[-1]) < batch_size:
         out.pop()
@@ -354,10 +361,11 @@ class DeviceBatchLoader:
     that work on the device."""
 
     def __init__(self, dataset, batch_size, shuffle=False, drop_last=False, device="cuda", depth=3, workers=8, seed=0,
-                 audio_decoder=None, max_channels=2):
+                 audio_decoder=None, max_channels=2, rank=0, world=1):
         if len(dataset) == 0:
             raise RuntimeError("empty dataset")
         self.ds, self.batch_size, self.shuffle, self.drop_last = dataset, int(batch_size), shuffle, drop_last
+        self.rank, self.world = int(rank), int(world)        # data parallel: batch_size is per rank, same seed everywhere
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise NotImplementedError("DeviceBatchLoader feeds the GPU path; there is no CPU frontend here")
@@ -393,6 +401,8 @@ class DeviceBatchLoader:
 
     def __len__(self):
         n = len(self.ds)
+        if self.world > 1:
+            return n // (self.batch_size * self.world)
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
     def _stage(self, slot, idxs):
@@ -446,7 +456,7 @@ class DeviceBatchLoader:
         return {"lip_regions": frames, "label": labels}
 
     def __iter__(self):
-        batches = batch_indices(len(self.ds), self.batch_size, self.shuffle, self.drop_last, self.gen)
+        batches = batch_indices(len(self.ds), self.batch_size, self.shuffle, self.drop_last, self.gen, self.rank, self.world)
         inflight = collections.deque()
         nxt = 0
         while nxt < len(batches) and len(inflight) < self.depth - 1:

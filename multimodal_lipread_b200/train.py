@@ -128,12 +128,14 @@ def _to_dev(t, device):
     return t.to(device, non_blocking=True)
 
 
-def train_epoch(model, loader, device, batch_to_inputs=None, per_sample_loss=False):
+def train_epoch(model, loader, device, batch_to_inputs=None, per_sample_loss=False, grad_allreduce=None, world=1):
     """One epoch with the fused step.  Returns (mean of the per-batch mean losses, accuracy %) exactly as
     audio_video/train.py:57-75, video/train.py:85-114 and audio/train.py:59-84 report them
     (sum(batch_mean_loss) / len(loader)); per_sample_loss=True weights every batch by its size instead, as
     audio_cues_video/train.py:52-81 does (sum(loss * n) / total).  `batch_to_inputs(batch)` maps a DataLoader batch
-    to (inputs tuple, labels); the default handles the reference's tuple / dict items."""
+    to (inputs tuple, labels); the default handles the reference's tuple / dict items.  Data parallel: hand in
+    dp.GradAllReduce() and the world size (the loader then shards by rank, data.DeviceBatchLoader(rank=, world=));
+    loss / accuracy are this rank's."""
     model.train()
     loss_sum = torch.zeros((), device=device)
     correct = torch.zeros((), dtype=torch.int64, device=device)
@@ -142,7 +144,8 @@ def train_epoch(model, loader, device, batch_to_inputs=None, per_sample_loss=Fal
         inputs, labels = (batch_to_inputs or default_batch_to_inputs)(batch)
         inputs = tuple(_to_dev(t, device) for t in inputs)
         labels = _to_dev(labels, device)
-        loss, logits = model.train_step(*inputs, labels)
+        loss, logits = (model.train_step(*inputs, labels) if grad_allreduce is None else
+                        model.train_step(*inputs, labels, grad_allreduce=grad_allreduce, world=world))
         # device-side accumulation: no host sync per step
         loss_sum += loss.reshape(()) * (labels.numel() if per_sample_loss else 1)
         correct += (logits.argmax(1) == labels).sum()
@@ -289,7 +292,7 @@ def resume(model, path):
 
 
 def fit(model, model_name, loaders, device, epochs, save_dir, out_dir="./metrics", schedule=None, resume_from=None,
-        batch_to_inputs=None, log=print, per_sample_loss=False):
+        batch_to_inputs=None, log=print, per_sample_loss=False, grad_allreduce=None, world=1):
     """The epoch loop of the reference's main(): train, validate, test every epoch, log, keep
     `<model>_checkpoint.pth` and `model_best.pth`, reload the best weights for the final test and write
     test_results.txt (video/train.py:232-283; audio_cues_video/train.py:166-207).
@@ -301,7 +304,7 @@ def fit(model, model_name, loaders, device, epochs, save_dir, out_dir="./metrics
     sched = ReduceLROnPlateau(model, mode=schedule[0], factor=0.5, patience=schedule[1]) if schedule else None
     start_epoch, best_val_acc = (1, 0.0) if not resume_from else resume(model, resume_from)
     for epoch in range(start_epoch, epochs + 1):
-        train_loss, train_acc = train_epoch(model, train_loader, device, batch_to_inputs, per_sample_loss)
+        train_loss, train_acc = train_epoch(model, train_loader, device, batch_to_inputs, per_sample_loss, grad_allreduce, world)
         val_loss, val_acc = validate(model, val_loader, device, batch_to_inputs, per_sample_loss)
         if sched:
             sched.step(val_acc if sched.mode == "max" else val_loss)

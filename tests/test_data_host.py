@@ -243,3 +243,18 @@ def test_get_data_loaders_error_convention(tmp_path):
         data.get_data_loaders(str(cfg))
     with pytest.raises(FileNotFoundError, match="Config file not found"):
         data.get_data_loaders(str(tmp_path / "nope.yaml"))
+
+
+@pytest.mark.parametrize("n,B,world,shuffle", [(37, 4, 2, True), (64, 8, 4, False), (10, 4, 4, True), (33, 2, 8, True)])
+def test_rank_sharding_of_the_batch_order(n, B, world, shuffle):
+    """rank r takes clips [r*B, (r+1)*B) of every global batch; equal step counts on all ranks; no clip
+    twice; the global order is the single-process order of the same seed."""
+    per_rank = [data.batch_indices(n, B, shuffle, False, torch.Generator().manual_seed(5), r, world) for r in range(world)]
+    single = data.batch_indices(n, B * world, shuffle, True, torch.Generator().manual_seed(5))
+    steps = n // (B * world)
+    assert all(len(b) == steps for b in per_rank) and len(single) == steps
+    for step in range(steps):
+        glob = sum((per_rank[r][step] for r in range(world)), [])
+        assert glob == single[step] and all(len(per_rank[r][step]) == B for r in range(world))
+    flat = [i for r in per_rank for b in r for i in b]
+    assert len(flat) == len(set(flat)) == steps * B * world
