@@ -95,3 +95,63 @@ def pcm_ingest(pcm: torch.Tensor, offset: torch.Tensor, n_frames: torch.Tensor, 
 @pcm_ingest.register_fake
 def _(pcm, offset, n_frames, channels, scale, target):
     return pcm.new_empty(offset.numel(), target, dtype=torch.float32)
+
+
+# ---------------------------------------------------------------- nn.Linear (+ ReLU) with autograd
+@torch.library.custom_op("lipread::linear", mutates_args=(), device_types="cuda")
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, act: int) -> torch.Tensor:
+    """y = act(x @ weight^T + bias) for x [M, K], weight [N, K], bias [N] (empty tensor: no bias); act 0 none, 1 ReLU
+    -- nn.Linear / a 1x1 convolution on channels-last rows, e.g. the classifier of
+    audio_video/models/middle_fusion_fast.py:20-25.  One lr_gemm launch with the bias / activation in its epilogue."""
+    from . import kernels as K
+    for t, n in ((x, "x"), (weight, "weight")):
+        _need(t, torch.float32, n)
+    if x.dim() != 2 or weight.dim() != 2 or x.shape[1] != weight.shape[1] or act not in (0, 1):
+        raise _lib.LipreadError(f"linear: x {tuple(x.shape)}, weight {tuple(weight.shape)}, act {act}")
+    out = torch.empty(x.shape[0], weight.shape[0], dtype=torch.float32, device=x.device)
+    K.linear_fwd(x, weight, out, bias=bias if bias.numel() else None, act=act)
+    return out
+
+
+@linear.register_fake
+def _(x, weight, bias, act):
+    return x.new_empty(x.shape[0], weight.shape[0])
+
+
+@torch.library.custom_op("lipread::linear_bwd", mutates_args=(), device_types="cuda")
+def linear_bwd(dy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, y: torch.Tensor, act: int,
+               has_bias: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(dx, dweight, dbias) of lipread::linear: lr_act_bwd through the output, then the dgrad / wgrad GEMMs and the
+    bias column sum -- the launches the step graphs use for every Linear."""
+    from . import kernels as K
+    g = dy.contiguous().clone()
+    if act:
+        K.act_bwd(g, y, g.numel(), act)
+    dx = torch.empty_like(x)
+    K.linear_dgrad(g, weight, dx)
+    dw = torch.zeros_like(weight)
+    K.linear_wgrad(g, x, dw)
+    db = torch.zeros(weight.shape[0] if has_bias else 0, dtype=torch.float32, device=x.device)
+    if has_bias:
+        K.colsum(g, g.shape[1], g.shape[0], g.shape[1], db)
+    return dx, dw, db
+
+
+@linear_bwd.register_fake
+def _(dy, x, weight, y, act, has_bias):
+    return torch.empty_like(x), torch.empty_like(weight), x.new_empty(weight.shape[0] if has_bias else 0)
+
+
+def _linear_setup(ctx, inputs, output):
+    x, weight, bias, act = inputs
+    ctx.save_for_backward(x, weight, output)
+    ctx.act, ctx.has_bias = act, bool(bias.numel())
+
+
+def _linear_backward(ctx, dy):
+    x, weight, y = ctx.saved_tensors
+    dx, dw, db = linear_bwd(dy, x, weight, y, ctx.act, ctx.has_bias)
+    return dx, dw, (db if ctx.has_bias else None), None
+
+
+linear.register_autograd(_linear_backward, setup_context=_linear_setup)

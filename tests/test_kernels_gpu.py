@@ -456,3 +456,34 @@ def test_channel_shuffle_interleave(K):
     check(lib.lr_shuffle2_bwd(dout.data_ptr(), dx.data_ptr(), C, dr.data_ptr(), bf, F * H * W, bf, s))
     assert torch.equal(dx[:, :bf].cpu(), dout[:, 0::2].cpu()) and torch.equal(dr.cpu(), dout[:, 1::2].cpu())
     assert (dx[:, bf:] == 0).all()                                     # the other half belongs to branch2's 1x1 conv
+
+
+@pytest.mark.parametrize("M,K_,N,act,bias", [(37, 384, 256, 1, True), (5, 128, 40, 0, True), (64, 100, 24, 1, False)])
+def test_custom_op_linear_with_autograd(K, M, K_, N, act, bias):
+    """torch.ops.lipread.linear: forward and register_autograd backward against nn.functional.linear (+ ReLU), and the
+    fake (meta) kernel the dispatcher uses for shape inference."""
+    from multimodal_lipread_b200 import ops
+    torch.manual_seed(M)
+    x = torch.randn(M, K_, device="cuda", requires_grad=True)
+    w = torch.randn(N, K_, device="cuda", requires_grad=True)
+    b = torch.randn(N, device="cuda", requires_grad=True) if bias else torch.empty(0, device="cuda")
+    y = torch.ops.lipread.linear(x, w, b, act)
+    ref = Fn.linear(x.detach().cpu().double(), w.detach().cpu().double(), b.detach().cpu().double() if bias else None)
+    ref_y = torch.relu(ref) if act else ref
+    _close(y, ref_y, rtol=1e-5)
+    dy = torch.randn(M, N, device="cuda")
+    y.backward(dy)
+    xr, wr = x.detach().cpu().double().requires_grad_(True), w.detach().cpu().double().requires_grad_(True)
+    br = b.detach().cpu().double().requires_grad_(True) if bias else None
+    yr = Fn.linear(xr, wr, br)
+    (torch.relu(yr) if act else yr).backward(dy.cpu().double())
+    _close(x.grad, xr.grad, rtol=2e-5)
+    _close(w.grad, wr.grad, rtol=2e-5)
+    if bias:
+        _close(b.grad, br.grad, rtol=2e-5)
+    with torch._subclasses.fake_tensor.FakeTensorMode():
+        fy = torch.ops.lipread.linear(torch.empty(M, K_, device="cuda"), torch.empty(N, K_, device="cuda"),
+                                      torch.empty(N, device="cuda"), act)
+        assert tuple(fy.shape) == (M, N)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.lipread.linear(x.detach().cpu(), w.detach().cpu(), b.detach().cpu(), act)       # no CPU kernel
