@@ -258,3 +258,63 @@ def test_rank_sharding_of_the_batch_order(n, B, world, shuffle):
         assert glob == single[step] and all(len(per_rank[r][step]) == B for r in range(world))
     flat = [i for r in per_rank for b in r for i in b]
     assert len(flat) == len(set(flat)) == steps * B * world
+
+
+def test_native_npy_reader_property(tmp_path):
+    """lr_host_read_npy_u8 / lr_host_read_npy_pcm16 against numpy for random shapes, .npy format versions 1.0 / 2.0 /
+    3.0 and every thread count (hypothesis)."""
+    import ctypes
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    from numpy.lib import format as npf
+    from multimodal_lipread_b200._lib import lib, check
+
+    def write(path, arr, version):
+        with open(path, "wb") as f:
+            npf.write_array(f, arr, version=version)
+
+    counter = [0]
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(shape=st.lists(st.integers(1, 7), min_size=1, max_size=5), n=st.integers(1, 6), threads=st.integers(1, 9),
+           version=st.sampled_from([(1, 0), (2, 0), (3, 0)]), seed=st.integers(0, 2 ** 16))
+    def frames(shape, n, threads, version, seed):
+        rng = np.random.default_rng(seed)
+        counter[0] += 1
+        arrs = [rng.integers(0, 256, size=shape, dtype=np.uint8) for _ in range(n)]
+        paths = []
+        for i, a in enumerate(arrs):
+            p = str(tmp_path / f"f{counter[0]}_{i}.npy")
+            write(p, a, version)
+            paths.append(p)
+        dst = np.zeros((n,) + tuple(shape), np.uint8)
+        cp = (ctypes.c_char_p * n)(*[os.fsencode(p) for p in paths])
+        cs = (ctypes.c_longlong * len(shape))(*shape)
+        check(lib.lr_host_read_npy_u8(cp, n, dst.ctypes.data, cs, len(shape), threads))
+        assert np.array_equal(dst, np.stack(arrs))
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(lens=st.lists(st.integers(0, 90), min_size=1, max_size=5), ch=st.integers(1, 2), threads=st.integers(1, 4),
+           version=st.sampled_from([(1, 0), (2, 0)]), seed=st.integers(0, 2 ** 16))
+    def pcm(lens, ch, threads, version, seed):
+        rng = np.random.default_rng(seed)
+        counter[0] += 1
+        target, cap = 64, 64 * 2
+        n = len(lens)
+        arrs = [rng.integers(-32768, 32768, size=(L,) if ch == 1 else (L, ch), dtype=np.int16) for L in lens]
+        paths = []
+        for i, a in enumerate(arrs):
+            p = str(tmp_path / f"p{counter[0]}_{i}.npy")
+            write(p, a, version)
+            paths.append(p)
+        dst = np.full((n, cap), 7, np.int16)
+        meta = np.zeros((3, n), np.int64)
+        cp = (ctypes.c_char_p * n)(*[os.fsencode(p) for p in paths])
+        check(lib.lr_host_read_npy_pcm16(cp, n, dst.ctypes.data, cap, target, meta.ctypes.data, threads))
+        for i, a in enumerate(arrs):
+            keep = min(lens[i], target)
+            assert meta[:, i].tolist() == [i * cap, keep, ch]
+            assert np.array_equal(dst[i, :keep * ch], a.reshape(-1)[:keep * ch])
+            assert (dst[i, keep * ch:] == 7).all()                      # nothing written past the kept frames
+
+    frames()
+    pcm()
