@@ -176,7 +176,8 @@ lstm_bwd_kernel(const Bwd p) {
 namespace lsc {
 
 constexpr int NC = 8;          // CTAs per cluster (portable maximum)
-constexpr int BG = 32;         // batch rows per cluster
+// batch rows per cluster (template parameter BGT): 32, or 16 when that still fits one wave -- twice the clusters,
+// half the rows (and gate activations) per thread and step, for the small batches where one cluster would walk alone
 constexpr int TH = 256;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -195,27 +196,27 @@ __device__ __forceinline__ void st_cluster(uint32_t addr, float v) {
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
-// thread t: unit u = t % U, row group rg = t / U (TH / U groups of RPT = BG * U / TH rows)
-template <int H>
+// thread t: unit u = t % U, row group rg = t / U (TH / U groups of RPT = BGT * U / TH rows)
+template <int H, int BGT>
 __global__ void __launch_bounds__(TH)
 lstm_fwd_cluster_kernel(const ls::Fwd p) {
     constexpr int U = H / NC;                 // hidden units per CTA
     constexpr int NRG = TH / U;               // row groups
-    constexpr int RPT = BG / NRG;             // rows per thread
+    constexpr int RPT = BGT / NRG;             // rows per thread
     constexpr int HP = H + 4;                 // h row pitch (floats): rows land on different banks
-    static_assert(BG % NRG == 0 && RPT >= 1, "bad thread mapping");
+    static_assert(BGT % NRG == 0 && RPT >= 1, "bad thread mapping");
     extern __shared__ __align__(16) float sm[];
     float* Wt = sm;                           // [H][U][4]   Wt[k][u][g] = whh[(g*H + c*U + u)*H + k]
-    float* hb = Wt + H * U * 4;               // [2][BG][HP]
+    float* hb = Wt + H * U * 4;               // [2][BGT][HP]
     const unsigned c = cluster_ctarank();
-    const int b0 = (blockIdx.x / NC) * BG;
+    const int b0 = (blockIdx.x / NC) * BGT;
     const int u = threadIdx.x % U, rg = threadIdx.x / U;
     for (int i = threadIdx.x; i < 4 * U * H; i += TH) {
         const int k = i % H, ju = i / H;                       // ju = g*U + uu: coalesced reads of the row
         const int g = ju / U, uu = ju - g * U;
         Wt[(k * U + uu) * 4 + g] = p.whh[(long long)(g * H + c * U + uu) * H + k];
     }
-    for (int i = threadIdx.x; i < 2 * BG * HP; i += TH) hb[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * BGT * HP; i += TH) hb[i] = 0.f;
     float bias[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) bias[g] = p.bhh ? p.bhh[g * H + c * U + u] : 0.f;
@@ -228,7 +229,7 @@ lstm_fwd_cluster_kernel(const ls::Fwd p) {
     cluster_sync();                           // every CTA's buffers are initialised before anyone writes into them
     for (int s = 0; s < p.nsteps; ++s) {
         const int t = p.reverse ? p.T - 1 - s : s;
-        const float* hcur = hb + (s & 1) * BG * HP;
+        const float* hcur = hb + (s & 1) * BGT * HP;
         float acc[RPT][4], xp[RPT][4];          // xp: issued now, consumed after the recurrent product (latency hidden)
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
@@ -257,7 +258,7 @@ lstm_fwd_cluster_kernel(const ls::Fwd p) {
                 }
             }
         }
-        const int nxt = ((s + 1) & 1) * BG * HP;
+        const int nxt = ((s + 1) & 1) * BGT * HP;
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
             const int rl = rg * RPT + r, b = b0 + rl;
@@ -284,29 +285,29 @@ lstm_fwd_cluster_kernel(const ls::Fwd p) {
 
 // BPTT with the same partition.  Per step: local dgates for the CTA's units, partial dh_prev[r][k] = sum over the
 // CTA's 4U gate rows of dg[r][j] * whh[j][k] for ALL k, scattered to the owner of column k.
-template <int H>
+template <int H, int BGT>
 __global__ void __launch_bounds__(TH)
 lstm_bwd_cluster_kernel(const ls::Bwd p) {
     constexpr int U = H / NC;
     constexpr int NRG = TH / U;
-    constexpr int RPT = BG / NRG;
+    constexpr int RPT = BGT / NRG;
     constexpr int GP = 4 * U + 4;             // dg row pitch
     constexpr int KPT = H / 32;               // columns per thread in the transposed product (32 column lanes)
     constexpr int NRG2 = TH / 32;             // row groups of the transposed product
-    constexpr int RPT2 = BG / NRG2;
+    constexpr int RPT2 = BGT / NRG2;
     extern __shared__ __align__(16) float sm[];
     float* Ws = sm;                           // [4U][H]    Ws[g*U+uu][k] = whh[(g*H + c*U + uu)*H + k]
-    float* dg = Ws + 4 * U * H;               // [BG][GP]   this step's gate gradients of the CTA's units
-    float* part = dg + BG * GP;               // [2][NC][BG][U]  partial dh of MY units from every CTA
+    float* dg = Ws + 4 * U * H;               // [BGT][GP]   this step's gate gradients of the CTA's units
+    float* part = dg + BGT * GP;               // [2][NC][BGT][U]  partial dh of MY units from every CTA
     const unsigned c = cluster_ctarank();
-    const int b0 = (blockIdx.x / NC) * BG;
+    const int b0 = (blockIdx.x / NC) * BGT;
     const int u = threadIdx.x % U, rg = threadIdx.x / U;
     for (int i = threadIdx.x; i < 4 * U * H; i += TH) {
         const int k = i % H, ju = i / H;
         const int g = ju / U, uu = ju - g * U;
         Ws[ju * H + k] = p.whh[(long long)(g * H + c * U + uu) * H + k];
     }
-    for (int i = threadIdx.x; i < 2 * NC * BG * U; i += TH) part[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * NC * BGT * U; i += TH) part[i] = 0.f;
     float dc[RPT];
 #pragma unroll
     for (int r = 0; r < RPT; ++r) dc[r] = 0.f;
@@ -320,7 +321,7 @@ lstm_bwd_cluster_kernel(const ls::Bwd p) {
         const int tprev = p.reverse ? t + 1 : t - 1;
         const int par = s & 1;
         // ---- gate gradients of my units: dh = sum of the 8 partials scattered to me in the previous iteration
-        const float* pin = part + par * NC * BG * U;
+        const float* pin = part + par * NC * BGT * U;
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
             const int rl = rg * RPT + r, b = b0 + rl;
@@ -330,7 +331,7 @@ lstm_bwd_cluster_kernel(const ls::Bwd p) {
                 float dht = 0.f;
                 if (s < p.nsteps - 1) {
 #pragma unroll
-                    for (int d = 0; d < NC; ++d) dht += pin[(d * BG + rl) * U + u];
+                    for (int d = 0; d < NC; ++d) dht += pin[(d * BGT + rl) * U + u];
                 }
                 const long long row = (long long)b * p.T + t;
                 if (p.dout) {
@@ -385,7 +386,7 @@ lstm_bwd_cluster_kernel(const ls::Bwd p) {
 #pragma unroll
                 for (int r = 0; r < RPT2; ++r) {
                     const int rl = rg2 * RPT2 + r;
-                    st_cluster(remote[dst] + (uint32_t)(((npar * NC + (int)c) * BG + rl) * U + ku) * 4u, acc[r][i]);
+                    st_cluster(remote[dst] + (uint32_t)(((npar * NC + (int)c) * BGT + rl) * U + ku) * 4u, acc[r][i]);
                 }
             }
         }
@@ -411,26 +412,37 @@ static int launch_cluster(Kern kern, int clusters, size_t smem, lr_stream_t stre
     return LR_OK;
 }
 
-template <int H> static size_t fwd_smem() { return (size_t)(H * (H / NC) * 4 + 2 * BG * (H + 4)) * sizeof(float); }
-template <int H> static size_t bwd_smem() {
-    return (size_t)(4 * (H / NC) * H + BG * (4 * (H / NC) + 4) + 2 * NC * BG * (H / NC)) * sizeof(float);
+template <int H, int BGT> static size_t fwd_smem() { return (size_t)(H * (H / NC) * 4 + 2 * BGT * (H + 4)) * sizeof(float); }
+template <int H, int BGT> static size_t bwd_smem() {
+    return (size_t)(4 * (H / NC) * H + BGT * (4 * (H / NC) + 4) + 2 * NC * BGT * (H / NC)) * sizeof(float);
 }
 
-template <int H>
+template <int H, int BGT>
 static int run_fwd(const ls::Fwd& p, lr_stream_t stream) {
-    auto k = lstm_fwd_cluster_kernel<H>;
-    return launch_cluster(k, (p.B + BG - 1) / BG, fwd_smem<H>(), stream, &p, "lstm_fwd_cluster_kernel",
+    auto k = lstm_fwd_cluster_kernel<H, BGT>;
+    return launch_cluster(k, (p.B + BGT - 1) / BGT, fwd_smem<H, BGT>(), stream, &p, "lstm_fwd_cluster_kernel",
                           +[](decltype(k) kk, cudaLaunchConfig_t* cfg, const void* a) {
                               cudaLaunchKernelEx(cfg, kk, *static_cast<const ls::Fwd*>(a));
                           });
 }
-template <int H>
+template <int H, int BGT>
 static int run_bwd(const ls::Bwd& p, lr_stream_t stream) {
-    auto k = lstm_bwd_cluster_kernel<H>;
-    return launch_cluster(k, (p.B + BG - 1) / BG, bwd_smem<H>(), stream, &p, "lstm_bwd_cluster_kernel",
+    auto k = lstm_bwd_cluster_kernel<H, BGT>;
+    return launch_cluster(k, (p.B + BGT - 1) / BGT, bwd_smem<H, BGT>(), stream, &p, "lstm_bwd_cluster_kernel",
                           +[](decltype(k) kk, cudaLaunchConfig_t* cfg, const void* a) {
                               cudaLaunchKernelEx(cfg, kk, *static_cast<const ls::Bwd*>(a));
                           });
+}
+
+
+// 16 rows per cluster while all clusters still run in one wave, else 32
+static bool small_groups(int B) { return ((B + 15) / 16) * NC <= lr::sm_count() && getenv("LIPREAD_LSTM_BG32") == nullptr; }
+
+template <int H> static int run_fwd_auto(const ls::Fwd& p, lr_stream_t stream) {
+    return small_groups(p.B) ? run_fwd<H, 16>(p, stream) : run_fwd<H, 32>(p, stream);
+}
+template <int H> static int run_bwd_auto(const ls::Bwd& p, lr_stream_t stream) {
+    return small_groups(p.B) ? run_bwd<H, 16>(p, stream) : run_bwd<H, 32>(p, stream);
 }
 
 }  // namespace lsc
@@ -681,7 +693,7 @@ extern "C" int lr_lstm_fwd(const float* xproj, long long ldx, const float* bhh, 
     p.B = B; p.T = T; p.H = H; p.nsteps = nsteps; p.reverse = reverse;
     // more than one step of a long walk: the cluster kernel keeps W_hh in shared memory (H = 128 / 256)
     if (nsteps > 1 && (H == 128 || H == 256) && lr_lstm_use_cluster()) {
-        const int rc = H == 128 ? lsc::run_fwd<128>(p, stream) : lsc::run_fwd<256>(p, stream);
+        const int rc = H == 128 ? lsc::run_fwd_auto<128>(p, stream) : lsc::run_fwd_auto<256>(p, stream);
         if (rc) return rc;
         lr::count_launch();
         LR_CHECK_LAUNCH("lstm_fwd_cluster_kernel");
@@ -720,7 +732,7 @@ extern "C" int lr_lstm_bwd(const float* dout, long long ldo, int dout_step, cons
     p.dout = dout; p.ldo = ldo; p.gates = gates; p.cst = cst; p.whh = whh; p.dgates = dgates;
     p.B = B; p.T = T; p.H = H; p.nsteps = nsteps; p.reverse = reverse; p.dout_step = dout_step;
     if (nsteps > 1 && (H == 128 || H == 256) && lr_lstm_use_cluster()) {
-        const int rc = H == 128 ? lsc::run_bwd<128>(p, stream) : lsc::run_bwd<256>(p, stream);
+        const int rc = H == 128 ? lsc::run_bwd_auto<128>(p, stream) : lsc::run_bwd_auto<256>(p, stream);
         if (rc) return rc;
         lr::count_launch();
         LR_CHECK_LAUNCH("lstm_bwd_cluster_kernel");
