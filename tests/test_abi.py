@@ -47,3 +47,28 @@ def test_ops_refuse_cpu_tensors():
     from multimodal_lipread_b200 import ops
     with pytest.raises((NotImplementedError, RuntimeError)):
         ops.logmel(torch.zeros(1, 20000), torch.zeros(16, dtype=torch.uint8), 117, 0)
+
+
+def test_product_path_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU arm may touch it.  The
+    package and the B200 bench workloads must not import it (a product path through the oracle would void parity)."""
+    import ast
+    import glob
+    files = glob.glob(os.path.join(ROOT, "multimodal_lipread_b200", "*.py")) + [os.path.join(ROOT, "bench_workloads.py")]
+    assert len(files) > 10
+    for path in files:
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n == "oracle" or n.startswith("oracle.") for n in names), f"{path} imports the oracle"
+    # bench.py: the oracle appears only inside cpu_reference()
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+        uses = any(isinstance(n, ast.ImportFrom) and (n.module or "").startswith("oracle") for n in ast.walk(fn))
+        assert uses == (fn.name == "cpu_reference") or not uses, fn.name
+    src = open(os.path.join(ROOT, "multimodal_lipread_b200", "_lib.py")).read()
+    assert "raise ImportError" in src                      # a missing library fails loudly; there is no fallback
