@@ -125,6 +125,15 @@ int lr_gemm(const float* A, long long lda, int a_trans, const float* B, long lon
             long long ldc, int M, int N, int K, const float* bias, int act, const float* R, long long ldr,
             double* stats, int ksplit, lr_stream_t stream);
 
+/* Deterministic split-K for FORWARD GEMMs with a long reduction and few output tiles (audio_fc: K = 37120, M = batch,
+ * audio_video/models/middle_fusion_fast.py:13,30): slice z of the reduction stores its partial tile in ws[z][M][N] and a
+ * second kernel adds the slices in z order, then bias and activation -- no atomics, so two runs are bit-identical.
+ * ws: caller-allocated, lr_gemm_splitk_workspace_bytes(M, N, ksplit) bytes. */
+size_t lr_gemm_splitk_workspace_bytes(int M, int N, int ksplit);
+int lr_gemm_splitk(const float* A, long long lda, int a_trans, const float* B, long long ldb, int b_trans, float* C,
+                   long long ldc, int M, int N, int K, const float* bias, int act, int ksplit, float* ws,
+                   size_t ws_bytes, lr_stream_t stream);
+
 /* Tensor-core variant of lr_gemm (same layout flags and epilogue): TF32 products with fp32 accumulation
  * (tcgen05.mma kind::tf32; operands fetched by TMA from the fp32 matrices where they live, K-major or MN-major
  * with the 128-byte swizzle; accumulator in TMEM).  lda and ldb must be multiples of 4 floats, A and B 16-byte

@@ -9,13 +9,31 @@
 
 forward(mel (B,80,117), cue (B,768), lip (B,3,T,H,W) [or uint8 (B,T,H,W,3)]) -> (B, num_classes).
 Sub-modules are parameter containers (reference names / construction order / state_dict keys)."""
+import torch
 import torch.nn as nn
 from torchvision.models import mobilenet_v2, resnet18
 
 from . import engine
 from ._lib import ACT_RELU
-from .model_base import ModelPlan, PlanModel, N_MELS, N_FRAMES_OUT
+from .model_base import ModelPlan, PlanModel, N_MELS, N_FRAMES_OUT, load_torchvision_weights
 from .video_models import TimeDistributed
+
+
+def _load_pretrained_trunks(model):
+    """pretrained=True is the reference's default (audio_cues_video/models/*: resnet18 / mobilenet_v2 IMAGENET1K_V1 for
+    the audio and video encoders).  Offline the checkpoints come in as pretrained_state_dicts = {"audio": resnet18
+    state_dict, "video": mobilenet_v2 / resnet18 state_dict}; asked for and not supplied, the deviation is announced."""
+    pretrained, dicts = model._pretrained
+    if dicts:
+        with torch.no_grad():
+            for attr, sd in dicts.items():
+                if load_torchvision_weights(getattr(model, attr), sd) == 0:
+                    raise ValueError(f"pretrained_state_dicts[{attr!r}] matches no tensor of the {attr} encoder")
+    elif pretrained:
+        import warnings
+        warnings.warn(f"{type(model).__name__}: the reference initialises its audio / video trunks from ImageNet "
+                      "(pretrained=True); no pretrained_state_dicts were supplied, so they keep their random init "
+                      "(the frozen-backbone variants then train on frozen random features)", stacklevel=3)
 
 
 class AttentionFusion(nn.Module):
@@ -136,10 +154,10 @@ class MultimodalAttentionLate(PlanModel):
     PLAN = LateFusionPlan
     DEFAULT_LR = 1e-5            # audio_cues_video/configs/acv_config.yaml:14
 
-    def __init__(self, num_classes, cue_dim=768, video_cfg=None, pretrained=False, precision=None, lstm_dropout=0.3):
+    def __init__(self, num_classes, cue_dim=768, video_cfg=None, pretrained=False, precision=None, lstm_dropout=0.3,
+                 pretrained_state_dicts=None):
         super().__init__()
-        if pretrained:
-            raise ValueError("no network here: pass ImageNet weights through the sub-modules' pretrained_state_dict")
+        self._pretrained = (pretrained, pretrained_state_dicts)
         self._init_base(num_classes, type("C", (), {"get": staticmethod(lambda k, d=None: d)})(), precision)
         self.audio = AudioEncoder()
         self.cue = CueEncoder(cue_dim)
@@ -149,6 +167,7 @@ class MultimodalAttentionLate(PlanModel):
         self.cfc = nn.Linear(256, num_classes)
         self.vfc = nn.Linear(vdim, num_classes)
         self.attn = AttentionFusion(num_classes)
+        _load_pretrained_trunks(self)
 
 
 class ResNetLSTM(nn.Module):
@@ -172,10 +191,10 @@ class MultimodalAttentionLateResNet(PlanModel):
     PLAN = LateFusionPlan
     DEFAULT_LR = 1e-5
 
-    def __init__(self, num_classes, cue_dim=768, video_cfg=None, pretrained=False, precision=None, lstm_dropout=0.3):
+    def __init__(self, num_classes, cue_dim=768, video_cfg=None, pretrained=False, precision=None, lstm_dropout=0.3,
+                 pretrained_state_dicts=None):
         super().__init__()
-        if pretrained:
-            raise ValueError("no network here: pass ImageNet weights through the sub-modules' pretrained_state_dict")
+        self._pretrained = (pretrained, pretrained_state_dicts)
         self._init_base(num_classes, type("C", (), {"get": staticmethod(lambda k, d=None: d)})(), precision)
         self.audio = AudioEncoder()
         self.cue = CueEncoder(cue_dim)
@@ -185,6 +204,7 @@ class MultimodalAttentionLateResNet(PlanModel):
         self.vfc = nn.Linear(vdim, num_classes)
         self.cfc = nn.Linear(256, num_classes)
         self.attn = AttentionFusion(num_classes)
+        _load_pretrained_trunks(self)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -377,10 +397,9 @@ class _AttentionFusionModel(PlanModel):
     PLAN = AttentionFusionPlan
     DEFAULT_LR = 1e-4            # audio_cues_video/train.py:162  cfg.get("train.lr", 1e-4)
 
-    def _start(self, num_classes, pretrained, precision):
+    def _start(self, num_classes, pretrained, precision, pretrained_state_dicts=None):
         super().__init__()
-        if pretrained:
-            raise ValueError("no network here: load ImageNet weights into the sub-modules' state_dict instead")
+        self._pretrained = (pretrained, pretrained_state_dicts)
         self._init_base(num_classes, type("C", (), {"get": staticmethod(lambda k, d=None: d)})(), precision)
 
     @staticmethod
@@ -392,8 +411,8 @@ class MultimodalAttentionMiddle(_AttentionFusionModel):
     """audio_cues_video/models/middle_fusion_mobile.py:84-110 (train.model_name == "middle_fusion_mobile")."""
 
     def __init__(self, num_classes, cue_dim=768, video_cfg=None, pretrained=False, precision=None, lstm_dropout=0.3,
-                 head_dropout=0.4):
-        self._start(num_classes, pretrained, precision)
+                 head_dropout=0.4, pretrained_state_dicts=None):
+        self._start(num_classes, pretrained, precision, pretrained_state_dicts)
         self.audio = AudioEncoder()
         self.cue = CueEncoder(cue_dim)
         vdim = self._vdim(video_cfg)
@@ -403,13 +422,15 @@ class MultimodalAttentionMiddle(_AttentionFusionModel):
         self.attn = AttentionFusion(256)
         self.cls = nn.Sequential(nn.Linear(256, 512), nn.BatchNorm1d(512), nn.ReLU(), nn.Dropout(head_dropout),
                                  nn.Linear(512, num_classes))
+        _load_pretrained_trunks(self)
 
 
 class MultimodalAttentionMiddleResNet(_AttentionFusionModel):
     """audio_cues_video/models/middle_fusion_resnet.py:164-191 ("middle_fusion_resnet"): frozen ResNet-18 encoders."""
 
-    def __init__(self, num_classes, cue_dim=768, video_cfg=None, pretrained=False, precision=None, head_dropout=0.4):
-        self._start(num_classes, pretrained, precision)
+    def __init__(self, num_classes, cue_dim=768, video_cfg=None, pretrained=False, precision=None, head_dropout=0.4,
+                 pretrained_state_dicts=None):
+        self._start(num_classes, pretrained, precision, pretrained_state_dicts)
         self.audio = FrozenAudioEncoder("enc")
         self.cue = CueEncoder(cue_dim)
         vdim = self._vdim(video_cfg)
@@ -418,6 +439,7 @@ class MultimodalAttentionMiddleResNet(_AttentionFusionModel):
         self.vp = nn.Linear(vdim, 256)
         self.attn = AttentionFusion(256)
         self.cls = nn.Sequential(nn.Linear(256, 512), nn.ReLU(), nn.Dropout(head_dropout), nn.Linear(512, num_classes))
+        _load_pretrained_trunks(self)
 
 
 class MultimodalAttentionEarly(_AttentionFusionModel):
@@ -425,8 +447,8 @@ class MultimodalAttentionEarly(_AttentionFusionModel):
     frozen MobileNetV2 features under the chunked TimeDistributed, cp projection."""
 
     def __init__(self, num_classes, cue_dim=768, video_cfg=None, pretrained=False, precision=None, cue_dropout=0.3,
-                 head_dropout=0.4, trunk="mobilenet"):
-        self._start(num_classes, pretrained, precision)
+                 head_dropout=0.4, trunk="mobilenet", pretrained_state_dicts=None):
+        self._start(num_classes, pretrained, precision, pretrained_state_dicts)
         self.audio = FrozenAudioEncoder("encoder")
         self.cue = CueEncoderEarly(cue_dim, cue_dropout)
         vdim = self._vdim(video_cfg)
@@ -436,11 +458,13 @@ class MultimodalAttentionEarly(_AttentionFusionModel):
         self.cp = nn.Linear(256, 256)
         self.attn = AttentionFusion(256)
         self.classifier = nn.Sequential(nn.Linear(256, 256), nn.ReLU(), nn.Dropout(head_dropout), nn.Linear(256, num_classes))
+        _load_pretrained_trunks(self)
 
 
 class MultimodalAttentionEarlyResNet(MultimodalAttentionEarly):
     """audio_cues_video/models/early_fusion_resnet.py:158-191 ("early_fusion_resnet")."""
 
     def __init__(self, num_classes, cue_dim=768, video_cfg=None, pretrained=False, precision=None, cue_dropout=0.3,
-                 head_dropout=0.4):
-        super().__init__(num_classes, cue_dim, video_cfg, pretrained, precision, cue_dropout, head_dropout, trunk="resnet")
+                 head_dropout=0.4, pretrained_state_dicts=None):
+        super().__init__(num_classes, cue_dim, video_cfg, pretrained, precision, cue_dropout, head_dropout, trunk="resnet",
+                         pretrained_state_dicts=pretrained_state_dicts)

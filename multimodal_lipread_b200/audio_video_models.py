@@ -15,7 +15,7 @@ from torchvision.models import mobilenet_v3_small, resnet18
 
 from . import engine
 from ._lib import ACT_NONE, ACT_RELU
-from .model_base import Cfg, ModelPlan, PlanModel, N_MELS, N_FRAMES_OUT, video_layout
+from .model_base import Cfg, ModelPlan, PlanModel, N_MELS, N_FRAMES_OUT, video_layout, load_torchvision_weights
 
 _Cfg = Cfg
 _video_layout = video_layout
@@ -36,8 +36,6 @@ class MidFusionPlan(ModelPlan):
         dfused = self.alloc(B * FD) if with_backward else None
         KA = m.audio_fc.in_features
         ks = engine._ksplit(B, FA, KA, self.sms)
-        if ks > 1:
-            self.fwd.add("lr_memset", self.fused, B * FD * 4)          # split-K accumulates onto zeros
 
         # ---- audio branch (independent of the video trunk: its own branch of the step graph):
         #      [log-mel ->] conv+relu+pool -> [B,37120] -> audio_fc -> fused[:, 0:FA]
@@ -96,9 +94,9 @@ class MidFusionFast(PlanModel):
         self.classifier = nn.Sequential(nn.Linear(128 + 256, 256), nn.ReLU(), nn.Linear(256, num_classes))
 
 
-def create_mid_fusion_fast(num_classes, config=None):
+def create_mid_fusion_fast(num_classes, config=None, pretrained_state_dict=None):
     """audio_video/models/middle_fusion_fast.py:41-42."""
-    return MidFusionFast(num_classes, config)
+    return MidFusionFast(num_classes, config, pretrained_state_dict=pretrained_state_dict)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -219,19 +217,29 @@ class EarlyFusionAV(_EarlyFusionBase):
     backbone = "resnet18"
 
 
-def create_early_fusion_mobilenet_model(num_classes, config=None):
+def create_early_fusion_mobilenet_model(num_classes, config=None, pretrained_state_dict=None):
     """audio_video/models/early_fusion.py:116-117."""
-    return EarlyFusionAVMobileNet(num_classes, config)
+    return EarlyFusionAVMobileNet(num_classes, config, pretrained_state_dict=pretrained_state_dict)
 
 
-def create_early_fusion_resnet_model(num_classes, config=None):
+def create_early_fusion_resnet_model(num_classes, config=None, pretrained_state_dict=None):
     """audio_video/models/ef_cnn_lstm_resnet.py:132-133."""
-    return EarlyFusionAV(num_classes, config)
+    return EarlyFusionAV(num_classes, config, pretrained_state_dict=pretrained_state_dict)
 
 
 # ------------------------------------------------------------------------------------------------------------
 # The remaining audio_video models (all MobileNetV3-small video trunks, single-layer BiLSTM)
 # ------------------------------------------------------------------------------------------------------------
+def _load_mbv3(model):
+    """ImageNet mobilenet_v3_small checkpoint (torchvision key names) into the model's video trunk, when one was given."""
+    sd = getattr(model, "_pretrained_sd", None)
+    model._pretrained_sd = None
+    if sd is not None:
+        with torch.no_grad():
+            if load_torchvision_weights(model, sd) == 0:
+                raise ValueError("pretrained_state_dict matches no tensor of the video trunk")
+
+
 def _mbv3_lstm(config, hidden_default, pretrained_state_dict=None):
     base = mobilenet_v3_small(weights=None)
     if pretrained_state_dict is not None:
@@ -330,15 +338,17 @@ class LateFusionAVMobileNet(PlanModel):
     """audio_video/models/late_fusion.py:70-93."""
     PLAN = _AlphaLatePlan
 
-    def __init__(self, num_classes, config=None, precision=None):
+    def __init__(self, num_classes, config=None, pretrained_state_dict=None, precision=None):
         super().__init__()
         config = config or Cfg()
         self._init_base(num_classes, config, precision)
+        self._pretrained_sd = pretrained_state_dict
         self.audio_encoder = AudioEncoderLate(config)
         self.video_encoder = _VideoEncoderLstm(config, 256)
         self.audio_classifier = nn.Linear(self.audio_encoder.output_dim, num_classes)
         self.video_classifier = nn.Linear(self.video_encoder.output_dim, num_classes)
         self.alpha = nn.Parameter(torch.tensor(0.5))
+        _load_mbv3(self)
 
     def _parts(self):
         return (self.audio_encoder.cnn, self.audio_encoder.fc, self.audio_classifier, self.video_encoder.cnn,
@@ -349,10 +359,11 @@ class LateFusionFast(PlanModel):
     """audio_video/models/late_fusion_fast.py:5-59."""
     PLAN = _AlphaLatePlan
 
-    def __init__(self, num_classes, config=None, precision=None):
+    def __init__(self, num_classes, config=None, pretrained_state_dict=None, precision=None):
         super().__init__()
         config = config or Cfg()
         self._init_base(num_classes, config, precision)
+        self._pretrained_sd = pretrained_state_dict
         cin = config.get("dataset.audio_channels", 1)
         self.audio_cnn = nn.Sequential(nn.Conv2d(cin, 16, 3, padding=1), nn.ReLU(), nn.AdaptiveAvgPool2d((1, 1)))
         self.audio_fc = nn.Linear(16, config.get("model.audio_feature_dim", 128))
@@ -363,6 +374,7 @@ class LateFusionFast(PlanModel):
         self.video_lstm = nn.LSTM(input_size=576, hidden_size=128, num_layers=1, batch_first=True, bidirectional=True)
         self.video_classifier = nn.Linear(128 * 2, num_classes)
         self.alpha = nn.Parameter(torch.tensor(0.5))
+        _load_mbv3(self)
 
     def _parts(self):
         return self.audio_cnn, self.audio_fc, self.audio_classifier, self.video_cnn, self.video_lstm, self.video_classifier
@@ -407,15 +419,17 @@ class MidFusionAVMobileNet(PlanModel):
     PLAN = _ConcatFusionPlan
     head = "last"
 
-    def __init__(self, num_classes, config=None, precision=None):
+    def __init__(self, num_classes, config=None, pretrained_state_dict=None, precision=None):
         super().__init__()
         config = config or Cfg()
         self._init_base(num_classes, config, precision)
+        self._pretrained_sd = pretrained_state_dict
         self.audio_encoder = AudioEncoderMid(config)
         self.video_encoder = _VideoEncoderLstm(config, 256)
         fusion_dim = self.audio_encoder.output_dim + self.video_encoder.output_dim
         self.classifier = nn.Sequential(nn.Linear(fusion_dim, 512), nn.ReLU(),
                                         nn.Dropout(config.get("model.classifier_dropout", 0.3)), nn.Linear(512, num_classes))
+        _load_mbv3(self)
 
 
 class EarlyFusionFast(PlanModel):
@@ -423,31 +437,33 @@ class EarlyFusionFast(PlanModel):
     PLAN = _ConcatFusionPlan
     head = "hn"
 
-    def __init__(self, num_classes, config=None, precision=None):
+    def __init__(self, num_classes, config=None, pretrained_state_dict=None, precision=None):
         super().__init__()
         config = config or Cfg()
         self._init_base(num_classes, config, precision)
+        self._pretrained_sd = pretrained_state_dict
         self.audio_encoder = AudioEncoderFast(config)
         self.video_encoder = _VideoEncoderLstm(config, 128)
         fusion_dim = self.audio_encoder.output_dim + self.video_encoder.output_dim
         self.classifier = nn.Sequential(nn.Linear(fusion_dim, 256), nn.ReLU(), nn.Linear(256, num_classes))
+        _load_mbv3(self)
 
 
-def create_late_fusion_mobilenet_model(num_classes, config=None):
+def create_late_fusion_mobilenet_model(num_classes, config=None, pretrained_state_dict=None):
     """audio_video/models/late_fusion.py:98-99."""
-    return LateFusionAVMobileNet(num_classes, config)
+    return LateFusionAVMobileNet(num_classes, config, pretrained_state_dict=pretrained_state_dict)
 
 
-def create_mid_fusion_mobilenet_model(num_classes, config=None):
+def create_mid_fusion_mobilenet_model(num_classes, config=None, pretrained_state_dict=None):
     """audio_video/models/middle_fusion.py:91-92."""
-    return MidFusionAVMobileNet(num_classes, config)
+    return MidFusionAVMobileNet(num_classes, config, pretrained_state_dict=pretrained_state_dict)
 
 
-def create_early_fusion_fast(num_classes, config=None):
+def create_early_fusion_fast(num_classes, config=None, pretrained_state_dict=None):
     """audio_video/models/early_fusion_fast.py:79-80."""
-    return EarlyFusionFast(num_classes, config)
+    return EarlyFusionFast(num_classes, config, pretrained_state_dict=pretrained_state_dict)
 
 
-def create_late_fusion_fast(num_classes, config=None):
+def create_late_fusion_fast(num_classes, config=None, pretrained_state_dict=None):
     """audio_video/models/late_fusion_fast.py:62-63."""
-    return LateFusionFast(num_classes, config)
+    return LateFusionFast(num_classes, config, pretrained_state_dict=pretrained_state_dict)

@@ -1,7 +1,9 @@
 // ABI bookkeeping: version, thread-local error message, launch counter, cached device attributes.
 #include "common.cuh"
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <utility>
 
 namespace lr {
 
@@ -19,6 +21,21 @@ int fail(int code, const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+cudaError_t ensure_max_dynamic_smem(const void* func, int bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, int> done;          // (device, kernel) -> configured limit
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(dev, func);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done[key] = bytes;
+    return e;
+}
 
 int sm_count() {
     // Immutable after first use; one value per process is enough (one process drives one GPU).

@@ -233,29 +233,37 @@ bn_act_bwd_apply_kernel(const Bn b, const float* __restrict__ x, const float* __
 // ------------------------------------------------------------------------- per-frame pooling / SE
 // mode 0: p[f,c]  = mean_hw a[f,hw,c]
 // mode 1: p[f,c]  = sum_hw a[f,hw,c] * g[f,hw,c]        (ds of the SE scale)
+// Deterministic: every thread sums its row lane in index order, the row lanes of a channel are then added in lane
+// order from a shared-memory slab -- no atomics, so two runs on the same input are bit-identical (eval forwards,
+// validate() and model selection depend on that).
 __global__ void __launch_bounds__(TH)
 frame_reduce_kernel(const float* __restrict__ a, const float* __restrict__ g, float* __restrict__ p, int HW, int C,
                     int mode) {
-    extern __shared__ float sh[];                       // [C]
-    for (int i = threadIdx.x; i < C; i += blockDim.x) sh[i] = 0.f;
-    __syncthreads();
+    __shared__ __align__(16) float sh[TH * 4];          // [row lane][4 * groups of this pass]
     const long long f = blockIdx.x;
+    const float sc = mode == 0 ? 1.f / (float)HW : 1.f;
     for (int cg0 = 0; cg0 < (C >> 2); cg0 += blockDim.x) {
         const nn::CgMap map(C, cg0);
-        if (!map.active) continue;
-        const int c = map.cg * 4;
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = map.rlane; r < HW; r += map.rpp) {
-            const long long off = (f * HW + r) * C + c;
-            float4 v = nn::ld4(a + off);
-            if (mode == 1) { const float4 w = nn::ld4(g + off); v.x *= w.x; v.y *= w.y; v.z *= w.z; v.w *= w.w; }
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        const int w = min(map.ncg - cg0, (int)blockDim.x);               // channel groups of this pass
+        if (map.active) {
+            const int c = map.cg * 4;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = map.rlane; r < HW; r += map.rpp) {
+                const long long off = (f * HW + r) * C + c;
+                float4 v = nn::ld4(a + off);
+                if (mode == 1) { const float4 q = nn::ld4(g + off); v.x *= q.x; v.y *= q.y; v.z *= q.z; v.w *= q.w; }
+                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            }
+            *reinterpret_cast<float4*>(&sh[(map.rlane * w + (map.cg - cg0)) * 4]) = s;
         }
-        atomicAdd(&sh[c], s.x); atomicAdd(&sh[c + 1], s.y); atomicAdd(&sh[c + 2], s.z); atomicAdd(&sh[c + 3], s.w);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 4 * w; i += blockDim.x) {
+            float t = 0.f;
+            for (int rl = 0; rl < map.rpp; ++rl) t += sh[rl * 4 * w + i];
+            p[f * C + cg0 * 4 + i] = t * sc;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const float sc = mode == 0 ? 1.f / (float)HW : 1.f;
-    for (int i = threadIdx.x; i < C; i += blockDim.x) p[f * C + i] = sh[i] * sc;
 }
 
 // out[f,hw,c] = (a ? a[f,hw,c] * s[f,c] : 0) + (dp ? dp[f,c] * inv_hw : 0)
@@ -404,7 +412,7 @@ extern "C" int lr_frame_reduce(const float* a, const float* g, float* p, int F, 
     if (F == 0) return LR_OK;
     LR_CHECK_ARG(a && p, "lr_frame_reduce: null pointer");
     LR_CHECK_ALIGN(a); LR_CHECK_ALIGN(g);
-    bn::frame_reduce_kernel<<<F, bn::TH, C * sizeof(float), stream>>>(a, g, p, HW, C, mode);
+    bn::frame_reduce_kernel<<<F, bn::TH, 0, stream>>>(a, g, p, HW, C, mode);
     lr::count_launch();
     LR_CHECK_LAUNCH("frame_reduce_kernel");
     return LR_OK;

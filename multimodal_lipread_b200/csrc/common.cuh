@@ -36,6 +36,12 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
     } while (0)
 
 void count_launch(int n = 1);
+// Raise a kernel's opt-in dynamic shared-memory limit to `bytes` once per (device, kernel); thread-safe, and a later
+// call with a smaller size never lowers a limit that captured graph nodes rely on.
+cudaError_t ensure_max_dynamic_smem(const void* func, int bytes);
+template <typename F> inline cudaError_t ensure_max_dynamic_smem(F* func, int bytes) {
+    return ensure_max_dynamic_smem(reinterpret_cast<const void*>(func), bytes);
+}
 int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
 
 // uint8 pixel -> float.  The reference divides (`lip_regions.astype(np.float32) / 255.0`,

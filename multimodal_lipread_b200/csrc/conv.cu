@@ -49,9 +49,8 @@ __global__ void __launch_bounds__(TH)
 stem_fwd_kernel(const StemIn2 s, const float* __restrict__ w /*[16][3][3][3]*/, float* __restrict__ y,
                 double* __restrict__ stats) {
     __shared__ float ws[ST][SC];      // [ci*9 + kh*3 + kw][co]
-    __shared__ float ssum[SC], ssq[SC];
+    __shared__ float ssum[TH / 32][SC], ssq[TH / 32][SC];      // one row per warp, added in warp order (no float atomics)
     for (int i = threadIdx.x; i < ST * SC; i += TH) { const int co = i / ST, tp = i - co * ST; ws[tp][co] = w[i]; }
-    if (threadIdx.x < SC) { ssum[threadIdx.x] = 0.f; ssq[threadIdx.x] = 0.f; }
     __syncthreads();
     const int Ho = s.in.Ho, Wo = s.in.Wo, H = s.in.H, W = s.in.W;
     const long long total = (long long)s.in.F * Ho * Wo;
@@ -91,12 +90,15 @@ stem_fwd_kernel(const StemIn2 s, const float* __restrict__ w /*[16][3][3][3]*/, 
 #pragma unroll
     for (int c = 0; c < SC; ++c) {
         const float a = lr::warp_sum(lsum[c]), b = lr::warp_sum(lsq[c]);
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&ssum[c], a); atomicAdd(&ssq[c], b); }
+        if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5][c] = a; ssq[threadIdx.x >> 5][c] = b; }
     }
     __syncthreads();
     if (threadIdx.x < SC) {
-        nn::atomic_add_double(stats + threadIdx.x, (double)ssum[threadIdx.x]);
-        nn::atomic_add_double(stats + SC + threadIdx.x, (double)ssq[threadIdx.x]);
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w_ = 0; w_ < TH / 32; ++w_) { a += ssum[w_][threadIdx.x]; b += ssq[w_][threadIdx.x]; }
+        nn::atomic_add_double(stats + threadIdx.x, (double)a);
+        nn::atomic_add_double(stats + SC + threadIdx.x, (double)b);
     }
 }
 

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(TH)
 fwd_kernel(const Geo d, const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
            double* __restrict__ stats) {
     extern __shared__ __align__(16) float smem[];
-    __shared__ float ssum[32], ssq[32];
+    __shared__ float ssum[TH], ssq[TH];                 // one slot per thread: [row lane][channel], added in lane order
     __shared__ int tab[MAX_PIX];
     build_pixel_table(d, tab);
     __syncthreads();
@@ -92,7 +92,6 @@ fwd_kernel(const Geo d, const float* __restrict__ x, const float* __restrict__ w
     const bool ok = c < d.C;
     const int tile_floats = d.UB * d.rows_t * d.cols_t * d.CC;
     const int rounds = (int)((d.units + d.UB - 1) / d.UB);
-    if (threadIdx.x < 32) { ssum[threadIdx.x] = 0.f; ssq[threadIdx.x] = 0.f; }
     float wr[K * K];
     load_weights<K>(w, c, ok, wr);
     constexpr int NX = (WS - 1) * S + K;               // input columns one row segment touches
@@ -142,11 +141,15 @@ fwd_kernel(const Geo d, const float* __restrict__ x, const float* __restrict__ w
         buf ^= 1;
     }
     if (stats) {
-        if (ok) { atomicAdd(&ssum[cl], ls); atomicAdd(&ssq[cl], lq); }
+        // fixed-order block reduction (no float atomics: the forward is bit-reproducible); across blocks the double
+        // atomics add 24-bit partials into 53-bit sums, exact unless the partials span more than 2^29
+        ssum[threadIdx.x] = ok ? ls : 0.f; ssq[threadIdx.x] = ok ? lq : 0.f;
         __syncthreads();
         if (threadIdx.x < d.CC && chunk * d.CC + threadIdx.x < d.C) {
-            nn::atomic_add_double(stats + chunk * d.CC + threadIdx.x, (double)ssum[threadIdx.x]);
-            nn::atomic_add_double(stats + d.C + chunk * d.CC + threadIdx.x, (double)ssq[threadIdx.x]);
+            float a = 0.f, b = 0.f;
+            for (int l = 0; l < nrl; ++l) { a += ssum[l * d.CC + threadIdx.x]; b += ssq[l * d.CC + threadIdx.x]; }
+            nn::atomic_add_double(stats + chunk * d.CC + threadIdx.x, (double)a);
+            nn::atomic_add_double(stats + d.C + chunk * d.CC + threadIdx.x, (double)b);
         }
     }
 }
@@ -397,11 +400,7 @@ constexpr int SMEM_CEILING = 160 * 1024;
 
 #define DW_LAUNCH(KERNEL, K_, S_, WS_, ...)                                              \
     do {                                                                                 \
-        static bool configured = false;                                                  \
-        if (!configured) {                                                               \
-            err = cudaFuncSetAttribute(KERNEL<K_, S_, WS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CEILING); \
-            configured = err == cudaSuccess;                                             \
-        }                                                                                \
+        err = lr::ensure_max_dynamic_smem(KERNEL<K_, S_, WS_>, SMEM_CEILING);            \
         if (err == cudaSuccess && smem > (size_t)SMEM_CEILING) err = cudaErrorInvalidValue; \
         if (err == cudaSuccess) KERNEL<K_, S_, WS_><<<grid, TH, smem, stream>>>(__VA_ARGS__); \
     } while (0)

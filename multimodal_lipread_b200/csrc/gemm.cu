@@ -24,6 +24,7 @@ struct P {
     const float* bias; const float* R;
     double* stats;
     int act, kchunk;
+    float* part;            // ordered split-K: slice z stores its partial tile at part[z][M][N] instead of adding into C
 };
 
 // tile source contiguous along k: stored [rows][K]; thread -> (row = t>>2, 4 consecutive k)
@@ -130,6 +131,12 @@ __global__ void __launch_bounds__(TH) gemm_kernel(const P p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bias[j];
         float* crow = p.C + (long long)m * p.ldc + n;
+        if (p.part) {                                      // ordered split-K: plain stores, reduced in slice order later
+            float* prow = p.part + ((long long)blockIdx.z * p.M + m) * p.N + n;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (n + j < p.N) prow[j] = acc[i][j];
+            continue;
+        }
         if (gridDim.z > 1) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) if (n + j < p.N) atomicAdd(crow + j, v[j]);
@@ -171,6 +178,20 @@ __global__ void __launch_bounds__(TH) gemm_kernel(const P p) {
     }
 }
 
+// C[m,n] = act(sum_z part[z][m][n] + bias[n]), slices added in z order (deterministic split-K, second pass)
+__global__ void __launch_bounds__(TH)
+splitk_reduce_kernel(const float* __restrict__ part, int nz, float* __restrict__ C, long long ldc, int M, int N,
+                     const float* __restrict__ bias, int act) {
+    const long long total = (long long)M * N;
+    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < total; i += (long long)gridDim.x * TH) {
+        const int m = (int)(i / N), n = (int)(i - (long long)m * N);
+        float s = 0.f;
+        for (int z = 0; z < nz; ++z) s += part[(long long)z * total + i];
+        if (bias) s += bias[n];
+        C[(long long)m * ldc + n] = nn::act_fwd(s, act);
+    }
+}
+
 }  // namespace gm
 
 extern "C" int lr_gemm(const float* A, long long lda, int a_trans, const float* B, long long ldb, int b_trans,
@@ -186,6 +207,7 @@ extern "C" int lr_gemm(const float* A, long long lda, int a_trans, const float* 
     gm::P p;
     p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K;
     p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldr = ldr; p.bias = bias; p.R = R; p.stats = stats; p.act = act;
+    p.part = nullptr;
     int kchunk = (K + ksplit - 1) / ksplit;
     kchunk = ((kchunk + gm::BK - 1) / gm::BK) * gm::BK;
     if (kchunk == 0) kchunk = gm::BK;
@@ -203,5 +225,49 @@ extern "C" int lr_gemm(const float* A, long long lda, int a_trans, const float* 
     }
     lr::count_launch();
     LR_CHECK_LAUNCH("gemm_kernel");
+    return LR_OK;
+}
+
+extern "C" size_t lr_gemm_splitk_workspace_bytes(int M, int N, int ksplit) {
+    return (size_t)(ksplit < 1 ? 1 : ksplit) * (size_t)M * (size_t)N * sizeof(float);
+}
+
+extern "C" int lr_gemm_splitk(const float* A, long long lda, int a_trans, const float* B, long long ldb, int b_trans,
+                              float* C, long long ldc, int M, int N, int K, const float* bias, int act, int ksplit,
+                              float* ws, size_t ws_bytes, lr_stream_t stream) {
+    LR_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "lr_gemm_splitk: negative dimension");
+    if (M == 0 || N == 0) return LR_OK;
+    LR_CHECK_ARG(A && B && C && ws, "lr_gemm_splitk: null pointer");
+    LR_CHECK_ARG(act >= LR_ACT_NONE && act <= LR_ACT_RELU6, "lr_gemm_splitk: bad activation %d", act);
+    LR_CHECK_ARG(ksplit >= 1, "lr_gemm_splitk: ksplit must be >= 1");
+    if (ws_bytes < lr_gemm_splitk_workspace_bytes(M, N, ksplit))
+        return lr::fail(LR_ENOSPC, "lr_gemm_splitk: workspace %zu < %zu bytes", ws_bytes,
+                        lr_gemm_splitk_workspace_bytes(M, N, ksplit));
+    gm::P p;
+    p.A = A; p.B = B; p.C = C; p.M = M; p.N = N; p.K = K;
+    p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldr = 0; p.bias = nullptr; p.R = nullptr; p.stats = nullptr; p.act = LR_ACT_NONE;
+    p.part = ws;
+    int kchunk = (K + ksplit - 1) / ksplit;
+    kchunk = ((kchunk + gm::BK - 1) / gm::BK) * gm::BK;
+    if (kchunk == 0) kchunk = gm::BK;
+    const int nz = K == 0 ? 1 : (K + kchunk - 1) / kchunk;      // <= ksplit: every slice z < nz writes its whole tile
+    p.kchunk = kchunk;
+    const long long mt = (M + gm::BM - 1) / gm::BM, nt = (N + gm::BN - 1) / gm::BN;
+    LR_CHECK_ARG(nt <= 65535 && nz <= 65535, "lr_gemm_splitk: N or split too large");
+    dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)nz);
+    if (a_trans) {
+        if (b_trans) gm::gemm_kernel<true, true><<<grid, gm::TH, 0, stream>>>(p);
+        else gm::gemm_kernel<true, false><<<grid, gm::TH, 0, stream>>>(p);
+    } else {
+        if (b_trans) gm::gemm_kernel<false, true><<<grid, gm::TH, 0, stream>>>(p);
+        else gm::gemm_kernel<false, false><<<grid, gm::TH, 0, stream>>>(p);
+    }
+    lr::count_launch();
+    LR_CHECK_LAUNCH("gemm_kernel (ordered split-K)");
+    long long g = ((long long)M * N + gm::TH - 1) / gm::TH;
+    if (g > 4LL * lr::sm_count()) g = 4LL * lr::sm_count();
+    gm::splitk_reduce_kernel<<<(unsigned)g, gm::TH, 0, stream>>>(ws, nz, C, ldc, M, N, bias, act);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("splitk_reduce_kernel");
     return LR_OK;
 }

@@ -152,7 +152,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 1];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ __align__(16) float s_sum[256], s_sq[256], s_bias[256];
+    __shared__ __align__(16) float s_sum[4][256], s_sq[4][256], s_bias[256];   // statistics: one row per epilogue warp
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.BN;
@@ -170,7 +170,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (threadIdx.x == 0) LR_STAMP(0);
     for (int i = threadIdx.x; i < 256; i += THREADS) {
-        s_sum[i] = 0.f; s_sq[i] = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { s_sum[w][i] = 0.f; s_sq[w][i] = 0.f; }
         s_bias[i] = (p.bias && i < p.BN && blockIdx.y * p.BN + i < p.N) ? p.bias[blockIdx.y * p.BN + i] : 0.f;
     }
     if (threadIdx.x == 0) {
@@ -326,8 +327,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             a += x; b = fmaf(x, x, b);
                         }
                     }
-                    atomicAdd(&s_sum[c0 + lane], a);
-                    atomicAdd(&s_sq[c0 + lane], b);
+                    s_sum[q][c0 + lane] = a;                                 // warp q's own slot: no atomics, the four
+                    s_sq[q][c0 + lane] = b;                                  // warps are added in fixed order below
                 }
                 if (threadIdx.x == 64 && nbox == 1) LR_STAMP(24);
             }
@@ -388,8 +389,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int c = lane; c < pwv; c += 32) {
                     float a = 0.f, b = 0.f;
                     for (int r = 0; r < rv; ++r) { const float x = slab[r * EPI_PITCH + c]; a += x; b = fmaf(x, x, b); }
-                    atomicAdd(&s_sum[p0 + c], a);
-                    atomicAdd(&s_sq[p0 + c], b);
+                    s_sum[q][p0 + c] = a;
+                    s_sq[q][p0 + c] = b;
                 }
             }
             __syncwarp();
@@ -399,13 +400,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.stats) {
             asm volatile("bar.sync 1, 128;" ::: "memory");            // the four epilogue warps only
             const int col = threadIdx.x - 64;
-            if (col < p.BN && n0 + col < p.N) {
-                nn::atomic_add_double(p.stats + n0 + col, (double)s_sum[col]);
-                nn::atomic_add_double(p.stats + p.N + n0 + col, (double)s_sq[col]);
-            }
-            if (col + 128 < p.BN && n0 + col + 128 < p.N) {
-                nn::atomic_add_double(p.stats + n0 + col + 128, (double)s_sum[col + 128]);
-                nn::atomic_add_double(p.stats + p.N + n0 + col + 128, (double)s_sq[col + 128]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int cc = col + 128 * h;
+                if (cc < p.BN && n0 + cc < p.N) {
+                    // the CTA's 128 rows in fixed warp order; across CTAs the double atomics add 24-bit partials into
+                    // 53-bit sums, which is exact (order-independent) unless the partials span more than 2^29
+                    const float cs = (s_sum[0][cc] + s_sum[1][cc]) + (s_sum[2][cc] + s_sum[3][cc]);
+                    const float cq = (s_sq[0][cc] + s_sq[1][cc]) + (s_sq[2][cc] + s_sq[3][cc]);
+                    nn::atomic_add_double(p.stats + n0 + cc, (double)cs);
+                    nn::atomic_add_double(p.stats + p.N + n0 + cc, (double)cq);
+                }
             }
         }
     }
@@ -502,14 +507,12 @@ extern "C" int lr_gemm_tf32(const float* A, long long lda, int a_trans, const fl
     size_t smem = (size_t)p.stages * (tc::A_STAGE_BYTES + b_stage);
     if (smem < (size_t)tc::EPI_BYTES) smem = tc::EPI_BYTES;           // the epilogue slabs reuse the pipeline buffers
     smem += 1024;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc::gemm_tf32_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tf32_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tf32_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tf32_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    {
+        cudaError_t e = lr::ensure_max_dynamic_smem(tc::gemm_tf32_kernel<false, false>, 200 * 1024);
+        if (e == cudaSuccess) e = lr::ensure_max_dynamic_smem(tc::gemm_tf32_kernel<false, true>, 200 * 1024);
+        if (e == cudaSuccess) e = lr::ensure_max_dynamic_smem(tc::gemm_tf32_kernel<true, true>, 200 * 1024);
+        if (e == cudaSuccess) e = lr::ensure_max_dynamic_smem(tc::gemm_tf32_kernel<true, false>, 200 * 1024);
         if (e != cudaSuccess) return lr::fail(LR_ECUDA, "lr_gemm_tf32 smem: %s", cudaGetErrorString(e));
-        configured = true;
     }
     dim3 grid((unsigned)((M + tc::BM - 1) / tc::BM), (unsigned)((N + bn - 1) / bn), (unsigned)nz);
     if (a_trans) {

@@ -99,32 +99,45 @@ audio_conv_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dA,
     }
 }
 
-// one warp per row: loss += -log_softmax(logits)[label] * inv_n ; dlogits = (softmax - onehot) * inv_n
-__global__ void __launch_bounds__(TH)
+// One block, one warp per row at a time: loss += -log_softmax(logits)[label] * inv_n ; dlogits = (softmax - onehot) * inv_n.
+// Every warp walks its rows in index order and the per-warp partial losses are added in warp order, so the loss is
+// bit-reproducible (a batch is at most a few hundred rows of <= 40 logits: one block is plenty).
+constexpr int CE_TH = 1024;
+__global__ void __launch_bounds__(CE_TH)
 ce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, float* __restrict__ loss,
           float* __restrict__ dlogits, int* __restrict__ correct, int B, int C, float inv_n) {
-    const int row = blockIdx.x * (TH / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= B) return;
-    const float* l = logits + (long long)row * C;
-    float mx = -INFINITY; int am = 0;
-    for (int j = lane; j < C; j += 32) if (l[j] > mx) { mx = l[j]; am = j; }
-    // arg-max with the lowest index on ties (torch.max semantics)
+    __shared__ float wloss[CE_TH / 32];
+    __shared__ int wcorr[CE_TH / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float lsum = 0.f; int csum = 0;
+    for (int row = warp; row < B; row += CE_TH / 32) {
+        const float* l = logits + (long long)row * C;
+        float mx = -INFINITY; int am = 0;
+        for (int j = lane; j < C; j += 32) if (l[j] > mx) { mx = l[j]; am = j; }
+        // arg-max with the lowest index on ties (torch.max semantics)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-        const int oa = __shfl_xor_sync(0xffffffffu, am, o);
-        if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+            if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
+        }
+        float se = 0.f;
+        for (int j = lane; j < C; j += 32) se += expf(l[j] - mx);
+        se = lr::warp_sum(se);
+        const float lse = logf(se) + mx;
+        const int y = (int)labels[row];
+        if (dlogits)
+            for (int j = lane; j < C; j += 32) dlogits[(long long)row * C + j] = (expf(l[j] - lse) - (j == y ? 1.f : 0.f)) * inv_n;
+        lsum += (lse - l[y]) * inv_n;
+        csum += (am == y) ? 1 : 0;
     }
-    float se = 0.f;
-    for (int j = lane; j < C; j += 32) se += expf(l[j] - mx);
-    se = lr::warp_sum(se);
-    const float lse = logf(se) + mx;
-    const int y = (int)labels[row];
-    if (dlogits)
-        for (int j = lane; j < C; j += 32) dlogits[(long long)row * C + j] = (expf(l[j] - lse) - (j == y ? 1.f : 0.f)) * inv_n;
-    if (lane == 0) {
-        atomicAdd(loss, (lse - l[y]) * inv_n);
-        if (correct && am == y) atomicAdd(correct, 1);
+    if (lane == 0) { wloss[warp] = lsum; wcorr[warp] = csum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f; int n = 0;
+        for (int w = 0; w < CE_TH / 32; ++w) { t += wloss[w]; n += wcorr[w]; }
+        *loss += t;                                  // accumulates onto the caller's (zeroed) scalar, as before
+        if (correct) *correct += n;
     }
 }
 
@@ -190,7 +203,7 @@ extern "C" int lr_ce_loss(const float* logits, const long long* labels, float* l
     LR_CHECK_ARG(B >= 0 && C > 0, "lr_ce_loss: bad shape");
     if (B == 0) return LR_OK;
     LR_CHECK_ARG(logits && labels && loss, "lr_ce_loss: null pointer");
-    hd::ce_kernel<<<(B + hd::TH / 32 - 1) / (hd::TH / 32), hd::TH, 0, stream>>>(logits, labels, loss, dlogits, correct, B, C, inv_n);
+    hd::ce_kernel<<<1, hd::CE_TH, 0, stream>>>(logits, labels, loss, dlogits, correct, B, C, inv_n);
     lr::count_launch();
     LR_CHECK_LAUNCH("ce_kernel");
     return LR_OK;

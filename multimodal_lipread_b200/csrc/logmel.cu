@@ -203,8 +203,7 @@ extern "C" int lr_logmel_fwd(const float* wav, const void* plan, float* out, int
     LR_CHECK_ARG(mode != LR_LOGMEL_RAW || n_out == lm::NFRAMES, "lr_logmel_fwd: raw mode needs n_out == 126");
     LR_CHECK_ALIGN(wav); LR_CHECK_ALIGN(plan); LR_CHECK_ALIGN(out);
     static const int smem = int(sizeof(lm::Smem));
-    static const cudaError_t attr = cudaFuncSetAttribute(lm::logmel_kernel,
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const cudaError_t attr = lr::ensure_max_dynamic_smem(lm::logmel_kernel, smem);
     if (attr != cudaSuccess) return lr::fail(LR_ECUDA, "logmel smem attribute: %s", cudaGetErrorString(attr));
     const int grid = B < lr::sm_count() ? B : lr::sm_count();
     lm::logmel_kernel<<<grid, lm::THREADS, smem, stream>>>(wav, static_cast<const lm::Plan*>(plan), out, B,

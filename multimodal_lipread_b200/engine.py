@@ -195,6 +195,17 @@ def _ksplit(M, N, K, sms, min_k=256):
     return max(1, min(want, K // min_k if K >= min_k else 1))
 
 
+def dropout_seed(layer_index):
+    """Seed of one dropout layer's counter-based generator: torch's global seed (so torch.manual_seed selects the mask
+    sequence, as it does for the reference's nn.Dropout), the data-parallel rank (replicas draw different masks, as
+    independent torch processes would) and the layer's index in the plan."""
+    base = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    rank = int(os.environ.get("RANK", "0"))
+    x = (base * 0x9E3779B97F4A7C15 + (rank + 1) * 0xBF58476D1CE4E5B9 + layer_index * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    x ^= x >> 31
+    return x & 0x7FFFFFFFFFFFFFFF
+
+
 class FlatParams:
     """All parameters of a module in ONE flat fp32 buffer (+ gradient, Adam moments); the module's Parameters
     become views into it, so state_dict()/load_state_dict() keep working with the reference's key names."""
@@ -213,6 +224,7 @@ class FlatParams:
         self.m = None
         self.v = None
         self.adam_state = None
+        self.rng_step = None                           # device counter behind the dropout masks (created on first use)
         for p, o in zip(self.params, offs):
             view = self.flat[o:o + p.numel()].view(p.shape)
             view.copy_(p.detach().to(self.device, torch.float32))
@@ -355,7 +367,10 @@ class Plan:
     def linear(self, x, lda, M, w, b, out, ldc, act=ACT_NONE, stats=0, ksplit=1):
         N, K = w.shape[0], w[0].numel()
         if ksplit > 1:
-            self.gemm(self.fwd, x, lda, 0, w, K, 0, out, ldc, M, N, K, bias=(b if b is not None else 0), ksplit=ksplit)
+            # forward split-K is the ORDERED kind (partials in a workspace, reduced in slice order): bit-reproducible
+            ws = self.alloc(ksplit * M * N)
+            self.fwd.add("lr_gemm_splitk", x, lda, 0, w, K, 0, out, ldc, M, N, K, (b if b is not None else 0), act, ksplit,
+                         ws, ws.numel() * 4)
         else:
             self.gemm_auto(self.fwd, x, lda, 0, w, K, 0, out, ldc, M, N, K, bias=(b if b is not None else 0), act=act,
                            stats=stats)
@@ -761,11 +776,14 @@ class Plan:
         if not self.dropout_active(p):
             return x, dx
         if self.rng_step is None:
-            self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.dev)
-            self.bufs.append(self.rng_step)
+            # ONE device counter per model (shared by all its plans, saved in checkpoints): a new batch shape or a
+            # resumed run continues the mask sequence instead of restarting it
+            if self.flat.rng_step is None:
+                self.flat.rng_step = torch.zeros(1, dtype=torch.int64, device=self.dev)
+            self.rng_step = self.flat.rng_step
         self._n_dropout += 1
         y, mask = self.alloc(n), self.alloc(n, torch.uint8)
-        self.fwd.add("lr_dropout_fwd", x, y, mask, n, float(p), 0x5EED0000 + self._n_dropout, self.rng_step)
+        self.fwd.add("lr_dropout_fwd", x, y, mask, n, float(p), dropout_seed(self._n_dropout), self.rng_step)
         if self.with_backward:
             dy = self.alloc(n) if dy is None else dy
             if dx is not None:

@@ -34,6 +34,50 @@ class Cfg:
         return cur
 
 
+def load_torchvision_weights(module, state_dict):
+    """Copy a torchvision checkpoint (e.g. IMAGENET1K_V1 of resnet18 / mobilenet_v2 / mobilenet_v3_small, torchvision key
+    names) into `module`, whatever prefix the trunk sits under: every entry of module.state_dict() takes the
+    checkpoint tensor whose key equals one of the entry's dotted suffixes (optionally under "features.") and whose
+    shape matches.  Layers the reference re-creates after loading (a 1-channel conv1, fc = Identity) simply find
+    no match.  Returns the number of tensors copied."""
+    own = module.state_dict()
+    n = 0
+    for key, dst in own.items():
+        parts = key.split(".")
+        for i in range(len(parts)):
+            tail = ".".join(parts[i:])
+            for cand in (tail, "features." + tail):
+                src = state_dict.get(cand)
+                if src is not None and tuple(src.shape) == tuple(dst.shape):
+                    dst.copy_(src)
+                    n += 1
+                    break
+            else:
+                continue
+            break
+    return n
+
+
+def pretrained_weights(config, explicit, what):
+    """The ImageNet checkpoint the reference downloads (weights=...IMAGENET1K_V1 / pretrained=True:
+    audio_video/models/middle_fusion_fast.py:15, video/models/resnet_lstm.py:80, audio_cues_video/models/*).  There is
+    no network here, so it comes from the caller: `explicit` (a state_dict) or the YAML key `model.pretrained_weights`
+    (a torch.save'd state_dict).  With neither, the trunk keeps its seeded random init -- a DEVIATION from the
+    reference's flow that is announced, not silent (for the frozen-backbone models it means frozen random features)."""
+    if explicit is not None:
+        return explicit
+    path = config.get("model.pretrained_weights", None) if config is not None else None
+    if path:
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"model.pretrained_weights not found: {path}")
+        return torch.load(path, map_location="cpu")
+    import warnings
+    warnings.warn(f"{what}: the reference initialises this trunk from ImageNet (IMAGENET1K_V1); no weights were supplied "
+                  "(pretrained_state_dict= or config model.pretrained_weights), so it starts from random init",
+                  stacklevel=3)
+    return None
+
+
 def video_layout(video):
     """(kind, B, T, H, W, sb, st, sc, sh, sw), scale of lip frames in the caller's own layout:
     uint8 (B,T,H,W,3) as the .npy files hold them (video/data_utils/dataset_loader.py:87-96) or float32
@@ -252,6 +296,8 @@ class PlanModel(nn.Module):
             self._graphs.clear()
             if old is not None and old.m is not None and old.numel == self._flat.numel and old.device == self._flat.device:
                 self._flat.m, self._flat.v, self._flat.adam_state = old.m, old.v, old.adam_state
+            if old is not None and old.rng_step is not None and old.device == self._flat.device:
+                self._flat.rng_step = old.rng_step
         return self._flat
 
     def logmel_plan(self, device):
@@ -304,6 +350,23 @@ class PlanModel(nn.Module):
                 raise _lib.LipreadError("multimodal_lipread_b200 models run on CUDA tensors only (no CPU path)")
         flat = self._ensure_flat(inputs[0].device)
         return _PlanFn.apply(self, torch.is_grad_enabled(), len(inputs), *inputs, *flat.params)
+
+    @torch.no_grad()
+    def eval_step(self, *inputs_and_labels):
+        """Forward in the module's current mode + CrossEntropyLoss (mean) + number of correct arg-max predictions, all in
+        lipread_b200 kernels and without a host sync: the body of the reference's validate()
+        (audio_video/train.py:82-88).  Returns (loss, correct, logits) device tensors owned by the plan."""
+        *inputs, labels = inputs_and_labels
+        named = dict(zip(self.INPUTS, inputs))
+        plan = self._plan_for(named, training=self.training, with_backward=False)
+        for name, t in named.items():
+            buf = plan.inputs[name]
+            buf.copy_(t.reshape(buf.shape), non_blocking=True)
+        plan.labels.copy_(labels, non_blocking=True)
+        s = torch.cuda.current_stream().cuda_stream
+        plan.run_forward(s)
+        plan.ce.run(s)
+        return plan.loss, plan.correct, plan.logits
 
     # ------------------------------------------------------------------ fused training step
     def configure_optimizer(self, lr=None, betas=(0.9, 0.999), eps=1e-8, weight_decay=None):
@@ -377,6 +440,20 @@ class PlanModel(nn.Module):
         if len(steps) != 1:
             raise ValueError("per-parameter step counts differ; the flat Adam state keeps one")
         flat.adam_state[0] = steps.pop()
+
+    def rng_step(self):
+        """Number of dropout mask draws so far (the device counter behind lr_dropout_fwd); saved in checkpoints."""
+        f = self._flat
+        return 0 if f is None or f.rng_step is None else int(f.rng_step.item())
+
+    def set_rng_step(self, n):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("move the model to its CUDA device before restoring the dropout counter")
+        f = self._ensure_flat(dev)
+        if f.rng_step is None:
+            f.rng_step = torch.zeros(1, dtype=torch.int64, device=dev)
+        f.rng_step.fill_(int(n))
 
     def train_step(self, *inputs_and_labels, grad_allreduce=None, world=1, use_graph=True):
         """One training iteration entirely in lipread_b200 kernels:

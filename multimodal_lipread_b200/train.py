@@ -43,82 +43,82 @@ def _no_plan(name):
     raise NotImplementedError(f"model {name!r} of the reference has no lipread_b200 launch plan yet (DESIGN.md section 7)")
 
 
-def create_av_model(model_name, num_classes, config):
-    """audio_video/train.py:112-127."""
+def create_av_model(model_name, num_classes, config, pretrained_state_dict=None):
+    """audio_video/train.py:112-127.  Every AV model's video trunk is ImageNet-initialised in the reference
+    (weights=...IMAGENET1K_V1, e.g. middle_fusion_fast.py:15): offline the checkpoint is `pretrained_state_dict` or the
+    YAML key model.pretrained_weights; with neither the factory warns and keeps the seeded random init."""
     from . import audio_video_models as M
-    if model_name == "early_fusion_resnet":
-        return M.create_early_fusion_resnet_model(num_classes, config)
-    if model_name == "early_fusion_mobilenet":
-        return M.create_early_fusion_mobilenet_model(num_classes, config)
-    if model_name == "middle_fusion_fast":
-        return M.create_mid_fusion_fast(num_classes, config)
-    if model_name == "late_fusion_mobilenet":
-        return M.create_late_fusion_mobilenet_model(num_classes, config)
-    if model_name == "middle_fusion_mobilenet":
-        return M.create_mid_fusion_mobilenet_model(num_classes, config)
-    if model_name == "early_fusion_fast":
-        return M.create_early_fusion_fast(num_classes, config)
-    if model_name == "late_fusion_fast":
-        return M.create_late_fusion_fast(num_classes, config)
-    raise ValueError(f"Unknown model name: {model_name}")
+    from .model_base import pretrained_weights
+    classes = {"early_fusion_resnet": M.EarlyFusionAV, "early_fusion_mobilenet": M.EarlyFusionAVMobileNet,
+               "middle_fusion_fast": M.MidFusionFast, "late_fusion_mobilenet": M.LateFusionAVMobileNet,
+               "middle_fusion_mobilenet": M.MidFusionAVMobileNet, "early_fusion_fast": M.EarlyFusionFast,
+               "late_fusion_fast": M.LateFusionFast}
+    if model_name not in classes:
+        raise ValueError(f"Unknown model name: {model_name}")
+    sd = pretrained_weights(config, pretrained_state_dict, f"audio_video {model_name}")
+    return classes[model_name](num_classes, config, pretrained_state_dict=sd)
 
 
-def create_video_model(model_name, num_classes, config):
-    """video/train.py:189-204."""
+def create_video_model(model_name, num_classes, config, pretrained_state_dict=None):
+    """video/train.py:189-204.  resnet / mobilenet / shufflenet trunks are ImageNet-initialised in the reference
+    (video/models/resnet_lstm.py:80-84): see create_av_model for how the checkpoint gets here offline; vgg_lstm (VGGLite)
+    and cnn have no pretrained part."""
     from . import video_models as M
-    if model_name == "resnet_lstm":
-        return M.ResNet2DBiLSTM(num_classes=num_classes, config=config)
-    if model_name == "mobilenet_lstm":
-        return M.MobileNetLSTM(num_classes=num_classes, config=config)
+    from .model_base import pretrained_weights
     if model_name == "vgg_lstm":
         return M.VGGLSTM(num_classes=num_classes, config=config)
     if model_name == "cnn":
         return M.CNNOnly(num_classes=num_classes, config=config)
-    if model_name == "resnet_attn":
-        return M.ResNet2DAttention(num_classes=num_classes, config=config)
-    if model_name == "shufflenet_lstm":
-        return M.ShuffleNet2DBiLSTM(num_classes=num_classes, config=config)
-    if model_name == "resnet_trans":
-        return M.ResNet2DTransformer(num_classes=num_classes, config=config)
+    classes = {"resnet_lstm": M.ResNet2DBiLSTM, "mobilenet_lstm": M.MobileNetLSTM, "resnet_attn": M.ResNet2DAttention,
+               "shufflenet_lstm": M.ShuffleNet2DBiLSTM, "resnet_trans": M.ResNet2DTransformer}
+    if model_name in classes:
+        sd = pretrained_weights(config, pretrained_state_dict, f"video {model_name}")
+        return classes[model_name](num_classes=num_classes, config=config, pretrained_state_dict=sd)
     if model_name in VIDEO_MODELS:
         _no_plan(model_name)
     raise ValueError(f"Unknown model: {model_name}")
 
 
-def create_audio_model(model_name, num_classes, input_size=117, version=None):
-    """audio/train.py:118-134 (get_model)."""
+def create_audio_model(model_name, num_classes, input_size=117, version=None, pretrained_state_dict=None, config=None):
+    """audio/train.py:118-134 (get_model).  The resnet18 / vgg trunks are ImageNet-initialised in the reference
+    (audio/models/resnet_model.py:12): see create_av_model for how the checkpoint gets here offline."""
     from . import audio_models as M
+    from .model_base import pretrained_weights
+    if model_name in AUDIO_MODELS and model_name != "lstm_resnet_attn":
+        pretrained_state_dict = pretrained_weights(config, pretrained_state_dict, f"audio {model_name}")
+    kw = {"pretrained_state_dict": pretrained_state_dict}
     if model_name == "resnet":
-        return M.AudioResNet(num_classes=num_classes)
+        return M.AudioResNet(num_classes=num_classes, **kw)
     if model_name == "resnet_lstm":
-        return M.AudioResNetLSTM(num_classes=num_classes)
+        return M.AudioResNetLSTM(num_classes=num_classes, **kw)
     if model_name == "vgg":
-        return M.VGGAudioClassifier(num_classes=num_classes, version=version or 11)
+        return M.VGGAudioClassifier(num_classes=num_classes, version=version or 11, **kw)
     if model_name == "vgg_lstm":
-        return M.VGGWithLSTMClassifier(num_classes=num_classes, version=version or 11)
+        return M.VGGWithLSTMClassifier(num_classes=num_classes, version=version or 11, **kw)
     if model_name == "lstm_resnet":
-        return M.LSTMResNet(num_classes=num_classes, input_size=input_size)
+        return M.LSTMResNet(num_classes=num_classes, input_size=input_size, **kw)
     if model_name == "lstm_resnet_attn":
         return M.DeepAudioNetWithAttention(num_classes=num_classes, input_size=input_size)
     if model_name == "lstm_resnet_trans":
-        return M.LSTMResNetWithTransformer(num_classes=num_classes, input_size=input_size)
+        return M.LSTMResNetWithTransformer(num_classes=num_classes, input_size=input_size, **kw)
     if model_name in AUDIO_MODELS:
         _no_plan(model_name)
     raise ValueError(f"Invalid model name: {model_name}")
 
 
-def create_acv_model(model_name, num_classes, cue_dim=768, video_cfg=None):
-    """audio_cues_video/train.py:144-155."""
+def create_acv_model(model_name, num_classes, cue_dim=768, video_cfg=None, pretrained_state_dicts=None):
+    """audio_cues_video/train.py:144-155.  The reference builds every ACV model with pretrained=True (ImageNet resnet18
+    audio encoder, mobilenet_v2 / resnet18 video trunk; FROZEN in the early / middle-resnet variants).  Offline the
+    checkpoints are pretrained_state_dicts = {"audio": ..., "video": ...} (torchvision key names); without them the
+    models warn that their trunks start from random init."""
     from . import audio_cues_video_models as M
-    if model_name == "late_fusion_mobile":
-        return M.MultimodalAttentionLate(num_classes, cue_dim=cue_dim, video_cfg=video_cfg, pretrained=False)
-    if model_name == "late_fusion_resnet":
-        return M.MultimodalAttentionLateResNet(num_classes, cue_dim=cue_dim, video_cfg=video_cfg, pretrained=False)
-    cls = {"early_fusion_mobile": M.MultimodalAttentionEarly, "middle_fusion_mobile": M.MultimodalAttentionMiddle,
+    cls = {"late_fusion_mobile": M.MultimodalAttentionLate, "late_fusion_resnet": M.MultimodalAttentionLateResNet,
+           "early_fusion_mobile": M.MultimodalAttentionEarly, "middle_fusion_mobile": M.MultimodalAttentionMiddle,
            "early_fusion_resnet": M.MultimodalAttentionEarlyResNet,
            "middle_fusion_resnet": M.MultimodalAttentionMiddleResNet}.get(model_name)
     if cls is not None:
-        return cls(num_classes, cue_dim=cue_dim, video_cfg=video_cfg, pretrained=False)
+        return cls(num_classes, cue_dim=cue_dim, video_cfg=video_cfg, pretrained=True,
+                   pretrained_state_dicts=pretrained_state_dicts)
     if model_name in ACV_MODELS:
         _no_plan(model_name)
     raise ValueError(f"Unknown model name: {model_name}")
@@ -160,17 +160,20 @@ def validate(model, loader, device, batch_to_inputs=None, per_sample_loss=False)
     """audio_video/train.py:78-90: eval mode, mean CE per batch, accuracy %  (per_sample_loss: the size-weighted mean
     of audio_cues_video/train.py:52-81)."""
     model.eval()
-    loss_sum, correct, total, n_batches = 0.0, 0, 0, 0
+    loss_sum = torch.zeros((), device=device)
+    correct = torch.zeros((), dtype=torch.int64, device=device)
+    total, n_batches = 0, 0
     for batch in loader:
         inputs, labels = (batch_to_inputs or default_batch_to_inputs)(batch)
         inputs = tuple(_to_dev(t, device) for t in inputs)
         labels = _to_dev(labels, device)
-        out = model(*inputs)
-        loss_sum += torch.nn.functional.cross_entropy(out, labels).item() * (labels.numel() if per_sample_loss else 1)
-        correct += (out.argmax(1) == labels).sum().item()
+        loss, n_ok, _ = model.eval_step(*inputs, labels)          # lr_ce_loss on the device: no host sync per batch
+        loss_sum += loss.reshape(()) * (labels.numel() if per_sample_loss else 1)
+        correct += n_ok.reshape(())
         total += labels.numel()
         n_batches += 1
-    return loss_sum / (max(total, 1) if per_sample_loss else max(n_batches, 1)), 100.0 * correct / max(total, 1)
+    denom = max(total, 1) if per_sample_loss else max(n_batches, 1)
+    return (loss_sum / denom).item(), 100.0 * correct.item() / max(total, 1)
 
 
 def default_batch_to_inputs(batch):
@@ -271,7 +274,7 @@ def make_checkpoint(model, epoch, best_val_acc):
     """video/train.py:246-251 / audio_cues_video/train.py:178-183: {"epoch": next epoch, "state_dict", "optimizer",
     "best_val_acc"}; the optimizer entry has torch.optim.Adam's state_dict layout."""
     return {"epoch": epoch + 1, "state_dict": model.state_dict(), "optimizer": model.optimizer_state_dict(),
-            "best_val_acc": best_val_acc}
+            "best_val_acc": best_val_acc, "rng_step": model.rng_step()}          # extra key: dropout mask counter
 
 
 def resume(model, path):
@@ -282,6 +285,8 @@ def resume(model, path):
     if "state_dict" in ckpt:
         model.load_state_dict(ckpt["state_dict"])
         model.load_optimizer_state_dict(ckpt["optimizer"])
+        if ckpt.get("rng_step") and next(model.parameters()).device.type == "cuda":
+            model.set_rng_step(ckpt["rng_step"])                 # absent in checkpoints written by the reference
         return ckpt["epoch"], ckpt["best_val_acc"]
     if "model_state_dict" in ckpt:
         model.load_state_dict(ckpt["model_state_dict"])

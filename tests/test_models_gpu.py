@@ -434,3 +434,28 @@ def test_tf32_mode_resnet_within_tolerance(cuda_device):
     assert _rel(logits, logits_ref) <= 5e-3, _rel(logits, logits_ref)
     assert abs(loss.item() - loss_ref.item()) <= 2e-3 * abs(loss_ref.item())
     assert torch.equal(logits.argmax(1).cpu(), logits_ref.argmax(1))
+
+
+def test_benchmarked_resnet_configuration_matches_oracle(cuda_device):
+    """BASELINE.json config 2 as bench.py times it: video resnet_lstm, precision="tf32", batch 32, 29 frames of 88x88
+    (uint8 frames), dropout off on both sides, lr = 0, the step replayed as a CUDA graph: logits <= 5e-3 norm-wise,
+    loss <= 2e-3, argmax identical on the rows whose top-2 margin is above the tolerance."""
+    name = "video_resnet_lstm"
+    ref, ours, C = _case(name, precision="tf32")
+    B, T, size = 32, 29, 88
+    wav, mel, lips, labels = _data(B, size, T, C)
+    video = lips_u8_to_model_input(lips)
+    ref.train(); ours.train()
+    with torch.no_grad():
+        logits_ref = ref(video)
+    loss_ref = torch.nn.functional.cross_entropy(logits_ref, labels)
+    ours.configure_optimizer(lr=0.0)
+    for _ in range(3):
+        loss, logits = ours.train_step(lips.cuda(), labels.cuda(), use_graph=True)
+    e = _rel(logits, logits_ref)
+    assert e <= 5e-3, e
+    assert abs(loss.item() - loss_ref.item()) <= 2e-3 * abs(loss_ref.item())
+    top2 = logits_ref.topk(2, dim=1).values
+    keep = (top2[:, 0] - top2[:, 1]) > 2 * 5e-3 * logits_ref.abs().max().item()
+    assert keep.sum().item() >= B // 2
+    assert torch.equal(logits.argmax(1).cpu()[keep], logits_ref.argmax(1)[keep])

@@ -143,6 +143,11 @@ def test_epoch_bookkeeping_follows_each_train_script():
             out = self(x)
             return torch.nn.functional.cross_entropy(out, labels).detach().reshape(1), out.detach()
 
+        def eval_step(self, x, labels):                      # PlanModel.eval_step: (loss, correct, logits) tensors
+            out = self(x)
+            return (torch.nn.functional.cross_entropy(out, labels).detach().reshape(1),
+                    (out.argmax(1) == labels).sum().reshape(1), out.detach())
+
     g = torch.Generator().manual_seed(0)
     batches = [(torch.randn(n, 4, generator=g), torch.randint(0, 4, (n,), generator=g)) for n in (5, 5, 2)]
     losses = [torch.nn.functional.cross_entropy(x, y).item() for x, y in batches]
@@ -155,3 +160,37 @@ def test_epoch_bookkeeping_follows_each_train_script():
         assert loss == pytest.approx((5 * losses[0] + 5 * losses[1] + 2 * losses[2]) / 12, rel=1e-6)
     dict_batches = [{"lip_regions": x, "label": y} for x, y in batches]                  # video/data_utils items
     assert T.validate(m, dict_batches, "cpu")[0] == pytest.approx(sum(losses) / 3, rel=1e-6)
+
+
+def test_factories_take_the_imagenet_checkpoint_or_warn(tmp_path):
+    """The reference initialises every torchvision trunk from ImageNet (weights=...IMAGENET1K_V1 / pretrained=True);
+    offline the checkpoint is an argument or the YAML key model.pretrained_weights, and its absence is announced."""
+    import warnings
+    from torchvision.models import mobilenet_v2, mobilenet_v3_small, resnet18
+    from multimodal_lipread_b200 import train as T
+    from multimodal_lipread_b200.model_base import Cfg
+    torch.manual_seed(11)
+    v3, r18, v2 = mobilenet_v3_small(weights=None).state_dict(), resnet18(weights=None).state_dict(), mobilenet_v2(weights=None).state_dict()
+    with pytest.warns(UserWarning, match="ImageNet"):
+        T.create_av_model("middle_fusion_fast", 8, Cfg())
+    with pytest.warns(UserWarning, match="ImageNet"):
+        T.create_acv_model("early_fusion_mobile", 8)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        m = T.create_av_model("middle_fusion_fast", 8, Cfg(), pretrained_state_dict=v3)
+        assert torch.equal(m.state_dict()["video_cnn.features.3.block.0.0.weight"], v3["features.3.block.0.0.weight"])
+        path = str(tmp_path / "r18.pt")
+        torch.save(r18, path)
+        m = T.create_video_model("resnet_lstm", 8, Cfg({"model": {"pretrained_weights": path, "feature_dim": 256}}))
+        # video/models/resnet_lstm.py:90-93 keeps children()[:-2] as a Sequential: index 6 is layer3
+        assert torch.equal(m.state_dict()["cnn_features.6.1.conv2.weight"], r18["layer3.1.conv2.weight"])
+        m = T.create_acv_model("early_fusion_mobile", 8, pretrained_state_dicts={"audio": r18, "video": v2})
+        sd = m.state_dict()
+        ka = [k for k in sd if k.startswith("audio") and k.endswith("layer2.0.conv1.weight")][0]
+        kv = [k for k in sd if k.startswith("video") and k.endswith("3.conv.0.0.weight")][0]
+        assert torch.equal(sd[ka], r18["layer2.0.conv1.weight"]) and torch.equal(sd[kv], v2["features.3.conv.0.0.weight"])
+        # the 1-channel audio conv1 the reference re-creates after loading keeps its own init
+        k1 = [k for k in sd if k.startswith("audio") and k.endswith("conv1.weight") and "layer" not in k][0]
+        assert sd[k1].shape[1] == 1
+    with pytest.raises(FileNotFoundError):
+        T.create_video_model("resnet_lstm", 8, Cfg({"model": {"pretrained_weights": str(tmp_path / "missing.pt")}}))
