@@ -153,7 +153,8 @@ def test_fit_run_checkpoints_logs_and_resume_interop(cuda_device, tmp_path):
     assert all(np.isfinite(float(v)) for r in rows[1:] for v in r[1:])
     assert 0.0 <= res["test_acc"] <= 100.0 and os.path.exists(os.path.join(save_dir, "test_results.txt"))
     ck = torch.load(os.path.join(save_dir, "middle_fusion_fast_checkpoint.pth"), map_location="cpu")
-    assert set(ck) == {"epoch", "state_dict", "optimizer", "best_val_acc"} and ck["epoch"] == 3
+    # the reference's four keys (video/train.py:246-251) + the dropout mask counter, which its resume code never reads
+    assert set(ck) == {"epoch", "state_dict", "optimizer", "best_val_acc", "rng_step"} and ck["epoch"] == 3
     # the reference side can resume from it: same keys, and torch's Adam accepts the optimizer entry
     ref = O.MidFusionFastOracle(3)
     ref.load_state_dict(ck["state_dict"])
