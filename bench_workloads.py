@@ -72,35 +72,51 @@ class LogmelWorkload:
     def roofline(self, kernel_ms, ms_step, peaks):
         ms = kernel_ms or ms_step
         achieved = self.batch * LOGMEL_BYTES_PER_CLIP / 1e9 / (ms / 1e3)
+        traffic = _committed_traffic().get("lm::logmel_kernel")
         return {"kernel": "lm::logmel_kernel", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
-                "kernel_ms": ms}
+                "unit": "GB/s", "frac": achieved / peaks["hbm"],
+                "traffic": None if traffic is None else traffic["dram_bytes_per_clip"] * self.batch,
+                "peak_source": peaks["src"], "kernel_ms": ms,
+                "binds": "fp32 issue slots (a 400-point real FFT + mel + log per frame), not HBM: see DESIGN.md section 4"}
 
     def extra(self):
         return {"clips_per_sec": None}
 
+    def release(self):
+        self.wav = self.stage = self.host = self.out_host = None
+        torch.cuda.empty_cache()
 
-def _build_model(kind, num_classes):
+
+def _build_model(kind, num_classes, precision="tf32"):
     """(model, input names) of a train workload; dropout keeps the reference's rates (it is part of the step)."""
     if kind == "mid_fusion_fast":
         from multimodal_lipread_b200.audio_video_models import MidFusionFast
-        return MidFusionFast(num_classes), ("audio", "video")
+        return MidFusionFast(num_classes, precision=precision), ("audio", "video")
     if kind == "early_fusion_mobilenet":
         from multimodal_lipread_b200.audio_video_models import EarlyFusionAVMobileNet
-        return EarlyFusionAVMobileNet(num_classes), ("audio", "video")
+        return EarlyFusionAVMobileNet(num_classes, precision=precision), ("audio", "video")
     if kind == "early_fusion_resnet":
         from multimodal_lipread_b200.audio_video_models import EarlyFusionAV
-        return EarlyFusionAV(num_classes), ("audio", "video")
+        return EarlyFusionAV(num_classes, precision=precision), ("audio", "video")
     if kind == "video_resnet_lstm":
         from multimodal_lipread_b200.video_models import ResNet2DBiLSTM
-        return ResNet2DBiLSTM(num_classes), ("video",)
+        return ResNet2DBiLSTM(num_classes, precision=precision), ("video",)
     if kind == "audio_resnet":
         from multimodal_lipread_b200.audio_models import AudioResNet
-        return AudioResNet(num_classes), ("audio",)
+        return AudioResNet(num_classes, precision=precision), ("audio",)
     if kind == "acv_late_fusion_mobile":
         from multimodal_lipread_b200.audio_cues_video_models import MultimodalAttentionLate
-        return MultimodalAttentionLate(num_classes), ("audio", "cue", "video")
+        return MultimodalAttentionLate(num_classes, precision=precision), ("audio", "cue", "video")
     raise ValueError(f"unknown train workload {kind!r}")
+
+
+def _committed_traffic():
+    """ncu-measured DRAM traffic committed under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum), keyed by
+    kernel / op family / workload; absent entries report `traffic: null`."""
+    import json
+    import os
+    tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_traffic.json")
+    return json.load(open(tp)) if os.path.exists(tp) else {}
 
 
 # forward GFLOP per clip at 44 / 88 px (SURVEY.md 8(a) a16, analytic 2*MAC counts of the reference modules)
@@ -120,14 +136,16 @@ class AvTrainWorkload:
     """One train step of a lipread_b200 model on synthetic GLips-shaped clips (audio_video/train.py:61-67 and its
     video / audio / audio_cues_video siblings): [log-mel ->] forward -> CE -> backward -> (NCCL allreduce) -> Adam,
     all in lipread_b200 kernels.  The headline workload is audio_video middle_fusion_fast."""
-    dtype = "f32"
-
     def __init__(self, dev, batch, cfg, rank, world):
         import torch.distributed as dist
         self.dev, self.batch, self.world, self.cfg = dev, batch, world, cfg
         self.kind = cfg.get("model", "mid_fusion_fast")
+        self.precision = cfg.get("precision", "tf32")
+        # the arithmetic type of the GEMM-shaped work: "tf32" = tcgen05 kind::tf32 products on fp32 storage (fp32
+        # accumulate); "bf16" = bf16 activations / kind::f16; "f32" = strict fp32 SIMT everywhere
+        self.dtype = {"tf32": "tf32", "fp32": "f32", "bf16": "bf16"}[self.precision]
         torch.manual_seed(0)                                   # identical replicas on every rank
-        model, self.names = _build_model(self.kind, cfg["num_classes"])
+        model, self.names = _build_model(self.kind, cfg["num_classes"], self.precision)
         self.model = model.to(dev).train()
         self.model.configure_optimizer()
         # a ring of distinct input batches larger than L2 (126 MB), resident in HBM
@@ -282,51 +300,76 @@ class AvTrainWorkload:
         return rows
 
     def roofline(self, kernel_ms, ms_step, peaks):
-        """Dominant kernel = the HBM-streaming launch with the largest device time in the step; achieved = its
-        algorithmic bytes / its CUDA-event duration.  `traffic` = dram bytes of that launch from the committed
-        ncu --set full capture (profiles/r1_traffic.json), when there is one for this kernel and shape."""
-        import json
-        import os
+        """Dominant kernel = the op FAMILY (all launches of one C-ABI kernel) with the largest share of the step's
+        device time; achieved = sum of algorithmic bytes / sum of CUDA-event durations over ALL its launches (each
+        timed alone from its own graph after an L2 flush).  `traffic` (per launch, averaged) and `step_frac` use the
+        ncu DRAM byte counts committed in profiles/r2_traffic.json for this workload."""
         rows = self.profile_ops()
         self.op_rows = rows
         total = sum(r["ms"] for r in rows)
-        cand = sorted((r for r in rows if r["bytes"]), key=lambda r: -r["ms"])
-        lab = lambda r: f"{r['op']} {r['shape']} ({r['phase']})"
-        tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")
-        captured = json.load(open(tp)) if os.path.exists(tp) else {}
-        # the two largest streaming launches of this step are within run-to-run noise of each other (~125 us): among
-        # launches within 5 % of the longest, the one with a committed ncu --set full capture is reported, so that the
-        # line is stable from run to run and carries its measured DRAM traffic; the runner-up is listed beside it
-        near = [r for r in cand if r["ms"] >= 0.95 * cand[0]["ms"]]
-        top = next((r for r in near if lab(r) in captured), cand[0])
-        runner = next((r for r in cand if r is not top), None)
-        achieved = top["bytes"] / 1e9 / (top["ms"] / 1e3)
-        by_op, by_bytes = {}, {}
+        fam = {}
         for r in rows:
-            by_op[r["op"]] = by_op.get(r["op"], 0.0) + r["ms"]
+            f = fam.setdefault(r["op"], {"ms": 0.0, "bytes": 0.0, "n": 0, "n_bytes": 0, "ms_bytes": 0.0})
+            f["ms"] += r["ms"]; f["n"] += 1
             if r["bytes"]:
-                b = by_bytes.setdefault(r["op"], [0.0, 0.0, 0])
-                b[0] += r["bytes"]; b[1] += r["ms"]; b[2] += 1
-        label = lab(top)
-        traffic = captured.get(label)
+                f["bytes"] += r["bytes"]; f["n_bytes"] += 1; f["ms_bytes"] += r["ms"]
+        top_name, top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+        achieved = top["bytes"] / 1e9 / (top["ms_bytes"] / 1e3) if top["ms_bytes"] else None
+        committed = _committed_traffic().get(f"{self.kind}:{self.precision}", {})
+        fam_traffic = committed.get("families", {}).get(top_name)
+        step_dram = committed.get("step_dram_bytes")
         f44, f88 = FWD_GFLOP[self.kind]
         fwd_gflop = f88 if self.cfg["size"] == 88 else f44
         slowest = max(rows, key=lambda r: r["ms"])
-        return {"kernel": label, "bound": "hbm", "achieved": achieved,
-                "peak": peaks["hbm"], "unit": "GB/s", "frac": achieved / peaks["hbm"], "traffic": traffic,
-                "peak_source": peaks["src"], "kernel_ms": top["ms"], "kernel_share_of_step": top["ms"] / total,
-                "step_ms_sum_of_kernels_cold": total,
+        return {"kernel": f"{top_name} (op family: {top['n']} launches per step)", "bound": "hbm", "achieved": achieved,
+                "peak": peaks["hbm"], "unit": "GB/s", "frac": None if achieved is None else achieved / peaks["hbm"],
+                "traffic": None if not fam_traffic else fam_traffic["dram_bytes"] / fam_traffic["launches"],
+                "algorithmic_bytes_per_launch": top["bytes"] / max(top["n_bytes"], 1),
+                "peak_source": peaks["src"], "kernel_ms": top["ms"] / top["n"], "family_ms_per_step": top["ms"],
+                "kernel_share_of_step": top["ms"] / total, "step_ms_sum_of_kernels_cold": total,
+                # whole step: DRAM bytes of one step (ncu, committed) / the device-timed step / peak
+                "step_dram_bytes": step_dram,
+                "step_frac": None if not step_dram else step_dram / 1e9 / (ms_step / 1e3) / peaks["hbm"],
                 "slowest_launch": f"{slowest['op']} {slowest['shape']} ({slowest['phase']}): {slowest['ms'] * 1e3:.0f} us",
-                "runner_up": (None if runner is None else
-                              {"kernel": lab(runner), "kernel_ms": runner["ms"],
-                               "frac": runner["bytes"] / 1e9 / (runner["ms"] / 1e3) / peaks["hbm"]}),
-                "time_by_op_ms": {k: round(v, 4) for k, v in sorted(by_op.items(), key=lambda kv: -kv[1])},
-                # every launch of an op family: sum of algorithmic bytes / sum of cold device times, as a fraction of peak
-                "hbm_frac_by_op": {k: {"launches": v[2], "GBps": round(v[0] / 1e9 / (v[1] / 1e3), 1),
-                                       "frac": round(v[0] / 1e9 / (v[1] / 1e3) / peaks["hbm"], 3)}
-                                   for k, v in sorted(by_bytes.items(), key=lambda kv: -kv[1][1])},
-                "step_model_tflops": 3 * fwd_gflop * self.batch / (ms_step / 1e3) / 1e3}
+                "time_by_op_ms": {k: round(v["ms"], 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
+                # every op family with a byte model: sum of algorithmic bytes / sum of cold device times, vs the HBM peak
+                "hbm_frac_by_op": {k: {"launches": v["n_bytes"], "GBps": round(v["bytes"] / 1e9 / (v["ms_bytes"] / 1e3), 1),
+                                       "frac": round(v["bytes"] / 1e9 / (v["ms_bytes"] / 1e3) / peaks["hbm"], 3)}
+                                   for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]) if v["ms_bytes"]},
+                "step_model_tflops": self.model_tflops(ms_step)}
+
+    def model_tflops(self, ms_step):
+        """3 x analytic forward FLOPs of the reference model per device-timed step."""
+        f44, f88 = FWD_GFLOP[self.kind]
+        return 3 * (f88 if self.cfg["size"] == 88 else f44) * self.batch / (ms_step / 1e3) / 1e3
+
+    def time_without_allreduce(self, steps, barrier):
+        """ms per step of the same captured step WITHOUT the collective (grad_allreduce=None keeps 1/world in Adam):
+        the difference to the timed step is the exposed collective time."""
+        saved, self.allreduce = self.allreduce, None
+        for _ in range(3):
+            self.step_device()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            self.step_device()
+        b.record()
+        barrier()
+        self.allreduce = saved
+        return a.elapsed_time(b) / steps
+
+    def release(self):
+        """Drop graphs (they may hold captured NCCL kernels) and every device buffer of this workload."""
+        import gc
+        self.model._graphs.clear()
+        self.model._plans.clear()
+        self.devb = self.stages = self.host = None
+        self.model = None
+        gc.collect()
+        torch.cuda.empty_cache()
 
     def extra(self):
         return {"final_loss": float(self.last_loss.item()) if self.last_loss is not None else None,
                 "input_ring_batches": self.ring}
+

@@ -549,6 +549,10 @@ class PlanModel(nn.Module):
             update(torch.cuda.current_stream().cuda_stream)
         return (g0, g1)
 
+    def allreduce_buckets(self):
+        """Number of collectives a data-parallel step issues (the flat gradient goes out in this many pieces)."""
+        return 1
+
     def launches_per_step(self):
         """Kernels of this library launched by one train_step (counted by the library during the eager step)."""
         return max((getattr(p, "kernel_launches", 0) for p in self._plans.values()), default=0)

@@ -65,6 +65,8 @@ def test_product_path_never_imports_the_oracle():
             elif isinstance(node, ast.ImportFrom):
                 names = [node.module or ""]
             assert not any(n == "oracle" or n.startswith("oracle.") for n in names), f"{path} imports the oracle"
+    # bench_checks.py (dp_parity / torch_gpu_baseline: checker legs, never timed as the product) is the one other user
+    assert "oracle" in open(os.path.join(ROOT, "bench_checks.py")).read()
     # bench.py: the oracle appears only inside cpu_reference()
     tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
     for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
