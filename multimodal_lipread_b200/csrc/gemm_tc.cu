@@ -40,7 +40,7 @@ struct P {
     double* stats;
     int act;
 #ifdef LR_TRACE
-    long long* trace;    // [gridDim.x][32] clock64 stamps (debug builds only: scratch/gemm_trace.cu)
+    long long* trace;    // [gridDim.x][32] clock64 stamps (debug builds only, -DLR_TRACE)
 #endif
 };
 #ifdef LR_TRACE

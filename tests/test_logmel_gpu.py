@@ -43,12 +43,23 @@ def test_golden_vectors(ap, golden_dir):
     assert (_normwise(out[:n], ref64[:n]) <= RTOL_NORMWISE).all(), _normwise(out[:n], ref64[:n])
     ref_noise = _normwise(ref32[:n].astype(np.float64), ref64[:n])
     assert (_normwise(out[:n], ref32[:n]) <= RTOL_NORMWISE + ref_noise).all()
-    # silent clip: exact arithmetic gives 0 (the reference returns fp32 round-off / 1e-9 noise)
+    # silent clip: a DOCUMENTED DEVIATION.  Every log-mel value of digital silence equals
+    # ln(1e-9); exact arithmetic gives (x - mean) = 0 -> output 0, which is what the kernel returns.  The reference
+    # divides its fp32 round-off of (x - mean) (~1e-6) by (std + 1e-9) with std == 0 and returns -0.9994 everywhere;
+    # that golden value is kept as an expected failure below (test_silent_clip_golden_value_of_the_reference).
     assert (out[7] == 0.0).all()
     raw = ap.compute_melspectrogram(wave).cpu().numpy()
     assert raw.shape == (8, 80, 126)
     assert np.abs(raw - g["logmel_raw"]).max() < 2e-3
     assert np.allclose(raw[7], np.log(1e-9), atol=1e-5)
+
+
+@pytest.mark.xfail(strict=True, reason="documented deviation: the reference's silent-clip output is fp32 round-off / 1e-9 "
+                   "(-0.9994 everywhere); the kernel returns the exact-arithmetic value 0")
+def test_silent_clip_golden_value_of_the_reference(ap, golden_dir):
+    g = np.load(os.path.join(golden_dir, "logmel_golden.npz"))
+    out = ap.frontend(torch.from_numpy(g["wave"][7:8])).cpu().numpy()
+    assert np.abs(out[0] - g["out"][7]).max() <= 1e-4 * np.abs(g["out"][7]).max()
 
 
 @pytest.mark.parametrize("kind", ["pcm", "unit", "tone"])

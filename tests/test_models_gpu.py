@@ -65,8 +65,8 @@ def _grad_check(named_ours, gref, tol, ref=None, ref_inputs=None, labels=None):
     with the few rows these small test batches give a channel (18 frames x 2x2 pixels = 72 at the bottom of
     MobileNetV2) every flip moves that channel's gradients by ~1/rows and everything upstream a little.  The
     reference itself behaves that way: its fp32 gradients differ from its own fp64 gradients by up to 9e-2 on 103 of
-    248 tensors for the triple-fusion model (scratch/cond_check4.py), and jump by 3e-2 under a 2e-7 relative input
-    perturbation (scratch/cond_check2.py).  So when the strict bar is missed, the fallback bar is MEASURED: gradients
+    248 tensors for the triple-fusion model (round-1 probe cond_check4, git history), and jump by 3e-2 under a 2e-7 relative input
+    perturbation (round-1 probe cond_check2, git history).  So when the strict bar is missed, the fallback bar is MEASURED: gradients
     of the oracle in float64 are the truth, and our deviation from them must be no worse than the fp32 oracle's own
     deviation from them in the typical tensor (median within 5x), no tensor may be wrong as a whole (relative L2
     error <= 0.1, max-abs <= 0.25) and at most half of the tensors may be perturbed at all -- far inside the bf16
@@ -248,7 +248,7 @@ def _inputs_for(name, mel, lips):
 @pytest.mark.parametrize("name,B,T,size", [
     # (3, 7, 44) is deliberately avoided for early_fusion_mobilenet: with these seeds one activation sits on a
     # hard-swish kink and the REFERENCE's own gradient jumps by 3.4e-2 under a 2e-7 relative input perturbation
-    # (scratch/cond_check2.py) -- an ill-conditioned case, not a parity case
+    # (round-1 probe cond_check2, git history) -- an ill-conditioned case, not a parity case
     ("early_fusion_mobilenet", 3, 8, 44),
     ("early_fusion_resnet", 2, 5, 44),
     ("video_resnet_lstm", 2, 5, 44),
@@ -357,7 +357,7 @@ def test_golden_vectors_of_the_reference(cuda_device, golden_dir, name):
     gn[noise] = ref_gn[noise] = 0.0
     close = np.isclose(gn, ref_gn, rtol=3e-3, atol=3e-6)
     # MobileNetV2 at 18 frames: 41 % of the REFERENCE's own fp32 gradient tensors differ from its fp64 ones by
-    # more than 3e-3 (scratch/cond_check4.py); the other models are well conditioned
+    # more than 3e-3 (round-1 probe cond_check4, git history); the other models are well conditioned
     frac = 0.5 if name in ("acv_late_fusion_mobile", "video_mobilenet_lstm", "acv_middle_fusion_mobile", "video_shufflenet_lstm") else 0.06
     sd = ours.state_dict()
     assert [int(v) for k, v in sd.items() if k.endswith("num_batches_tracked")] == mg[f"{name}_nbt"].tolist()
