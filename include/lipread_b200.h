@@ -336,6 +336,54 @@ size_t lr_adam_state_bytes(void);
 int lr_adam_step(float* p, const float* g, float* m, float* v, void* state, long long n, float beta1, float beta2,
                  float eps, float weight_decay, float grad_scale, lr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * bf16 storage (precision "bf16": the north star's "bf16 on 1 B200").  The big per-pixel tensors -- activations and
+ * their gradients [rows, C] -- live in HBM as bfloat16 (void* below), which halves the bytes of every HBM-bound kernel;
+ * arithmetic inside the kernels stays fp32, BatchNorm statistics stay double sums, parameters / gradients of
+ * parameters / Adam state / per-frame vectors (SE gates, pooled features, LSTM) stay fp32.  Every `_h` entry point has
+ * the argument meaning of its fp32 namesake above; C must be a multiple of 4 (depthwise: 8).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Tensor-core GEMM on bf16 operands (tcgen05.mma kind::f16, fp32 accumulate in TMEM): A and B are bf16 (K-major or
+ * MN-major, fetched by TMA with the 128-byte swizzle; lda / ldb multiples of 8), C is bf16 (c_bf16 = 1: activations,
+ * dgrad; ldc multiple of 8; R, if given, is bf16 too) or fp32 (c_bf16 = 0: weight gradients -- split-K through TMA
+ * reduce-add --, LSTM input projections).  bias fp32.  Same flags and epilogue as lr_gemm_tf32; the BatchNorm statistics
+ * are those of the ROUNDED bf16 values. */
+int lr_gemm_bf16(const void* A, long long lda, int a_trans, const void* B, long long ldb, int b_trans, void* C,
+                 long long ldc, int c_bf16, int M, int N, int K, const float* bias, int act, const void* R,
+                 long long ldr, double* stats, int ksplit, lr_stream_t stream);
+/* dst[i] = bf16(src[i]): the bf16 shadow of the flat fp32 parameter buffer (refreshed once per step) */
+int lr_cast_bf16(const float* src, void* dst, long long n, lr_stream_t stream);
+
+int lr_bn_act_fwd_h(const void* x, const double* stats, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, long long* num_batches_tracked, float eps, float momentum, int act,
+                    int training, const void* residual, int res_pre, void* z, long long rows, int C,
+                    lr_stream_t stream);
+int lr_bn_act_bwd_h(const void* x, const double* stats, const float* gamma, const float* beta,
+                    const float* running_mean, const float* running_var, float eps, int act, int training,
+                    const void* dz, const void* z_out, void* dres, double* sums, void* dx, float* dgamma,
+                    float* dbeta, long long rows, int C, lr_stream_t stream);
+int lr_frame_reduce_h(const void* a, const void* g, float* p, int F, int HW, int C, int mode, lr_stream_t stream);
+int lr_frame_scale_h(const void* a, const float* s, const float* dp, void* out, int F, int HW, int C,
+                     lr_stream_t stream);
+int lr_act_bwd_h(void* dy, const void* y, long long n, int act, lr_stream_t stream);
+int lr_colsum_h(const void* dY, long long ld, long long M, int N, float* db, lr_stream_t stream);
+int lr_dwconv_fwd_h(const void* x, const float* w, void* y, double* stats, int F, int H, int W, int C, int k,
+                    int stride, lr_stream_t stream);
+int lr_dwconv_dgrad_h(const void* dy, const float* w, void* dx, int F, int H, int W, int C, int k, int stride,
+                      lr_stream_t stream);
+int lr_dwconv_wgrad_h(const void* dy, const void* x, float* dwt, int F, int H, int W, int C, int k, int stride,
+                      lr_stream_t stream);
+int lr_im2col_h(const void* x, int is_u8, float scale, int F, int T, long long sb, long long st, long long sc,
+                long long sh, long long sw, int Hs, int Ws, int C, int kh, int kw, int stride, int pad,
+                int transposed, int Hd, int Wd, void* col, long long ldk, lr_stream_t stream);
+int lr_im2col_tap_h(const void* x, int F, int Hs, int Ws, int C, int kh, int kw, int stride, int pad_h, int pad_w,
+                    int transposed, int Hd, int Wd, void* col, lr_stream_t stream);
+int lr_maxpool_fwd_h(const void* x, void* y, unsigned char* arg, int F, int H, int W, int C, int k, int stride,
+                     int pad, lr_stream_t stream);
+int lr_maxpool_bwd_h(const void* dy, const unsigned char* arg, void* dx, int F, int H, int W, int C, int k,
+                     int stride, int pad, lr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,8 +52,9 @@ __device__ __forceinline__ Coef coef4(const Bn& b, int c) {
 }
 
 // z = act(x * scale + shift) (+ residual).  Block (0,0) also performs the running-statistics update.
+template <typename T>
 __global__ void __launch_bounds__(TH, 4)
-bn_act_fwd_kernel(const Bn b, const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ z,
+bn_act_fwd_kernel(const Bn b, const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ z,
                   int rows_per_block, int res_pre, int gw) {
     const nn::CgMap map(b.C, blockIdx.y * gw, gw);
     if (b.training && b.running_mean && blockIdx.x == 0 && blockIdx.y == 0) {
@@ -113,9 +114,10 @@ __device__ __forceinline__ float4 mask_by_out(float4 g, const float4 z, int act)
 }
 
 // backward pass 1: dy = dz * act'(u), u = x*scale + shift;  sums[c] += dy, sums[C+c] += dy * xhat
+template <typename T>
 __global__ void __launch_bounds__(TH, 3)
-bn_act_bwd_reduce_kernel(const Bn b, const float* __restrict__ x, const float* __restrict__ dz,
-                         const float* __restrict__ zo, double* __restrict__ sums, int rows_per_block, int gw) {
+bn_act_bwd_reduce_kernel(const Bn b, const T* __restrict__ x, const T* __restrict__ dz,
+                         const T* __restrict__ zo, double* __restrict__ sums, int rows_per_block, int gw) {
     extern __shared__ float sh[];                       // [2C] (only this block column's channels are touched)
     const int c_lo = blockIdx.y * gw * 4, c_hi = min(b.C, c_lo + gw * 4);
     for (int i = c_lo + threadIdx.x; i < c_hi; i += blockDim.x) { sh[i] = 0.f; sh[b.C + i] = 0.f; }
@@ -168,10 +170,11 @@ bn_act_bwd_reduce_kernel(const Bn b, const float* __restrict__ x, const float* _
 // backward pass 2: dx = gamma*invstd * (dy - mean(dy) - xhat * mean(dy*xhat))   (training)
 //                  dx = gamma*invstd * dy                                        (eval)
 // block (0,0) writes dgamma += sum(dy*xhat), dbeta += sum(dy).
+template <typename T>
 __global__ void __launch_bounds__(TH, 3)
-bn_act_bwd_apply_kernel(const Bn b, const float* __restrict__ x, const float* __restrict__ dz,
-                        const float* __restrict__ zo, float* __restrict__ dres,
-                        const double* __restrict__ sums, float* __restrict__ dx, float* __restrict__ dgamma,
+bn_act_bwd_apply_kernel(const Bn b, const T* __restrict__ x, const T* __restrict__ dz,
+                        const T* __restrict__ zo, T* __restrict__ dres,
+                        const double* __restrict__ sums, T* __restrict__ dx, float* __restrict__ dgamma,
                         float* __restrict__ dbeta, int rows_per_block, int gw) {
     if (blockIdx.x == 0 && blockIdx.y == 0 && dgamma) {
         for (int c = threadIdx.x; c < b.C; c += blockDim.x) {
@@ -236,8 +239,9 @@ bn_act_bwd_apply_kernel(const Bn b, const float* __restrict__ x, const float* __
 // Deterministic: every thread sums its row lane in index order, the row lanes of a channel are then added in lane
 // order from a shared-memory slab -- no atomics, so two runs on the same input are bit-identical (eval forwards,
 // validate() and model selection depend on that).
+template <typename T>
 __global__ void __launch_bounds__(TH)
-frame_reduce_kernel(const float* __restrict__ a, const float* __restrict__ g, float* __restrict__ p, int HW, int C,
+frame_reduce_kernel(const T* __restrict__ a, const T* __restrict__ g, float* __restrict__ p, int HW, int C,
                     int mode) {
     __shared__ __align__(16) float sh[TH * 4];          // [row lane][4 * groups of this pass]
     const long long f = blockIdx.x;
@@ -270,9 +274,10 @@ frame_reduce_kernel(const float* __restrict__ a, const float* __restrict__ g, fl
 //   SE forward            : a = activation, s = gate, dp = null
 //   SE backward           : a = db, s = gate, dp = gradient of the pooled value
 //   avg-pool backward     : a = null, dp = gradient of the pooled value
+template <typename T>
 __global__ void __launch_bounds__(TH)
-frame_scale_kernel(const float* __restrict__ a, const float* __restrict__ s, const float* __restrict__ dp,
-                   float* __restrict__ out, long long rows, int HW, int C, float inv_hw, int rows_per_block, int gw) {
+frame_scale_kernel(const T* __restrict__ a, const float* __restrict__ s, const float* __restrict__ dp,
+                   T* __restrict__ out, long long rows, int HW, int C, float inv_hw, int rows_per_block, int gw) {
     const nn::CgMap map(C, blockIdx.y * gw, gw);
     if (!map.active) return;
     const int c = map.cg * 4;
@@ -294,10 +299,11 @@ frame_scale_kernel(const float* __restrict__ a, const float* __restrict__ s, con
 }
 
 // dy *= act'(y) with the derivative expressed through the OUTPUT (ReLU, hard-sigmoid), in place
+template <typename T>
 __global__ void __launch_bounds__(TH)
-act_bwd_kernel(float* __restrict__ dy, const float* __restrict__ y, long long n, int act) {
+act_bwd_kernel(T* __restrict__ dy, const T* __restrict__ y, long long n, int act) {
     for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < n; i += (long long)gridDim.x * TH)
-        dy[i] *= nn::act_grad_from_out(y[i], act);
+        nn::st1(dy + i, nn::ld1(dy + i) * nn::act_grad_from_out(nn::ld1(y + i), act));
 }
 
 // y = act(x) (stand-alone activation, e.g. the ReLU between nn.LSTM and the classifier in video/models/resnet_lstm.py:152)
@@ -308,8 +314,9 @@ act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, 
 }
 
 // db[n] += sum_m dY[m, n]   (row stride ld)
+template <typename T>
 __global__ void __launch_bounds__(TH)
-colsum_kernel(const float* __restrict__ dY, long long ld, long long M, int N, float* __restrict__ db,
+colsum_kernel(const T* __restrict__ dY, long long ld, long long M, int N, float* __restrict__ db,
               int rows_per_block) {
     // thread -> column (coalesced), y-lanes over rows
     const int cols = min(N, TH);
@@ -320,7 +327,7 @@ colsum_kernel(const float* __restrict__ dY, long long ld, long long M, int N, fl
     if (rl >= rpp) return;
     for (int n = blockIdx.y * cols + threadIdx.x % cols; n < N; n += gridDim.y * cols) {
         float s = 0.f;
-        for (long long r = r0 + rl; r < r1; r += rpp) s += dY[r * ld + n];
+        for (long long r = r0 + rl; r < r1; r += rpp) s += nn::ld1(dY + r * ld + n);
         atomicAdd(&db[n], s);
     }
 }
@@ -368,15 +375,16 @@ static bn::Bn make_bn(long long rows, int C, const double* stats, const float* g
     LR_CHECK_ARG(training ? stats != nullptr : (running_mean && running_var), name ": missing statistics"); \
     if (rows == 0) return LR_OK
 
-extern "C" int lr_bn_act_fwd(const float* x, const double* stats, const float* gamma, const float* beta,
-                             float* running_mean, float* running_var, long long* num_batches_tracked, float eps,
-                             float momentum, int act, int training, const float* residual, int res_pre, float* z,
-                             long long rows, int C, lr_stream_t stream) {
+template <typename T>
+static int bn_act_fwd_impl(const T* x, const double* stats, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, long long* num_batches_tracked, float eps,
+                           float momentum, int act, int training, const T* residual, int res_pre, T* z,
+                           long long rows, int C, lr_stream_t stream) {
     LR_BN_CHECK("lr_bn_act_fwd");
     LR_CHECK_ARG(x && gamma && beta && z, "lr_bn_act_fwd: null pointer");
     LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(z); LR_CHECK_ALIGN(residual);
     dim3 grid; int gw; const int rpb = rows_per_block_for(rows, C, &grid, &gw);
-    bn::bn_act_fwd_kernel<<<grid, bn::TH, 0, stream>>>(
+    bn::bn_act_fwd_kernel<T><<<grid, bn::TH, 0, stream>>>(
         make_bn(rows, C, stats, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, act, training),
         x, residual, z, rpb, res_pre, gw);
     lr::count_launch();
@@ -384,10 +392,27 @@ extern "C" int lr_bn_act_fwd(const float* x, const double* stats, const float* g
     return LR_OK;
 }
 
-extern "C" int lr_bn_act_bwd(const float* x, const double* stats, const float* gamma, const float* beta,
-                             const float* running_mean, const float* running_var, float eps, int act, int training,
-                             const float* dz, const float* z_out, float* dres, double* sums /*[2C], zeroed by the caller*/,
-                             float* dx, float* dgamma, float* dbeta, long long rows, int C, lr_stream_t stream) {
+extern "C" int lr_bn_act_fwd(const float* x, const double* stats, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var, long long* num_batches_tracked, float eps,
+                             float momentum, int act, int training, const float* residual, int res_pre, float* z,
+                             long long rows, int C, lr_stream_t stream) {
+    return bn_act_fwd_impl<float>(x, stats, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, act,
+                                  training, residual, res_pre, z, rows, C, stream);
+}
+extern "C" int lr_bn_act_fwd_h(const void* x, const double* stats, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, long long* num_batches_tracked, float eps,
+                               float momentum, int act, int training, const void* residual, int res_pre, void* z,
+                               long long rows, int C, lr_stream_t stream) {
+    return bn_act_fwd_impl<nn::bf16>(static_cast<const nn::bf16*>(x), stats, gamma, beta, running_mean, running_var,
+                                     num_batches_tracked, eps, momentum, act, training,
+                                     static_cast<const nn::bf16*>(residual), res_pre, static_cast<nn::bf16*>(z), rows, C, stream);
+}
+
+template <typename T>
+static int bn_act_bwd_impl(const T* x, const double* stats, const float* gamma, const float* beta,
+                           const float* running_mean, const float* running_var, float eps, int act, int training,
+                           const T* dz, const T* z_out, T* dres, double* sums, T* dx, float* dgamma, float* dbeta,
+                           long long rows, int C, lr_stream_t stream) {
     LR_BN_CHECK("lr_bn_act_bwd");
     LR_CHECK_ARG(x && gamma && beta && dz && sums && dx, "lr_bn_act_bwd: null pointer");
     LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(dz); LR_CHECK_ALIGN(dx); LR_CHECK_ALIGN(z_out); LR_CHECK_ALIGN(dres);
@@ -396,30 +421,55 @@ extern "C" int lr_bn_act_bwd(const float* x, const double* stats, const float* g
     dim3 grid; int gw; const int rpb = rows_per_block_for(rows, C, &grid, &gw);
     const bn::Bn b = make_bn(rows, C, stats, gamma, beta, const_cast<float*>(running_mean),
                              const_cast<float*>(running_var), nullptr, eps, 0.f, act, training);
-    bn::bn_act_bwd_reduce_kernel<<<grid, bn::TH, 2 * C * sizeof(float), stream>>>(b, x, dz, z_out, sums, rpb, gw);
+    bn::bn_act_bwd_reduce_kernel<T><<<grid, bn::TH, 2 * C * sizeof(float), stream>>>(b, x, dz, z_out, sums, rpb, gw);
     lr::count_launch();
     LR_CHECK_LAUNCH("bn_act_bwd_reduce_kernel");
-    bn::bn_act_bwd_apply_kernel<<<grid, bn::TH, 0, stream>>>(b, x, dz, z_out, dres, sums, dx, dgamma, dbeta, rpb, gw);
+    bn::bn_act_bwd_apply_kernel<T><<<grid, bn::TH, 0, stream>>>(b, x, dz, z_out, dres, sums, dx, dgamma, dbeta, rpb, gw);
     lr::count_launch();
     LR_CHECK_LAUNCH("bn_act_bwd_apply_kernel");
     return LR_OK;
 }
 
-extern "C" int lr_frame_reduce(const float* a, const float* g, float* p, int F, int HW, int C, int mode,
-                               lr_stream_t stream) {
+extern "C" int lr_bn_act_bwd(const float* x, const double* stats, const float* gamma, const float* beta,
+                             const float* running_mean, const float* running_var, float eps, int act, int training,
+                             const float* dz, const float* z_out, float* dres, double* sums /*[2C], zeroed by the caller*/,
+                             float* dx, float* dgamma, float* dbeta, long long rows, int C, lr_stream_t stream) {
+    return bn_act_bwd_impl<float>(x, stats, gamma, beta, running_mean, running_var, eps, act, training, dz, z_out, dres, sums,
+                                  dx, dgamma, dbeta, rows, C, stream);
+}
+extern "C" int lr_bn_act_bwd_h(const void* x, const double* stats, const float* gamma, const float* beta,
+                               const float* running_mean, const float* running_var, float eps, int act, int training,
+                               const void* dz, const void* z_out, void* dres, double* sums, void* dx, float* dgamma,
+                               float* dbeta, long long rows, int C, lr_stream_t stream) {
+    typedef nn::bf16 H;
+    return bn_act_bwd_impl<H>(static_cast<const H*>(x), stats, gamma, beta, running_mean, running_var, eps, act, training,
+                              static_cast<const H*>(dz), static_cast<const H*>(z_out), static_cast<H*>(dres), sums,
+                              static_cast<H*>(dx), dgamma, dbeta, rows, C, stream);
+}
+
+template <typename T>
+static int frame_reduce_impl(const T* a, const T* g, float* p, int F, int HW, int C, int mode, lr_stream_t stream) {
     LR_CHECK_ARG(F >= 0 && HW > 0 && C > 0 && (C & 3) == 0, "lr_frame_reduce: bad shape");
     LR_CHECK_ARG(mode == 0 || (mode == 1 && g), "lr_frame_reduce: bad mode");
     if (F == 0) return LR_OK;
     LR_CHECK_ARG(a && p, "lr_frame_reduce: null pointer");
     LR_CHECK_ALIGN(a); LR_CHECK_ALIGN(g);
-    bn::frame_reduce_kernel<<<F, bn::TH, 0, stream>>>(a, g, p, HW, C, mode);
+    bn::frame_reduce_kernel<T><<<F, bn::TH, 0, stream>>>(a, g, p, HW, C, mode);
     lr::count_launch();
     LR_CHECK_LAUNCH("frame_reduce_kernel");
     return LR_OK;
 }
+extern "C" int lr_frame_reduce(const float* a, const float* g, float* p, int F, int HW, int C, int mode,
+                               lr_stream_t stream) {
+    return frame_reduce_impl<float>(a, g, p, F, HW, C, mode, stream);
+}
+extern "C" int lr_frame_reduce_h(const void* a, const void* g, float* p, int F, int HW, int C, int mode,
+                                 lr_stream_t stream) {
+    return frame_reduce_impl<nn::bf16>(static_cast<const nn::bf16*>(a), static_cast<const nn::bf16*>(g), p, F, HW, C, mode, stream);
+}
 
-extern "C" int lr_frame_scale(const float* a, const float* s, const float* dp, float* out, int F, int HW, int C,
-                              lr_stream_t stream) {
+template <typename T>
+static int frame_scale_impl(const T* a, const float* s, const float* dp, T* out, int F, int HW, int C, lr_stream_t stream) {
     LR_CHECK_ARG(F >= 0 && HW > 0 && C > 0 && (C & 3) == 0, "lr_frame_scale: bad shape");
     LR_CHECK_ARG((a && s) || dp, "lr_frame_scale: nothing to do");
     if (F == 0) return LR_OK;
@@ -427,13 +477,22 @@ extern "C" int lr_frame_scale(const float* a, const float* s, const float* dp, f
     LR_CHECK_ALIGN(a); LR_CHECK_ALIGN(s); LR_CHECK_ALIGN(dp); LR_CHECK_ALIGN(out);
     const long long rows = (long long)F * HW;
     dim3 grid; int gw; const int rpb = rows_per_block_for(rows, C, &grid, &gw, 8);
-    bn::frame_scale_kernel<<<grid, bn::TH, 0, stream>>>(a, s, dp, out, rows, HW, C, 1.f / (float)HW, rpb, gw);
+    bn::frame_scale_kernel<T><<<grid, bn::TH, 0, stream>>>(a, s, dp, out, rows, HW, C, 1.f / (float)HW, rpb, gw);
     lr::count_launch();
     LR_CHECK_LAUNCH("frame_scale_kernel");
     return LR_OK;
 }
+extern "C" int lr_frame_scale(const float* a, const float* s, const float* dp, float* out, int F, int HW, int C,
+                              lr_stream_t stream) {
+    return frame_scale_impl<float>(a, s, dp, out, F, HW, C, stream);
+}
+extern "C" int lr_frame_scale_h(const void* a, const float* s, const float* dp, void* out, int F, int HW, int C,
+                                lr_stream_t stream) {
+    return frame_scale_impl<nn::bf16>(static_cast<const nn::bf16*>(a), s, dp, static_cast<nn::bf16*>(out), F, HW, C, stream);
+}
 
-extern "C" int lr_act_bwd(float* dy, const float* y, long long n, int act, lr_stream_t stream) {
+template <typename T>
+static int act_bwd_impl(T* dy, const T* y, long long n, int act, lr_stream_t stream) {
     LR_CHECK_ARG(n >= 0, "lr_act_bwd: negative size");
     LR_CHECK_ARG(act == LR_ACT_RELU || act == LR_ACT_HSIGMOID || act == LR_ACT_RELU6 || act == LR_ACT_NONE, "lr_act_bwd: activation has no output-form derivative");
     if (n == 0 || act == LR_ACT_NONE) return LR_OK;
@@ -441,10 +500,16 @@ extern "C" int lr_act_bwd(float* dy, const float* y, long long n, int act, lr_st
     long long g = (n + bn::TH - 1) / bn::TH;
     const long long cap = (long long)lr::sm_count() * 16;
     if (g > cap) g = cap;
-    bn::act_bwd_kernel<<<(unsigned)g, bn::TH, 0, stream>>>(dy, y, n, act);
+    bn::act_bwd_kernel<T><<<(unsigned)g, bn::TH, 0, stream>>>(dy, y, n, act);
     lr::count_launch();
     LR_CHECK_LAUNCH("act_bwd_kernel");
     return LR_OK;
+}
+extern "C" int lr_act_bwd(float* dy, const float* y, long long n, int act, lr_stream_t stream) {
+    return act_bwd_impl<float>(dy, y, n, act, stream);
+}
+extern "C" int lr_act_bwd_h(void* dy, const void* y, long long n, int act, lr_stream_t stream) {
+    return act_bwd_impl<nn::bf16>(static_cast<nn::bf16*>(dy), static_cast<const nn::bf16*>(y), n, act, stream);
 }
 
 extern "C" int lr_act_fwd(const float* x, float* y, long long n, int act, lr_stream_t stream) {
@@ -461,7 +526,8 @@ extern "C" int lr_act_fwd(const float* x, float* y, long long n, int act, lr_str
     return LR_OK;
 }
 
-extern "C" int lr_colsum(const float* dY, long long ld, long long M, int N, float* db, lr_stream_t stream) {
+template <typename T>
+static int colsum_impl(const T* dY, long long ld, long long M, int N, float* db, lr_stream_t stream) {
     LR_CHECK_ARG(M >= 0 && N > 0, "lr_colsum: bad shape");
     if (M == 0) return LR_OK;
     LR_CHECK_ARG(dY && db, "lr_colsum: null pointer");
@@ -471,9 +537,42 @@ extern "C" int lr_colsum(const float* dY, long long ld, long long M, int N, floa
     rpb = ((rpb + rpp - 1) / rpp) * rpp;
     if (rpb < rpp) rpb = rpp;
     dim3 grid((unsigned)((M + rpb - 1) / rpb), 1);
-    bn::colsum_kernel<<<grid, bn::TH, 0, stream>>>(dY, ld, M, N, db, (int)rpb);
+    bn::colsum_kernel<T><<<grid, bn::TH, 0, stream>>>(dY, ld, M, N, db, (int)rpb);
     lr::count_launch();
     LR_CHECK_LAUNCH("colsum_kernel");
+    return LR_OK;
+}
+extern "C" int lr_colsum(const float* dY, long long ld, long long M, int N, float* db, lr_stream_t stream) {
+    return colsum_impl<float>(dY, ld, M, N, db, stream);
+}
+extern "C" int lr_colsum_h(const void* dY, long long ld, long long M, int N, float* db, lr_stream_t stream) {
+    return colsum_impl<nn::bf16>(static_cast<const nn::bf16*>(dY), ld, M, N, db, stream);
+}
+
+// fp32 -> bf16 copy of a contiguous buffer (the bf16 shadow of the flat parameter buffer, refreshed once per step,
+// and of re-laid-out weight matrices); n need not be a multiple of 4
+namespace bn {
+__global__ void __launch_bounds__(TH)
+cast_bf16_kernel(const float* __restrict__ src, nn::bf16* __restrict__ dst, long long n) {
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < n4; i += (long long)gridDim.x * TH)
+        nn::st4(dst + 4 * i, nn::ld4(src + 4 * i));
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[4 * n4 + threadIdx.x] = __float2bfloat16_rn(src[4 * n4 + threadIdx.x]);
+}
+}  // namespace bn
+extern "C" int lr_cast_bf16(const float* src, void* dst, long long n, lr_stream_t stream) {
+    LR_CHECK_ARG(n >= 0, "lr_cast_bf16: negative size");
+    if (n == 0) return LR_OK;
+    LR_CHECK_ARG(src && dst, "lr_cast_bf16: null pointer");
+    LR_CHECK_ALIGN(src);
+    LR_CHECK_ARG((reinterpret_cast<uintptr_t>(dst) & 7) == 0, "lr_cast_bf16: dst must be 8-byte aligned");
+    long long g = ((n >> 2) + bn::TH - 1) / bn::TH;
+    const long long cap = (long long)lr::sm_count() * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    bn::cast_bf16_kernel<<<(unsigned)g, bn::TH, 0, stream>>>(src, static_cast<nn::bf16*>(dst), n);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("cast_bf16_kernel");
     return LR_OK;
 }
 

@@ -35,8 +35,9 @@ __device__ __forceinline__ float src_ld(const Src& s, long long fb, int c, int h
 }
 
 // one thread -> 4 consecutive columns of one row (coalesced float4 store; the gathers hit L1)
+template <typename T>
 __global__ void __launch_bounds__(TH)
-im2col_kernel(const Src s, const Geo g, float* __restrict__ col, long long rows) {
+im2col_kernel(const Src s, const Geo g, T* __restrict__ col, long long rows) {
     const int q4 = g.ldk >> 2;
     const long long total = rows * q4;
     const int kk = g.kh * g.kw;
@@ -75,8 +76,9 @@ im2col_kernel(const Src s, const Geo g, float* __restrict__ col, long long rows)
 // Fast path of the stems on raw uint8 lip frames (3 channels, 3x3 window, any stride / padding): one thread per
 // output pixel reads its 3 x 3 x 3 byte patch (L1 serves the overlap with the neighbours) and writes its whole
 // 28-float row (7 coalesced float4 stores) -- no per-element index arithmetic.
+template <typename T>
 __global__ void __launch_bounds__(TH)
-im2col_u8c3_3x3_kernel(const Src s, const Geo g, float* __restrict__ col, long long rows) {
+im2col_u8c3_3x3_kernel(const Src s, const Geo g, T* __restrict__ col, long long rows) {
     const unsigned char* xb = static_cast<const unsigned char*>(s.x);
     for (long long row = (long long)blockIdx.x * TH + threadIdx.x; row < rows; row += (long long)gridDim.x * TH) {
         const int wd = int(row % g.Wd);
@@ -97,9 +99,10 @@ im2col_u8c3_3x3_kernel(const Src s, const Geo g, float* __restrict__ col, long l
             }
         }
         v[27] = 0.f;
-        float* o = col + row * g.ldk;
+        T* o = col + row * g.ldk;
 #pragma unroll
         for (int j = 0; j < 28; j += 4) nn::st4(o + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        for (int j = 28; j < g.ldk; j += 4) nn::st4(o + j, make_float4(0.f, 0.f, 0.f, 0.f));   // bf16 rows are padded to 32
     }
 }
 
@@ -107,8 +110,9 @@ im2col_u8c3_3x3_kernel(const Src s, const Geo g, float* __restrict__ col, long l
 //   col[(f,hd,wd)][(r*kw + s)*C + c] = x[f, hs, ws, c]   (0 outside the image)
 // A thread moves one float4 of channels: the gather is a shifted, fully coalesced copy (both sides), which is what
 // lets the ResNet trunk's patch matrices be written at HBM speed.  transposed: the dgrad operand (see lr_im2col).
+template <typename T>
 __global__ void __launch_bounds__(TH)
-im2col_tap_kernel(const float* __restrict__ x, const Geo g, int Hs, int Ws, int C, float* __restrict__ col, long long rows) {
+im2col_tap_kernel(const T* __restrict__ x, const Geo g, int Hs, int Ws, int C, T* __restrict__ col, long long rows) {
     // one thread = one (row, 4-channel group): the pixel decode is done once and reused for all kh*kw taps
     const int c4n = C >> 2;
     const long long total = rows * c4n;
@@ -118,8 +122,8 @@ im2col_tap_kernel(const float* __restrict__ x, const Geo g, int Hs, int Ws, int 
         const int wd = int(row % g.Wd);
         const long long t = row / g.Wd;
         const int hd = int(t % g.Hd), f = int(t / g.Hd);
-        const float* xf = x + (long long)f * Hs * Ws * C + c;
-        float* o = col + row * g.ldk + c;
+        const T* xf = x + (long long)f * Hs * Ws * C + c;
+        T* o = col + row * g.ldk + c;
         for (int r = 0; r < g.kh; ++r) {
             int hs; bool okh;
             if (!g.transposed) { hs = hd * g.stride - g.pad + r; okh = hs >= 0 && hs < Hs; }
@@ -172,8 +176,9 @@ weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int
 // ------------------------------------------------------------------------------------------ max pooling
 // y[f,ho,wo,c] = max over the window (padding = -inf), arg = r*k + s of the FIRST maximum in scan order
 // (torch.nn.MaxPool2d tie rule: `val > maxval`).
+template <typename T>
 __global__ void __launch_bounds__(TH)
-maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned char* __restrict__ arg, int F, int H,
+maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ arg, int F, int H,
                    int W, int C, int k, int stride, int pad, int Ho, int Wo) {
     const int c4n = C >> 2;
     const long long total = (long long)F * Ho * Wo * c4n;
@@ -205,8 +210,9 @@ maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned 
 }
 
 // dx[f,h,w,c] = sum of dy over the windows whose saved arg-max is (h, w)   (gather form: no atomics)
+template <typename T>
 __global__ void __launch_bounds__(TH)
-maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ arg, float* __restrict__ dx, int F,
+maxpool_bwd_kernel(const T* __restrict__ dy, const unsigned char* __restrict__ arg, T* __restrict__ dx, int F,
                    int H, int W, int C, int k, int stride, int pad, int Ho, int Wo) {
     const int c4n = C >> 2;
     const long long total = (long long)F * H * W * c4n;
@@ -277,10 +283,11 @@ static unsigned grid_for(long long work) {
 
 }  // namespace c2
 
-extern "C" int lr_im2col(const void* x, int is_u8, float scale, int F, int T, long long sb, long long st, long long sc,
-                         long long sh, long long sw, int Hs, int Ws, int C, int kh, int kw, int stride, int pad,
-                         int transposed, int Hd, int Wd, float* col, long long ldk, lr_stream_t stream) {
-    LR_CHECK_ARG(F >= 0 && T > 0 && Hs > 0 && Ws > 0 && C > 0 && Hd > 0 && Wd > 0, "lr_im2col: bad shape");
+template <typename T>
+static int im2col_impl(const void* x, int is_u8, float scale, int F, int T_, long long sb, long long st, long long sc,
+                       long long sh, long long sw, int Hs, int Ws, int C, int kh, int kw, int stride, int pad,
+                       int transposed, int Hd, int Wd, T* col, long long ldk, lr_stream_t stream) {
+    LR_CHECK_ARG(F >= 0 && T_ > 0 && Hs > 0 && Ws > 0 && C > 0 && Hd > 0 && Wd > 0, "lr_im2col: bad shape");
     LR_CHECK_ARG(kh > 0 && kw > 0 && stride > 0 && pad >= 0, "lr_im2col: bad window");
     const long long K = (long long)C * kh * kw;
     LR_CHECK_ARG(ldk >= K && (ldk & 3) == 0, "lr_im2col: ldk must be >= C*kh*kw and a multiple of 4");
@@ -288,24 +295,38 @@ extern "C" int lr_im2col(const void* x, int is_u8, float scale, int F, int T, lo
     LR_CHECK_ARG(x && col, "lr_im2col: null pointer");
     LR_CHECK_ALIGN(col);
     c2::Src s;
-    s.x = x; s.is_u8 = is_u8; s.scale = scale; s.T = T; s.sb = sb; s.st = st; s.sc = sc; s.sh = sh; s.sw = sw;
+    s.x = x; s.is_u8 = is_u8; s.scale = scale; s.T = T_; s.sb = sb; s.st = st; s.sc = sc; s.sh = sh; s.sw = sw;
     s.Hs = Hs; s.Ws = Ws; s.C = C;
     c2::Geo g;
     g.Hd = Hd; g.Wd = Wd; g.kh = kh; g.kw = kw; g.stride = stride; g.pad = pad; g.transposed = transposed;
     g.pad_w = pad;
     g.K = (int)K; g.ldk = (int)ldk;
     const long long rows = (long long)F * Hd * Wd;
-    if (is_u8 && C == 3 && kh == 3 && kw == 3 && !transposed && ldk == 28)
-        c2::im2col_u8c3_3x3_kernel<<<c2::grid_for(rows), c2::TH, 0, stream>>>(s, g, col, rows);
+    if (is_u8 && C == 3 && kh == 3 && kw == 3 && !transposed && ldk >= 28 && ldk <= 32)
+        c2::im2col_u8c3_3x3_kernel<T><<<c2::grid_for(rows), c2::TH, 0, stream>>>(s, g, col, rows);
     else
-        c2::im2col_kernel<<<c2::grid_for(rows * (ldk >> 2)), c2::TH, 0, stream>>>(s, g, col, rows);
+        c2::im2col_kernel<T><<<c2::grid_for(rows * (ldk >> 2)), c2::TH, 0, stream>>>(s, g, col, rows);
     lr::count_launch();
     LR_CHECK_LAUNCH("im2col_kernel");
     return LR_OK;
 }
+extern "C" int lr_im2col(const void* x, int is_u8, float scale, int F, int T, long long sb, long long st, long long sc,
+                         long long sh, long long sw, int Hs, int Ws, int C, int kh, int kw, int stride, int pad,
+                         int transposed, int Hd, int Wd, float* col, long long ldk, lr_stream_t stream) {
+    return im2col_impl<float>(x, is_u8, scale, F, T, sb, st, sc, sh, sw, Hs, Ws, C, kh, kw, stride, pad, transposed, Hd, Wd,
+                              col, ldk, stream);
+}
+/* bf16 patch matrix (precision "bf16"): the source is still the caller's uint8 / float frames */
+extern "C" int lr_im2col_h(const void* x, int is_u8, float scale, int F, int T, long long sb, long long st, long long sc,
+                           long long sh, long long sw, int Hs, int Ws, int C, int kh, int kw, int stride, int pad,
+                           int transposed, int Hd, int Wd, void* col, long long ldk, lr_stream_t stream) {
+    return im2col_impl<nn::bf16>(x, is_u8, scale, F, T, sb, st, sc, sh, sw, Hs, Ws, C, kh, kw, stride, pad, transposed, Hd, Wd,
+                                 static_cast<nn::bf16*>(col), ldk, stream);
+}
 
-extern "C" int lr_im2col_tap(const float* x, int F, int Hs, int Ws, int C, int kh, int kw, int stride, int pad_h,
-                             int pad_w, int transposed, int Hd, int Wd, float* col, lr_stream_t stream) {
+template <typename T>
+static int im2col_tap_impl(const T* x, int F, int Hs, int Ws, int C, int kh, int kw, int stride, int pad_h,
+                           int pad_w, int transposed, int Hd, int Wd, T* col, lr_stream_t stream) {
     const int pad = pad_h;
     LR_CHECK_ARG(F >= 0 && Hs > 0 && Ws > 0 && C > 0 && (C & 3) == 0 && Hd > 0 && Wd > 0, "lr_im2col_tap: bad shape (C %% 4 != 0?)");
     LR_CHECK_ARG(kh > 0 && kw > 0 && stride > 0 && pad_h >= 0 && pad_w >= 0, "lr_im2col_tap: bad window");
@@ -317,10 +338,19 @@ extern "C" int lr_im2col_tap(const float* x, int F, int Hs, int Ws, int C, int k
     g.pad_w = pad_w;
     g.K = C * kh * kw; g.ldk = g.K;
     const long long rows = (long long)F * Hd * Wd;
-    c2::im2col_tap_kernel<<<c2::grid_for(rows * (C >> 2)), c2::TH, 0, stream>>>(x, g, Hs, Ws, C, col, rows);
+    c2::im2col_tap_kernel<T><<<c2::grid_for(rows * (C >> 2)), c2::TH, 0, stream>>>(x, g, Hs, Ws, C, col, rows);
     lr::count_launch();
     LR_CHECK_LAUNCH("im2col_tap_kernel");
     return LR_OK;
+}
+extern "C" int lr_im2col_tap(const float* x, int F, int Hs, int Ws, int C, int kh, int kw, int stride, int pad_h,
+                             int pad_w, int transposed, int Hd, int Wd, float* col, lr_stream_t stream) {
+    return im2col_tap_impl<float>(x, F, Hs, Ws, C, kh, kw, stride, pad_h, pad_w, transposed, Hd, Wd, col, stream);
+}
+extern "C" int lr_im2col_tap_h(const void* x, int F, int Hs, int Ws, int C, int kh, int kw, int stride, int pad_h,
+                               int pad_w, int transposed, int Hd, int Wd, void* col, lr_stream_t stream) {
+    return im2col_tap_impl<nn::bf16>(static_cast<const nn::bf16*>(x), F, Hs, Ws, C, kh, kw, stride, pad_h, pad_w, transposed,
+                                     Hd, Wd, static_cast<nn::bf16*>(col), stream);
 }
 
 extern "C" int lr_weight_tap(const float* src, float* dst, int Cout, int Cin, int kk, int mode, lr_stream_t stream) {
@@ -342,8 +372,9 @@ extern "C" int lr_weight_transpose(const float* w, float* wt, int Cout, int Cin,
     return LR_OK;
 }
 
-extern "C" int lr_maxpool_fwd(const float* x, float* y, unsigned char* arg, int F, int H, int W, int C, int k,
-                              int stride, int pad, lr_stream_t stream) {
+template <typename T>
+static int maxpool_fwd_impl(const T* x, T* y, unsigned char* arg, int F, int H, int W, int C, int k,
+                            int stride, int pad, lr_stream_t stream) {
     LR_CHECK_ARG(F >= 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, "lr_maxpool_fwd: bad shape (C %% 4 != 0?)");
     LR_CHECK_ARG(k > 0 && k <= 15 && stride > 0 && pad >= 0 && 2 * pad <= k, "lr_maxpool_fwd: bad window");
     if (F == 0) return LR_OK;
@@ -351,26 +382,43 @@ extern "C" int lr_maxpool_fwd(const float* x, float* y, unsigned char* arg, int 
     LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(y);
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     LR_CHECK_ARG(Ho > 0 && Wo > 0, "lr_maxpool_fwd: window larger than the input");
-    c2::maxpool_fwd_kernel<<<c2::grid_for((long long)F * Ho * Wo * (C >> 2)), c2::TH, 0, stream>>>(
+    c2::maxpool_fwd_kernel<T><<<c2::grid_for((long long)F * Ho * Wo * (C >> 2)), c2::TH, 0, stream>>>(
         x, y, arg, F, H, W, C, k, stride, pad, Ho, Wo);
     lr::count_launch();
     LR_CHECK_LAUNCH("maxpool_fwd_kernel");
     return LR_OK;
 }
-
-extern "C" int lr_maxpool_bwd(const float* dy, const unsigned char* arg, float* dx, int F, int H, int W, int C, int k,
+extern "C" int lr_maxpool_fwd(const float* x, float* y, unsigned char* arg, int F, int H, int W, int C, int k,
                               int stride, int pad, lr_stream_t stream) {
+    return maxpool_fwd_impl<float>(x, y, arg, F, H, W, C, k, stride, pad, stream);
+}
+extern "C" int lr_maxpool_fwd_h(const void* x, void* y, unsigned char* arg, int F, int H, int W, int C, int k,
+                                int stride, int pad, lr_stream_t stream) {
+    return maxpool_fwd_impl<nn::bf16>(static_cast<const nn::bf16*>(x), static_cast<nn::bf16*>(y), arg, F, H, W, C, k, stride, pad, stream);
+}
+
+template <typename T>
+static int maxpool_bwd_impl(const T* dy, const unsigned char* arg, T* dx, int F, int H, int W, int C, int k,
+                            int stride, int pad, lr_stream_t stream) {
     LR_CHECK_ARG(F >= 0 && H > 0 && W > 0 && C > 0 && (C & 3) == 0, "lr_maxpool_bwd: bad shape");
     LR_CHECK_ARG(k > 0 && k <= 15 && stride > 0 && pad >= 0 && 2 * pad <= k, "lr_maxpool_bwd: bad window");
     if (F == 0) return LR_OK;
     LR_CHECK_ARG(dy && arg && dx, "lr_maxpool_bwd: null pointer");
     LR_CHECK_ALIGN(dy); LR_CHECK_ALIGN(dx);
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-    c2::maxpool_bwd_kernel<<<c2::grid_for((long long)F * H * W * (C >> 2)), c2::TH, 0, stream>>>(
+    c2::maxpool_bwd_kernel<T><<<c2::grid_for((long long)F * H * W * (C >> 2)), c2::TH, 0, stream>>>(
         dy, arg, dx, F, H, W, C, k, stride, pad, Ho, Wo);
     lr::count_launch();
     LR_CHECK_LAUNCH("maxpool_bwd_kernel");
     return LR_OK;
+}
+extern "C" int lr_maxpool_bwd(const float* dy, const unsigned char* arg, float* dx, int F, int H, int W, int C, int k,
+                              int stride, int pad, lr_stream_t stream) {
+    return maxpool_bwd_impl<float>(dy, arg, dx, F, H, W, C, k, stride, pad, stream);
+}
+extern "C" int lr_maxpool_bwd_h(const void* dy, const unsigned char* arg, void* dx, int F, int H, int W, int C, int k,
+                                int stride, int pad, lr_stream_t stream) {
+    return maxpool_bwd_impl<nn::bf16>(static_cast<const nn::bf16*>(dy), arg, static_cast<nn::bf16*>(dx), F, H, W, C, k, stride, pad, stream);
 }
 
 extern "C" int lr_dropout_fwd(const float* x, float* y, unsigned char* mask, long long n, float p,

@@ -27,7 +27,7 @@ struct Geo {
     long long units;       // F * nb
 };
 
-__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bool valid) {
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, bool valid) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
     const int n = valid ? 16 : 0;                       // src-size 0: the 16 destination bytes are zero filled
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
@@ -47,26 +47,29 @@ __device__ __forceinline__ void build_pixel_table(const Geo& d, int* tab) {
 // Asynchronously stage tile[ul][r][col][c] = src[f, row0(band) + r, col0 + col, chunk*CC + c] (zero outside
 // [0,SH) x [0,SW) and past the last unit) for the UB units starting at u0; cp.async keeps many 16-byte requests
 // in flight per thread without a register round trip, so a round's loads overlap the previous round's math.
-__device__ __forceinline__ void stage_async(const Geo& d, const float* __restrict__ src, float* tile, const int* tab,
+// (T = float: 4 channels per 16-byte request; T = bf16: 8 channels; the tile keeps the storage type)
+template <typename T>
+__device__ __forceinline__ void stage_async(const Geo& d, const T* __restrict__ src, T* tile, const int* tab,
                                             int u0, int chunk, int SH, int SW, int band_rows, int row_shift,
                                             int row_off, int col0) {
-    const int g4 = d.CC >> 2, lanes = TH / g4;
+    constexpr int V = 16 / (int)sizeof(T);                         // channels per 16-byte request
+    const int g4 = d.CC / V, lanes = TH / g4;
     const int g = threadIdx.x % g4, p = threadIdx.x / g4;
     const int npix = d.rows_t * d.cols_t;
-    const int c = chunk * d.CC + g * 4;
+    const int c = chunk * d.CC + g * V;
     const bool cvalid = c < d.C;
     for (int ul = 0; ul < d.UB; ++ul) {
         const int u = u0 + ul;
         const int f = u / d.nb, b = u - f * d.nb;
         const int row0 = (b * band_rows + row_off) >> row_shift;
         const bool uvalid = cvalid && u < (int)d.units;
-        const float* base = src + (((long long)f * SH + row0) * SW + col0) * d.C + c;
-        float* dst = tile + ((long long)ul * npix * g4 + g) * 4;
+        const T* base = src + (((long long)f * SH + row0) * SW + col0) * d.C + c;
+        T* dst = tile + ((long long)ul * npix * g4 + g) * V;
         for (int rc = p; rc < npix; rc += lanes) {
             const int e = tab[rc], r = e >> 16, col = e & 0xffff;
             const int row = row0 + r, cc = col0 + col;
             const bool valid = uvalid && row >= 0 && row < SH && cc >= 0 && cc < SW;
-            cp_async16(dst + (long long)rc * g4 * 4, valid ? base + ((long long)r * SW + col) * d.C : src, valid);
+            cp_async16(dst + (long long)rc * g4 * V, valid ? base + ((long long)r * SW + col) * d.C : src, valid);
         }
     }
 }
@@ -78,11 +81,12 @@ __device__ __forceinline__ void load_weights(const float* __restrict__ w, int c,
 }
 
 // ------------------------------------------------------------------------------------------ forward
-template <int K, int S, int WS>
+template <typename T, int K, int S, int WS>
 __global__ void __launch_bounds__(TH)
-fwd_kernel(const Geo d, const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+fwd_kernel(const Geo d, const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
            double* __restrict__ stats) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
     __shared__ float ssum[TH], ssq[TH];                 // one slot per thread: [row lane][channel], added in lane order
     __shared__ int tab[MAX_PIX];
     build_pixel_table(d, tab);
@@ -105,7 +109,7 @@ fwd_kernel(const Geo d, const float* __restrict__ x, const float* __restrict__ w
         cp_async_commit();
         cp_async_wait<1>();                             // this round's tile has landed (the prefetch may be in flight)
         __syncthreads();
-        const float* tile = smem + buf * tile_floats;
+        const T* tile = smem + buf * tile_floats;
         const int u0 = rd * d.UB;
         const int per_unit = d.RB * d.nseg;
         for (int it = rl; it < d.UB * per_unit && ok; it += nrl) {       // flat over (unit, row, segment): balanced lanes
@@ -120,21 +124,25 @@ fwd_kernel(const Geo d, const float* __restrict__ x, const float* __restrict__ w
             float acc[WS];
 #pragma unroll
             for (int j = 0; j < WS; ++j) acc[j] = 0.f;
-            const float* base = tile + ((long long)(ul * d.rows_t + ro * S) * d.cols_t + wo0 * S) * d.CC + cl;
+            const T* base = tile + ((long long)(ul * d.rows_t + ro * S) * d.cols_t + wo0 * S) * d.CC + cl;
 #pragma unroll
             for (int kh = 0; kh < K; ++kh) {
                 float xr[NX];
 #pragma unroll
-                for (int i = 0; i < NX; ++i) xr[i] = base[(kh * d.cols_t + i) * d.CC];
+                for (int i = 0; i < NX; ++i) xr[i] = nn::ld1(base + (kh * d.cols_t + i) * d.CC);
 #pragma unroll
                 for (int j = 0; j < WS; ++j)
 #pragma unroll
                     for (int kw = 0; kw < K; ++kw) acc[j] = fmaf(xr[j * S + kw], wr[kh * K + kw], acc[j]);
             }
-            float* o = y + (((long long)f * d.Ho + ho) * d.Wo + wo0) * d.C + c;
+            T* o = y + (((long long)f * d.Ho + ho) * d.Wo + wo0) * d.C + c;
 #pragma unroll
             for (int j = 0; j < WS; ++j)
-                if (wo0 + j < d.Wo) { o[(long long)j * d.C] = acc[j]; ls += acc[j]; lq = fmaf(acc[j], acc[j], lq); }
+                if (wo0 + j < d.Wo) {
+                    nn::st1(o + (long long)j * d.C, acc[j]);
+                    const float v = sizeof(T) == 2 ? __bfloat162float(__float2bfloat16_rn(acc[j])) : acc[j];   // the STORED value
+                    ls += v; lq = fmaf(v, v, lq);
+                }
         }
         }
         __syncthreads();                                // everyone is done with `buf` before it is refilled
@@ -156,29 +164,32 @@ fwd_kernel(const Geo d, const float* __restrict__ x, const float* __restrict__ w
 
 // ------------------------------------------------------------------------------------------ wgrad
 // dw[c,kh,kw] += sum_{f,ho,wo} dy[f,ho,wo,c] * x[f, ho*s-pad+kh, wo*s-pad+kw, c]; persistent, double buffered.
-__device__ __forceinline__ void stage_dy_async(const Geo& d, const float* __restrict__ dy, float* gt, int u0, int chunk,
+template <typename T>
+__device__ __forceinline__ void stage_dy_async(const Geo& d, const T* __restrict__ dy, T* gt, int u0, int chunk,
                                                int gw) {
-    const int g4 = d.CC >> 2, lanes = TH / g4;
+    constexpr int V = 16 / (int)sizeof(T);
+    const int g4 = d.CC / V, lanes = TH / g4;
     const int g = threadIdx.x % g4, p = threadIdx.x / g4;
-    const int cc = chunk * d.CC + g * 4;
+    const int cc = chunk * d.CC + g * V;
     const int npix = d.RB * gw;
     for (int ul = 0; ul < d.UB; ++ul) {
         const int u = u0 + ul;
         const int f = u / d.nb, ho0 = (u - f * d.nb) * d.RB;
         const bool uvalid = cc < d.C && u < (int)d.units;
-        float* dst = gt + ((long long)ul * npix * g4 + g) * 4;
+        T* dst = gt + ((long long)ul * npix * g4 + g) * V;
         for (int rw = p; rw < npix; rw += lanes) {
             const int ro = rw / gw, wo = rw - ro * gw, ho = ho0 + ro;
             const bool valid = uvalid && ho < d.Ho && wo < d.Wo;
-            cp_async16(dst + (long long)rw * g4 * 4, valid ? dy + (((long long)f * d.Ho + ho) * d.Wo + wo) * d.C + cc : dy, valid);
+            cp_async16(dst + (long long)rw * g4 * V, valid ? dy + (((long long)f * d.Ho + ho) * d.Wo + wo) * d.C + cc : dy, valid);
         }
     }
 }
 
-template <int K, int S, int WS>
+template <typename T, int K, int S, int WS>
 __global__ void __launch_bounds__(TH)
-wgrad_kernel(const Geo d, const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dwt) {
-    extern __shared__ __align__(16) float smem[];
+wgrad_kernel(const Geo d, const T* __restrict__ dy, const T* __restrict__ x, float* __restrict__ dwt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
     __shared__ float red[K * K][32];
     __shared__ int tab[MAX_PIX];
     build_pixel_table(d, tab);
@@ -204,15 +215,15 @@ wgrad_kernel(const Geo d, const float* __restrict__ dy, const float* __restrict_
     for (int rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
         const int nxt = rd + gridDim.x;
         if (nxt < rounds) {
-            float* nb_ = smem + (buf ^ 1) * buf_floats;
+            T* nb_ = smem + (buf ^ 1) * buf_floats;
             stage_async(d, x, nb_, tab, nxt * d.UB, chunk, d.H, d.W, d.RB * S, 0, -d.pad, -d.pad);
             stage_dy_async(d, dy, nb_ + x_floats, nxt * d.UB, chunk, gw);
         }
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        const float* tile = smem + buf * buf_floats;
-        const float* gt = tile + x_floats;
+        const T* tile = smem + buf * buf_floats;
+        const T* gt = tile + x_floats;
         const int u0 = rd * d.UB;
         if (ok) {
             const int per_unit = d.RB * d.nseg;
@@ -223,15 +234,15 @@ wgrad_kernel(const Geo d, const float* __restrict__ dy, const float* __restrict_
                 const int ro = rs / d.nseg, seg = rs - ro * d.nseg;
                 const int wo0 = seg * WS;
                 float g[WS];
-                const float* gb = gt + ((long long)(ul * d.RB + ro) * gw + wo0) * d.CC + cl;
+                const T* gb = gt + ((long long)(ul * d.RB + ro) * gw + wo0) * d.CC + cl;
 #pragma unroll
-                for (int j = 0; j < WS; ++j) g[j] = gb[j * d.CC];
-                const float* base = tile + ((long long)(ul * d.rows_t + ro * S) * d.cols_t + wo0 * S) * d.CC + cl;
+                for (int j = 0; j < WS; ++j) g[j] = nn::ld1(gb + j * d.CC);
+                const T* base = tile + ((long long)(ul * d.rows_t + ro * S) * d.cols_t + wo0 * S) * d.CC + cl;
 #pragma unroll
                 for (int kh = 0; kh < K; ++kh) {
                     float xr[NX];
 #pragma unroll
-                    for (int i = 0; i < NX; ++i) xr[i] = base[(kh * d.cols_t + i) * d.CC];
+                    for (int i = 0; i < NX; ++i) xr[i] = nn::ld1(base + (kh * d.cols_t + i) * d.CC);
 #pragma unroll
                     for (int kw = 0; kw < K; ++kw)
 #pragma unroll
@@ -262,10 +273,11 @@ wgrad_kernel(const Geo d, const float* __restrict__ dy, const float* __restrict_
 template <int S>
 __host__ __device__ constexpr int floor_div(int a) { return S == 1 ? a : (a >= 0 ? a / 2 : -((-a + 1) / 2)); }
 
-template <int K, int S, int WS>
+template <typename T, int K, int S, int WS>
 __global__ void __launch_bounds__(TH)
-dgrad_kernel(const Geo d, const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx) {
-    extern __shared__ __align__(16) float smem[];
+dgrad_kernel(const Geo d, const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
     static_assert(S == 1 || (WS % 2) == 0, "stride-2 dgrad needs an even row segment");
     constexpr int SH_ = S == 2 ? 1 : 0, P = K / 2;
     __shared__ int tab[MAX_PIX];
@@ -290,7 +302,7 @@ dgrad_kernel(const Geo d, const float* __restrict__ dy, const float* __restrict_
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        const float* tile = smem + buf * tile_floats;
+        const T* tile = smem + buf * tile_floats;
         const int u0 = rd * d.UB;
         const int per_unit = d.RB * d.nseg;
         for (int it = rl; it < d.UB * per_unit && ok; it += nrl) {
@@ -312,10 +324,10 @@ dgrad_kernel(const Geo d, const float* __restrict__ dy, const float* __restrict_
                 const int hn = hi + P - kh;
                 if (S == 2 && (hn & 1)) continue;
                 const int tr = (hn >> SH_) - lo_r;
-                const float* row = tile + ((long long)(ul * d.rows_t + tr) * d.cols_t + tc0) * d.CC + cl;
+                const T* row = tile + ((long long)(ul * d.rows_t + tr) * d.cols_t + tc0) * d.CC + cl;
                 float gr[NG];
 #pragma unroll
-                for (int i = 0; i < NG; ++i) gr[i] = row[i * d.CC];
+                for (int i = 0; i < NG; ++i) gr[i] = nn::ld1(row + i * d.CC);
 #pragma unroll
                 for (int j = 0; j < WS; ++j)
 #pragma unroll
@@ -325,9 +337,9 @@ dgrad_kernel(const Geo d, const float* __restrict__ dy, const float* __restrict_
                         acc[j] = fmaf(gr[floor_div<S>(j + P - kw) - BASE_OFF], wr[kh * K + kw], acc[j]);
                     }
             }
-            float* o = dx + (((long long)f * d.H + hi) * d.W + wi0) * d.C + c;
+            T* o = dx + (((long long)f * d.H + hi) * d.W + wi0) * d.C + c;
 #pragma unroll
-            for (int j = 0; j < WS; ++j) if (wi0 + j < d.W) o[(long long)j * d.C] = acc[j];
+            for (int j = 0; j < WS; ++j) if (wi0 + j < d.W) nn::st1(o + (long long)j * d.C, acc[j]);
           }
         }
         __syncthreads();
@@ -378,9 +390,11 @@ static Geo make_geo(int F, int H, int W, int C, int k, int stride, int mode /*0 
     if (d.units < d.UB) d.UB = (int)d.units;
     return d;
 }
-static size_t smem_bytes(const Geo& d, int mode, int ws) {
-    size_t b = (size_t)d.UB * d.rows_t * d.cols_t * d.CC * 4;
-    if (mode == 1) b += (size_t)d.UB * d.RB * d.nseg * ws * d.CC * 4;
+// es: bytes per staged element (4 = fp32, 2 = bf16).  The tile GEOMETRY (make_geo) is the same for both storage
+// types -- it is sized for fp32 -- so the bf16 kernels simply use half the shared memory.
+static size_t smem_bytes(const Geo& d, int mode, int ws, int es) {
+    size_t b = (size_t)d.UB * d.rows_t * d.cols_t * d.CC * es;
+    if (mode == 1) b += (size_t)d.UB * d.RB * d.nseg * ws * d.CC * es;
     return 2 * b;
 }
 // persistent grid: enough CTAs to fill the GPU a few times over, never more than there are rounds
@@ -400,9 +414,9 @@ constexpr int SMEM_CEILING = 160 * 1024;
 
 #define DW_LAUNCH(KERNEL, K_, S_, WS_, ...)                                              \
     do {                                                                                 \
-        err = lr::ensure_max_dynamic_smem(KERNEL<K_, S_, WS_>, SMEM_CEILING);            \
+        err = lr::ensure_max_dynamic_smem(KERNEL<T, K_, S_, WS_>, SMEM_CEILING);         \
         if (err == cudaSuccess && smem > (size_t)SMEM_CEILING) err = cudaErrorInvalidValue; \
-        if (err == cudaSuccess) KERNEL<K_, S_, WS_><<<grid, TH, smem, stream>>>(__VA_ARGS__); \
+        if (err == cudaSuccess) KERNEL<T, K_, S_, WS_><<<grid, TH, smem, stream>>>(__VA_ARGS__); \
     } while (0)
 #define DW_DISPATCH_WS(KERNEL, K_, S_, ...)                                              \
     switch (ws) {                                                                        \
@@ -424,13 +438,15 @@ constexpr int SMEM_CEILING = 160 * 1024;
     LR_CHECK_ARG(stride == 1 || stride == 2, name ": stride %d not in {1,2}", stride);                \
     if (F == 0) return LR_OK
 
-extern "C" int lr_dwconv_fwd(const float* x, const float* w, float* y, double* stats, int F, int H, int W, int C,
-                             int k, int stride, lr_stream_t stream) {
+template <typename T>
+static int dwconv_fwd_impl(const T* x, const float* w, T* y, double* stats, int F, int H, int W, int C,
+                           int k, int stride, lr_stream_t stream) {
     using namespace dw;
     LR_DW_CHECK("lr_dwconv_fwd");
     LR_CHECK_ARG(x && w && y, "lr_dwconv_fwd: null pointer");
+    LR_CHECK_ARG(sizeof(T) == 4 || (C & 7) == 0, "lr_dwconv_fwd: bf16 storage needs C %% 8 == 0");
     LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(y);
-    if (dws::dispatch(0, x, w, y, stats, F, H, W, C, k, stride, stream)) {
+    if (dws::dispatch<T>(0, x, w, y, stats, F, H, W, C, k, stride, stream)) {
         lr::count_launch();
         LR_CHECK_LAUNCH("dws::fwd_kernel");
         return LR_OK;
@@ -439,7 +455,7 @@ extern "C" int lr_dwconv_fwd(const float* x, const float* w, float* y, double* s
     const int ws = pick_ws(Wo, false);
     const Geo d = make_geo(F, H, W, C, k, stride, 0, ws);
     LR_CHECK_ARG(d.rows_t * d.cols_t <= MAX_PIX, "lr_dwconv: image row of %d pixels is too wide for the staged tile", W);
-    const size_t smem = smem_bytes(d, 0, ws);
+    const size_t smem = smem_bytes(d, 0, ws, (int)sizeof(T));
     const dim3 grid = persistent_grid(d, 4);
     cudaError_t err = cudaSuccess;
     if (k == 3 && stride == 1) { DW_DISPATCH_WS(fwd_kernel, 3, 1, d, x, w, y, stats) }
@@ -451,14 +467,24 @@ extern "C" int lr_dwconv_fwd(const float* x, const float* w, float* y, double* s
     LR_CHECK_LAUNCH("dw::fwd_kernel");
     return LR_OK;
 }
+extern "C" int lr_dwconv_fwd(const float* x, const float* w, float* y, double* stats, int F, int H, int W, int C,
+                             int k, int stride, lr_stream_t stream) {
+    return dwconv_fwd_impl<float>(x, w, y, stats, F, H, W, C, k, stride, stream);
+}
+extern "C" int lr_dwconv_fwd_h(const void* x, const float* w, void* y, double* stats, int F, int H, int W, int C,
+                               int k, int stride, lr_stream_t stream) {
+    return dwconv_fwd_impl<nn::bf16>(static_cast<const nn::bf16*>(x), w, static_cast<nn::bf16*>(y), stats, F, H, W, C, k, stride, stream);
+}
 
-extern "C" int lr_dwconv_dgrad(const float* dy, const float* w, float* dx, int F, int H, int W, int C, int k,
-                               int stride, lr_stream_t stream) {
+template <typename T>
+static int dwconv_dgrad_impl(const T* dy, const float* w, T* dx, int F, int H, int W, int C, int k,
+                             int stride, lr_stream_t stream) {
     using namespace dw;
     LR_DW_CHECK("lr_dwconv_dgrad");
     LR_CHECK_ARG(dy && w && dx, "lr_dwconv_dgrad: null pointer");
+    LR_CHECK_ARG(sizeof(T) == 4 || (C & 7) == 0, "lr_dwconv_dgrad: bf16 storage needs C %% 8 == 0");
     LR_CHECK_ALIGN(dy); LR_CHECK_ALIGN(dx);
-    if (dws::dispatch(1, dy, w, dx, nullptr, F, H, W, C, k, stride, stream)) {
+    if (dws::dispatch<T>(1, dy, w, dx, nullptr, F, H, W, C, k, stride, stream)) {
         lr::count_launch();
         LR_CHECK_LAUNCH("dws::dgrad_kernel");
         return LR_OK;
@@ -466,7 +492,7 @@ extern "C" int lr_dwconv_dgrad(const float* dy, const float* w, float* dx, int F
     const int ws = pick_ws(W, stride == 2);
     const Geo d = make_geo(F, H, W, C, k, stride, 2, ws);
     LR_CHECK_ARG(d.rows_t * d.cols_t <= MAX_PIX, "lr_dwconv: image row of %d pixels is too wide for the staged tile", W);
-    const size_t smem = smem_bytes(d, 2, ws);
+    const size_t smem = smem_bytes(d, 2, ws, (int)sizeof(T));
     const dim3 grid = persistent_grid(d, 4);
     cudaError_t err = cudaSuccess;
     if (k == 3 && stride == 1) { DW_DISPATCH_WS(dgrad_kernel, 3, 1, d, dy, w, dx) }
@@ -478,14 +504,24 @@ extern "C" int lr_dwconv_dgrad(const float* dy, const float* w, float* dx, int F
     LR_CHECK_LAUNCH("dw::dgrad_kernel");
     return LR_OK;
 }
-
-extern "C" int lr_dwconv_wgrad(const float* dy, const float* x, float* dwt, int F, int H, int W, int C, int k,
+extern "C" int lr_dwconv_dgrad(const float* dy, const float* w, float* dx, int F, int H, int W, int C, int k,
                                int stride, lr_stream_t stream) {
+    return dwconv_dgrad_impl<float>(dy, w, dx, F, H, W, C, k, stride, stream);
+}
+extern "C" int lr_dwconv_dgrad_h(const void* dy, const float* w, void* dx, int F, int H, int W, int C, int k,
+                                 int stride, lr_stream_t stream) {
+    return dwconv_dgrad_impl<nn::bf16>(static_cast<const nn::bf16*>(dy), w, static_cast<nn::bf16*>(dx), F, H, W, C, k, stride, stream);
+}
+
+template <typename T>
+static int dwconv_wgrad_impl(const T* dy, const T* x, float* dwt, int F, int H, int W, int C, int k,
+                             int stride, lr_stream_t stream) {
     using namespace dw;
     LR_DW_CHECK("lr_dwconv_wgrad");
     LR_CHECK_ARG(dy && x && dwt, "lr_dwconv_wgrad: null pointer");
+    LR_CHECK_ARG(sizeof(T) == 4 || (C & 7) == 0, "lr_dwconv_wgrad: bf16 storage needs C %% 8 == 0");
     LR_CHECK_ALIGN(dy); LR_CHECK_ALIGN(x);
-    if (dws::dispatch(2, dy, x, dwt, nullptr, F, H, W, C, k, stride, stream)) {
+    if (dws::dispatch<T>(2, dy, x, dwt, nullptr, F, H, W, C, k, stride, stream)) {
         lr::count_launch();
         LR_CHECK_LAUNCH("dws::wgrad_kernel");
         return LR_OK;
@@ -494,7 +530,7 @@ extern "C" int lr_dwconv_wgrad(const float* dy, const float* x, float* dwt, int 
     const int ws = pick_ws(Wo, false);
     const Geo d = make_geo(F, H, W, C, k, stride, 1, ws);
     LR_CHECK_ARG(d.rows_t * d.cols_t <= MAX_PIX, "lr_dwconv: image row of %d pixels is too wide for the staged tile", W);
-    const size_t smem = smem_bytes(d, 1, ws);
+    const size_t smem = smem_bytes(d, 1, ws, (int)sizeof(T));
     const dim3 grid = persistent_grid(d, 4);
     cudaError_t err = cudaSuccess;
     if (k == 3 && stride == 1) { DW_DISPATCH_WS(wgrad_kernel, 3, 1, d, dy, x, dwt) }
@@ -505,4 +541,12 @@ extern "C" int lr_dwconv_wgrad(const float* dy, const float* x, float* dwt, int 
     lr::count_launch();
     LR_CHECK_LAUNCH("dw::wgrad_kernel");
     return LR_OK;
+}
+extern "C" int lr_dwconv_wgrad(const float* dy, const float* x, float* dwt, int F, int H, int W, int C, int k,
+                               int stride, lr_stream_t stream) {
+    return dwconv_wgrad_impl<float>(dy, x, dwt, F, H, W, C, k, stride, stream);
+}
+extern "C" int lr_dwconv_wgrad_h(const void* dy, const void* x, float* dwt, int F, int H, int W, int C, int k,
+                                 int stride, lr_stream_t stream) {
+    return dwconv_wgrad_impl<nn::bf16>(static_cast<const nn::bf16*>(dy), static_cast<const nn::bf16*>(x), dwt, F, H, W, C, k, stride, stream);
 }

@@ -15,9 +15,9 @@ struct G {
     static constexpr int P = K / 2, Ho = (H + 2 * P - K) / S + 1;
 };
 
-template <int H, int K, int S>
+template <typename T, int H, int K, int S>
 __global__ void __launch_bounds__(TH)
-fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, double* __restrict__ stats,
+fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, double* __restrict__ stats,
            int F, int C) {
     constexpr int P = G<H, K, S>::P, Ho = G<H, K, S>::Ho;
     __shared__ float ssum[FL][CW], ssq[FL][CW];
@@ -29,11 +29,11 @@ fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __re
     for (int t = 0; t < K * K; ++t) wr[t] = ok ? w[c * K * K + t] : 0.f;
     float ls = 0.f, lq = 0.f;
     for (int f = blockIdx.x * FL + fl; f < F && ok; f += gridDim.x * FL) {
-        const float* xf = x + (long long)f * H * H * C + c;
+        const T* xf = x + (long long)f * H * H * C + c;
         float xr[H * H];
 #pragma unroll
-        for (int i = 0; i < H * H; ++i) xr[i] = xf[(long long)i * C];
-        float* yf = y + (long long)f * Ho * Ho * C + c;
+        for (int i = 0; i < H * H; ++i) xr[i] = nn::ld1(xf + (long long)i * C);
+        T* yf = y + (long long)f * Ho * Ho * C + c;
 #pragma unroll
         for (int ho = 0; ho < Ho; ++ho)
 #pragma unroll
@@ -50,7 +50,8 @@ fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __re
                         acc = fmaf(xr[hi * H + wi], wr[kh * K + kw], acc);
                     }
                 }
-                yf[(long long)(ho * Ho + wo) * C] = acc;
+                nn::st1(yf + (long long)(ho * Ho + wo) * C, acc);
+                if (sizeof(T) == 2) acc = __bfloat162float(__float2bfloat16_rn(acc));   // statistics of the STORED value
                 ls += acc; lq = fmaf(acc, acc, lq);
             }
     }
@@ -67,9 +68,9 @@ fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __re
     }
 }
 
-template <int H, int K, int S>
+template <typename T, int H, int K, int S>
 __global__ void __launch_bounds__(TH)
-dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int F, int C) {
+dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx, int F, int C) {
     constexpr int P = G<H, K, S>::P, Ho = G<H, K, S>::Ho;
     const int cl = threadIdx.x % CW, fl = threadIdx.x / CW;
     const int c = blockIdx.y * CW + cl;
@@ -78,11 +79,11 @@ dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* _
 #pragma unroll
     for (int t = 0; t < K * K; ++t) wr[t] = w[c * K * K + t];
     for (int f = blockIdx.x * FL + fl; f < F; f += gridDim.x * FL) {
-        const float* gf = dy + (long long)f * Ho * Ho * C + c;
+        const T* gf = dy + (long long)f * Ho * Ho * C + c;
         float gr[Ho * Ho];
 #pragma unroll
-        for (int i = 0; i < Ho * Ho; ++i) gr[i] = gf[(long long)i * C];
-        float* xf = dx + (long long)f * H * H * C + c;
+        for (int i = 0; i < Ho * Ho; ++i) gr[i] = nn::ld1(gf + (long long)i * C);
+        T* xf = dx + (long long)f * H * H * C + c;
 #pragma unroll
         for (int hi = 0; hi < H; ++hi)
 #pragma unroll
@@ -99,14 +100,14 @@ dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* _
                         acc = fmaf(gr[ho * Ho + wo], wr[kh * K + kw], acc);
                     }
                 }
-                xf[(long long)(hi * H + wi) * C] = acc;
+                nn::st1(xf + (long long)(hi * H + wi) * C, acc);
             }
     }
 }
 
-template <int H, int K, int S>
+template <typename T, int H, int K, int S>
 __global__ void __launch_bounds__(TH)
-wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dwt, int F, int C) {
+wgrad_kernel(const T* __restrict__ dy, const T* __restrict__ x, float* __restrict__ dwt, int F, int C) {
     constexpr int P = G<H, K, S>::P, Ho = G<H, K, S>::Ho;
     __shared__ float red[FL][CW];
     const int cl = threadIdx.x % CW, fl = threadIdx.x / CW;
@@ -116,13 +117,13 @@ wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* _
 #pragma unroll
     for (int t = 0; t < K * K; ++t) acc[t] = 0.f;
     for (int f = blockIdx.x * FL + fl; f < F && ok; f += gridDim.x * FL) {
-        const float* xf = x + (long long)f * H * H * C + c;
-        const float* gf = dy + (long long)f * Ho * Ho * C + c;
+        const T* xf = x + (long long)f * H * H * C + c;
+        const T* gf = dy + (long long)f * Ho * Ho * C + c;
         float xr[H * H], gr[Ho * Ho];
 #pragma unroll
-        for (int i = 0; i < H * H; ++i) xr[i] = xf[(long long)i * C];
+        for (int i = 0; i < H * H; ++i) xr[i] = nn::ld1(xf + (long long)i * C);
 #pragma unroll
-        for (int i = 0; i < Ho * Ho; ++i) gr[i] = gf[(long long)i * C];
+        for (int i = 0; i < Ho * Ho; ++i) gr[i] = nn::ld1(gf + (long long)i * C);
 #pragma unroll
         for (int kh = 0; kh < K; ++kh)
 #pragma unroll
@@ -168,19 +169,21 @@ inline dim3 grid_for(int F, int C, int blocks_per_sm = 4) {
 }
 
 // mode 0 fwd (a = x, b = w, out = y, stats), 1 dgrad (a = dy, b = w, out = dx), 2 wgrad (a = dy, b = x, out = dw)
-template <int H, int K, int S>
-inline void launch(int mode, const float* a, const float* b, float* out, double* stats, int F, int C, cudaStream_t st) {
+// (the activation operands are T, the weights and the weight gradient are always fp32)
+template <typename T, int H, int K, int S>
+inline void launch(int mode, const void* a, const void* b, void* out, double* stats, int F, int C, cudaStream_t st) {
     const dim3 grid = grid_for(F, C, mode == 2 ? 1 : 4);
-    if (mode == 0) fwd_kernel<H, K, S><<<grid, TH, 0, st>>>(a, b, out, stats, F, C);
-    else if (mode == 1) dgrad_kernel<H, K, S><<<grid, TH, 0, st>>>(a, b, out, F, C);
-    else wgrad_kernel<H, K, S><<<grid, TH, 0, st>>>(a, b, out, F, C);
+    if (mode == 0) fwd_kernel<T, H, K, S><<<grid, TH, 0, st>>>(static_cast<const T*>(a), static_cast<const float*>(b), static_cast<T*>(out), stats, F, C);
+    else if (mode == 1) dgrad_kernel<T, H, K, S><<<grid, TH, 0, st>>>(static_cast<const T*>(a), static_cast<const float*>(b), static_cast<T*>(out), F, C);
+    else wgrad_kernel<T, H, K, S><<<grid, TH, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(b), static_cast<float*>(out), F, C);
 }
 
 // true if a specialised kernel exists (and was launched) for this geometry
-inline bool dispatch(int mode, const float* a, const float* b, float* out, double* stats, int F, int H, int W, int C, int k,
+template <typename T>
+inline bool dispatch(int mode, const void* a, const void* b, void* out, double* stats, int F, int H, int W, int C, int k,
                      int stride, cudaStream_t st) {
     if (H != W) return false;
-#define DWS_CASE(H_, K_, S_) if (H == H_ && k == K_ && stride == S_) { launch<H_, K_, S_>(mode, a, b, out, stats, F, C, st); return true; }
+#define DWS_CASE(H_, K_, S_) if (H == H_ && k == K_ && stride == S_) { launch<T, H_, K_, S_>(mode, a, b, out, stats, F, C, st); return true; }
     DWS_CASE(6, 5, 1) DWS_CASE(6, 5, 2) DWS_CASE(3, 5, 1) DWS_CASE(3, 5, 2) DWS_CASE(2, 5, 1) DWS_CASE(6, 3, 1)
 #undef DWS_CASE
     return false;

@@ -1,5 +1,9 @@
-// Tensor-core GEMM for the trunk's 1x1 convolutions (sm_100a: TMA -> shared memory -> tcgen05.mma kind::tf32
-// -> TMEM accumulator -> tcgen05.ld epilogue).
+// Tensor-core GEMM for the trunk's 1x1 convolutions (sm_100a: TMA -> shared memory -> tcgen05.mma kind::tf32 /
+// kind::f16 -> TMEM accumulator -> tcgen05.ld epilogue).  Two operand types share the kernel: fp32 storage with TF32
+// products (lr_gemm_tf32) and bf16 storage with bf16 products (lr_gemm_bf16, precision "bf16": activations, their
+// gradients and a bf16 shadow of the weights live in HBM as bfloat16; the accumulator is fp32 in both cases and the
+// result leaves as fp32 or bf16).  A 128-byte swizzled smem row holds 32 floats or 64 bf16, so a pipeline stage is
+// the same 16 KB + B tile in both modes and covers twice the reduce-depth in bf16.
 //
 //   C[M,N] (ldc) = epilogue( A[M,K] (lda, K-major) . B[N,K]^T (ldb, K-major) )        fp32 in HBM, TF32 products,
 //                                                                                     fp32 accumulation in TMEM
@@ -24,8 +28,10 @@
 
 namespace tc {
 
-constexpr int BM = 128, BK = 32, MAX_STAGES = 4, THREADS = 192;
-constexpr int A_STAGE_BYTES = BM * BK * 4;     // 16 KB
+constexpr int BM = 128, MAX_STAGES = 4, THREADS = 192;
+constexpr int A_STAGE_BYTES = BM * 128;        // 16 KB: 128 rows of one 128-byte swizzle span
+// per operand type: elements per 128-byte span = reduce-elements per stage (K-major) = MN-elements per chunk (MN-major)
+template <typename TO> struct Op { static constexpr int BK = 128 / (int)sizeof(TO); };
 constexpr int EPI_PW = 64, EPI_PITCH = EPI_PW + 4;                    // epilogue panel width / slab pitch (floats)
 constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;                    // four 32-row slabs
 
@@ -35,8 +41,8 @@ struct P {
     int atomic_out;      // 1: C += tile with red.global.add (split-K wgrad); bias / act / residual / stats unused
     int tma_out;         // 1: tiles leave through TMA (store, or reduce-add when accum_out) from swizzled 32x32 boxes
     int accum_out;       // tma_out only: C += tile (split-K, or an accumulating call whose R aliases C)
-    float* C; long long ldc;
-    const float* bias; const float* R; long long ldr;
+    void* C; long long ldc;          // fp32 or bf16 (the kernel's TC)
+    const float* bias; const void* R; long long ldr;
     double* stats;
     int act;
 #ifdef LR_TRACE
@@ -119,6 +125,24 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
            (1ull << 46) | (1ull << 61);
 }
+// MN-major 16-bit operand: the plain 128-byte swizzle (layout type 2; CUTLASS Layout_MN_SW128_Atom<bf16>, TMA
+// CU_TENSOR_MAP_SWIZZLE_128B): chunks of 64 MN-contiguous elements; inside a chunk the 64 reduce-rows of a stage sit
+// at a 128 B pitch, the swizzle atom is 8 rows (SBO = 1024 B between 8-row groups), chunks are 8192 B apart (= LBO).
+__device__ __forceinline__ uint64_t make_desc_mn_sw128_b16(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor, kind::f16 with bf16 operands: D = F32, A = B = BF16 (format 1)
+__device__ __forceinline__ uint32_t make_idesc_bf16(int bn, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
+           ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 // instruction descriptor, kind::tf32: D = F32, A = B = TF32, M = 128, N = bn; bit 15 / 16: A / B is MN-major
 __device__ __forceinline__ uint32_t make_idesc_tf32(int bn, bool a_mn, bool b_mn) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
@@ -145,10 +169,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <bool A_MN, bool B_MN>
+template <typename TO, typename TC, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const P p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const P p) {
+    constexpr int BK = Op<TO>::BK;                         // 32 (tf32) / 64 (bf16): also the MN-chunk width
+    constexpr bool H = sizeof(TO) == 2;
+    constexpr uint32_t CHUNK_BYTES = (uint32_t)BK * 128u;  // one MN-major chunk: BK reduce-rows of 128 bytes
+    static_assert(sizeof(TC) == 4 || sizeof(TC) == 2, "output is fp32 or bf16");
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 1];
     __shared__ uint32_t tmem_base_slot;
@@ -159,14 +187,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int kbeg = blockIdx.z * p.kchunk;
     const int kend = min(p.K, kbeg + p.kchunk);
     const int num_kb = (kend - kbeg + BK - 1) / BK;
-    const int b_chunks = (p.BN + 31) / 32;
-    const uint32_t b_stage_bytes = B_MN ? (uint32_t)b_chunks * 4096u : (uint32_t)p.BN * BK * 4;
+    const int b_chunks = (p.BN + BK - 1) / BK;
+    const uint32_t b_stage_bytes = B_MN ? (uint32_t)b_chunks * CHUNK_BYTES : (uint32_t)p.BN * 128u;
     const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
     const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;        // 1024 B alignment for SWIZZLE_128B
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[MAX_STAGES]);
     const uint32_t tmem_full = smem_u32(&bars[2 * MAX_STAGES]);
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)((p.BN + 31) & ~31)) tmem_cols <<= 1;     // the epilogue reads 32 columns at a time
+    // the epilogue reads 32 columns at a time (fp32 out) or two such loads per 64-column box (bf16 out)
+    while (tmem_cols < (uint32_t)(sizeof(TC) == 2 ? ((p.BN + 63) & ~63) : ((p.BN + 31) & ~31))) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) LR_STAMP(0);
     for (int i = threadIdx.x; i < 256; i += THREADS) {
@@ -202,12 +231,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int k0 = kbeg + kb * BK;
                 if (A_MN) {
 #pragma unroll
-                    for (int c = 0; c < BM / 32; ++c) tma_load_2d(a_dst + c * 4096, &tmA, full0 + 8 * s, m0 + c * 32, k0);
+                    for (int c = 0; c < BM / BK; ++c) tma_load_2d(a_dst + c * CHUNK_BYTES, &tmA, full0 + 8 * s, m0 + c * BK, k0);
                 } else {
                     tma_load_2d(a_dst, &tmA, full0 + 8 * s, k0, m0);
                 }
                 if (B_MN) {
-                    for (int c = 0; c < b_chunks; ++c) tma_load_2d(b_dst + c * 4096, &tmB, full0 + 8 * s, n0 + c * 32, k0);
+                    for (int c = 0; c < b_chunks; ++c) tma_load_2d(b_dst + c * CHUNK_BYTES, &tmB, full0 + 8 * s, n0 + c * BK, k0);
                 } else {
                     tma_load_2d(b_dst, &tmB, full0 + 8 * s, k0, n0);
                 }
@@ -215,7 +244,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(p.BN, A_MN, B_MN);
+            const uint32_t idesc = H ? make_idesc_bf16(p.BN, A_MN, B_MN) : make_idesc_tf32(p.BN, A_MN, B_MN);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % p.stages;
                 const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
@@ -223,14 +252,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (kb < 6) LR_STAMP(8 + kb);
                 fence_after();
                 const uint32_t a_src = tiles + s * stage_bytes, b_src = a_src + A_STAGE_BYTES;
-                const uint64_t adesc = A_MN ? make_desc_mn_sw128(a_src) : make_desc_k_sw128(a_src);
-                const uint64_t bdesc = B_MN ? make_desc_mn_sw128(b_src) : make_desc_k_sw128(b_src);
-                // one MMA consumes 8 reduce-elements: K-major: 32 bytes along the swizzled row (2 address units);
-                // MN-major: one 8-row group = 1024 bytes (64 address units)
+                const uint64_t adesc = A_MN ? (H ? make_desc_mn_sw128_b16(a_src) : make_desc_mn_sw128(a_src)) : make_desc_k_sw128(a_src);
+                const uint64_t bdesc = B_MN ? (H ? make_desc_mn_sw128_b16(b_src) : make_desc_mn_sw128(b_src)) : make_desc_k_sw128(b_src);
+                // one MMA consumes 32 bytes of reduce-depth (8 tf32 / 16 bf16 elements): K-major: 32 bytes along the
+                // swizzled row (2 address units); MN-major: 8 / 16 reduce-rows of 128 bytes (64 / 128 address units)
+                constexpr int MN_STEP = H ? 128 : 64;
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k)
-                    mma_tf32(tmem_d, adesc + (A_MN ? 64 : 2) * k, bdesc + (B_MN ? 64 : 2) * k, idesc,
-                             (kb > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                    if (H) mma_bf16(tmem_d, adesc + (A_MN ? MN_STEP : 2) * k, bdesc + (B_MN ? MN_STEP : 2) * k, idesc,
+                                    (kb > 0 || k > 0) ? 1u : 0u);
+                    else mma_tf32(tmem_d, adesc + (A_MN ? MN_STEP : 2) * k, bdesc + (B_MN ? MN_STEP : 2) * k, idesc,
+                                  (kb > 0 || k > 0) ? 1u : 0u);
+                }
                 mma_commit(empty0 + 8 * s);
             }
             mma_commit(tmem_full);
@@ -250,8 +283,92 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(tmem_full, 0);
         if (threadIdx.x == 64) LR_STAMP(15);
         fence_after();
+        float* const Cf = static_cast<float*>(p.C);                          // used by the fp32-output paths only
+        const float* const Rf = static_cast<const float*>(p.R);
         const bool vec_c = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         const bool vec_r = p.R && ((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
+        if constexpr (sizeof(TC) == 2) {
+            // ---- bf16 output: 32 rows x 64 columns per box (again one 128-byte swizzled row per tile row).  A lane
+            // owns its row: two 32-column TMEM loads -> bias / activation (+ residual, read straight from HBM: the
+            // lane's 64 bf16 are one contiguous 128-byte line) -> round to bf16 -> eight 16-byte chunks at chunk
+            // position j ^ (row & 7) -> TMA store (clips rows >= M, columns >= N).  Train-mode BatchNorm statistics are
+            // taken from the ROUNDED values (what the consumer will normalise): lane L sums columns 2L, 2L+1 down the
+            // 32 rows, one conflict-free 4-byte read per row.
+            const nn::bf16* const Rh = static_cast<const nn::bf16*>(p.R);
+            const uint32_t stg0 = tiles + (uint32_t)q * 8192u;
+            uint8_t* stg0_g = smem_raw + (stg0 - smem_u32(smem_raw));
+            int nbox = 0;
+            const int plain_out = (p.bias == nullptr && p.act == LR_ACT_NONE) ? 1 : 0;
+            for (int c0 = 0; c0 < p.BN; c0 += 64, ++nbox) {
+                const int n = n0 + c0;
+                if (n >= p.N) break;                                         // warp-uniform
+                const uint32_t buf = (uint32_t)(nbox & 1) * 4096u;
+                if (nbox >= 2) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }
+                uint8_t* rowp = stg0_g + buf + lane * 128;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v[32];
+                    tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 32 * h), v);
+                    if (plain_out == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bq = *reinterpret_cast<const float4*>(&s_bias[c0 + 32 * h + j]);
+                            v[j] += bq.x; v[j + 1] += bq.y; v[j + 2] += bq.z; v[j + 3] += bq.w;
+                        }
+                        switch (p.act) {
+                            case LR_ACT_RELU:
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                                break;
+                            case LR_ACT_NONE: break;
+                            default:
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) v[j] = nn::act_fwd(v[j], p.act);
+                        }
+                    }
+                    if (Rh && lane < rv) {
+                        const nn::bf16* rrow = Rh + (long long)(row0 + lane) * p.ldr + n + 32 * h;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (n + 32 * h + 8 * j < p.N) {                  // N % 8 == 0: a chunk is wholly in or out
+                                const uint4 u = *reinterpret_cast<const uint4*>(rrow + 8 * j);
+                                const float4 a = nn::unpack4(make_uint2(u.x, u.y)), b = nn::unpack4(make_uint2(u.z, u.w));
+                                v[8 * j] += a.x; v[8 * j + 1] += a.y; v[8 * j + 2] += a.z; v[8 * j + 3] += a.w;
+                                v[8 * j + 4] += b.x; v[8 * j + 5] += b.y; v[8 * j + 6] += b.z; v[8 * j + 7] += b.w;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint2 lo = nn::pack4(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]));
+                        const uint2 hi = nn::pack4(make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
+                        *reinterpret_cast<uint4*>(rowp + (((4 * h + j) ^ (lane & 7)) << 4)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0 && num_kb > 0) {
+                    tma_store_2d(&tmC, stg0 + buf, n, row0);
+                    bulk_commit();
+                }
+                if (p.stats) {
+                    // lane L: columns 2L, 2L+1 = 4-byte word (L & 3) of 16-byte chunk (L >> 2)
+                    const uint8_t* colp = stg0_g + buf + (lane & 3) * 4;
+                    float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+                    for (int r = 0; r < rv; ++r) {
+                        const unsigned w = *reinterpret_cast<const unsigned*>(colp + r * 128 + (((lane >> 2) ^ (r & 7)) << 4));
+                        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+                        a0 += x.x; b0 = fmaf(x.x, x.x, b0); a1 += x.y; b1 = fmaf(x.y, x.y, b1);
+                    }
+                    if (n + 2 * lane < p.N) {                                // N even
+                        s_sum[q][c0 + 2 * lane] = a0; s_sq[q][c0 + 2 * lane] = b0;
+                        s_sum[q][c0 + 2 * lane + 1] = a1; s_sq[q][c0 + 2 * lane + 1] = b1;
+                    }
+                }
+            }
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+        } else
         if (p.tma_out) {
             // ---- TMA epilogue: 32 rows x 32 columns at a time through a 128-byte-swizzled box (row r, 16-byte chunk
             // c stored at chunk c ^ (r & 7): the row-per-lane writes and the column-per-lane statistic reads are both
@@ -359,10 +476,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int idx = lane; idx < total; idx += 32) {
                         const int r = idx / nv, c4 = (idx - r * nv) * 4;
                         float4 x = *reinterpret_cast<const float4*>(slab + r * EPI_PITCH + c4);
-                        float* cp = p.C + (long long)(row0 + r) * p.ldc + nbase + c4;
+                        float* cp = Cf + (long long)(row0 + r) * p.ldc + nbase + c4;
                         if (p.atomic_out) { atomicAdd(reinterpret_cast<float4*>(cp), x); continue; }
                         if (p.R) {
-                            const float4 t = nn::ld4(p.R + (long long)(row0 + r) * p.ldr + nbase + c4);
+                            const float4 t = nn::ld4(Rf + (long long)(row0 + r) * p.ldr + nbase + c4);
                             x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
                             if (p.stats) *reinterpret_cast<float4*>(slab + r * EPI_PITCH + c4) = x;
                         }
@@ -373,10 +490,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int idx = lane; idx < total; idx += 32) {
                         const int r = idx / pwv, c = idx - r * pwv;
                         float x = slab[r * EPI_PITCH + c];
-                        float* cp = p.C + (long long)(row0 + r) * p.ldc + nbase + c;
+                        float* cp = Cf + (long long)(row0 + r) * p.ldc + nbase + c;
                         if (p.atomic_out) { atomicAdd(cp, x); continue; }
                         if (p.R) {
-                            x += p.R[(long long)(row0 + r) * p.ldr + nbase + c];
+                            x += Rf[(long long)(row0 + r) * p.ldr + nbase + c];
                             if (p.stats) slab[r * EPI_PITCH + c] = x;
                         }
                         *cp = x;
@@ -438,20 +555,94 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// row-major fp32 matrix [rows][cols] (ld floats) -> tensor map with a {32 floats, box_rows} box, 128 B swizzle
-static int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows,
-                    bool mn_major = false) {
+// row-major matrix [rows][cols] (ld elements, fp32 or bf16) -> tensor map with a {box_cols, box_rows} box whose
+// inner extent is one 128-byte span, 128 B swizzle (the 32-byte-atom flavour for MN-major fp32 operands)
+static int make_map(CUtensorMap* map, const void* base, bool is_bf16, long long rows, long long cols, long long ld,
+                    int box_cols, int box_rows, bool atom32 = false) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return lr::fail(LR_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const size_t es = is_bf16 ? 2 : 4;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return lr::fail(LR_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return LR_OK;
+}
+
+template <typename TO, typename TC>
+static int launch(const void* A, long long lda, int a_trans, const void* B, long long ldb, int b_trans, void* C,
+                  long long ldc, int M, int N, int K, const float* bias, int act, const void* R, long long ldr,
+                  double* stats, int ksplit, lr_stream_t stream, const char* name) {
+    constexpr bool H = sizeof(TO) == 2, HC = sizeof(TC) == 2;
+    constexpr int BK = Op<TO>::BK;
+    const int ntile = (N + 255) / 256;
+    int bn = (N + ntile - 1) / ntile;
+    bn = (bn + 15) / 16 * 16;
+    if (ntile > 1) bn = HC ? (bn + 63) / 64 * 64 : (bn + 31) / 32 * 32;   // output boxes must not straddle two CTAs' tiles
+    P p;
+    p.M = M; p.N = N; p.K = K; p.BN = bn; p.C = C; p.ldc = ldc; p.bias = bias; p.R = R; p.ldr = ldr; p.stats = stats; p.act = act;
+    int kchunk = (K + ksplit - 1) / ksplit;
+    kchunk = (kchunk + BK - 1) / BK * BK;
+    const int nz = (K + kchunk - 1) / kchunk;
+    p.kchunk = kchunk;
+    p.atomic_out = ksplit > 1 ? 1 : 0;
+#ifdef LR_TRACE
+    extern long long* g_lr_trace;
+    p.trace = g_lr_trace;
+#endif
+    const int num_kb = kchunk / BK;
+    p.stages = num_kb < MAX_STAGES ? num_kb : MAX_STAGES;
+    // Output path: TMA store / reduce-add whenever C is TMA-addressable (16-byte aligned rows) and the residual
+    // is absent or IS C (then the call accumulates: reduce-add); otherwise the shared-memory slab path (fp32 out only).
+    const bool c_tma_ok = ((ldc * (long long)sizeof(TC)) & 15) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+    const bool r_is_c = R == C && ldr == ldc;
+    if (HC) {
+        if (!c_tma_ok) return lr::fail(LR_EALIGN, "%s: a bf16 result needs 16-byte aligned rows (ldc %% 8 == 0)", name);
+        if (R && (((ldr * 2) & 15) != 0 || (reinterpret_cast<uintptr_t>(R) & 15) != 0 || (N & 7) != 0))
+            return lr::fail(LR_EALIGN, "%s: a bf16 residual needs 16-byte aligned rows and N %% 8 == 0", name);
+        if (ksplit > 1) return lr::fail(LR_EINVAL, "%s: split-K accumulates in fp32 (use an fp32 result)", name);
+        p.tma_out = 1; p.accum_out = 0;
+    } else {
+        p.tma_out = (c_tma_ok && (R == nullptr || (r_is_c && !stats && act == LR_ACT_NONE && !bias))) ? 1 : 0;
+        p.accum_out = (p.atomic_out || (R != nullptr && r_is_c)) ? 1 : 0;
+    }
+    CUtensorMap ma, mb, mc;
+    if (p.tma_out) {
+        int rcc = make_map(&mc, C, HC, M, N, ldc, HC ? 64 : 32, 32);
+        if (rcc) return rcc;
+    } else {
+        memset(&mc, 0, sizeof(mc));
+    }
+    int rc = a_trans ? make_map(&ma, A, H, K, M, lda, BK, BK, !H) : make_map(&ma, A, H, M, K, lda, BK, BM);
+    if (rc) return rc;
+    rc = b_trans ? make_map(&mb, B, H, K, N, ldb, BK, BK, !H) : make_map(&mb, B, H, N, K, ldb, BK, bn);
+    if (rc) return rc;
+    const size_t b_stage = b_trans ? (size_t)((bn + BK - 1) / BK) * (size_t)BK * 128 : (size_t)bn * 128;
+    size_t smem = (size_t)p.stages * (A_STAGE_BYTES + b_stage);
+    if (smem < (size_t)EPI_BYTES) smem = EPI_BYTES;           // the epilogue slabs reuse the pipeline buffers
+    smem += 1024;
+    {
+        cudaError_t e = lr::ensure_max_dynamic_smem(gemm_tc_kernel<TO, TC, false, false>, 200 * 1024);
+        if (e == cudaSuccess) e = lr::ensure_max_dynamic_smem(gemm_tc_kernel<TO, TC, false, true>, 200 * 1024);
+        if (e == cudaSuccess) e = lr::ensure_max_dynamic_smem(gemm_tc_kernel<TO, TC, true, true>, 200 * 1024);
+        if (e == cudaSuccess) e = lr::ensure_max_dynamic_smem(gemm_tc_kernel<TO, TC, true, false>, 200 * 1024);
+        if (e != cudaSuccess) return lr::fail(LR_ECUDA, "%s smem: %s", name, cudaGetErrorString(e));
+    }
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + bn - 1) / bn), (unsigned)nz);
+    if (a_trans) {
+        if (b_trans) gemm_tc_kernel<TO, TC, true, true><<<grid, THREADS, smem, stream>>>(ma, mb, mc, p);
+        else gemm_tc_kernel<TO, TC, true, false><<<grid, THREADS, smem, stream>>>(ma, mb, mc, p);
+    } else {
+        if (b_trans) gemm_tc_kernel<TO, TC, false, true><<<grid, THREADS, smem, stream>>>(ma, mb, mc, p);
+        else gemm_tc_kernel<TO, TC, false, false><<<grid, THREADS, smem, stream>>>(ma, mb, mc, p);
+    }
+    lr::count_launch();
+    LR_CHECK_LAUNCH("gemm_tc_kernel");
     return LR_OK;
 }
 
@@ -469,60 +660,25 @@ extern "C" int lr_gemm_tf32(const float* A, long long lda, int a_trans, const fl
     LR_CHECK_ARG(ksplit == 1 || (act == LR_ACT_NONE && !R && !stats && !bias),
                  "lr_gemm_tf32: split-K accumulates atomically and cannot fuse bias / act / residual / stats");
     LR_CHECK_ALIGN(A); LR_CHECK_ALIGN(B);
-    const int ntile = (N + 255) / 256;
-    int bn = (N + ntile - 1) / ntile;
-    bn = (bn + 15) / 16 * 16;
-    if (ntile > 1) bn = (bn + 31) / 32 * 32;      // 32-column output boxes must not straddle two CTAs' tiles
-    tc::P p;
-    p.M = M; p.N = N; p.K = K; p.BN = bn; p.C = C; p.ldc = ldc; p.bias = bias; p.R = R; p.ldr = ldr; p.stats = stats; p.act = act;
-    int kchunk = (K + ksplit - 1) / ksplit;
-    kchunk = (kchunk + tc::BK - 1) / tc::BK * tc::BK;
-    const int nz = (K + kchunk - 1) / kchunk;
-    p.kchunk = kchunk;
-    p.atomic_out = ksplit > 1 ? 1 : 0;
-#ifdef LR_TRACE
-    extern long long* g_lr_trace;
-    p.trace = g_lr_trace;
-#endif
-    const int num_kb = kchunk / tc::BK;
-    p.stages = num_kb < tc::MAX_STAGES ? num_kb : tc::MAX_STAGES;
-    // Output path: TMA store / reduce-add whenever C is TMA-addressable (16-byte aligned rows) and the residual
-    // is absent or IS C (then the call accumulates: reduce-add); otherwise the shared-memory slab path.
-    const bool c_tma_ok = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
-    const bool r_is_c = R == C && ldr == ldc;
-    p.tma_out = (c_tma_ok && (R == nullptr || (r_is_c && !stats && act == LR_ACT_NONE && !bias))) ? 1 : 0;
-    p.accum_out = (p.atomic_out || (R != nullptr && r_is_c)) ? 1 : 0;
-    CUtensorMap ma, mb, mc;
-    if (p.tma_out) {
-        int rcc = tc::make_map(&mc, C, M, N, ldc, 32);
-        if (rcc) return rcc;
-    } else {
-        memset(&mc, 0, sizeof(mc));
-    }
-    int rc = a_trans ? tc::make_map(&ma, A, K, M, lda, 32, true) : tc::make_map(&ma, A, M, K, lda, tc::BM);
-    if (rc) return rc;
-    rc = b_trans ? tc::make_map(&mb, B, K, N, ldb, 32, true) : tc::make_map(&mb, B, N, K, ldb, bn);
-    if (rc) return rc;
-    const size_t b_stage = b_trans ? (size_t)((bn + 31) / 32) * 4096 : (size_t)bn * tc::BK * 4;
-    size_t smem = (size_t)p.stages * (tc::A_STAGE_BYTES + b_stage);
-    if (smem < (size_t)tc::EPI_BYTES) smem = tc::EPI_BYTES;           // the epilogue slabs reuse the pipeline buffers
-    smem += 1024;
-    {
-        cudaError_t e = lr::ensure_max_dynamic_smem(tc::gemm_tf32_kernel<false, false>, 200 * 1024);
-        if (e == cudaSuccess) e = lr::ensure_max_dynamic_smem(tc::gemm_tf32_kernel<false, true>, 200 * 1024);
-        if (e == cudaSuccess) e = lr::ensure_max_dynamic_smem(tc::gemm_tf32_kernel<true, true>, 200 * 1024);
-        if (e == cudaSuccess) e = lr::ensure_max_dynamic_smem(tc::gemm_tf32_kernel<true, false>, 200 * 1024);
-        if (e != cudaSuccess) return lr::fail(LR_ECUDA, "lr_gemm_tf32 smem: %s", cudaGetErrorString(e));
-    }
-    dim3 grid((unsigned)((M + tc::BM - 1) / tc::BM), (unsigned)((N + bn - 1) / bn), (unsigned)nz);
-    if (a_trans) {
-        if (b_trans) tc::gemm_tf32_kernel<true, true><<<grid, tc::THREADS, smem, stream>>>(ma, mb, mc, p);
-        else tc::gemm_tf32_kernel<true, false><<<grid, tc::THREADS, smem, stream>>>(ma, mb, mc, p);
-    } else {
-        if (b_trans) tc::gemm_tf32_kernel<false, true><<<grid, tc::THREADS, smem, stream>>>(ma, mb, mc, p);
-        else tc::gemm_tf32_kernel<false, false><<<grid, tc::THREADS, smem, stream>>>(ma, mb, mc, p);
-    }
-    lr::count_launch();
-    LR_CHECK_LAUNCH("gemm_tf32_kernel");
-    return LR_OK;
+    return tc::launch<float, float>(A, lda, a_trans, B, ldb, b_trans, C, ldc, M, N, K, bias, act, R, ldr, stats, ksplit,
+                                    stream, "lr_gemm_tf32");
+}
+
+extern "C" int lr_gemm_bf16(const void* A, long long lda, int a_trans, const void* B, long long ldb, int b_trans,
+                            void* C, long long ldc, int c_bf16, int M, int N, int K, const float* bias, int act,
+                            const void* R, long long ldr, double* stats, int ksplit, lr_stream_t stream) {
+    LR_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "lr_gemm_bf16: bad dimension");
+    if (M == 0 || N == 0) return LR_OK;
+    LR_CHECK_ARG(A && B && C, "lr_gemm_bf16: null pointer");
+    LR_CHECK_ARG(act >= LR_ACT_NONE && act <= LR_ACT_RELU6, "lr_gemm_bf16: bad activation %d", act);
+    LR_CHECK_ARG((lda & 7) == 0 && (ldb & 7) == 0, "lr_gemm_bf16: lda / ldb must be multiples of 8 bf16 (TMA 16-byte stride)");
+    LR_CHECK_ARG(ksplit >= 1, "lr_gemm_bf16: ksplit must be >= 1");
+    LR_CHECK_ARG(ksplit == 1 || (act == LR_ACT_NONE && !R && !stats && !bias),
+                 "lr_gemm_bf16: split-K accumulates atomically and cannot fuse bias / act / residual / stats");
+    LR_CHECK_ALIGN(A); LR_CHECK_ALIGN(B);
+    if (c_bf16)
+        return tc::launch<nn::bf16, nn::bf16>(A, lda, a_trans, B, ldb, b_trans, C, ldc, M, N, K, bias, act, R, ldr, stats,
+                                              ksplit, stream, "lr_gemm_bf16");
+    return tc::launch<nn::bf16, float>(A, lda, a_trans, B, ldb, b_trans, C, ldc, M, N, K, bias, act, R, ldr, stats, ksplit,
+                                       stream, "lr_gemm_bf16");
 }

@@ -1,6 +1,8 @@
 // Device helpers shared by the trunk / head kernels: activations, vector access, and the
 // "fixed channel group per thread" mapping used by every [rows, C] channels-last kernel.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace nn {
@@ -39,6 +41,28 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act) {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// ---- bf16 storage (precision "bf16": activations and their gradients live in HBM as bfloat16, all arithmetic stays
+// fp32 in registers).  The kernels are templates over the storage type T in {float, bf16}; these overloads are the
+// only place the type shows: 4 consecutive channels are one 8-byte access instead of one 16-byte access.
+typedef __nv_bfloat16 bf16;
+__device__ __forceinline__ float4 unpack4(uint2 u) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ uint2 pack4(float4 v) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const unsigned*>(&a); u.y = *reinterpret_cast<const unsigned*>(&b);
+    return u;
+}
+__device__ __forceinline__ float4 ld4(const bf16* p) { return unpack4(*reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ void st4(bf16* p, float4 v) { *reinterpret_cast<uint2*>(p) = pack4(v); }
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
+__device__ __forceinline__ float ld1(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
 // L2 residency hints for two-pass kernels: the first pass loads with evict_last so that the second pass (the next
 // kernel) finds the tensor in the 126 MB L2 instead of HBM; the second pass loads with evict_first.
 __device__ __forceinline__ unsigned long long l2_policy_evict_last() {
@@ -56,6 +80,11 @@ __device__ __forceinline__ float4 ld4_hint(const float* p, unsigned long long po
     asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
     return v;
+}
+__device__ __forceinline__ float4 ld4_hint(const bf16* p, unsigned long long pol) {
+    uint2 u;
+    asm volatile("ld.global.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(u.x), "=r"(u.y) : "l"(p), "l"(pol));
+    return unpack4(u);
 }
 
 // Channel-group mapping for a row-major [rows, C] tensor with C % 4 == 0: a thread owns ONE group of
