@@ -137,7 +137,7 @@ class VGGAudioPlan(ModelPlan):
     def build(self, m, spec):
         B, wb = self.B, self.with_backward
         mel = self.audio_input()
-        kind, fmap = self.cnn_sequential(list(m.vgg.features), _mel_frames(mel, B))
+        kind, fmap = self.cnn_sequential(list(m.vgg.features), _mel_frames(mel, B), h=False)      # flattened to fp32 below
         assert kind == "map"
         osz = m.adaptive_pool.output_size
         if (fmap.H, fmap.W) != tuple(osz):
@@ -185,7 +185,7 @@ class VGGLstmAudioPlan(ModelPlan):
     def build(self, m, spec):
         B, wb = self.B, self.with_backward
         mel = self.audio_input()
-        kind, fmap = self.cnn_sequential(list(m.vgg_features), _mel_frames(mel, B))
+        kind, fmap = self.cnn_sequential(list(m.vgg_features), _mel_frames(mel, B), h=False)      # viewed as fp32 rows below
         assert kind == "map"
         # AdaptiveAvgPool2d((None, 1)) + squeeze + permute: mean over W per (clip, row) -> a sequence of H steps of C
         # features; on the channels-last map that is a per-"frame" pooling with frames = (clip, row)

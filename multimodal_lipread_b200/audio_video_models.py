@@ -124,7 +124,9 @@ def audio_cnn_plan(plan, cnn, mel, B):
         raise ValueError("audio CNN plans handle dataset.audio_channels == 1 (the reference default)")
     # (B,80,117) contiguous == NHWC with C = 1
     frames = (mel, (0, B, 1, N_MELS, N_FRAMES_OUT, N_MELS * N_FRAMES_OUT, 0, 0, N_FRAMES_OUT, 1), 1.0)
-    return plan.cnn_sequential(mods, frames)
+    # the small audio encoders keep fp32 storage in every precision mode: their consumers (flatten to the fusion row,
+    # fp32 heads) read fp32, and 32 x 80 x 117 images are a sliver of the step's traffic
+    return plan.cnn_sequential(mods, frames, h=False)
 
 
 def audio_encoder_plan(plan, enc, mel, B, out, ldo, dout):

@@ -52,7 +52,7 @@ __device__ __forceinline__ Coef coef4(const Bn& b, int c) {
 }
 
 // z = act(x * scale + shift) (+ residual).  Block (0,0) also performs the running-statistics update.
-template <typename T>
+template <typename T, bool RES>
 __global__ void __launch_bounds__(TH, 4)
 bn_act_fwd_kernel(const Bn b, const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ z,
                   int rows_per_block, int res_pre, int gw) {
@@ -74,31 +74,36 @@ bn_act_fwd_kernel(const Bn b, const T* __restrict__ x, const T* __restrict__ res
     const Coef k = coef4(b, c);
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = min(b.rows, r0 + rows_per_block);
-    constexpr int U = 4;                       // independent rows in flight per thread (memory-level parallelism)
+    // independent rows in flight per thread (memory-level parallelism): the same BYTES in flight in both storage
+    // modes -- the raw vectors (float4 / 2 x bf16x2) stay in registers until used, so bf16 affords twice the rows
+    // (with a residual stream the rows in flight stay at 4: RES is a template flag so that its array vanishes otherwise)
+    constexpr int U = (sizeof(T) == 2 && !RES) ? 8 : 4;
     const long long step = map.rpp;
     for (long long r = r0 + map.rlane; r < r1; r += U * step) {
-        float4 v[U], q[U];
+        typename nn::Raw4<T>::type vr[U], qr[RES ? U : 1];
 #pragma unroll
-        for (int u = 0; u < U; ++u) if (r + u * step < r1) v[u] = nn::ld4(x + (r + u * step) * b.C + c);
-        if (res) {
+        for (int u = 0; u < U; ++u) if (r + u * step < r1) vr[u] = nn::ldraw(x + (r + u * step) * b.C + c);
+        if (RES) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) if (r + u * step < r1) q[u] = nn::ld4(res + (r + u * step) * b.C + c);
+            for (int u = 0; u < U; ++u) if (r + u * step < r1) qr[u] = nn::ldraw(res + (r + u * step) * b.C + c);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (r + u * step >= r1) break;
+            const float4 v = nn::cvt4(vr[u]);
             float4 o;
-            if (res && res_pre) {               // ResNet BasicBlock: act(bn(x) + identity)
-                o.x = nn::act_fwd(fmaf(v[u].x, k.scale.x, k.shift.x) + q[u].x, b.act);
-                o.y = nn::act_fwd(fmaf(v[u].y, k.scale.y, k.shift.y) + q[u].y, b.act);
-                o.z = nn::act_fwd(fmaf(v[u].z, k.scale.z, k.shift.z) + q[u].z, b.act);
-                o.w = nn::act_fwd(fmaf(v[u].w, k.scale.w, k.shift.w) + q[u].w, b.act);
+            if (RES && res_pre) {               // ResNet BasicBlock: act(bn(x) + identity)
+                const float4 q = nn::cvt4(qr[u]);
+                o.x = nn::act_fwd(fmaf(v.x, k.scale.x, k.shift.x) + q.x, b.act);
+                o.y = nn::act_fwd(fmaf(v.y, k.scale.y, k.shift.y) + q.y, b.act);
+                o.z = nn::act_fwd(fmaf(v.z, k.scale.z, k.shift.z) + q.z, b.act);
+                o.w = nn::act_fwd(fmaf(v.w, k.scale.w, k.shift.w) + q.w, b.act);
             } else {
-                o.x = nn::act_fwd(fmaf(v[u].x, k.scale.x, k.shift.x), b.act);
-                o.y = nn::act_fwd(fmaf(v[u].y, k.scale.y, k.shift.y), b.act);
-                o.z = nn::act_fwd(fmaf(v[u].z, k.scale.z, k.shift.z), b.act);
-                o.w = nn::act_fwd(fmaf(v[u].w, k.scale.w, k.shift.w), b.act);
-                if (res) { o.x += q[u].x; o.y += q[u].y; o.z += q[u].z; o.w += q[u].w; }
+                o.x = nn::act_fwd(fmaf(v.x, k.scale.x, k.shift.x), b.act);
+                o.y = nn::act_fwd(fmaf(v.y, k.scale.y, k.shift.y), b.act);
+                o.z = nn::act_fwd(fmaf(v.z, k.scale.z, k.shift.z), b.act);
+                o.w = nn::act_fwd(fmaf(v.w, k.scale.w, k.shift.w), b.act);
+                if (RES) { const float4 q = nn::cvt4(qr[u]); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
             }
             nn::st4(z + (r + u * step) * b.C + c, o);
         }
@@ -114,7 +119,9 @@ __device__ __forceinline__ float4 mask_by_out(float4 g, const float4 z, int act)
 }
 
 // backward pass 1: dy = dz * act'(u), u = x*scale + shift;  sums[c] += dy, sums[C+c] += dy * xhat
-template <typename T>
+// ZO: the derivative goes through the saved OUTPUT zo (ResNet pre-activation residual blocks): a third stream, so the
+// rows in flight stay at 4 there; otherwise bf16 keeps 8 rows (the same bytes as fp32's 4) in flight.
+template <typename T, bool ZO>
 __global__ void __launch_bounds__(TH, 3)
 bn_act_bwd_reduce_kernel(const Bn b, const T* __restrict__ x, const T* __restrict__ dz,
                          const T* __restrict__ zo, double* __restrict__ sums, int rows_per_block, int gw) {
@@ -130,21 +137,23 @@ bn_act_bwd_reduce_kernel(const Bn b, const T* __restrict__ x, const T* __restric
         const long long r1 = min(b.rows, r0 + rows_per_block);
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
         const unsigned long long keep = nn::l2_policy_evict_last();     // the apply pass re-reads x and dz right away
-        constexpr int U = 4;
+        constexpr int U = (sizeof(T) == 2 && !ZO) ? 8 : 4;
         const long long step = map.rpp;
         for (long long r = r0 + map.rlane; r < r1; r += U * step) {
-            float4 vv[U], gg[U];
+            typename nn::Raw4<T>::type vv[U], gg[U], zz[ZO ? U : 1];
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (r + u * step < r1) {
-                    vv[u] = nn::ld4_hint(x + (r + u * step) * b.C + c, keep); gg[u] = nn::ld4_hint(dz + (r + u * step) * b.C + c, keep);
-                    if (zo) gg[u] = mask_by_out(gg[u], nn::ld4_hint(zo + (r + u * step) * b.C + c, keep), b.act);
+                    vv[u] = nn::ldraw_hint(x + (r + u * step) * b.C + c, keep); gg[u] = nn::ldraw_hint(dz + (r + u * step) * b.C + c, keep);
+                    if (ZO) zz[u] = nn::ldraw_hint(zo + (r + u * step) * b.C + c, keep);
                 }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (r + u * step >= r1) break;
-                const float4 v = vv[u], g = gg[u];
-                const int ga = zo ? LR_ACT_NONE : b.act;
+                const float4 v = nn::cvt4(vv[u]);
+                float4 g = nn::cvt4(gg[u]);
+                if (ZO) g = mask_by_out(g, nn::cvt4(zz[u]), b.act);
+                const int ga = ZO ? LR_ACT_NONE : b.act;
                 const float d0 = g.x * nn::act_grad(fmaf(v.x, k.scale.x, k.shift.x), ga);
                 const float d1 = g.y * nn::act_grad(fmaf(v.y, k.scale.y, k.shift.y), ga);
                 const float d2 = g.z * nn::act_grad(fmaf(v.z, k.scale.z, k.shift.z), ga);
@@ -170,7 +179,7 @@ bn_act_bwd_reduce_kernel(const Bn b, const T* __restrict__ x, const T* __restric
 // backward pass 2: dx = gamma*invstd * (dy - mean(dy) - xhat * mean(dy*xhat))   (training)
 //                  dx = gamma*invstd * dy                                        (eval)
 // block (0,0) writes dgamma += sum(dy*xhat), dbeta += sum(dy).
-template <typename T>
+template <typename T, bool ZO>
 __global__ void __launch_bounds__(TH, 3)
 bn_act_bwd_apply_kernel(const Bn b, const T* __restrict__ x, const T* __restrict__ dz,
                         const T* __restrict__ zo, T* __restrict__ dres,
@@ -204,25 +213,27 @@ bn_act_bwd_apply_kernel(const Bn b, const T* __restrict__ x, const T* __restrict
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const long long r1 = min(b.rows, r0 + rows_per_block);
     const unsigned long long drop = nn::l2_policy_evict_first();       // last use of x and dz
-    constexpr int U = 4;
+    constexpr int U = (sizeof(T) == 2 && !ZO) ? 8 : 4;
     const long long step = map.rpp;
     for (long long rb = r0 + map.rlane; rb < r1; rb += U * step) {
-      float4 vv[U], gg[U];
+      typename nn::Raw4<T>::type vv[U], gg[U], zz[ZO ? U : 1];
 #pragma unroll
       for (int u = 0; u < U; ++u)
           if (rb + u * step < r1) {
-              vv[u] = nn::ld4_hint(x + (rb + u * step) * b.C + c, drop); gg[u] = nn::ld4_hint(dz + (rb + u * step) * b.C + c, drop);
-              if (zo) {
-                  gg[u] = mask_by_out(gg[u], nn::ld4_hint(zo + (rb + u * step) * b.C + c, drop), b.act);
-                  if (dres) nn::st4(dres + (rb + u * step) * b.C + c, gg[u]);     // gradient of the identity branch
-              }
+              vv[u] = nn::ldraw_hint(x + (rb + u * step) * b.C + c, drop); gg[u] = nn::ldraw_hint(dz + (rb + u * step) * b.C + c, drop);
+              if (ZO) zz[u] = nn::ldraw_hint(zo + (rb + u * step) * b.C + c, drop);
           }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long r = rb + u * step;
         if (r >= r1) break;
-        const float4 v = vv[u], g = gg[u];
-        const int ga = zo ? LR_ACT_NONE : b.act;
+        const float4 v = nn::cvt4(vv[u]);
+        float4 g = nn::cvt4(gg[u]);
+        if (ZO) {
+            g = mask_by_out(g, nn::cvt4(zz[u]), b.act);
+            if (dres) nn::st4(dres + r * b.C + c, g);                         // gradient of the identity branch
+        }
+        const int ga = ZO ? LR_ACT_NONE : b.act;
         float4 o;
         o.x = sc[0] * (g.x * nn::act_grad(fmaf(v.x, sc[0], sh[0]), ga)) - fmaf(v.x - mu[0], ka[0], kd[0]);
         o.y = sc[1] * (g.y * nn::act_grad(fmaf(v.y, sc[1], sh[1]), ga)) - fmaf(v.y - mu[1], ka[1], kd[1]);
@@ -384,9 +395,9 @@ static int bn_act_fwd_impl(const T* x, const double* stats, const float* gamma, 
     LR_CHECK_ARG(x && gamma && beta && z, "lr_bn_act_fwd: null pointer");
     LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(z); LR_CHECK_ALIGN(residual);
     dim3 grid; int gw; const int rpb = rows_per_block_for(rows, C, &grid, &gw);
-    bn::bn_act_fwd_kernel<T><<<grid, bn::TH, 0, stream>>>(
-        make_bn(rows, C, stats, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, act, training),
-        x, residual, z, rpb, res_pre, gw);
+    const bn::Bn b = make_bn(rows, C, stats, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, act, training);
+    if (residual) bn::bn_act_fwd_kernel<T, true><<<grid, bn::TH, 0, stream>>>(b, x, residual, z, rpb, res_pre, gw);
+    else bn::bn_act_fwd_kernel<T, false><<<grid, bn::TH, 0, stream>>>(b, x, residual, z, rpb, res_pre, gw);
     lr::count_launch();
     LR_CHECK_LAUNCH("bn_act_fwd_kernel");
     return LR_OK;
@@ -421,10 +432,12 @@ static int bn_act_bwd_impl(const T* x, const double* stats, const float* gamma, 
     dim3 grid; int gw; const int rpb = rows_per_block_for(rows, C, &grid, &gw);
     const bn::Bn b = make_bn(rows, C, stats, gamma, beta, const_cast<float*>(running_mean),
                              const_cast<float*>(running_var), nullptr, eps, 0.f, act, training);
-    bn::bn_act_bwd_reduce_kernel<T><<<grid, bn::TH, 2 * C * sizeof(float), stream>>>(b, x, dz, z_out, sums, rpb, gw);
+    if (z_out) bn::bn_act_bwd_reduce_kernel<T, true><<<grid, bn::TH, 2 * C * sizeof(float), stream>>>(b, x, dz, z_out, sums, rpb, gw);
+    else bn::bn_act_bwd_reduce_kernel<T, false><<<grid, bn::TH, 2 * C * sizeof(float), stream>>>(b, x, dz, z_out, sums, rpb, gw);
     lr::count_launch();
     LR_CHECK_LAUNCH("bn_act_bwd_reduce_kernel");
-    bn::bn_act_bwd_apply_kernel<T><<<grid, bn::TH, 0, stream>>>(b, x, dz, z_out, dres, sums, dx, dgamma, dbeta, rpb, gw);
+    if (z_out) bn::bn_act_bwd_apply_kernel<T, true><<<grid, bn::TH, 0, stream>>>(b, x, dz, z_out, dres, sums, dx, dgamma, dbeta, rpb, gw);
+    else bn::bn_act_bwd_apply_kernel<T, false><<<grid, bn::TH, 0, stream>>>(b, x, dz, z_out, dres, sums, dx, dgamma, dbeta, rpb, gw);
     lr::count_launch();
     LR_CHECK_LAUNCH("bn_act_bwd_apply_kernel");
     return LR_OK;

@@ -87,6 +87,21 @@ __device__ __forceinline__ float4 ld4_hint(const bf16* p, unsigned long long pol
     return unpack4(u);
 }
 
+// Raw 4-channel vectors: what a streaming kernel keeps IN FLIGHT (float4 = 4 registers, bf16 = 2 registers), converted
+// to float4 only at the point of use so that doubling the rows in flight for bf16 costs no extra registers.
+template <typename T> struct Raw4 { typedef float4 type; };
+template <> struct Raw4<bf16> { typedef uint2 type; };
+__device__ __forceinline__ float4 ldraw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ uint2 ldraw(const bf16* p) { return *reinterpret_cast<const uint2*>(p); }
+__device__ __forceinline__ float4 ldraw_hint(const float* p, unsigned long long pol) { return ld4_hint(p, pol); }
+__device__ __forceinline__ uint2 ldraw_hint(const bf16* p, unsigned long long pol) {
+    uint2 u;
+    asm volatile("ld.global.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(u.x), "=r"(u.y) : "l"(p), "l"(pol));
+    return u;
+}
+__device__ __forceinline__ float4 cvt4(float4 v) { return v; }
+__device__ __forceinline__ float4 cvt4(uint2 u) { return unpack4(u); }
+
 // Channel-group mapping for a row-major [rows, C] tensor with C % 4 == 0: a thread owns ONE group of
 // 4 consecutive channels (so per-channel parameters live in registers) and strides over rows.
 // Consecutive threads touch consecutive float4s, so every warp access is fully coalesced.

@@ -159,23 +159,35 @@ def profile_ops_graph(ops, reps=20, flush=None):
 
 
 def op_algorithmic_bytes(name, args):
-    """Algorithmic HBM bytes of one launch (every operand read once, every result written once, fp32)."""
+    """Algorithmic HBM bytes of one launch (every operand read once, every result written once; 4 bytes per fp32
+    element, 2 per bf16 element of the `_h` / lr_gemm_bf16 variants)."""
     if name in ("lr_gemm", "lr_gemm_tf32"):
         M, N, K = args[8], args[9], args[10]
         extra = M * N if args[13] else 0                 # residual / accumulate operand
         return 4 * (M * K + N * K + M * N + extra)
-    if name == "lr_bn_act_fwd":
+    if name == "lr_gemm_bf16":
+        c_h, M, N, K = args[8], args[9], args[10], args[11]
+        ce = 2 if c_h else 4
+        extra = M * N if args[14] else 0
+        return 2 * (M * K + N * K) + ce * (M * N + extra)
+    es = 2 if name.endswith("_h") else 4
+    base = name[:-2] if name.endswith("_h") else name
+    if base == "lr_bn_act_fwd":
         rows, C = args[-2], args[-1]
-        return 4 * rows * C * (3 if args[-4] else 2)
-    if name == "lr_bn_act_bwd":
+        return es * rows * C * (3 if args[-4] else 2)
+    if base == "lr_bn_act_bwd":
         rows, C = args[-2], args[-1]
-        return 4 * rows * C * 3                          # x, dz in; dx out (the two passes re-read x and dz)
-    if name in ("lr_dwconv_fwd", "lr_dwconv_dgrad", "lr_dwconv_wgrad"):
+        return es * rows * C * 3                         # x, dz in; dx out (the two passes re-read x and dz)
+    if base in ("lr_dwconv_fwd", "lr_dwconv_dgrad", "lr_dwconv_wgrad"):
         F, H, W, C, k, st = args[-6:]
         Ho, Wo = (H + 2 * (k // 2) - k) // st + 1, (W + 2 * (k // 2) - k) // st + 1
-        return 4 * F * C * (H * W + Ho * Wo)
-    if name == "lr_im2col":
-        return None
+        return es * F * C * (H * W + Ho * Wo)
+    if base == "lr_frame_reduce":
+        F, HW, C, mode = args[-4:]
+        return es * F * HW * C * (2 if mode else 1) + 4 * F * C
+    if base == "lr_frame_scale":
+        F, HW, C = args[-3:]
+        return es * F * HW * C * (2 if args[0] else 1) + 4 * F * C
     return None
 
 
@@ -234,6 +246,12 @@ class FlatParams:
     def intact(self):
         return all(p.data_ptr() == q for p, q in zip(self.params, self._ptrs))
 
+    def shadow(self):
+        """bf16 copy of the flat parameter buffer (precision "bf16": the B operands of the tcgen05 kind::f16 GEMMs)."""
+        if getattr(self, "h16", None) is None:
+            self.h16 = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.device)
+        return self.h16
+
     def g(self, p):
         """Gradient view of parameter p inside the flat gradient buffer."""
         for q, o in zip(self.params, self.offsets):
@@ -257,17 +275,21 @@ class FlatParams:
 class T2:
     """A [rows, C] channels-last activation (value + gradient buffer) with its frame geometry."""
 
-    def __init__(self, plan, F, H, W, C, need_grad=True):
+    def __init__(self, plan, F, H, W, C, need_grad=True, h=None):
+        """h: bf16 storage (default: the plan's precision); arithmetic on it is fp32 either way."""
         self.F, self.H, self.W, self.C = F, H, W, C
         self.rows = F * H * W
-        self.val = plan.alloc(self.rows * C)
-        self.grad = plan.alloc(self.rows * C) if (need_grad and plan.with_backward) else None
+        self.h = plan.h if h is None else bool(h)
+        dt = torch.bfloat16 if self.h else torch.float32
+        self.val = plan.alloc(self.rows * C, dt)
+        self.grad = plan.alloc(self.rows * C, dt) if (need_grad and plan.with_backward) else None
 
     @classmethod
     def of(cls, F, H, W, C, val, grad):
-        """A view of existing buffers under another frame geometry (e.g. [B*T, C] features as a [B, 1, T, C] map)."""
+        """A view of existing fp32 buffers under another frame geometry (e.g. [B*T, C] features as a [B, 1, T, C] map)."""
         t = cls.__new__(cls)
         t.F, t.H, t.W, t.C, t.rows, t.val, t.grad = F, H, W, C, F * H * W, val, grad
+        t.h = isinstance(val, torch.Tensor) and val.dtype == torch.bfloat16
         return t
 
 
@@ -276,11 +298,16 @@ class Plan:
 
     def __init__(self, flat, device, training, with_backward, precision="tf32"):
         """precision: "tf32" -- the GEMMs with enough rows run on the tensor cores (tcgen05, TF32 products, fp32
-        accumulate); "fp32" -- every GEMM on the fp32 SIMT kernel (strict-parity mode)."""
-        if precision not in ("tf32", "fp32"):
-            raise ValueError(f"precision must be 'tf32' or 'fp32', got {precision!r}")
+        accumulate); "fp32" -- every GEMM on the fp32 SIMT kernel (strict-parity mode); "bf16" -- as "tf32" plus
+        bf16 storage of the trunk activations and bf16 tensor-core products there."""
+        if precision not in ("tf32", "fp32", "bf16"):
+            raise ValueError(f"precision must be 'tf32', 'fp32' or 'bf16', got {precision!r}")
         self.flat, self.dev, self.training, self.with_backward = flat, torch.device(device), training, with_backward
-        self.tc = precision == "tf32"
+        self.tc = precision in ("tf32", "bf16")
+        # "bf16": the trunk's per-pixel activations and their gradients are stored as bfloat16 and its GEMMs run
+        # tcgen05 kind::f16 on a bf16 shadow of the weights; per-frame vectors, heads, LSTM stay fp32 / tf32
+        self.h = precision == "bf16"
+        self._uses_shadow = False
         self.fwd, self.bwd_rev = OpList(), []          # bwd_rev: groups appended in forward order, run reversed
         self.bufs = []
         self.sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
@@ -326,11 +353,31 @@ class Plan:
         self.bwd_rev.append(g)
         return g
 
-    def workspace(self, n_floats):
+    def workspace(self, n_elems, h=False):
         """A scratch buffer shared by every op that asks (used and consumed within one backward group on the
-        main stream); returns a thunk resolved by finalize()."""
-        self._ws_floats = max(self._ws_floats, int(n_floats))
+        main stream); returns a thunk resolved by finalize().  h: the elements are bf16."""
+        n_floats = (int(n_elems) + 1) // 2 if h else int(n_elems)
+        self._ws_floats = max(self._ws_floats, n_floats)
         return lambda: self._ws.data_ptr()
+
+    # ---- bf16 operands
+    def wh(self, w):
+        """Pointer to the bf16 shadow of parameter tensor `w` (a view into the flat buffer).  The shadow of the whole
+        flat parameter buffer is refreshed by ONE cast launch at the start of every step (ModelPlan._finish)."""
+        off = (w.data_ptr() - self.flat.flat.data_ptr()) // 4
+        assert 0 <= off and off + w.numel() <= self.flat.numel, "not a parameter of this model"
+        self._uses_shadow = True
+        return self.flat.shadow().data_ptr() + 2 * off
+
+    def cast_h(self, ops, src, leaf=False):
+        """bf16 copy of an fp32 scratch matrix (a re-laid-out weight), emitted into `ops`."""
+        dst = self.alloc(src.numel(), torch.bfloat16)
+        ops.add("lr_cast_bf16", src, dst, src.numel(), leaf=leaf)
+        return dst
+
+    def alloc_like(self, t, n):
+        """n elements with T2 t's storage type."""
+        return self.alloc(n, torch.bfloat16 if t.h else torch.float32)
 
     # ---- op emitters ----------------------------------------------------------------------------------
     def gemm(self, ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias=0, act=ACT_NONE, R=0, ldr=0, stats=0, ksplit=1,
@@ -343,9 +390,24 @@ class Plan:
         return self.tc and lda % 4 == 0 and ldb % 4 == 0 and max(M, K) >= 512
 
     def gemm_auto(self, ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias=0, act=ACT_NONE, R=0, ldr=0, stats=0,
-                  split_ok=False):
+                  split_ok=False, h=False):
         """Emit one GEMM, choosing the tcgen05 kernel when it pays; split_ok: the caller accumulates into a
-        pre-initialised C, so the reduction may be split over CTAs with atomic adds."""
+        pre-initialised C, so the reduction may be split over CTAs with atomic adds.
+        h: A and B are bf16 (activations / bf16 weight shadow): tcgen05 kind::f16; the result is bf16 too, except for
+        split_ok calls (weight gradients accumulate in fp32)."""
+        if h:
+            if lda % 8 or ldb % 8 or (not split_ok and ldc % 8):
+                raise NotImplementedError(f"bf16 GEMM operands need row pitches that are multiples of 8 (got {lda}, {ldb}, {ldc})")
+            ks = 1
+            if split_ok:
+                bn_tiles = ((M + 127) // 128) * ((N + 255) // 256)
+                ks = max(1, min((K + 255) // 256, (2 * self.sms) // bn_tiles))
+            if ks > 1:
+                ops.add("lr_gemm_bf16", A, lda, at, B, ldb, bt, C, ldc, 0, M, N, K, 0, ACT_NONE, 0, 0, 0, ks, leaf=True)
+            else:
+                ops.add("lr_gemm_bf16", A, lda, at, B, ldb, bt, C, ldc, int(not split_ok), M, N, K, bias, act,
+                        (C if split_ok else R), (ldc if split_ok else ldr), stats, 1, leaf=split_ok)
+            return
         if N >= 4 and self.use_tc(M, N, K, lda, ldb):
             ks = 1
             if split_ok:
@@ -375,15 +437,16 @@ class Plan:
             self.gemm_auto(self.fwd, x, lda, 0, w, K, 0, out, ldc, M, N, K, bias=(b if b is not None else 0), act=act,
                            stats=stats)
 
-    def linear_bwd(self, g, x, lda, M, w, b, dy, ldy, dx=None, ldx=0, dx_residual=0, ldr=0):
-        """dw += dy^T x, db += colsum(dy), dx = dy w (+ residual).  Ops are appended to backward group g."""
+    def linear_bwd(self, g, x, lda, M, w, b, dy, ldy, dx=None, ldx=0, dx_residual=0, ldr=0, h=False):
+        """dw += dy^T x, db += colsum(dy), dx = dy w (+ residual).  Ops are appended to backward group g.
+        h: x, dy, dx (and the residual) are bf16 activations; dw / db stay fp32."""
         N, K = w.shape[0], w[0].numel()
         dw = self.flat.g(w)
-        self.gemm_auto(g, dy, ldy, 1, x, lda, 1, dw, K, N, K, M, split_ok=True)       # dw += dy^T x
+        self.gemm_auto(g, dy, ldy, 1, x, lda, 1, dw, K, N, K, M, split_ok=True, h=h)       # dw += dy^T x
         if b is not None:
-            g.add("lr_colsum", dy, ldy, M, N, self.flat.g(b), leaf=True)
+            g.add("lr_colsum_h" if h else "lr_colsum", dy, ldy, M, N, self.flat.g(b), leaf=True)
         if dx is not None:
-            self.gemm_auto(g, dy, ldy, 0, w, K, 1, dx, ldx, M, K, N, R=dx_residual, ldr=ldr)
+            self.gemm_auto(g, dy, ldy, 0, (self.wh(w) if h else w), K, 1, dx, ldx, M, K, N, R=dx_residual, ldr=ldr, h=h)
 
     def bn_act(self, x, bn, act, out, residual=None, res_pre=False, dres=None):
         """out.val = act(bn(x.val)) (+ residual.val); backward: x.grad from out.grad (residual.grad is out.grad).
@@ -392,36 +455,39 @@ class Plan:
         slot = x.stat_slot
         st = (lambda s=slot: s["fwd"]) if self.training else 0
         momentum = 0.1 if bn.momentum is None else float(bn.momentum)
-        self.fwd.add("lr_bn_act_fwd", x.val, st, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+        sfx = "_h" if x.h else ""
+        self.fwd.add("lr_bn_act_fwd" + sfx, x.val, st, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                      bn.num_batches_tracked, float(bn.eps), momentum, act, int(self.training),
                      residual.val if residual is not None else 0, int(res_pre), out.val, x.rows, x.C)
         if self.with_backward:
             g = self.bgroup()
-            g.add("lr_bn_act_bwd", x.val, st, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.eps), act,
+            g.add("lr_bn_act_bwd" + sfx, x.val, st, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.eps), act,
                   int(self.training), out.grad, (out.val if res_pre else 0), (dres if dres is not None else 0),
                   (lambda s=slot: s["bwd"]), x.grad, self.flat.g(bn.weight), self.flat.g(bn.bias), x.rows, x.C)
 
     def pw_conv(self, x, conv, F, H, W):
         """1x1 convolution as a GEMM on [rows, Cin]; returns the raw output tensor (with BN statistics slot)."""
         Cout, Cin = conv.out_channels, conv.in_channels
-        y = T2(self, F, H, W, Cout)
+        y = T2(self, F, H, W, Cout, h=x.h)
         y.stat_slot = self.stat_slot(Cout)
         st = (lambda s=y.stat_slot: s["fwd"]) if self.training else 0
-        self.gemm_auto(self.fwd, x.val, Cin, 0, conv.weight, Cin, 0, y.val, Cout, x.rows, Cout, Cin, stats=st)
+        self.gemm_auto(self.fwd, x.val, Cin, 0, (self.wh(conv.weight) if x.h else conv.weight), Cin, 0, y.val, Cout, x.rows,
+                       Cout, Cin, stats=st, h=x.h)
         return y
 
     def dw_conv(self, x, conv):
         C, k, s = conv.in_channels, conv.kernel_size[0], conv.stride[0]
         Ho = (x.H + 2 * (k // 2) - k) // s + 1
         Wo = (x.W + 2 * (k // 2) - k) // s + 1
-        y = T2(self, x.F, Ho, Wo, C)
+        y = T2(self, x.F, Ho, Wo, C, h=x.h)
         y.stat_slot = self.stat_slot(C)
         st = (lambda sl=y.stat_slot: sl["fwd"]) if self.training else self.dummy_stats()
-        self.fwd.add("lr_dwconv_fwd", x.val, conv.weight, y.val, st, x.F, x.H, x.W, C, k, s)
+        sfx = "_h" if x.h else ""
+        self.fwd.add("lr_dwconv_fwd" + sfx, x.val, conv.weight, y.val, st, x.F, x.H, x.W, C, k, s)
         if self.with_backward:
             g = self.bgroup()
-            g.add("lr_dwconv_wgrad", y.grad, x.val, self.flat.g(conv.weight), x.F, x.H, x.W, C, k, s, leaf=True)
-            g.add("lr_dwconv_dgrad", y.grad, conv.weight, x.grad, x.F, x.H, x.W, C, k, s)
+            g.add("lr_dwconv_wgrad" + sfx, y.grad, x.val, self.flat.g(conv.weight), x.F, x.H, x.W, C, k, s, leaf=True)
+            g.add("lr_dwconv_dgrad" + sfx, y.grad, conv.weight, x.grad, x.F, x.H, x.W, C, k, s)
         return y
 
     @contextlib.contextmanager
@@ -457,14 +523,14 @@ class Plan:
             if self.with_backward:
                 self.dense_conv_bwd(raw)
         else:
-            raw = T2(self, F, Ho, Wo, 16)
+            raw = T2(self, F, Ho, Wo, 16, h=False)
             raw.stat_slot = self.stat_slot(16)
             st = (lambda s=raw.stat_slot: s["fwd"]) if self.training else self.dummy_stats()
             self.fwd.add("lr_stem_conv_fwd", frames, *layout, float(scale), conv.weight, raw.val, st)
             if self.with_backward:
                 g = self.bgroup()
                 g.add("lr_stem_conv_wgrad", frames, *layout, float(scale), raw.grad, self.flat.g(conv.weight), leaf=True)
-        cur = T2(self, F, Ho, Wo, 16)
+        cur = T2(self, F, Ho, Wo, 16, h=raw.h)
         self.bn_act(raw, bn, act, cur)
         for blk in feats[1:]:
             if hasattr(blk, "block"):
@@ -515,13 +581,13 @@ class Plan:
                 if (cur is x) and use_res:
                     raise NotImplementedError("residual block without an expansion conv")
                 raw = self.dw_conv(cur, conv)
-            out = T2(self, raw.F, raw.H, raw.W, raw.C)
+            out = T2(self, raw.F, raw.H, raw.W, raw.C, h=raw.h)
             self.bn_act(raw, bn, act, out, residual=x if (last and use_res) else None)
             cur = out
         for g, inp, conv, raw, add_res in deferred:
             Cout, Cin = conv.out_channels, conv.in_channels
             self.linear_bwd(g, inp.val, Cin, inp.rows, conv.weight, None, raw.grad, Cout, dx=inp.grad, ldx=Cin,
-                            dx_residual=(cur.grad if add_res else 0), ldr=Cin)
+                            dx_residual=(cur.grad if add_res else 0), ldr=Cin, h=inp.h)
         return cur
 
     def pw_bn_act(self, cur, conv, bn, act):
@@ -530,8 +596,8 @@ class Plan:
         raw = self.pw_conv(cur, conv, cur.F, cur.H, cur.W)
         if self.with_backward:
             self.linear_bwd(self.bgroup(), cur.val, conv.in_channels, cur.rows, conv.weight, None, raw.grad,
-                            conv.out_channels, dx=cur.grad, ldx=conv.in_channels)
-        out = T2(self, cur.F, cur.H, cur.W, conv.out_channels)
+                            conv.out_channels, dx=cur.grad, ldx=conv.in_channels, h=cur.h)
+        out = T2(self, cur.F, cur.H, cur.W, conv.out_channels, h=raw.h)
         self.bn_act(raw, bn, act, out)
         return out
 
@@ -542,7 +608,7 @@ class Plan:
         raw = self.dense_conv(None, stem[0], frames=frames)
         if self.with_backward:
             self.dense_conv_bwd(raw)
-        cur = T2(self, raw.F, raw.H, raw.W, raw.C)
+        cur = T2(self, raw.F, raw.H, raw.W, raw.C, h=raw.h)
         self.bn_act(raw, stem[1], _act_code(stem[2]), cur)
         self.trace = [cur]
         for blk in feats[1:]:
@@ -559,20 +625,22 @@ class Plan:
         goes to the matching slice of that activation's gradient (written, or accumulated when another branch wrote)."""
         Cout, Cin = conv.out_channels, conv.in_channels
         assert conv.kernel_size == (1, 1) and conv.groups == 1 and conv.bias is None
-        raw = T2(self, x.F, x.H, x.W, Cout)
+        if x.h:
+            raise NotImplementedError("ShuffleNetV2 units address column slices of fp32 rows (fp32 storage only)")
+        raw = T2(self, x.F, x.H, x.W, Cout, h=False)
         raw.stat_slot = self.stat_slot(Cout)
         st = (lambda sl=raw.stat_slot: sl["fwd"]) if self.training else 0
         self.gemm_auto(self.fwd, xval, lda, 0, conv.weight, Cin, 0, raw.val, Cout, x.rows, Cout, Cin, stats=st)
         if self.with_backward:
             self.linear_bwd(self.bgroup(), xval, lda, x.rows, conv.weight, None, raw.grad, Cout, dx=xgrad, ldx=ldg,
                             dx_residual=(xgrad if accumulate else 0), ldr=ldg)
-        out = T2(self, x.F, x.H, x.W, Cout)
+        out = T2(self, x.F, x.H, x.W, Cout, h=raw.h)
         self.bn_act(raw, bn, act, out)
         return out
 
     def _dw_bn(self, x, conv, bn):
         raw = self.dw_conv(x, conv)
-        out = T2(self, raw.F, raw.H, raw.W, raw.C)
+        out = T2(self, raw.F, raw.H, raw.W, raw.C, h=raw.h)
         self.bn_act(raw, bn, ACT_NONE, out)
         return out
 
@@ -588,7 +656,7 @@ class Plan:
             h = self._pw_strided(x.val.data_ptr() + 4 * bf, C, xg, C, x, b2[0], b2[1], ACT_RELU)
             h = self._dw_bn(h, b2[3], b2[4])
             right = self.pw_bn_act(h, b2[5], b2[6], ACT_RELU)
-            out = T2(self, x.F, x.H, x.W, C)
+            out = T2(self, x.F, x.H, x.W, C, h=x.h)
             self.fwd.add("lr_shuffle2_fwd", x.val, C, right.val, bf, out.val, x.rows, bf)
             if wb:
                 self.bgroup().add("lr_shuffle2_bwd", out.grad, x.grad, C, right.grad, bf, x.rows, bf)
@@ -602,7 +670,7 @@ class Plan:
         l = self._dw_bn(x, b1[0], b1[1])
         left = self.pw_bn_act(l, b1[2], b1[3], ACT_RELU)
         bf = left.C
-        out = T2(self, left.F, left.H, left.W, 2 * bf)
+        out = T2(self, left.F, left.H, left.W, 2 * bf, h=left.h)
         self.fwd.add("lr_shuffle2_fwd", left.val, bf, right.val, bf, out.val, left.rows, bf)
         if wb:
             self.bgroup().add("lr_shuffle2_bwd", out.grad, left.grad, bf, right.grad, bf, left.rows, bf)
@@ -612,10 +680,11 @@ class Plan:
         """Sequential(conv1, maxpool, stage2, stage3, stage4, conv5) of torchvision shufflenet_v2_x0_5 / x1_0 on
         frames = (tensor, layout, scale) -> last activation T2 (video/models/shufflenet_lstm.py:47-55)."""
         conv1, mp, stages, conv5 = seq[0], seq[1], (seq[2], seq[3], seq[4]), seq[5]
-        raw = self.dense_conv(None, conv1[0], frames=frames)
+        # the split / shuffle kernels address column slices of fp32 rows: this trunk keeps fp32 storage in every mode
+        raw = self.dense_conv(None, conv1[0], frames=frames, h=False)
         if self.with_backward:
             self.dense_conv_bwd(raw)
-        cur = T2(self, raw.F, raw.H, raw.W, raw.C)
+        cur = T2(self, raw.F, raw.H, raw.W, raw.C, h=raw.h)
         self.bn_act(raw, conv1[1], ACT_RELU, cur)
         cur = self.maxpool(cur, mp.kernel_size, mp.stride, mp.padding)
         for stage in stages:
@@ -627,41 +696,45 @@ class Plan:
         """SqueezeExcitation: b = a * hardsigmoid(fc2(relu(fc1(mean_hw(a)))))."""
         F, HW, C = a.F, a.H * a.W, a.C
         Cs = se.fc1.out_channels
-        p, h1, s = self.alloc(F * C), self.alloc(F * Cs), self.alloc(F * C)
-        out = T2(self, a.F, a.H, a.W, C)
-        self.fwd.add("lr_frame_reduce", a.val, 0, p, F, HW, C, 0)
+        p, h1, s = self.alloc(F * C), self.alloc(F * Cs), self.alloc(F * C)      # per-frame vectors: always fp32
+        out = T2(self, a.F, a.H, a.W, C, h=a.h)
+        sfx = "_h" if a.h else ""
+        self.fwd.add("lr_frame_reduce" + sfx, a.val, 0, p, F, HW, C, 0)
         self.linear(p, C, F, se.fc1.weight, se.fc1.bias, h1, Cs, act=_act_code(se.activation))
         self.linear(h1, Cs, F, se.fc2.weight, se.fc2.bias, s, C, act=_act_code(se.scale_activation))
-        self.fwd.add("lr_frame_scale", a.val, s, 0, out.val, F, HW, C)
+        self.fwd.add("lr_frame_scale" + sfx, a.val, s, 0, out.val, F, HW, C)
         if self.with_backward:
             ds, dh1, dp = self.alloc(F * C), self.alloc(F * Cs), self.alloc(F * C)
             g = self.bgroup()
-            g.add("lr_frame_reduce", out.grad, a.val, ds, F, HW, C, 1)
+            g.add("lr_frame_reduce" + sfx, out.grad, a.val, ds, F, HW, C, 1)
             g.add("lr_act_bwd", ds, s, F * C, _act_code(se.scale_activation))
             self.linear_bwd(g, h1, Cs, F, se.fc2.weight, se.fc2.bias, ds, C, dx=dh1, ldx=Cs)
             g.add("lr_act_bwd", dh1, h1, F * Cs, _act_code(se.activation))
             self.linear_bwd(g, p, C, F, se.fc1.weight, se.fc1.bias, dh1, Cs, dx=dp, ldx=C)
-            g.add("lr_frame_scale", out.grad, s, dp, a.grad, F, HW, C)
+            g.add("lr_frame_scale" + sfx, out.grad, s, dp, a.grad, F, HW, C)
         return out
 
     def avgpool(self, a):
         """AdaptiveAvgPool2d(1) + flatten: [F, HW, C] -> feat [F, C] (value, gradient)."""
         F, HW, C = a.F, a.H * a.W, a.C
         feat, dfeat = self.alloc(F * C), (self.alloc(F * C) if self.with_backward else None)
-        self.fwd.add("lr_frame_reduce", a.val, 0, feat, F, HW, C, 0)
+        sfx = "_h" if a.h else ""
+        self.fwd.add("lr_frame_reduce" + sfx, a.val, 0, feat, F, HW, C, 0)
         if self.with_backward:
             g = self.bgroup()
-            g.add("lr_frame_scale", 0, 0, dfeat, a.grad, F, HW, C)
+            g.add("lr_frame_scale" + sfx, 0, 0, dfeat, a.grad, F, HW, C)
         return feat, dfeat
 
     # ---- dense convolutions (ResNet-18, AudioEncoder, MobileNetV2 stem) ----------------------------------
-    def dense_conv(self, x, conv, frames=None, need_dx=True, act=ACT_NONE, with_stats=True):
+    def dense_conv(self, x, conv, frames=None, need_dx=True, act=ACT_NONE, with_stats=True, h=None):
         """nn.Conv2d with groups == 1 on a channels-last T2 (or, for a stem, on the raw frames in the caller's
         layout: frames = (tensor, (is_u8, B, T, H, W, sb, st, sc, sh, sw), scale)) as im2col + GEMM.  Returns the
         raw output T2 (BatchNorm statistic slot attached).  The backward group is reserved here (its position fixes
-        when it runs) and filled by dense_conv_bwd once the caller knows what accumulates into x.grad."""
+        when it runs) and filled by dense_conv_bwd once the caller knows what accumulates into x.grad.
+        Storage type: that of x; for a stem the plan's (h overrides it: audio encoders whose consumers read fp32)."""
         Cout, Cin = conv.out_channels, conv.in_channels
         kh, kw, st_, pd, pw = _conv_geometry(conv)
+        hh = x.h if x is not None else (self.h if h is None else bool(h))
         if frames is not None:
             ft, (is_u8, B, T, Hs, Ws, sb, stt, sc, sh, sw), scale = frames
             F = B * T
@@ -672,22 +745,29 @@ class Plan:
             F, Hs, Ws = x.F, x.H, x.W
             src = (0, 1.0, F, 1, Hs * Ws * Cin, 0, 1, Ws * Cin, Cin)
             xptr = x.val
+        q = 8 if hh else 4                                     # row pitches: 16-byte multiples for TMA
+        if hh and Cout % 8:
+            raise NotImplementedError(f"bf16 storage needs Cout % 8 == 0 (conv with {Cout} output channels)")
         Ho, Wo = (Hs + 2 * pd - kh) // st_ + 1, (Ws + 2 * pw - kw) // st_ + 1
         rows = F * Ho * Wo
         K = Cin * kh * kw
-        pointwise = frames is None and kh == 1 and kw == 1 and st_ == 1 and pd == 0 and Cin % 4 == 0
-        # tap-major patch matrix (shifted float4 copies) for channels-last inputs; torch-order gather for the stems
-        tap = frames is None and not pointwise and Cin % 4 == 0 and Cout % 4 == 0
+        pointwise = frames is None and kh == 1 and kw == 1 and st_ == 1 and pd == 0 and Cin % q == 0
+        # tap-major patch matrix (shifted vector copies) for channels-last inputs; torch-order gather for the stems
+        tap = frames is None and not pointwise and Cin % q == 0 and Cout % 4 == 0
         assert tap or pw == pd, "unequal paddings need the tap-major path (channels-last input, C % 4 == 0)"
-        ldk = K if (pointwise or tap) else (K + 3) // 4 * 4
+        if hh and frames is None and not (pointwise or tap):
+            raise NotImplementedError("bf16 storage: dense conv on a channels-last input needs Cin % 8 == 0")
+        ldk = K if (pointwise or tap) else (K + q - 1) // q * q
+        adt = torch.bfloat16 if hh else torch.float32
+        sfx = "_h" if hh else ""
         if pointwise:
             col = xptr
         elif tap:
-            col = self.alloc(rows * K)
-            self.fwd.add("lr_im2col_tap", xptr, F, Hs, Ws, Cin, kh, kw, st_, pd, pw, 0, Ho, Wo, col)
+            col = self.alloc(rows * K, adt)
+            self.fwd.add("lr_im2col_tap" + sfx, xptr, F, Hs, Ws, Cin, kh, kw, st_, pd, pw, 0, Ho, Wo, col)
         else:
-            col = self.alloc(rows * ldk)
-            self.fwd.add("lr_im2col", xptr, *src, Hs, Ws, Cin, kh, kw, st_, pd, 0, Ho, Wo, col, ldk)
+            col = self.alloc(rows * ldk, adt)
+            self.fwd.add("lr_im2col" + sfx, xptr, *src, Hs, Ws, Cin, kh, kw, st_, pd, 0, Ho, Wo, col, ldk)
         if tap:
             wmat = self.alloc(Cout * K)
             self.fwd.add("lr_weight_tap", conv.weight, wmat, Cout, Cin, kh * kw, 0)
@@ -697,14 +777,18 @@ class Plan:
             self.fwd.add("lr_copy2d", wmat, ldk, conv.weight, K, Cout, K)
         else:
             wmat = conv.weight
-        y = T2(self, F, Ho, Wo, Cout)
+        if hh:                                                 # the GEMM's B operand in bf16
+            wop = self.wh(conv.weight) if wmat is conv.weight else self.cast_h(self.fwd, wmat)
+        else:
+            wop = wmat
+        y = T2(self, F, Ho, Wo, Cout, h=hh)
         stt_ = 0
         if with_stats:
             y.stat_slot = self.stat_slot(Cout)
             stt_ = (lambda s=y.stat_slot: s["fwd"]) if self.training else 0
         y._act = act
-        self.gemm_auto(self.fwd, col, ldk, 0, wmat, ldk, 0, y.val, Cout, rows, Cout, ldk,
-                       bias=(conv.bias if conv.bias is not None else 0), act=act, stats=stt_)
+        self.gemm_auto(self.fwd, col, ldk, 0, wop, ldk, 0, y.val, Cout, rows, Cout, ldk,
+                       bias=(conv.bias if conv.bias is not None else 0), act=act, stats=stt_, h=hh)
         if self.with_backward:
             g = self.bgroup()
             y._conv_bwd = (g, x, conv, col, ldk, wmat, src, (F, Hs, Ws, Ho, Wo), need_dx and frames is None, tap)
@@ -718,37 +802,43 @@ class Plan:
         kh, kw, st_, pd, pw = _conv_geometry(conv)
         K = Cin * kh * kw
         rows = F * Ho * Wo
+        hh = y.h
+        sfx = "_h" if hh else ""
         dw = self.flat.g(conv.weight)
         if getattr(y, "_act", ACT_NONE) != ACT_NONE:          # fused activation: dy *= act'(y) first
-            g.add("lr_act_bwd", y.grad, y.val, rows * Cout, y._act)
+            g.add("lr_act_bwd" + sfx, y.grad, y.val, rows * Cout, y._act)
         if tap:
             dwp = self.alloc(Cout * K)                              # gradient in the tap-major layout, then back to torch's
             g.add("lr_memset", dwp, Cout * K * 4, leaf=True)
-            self.gemm_auto(g, y.grad, Cout, 1, col, K, 1, dwp, K, Cout, K, rows, split_ok=True)
+            self.gemm_auto(g, y.grad, Cout, 1, col, K, 1, dwp, K, Cout, K, rows, split_ok=True, h=hh)
             g.add("lr_weight_tap", dwp, dw, Cout, Cin, kh * kw, 2, leaf=True)
         elif ldk != K:
             dwp = self.alloc(Cout * ldk)
             g.add("lr_memset", dwp, Cout * ldk * 4, leaf=True)
-            self.gemm_auto(g, y.grad, Cout, 1, col, ldk, 1, dwp, ldk, Cout, ldk, rows, split_ok=True)
+            self.gemm_auto(g, y.grad, Cout, 1, col, ldk, 1, dwp, ldk, Cout, ldk, rows, split_ok=True, h=hh)
             g.add("lr_copy2d", dw, K, dwp, ldk, Cout, K, leaf=True)
         else:
-            self.gemm_auto(g, y.grad, Cout, 1, col, ldk, 1, dw, ldk, Cout, ldk, rows, split_ok=True)
+            self.gemm_auto(g, y.grad, Cout, 1, col, ldk, 1, dw, ldk, Cout, ldk, rows, split_ok=True, h=hh)
         if conv.bias is not None:
-            g.add("lr_colsum", y.grad, Cout, rows, Cout, self.flat.g(conv.bias), leaf=True)
+            g.add("lr_colsum" + sfx, y.grad, Cout, rows, Cout, self.flat.g(conv.bias), leaf=True)
         if not need_dx:
             return
         rows_in = F * Hs * Ws
         if kh == 1 and kw == 1 and st_ == 1 and pd == 0:
-            self.gemm_auto(g, y.grad, Cout, 0, conv.weight, Cin, 1, x.grad, Cin, rows_in, Cin, Cout, R=dx_residual, ldr=Cin)
+            self.gemm_auto(g, y.grad, Cout, 0, (self.wh(conv.weight) if hh else conv.weight), Cin, 1, x.grad, Cin, rows_in, Cin,
+                           Cout, R=dx_residual, ldr=Cin, h=hh)
             return
         Kt = Cout * kh * kw
         if tap:
             wt = self.alloc(Cin * Kt)
             g.add("lr_weight_tap", conv.weight, wt, Cout, Cin, kh * kw, 1)
-            colT = self.workspace(rows_in * Kt)
-            g.add("lr_im2col_tap", y.grad, F, Ho, Wo, Cout, kh, kw, st_, pd, pw, 1, Hs, Ws, colT)
-            self.gemm_auto(g, colT, Kt, 0, wt, Kt, 0, x.grad, Cin, rows_in, Cin, Kt, R=dx_residual, ldr=Cin)
+            wt_op = self.cast_h(g, wt) if hh else wt
+            colT = self.workspace(rows_in * Kt, h=hh)
+            g.add("lr_im2col_tap" + sfx, y.grad, F, Ho, Wo, Cout, kh, kw, st_, pd, pw, 1, Hs, Ws, colT)
+            self.gemm_auto(g, colT, Kt, 0, wt_op, Kt, 0, x.grad, Cin, rows_in, Cin, Kt, R=dx_residual, ldr=Cin, h=hh)
             return
+        if hh:
+            raise NotImplementedError("bf16 storage: input gradient of a dense conv needs the tap-major path")
         ldt = (Kt + 3) // 4 * 4
         wt = self.alloc(Cin * ldt)
         wt.zero_()
@@ -760,11 +850,12 @@ class Plan:
 
     def maxpool(self, x, k, stride, pad):
         Ho, Wo = (x.H + 2 * pad - k) // stride + 1, (x.W + 2 * pad - k) // stride + 1
-        y = T2(self, x.F, Ho, Wo, x.C)
+        y = T2(self, x.F, Ho, Wo, x.C, h=x.h)
         arg = self.alloc(y.rows * x.C, torch.uint8)
-        self.fwd.add("lr_maxpool_fwd", x.val, y.val, arg, x.F, x.H, x.W, x.C, k, stride, pad)
+        sfx = "_h" if x.h else ""
+        self.fwd.add("lr_maxpool_fwd" + sfx, x.val, y.val, arg, x.F, x.H, x.W, x.C, k, stride, pad)
         if self.with_backward:
-            self.bgroup().add("lr_maxpool_bwd", y.grad, arg, x.grad, x.F, x.H, x.W, x.C, k, stride, pad)
+            self.bgroup().add("lr_maxpool_bwd" + sfx, y.grad, arg, x.grad, x.F, x.H, x.W, x.C, k, stride, pad)
         return y
 
     def dropout_active(self, p):
@@ -792,7 +883,7 @@ class Plan:
             dy = None
         return y, dy
 
-    def cnn_sequential(self, mods, frames):
+    def cnn_sequential(self, mods, frames, h=None):
         """nn.Sequential of Conv2d(3x3, padding 1) [+ BatchNorm2d] + ReLU, MaxPool2d(2) and a closing
         AdaptiveAvgPool2d on frames = (tensor, layout, scale): the audio encoders of audio_video/models/*.py, VGGLite
         (video/models/vgg_lstm.py:21-41), torchvision vgg*_bn features (audio/models/vgg_model.py:11-13).
@@ -805,16 +896,16 @@ class Plan:
                 has_bn = isinstance(mods[i + 1], nn.BatchNorm2d)
                 if has_bn:
                     assert isinstance(mods[i + 2], nn.ReLU)
-                    raw = self.dense_conv(cur, m, frames=frames if cur is None else None)
+                    raw = self.dense_conv(cur, m, frames=frames if cur is None else None, h=h)
                     if self.with_backward:
                         self.dense_conv_bwd(raw)
-                    a = T2(self, raw.F, raw.H, raw.W, raw.C)
+                    a = T2(self, raw.F, raw.H, raw.W, raw.C, h=raw.h)
                     self.bn_act(raw, mods[i + 1], ACT_RELU, a)
                     cur = a
                     i += 3                                       # conv, bn, relu
                 else:
                     assert isinstance(mods[i + 1], nn.ReLU)
-                    cur = self.dense_conv(cur, m, frames=frames if cur is None else None, act=ACT_RELU, with_stats=False)
+                    cur = self.dense_conv(cur, m, frames=frames if cur is None else None, act=ACT_RELU, with_stats=False, h=h)
                     if self.with_backward:
                         self.dense_conv_bwd(cur)
                     i += 2                                       # conv, relu
@@ -1048,7 +1139,7 @@ class Plan:
         raw = self.dense_conv(x, net.conv1, frames=frames if x is None else None)
         if self.with_backward:
             self.dense_conv_bwd(raw)
-        a = T2(self, raw.F, raw.H, raw.W, raw.C)
+        a = T2(self, raw.F, raw.H, raw.W, raw.C, h=raw.h)
         self.bn_act(raw, net.bn1, ACT_RELU, a)
         mp = net.maxpool
         k = mp.kernel_size if isinstance(mp.kernel_size, int) else mp.kernel_size[0]
@@ -1072,15 +1163,15 @@ class Plan:
         if blk.downsample is not None:
             dconv, dbn = blk.downsample[0], blk.downsample[1]
             ds_raw = self.dense_conv(x, dconv)
-            ident = T2(self, ds_raw.F, ds_raw.H, ds_raw.W, ds_raw.C)
+            ident = T2(self, ds_raw.F, ds_raw.H, ds_raw.W, ds_raw.C, h=ds_raw.h)
             self.bn_act(ds_raw, dbn, ACT_NONE, ident)
         raw1 = self.dense_conv(x, blk.conv1)
-        h1 = T2(self, raw1.F, raw1.H, raw1.W, raw1.C)
+        h1 = T2(self, raw1.F, raw1.H, raw1.W, raw1.C, h=raw1.h)
         self.bn_act(raw1, blk.bn1, ACT_RELU, h1)
         raw2 = self.dense_conv(h1, blk.conv2)
-        out = T2(self, raw2.F, raw2.H, raw2.W, raw2.C)
+        out = T2(self, raw2.F, raw2.H, raw2.W, raw2.C, h=raw2.h)
         if self.with_backward:
-            dmask = ident.grad if ds_raw is not None else self.alloc(out.rows * out.C)
+            dmask = ident.grad if ds_raw is not None else self.alloc_like(out, out.rows * out.C)
         self.bn_act(raw2, blk.bn2, ACT_RELU, out, residual=ident, res_pre=True, dres=dmask)
         if self.with_backward:
             self.dense_conv_bwd(raw2)

@@ -180,14 +180,14 @@ class ModelPlan(engine.Plan):
         """nn.Linear -> nn.BatchNorm1d -> activation on a [B, K] buffer: the GEMM epilogue emits the batch statistics,
         one lr_bn_act pass applies them.  Returns (value, gradient) buffers of the activation output."""
         D, K = fc.out_features, fc.in_features
-        raw = engine.T2(self, B, 1, 1, D)
+        raw = engine.T2(self, B, 1, 1, D, h=False)            # per-clip head vectors stay fp32 in every mode
         raw.stat_slot = self.stat_slot(D)
         st = (lambda s=raw.stat_slot: s["fwd"]) if self.training else 0
         self.gemm_auto(self.fwd, x, K, 0, fc.weight, K, 0, raw.val, D, B, D, K, bias=(fc.bias if fc.bias is not None else 0),
                        stats=st)
         if self.with_backward:
             self.linear_bwd(self.bgroup(), x, K, B, fc.weight, fc.bias, raw.grad, D, dx=dx, ldx=K)
-        h = engine.T2(self, B, 1, 1, D)
+        h = engine.T2(self, B, 1, 1, D, h=False)
         self.bn_act(raw, bn, act, h)
         return h.val, h.grad
 
@@ -205,6 +205,8 @@ class ModelPlan(engine.Plan):
         # per-step zeroing: BN statistic arena and (for the backward) the flat gradient
         self.pre = engine.OpList()
         self.pre.add("lr_memset", self.stats, self.stats.numel() * 8)
+        if self._uses_shadow:                          # precision "bf16": refresh the bf16 shadow of the weights
+            self.pre.add("lr_cast_bf16", self.flat.flat, self.flat.shadow(), self.flat.numel)
         if self.rng_step is not None:
             self.pre.add("lr_rng_tick", self.rng_step)
         self.pre_bwd = engine.OpList()
@@ -277,7 +279,8 @@ class PlanModel(nn.Module):
     def _init_base(self, num_classes, config, precision):
         self.num_classes = num_classes
         # "tf32": GEMM-shaped work on the tensor cores (tcgen05, TF32 products, fp32 accumulate; >= the bf16 the
-        # north star allows); "fp32": every kernel in fp32 SIMT arithmetic (strict parity with the reference)
+        # north star allows); "fp32": every kernel in fp32 SIMT arithmetic (strict parity with the reference);
+        # "bf16": the trunk's activations / gradients stored as bfloat16, its GEMMs tcgen05 kind::f16 (fp32 accumulate)
         self.precision = precision or config.get("precision.compute", "tf32")
         self._flat = None
         self._plans = {}

@@ -378,7 +378,7 @@ class CnnOnlyPlan(ModelPlan):
             raw = self.dense_conv(x, conv)
             if wb:
                 self.dense_conv_bwd(raw)
-            a = engine.T2(self, raw.F, raw.H, raw.W, raw.C)
+            a = engine.T2(self, raw.F, raw.H, raw.W, raw.C, h=raw.h)
             self.bn_act(raw, bn, ACT_RELU, a)
             x = a
         pooled, dpooled = self.avgpool(x)                           # x.mean(dim=2): over time
