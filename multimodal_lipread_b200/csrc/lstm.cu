@@ -449,13 +449,14 @@ template <int H> static int run_bwd_auto(const ls::Bwd& p, lr_stream_t stream) {
 
 // =====================================================================================================================
 // Grid-cooperative version for hidden sizes whose W_hh (4H x H floats: 4 MB at H = 512) does not fit the shared
-// memory of one 8-CTA cluster: NC = H / 16 CTAs per group of 32 batch rows, CTA c owns 16 hidden units and keeps its
-// W_hh slice (64 gate rows x H: 128 KB at H = 512) in shared memory for the whole walk.  h_t is exchanged through the
+// memory of one 8-CTA cluster: NC = H / 8 CTAs per group of 32 batch rows (64 CTAs at H = 512: twice the SMs and half
+// the per-step FMA chain of the first version's H / 16), CTA c owns 8 hidden units and keeps its W_hh slice (32 gate
+// rows x H: 64 KB at H = 512) in shared memory for the whole walk.  h_t is exchanged through the
 // `out` tensor itself (it is the next step's input and lives in L2), dgates through the `dgates` tensor; one
 // cooperative grid barrier per step.  Launched with cudaLaunchAttributeCooperative (all CTAs co-resident).
 namespace lsg {
 
-constexpr int U = 16, BG = 32, TH = 256, NRG = TH / U, RPT = BG / NRG;   // 16 units x 16 row groups of 2 rows
+constexpr int U = 8, BG = 32, TH = 256, NRG = TH / U, RPT = BG / NRG;    // 8 units x 32 row groups of 1 row: H/8 CTAs per group
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
@@ -485,16 +486,31 @@ lstm_fwd_coop_kernel(const ls::Fwd p) {
         const int t = p.reverse ? p.T - 1 - s : s;
         const int tprev = p.reverse ? t + 1 : t - 1;
         // h_{t-1}: the whole [BG][H] block from `out` (written by all CTAs of the group in the previous step)
-        for (int i = threadIdx.x; i < BG * (H / 4); i += TH) {
-            const int r = i / (H / 4), k4 = (i - r * (H / 4)) * 4;
-            const int b = b0 + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s > 0 && b < p.B) {
-                const float* src = p.out + ((long long)b * p.T + tprev) * p.ldo + k4;
-                v = vec_out ? __ldcg(reinterpret_cast<const float4*>(src))
-                            : make_float4(__ldcg(src), __ldcg(src + 1), __ldcg(src + 2), __ldcg(src + 3));
+        // (8 independent L2 loads in flight per thread: one at a time, this refill was most of the step's latency)
+        for (int i0 = threadIdx.x; i0 < BG * (H / 4); i0 += 8 * TH) {
+            float4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int i = i0 + q * TH;
+                v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < BG * (H / 4)) {
+                    const int r = i / (H / 4), k4 = (i - r * (H / 4)) * 4;
+                    const int b = b0 + r;
+                    if (s > 0 && b < p.B) {
+                        const float* src = p.out + ((long long)b * p.T + tprev) * p.ldo + k4;
+                        v[q] = vec_out ? __ldcg(reinterpret_cast<const float4*>(src))
+                                       : make_float4(__ldcg(src), __ldcg(src + 1), __ldcg(src + 2), __ldcg(src + 3));
+                    }
+                }
             }
-            *reinterpret_cast<float4*>(hb + r * HP + k4) = v;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int i = i0 + q * TH;
+                if (i < BG * (H / 4)) {
+                    const int r = i / (H / 4), k4 = (i - r * (H / 4)) * 4;
+                    *reinterpret_cast<float4*>(hb + r * HP + k4) = v[q];
+                }
+            }
         }
         float acc[RPT][4], xp[RPT][4];
 #pragma unroll

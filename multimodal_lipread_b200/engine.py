@@ -76,30 +76,42 @@ class OpList:
             if rc != 0:
                 raise _lib.LipreadError(f"{name} failed ({rc}): {lib.lr_last_error().decode()}")
 
-    def run_forked(self, main, side):
+    def run_forked(self, main, side, comm_hooks=None):
         """Same launches, but leaf ops go to `side` (a torch.cuda.Stream) behind an event recorded on `main`
         (their inputs are ready there), and `main` joins `side` at the end.  Under CUDA-graph capture this turns
-        the weight-gradient kernels into parallel branches of the graph."""
+        the weight-gradient kernels into parallel branches of the graph.
+        comm_hooks = (comm_stream, {op index: [callable, ...]}): after the op at that index has been issued, each
+        callable runs on `comm_stream` behind everything issued so far on main and side (gradient-bucket allreduces
+        that overlap the rest of the backward); main joins the comm stream at the end."""
         ms, ss = main.cuda_stream, side.cuda_stream
+        comm, hooks = comm_hooks if comm_hooks else (None, {})
         forked = False
-        for fn, args, name, leaf in self.ops:
+        for i, (fn, args, name, leaf) in enumerate(self.ops):
             if fn is None:                                 # join: the main chain needs everything the side branch produced
                 if forked:
                     main.wait_stream(side)
                     forked = False
-                continue
-            if leaf:
+            elif leaf:
                 ev = torch.cuda.Event()
                 ev.record(main)
                 side.wait_event(ev)
                 rc = fn(*args, ss)
                 forked = True
+                if rc != 0:
+                    raise _lib.LipreadError(f"{name} failed ({rc}): {lib.lr_last_error().decode()}")
             else:
                 rc = fn(*args, ms)
-            if rc != 0:
-                raise _lib.LipreadError(f"{name} failed ({rc}): {lib.lr_last_error().decode()}")
+                if rc != 0:
+                    raise _lib.LipreadError(f"{name} failed ({rc}): {lib.lr_last_error().decode()}")
+            for hook in hooks.get(i, ()):
+                comm.wait_stream(main)
+                comm.wait_stream(side)
+                with torch.cuda.stream(comm):
+                    hook()
         if forked:
             main.wait_stream(side)
+        if comm is not None:
+            main.wait_stream(comm)
 
     def __len__(self):
         return len(self.kernels())
@@ -352,6 +364,42 @@ class Plan:
         g = OpList()
         self.bwd_rev.append(g)
         return g
+
+    def grad_buckets(self, max_buckets=4, min_bytes=1 << 20):
+        """[(index of the LAST backward op that writes into the bucket, lo, hi)] over the flat gradient: contiguous
+        ranges of whole parameters, cut where the readiness (position in the backward schedule of the last op that
+        touches the parameter's gradient) changes most, so that each range can be allreduced as soon as it is final
+        while the rest of the backward still runs.  Derived from the launch list itself: an op writes a parameter's
+        gradient iff one of its pointer arguments lies inside that parameter's slice of flat.grad."""
+        flat = self.flat
+        base, nbytes = flat.grad.data_ptr(), flat.grad.numel() * 4
+        starts = flat.offsets + [flat.numel]
+        ready = [-1] * len(flat.params)
+        import bisect
+        for i, (fn, args, name, leaf) in enumerate(self.bwd.ops):
+            if fn is None:
+                continue
+            for a in args:
+                if isinstance(a, int) and base <= a < base + nbytes:
+                    k = bisect.bisect_right(flat.offsets, (a - base) // 4) - 1
+                    ready[k] = max(ready[k], i)
+        # greedy merge of adjacent parameters into at most max_buckets ranges: repeatedly merge the adjacent pair whose
+        # merge delays the earlier-ready side least (bytes * delay), never leaving a bucket below min_bytes
+        buckets = [[ready[k], starts[k], starts[k + 1]] for k in range(len(flat.params))]
+        def cost(a, b):
+            r = max(a[0], b[0])
+            return (r - a[0]) * (a[2] - a[1]) + (r - b[0]) * (b[2] - b[1])
+        while len(buckets) > 1:
+            small = [j for j in range(len(buckets)) if (buckets[j][2] - buckets[j][1]) * 4 < min_bytes]
+            if len(buckets) <= max_buckets and not small:
+                break
+            cands = range(len(buckets) - 1)
+            if len(buckets) <= max_buckets:                       # only the undersized ones still need a partner
+                cands = sorted({j for t in small for j in (t - 1, t) if 0 <= j < len(buckets) - 1})
+            j = min(cands, key=lambda j: cost(buckets[j], buckets[j + 1]))
+            a, b = buckets[j], buckets[j + 1]
+            buckets[j:j + 2] = [[max(a[0], b[0]), a[1], b[2]]]
+        return [tuple(b) for b in buckets]
 
     def workspace(self, n_elems, h=False):
         """A scratch buffer shared by every op that asks (used and consumed within one backward group on the
@@ -988,21 +1036,30 @@ class Plan:
         seq = self.alloc(F * 2 * H)
         dseq = self.alloc(F * 2 * H) if self.with_backward else None
         saved = []
-        for rev in (0, 1):
+        # the two directions are independent walks of T sequential steps: the reverse one runs as a side branch of the
+        # step graph, concurrently with the forward one (each is latency-bound on a fraction of the SMs)
+        for rev in (1, 0):
             xp, gates, cst, hp = self.alloc(F * G4), self.alloc(F * G4), self.alloc(F * H), self.alloc(F * H)
-            self.linear(cur, Icur, F, par("weight_ih", rev), par("bias_ih", rev), xp, G4)
-            self.fwd.add("lr_lstm_fwd", xp, G4, par("bias_hh", rev), par("weight_hh", rev),
-                         seq.data_ptr() + 4 * H * rev, 2 * H, gates, cst, hp, B, T, H, T, rev)
+            with (self.fwd.side_branch() if rev else contextlib.nullcontext()):
+                self.linear(cur, Icur, F, par("weight_ih", rev), par("bias_ih", rev), xp, G4)
+                self.fwd.add("lr_lstm_fwd", xp, G4, par("bias_hh", rev), par("weight_hh", rev),
+                             seq.data_ptr() + 4 * H * rev, 2 * H, gates, cst, hp, B, T, H, T, rev)
             saved.append((gates, cst, hp))
+        self.fwd.join()
+        saved.reverse()                                          # index by direction again
         if self.with_backward:
             g = self.bgroup()
+            dgs = [self.alloc(F * G4), self.alloc(F * G4)]
+            for rev in (1, 0):
+                gates, cst, hp = saved[rev]
+                with (g.side_branch() if rev else contextlib.nullcontext()):
+                    g.add("lr_lstm_bwd", dseq.data_ptr() + 4 * H * rev, 2 * H, -1, gates, cst, par("weight_hh", rev), dgs[rev],
+                          B, T, H, T, rev)
+            g.join()
             for rev in (0, 1):
                 gates, cst, hp = saved[rev]
-                dg = self.alloc(F * G4)
-                g.add("lr_lstm_bwd", dseq.data_ptr() + 4 * H * rev, 2 * H, -1, gates, cst, par("weight_hh", rev), dg,
-                      B, T, H, T, rev)
-                self.linear_bwd(g, hp, H, F, par("weight_hh", rev), par("bias_hh", rev), dg, G4)
-                self.linear_bwd(g, cur, Icur, F, par("weight_ih", rev), par("bias_ih", rev), dg, G4,
+                self.linear_bwd(g, hp, H, F, par("weight_hh", rev), par("bias_hh", rev), dgs[rev], G4)
+                self.linear_bwd(g, cur, Icur, F, par("weight_ih", rev), par("bias_ih", rev), dgs[rev], G4,
                                 dx=dcur, ldx=Icur, dx_residual=(dcur if rev else 0), ldr=Icur)
         return seq, dseq
 

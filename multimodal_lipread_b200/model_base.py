@@ -227,14 +227,15 @@ class ModelPlan(engine.Plan):
         else:
             self.fwd.run_forked(*forked)
 
-    def run_backward(self, stream, forked=None):
+    def run_backward(self, stream, forked=None, comm_hooks=None):
         """forked = (main, side) torch streams: weight-gradient kernels run on `side` concurrently with the
-        dgrad chain (used under CUDA-graph capture, where it becomes a parallel branch of the graph)."""
+        dgrad chain (used under CUDA-graph capture, where it becomes a parallel branch of the graph).
+        comm_hooks: see OpList.run_forked (bucketed gradient allreduce overlapped with the backward)."""
         self.pre_bwd.run(stream)
         if forked is None:
             self.bwd.run(stream)
         else:
-            self.bwd.run_forked(*forked)
+            self.bwd.run_forked(*forked, comm_hooks=comm_hooks)
 
     def n_launches(self):
         return len(self.fwd) + len(self.bwd) + 1
@@ -476,10 +477,10 @@ class PlanModel(nn.Module):
         plan.labels.copy_(labels, non_blocking=True)
         o = self._opt
 
-        def compute(stream, forked=None):
+        def compute(stream, forked=None, comm_hooks=None):
             plan.run_forward(stream, forked)
             plan.ce.run(stream)
-            plan.run_backward(stream, forked)
+            plan.run_backward(stream, forked, comm_hooks)
 
         def update(stream):
             _lib.check(lib.lr_adam_step(flat.flat.data_ptr(), flat.grad.data_ptr(), flat.m.data_ptr(), flat.v.data_ptr(),
@@ -501,7 +502,7 @@ class PlanModel(nn.Module):
         gkey = (id(plan), grad_allreduce is not None)
         graphs = self._graphs.get(gkey)
         if graphs is None:
-            graphs = self._capture(compute, update, grad_allreduce, flat)
+            graphs = self._capture(compute, update, grad_allreduce, flat, plan)
             self._graphs[gkey] = graphs
         graphs[0].replay()
         if len(graphs) > 1:                                  # split capture: the collective runs between two graphs
@@ -509,22 +510,35 @@ class PlanModel(nn.Module):
             graphs[1].replay()
         return plan.loss, plan.logits
 
-    def _capture(self, compute, update, grad_allreduce, flat):
+    def _capture(self, compute, update, grad_allreduce, flat, plan=None):
         """CUDA-graph capture of the step.  Single GPU: one graph.  Data parallel: the NCCL allreduce of the flat
-        gradient is captured INSIDE the same graph (compute -> allreduce -> Adam: one launch per step, no host
-        round trip between backward and optimizer); if the collective cannot be captured the step falls back to two
-        graphs with the collective launched between them."""
+        gradient is captured INSIDE the same graph, in BUCKETS on a communication branch: each contiguous range of
+        the flat gradient goes out as soon as the last backward op that writes it has been issued (audio_fc's 19 MB
+        at the very start of MidFusionFast's backward, the trunk last), so only the last bucket's collective is
+        exposed before Adam.  LIPREAD_ALLREDUCE_BUCKETS=1 restores the single collective after the backward; if the
+        collective cannot be captured the step falls back to two graphs with the collective launched between them."""
         main_serial = os.environ.get("LIPREAD_SERIAL_GRAPH", "0") == "1"
         if not hasattr(self, "_side"):
             self._side = torch.cuda.Stream()
+            self._comm = torch.cuda.Stream()
+        n_buckets = int(os.environ.get("LIPREAD_ALLREDUCE_BUCKETS", "4"))
 
         def body(with_update, with_allreduce):
             main = torch.cuda.current_stream()
             # LIPREAD_SERIAL_GRAPH=1: one linear chain of kernel nodes (what the ncu launch lists are taken from);
             # default: weight-gradient kernels as parallel branches of the graph
-            compute(main.cuda_stream, forked=None if main_serial else (main, self._side))
-            if with_allreduce:
+            hooks = None
+            if with_allreduce and not main_serial and plan is not None and n_buckets > 1:
+                table = {}
+                buckets = plan.grad_buckets(max_buckets=n_buckets)
+                for idx, lo, hi in buckets:
+                    table.setdefault(max(idx, 0), []).append(lambda lo=lo, hi=hi: grad_allreduce(flat.grad[lo:hi]))
+                hooks = (self._comm, table)
+                self._n_buckets = len(buckets)
+            compute(main.cuda_stream, forked=None if main_serial else (main, self._side), comm_hooks=hooks)
+            if with_allreduce and hooks is None:
                 grad_allreduce(flat.grad)
+                self._n_buckets = 1
             if with_update:
                 update(main.cuda_stream)
 
@@ -554,7 +568,7 @@ class PlanModel(nn.Module):
 
     def allreduce_buckets(self):
         """Number of collectives a data-parallel step issues (the flat gradient goes out in this many pieces)."""
-        return 1
+        return getattr(self, "_n_buckets", 1)
 
     def launches_per_step(self):
         """Kernels of this library launched by one train_step (counted by the library during the eager step)."""
