@@ -384,6 +384,20 @@ int lr_maxpool_fwd_h(const void* x, void* y, unsigned char* arg, int F, int H, i
 int lr_maxpool_bwd_h(const void* dy, const unsigned char* arg, void* dx, int F, int H, int W, int C, int k,
                      int stride, int pad, lr_stream_t stream);
 
+/* Implicit-GEMM 3x3 / stride 1 / pad 1 convolution on bf16 channels-last activations (tcgen05.mma kind::f16, fp32
+ * accumulate in TMEM; the shifted activation tile of every tap is a 4-D TMA box whose out-of-image part is zero filled:
+ * no patch matrix).  Cin, N multiples of 64, W <= 128.
+ *   lr_conv3x3_bf16        y[F*H*W, N] = conv(x[F,H,W,Cin], wt[N][9*Cin]) (+ R), wt tap-major (lr_weight_tap mode 0);
+ *                          flip = 1: the input gradient, dx = conv(dy, wt[Cin_conv][9*Cout] (lr_weight_tap mode 1)) with
+ *                          the taps mirrored; stats: double [2N] sums of the rounded outputs (train-mode BatchNorm).
+ *   lr_conv3x3_wgrad_bf16  dwp[Cout][9*Cin] (fp32, tap-major) += dy^T * shifted(x), split over pixel blocks, TMA reduce-add.
+ * replaces: torchvision BasicBlock conv1 / conv2 of the ResNet-18 trunks (video/models/resnet_lstm.py:79-110,
+ * audio_video/models/ef_cnn_lstm_resnet.py:62-64,86, audio/models/resnet_model.py:12-17), forward, dgrad and wgrad. */
+int lr_conv3x3_bf16(const void* x, const void* wt, void* y, const void* R, double* stats, int F, int H, int W, int Cin,
+                    int N, int flip, lr_stream_t stream);
+int lr_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dwp, int F, int H, int W, int Cin, int Cout,
+                          lr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -808,8 +808,14 @@ class Plan:
         ldk = K if (pointwise or tap) else (K + q - 1) // q * q
         adt = torch.bfloat16 if hh else torch.float32
         sfx = "_h" if hh else ""
+        # implicit GEMM (csrc/conv_igemm.cu): 3x3 / stride 1 / pad 1 on bf16 storage -- the tap's shifted tile comes
+        # straight from the activation through a 4-D TMA box, no patch matrix is written or read
+        igemm = (hh and tap and kh == 3 and kw == 3 and st_ == 1 and pd == 1 and pw == 1 and Cin % 64 == 0
+                 and Cout % 64 == 0 and Ws <= 128 and os.environ.get("LIPREAD_IGEMM", "1") == "1")
         if pointwise:
             col = xptr
+        elif igemm:
+            col = None
         elif tap:
             col = self.alloc(rows * K, adt)
             self.fwd.add("lr_im2col_tap" + sfx, xptr, F, Hs, Ws, Cin, kh, kw, st_, pd, pw, 0, Ho, Wo, col)
@@ -835,11 +841,17 @@ class Plan:
             y.stat_slot = self.stat_slot(Cout)
             stt_ = (lambda s=y.stat_slot: s["fwd"]) if self.training else 0
         y._act = act
-        self.gemm_auto(self.fwd, col, ldk, 0, wop, ldk, 0, y.val, Cout, rows, Cout, ldk,
-                       bias=(conv.bias if conv.bias is not None else 0), act=act, stats=stt_, h=hh)
+        if igemm and (conv.bias is not None or act != ACT_NONE):
+            raise NotImplementedError("implicit-GEMM conv: bias / fused activation (the ResNet convs have neither)")
+        if igemm:
+            self.fwd.add("lr_conv3x3_bf16", xptr, wop, y.val, 0, stt_, F, Hs, Ws, Cin, Cout, 0)
+        else:
+            self.gemm_auto(self.fwd, col, ldk, 0, wop, ldk, 0, y.val, Cout, rows, Cout, ldk,
+                           bias=(conv.bias if conv.bias is not None else 0), act=act, stats=stt_, h=hh)
         if self.with_backward:
             g = self.bgroup()
             y._conv_bwd = (g, x, conv, col, ldk, wmat, src, (F, Hs, Ws, Ho, Wo), need_dx and frames is None, tap)
+            y._igemm = igemm
         return y
 
     def dense_conv_bwd(self, y, dx_residual=0):
@@ -855,10 +867,14 @@ class Plan:
         dw = self.flat.g(conv.weight)
         if getattr(y, "_act", ACT_NONE) != ACT_NONE:          # fused activation: dy *= act'(y) first
             g.add("lr_act_bwd" + sfx, y.grad, y.val, rows * Cout, y._act)
+        igemm = getattr(y, "_igemm", False)
         if tap:
             dwp = self.alloc(Cout * K)                              # gradient in the tap-major layout, then back to torch's
             g.add("lr_memset", dwp, Cout * K * 4, leaf=True)
-            self.gemm_auto(g, y.grad, Cout, 1, col, K, 1, dwp, K, Cout, K, rows, split_ok=True, h=hh)
+            if igemm:
+                g.add("lr_conv3x3_wgrad_bf16", y.grad, x.val, dwp, F, Hs, Ws, Cin, Cout, leaf=True)
+            else:
+                self.gemm_auto(g, y.grad, Cout, 1, col, K, 1, dwp, K, Cout, K, rows, split_ok=True, h=hh)
             g.add("lr_weight_tap", dwp, dw, Cout, Cin, kh * kw, 2, leaf=True)
         elif ldk != K:
             dwp = self.alloc(Cout * ldk)
@@ -881,6 +897,9 @@ class Plan:
             wt = self.alloc(Cin * Kt)
             g.add("lr_weight_tap", conv.weight, wt, Cout, Cin, kh * kw, 1)
             wt_op = self.cast_h(g, wt) if hh else wt
+            if igemm:                                             # dx = conv(dy, mirrored taps) (+ residual): same kernel
+                g.add("lr_conv3x3_bf16", y.grad, wt_op, x.grad, dx_residual, 0, F, Hs, Ws, Cout, Cin, 1)
+                return
             colT = self.workspace(rows_in * Kt, h=hh)
             g.add("lr_im2col_tap" + sfx, y.grad, F, Ho, Wo, Cout, kh, kw, st_, pd, pw, 1, Hs, Ws, colT)
             self.gemm_auto(g, colT, Kt, 0, wt_op, Kt, 0, x.grad, Cin, rows_in, Cin, Kt, R=dx_residual, ldr=Cin, h=hh)
