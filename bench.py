@@ -14,8 +14,8 @@ buffers with the H2D copies and a D2H read of the result inside the timed region
 
 The DEFAULT invocation (no --workload) prints the headline line and carries, in the same JSON object, the rest of
 BASELINE.json's metric so that the driver sees it: `logmel` (GB/s, fraction of the HBM peak, its own cpu_baseline),
-`configs` (BASELINE.json configs 1, 2, 4, 5: clips/s, ms/step [, cpu_baseline at N = 1]), `value_fp32` (the same step
-with every GEMM in strict fp32), and at N > 1 `dp_parity` (allreduced gradient against the mean of per-shard oracle
+`configs` (BASELINE.json configs 1, 2, 4, 5: clips/s, ms/step [, cpu_baseline at N = 1]), `value_tf32` / `value_fp32` (the
+same step on fp32 storage with TF32 tensor-core products / with every GEMM in strict fp32), and at N > 1 `dp_parity` (allreduced gradient against the mean of per-shard oracle
 gradients) and `comm` (exposed collective time per step).
 
 `--impl reference` times the reference's CPU implementation on the host cores, same metric/config: the UNMODIFIED
@@ -256,7 +256,9 @@ def main():
     ap_.add_argument("--batch", type=int, default=None, help="clips per GPU per step")
     ap_.add_argument("--size", type=int, default=88, help="lip frame height = width (88 benchmark, 44 reference)")
     ap_.add_argument("--classes", type=int, default=40)
-    ap_.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "bf16"])
+    ap_.add_argument("--precision", default="bf16", choices=["tf32", "fp32", "bf16"],
+                     help="bf16 (default; the north star's precision): bf16 activation storage + tcgen05 kind::f16; "
+                          "tf32: fp32 storage + tcgen05 kind::tf32; fp32: strict fp32 SIMT everywhere")
     ap_.add_argument("--no-cpu-baseline", action="store_true")
     ap_.add_argument("--no-sub-records", action="store_true", help="headline line only (no logmel / configs / value_fp32)")
     ap_.add_argument("--dump-ops", default=None, help="write the per-op device times of one step (JSON) to this file")
@@ -386,7 +388,8 @@ def main():
         t = torch.tensor([ms_nocomm], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
-            line["comm"] = {"collective": "ncclAllReduce(sum) of the flat fp32 gradient, captured in the step graph",
+            line["comm"] = {"collective": "ncclAllReduce(sum) of the flat fp32 gradient in buckets on a communication branch of "
+                                          "the step graph, each issued when the last backward op that writes it has been issued",
                             "payload_bytes": wl.model._flat.grad.numel() * 4, "buckets": wl.model.allreduce_buckets(),
                             "ms_per_step_without_collective": t.item(),
                             "exposed_ms_per_step": max(0.0, ms_step - t.item())}
@@ -396,14 +399,19 @@ def main():
     # ---- the rest of BASELINE.json's metric, in the default invocation
     if default_run and not args.no_sub_records:
         sub_steps = min(args.steps, 10)
-        # (1) strict fp32 arithmetic beside the tensor-core number
-        w32 = BW.AvTrainWorkload(dev, batch, dict(cfg, precision="fp32"), rank, world)
-        ms32, _, _, _ = time_workload(w32, sub_steps, 3, with_e2e=False)
-        if rank == 0:
-            line["value_fp32"] = {"value": batch * world / (ms32 / 1e3), "unit": unit, "ms_per_step": ms32,
-                                  "note": "every GEMM on the fp32 SIMT kernel (precision='fp32'): the reference's arithmetic type"}
-        w32.release()
-        del w32
+        # (1) the same step in the wider arithmetic types, beside the headline number
+        notes = {"fp32": "every GEMM on the fp32 SIMT kernel (precision='fp32'): the reference's arithmetic type",
+                 "tf32": "fp32 storage, tcgen05 kind::tf32 products (precision='tf32': round 1's benchmarked mode)",
+                 "bf16": "bf16 activation storage, tcgen05 kind::f16 (precision='bf16')"}
+        for other in ("tf32", "fp32", "bf16"):
+            if other == args.precision:
+                continue
+            wo = BW.AvTrainWorkload(dev, batch, dict(cfg, precision=other), rank, world)
+            ms_o, _, _, _ = time_workload(wo, sub_steps, 3, with_e2e=False)
+            if rank == 0:
+                line["value_" + other] = {"value": batch * world / (ms_o / 1e3), "unit": unit, "ms_per_step": ms_o, "note": notes[other]}
+            wo.release()
+            del wo
         # (2) log-mel frontend
         lb = 16384
         lcfg = cfg_for("logmel", lb)
