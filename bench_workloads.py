@@ -77,7 +77,9 @@ class LogmelWorkload:
                 "unit": "GB/s", "frac": achieved / peaks["hbm"],
                 "traffic": None if traffic is None else traffic["dram_bytes_per_clip"] * self.batch,
                 "peak_source": peaks["src"], "kernel_ms": ms,
-                "binds": "fp32 issue slots (a 400-point real FFT + mel + log per frame), not HBM: see DESIGN.md section 4"}
+                "binds": "fp32 issue slots and the shared-memory pipe (a 400-point real FFT + mel + log per frame: ~490 warp-instructions and "
+                         "~134 shared-memory wavefronts per frame; ncu: issue 61-65 %, LSU shared wavefronts 62-68 % of peak, DRAM 21 %), "
+                         "not HBM: see DESIGN.md section 4 and profiles/README.md"}
 
     def extra(self):
         return {"clips_per_sec": None}

@@ -2,23 +2,43 @@
 // Replaces audio/utils/audio_processor.py:48-52,60-64 + audio/data_utils/dataset.py:52 (reference:
 // torch.stft on the CPU, one clip at a time inside DataLoader workers).
 //
-// One persistent CTA per SM loops over clips.  A clip's 126 frames go through shared memory in two
-// chunks of 63; the 80x126 log-mel tile stays in shared memory until the clip statistics are known,
-// so HBM sees each waveform once (80 000 B in) and only the cropped result (80*117*4 B out).
+// v1 layout (v0 ran one 512-thread CTA per SM through four block-wide barriers per 63-frame chunk and sat at 0.096
+// of HBM: latency / issue bound at 16 resident warps that all waited on the same barriers):
+//   * a CTA of 8 warps owns one clip at a time (persistent over clips), two CTAs per SM;
+//   * each WARP takes groups of 4 consecutive frames through the FFT pipeline on its own 6.8 KB of shared memory,
+//     with __syncwarp only: waveform staging -> windowed 8-point DFTs (lane = residue r, window and twiddles in
+//     registers) -> 25-point DFTs (lane = frame x k2, exactly 32 tasks) -> even/odd split + power (lane = bin).
+//     The FFT buffer is reused in place for every stage (ordering argued at each step below);
+//   * the eight warps' groups of one round are 32 consecutive frames: after a block barrier the banded mel filters
+//     + log run with lane = frame and a warp-uniform mel (exact tap counts, no divergence, weights broadcast);
+//   * the 880 samples of a warp's NEXT group are fetched with coalesced 16-byte loads into registers while the
+//     current group is in its power / mel stages (HBM latency hidden per warp), then stored to shared memory: HBM
+//     sees a waveform once (the 240-sample overlap of neighbouring groups hits L1 / L2);
+//   * the 80 x 126 log-mel tile stays in shared memory until the clip statistics are known; only the cropped
+//     result (80 x n_out) is written.
+// Per clip: 80 000 B in, 80 * 117 * 4 = 37 440 B out.  What binds: fp32 issue slots (about 13 k thread-instructions
+// per frame), not HBM -- see DESIGN.md section 4.
 #include "common.cuh"
 #include "logmel_core.cuh"
 
 namespace lm {
 
-constexpr int THREADS = 512;
-constexpr int PLD = 203;                                  // power row stride (201 bins, odd-ish padding)
+constexpr int WARPS = 8, THREADS = WARPS * 32;
+constexpr int GROUPS_PER_WARP = GROUPS / WARPS;           // 4
+// A warp's buffer, in floats: [0, 1600) the FFT buffer of its four frames (800 float2), whose first 804 floats later
+// hold the four power rows (stride 201); [804, 1684) the staged samples of the group.  The buffers are 1700 floats
+// apart: 4 (mod 32), which with the odd row stride puts the 32 power rows of a round on 32 different banks.
+constexpr int WAV_OFS = GF * PLD;                         // 804
+constexpr int WBUF = 1700;
+static_assert(GROUPS % WARPS == 0 && WARPS * GF == 32, "a round of groups is 32 consecutive frames");
+static_assert(WAV_OFS % 4 == 0 && WBUF % 4 == 0 && WAV_OFS + GSAMP <= WBUF && WBUF % 32 == 4, "staging / bank layout");
+static_assert(WAV_OFS >= 2 * NHALF * (GF - 2) + 2 * NHALF - HOP * (GF - 1), "stage A in place: see the kernel");
 
 struct Smem {
-    Plan plan;                                            // tables                              9 776 B
-    float2 Z[CHUNK][NHALF];                               // stage A/B buffer (in place)       100 800 B
-    float P[CHUNK][PLD];                                  // power spectra                      51 156 B
-    float L[NMEL][LLD];                                   // log-mel tile of the clip           40 640 B
-    float red[THREADS / 32];
+    float Zb[WARPS][WBUF];                                // per-warp frame pipeline buffers             54 400 B
+    float L[NMEL][LLD];                                   // log-mel tile of the clip                    40 640 B
+    Plan plan;                                            // tables                                       9 776 B
+    float red[WARPS];
     float bcast[2];
 };
 
@@ -36,12 +56,56 @@ __device__ __forceinline__ float block_sum(float v, float* red, float* out_slot)
     return *out_slot;
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+// the 880 padded samples of group g of one clip -> 7 float4 per lane (lane owns float4 number lane + 32 q).
+// Groups 1..30 lie inside the signal: plain 16-byte loads; groups 0 and 31 touch the reflect padding.
+__device__ __forceinline__ void fetch_group(const float* __restrict__ x, int g, int lane, float4 (&pre)[7]) {
+    const int base = GF * HOP * g;                         // padded position of the group's first sample
+    if (g >= 1 && g < GROUPS - 1) {
+        const float4* src = reinterpret_cast<const float4*>(x + (base - PAD));
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            const int i = lane + 32 * q;
+            pre[q] = i < GSAMP / 4 ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            const int p = base + 4 * (lane + 32 * q);
+            pre[q] = lane + 32 * q < GSAMP / 4
+                         ? make_float4(padded_sample(x, p), padded_sample(x, p + 1), padded_sample(x, p + 2), padded_sample(x, p + 3))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+// two banded filters over NQ tap quads each: all loads first, then two independent FMA chains
+template <int NQ>
+__device__ __forceinline__ void mel_pair(const float* __restrict__ pa, const float* __restrict__ pb,
+                                         const float4* __restrict__ wa, const float4* __restrict__ wb,
+                                         float& acc_a, float& acc_b) {
+    float xa[4 * NQ], xb[4 * NQ];
+    float4 ua[NQ], ub[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) { ua[q] = wa[q]; ub[q] = wb[q]; }
+#pragma unroll
+    for (int j = 0; j < 4 * NQ; ++j) { xa[j] = pa[j]; xb[j] = pb[j]; }
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        a = fmaf(xa[4 * q], ua[q].x, a);     b = fmaf(xb[4 * q], ub[q].x, b);
+        a = fmaf(xa[4 * q + 1], ua[q].y, a); b = fmaf(xb[4 * q + 1], ub[q].y, b);
+        a = fmaf(xa[4 * q + 2], ua[q].z, a); b = fmaf(xb[4 * q + 2], ub[q].z, b);
+        a = fmaf(xa[4 * q + 3], ua[q].w, a); b = fmaf(xb[4 * q + 3], ub[q].w, b);
+    }
+    acc_a = a; acc_b = b;
+}
+
+__global__ void __launch_bounds__(THREADS, 2)
 logmel_kernel(const float* __restrict__ wav, const Plan* __restrict__ gplan, float* __restrict__ out,
               int B, int n_out, int mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     {   // tables -> shared memory once per CTA (the CTA is persistent)
         const int4* src = reinterpret_cast<const int4*>(gplan);
@@ -49,73 +113,177 @@ logmel_kernel(const float* __restrict__ wav, const Plan* __restrict__ gplan, flo
         for (int i = tid; i < int(sizeof(Plan) / sizeof(int4)); i += THREADS) dst[i] = src[i];
     }
     __syncthreads();
-    const float* win = S.plan.win;
-    const float2* tw200 = &S.plan.tw200[0][0];
-    const float2* tw400 = S.plan.tw400;
+    const Plan& T = S.plan;
+    float* const Fw = S.Zb[warp];
+    float2* const Zw = reinterpret_cast<float2*>(Fw);        // FFT buffer; its front later holds the power rows
+    float* const wavbuf = Fw + WAV_OFS;                      // staged samples
 
-    for (int clip = blockIdx.x; clip < B; clip += gridDim.x) {
-        const float* x = wav + size_t(clip) * NSAMP;
+    float4 pre[7];
+    int clip = blockIdx.x;
+    if (clip < B) fetch_group(wav + size_t(clip) * NSAMP, warp, lane, pre);
 
-        for (int chunk = 0; chunk < NFRAMES / CHUNK; ++chunk) {
-            const int f0 = chunk * CHUNK;
-            // A: windowed load + 8-point DFTs + outer twiddles
-            for (int task = tid; task < CHUNK * 25; task += THREADS) {
-                const int f = task / 25, r = task - f * 25;
-                stage_a(x, f0 + f, r, win, tw200, S.Z[f]);
-            }
-            __syncthreads();
-            // B: 25-point DFTs, in place.  The 8 tasks of a frame sit in one warp, so a warp-level
-            // barrier between the loads and the stores is enough.
+    for (; clip < B; clip += gridDim.x) {
+#pragma unroll 1
+        for (int gi = 0; gi < GROUPS_PER_WARP; ++gi) {
+            const int g = warp + WARPS * gi;
+            // ---- staging: registers -> the buffer's sample area (disjoint from the FFT buffer and the power rows)
+#pragma unroll
+            for (int q = 0; q < 7; ++q)
+                if (lane + 32 * q < GSAMP / 4) reinterpret_cast<float4*>(wavbuf)[lane + 32 * q] = pre[q];
+            __syncwarp();
+
+            // ---- stage A, one frame per round, lane = residue r (25 of 32 lanes).  Frame f reads floats
+            // [804 + 160 f, +400) of the buffer and writes Y to [400 f, +400): a round's stores never touch samples
+            // that a LATER round still reads (f = 2 ends at 1200, frame 3 starts at 1284), and inside a round every
+            // lane has loaded before any lane stores (the __syncwarp).  The previous round's stage D, which read the
+            // power rows that Y overwrites, ended with a block barrier.
             {
-                const int f = tid >> 3, k2 = tid & 7;
-                float2 y[25], z[25];
-                if (f < CHUNK) { stage_b_load(S.Z[f], k2, y); dft25(y, z); }
-                __syncwarp();
-                if (f < CHUNK) stage_b_store(S.Z[f], k2, z);
+                const int r = lane < 25 ? lane : 24;
+                float w16[16];
+                float2 tw7[7];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float2 ww = *reinterpret_cast<const float2*>(&T.win[2 * (r + 25 * j)]);
+                    w16[2 * j] = ww.x; w16[2 * j + 1] = ww.y;
+                }
+#pragma unroll
+                for (int k2 = 1; k2 < 8; ++k2) tw7[k2 - 1] = T.tw200[k2][r];
+#pragma unroll 1
+                for (int f = 0; f < GF; ++f) {
+                    float2 v[8];
+                    const float2* xf = reinterpret_cast<const float2*>(wavbuf + HOP * f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = xf[r + 25 * j];
+                    __syncwarp();
+                    stage_a_regs(v, w16, tw7);
+                    if (lane < 25) {
+                        float2* Yf = Zw + NHALF * f;
+#pragma unroll
+                        for (int k2 = 0; k2 < 8; ++k2) Yf[k2 * 25 + r] = v[k2];
+                    }
+                }
             }
-            __syncthreads();
-            // C: even/odd split + power
-            for (int task = tid; task < CHUNK * 101; task += THREADS) {
-                const int f = task / 101, k = task - f * 101;
-                stage_c(S.Z[f], k, tw400, S.P[f]);
-            }
-            __syncthreads();
-            // D: mel filters + log
-            for (int task = tid; task < CHUNK * NMEL; task += THREADS) {
-                const int f = task / NMEL, m = task - f * NMEL;
-                S.L[m][f0 + f] = stage_d(S.P[f], m, S.plan.mel_lo, S.plan.mel_n, &S.plan.mel_w[0][0]);
-            }
-            __syncthreads();
-        }
+            __syncwarp();
 
+            // ---- stage B: 25-point DFTs in place, lane = (frame, k2): 32 tasks.  Loads: the 8 lanes of a frame are
+            // 50 words apart, the frames of a half-warp 400 words: 16 different bank pairs.  Stores: 8 consecutive float2.
+            {
+                float2* Zf = Zw + NHALF * (lane >> 3);
+                const int k2 = lane & 7;
+                float2 y[25], z[25];
+                stage_b_load(Zf, k2, y);
+                dft25(y, z);
+                __syncwarp();
+                stage_b_store(Zf, k2, z);
+            }
+            __syncwarp();
+
+            // ---- the warp's next group (possibly of the CTA's next clip) starts its way from HBM now and lands in
+            // registers while stages C and D run
+            {
+                int nclip = clip, ng = g + WARPS;
+                if (gi == GROUPS_PER_WARP - 1) { nclip = clip + gridDim.x; ng = warp; }
+                if (nclip < B) fetch_group(wav + size_t(nclip) * NSAMP, ng, lane, pre);
+            }
+
+            // ---- stage C: even/odd split + power, lane = bin k (k = lane + 32 j <= 100) for the four frames.  All
+            // powers are formed in registers first: the power rows (4 x 201 floats) overwrite the front of the FFT buffer.
+            {
+                float2 pw[4][GF];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = lane + 32 * j;
+                    if (k <= 100) {
+                        const float2 tw = T.tw400[k];
+#pragma unroll
+                        for (int f = 0; f < GF; ++f) {
+                            const float2* Zf = Zw + NHALF * f;
+                            pw[j][f] = stage_c_pair(Zf[k], Zf[k == 0 ? 0 : NHALF - k], tw);
+                        }
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = lane + 32 * j;
+                    if (k <= 100) {
+#pragma unroll
+                        for (int f = 0; f < GF; ++f) {
+                            Fw[PLD * f + k] = pw[j][f].x;
+                            Fw[PLD * f + NHALF - k] = pw[j][f].y;   // k == 100: the same bin, the same value
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+
+            // ---- stage D for the round's 32 frames (frame 32 gi + lane; its power row lives in warp lane / 4's buffer):
+            // banded mel filters + log with a warp-uniform mel m = warp + 8 s, i.e. exact tap counts and broadcast weights.
+            // Same summation order as stage_d().
+            __syncthreads();                               // the eight warps' power rows are complete
+            {
+                const float* Pf = S.Zb[lane >> 2] + PLD * (lane & 3);
+                const int t = 32 * gi + lane;
+                // two filters (m, m + 8: close tap counts) per iteration = two independent FMA chains; the longer one
+                // sets the trip count, the shorter one adds exact zeros (zero weights, finite in-row power values)
+#pragma unroll 1
+                for (int ma = warp; ma < NMEL; ma += 2 * WARPS) {
+                    const int mb = ma + WARPS;
+                    const float* pa = Pf + T.mel_lo[ma];
+                    const float* pb = Pf + T.mel_lo[mb];
+                    const float4* wa = reinterpret_cast<const float4*>(T.mel_w[ma]);
+                    const float4* wb = reinterpret_cast<const float4*>(T.mel_w[mb]);
+                    const int nq = max(T.mel_nq[ma], T.mel_nq[mb]);
+                    float acc_a, acc_b;
+                    switch (nq) {                              // warp-uniform; each case is straight-line code
+                        case 1: mel_pair<1>(pa, pb, wa, wb, acc_a, acc_b); break;
+                        case 2: mel_pair<2>(pa, pb, wa, wb, acc_a, acc_b); break;
+                        case 3: mel_pair<3>(pa, pb, wa, wb, acc_a, acc_b); break;
+                        default: mel_pair<4>(pa, pb, wa, wb, acc_a, acc_b); break;
+                    }
+                    if (t < NFRAMES) { S.L[ma][t] = log_eps(acc_a); S.L[mb][t] = log_eps(acc_b); }
+                }
+            }
+            __syncthreads();                               // the power rows may be overwritten (next round's stage A)
+        }
+        // ---- statistics over all 80 x 126 values (two-pass, shifted by L[0][0] so that a constant tile -- a silent
+        // clip -- gives exactly zero deviations), normalise, crop, write.  Thread = (mel row warp + 8 a, frames lane + 32 b).
         float* o = out + size_t(clip) * NMEL * n_out;
         if (mode == LR_LOGMEL_RAW) {
-            for (int i = tid; i < NMEL * NFRAMES; i += THREADS) {
-                const int m = i / NFRAMES, t = i - m * NFRAMES;
-                o[i] = S.L[m][t];
-            }
+#pragma unroll 1
+            for (int m = warp; m < NMEL; m += WARPS)
+                for (int t = lane; t < NFRAMES; t += 32) o[m * NFRAMES + t] = S.L[m][t];
         } else {
-            // statistics over all 80 x 126 values, two-pass, shifted by L[0][0] so that a constant
-            // tile (silent clip) gives exactly zero deviations.
             const float pivot = S.L[0][0];
+            float v[NMEL / WARPS][4];
             float s = 0.f;
-            for (int i = tid; i < NMEL * NFRAMES; i += THREADS) {
-                const int m = i / NFRAMES, t = i - m * NFRAMES;
-                s += S.L[m][t] - pivot;
-            }
+#pragma unroll
+            for (int a = 0; a < NMEL / WARPS; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int t = lane + 32 * b;
+                    v[a][b] = t < NFRAMES ? S.L[warp + WARPS * a][t] - pivot : 0.f;
+                    s += v[a][b];
+                }
             const float mean_d = block_sum(s, S.red, &S.bcast[0]) * (1.0f / float(NMEL * NFRAMES));
             float q = 0.f;
-            for (int i = tid; i < NMEL * NFRAMES; i += THREADS) {
-                const int m = i / NFRAMES, t = i - m * NFRAMES;
-                const float d = (S.L[m][t] - pivot) - mean_d;
-                q = fmaf(d, d, q);
-            }
+#pragma unroll
+            for (int a = 0; a < NMEL / WARPS; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const float d = v[a][b] - mean_d;
+                    v[a][b] = d;
+                    if (lane + 32 * b < NFRAMES) q = fmaf(d, d, q);
+                }
             const float var = block_sum(q, S.red, &S.bcast[1]) * (1.0f / float(NMEL * NFRAMES - 1));
             const float inv = 1.0f / (sqrtf(var) + 1e-9f);
-            for (int i = tid; i < NMEL * n_out; i += THREADS) {
-                const int m = i / n_out, t = i - m * n_out;
-                o[i] = ((S.L[m][t] - pivot) - mean_d) * inv;
-            }
+#pragma unroll
+            for (int a = 0; a < NMEL / WARPS; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int t = lane + 32 * b;
+                    if (t < n_out) o[(warp + WARPS * a) * n_out + t] = v[a][b] * inv;
+                }
         }
         __syncthreads();   // L is rewritten by the next clip
     }
@@ -145,17 +313,8 @@ __global__ void logmel_plan_kernel(const float* __restrict__ window, const float
         sincospi(-2.0 * double(k) / 400.0, &sn, &cs);
         plan->tw400[k] = make_float2(float(cs), float(sn));
     }
-    for (int m = tid; m < NMEL; m += blockDim.x) {
-        int lo = -1, hi = -1;
-        for (int k = 0; k < NBINS; ++k)
-            if (fb[k * NMEL + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
-        if (lo < 0) { lo = 0; hi = -1; }
-        int n = hi - lo + 1;
-        if (n > MAXTAPS) { plan->status = 1; n = MAXTAPS; }
-        plan->mel_lo[m] = lo;
-        plan->mel_n[m] = n;
-        for (int j = 0; j < MAXTAPS; ++j) plan->mel_w[j][m] = (j < n) ? fb[(lo + j) * NMEL + m] : 0.f;
-    }
+    for (int m = tid; m < NMEL; m += blockDim.x)
+        if (!plan_mel(fb, m, &plan->mel_lo[m], &plan->mel_nq[m], plan->mel_w[m])) plan->status = 1;
 }
 
 // ---- normalize_spectrogram on its own ---------------------------------------------------------
@@ -205,7 +364,7 @@ extern "C" int lr_logmel_fwd(const float* wav, const void* plan, float* out, int
     static const int smem = int(sizeof(lm::Smem));
     const cudaError_t attr = lr::ensure_max_dynamic_smem(lm::logmel_kernel, smem);
     if (attr != cudaSuccess) return lr::fail(LR_ECUDA, "logmel smem attribute: %s", cudaGetErrorString(attr));
-    const int grid = B < lr::sm_count() ? B : lr::sm_count();
+    const int grid = B < 2 * lr::sm_count() ? B : 2 * lr::sm_count();        // two resident CTAs per SM
     lm::logmel_kernel<<<grid, lm::THREADS, smem, stream>>>(wav, static_cast<const lm::Plan*>(plan), out, B,
                                                            n_out, mode);
     lr::count_launch();

@@ -9,26 +9,30 @@
 //   so only 201 bins are ever formed.  Power -> banded (<=16 tap) mel filters -> ln(. + 1e-9).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstddef>
 
 namespace lm {
 
 constexpr int NFFT = 400, HOP = 160, NHALF = 200, NBINS = 201, NMEL = 80;
 constexpr int NSAMP = 20000, NFRAMES = 126, PAD = 200;
 constexpr int MAXTAPS = 16;
-constexpr int CHUNK = 63;             // frames per pass through shared memory (126 = 2 x 63)
-constexpr int LLD = 127;              // leading dimension of the 80 x 126 log-mel tile (odd: no bank conflicts)
+constexpr int GF = 4;                               // frames per warp group: 4 frames x 8 residues = one 25-point DFT per lane
+constexpr int GROUPS = (NFRAMES + GF - 1) / GF;     // 32 groups per clip (the last one holds frames 124, 125)
+constexpr int GSAMP = (GF - 1) * HOP + NFFT;        // 880 consecutive padded samples cover a group's four frames
+constexpr int PLD = NBINS;                          // power row stride inside a group (odd)
+constexpr int LLD = 127;              // leading dimension of the 80 x 126 log-mel tile
 
 struct Plan {
     float win[NFFT];                  // hann[n] * 0.5 / sqrt(sum hann^2)   (0.5 = even/odd split factor)
     float2 tw200[8][25];              // W200^(r*k2), [k2][r]
+    alignas(16) float mel_w[NMEL][MAXTAPS];   // the window's weights fb[mel_lo + j][m] (zero outside the filter)
     float2 tw400[101];                // W400^k, k = 0..100
-    int mel_lo[NMEL];                 // first bin with a non-zero weight
-    int mel_n[NMEL];                  // number of taps (<= MAXTAPS)
-    float mel_w[MAXTAPS][NMEL];       // weights, zero padded
+    int mel_lo[NMEL];                 // first bin of the filter's 16-bin window: min(first non-zero bin, 201 - 16)
+    int mel_nq[NMEL];                 // tap quads to sum: ceil((last non-zero bin + 1 - mel_lo) / 4), 1..4
     int status;                       // 0 ok, 1 = a filter had more than MAXTAPS taps
     int pad_;
 };
-static_assert(sizeof(Plan) % 16 == 0, "Plan is copied with 16-byte vectors");
+static_assert(sizeof(Plan) % 16 == 0 && offsetof(Plan, mel_w) % 16 == 0, "Plan is copied with 16-byte vectors");
 
 #define LM_HD __host__ __device__ __forceinline__
 
@@ -131,6 +135,23 @@ LM_HD void dft25(const float2* y, float2* z) {
     }
 }
 
+// padded position p (0 .. NSAMP + 2 PAD - 1) -> sample under reflect padding; 0 beyond the padded signal (the two
+// frames that pad the last group)
+LM_HD float padded_sample(const float* __restrict__ wav, int p) {
+    return p < NSAMP + 2 * PAD ? wav[reflect_index(p)] : 0.f;
+}
+
+// ---- stage A in registers: v[j] = the frame's sample pair at complex point r + 25 j (already reflect-padded),
+// w16[2j], w16[2j+1] = the window at those two samples, tw7[k2-1] = W200^(r k2).  Out: the twiddled 8-point DFT,
+// v[k2] = Y[k2*25 + r].
+LM_HD void stage_a_regs(float2* v, const float* w16, const float2* tw7) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = make_float2(v[j].x * w16[2 * j], v[j].y * w16[2 * j + 1]);
+    dft8(v);
+#pragma unroll
+    for (int k2 = 1; k2 < 8; ++k2) v[k2] = cmul(v[k2], tw7[k2 - 1]);
+}
+
 // ---- stage A: task (frame f, residue r): windowed load, 8-point DFTs, outer twiddle ------------
 // Y layout per frame: Y[k2*25 + r] (float2).  `wav` is one clip (NSAMP floats), t the frame index.
 LM_HD void stage_a(const float* __restrict__ wav, int t, int r, const float* __restrict__ win,
@@ -168,26 +189,55 @@ LM_HD void stage_b_store(float2* __restrict__ Zf, int k2, const float2* z) {
 }
 
 // ---- stage C: task (frame f, k in 0..100): power of bins k and 200-k ---------------------------
-LM_HD void stage_c(const float2* __restrict__ Zf, int k, const float2* __restrict__ tw400,
-                   float* __restrict__ Pf) {
-    const float2 zk = Zf[k];
-    const float2 zn = Zf[k == 0 ? 0 : NHALF - k];
+// zk = Z[k], zn = Z[200 - k] (Z[0] for k = 0), tw = W400^k  ->  (|X[k]|^2, |X[200-k]|^2)
+LM_HD float2 stage_c_pair(float2 zk, float2 zn, float2 tw) {
     const float2 E = make_float2(zk.x + zn.x, zk.y - zn.y);
     const float2 O = make_float2(zk.y + zn.y, zn.x - zk.x);
-    const float2 T = cmul(tw400[k], O);
+    const float2 T = cmul(tw, O);
     const float ar = E.x + T.x, ai = E.y + T.y;
     const float br = E.x - T.x, bi = E.y - T.y;
-    Pf[k] = ar * ar + ai * ai;
-    Pf[NHALF - k] = br * br + bi * bi;      // k == 100 writes the same bin twice with the same value
+    return make_float2(ar * ar + ai * ai, br * br + bi * bi);
+}
+LM_HD void stage_c(const float2* __restrict__ Zf, int k, const float2* __restrict__ tw400,
+                   float* __restrict__ Pf) {
+    const float2 pw = stage_c_pair(Zf[k], Zf[k == 0 ? 0 : NHALF - k], tw400[k]);
+    Pf[k] = pw.x;
+    Pf[NHALF - k] = pw.y;                   // k == 100 writes the same bin twice with the same value
+}
+
+// ln(acc + 1e-9): on the device lg2.approx * ln 2 (relative error 2^-22 on values of magnitude <= 21: far inside the
+// 1e-4 bar), on the host (CPU emulation in the test-suite) the C library's logf
+LM_HD float log_eps(float acc) {
+#ifdef __CUDA_ARCH__
+    return __logf(acc + 1e-9f);
+#else
+    return logf(acc + 1e-9f);
+#endif
 }
 
 // ---- stage D: task (frame f, mel m): banded filter + log --------------------------------------
+// One filter's entry of the plan from the [201][80] filterbank: a 16-bin window that always lies inside the power row,
+// so the kernel needs neither bounds checks nor predicates; zero weights around the filter add exact zeros.
+// Returns false if the filter has more than MAXTAPS taps.
+LM_HD bool plan_mel(const float* __restrict__ fb, int m, int* lo_out, int* nq_out, float* w16) {
+    int lo = -1, hi = -1;
+    for (int k = 0; k < NBINS; ++k)
+        if (fb[k * NMEL + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
+    if (lo < 0) { lo = 0; hi = 0; }
+    const bool ok = hi - lo + 1 <= MAXTAPS;
+    if (!ok) hi = lo + MAXTAPS - 1;
+    const int w0 = lo < NBINS - MAXTAPS ? lo : NBINS - MAXTAPS;
+    *lo_out = w0;
+    *nq_out = (hi + 1 - w0 + 3) / 4;
+    for (int j = 0; j < MAXTAPS; ++j) w16[j] = (w0 + j >= lo && w0 + j <= hi) ? fb[(w0 + j) * NMEL + m] : 0.f;
+    return ok;
+}
 LM_HD float stage_d(const float* __restrict__ Pf, int m, const int* __restrict__ mel_lo,
-                    const int* __restrict__ mel_n, const float* __restrict__ mel_w /*[MAXTAPS][NMEL]*/) {
-    const int lo = mel_lo[m], n = mel_n[m];
+                    const int* __restrict__ mel_nq, const float* __restrict__ mel_w /*[NMEL][MAXTAPS]*/) {
+    const float* pp = Pf + mel_lo[m];
     float acc = 0.f;
-    for (int j = 0; j < n; ++j) acc = fmaf(Pf[lo + j], mel_w[j * NMEL + m], acc);
-    return logf(acc + 1e-9f);
+    for (int j = 0; j < 4 * mel_nq[m]; ++j) acc = fmaf(pp[j], mel_w[m * MAXTAPS + j], acc);
+    return log_eps(acc);
 }
 
 }  // namespace lm

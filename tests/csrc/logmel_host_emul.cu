@@ -24,32 +24,48 @@ static void build_plan(const float* window, const float* fb, Plan& p) {
         p.tw400[k] = make_float2(float(std::cos(a)), float(std::sin(a)));
     }
     p.status = 0;
-    for (int m = 0; m < NMEL; ++m) {
-        int lo = -1, hi = -1;
-        for (int k = 0; k < NBINS; ++k)
-            if (fb[k * NMEL + m] != 0.f) { if (lo < 0) lo = k; hi = k; }
-        if (lo < 0) { lo = 0; hi = -1; }
-        int n = hi - lo + 1;
-        if (n > MAXTAPS) { p.status = 1; n = MAXTAPS; }
-        p.mel_lo[m] = lo; p.mel_n[m] = n;
-        for (int j = 0; j < MAXTAPS; ++j) p.mel_w[j][m] = j < n ? fb[(lo + j) * NMEL + m] : 0.f;
-    }
+    for (int m = 0; m < NMEL; ++m)
+        if (!plan_mel(fb, m, &p.mel_lo[m], &p.mel_nq[m], p.mel_w[m])) p.status = 1;
 }
 
-// wav [20000] -> raw log-mel [80][126]; returns plan.status
+// wav [20000] -> raw log-mel [80][126]; returns plan.status.  Driven the way the kernel's warps drive it: groups of
+// four frames, 880 staged (reflect-padded) samples per group, stage A on registers with the lane's window / twiddle
+// values, 25-point DFTs in place, powers formed from (Z[k], Z[200-k]) pairs, banded mel filters.
 extern "C" int logmel_host_emul(const float* wav, const float* window, const float* fb, float* out) {
     Plan p;
     build_plan(window, fb, p);
+    std::vector<float> stage(GSAMP);
     std::vector<float2> Z(NHALF);
     std::vector<float> P(NBINS + 2);
-    for (int t = 0; t < NFRAMES; ++t) {
-        for (int r = 0; r < 25; ++r) stage_a(wav, t, r, p.win, &p.tw200[0][0], Z.data());
-        float2 y[8][25], z[8][25];
-        for (int k2 = 0; k2 < 8; ++k2) { stage_b_load(Z.data(), k2, y[k2]); dft25(y[k2], z[k2]); }
-        for (int k2 = 0; k2 < 8; ++k2) stage_b_store(Z.data(), k2, z[k2]);
-        for (int k = 0; k <= 100; ++k) stage_c(Z.data(), k, p.tw400, P.data());
-        for (int m = 0; m < NMEL; ++m)
-            out[m * NFRAMES + t] = stage_d(P.data(), m, p.mel_lo, p.mel_n, &p.mel_w[0][0]);
+    for (int g = 0; g < GROUPS; ++g) {
+        for (int i = 0; i < GSAMP; ++i) stage[i] = padded_sample(wav, GF * HOP * g + i);
+        for (int f = 0; f < GF; ++f) {
+            const int t = GF * g + f;
+            if (t >= NFRAMES) break;
+            const float2* xf = reinterpret_cast<const float2*>(stage.data() + HOP * f);
+            for (int r = 0; r < 25; ++r) {
+                float w16[16];
+                float2 tw7[7], v[8];
+                for (int j = 0; j < 8; ++j) {
+                    w16[2 * j] = p.win[2 * (r + 25 * j)];
+                    w16[2 * j + 1] = p.win[2 * (r + 25 * j) + 1];
+                    v[j] = xf[r + 25 * j];
+                }
+                for (int k2 = 1; k2 < 8; ++k2) tw7[k2 - 1] = p.tw200[k2][r];
+                stage_a_regs(v, w16, tw7);
+                for (int k2 = 0; k2 < 8; ++k2) Z[k2 * 25 + r] = v[k2];
+            }
+            float2 y[8][25], z[8][25];
+            for (int k2 = 0; k2 < 8; ++k2) { stage_b_load(Z.data(), k2, y[k2]); dft25(y[k2], z[k2]); }
+            for (int k2 = 0; k2 < 8; ++k2) stage_b_store(Z.data(), k2, z[k2]);
+            for (int k = 0; k <= 100; ++k) {
+                const float2 pw = stage_c_pair(Z[k], Z[k == 0 ? 0 : NHALF - k], p.tw400[k]);
+                P[k] = pw.x;
+                P[NHALF - k] = pw.y;
+            }
+            for (int m = 0; m < NMEL; ++m)
+                out[m * NFRAMES + t] = stage_d(P.data(), m, p.mel_lo, p.mel_nq, &p.mel_w[0][0]);
+        }
     }
     return p.status;
 }
