@@ -21,14 +21,23 @@
 //               per-column sum / sum of squares (train-mode BatchNorm statistics) read column-wise from the slab,
 //               shared-memory float atomics, one double atomic per column and CTA
 // Several CTAs are co-resident per SM (smem <= 2/SM for BN <= 96), so one CTA's epilogue overlaps another's loads.
+//
+// Tile batching (P::mt > 1, ksplit == 1): for the tall-skinny 1x1 convolutions (M up to 1.8 M rows, K and N <= 96: one or
+// two k-blocks per tile) a CTA's life was a chain of latencies -- barrier init, TMEM allocation, descriptor fetch, one
+// TMA round trip, one MMA, the epilogue, the store drain, 144 statistic atomics -- about 9 us for 20 KB of traffic, and
+// 3 509 .. 14 036 such CTAs per launch.  With mt consecutive 128-row tiles per CTA the producer streams all their
+// k-blocks through the same ring, each tile accumulates in its own TMEM columns and signals its own barrier, the
+// epilogue warps drain tile t while the loads / MMAs of tile t+1.. are in flight, and the BatchNorm statistics leave
+// once per CTA (mt times fewer atomics).
 #include <cuda.h>
 #include <cstring>
+#include <cstdlib>
 
 #include "nn_common.cuh"
 
 namespace tc {
 
-constexpr int BM = 128, MAX_STAGES = 4, THREADS = 192;
+constexpr int BM = 128, MAX_STAGES = 4, THREADS = 192, MAX_MT = 8;
 constexpr int A_STAGE_BYTES = BM * 128;        // 16 KB: 128 rows of one 128-byte swizzle span
 // per operand type: elements per 128-byte span = reduce-elements per stage (K-major) = MN-elements per chunk (MN-major)
 template <typename TO> struct Op { static constexpr int BK = 128 / (int)sizeof(TO); };
@@ -37,6 +46,8 @@ constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;                    // four 32-
 
 struct P {
     int M, N, K, BN, stages;
+    int mt;              // consecutive M tiles per CTA (1 unless ksplit == 1 and the output leaves through TMA)
+    int tile_cols;       // TMEM columns per tile
     int kchunk;          // reduce-dimension elements handled by one CTA (multiple of BK); gridDim.z CTAs split K
     int atomic_out;      // 1: C += tile with red.global.add (split-K wgrad); bias / act / residual / stats unused
     int tma_out;         // 1: tiles leave through TMA (store, or reduce-add when accum_out) from swizzled 32x32 boxes
@@ -178,12 +189,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t CHUNK_BYTES = (uint32_t)BK * 128u;  // one MN-major chunk: BK reduce-rows of 128 bytes
     static_assert(sizeof(TC) == 4 || sizeof(TC) == 2, "output is fp32 or bf16");
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 1];
+    __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + MAX_MT];
     __shared__ uint32_t tmem_base_slot;
     __shared__ __align__(16) float s_sum[4][256], s_sq[4][256], s_bias[256];   // statistics: one row per epilogue warp
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.BN;
+    const int m_first = blockIdx.x * p.mt * BM, n0 = blockIdx.y * p.BN;
+    const int nt = min(p.mt, (p.M - m_first + BM - 1) / BM);            // tiles of this CTA (>= 1)
     const int kbeg = blockIdx.z * p.kchunk;
     const int kend = min(p.K, kbeg + p.kchunk);
     const int num_kb = (kend - kbeg + BK - 1) / BK;
@@ -194,8 +206,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[MAX_STAGES]);
     const uint32_t tmem_full = smem_u32(&bars[2 * MAX_STAGES]);
     uint32_t tmem_cols = 32;
-    // the epilogue reads 32 columns at a time (fp32 out) or two such loads per 64-column box (bf16 out)
-    while (tmem_cols < (uint32_t)(sizeof(TC) == 2 ? ((p.BN + 63) & ~63) : ((p.BN + 31) & ~31))) tmem_cols <<= 1;
+    // the epilogue reads 32 columns at a time (fp32 out) or two such loads per 64-column box (bf16 out): tile_cols
+    while (tmem_cols < (uint32_t)(p.mt * p.tile_cols)) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) LR_STAMP(0);
     for (int i = threadIdx.x; i < 256; i += THREADS) {
@@ -205,7 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        mbar_init(tmem_full, 1);
+        for (int t = 0; t < p.mt; ++t) mbar_init(tmem_full + 8 * t, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -221,52 +233,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                if (kb < 6) LR_STAMP(2 + kb);
-                const uint32_t a_dst = tiles + s * stage_bytes, b_dst = a_dst + A_STAGE_BYTES;
-                mbar_expect_tx(full0 + 8 * s, stage_bytes);
-                const int k0 = kbeg + kb * BK;
-                if (A_MN) {
+            int it = 0;
+            for (int t = 0; t < nt; ++t) {
+                const int m0 = m_first + t * BM;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    if (it < 6) LR_STAMP(2 + it);
+                    const uint32_t a_dst = tiles + s * stage_bytes, b_dst = a_dst + A_STAGE_BYTES;
+                    mbar_expect_tx(full0 + 8 * s, stage_bytes);
+                    const int k0 = kbeg + kb * BK;
+                    if (A_MN) {
 #pragma unroll
-                    for (int c = 0; c < BM / BK; ++c) tma_load_2d(a_dst + c * CHUNK_BYTES, &tmA, full0 + 8 * s, m0 + c * BK, k0);
-                } else {
-                    tma_load_2d(a_dst, &tmA, full0 + 8 * s, k0, m0);
-                }
-                if (B_MN) {
-                    for (int c = 0; c < b_chunks; ++c) tma_load_2d(b_dst + c * CHUNK_BYTES, &tmB, full0 + 8 * s, n0 + c * BK, k0);
-                } else {
-                    tma_load_2d(b_dst, &tmB, full0 + 8 * s, k0, n0);
+                        for (int c = 0; c < BM / BK; ++c) tma_load_2d(a_dst + c * CHUNK_BYTES, &tmA, full0 + 8 * s, m0 + c * BK, k0);
+                    } else {
+                        tma_load_2d(a_dst, &tmA, full0 + 8 * s, k0, m0);
+                    }
+                    if (B_MN) {
+                        for (int c = 0; c < b_chunks; ++c) tma_load_2d(b_dst + c * CHUNK_BYTES, &tmB, full0 + 8 * s, n0 + c * BK, k0);
+                    } else {
+                        tma_load_2d(b_dst, &tmB, full0 + 8 * s, k0, n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = H ? make_idesc_bf16(p.BN, A_MN, B_MN) : make_idesc_tf32(p.BN, A_MN, B_MN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                mbar_wait(full0 + 8 * s, ph);
-                if (kb < 6) LR_STAMP(8 + kb);
-                fence_after();
-                const uint32_t a_src = tiles + s * stage_bytes, b_src = a_src + A_STAGE_BYTES;
-                const uint64_t adesc = A_MN ? (H ? make_desc_mn_sw128_b16(a_src) : make_desc_mn_sw128(a_src)) : make_desc_k_sw128(a_src);
-                const uint64_t bdesc = B_MN ? (H ? make_desc_mn_sw128_b16(b_src) : make_desc_mn_sw128(b_src)) : make_desc_k_sw128(b_src);
-                // one MMA consumes 32 bytes of reduce-depth (8 tf32 / 16 bf16 elements): K-major: 32 bytes along the
-                // swizzled row (2 address units); MN-major: 8 / 16 reduce-rows of 128 bytes (64 / 128 address units)
-                constexpr int MN_STEP = H ? 128 : 64;
+            int it = 0;
+            for (int t = 0; t < nt; ++t) {
+                const uint32_t tmem_t = tmem_d + (uint32_t)(t * p.tile_cols);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(full0 + 8 * s, ph);
+                    if (it < 6) LR_STAMP(8 + it);
+                    fence_after();
+                    const uint32_t a_src = tiles + s * stage_bytes, b_src = a_src + A_STAGE_BYTES;
+                    const uint64_t adesc = A_MN ? (H ? make_desc_mn_sw128_b16(a_src) : make_desc_mn_sw128(a_src)) : make_desc_k_sw128(a_src);
+                    const uint64_t bdesc = B_MN ? (H ? make_desc_mn_sw128_b16(b_src) : make_desc_mn_sw128(b_src)) : make_desc_k_sw128(b_src);
+                    // one MMA consumes 32 bytes of reduce-depth (8 tf32 / 16 bf16 elements): K-major: 32 bytes along the
+                    // swizzled row (2 address units); MN-major: 8 / 16 reduce-rows of 128 bytes (64 / 128 address units)
+                    constexpr int MN_STEP = H ? 128 : 64;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (H) mma_bf16(tmem_d, adesc + (A_MN ? MN_STEP : 2) * k, bdesc + (B_MN ? MN_STEP : 2) * k, idesc,
-                                    (kb > 0 || k > 0) ? 1u : 0u);
-                    else mma_tf32(tmem_d, adesc + (A_MN ? MN_STEP : 2) * k, bdesc + (B_MN ? MN_STEP : 2) * k, idesc,
-                                  (kb > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {
+                        if (H) mma_bf16(tmem_t, adesc + (A_MN ? MN_STEP : 2) * k, bdesc + (B_MN ? MN_STEP : 2) * k, idesc,
+                                        (kb > 0 || k > 0) ? 1u : 0u);
+                        else mma_tf32(tmem_t, adesc + (A_MN ? MN_STEP : 2) * k, bdesc + (B_MN ? MN_STEP : 2) * k, idesc,
+                                      (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    mma_commit(empty0 + 8 * s);
                 }
-                mma_commit(empty0 + 8 * s);
+                mma_commit(tmem_full + 8 * t);
             }
-            mma_commit(tmem_full);
             LR_STAMP(14);
         }
     } else {
@@ -277,16 +297,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // 68 floats: conflict-free both ways) and then writes whole contiguous row segments, 512 bytes per
         // instruction.  The slabs reuse the pipeline buffers, which are idle once the last MMA has completed.
         const int q = warp & 3;
-        const int row0 = m0 + q * 32;
-        const int rv = max(0, min(32, p.M - row0));                         // valid rows of this warp's slab
-        float* slab = reinterpret_cast<float*>(smem_raw + (tiles - smem_u32(smem_raw))) + q * 32 * EPI_PITCH;
-        mbar_wait(tmem_full, 0);
-        if (threadIdx.x == 64) LR_STAMP(15);
-        fence_after();
         float* const Cf = static_cast<float*>(p.C);                          // used by the fp32-output paths only
         const float* const Rf = static_cast<const float*>(p.R);
         const bool vec_c = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         const bool vec_r = p.R && ((p.ldr & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.R) & 15) == 0);
+        // staging boxes: behind the pipeline ring when tiles are batched (the ring is still busy with later tiles),
+        // else on top of it (idle once the only tile's last MMA has completed)
+        const uint32_t epi0 = p.mt > 1 ? tiles + (uint32_t)p.stages * stage_bytes : tiles;
+        int nbox = 0;                                                        // runs across tiles: two boxes in flight
+        for (int t = 0; t < nt; ++t) {
+        const int m0 = m_first + t * BM;
+        const int row0 = m0 + q * 32;
+        const int rv = max(0, min(32, p.M - row0));                         // valid rows of this warp's slab
+        const uint32_t tmem_t = tmem_d + (uint32_t)(t * p.tile_cols);
+        float* slab = reinterpret_cast<float*>(smem_raw + (tiles - smem_u32(smem_raw))) + q * 32 * EPI_PITCH;
+        mbar_wait(tmem_full + 8 * t, 0);
+        if (threadIdx.x == 64) LR_STAMP(15);
+        fence_after();
         if constexpr (sizeof(TC) == 2) {
             // ---- bf16 output: 32 rows x 64 columns per box (again one 128-byte swizzled row per tile row).  A lane
             // owns its row: two 32-column TMEM loads -> bias / activation (+ residual, read straight from HBM: the
@@ -295,20 +322,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // taken from the ROUNDED values (what the consumer will normalise): lane L sums columns 2L, 2L+1 down the
             // 32 rows, one conflict-free 4-byte read per row.
             const nn::bf16* const Rh = static_cast<const nn::bf16*>(p.R);
-            const uint32_t stg0 = tiles + (uint32_t)q * 8192u;
+            const uint32_t stg0 = epi0 + (uint32_t)q * 8192u;
             uint8_t* stg0_g = smem_raw + (stg0 - smem_u32(smem_raw));
-            int nbox = 0;
             const int plain_out = (p.bias == nullptr && p.act == LR_ACT_NONE) ? 1 : 0;
             for (int c0 = 0; c0 < p.BN; c0 += 64, ++nbox) {
                 const int n = n0 + c0;
                 if (n >= p.N) break;                                         // warp-uniform
+                const int ncol = min(64, p.BN - c0);                         // columns of this box: 16, 32, 48 or 64
                 const uint32_t buf = (uint32_t)(nbox & 1) * 4096u;
                 if (nbox >= 2) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }
                 uint8_t* rowp = stg0_g + buf + lane * 128;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
+                    if (32 * h >= ncol) break;                               // narrow tiles (N = 16 / 24 / 32): one half only
                     float v[32];
-                    tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 32 * h), v);
+                    tmem_ld32(tmem_t + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 32 * h), v);
                     if (plain_out == 0) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -340,9 +368,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint2 lo = nn::pack4(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]));
-                        const uint2 hi = nn::pack4(make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
-                        *reinterpret_cast<uint4*>(rowp + (((4 * h + j) ^ (lane & 7)) << 4)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+                        if (32 * h + 8 * j < ncol) {                         // chunks beyond the tile are clipped by TMA anyway
+                            const uint2 lo = nn::pack4(make_float4(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3]));
+                            const uint2 hi = nn::pack4(make_float4(v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7]));
+                            *reinterpret_cast<uint4*>(rowp + (((4 * h + j) ^ (lane & 7)) << 4)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+                        }
                     }
                 }
                 fence_proxy_async();
@@ -352,31 +382,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     bulk_commit();
                 }
                 if (p.stats) {
-                    // lane L: columns 2L, 2L+1 = 4-byte word (L & 3) of 16-byte chunk (L >> 2)
-                    const uint8_t* colp = stg0_g + buf + (lane & 3) * 4;
+                    // column pair cp = columns 2cp, 2cp+1 = 4-byte word (cp & 3) of 16-byte chunk (cp >> 2).  A box of
+                    // ncol <= 32 / <= 16 columns has only 16 / 8 pairs: the lanes then split the 32 rows 2 / 4 ways
+                    // (row groups) and the groups are added by shuffles in fixed order.
+                    const int pg = ncol > 32 ? 32 : (ncol > 16 ? 16 : 8), nrg = 32 / pg;
+                    const int cp = lane & (pg - 1), rg = lane / pg;
+                    const uint8_t* colp = stg0_g + buf + (cp & 3) * 4;
                     float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
-                    for (int r = 0; r < rv; ++r) {
-                        const unsigned w = *reinterpret_cast<const unsigned*>(colp + r * 128 + (((lane >> 2) ^ (r & 7)) << 4));
+#pragma unroll 4
+                    for (int r = rg; r < rv; r += nrg) {
+                        const unsigned w = *reinterpret_cast<const unsigned*>(colp + r * 128 + (((cp >> 2) ^ (r & 7)) << 4));
                         const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
                         a0 += x.x; b0 = fmaf(x.x, x.x, b0); a1 += x.y; b1 = fmaf(x.y, x.y, b1);
                     }
-                    if (n + 2 * lane < p.N) {                                // N even
-                        s_sum[q][c0 + 2 * lane] = a0; s_sq[q][c0 + 2 * lane] = b0;
-                        s_sum[q][c0 + 2 * lane + 1] = a1; s_sq[q][c0 + 2 * lane + 1] = b1;
+                    for (int o = pg; o < 32; o <<= 1) {
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, o); b0 += __shfl_xor_sync(0xffffffffu, b0, o);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, o); b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+                    }
+                    if (rg == 0 && n + 2 * cp < p.N && 2 * cp < ncol) {      // N even; the slot is this lane's own
+                        s_sum[q][c0 + 2 * cp] += a0; s_sq[q][c0 + 2 * cp] += b0;
+                        s_sum[q][c0 + 2 * cp + 1] += a1; s_sq[q][c0 + 2 * cp + 1] += b1;
                     }
                 }
             }
-            if (lane == 0) bulk_wait_read<0>();
-            __syncwarp();
         } else
         if (p.tma_out) {
             // ---- TMA epilogue: 32 rows x 32 columns at a time through a 128-byte-swizzled box (row r, 16-byte chunk
             // c stored at chunk c ^ (r & 7): the row-per-lane writes and the column-per-lane statistic reads are both
             // bank-conflict free); one lane hands the box to TMA, which clips rows >= M / columns >= N and either
             // stores or reduce-adds it.  Two boxes per warp are in flight.
-            const uint32_t stg0 = tiles + (uint32_t)q * 8192u;
+            const uint32_t stg0 = epi0 + (uint32_t)q * 8192u;
             uint8_t* stg0_g = smem_raw + (stg0 - smem_u32(smem_raw));
-            int nbox = 0;
             const bool do_out = num_kb > 0 || !p.accum_out;
             const int plain_out = (p.atomic_out || (p.bias == nullptr && p.act == LR_ACT_NONE)) ? 1 : 0;
             for (int c0 = 0; c0 < p.BN; c0 += 32, ++nbox) {
@@ -388,7 +424,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint8_t* rowp = stg0_g + buf + lane * 128;
                 {
                     float v[32];
-                    tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                    tmem_ld32(tmem_t + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
                     if (threadIdx.x == 64 && nbox == 1) LR_STAMP(20);
                     if (plain_out == 0) {                                    // bias and / or activation (uniform branch)
 #pragma unroll
@@ -444,13 +480,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             a += x; b = fmaf(x, x, b);
                         }
                     }
-                    s_sum[q][c0 + lane] = a;                                 // warp q's own slot: no atomics, the four
-                    s_sq[q][c0 + lane] = b;                                  // warps are added in fixed order below
+                    s_sum[q][c0 + lane] += a;                                // warp q's own slot (this lane's): no atomics,
+                    s_sq[q][c0 + lane] += b;                                 // the four warps are added in fixed order below
                 }
                 if (threadIdx.x == 64 && nbox == 1) LR_STAMP(24);
             }
-            if (lane == 0) bulk_wait_read<0>();
-            __syncwarp();
         } else
         for (int p0 = 0; p0 < p.BN; p0 += EPI_PW) {
             const int nbase = n0 + p0;
@@ -459,7 +493,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // ---- TMEM -> registers (bias, activation) -> slab[row = lane][col]
             for (int c0 = 0; c0 < pwv; c0 += 16) {
                 float v[16];
-                tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(p0 + c0), v);
+                tmem_ld16(tmem_t + ((uint32_t)(q * 32) << 16) + (uint32_t)(p0 + c0), v);
                 if (!p.atomic_out) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = nn::act_fwd(v[j] + s_bias[p0 + c0 + j], p.act);
@@ -510,6 +544,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     s_sq[q][p0 + c] = b;
                 }
             }
+            __syncwarp();
+        }
+        }   // tiles of this CTA
+        if (p.tma_out || sizeof(TC) == 2) {
+            if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
         }
         fence_before();
@@ -596,7 +635,6 @@ static int launch(const void* A, long long lda, int a_trans, const void* B, long
     p.trace = g_lr_trace;
 #endif
     const int num_kb = kchunk / BK;
-    p.stages = num_kb < MAX_STAGES ? num_kb : MAX_STAGES;
     // Output path: TMA store / reduce-add whenever C is TMA-addressable (16-byte aligned rows) and the residual
     // is absent or IS C (then the call accumulates: reduce-add); otherwise the shared-memory slab path (fp32 out only).
     const bool c_tma_ok = ((ldc * (long long)sizeof(TC)) & 15) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0;
@@ -611,6 +649,31 @@ static int launch(const void* A, long long lda, int a_trans, const void* B, long
         p.tma_out = (c_tma_ok && (R == nullptr || (r_is_c && !stats && act == LR_ACT_NONE && !bias))) ? 1 : 0;
         p.accum_out = (p.atomic_out || (R != nullptr && r_is_c)) ? 1 : 0;
     }
+    // tile batching: tall single-pass problems whose result leaves through TMA (own staging boxes).  mt tiles per CTA
+    // while the grid still has >= ~3 CTAs per SM slot and the tiles' accumulators fit 256 TMEM columns (two CTAs / SM)
+    p.tile_cols = HC ? (bn + 31) / 32 * 32 : (bn + 31) / 32 * 32;
+    p.mt = 1;
+    {
+        static const int mt_env = getenv("LIPREAD_GEMM_MT") ? atoi(getenv("LIPREAD_GEMM_MT")) : 0;
+        const long long tiles_m = (M + BM - 1) / BM, n_tiles = (N + bn - 1) / bn;
+        if (nz == 1 && (HC || p.tma_out) && mt_env != 1 && num_kb == 1) {
+            // measured on B200 (tools/microbench.py gemm, profiles/r2_gemm_tile_batching.txt): single-k-block tiles gain
+            // from batching -- up to 8 per CTA for N <= 32 (1.8 M x 16 x 32: 124 -> 73 us), 2 for wider tiles
+            // (449 152 x 72 x 16: 53 -> 49 us) -- while two-k-block tiles (K = 72 .. 96) and grids below ~3 CTAs per
+            // SM slot do not
+            const int cap = p.tile_cols <= 32 ? MAX_MT : 2;
+            int mt = 1;
+            while (mt < cap && 2 * mt * p.tile_cols <= 256 && tiles_m * n_tiles / (2 * mt) >= 3LL * lr::sm_count()) mt *= 2;
+            if (mt_env > 1) mt = mt_env;
+            while (mt > 1 && mt * p.tile_cols > 512) mt /= 2;
+            p.mt = mt;
+        }
+    }
+    const int total_kb = num_kb * p.mt;
+    static const int st_env = getenv("LIPREAD_GEMM_STAGES") ? atoi(getenv("LIPREAD_GEMM_STAGES")) : 0;
+    // batched tiles: two ring slots (smem per CTA stays small enough for three CTAs per SM: more loads in flight)
+    const int max_stages = st_env >= 1 && st_env <= MAX_STAGES ? st_env : (p.mt > 1 ? 2 : MAX_STAGES);
+    p.stages = total_kb < max_stages ? total_kb : max_stages;
     CUtensorMap ma, mb, mc;
     if (p.tma_out) {
         int rcc = make_map(&mc, C, HC, M, N, ldc, HC ? 64 : 32, 32);
@@ -624,7 +687,8 @@ static int launch(const void* A, long long lda, int a_trans, const void* B, long
     if (rc) return rc;
     const size_t b_stage = b_trans ? (size_t)((bn + BK - 1) / BK) * (size_t)BK * 128 : (size_t)bn * 128;
     size_t smem = (size_t)p.stages * (A_STAGE_BYTES + b_stage);
-    if (smem < (size_t)EPI_BYTES) smem = EPI_BYTES;           // the epilogue slabs reuse the pipeline buffers
+    if (p.mt > 1) smem += 32768;                                // staging boxes of the epilogue behind the ring
+    else if (smem < (size_t)EPI_BYTES) smem = EPI_BYTES;        // one tile: the epilogue slabs reuse the pipeline buffers
     smem += 1024;
     {
         cudaError_t e = lr::ensure_max_dynamic_smem(gemm_tc_kernel<TO, TC, false, false>, 200 * 1024);
@@ -633,7 +697,7 @@ static int launch(const void* A, long long lda, int a_trans, const void* B, long
         if (e == cudaSuccess) e = lr::ensure_max_dynamic_smem(gemm_tc_kernel<TO, TC, true, false>, 200 * 1024);
         if (e != cudaSuccess) return lr::fail(LR_ECUDA, "%s smem: %s", name, cudaGetErrorString(e));
     }
-    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + bn - 1) / bn), (unsigned)nz);
+    dim3 grid((unsigned)(((M + BM - 1) / BM + p.mt - 1) / p.mt), (unsigned)((N + bn - 1) / bn), (unsigned)nz);
     if (a_trans) {
         if (b_trans) gemm_tc_kernel<TO, TC, true, true><<<grid, THREADS, smem, stream>>>(ma, mb, mc, p);
         else gemm_tc_kernel<TO, TC, true, false><<<grid, THREADS, smem, stream>>>(ma, mb, mc, p);

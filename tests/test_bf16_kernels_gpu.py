@@ -58,6 +58,32 @@ def test_gemm_bf16_forward_layout(cuda_device, M, N, K, out):
     assert torch.allclose(stats[N:], (Cd * Cd).sum(0), rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("M,N,K,out", [(460000, 16, 32, "bf16"), (460000, 16, 32, "f32"), (230000, 72, 16, "bf16"),
+                                       (115100, 24, 24, "bf16"), (230100, 32, 64, "bf16"), (120000, 96, 24, "f32")])
+def test_gemm_bf16_tile_batching(cuda_device, M, N, K, out):
+    """Tall single-k-block problems run several 128-row tiles per CTA (gemm_tc.cu, P::mt): tails (a last CTA with fewer
+    tiles, a last tile with fewer rows), bias + activation + residual, and the once-per-CTA statistics."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A, B = _bf(torch.randn(M, K, generator=g)).cuda(), _bf(torch.randn(N, K, generator=g)).cuda()
+    dt = torch.bfloat16 if out == "bf16" else torch.float32
+    ref = A.double() @ B.double().t()
+    C = torch.full((M, N), float("nan"), device="cuda", dtype=dt)
+    stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+    _gemm_bf16(A, K, 0, B, K, 0, C, N, M, N, K, stats=stats)
+    torch.cuda.synchronize()
+    tol = (2.0 ** -8 if out == "bf16" else 1e-5) * ref.abs().max().item()
+    assert torch.isfinite(C.float()).all() and (C.double() - ref).abs().max().item() <= tol
+    Cd = C.double()
+    assert torch.allclose(stats[:N], Cd.sum(0), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(stats[N:], (Cd * Cd).sum(0), rtol=1e-5, atol=1e-2)
+    if out == "bf16":
+        bias, R = torch.randn(N, generator=g).cuda(), _bf(torch.randn(M, N, generator=g)).cuda()
+        C2 = torch.full((M, N), float("nan"), device="cuda", dtype=dt)
+        _gemm_bf16(A, K, 0, B, K, 0, C2, N, M, N, K, bias=bias, act=1, R=R, ldr=N)
+        ref2 = torch.relu(ref + bias.double()) + R.double()
+        assert (C2.double() - ref2).abs().max().item() <= 2.0 ** -8 * ref2.abs().max().item()
+
+
 def test_gemm_bf16_epilogue_residual_and_strides(cuda_device):
     g = torch.Generator().manual_seed(0)
     M, N, K = 1500, 88, 24
