@@ -252,6 +252,19 @@ int lr_lstm_fwd(const float* xproj, long long ldx, const float* bhh /*[4H] or NU
 int lr_lstm_bwd(const float* dout, long long ldo, int dout_step, const float* gates, const float* cst, const float* whh,
                 float* dgates, int B, int T, int H, int nsteps, int reverse, lr_stream_t stream);
 
+/* The same recurrence / BPTT on the tensor cores (csrc/lstm_tc.cu, precision "bf16"): W_hh and h_{t-1} (forward),
+ * W_hh^T and dgates (backward) are rounded to bfloat16 and multiplied by tcgen05.mma with fp32 accumulation; the input
+ * projection, gate activations, cell states and every saved / returned tensor stay fp32.  H must be 128, 256 or 512
+ * (1 / 4 / 16 CTAs of one cluster per 32 batch rows keep a 128 KB bf16 slice of W_hh resident in shared memory);
+ * arguments and semantics as lr_lstm_fwd / lr_lstm_bwd.  Replaces nn.LSTM under torch.autocast(bfloat16) at the
+ * reference's call sites (video/models/resnet_lstm.py:113-120, audio_video/models/early_fusion.py:62-69,
+ * audio_video/models/middle_fusion_fast.py:18,35-36). */
+int lr_lstm_fwd_tc(const float* xproj, long long ldx, const float* bhh, const float* whh, float* out, long long ldo,
+                   float* gates, float* cst, float* hprev, int B, int T, int H, int nsteps, int reverse,
+                   lr_stream_t stream);
+int lr_lstm_bwd_tc(const float* dout, long long ldo, int dout_step, const float* gates, const float* cst, const float* whh,
+                   float* dgates, int B, int T, int H, int nsteps, int reverse, lr_stream_t stream);
+
 /* dst[r*ldd + c] = src[r*lds + c]  (strided row gather, e.g. out[:, -1] of a sequence into the fusion row) */
 int lr_copy2d(float* dst, long long ldd, const float* src, long long lds, int rows, int cols, lr_stream_t stream);
 

@@ -428,6 +428,15 @@ class Plan:
         return self.alloc(n, torch.bfloat16 if t.h else torch.float32)
 
     # ---- op emitters ----------------------------------------------------------------------------------
+    def lstm_op(self, which, H, nsteps):
+        """Name of the recurrence kernel: the tensor-core walk (csrc/lstm_tc.cu: bf16 W_hh / h operands, tcgen05) under
+        precision "bf16" for H = 256 / 512 and walks of more than one step, else the fp32 kernels.  Measured at B = 32,
+        T = 29 (tools/microbench.py lstm, profiles/r2_lstm_microbench.txt): H = 512 forward 483 -> 139 us, backward
+        580 -> 223 us; H = 256 237 -> 142 / 270 -> 179 us; at H = 128 the fp32 8-CTA cluster kernel (131 / 144 us) still
+        beats the single-CTA tensor-core walk (201 / 160 us: eight cells per thread and step), so it keeps that size."""
+        tc = self.h and H in (256, 512) and nsteps > 1 and os.environ.get("LIPREAD_LSTM_TC", "1") != "0"
+        return f"lr_lstm_{which}_tc" if tc else f"lr_lstm_{which}"
+
     def gemm(self, ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias=0, act=ACT_NONE, R=0, ldr=0, stats=0, ksplit=1,
              leaf=False):
         ops.add("lr_gemm", A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias, act, R, ldr, stats, ksplit, leaf=leaf)
@@ -1019,7 +1028,7 @@ class Plan:
         xp_f, hs_f = self.alloc(F * G4), self.alloc(F * H)
         gates_f, c_f, hp_f = self.alloc(F * G4), self.alloc(F * H), self.alloc(F * H)
         self.linear(cur, Icur, F, par("weight_ih", l, 0), par("bias_ih", l, 0), xp_f, G4)
-        self.fwd.add("lr_lstm_fwd", xp_f, G4, par("bias_hh", l, 0), par("weight_hh", l, 0), hs_f, H, gates_f, c_f, hp_f,
+        self.fwd.add(self.lstm_op("fwd", H, T), xp_f, G4, par("bias_hh", l, 0), par("weight_hh", l, 0), hs_f, H, gates_f, c_f, hp_f,
                      B, T, H, T, 0)
         optr = out if isinstance(out, int) else out.data_ptr()
         self.fwd.add("lr_copy2d", optr, ldo, hs_f.data_ptr() + 4 * (T - 1) * H, T * H, B, H)
@@ -1032,7 +1041,7 @@ class Plan:
             dptr = dout if isinstance(dout, int) else dout.data_ptr()
             dg_f, dg_r = self.alloc(F * G4), self.alloc(B * G4)
             g = self.bgroup()
-            g.add("lr_lstm_bwd", dptr, ldo, T - 1, gates_f, c_f, par("weight_hh", l, 0), dg_f, B, T, H, T, 0)
+            g.add(self.lstm_op("bwd", H, T), dptr, ldo, T - 1, gates_f, c_f, par("weight_hh", l, 0), dg_f, B, T, H, T, 0)
             self.linear_bwd(g, hp_f, H, F, par("weight_hh", l, 0), par("bias_hh", l, 0), dg_f, G4)
             self.linear_bwd(g, cur, Icur, F, par("weight_ih", l, 0), par("bias_ih", l, 0), dg_f, G4, dx=dcur, ldx=Icur)
             # reverse direction: one step from the zero state (W_hh_reverse gets no gradient)
@@ -1061,7 +1070,7 @@ class Plan:
             xp, gates, cst, hp = self.alloc(F * G4), self.alloc(F * G4), self.alloc(F * H), self.alloc(F * H)
             with (self.fwd.side_branch() if rev else contextlib.nullcontext()):
                 self.linear(cur, Icur, F, par("weight_ih", rev), par("bias_ih", rev), xp, G4)
-                self.fwd.add("lr_lstm_fwd", xp, G4, par("bias_hh", rev), par("weight_hh", rev),
+                self.fwd.add(self.lstm_op("fwd", H, T), xp, G4, par("bias_hh", rev), par("weight_hh", rev),
                              seq.data_ptr() + 4 * H * rev, 2 * H, gates, cst, hp, B, T, H, T, rev)
             saved.append((gates, cst, hp))
         self.fwd.join()
@@ -1072,7 +1081,7 @@ class Plan:
             for rev in (1, 0):
                 gates, cst, hp = saved[rev]
                 with (g.side_branch() if rev else contextlib.nullcontext()):
-                    g.add("lr_lstm_bwd", dseq.data_ptr() + 4 * H * rev, 2 * H, -1, gates, cst, par("weight_hh", rev), dgs[rev],
+                    g.add(self.lstm_op("bwd", H, T), dseq.data_ptr() + 4 * H * rev, 2 * H, -1, gates, cst, par("weight_hh", rev), dgs[rev],
                           B, T, H, T, rev)
             g.join()
             for rev in (0, 1):
@@ -1112,7 +1121,7 @@ class Plan:
             xp, hs = self.alloc(F * G4), self.alloc(F * H)
             gates, cst, hp = self.alloc(F * G4), self.alloc(F * H), self.alloc(F * H)
             self.linear(x, I, F, par("weight_ih", rev), par("bias_ih", rev), xp, G4)
-            self.fwd.add("lr_lstm_fwd", xp, G4, par("bias_hh", rev), par("weight_hh", rev), hs, H, gates, cst, hp,
+            self.fwd.add(self.lstm_op("fwd", H, T), xp, G4, par("bias_hh", rev), par("weight_hh", rev), hs, H, gates, cst, hp,
                          B, T, H, T, rev)
             t_final = 0 if rev else T - 1
             self.fwd.add("lr_copy2d", optr + 4 * H * rev, ldo, hs.data_ptr() + 4 * t_final * H, T * H, B, H)
@@ -1123,7 +1132,7 @@ class Plan:
             for rev in (0, 1):
                 gates, cst, hp, t_final = saved[rev]
                 dg = self.alloc(F * G4)
-                g.add("lr_lstm_bwd", dptr + 4 * H * rev, ldo, t_final, gates, cst, par("weight_hh", rev), dg, B, T, H, T, rev)
+                g.add(self.lstm_op("bwd", H, T), dptr + 4 * H * rev, ldo, t_final, gates, cst, par("weight_hh", rev), dg, B, T, H, T, rev)
                 self.linear_bwd(g, hp, H, F, par("weight_hh", rev), par("bias_hh", rev), dg, G4)
                 self.linear_bwd(g, x, I, F, par("weight_ih", rev), par("bias_ih", rev), dg, G4, dx=dx, ldx=I,
                                 dx_residual=(dx if rev else 0), ldr=I)

@@ -147,6 +147,16 @@ def lstm_bwd(dout, ldo, dout_step, gates, cst, whh, dgates, B, T, H, nsteps, rev
                           int(reverse), _s()))
 
 
+def lstm_fwd_tc(xproj, ldx, bhh, whh, out, ldo, gates, cst, hprev, B, T, H, nsteps, reverse):
+    check(lib.lr_lstm_fwd_tc(_p(xproj), ldx, _p(bhh), _p(whh), _p(out), ldo, _p(gates), _p(cst), _p(hprev), B, T, H,
+                             nsteps, int(reverse), _s()))
+
+
+def lstm_bwd_tc(dout, ldo, dout_step, gates, cst, whh, dgates, B, T, H, nsteps, reverse):
+    check(lib.lr_lstm_bwd_tc(_p(dout), ldo, dout_step, _p(gates), _p(cst), _p(whh), _p(dgates), B, T, H, nsteps,
+                             int(reverse), _s()))
+
+
 def audio_conv_fwd(x, w, bias, out, ldo, arg, B, H, W):
     check(lib.lr_audio_conv_fwd(_p(x), _p(w), _p(bias), _p(out), ldo, _p(arg), B, H, W, _s()))
 

@@ -258,6 +258,53 @@ def test_lstm_direction_kernels(K, H, I, B, T):
     _close(dx_total.view(B, T, I), x.grad, rtol=1e-4)
 
 
+@pytest.mark.parametrize("H,I,B,T", [(128, 64, 32, 29), (128, 48, 6, 5), (256, 64, 33, 7), (512, 32, 32, 29), (512, 32, 3, 4)])
+def test_lstm_tensor_core_kernels(K, H, I, B, T):
+    """csrc/lstm_tc.cu (precision "bf16"): W_hh / h and W_hh^T / dgates rounded to bf16, tcgen05 products, fp32 state.
+    Against torch's fp32 nn.LSTM: outputs within 2e-2 of max|out| (bf16 operand rounding through T recurrent steps; the
+    fp32 kernels sit at 2e-5), dgates-derived weight / input gradients within 5e-2 norm-wise; and against the fp32
+    kernel driven with the SAME bf16-rounded W_hh, where only the rounding of h / dgates remains."""
+    torch.manual_seed(H + B)
+    lstm = nn.LSTM(I, H, 1, batch_first=True, bidirectional=True)
+    x = torch.randn(B, T, I, requires_grad=True)
+    out, _ = lstm(x)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    xd = x.detach().cuda()
+    dod = dout.contiguous().cuda()
+    for d, sfx in enumerate(("", "_reverse")):
+        wih, whh = getattr(lstm, "weight_ih_l0" + sfx).detach().cuda(), getattr(lstm, "weight_hh_l0" + sfx).detach().cuda()
+        bih, bhh = getattr(lstm, "bias_ih_l0" + sfx).detach().cuda(), getattr(lstm, "bias_hh_l0" + sfx).detach().cuda()
+        xproj = torch.empty(B * T, 4 * H, device="cuda")
+        K.linear_fwd(xd.view(B * T, I), wih, xproj, bias=bih)
+        res = {}
+        for kind in ("tc", "fp32_rounded_w"):
+            w_used = whh if kind == "tc" else whh.to(torch.bfloat16).float()
+            o = torch.zeros(B, T, 2 * H, device="cuda")
+            gates, cst, hprev = (torch.full((B, T, 4 * H), float("nan"), device="cuda"), torch.full((B, T, H), float("nan"), device="cuda"),
+                                 torch.full((B, T, H), float("nan"), device="cuda"))
+            dg = torch.zeros(B, T, 4 * H, device="cuda")
+            fwd, bwd = (K.lstm_fwd_tc, K.lstm_bwd_tc) if kind == "tc" else (K.lstm_fwd, K.lstm_bwd)
+            fwd(xproj, 4 * H, bhh, w_used, o[:, :, d * H:], 2 * H, gates, cst, hprev, B, T, H, T, d)
+            bwd(dod[:, :, d * H:], 2 * H, -1, gates, cst, w_used, dg, B, T, H, T, d)
+            torch.cuda.synchronize()
+            assert torch.isfinite(gates).all() and torch.isfinite(cst).all() and torch.isfinite(hprev).all()
+            res[kind] = (o[:, :, d * H:(d + 1) * H].clone(), dg, hprev)
+        o_tc, dg_tc, hp_tc = res["tc"]
+        o_32, dg_32, _ = res["fp32_rounded_w"]
+        ref = out[:, :, d * H:(d + 1) * H].detach().cuda()
+        scale = ref.abs().max().item()
+        assert (o_tc - ref).abs().max().item() <= 2e-2 * scale
+        assert (o_tc - o_32).abs().max().item() <= 1e-2 * scale          # same rounded weights: only h's rounding differs
+        assert (dg_tc - dg_32).abs().max().item() <= 3e-2 * dg_32.abs().max().item()
+        dwih, dwhh = torch.zeros_like(wih), torch.zeros_like(whh)
+        K.linear_wgrad(dg_tc.view(B * T, 4 * H), xd.view(B * T, I), dwih)
+        K.linear_wgrad(dg_tc.view(B * T, 4 * H), hp_tc.view(B * T, H), dwhh)
+        for got, want in ((dwih, getattr(lstm, "weight_ih_l0" + sfx).grad), (dwhh, getattr(lstm, "weight_hh_l0" + sfx).grad)):
+            want = want.cuda()
+            assert (got - want).abs().max().item() <= 5e-2 * want.abs().max().item()
+
+
 def test_lstm_last_step_only(K):
     """out[:, -1] head (middle_fusion_fast.py:36): forward direction with a gradient at t = T-1 only, and the
     reverse direction reduced to its first step."""

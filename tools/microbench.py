@@ -52,3 +52,13 @@ for M, N, K in ((1796608, 16, 32), (449152, 72, 16), (449152, 16, 72), (112288, 
     Cc = torch.empty(M, N, device=dev, dtype=torch.bfloat16); stt = torch.zeros(2 * N, dtype=torch.float64, device=dev)
     timed(f"gemm_bf16 fwd+stats [{M}x{N}x{K}]", lambda: _lib.check(L.lr_gemm_bf16(p(A), K, 0, p(B), K, 0, p(Cc), N, 1, M, N, K, 0, 0, 0, 0, p(stt), 1, s)), 2 * (M * K + N * K + M * N))
     timed(f"gemm_bf16 fwd       [{M}x{N}x{K}]", lambda: _lib.check(L.lr_gemm_bf16(p(A), K, 0, p(B), K, 0, p(Cc), N, 1, M, N, K, 0, 0, 0, 0, 0, 1, s)), 2 * (M * K + N * K + M * N))
+for H in (128, 256, 512):
+    if which not in ("lstm", "all"): break
+    B, T = 32, 29
+    xp = torch.randn(B * T, 4 * H, device=dev) * 0.5; whh = torch.randn(4 * H, H, device=dev) * (H ** -0.5); bhh = torch.zeros(4 * H, device=dev)
+    out = torch.zeros(B, T, H, device=dev); gates = torch.zeros(B, T, 4 * H, device=dev); cst = torch.zeros(B, T, H, device=dev); hp = torch.zeros(B, T, H, device=dev)
+    dout = torch.randn(B, T, H, device=dev); dg = torch.zeros(B, T, 4 * H, device=dev)
+    for sfx in ("", "_tc"):
+        f, b = getattr(L, "lr_lstm_fwd" + sfx), getattr(L, "lr_lstm_bwd" + sfx)
+        timed(f"lstm_fwd{sfx} [B{B} T{T} H{H}]", lambda: _lib.check(f(p(xp), 4 * H, p(bhh), p(whh), p(out), H, p(gates), p(cst), p(hp), B, T, H, T, 0, s)), 4 * B * T * 11 * H)
+        timed(f"lstm_bwd{sfx} [B{B} T{T} H{H}]", lambda: _lib.check(b(p(dout), H, -1, p(gates), p(cst), p(whh), p(dg), B, T, H, T, 0, s)), 4 * B * T * 11 * H)
