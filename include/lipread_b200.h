@@ -221,6 +221,8 @@ int lr_im2col(const void* x, int is_u8, float scale, int F, int T, long long sb,
 int lr_im2col_tap(const float* x, int F, int Hs, int Ws, int C, int kh, int kw, int stride, int pad_h, int pad_w,
                   int transposed, int Hd, int Wd, float* col, lr_stream_t stream);
 int lr_weight_tap(const float* src, float* dst, int Cout, int Cin, int kk, int mode, lr_stream_t stream);
+/* modes 0 and 1 straight into the bf16 operand of the tensor-core convolutions (precision "bf16") */
+int lr_weight_tap_h(const float* src, void* dst, int Cout, int Cin, int kk, int mode, lr_stream_t stream);
 /* wt[c][k*kk + rs] (row pitch ldt) = w[k][c][rs]: the dgrad weight of a dense convolution. */
 int lr_weight_transpose(const float* w, float* wt, int Cout, int Cin, int kk, long long ldt, lr_stream_t stream);
 

@@ -73,6 +73,54 @@ im2col_kernel(const Src s, const Geo g, T* __restrict__ col, long long rows) {
     }
 }
 
+// Fast path of the ResNet stem on raw uint8 lip frames: 3 channels, 7x7 window, stride 2, padding 3, row pitch 152
+// (147 valid columns, torch order k = c*49 + r*7 + q).  One block per (frame, output row): the 3 x 7 source rows the
+// row needs are staged once in shared memory as floats (zero outside the image), then thread = (16-byte chunk j of the
+// patch row, pixel lane) copies 8 consecutive columns per pixel from offsets it computed ONCE -- no per-element index
+// arithmetic, 16-byte stores, 19 consecutive chunks per pixel = one contiguous 304-byte row.  (The generic kernel
+// spent a chain of 64-bit divisions per 4 columns: 1 080 us for the 1.8 M-pixel stem of the benchmark; this one is
+// bound by the 546 MB it writes.)
+constexpr int S7_W = 96;                                   // staged row pitch (floats) >= 2*(Wd-1) + 7, Wd <= 45
+template <typename T>
+__global__ void __launch_bounds__(TH)
+im2col_u8c3_7x7s2_kernel(const Src s, const Geo g, T* __restrict__ col, int rows_fh) {
+    __shared__ float S[3 * 7 * S7_W];
+    constexpr int NCH = 152 / 8;                           // 19 chunks of 8 columns
+    const int j = threadIdx.x % NCH, pl = threadIdx.x / NCH;       // pixel lanes: 13 (247 of 256 threads work)
+    int off[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = 8 * j + e;
+        const int c = k / 49, rs = k - c * 49, r = rs / 7, q = rs - r * 7;
+        off[e] = k < 147 ? (c * 7 + r) * S7_W + q : -1;
+    }
+    const unsigned char* xs = static_cast<const unsigned char*>(s.x);
+    for (int fh = blockIdx.x; fh < rows_fh; fh += gridDim.x) {
+        const int f = fh / g.Hd, hd = fh - f * g.Hd;
+        const long long fb = (long long)(f / s.T) * s.sb + (long long)(f % s.T) * s.st;
+        __syncthreads();                                   // the previous row's readers are done
+        for (int i = threadIdx.x; i < 3 * 7 * S7_W; i += TH) {
+            const int cr = i / S7_W, xw = i - cr * S7_W, c = cr / 7, r = cr - c * 7;
+            const int hs = 2 * hd - 3 + r, ws = xw - 3;
+            float v = 0.f;
+            if (hs >= 0 && hs < s.Hs && ws >= 0 && ws < s.Ws)
+                v = lr::u8_scaled(xs[fb + (long long)c * s.sc + (long long)hs * s.sh + (long long)ws * s.sw], s.scale);
+            S[i] = v;
+        }
+        __syncthreads();
+        if (pl < TH / NCH) {
+            T* const orow = col + (long long)fh * g.Wd * 152 + 8 * j;
+            for (int wd = pl; wd < g.Wd; wd += TH / NCH) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = off[e] >= 0 ? S[off[e] + 2 * wd] : 0.f;
+                nn::st4(orow + (long long)wd * 152, make_float4(v[0], v[1], v[2], v[3]));
+                nn::st4(orow + (long long)wd * 152 + 4, make_float4(v[4], v[5], v[6], v[7]));
+            }
+        }
+    }
+}
+
 // Fast path of the stems on raw uint8 lip frames (3 channels, 3x3 window, any stride / padding): one thread per
 // output pixel reads its 3 x 3 x 3 byte patch (L1 serves the overlap with the neighbours) and writes its whole
 // 28-float row (7 coalesced float4 stores) -- no per-element index arithmetic.
@@ -143,20 +191,21 @@ im2col_tap_kernel(const T* __restrict__ x, const Geo g, int Hs, int Ws, int C, T
 //   mode 0: wp[k][rs][c]  = w[k][c][rs]    forward / wgrad operand   [Cout][kk*Cin]
 //   mode 1: wp[c][rs][k]  = w[k][c][rs]    dgrad operand             [Cin][kk*Cout]
 //   mode 2: w[k][c][rs]   = wp[k][rs][c]   weight gradient back to torch's layout (overwrites w)
+template <typename TD>
 __global__ void __launch_bounds__(TH)
-weight_tap_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin, int kk, int mode) {
+weight_tap_kernel(const float* __restrict__ src, TD* __restrict__ dst, int Cout, int Cin, int kk, int mode) {
     const long long n = (long long)Cout * Cin * kk;
     for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < n; i += (long long)gridDim.x * TH) {
         // i enumerates the DESTINATION contiguously
         if (mode == 0) {
             const int c = int(i % Cin); const long long t = i / Cin; const int rs = int(t % kk), k = int(t / kk);
-            dst[i] = src[((long long)k * Cin + c) * kk + rs];
+            nn::st1(dst + i, src[((long long)k * Cin + c) * kk + rs]);
         } else if (mode == 1) {
             const int k = int(i % Cout); const long long t = i / Cout; const int rs = int(t % kk), c = int(t / kk);
-            dst[i] = src[((long long)k * Cin + c) * kk + rs];
+            nn::st1(dst + i, src[((long long)k * Cin + c) * kk + rs]);
         } else {
             const int rs = int(i % kk); const long long t = i / kk; const int c = int(t % Cin), k = int(t / Cin);
-            dst[i] = src[((long long)k * kk + rs) * Cin + c];
+            nn::st1(dst + i, src[((long long)k * kk + rs) * Cin + c]);
         }
     }
 }
@@ -210,37 +259,41 @@ maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __
 }
 
 // dx[f,h,w,c] = sum of dy over the windows whose saved arg-max is (h, w)   (gather form: no atomics)
+// One block per (frame, input row): the window rows that can hold it are block constants, a thread owns 4 channels of
+// one pixel of the row (all index arithmetic is 32-bit and per row, not a chain of 64-bit divisions per element).
 template <typename T>
 __global__ void __launch_bounds__(TH)
 maxpool_bwd_kernel(const T* __restrict__ dy, const unsigned char* __restrict__ arg, T* __restrict__ dx, int F,
                    int H, int W, int C, int k, int stride, int pad, int Ho, int Wo) {
     const int c4n = C >> 2;
-    const long long total = (long long)F * H * W * c4n;
-    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < total; i += (long long)gridDim.x * TH) {
-        const int c = int(i % c4n) * 4;
-        long long t = i / c4n;
-        const int w = int(t % W); t /= W;
-        const int h = int(t % H), f = int(t / H);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int items = W * c4n;
+    for (int fh = blockIdx.x; fh < F * H; fh += gridDim.x) {
+        const int f = fh / H, h = fh - f * H;
         const int ho_lo = max(0, (h + pad - k + stride) / stride), ho_hi = min(Ho - 1, (h + pad) / stride);
-        const int wo_lo = max(0, (w + pad - k + stride) / stride), wo_hi = min(Wo - 1, (w + pad) / stride);
-        for (int ho = ho_lo; ho <= ho_hi; ++ho) {
-            const int r = h + pad - ho * stride;
-            if (r < 0 || r >= k) continue;
-            for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-                const int s = w + pad - wo * stride;
-                if (s < 0 || s >= k) continue;
-                const long long o = (((long long)f * Ho + ho) * Wo + wo) * C + c;
-                const uchar4 a = *reinterpret_cast<const uchar4*>(arg + o);
-                const float4 g = nn::ld4(dy + o);
-                const unsigned char code = (unsigned char)(r * k + s);
-                if (a.x == code) acc.x += g.x;
-                if (a.y == code) acc.y += g.y;
-                if (a.z == code) acc.z += g.z;
-                if (a.w == code) acc.w += g.w;
+        const long long obase = (long long)f * Ho * Wo * C;
+        T* const drow = dx + (long long)fh * W * C;
+        for (int it = threadIdx.x; it < items; it += TH) {
+            const int w = it / c4n, c = (it - w * c4n) * 4;
+            const int wo_lo = max(0, (w + pad - k + stride) / stride), wo_hi = min(Wo - 1, (w + pad) / stride);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+                const int r = h + pad - ho * stride;
+                if (r < 0 || r >= k) continue;
+                for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+                    const int sft = w + pad - wo * stride;
+                    if (sft < 0 || sft >= k) continue;
+                    const long long o = obase + (long long)(ho * Wo + wo) * C + c;
+                    const uchar4 a = *reinterpret_cast<const uchar4*>(arg + o);
+                    const float4 g = nn::ld4(dy + o);
+                    const unsigned char code = (unsigned char)(r * k + sft);
+                    if (a.x == code) acc.x += g.x;
+                    if (a.y == code) acc.y += g.y;
+                    if (a.z == code) acc.z += g.z;
+                    if (a.w == code) acc.w += g.w;
+                }
             }
+            nn::st4(drow + (long long)w * C + c, acc);
         }
-        nn::st4(dx + (((long long)f * H + h) * W + w) * C + c, acc);
     }
 }
 
@@ -302,7 +355,12 @@ static int im2col_impl(const void* x, int is_u8, float scale, int F, int T_, lon
     g.pad_w = pad;
     g.K = (int)K; g.ldk = (int)ldk;
     const long long rows = (long long)F * Hd * Wd;
-    if (is_u8 && C == 3 && kh == 3 && kw == 3 && !transposed && ldk >= 28 && ldk <= 32)
+    if (is_u8 && C == 3 && kh == 7 && kw == 7 && stride == 2 && pad == 3 && !transposed && ldk == 152 &&
+        2 * (Wd - 1) + 7 <= c2::S7_W) {
+        const long long fh = (long long)F * Hd;
+        const int grid = (int)(fh < 16LL * lr::sm_count() ? fh : 16LL * lr::sm_count());
+        c2::im2col_u8c3_7x7s2_kernel<T><<<grid, c2::TH, 0, stream>>>(s, g, col, (int)fh);
+    } else if (is_u8 && C == 3 && kh == 3 && kw == 3 && !transposed && ldk >= 28 && ldk <= 32)
         c2::im2col_u8c3_3x3_kernel<T><<<c2::grid_for(rows), c2::TH, 0, stream>>>(s, g, col, rows);
     else
         c2::im2col_kernel<T><<<c2::grid_for(rows * (ldk >> 2)), c2::TH, 0, stream>>>(s, g, col, rows);
@@ -356,7 +414,17 @@ extern "C" int lr_im2col_tap_h(const void* x, int F, int Hs, int Ws, int C, int 
 extern "C" int lr_weight_tap(const float* src, float* dst, int Cout, int Cin, int kk, int mode, lr_stream_t stream) {
     LR_CHECK_ARG(Cout > 0 && Cin > 0 && kk > 0 && mode >= 0 && mode <= 2, "lr_weight_tap: bad argument");
     LR_CHECK_ARG(src && dst, "lr_weight_tap: null pointer");
-    c2::weight_tap_kernel<<<c2::grid_for((long long)Cout * Cin * kk), c2::TH, 0, stream>>>(src, dst, Cout, Cin, kk, mode);
+    c2::weight_tap_kernel<float><<<c2::grid_for((long long)Cout * Cin * kk), c2::TH, 0, stream>>>(src, dst, Cout, Cin, kk, mode);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("weight_tap_kernel");
+    return LR_OK;
+}
+/* the same re-layout straight into the bf16 operand of the tensor-core convolutions (modes 0 and 1) */
+extern "C" int lr_weight_tap_h(const float* src, void* dst, int Cout, int Cin, int kk, int mode, lr_stream_t stream) {
+    LR_CHECK_ARG(Cout > 0 && Cin > 0 && kk > 0 && (mode == 0 || mode == 1), "lr_weight_tap_h: bad argument (modes 0 and 1)");
+    LR_CHECK_ARG(src && dst, "lr_weight_tap_h: null pointer");
+    c2::weight_tap_kernel<nn::bf16><<<c2::grid_for((long long)Cout * Cin * kk), c2::TH, 0, stream>>>(
+        src, static_cast<nn::bf16*>(dst), Cout, Cin, kk, mode);
     lr::count_launch();
     LR_CHECK_LAUNCH("weight_tap_kernel");
     return LR_OK;
@@ -406,8 +474,9 @@ static int maxpool_bwd_impl(const T* dy, const unsigned char* arg, T* dx, int F,
     LR_CHECK_ARG(dy && arg && dx, "lr_maxpool_bwd: null pointer");
     LR_CHECK_ALIGN(dy); LR_CHECK_ALIGN(dx);
     const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-    c2::maxpool_bwd_kernel<T><<<c2::grid_for((long long)F * H * W * (C >> 2)), c2::TH, 0, stream>>>(
-        dy, arg, dx, F, H, W, C, k, stride, pad, Ho, Wo);
+    const long long fh = (long long)F * H;
+    const int grid = (int)(fh < 64LL * lr::sm_count() ? fh : 64LL * lr::sm_count());
+    c2::maxpool_bwd_kernel<T><<<grid, c2::TH, 0, stream>>>(dy, arg, dx, F, H, W, C, k, stride, pad, Ho, Wo);
     lr::count_launch();
     LR_CHECK_LAUNCH("maxpool_bwd_kernel");
     return LR_OK;

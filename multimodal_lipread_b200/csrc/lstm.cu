@@ -51,7 +51,7 @@ lstm_fwd_kernel(const Fwd p) {
             for (int r = 0; r < R; ++r)
                 acc[r] = r < nr ? p.xproj[((long long)(b0 + r) * p.T + t) * p.ldx + j] + bj : 0.f;
             const float* wr = p.whh + (long long)j * H;
-            for (int k = 0; k < H; k += 4) {
+            for (int k = 0; k < (s > 0 ? H : 0); k += 4) {    // h_{-1} = 0: the first step's product is exactly zero
                 const float4 w = nn::ld4(wr + k);
 #pragma unroll
                 for (int r = 0; r < R; ++r) {

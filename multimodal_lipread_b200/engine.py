@@ -831,7 +831,12 @@ class Plan:
         else:
             col = self.alloc(rows * ldk, adt)
             self.fwd.add("lr_im2col" + sfx, xptr, *src, Hs, Ws, Cin, kh, kw, st_, pd, 0, Ho, Wo, col, ldk)
-        if tap:
+        wop_tap = None
+        if tap and hh:                                         # tap-major bf16 operand in one launch
+            wmat = None
+            wop_tap = self.alloc(Cout * K, torch.bfloat16)
+            self.fwd.add("lr_weight_tap_h", conv.weight, wop_tap, Cout, Cin, kh * kw, 0)
+        elif tap:
             wmat = self.alloc(Cout * K)
             self.fwd.add("lr_weight_tap", conv.weight, wmat, Cout, Cin, kh * kw, 0)
         elif ldk != K:
@@ -840,7 +845,9 @@ class Plan:
             self.fwd.add("lr_copy2d", wmat, ldk, conv.weight, K, Cout, K)
         else:
             wmat = conv.weight
-        if hh:                                                 # the GEMM's B operand in bf16
+        if wop_tap is not None:
+            wop = wop_tap
+        elif hh:                                               # the GEMM's B operand in bf16
             wop = self.wh(conv.weight) if wmat is conv.weight else self.cast_h(self.fwd, wmat)
         else:
             wop = wmat
@@ -903,9 +910,12 @@ class Plan:
             return
         Kt = Cout * kh * kw
         if tap:
-            wt = self.alloc(Cin * Kt)
-            g.add("lr_weight_tap", conv.weight, wt, Cout, Cin, kh * kw, 1)
-            wt_op = self.cast_h(g, wt) if hh else wt
+            if hh:
+                wt_op = self.alloc(Cin * Kt, torch.bfloat16)
+                g.add("lr_weight_tap_h", conv.weight, wt_op, Cout, Cin, kh * kw, 1)
+            else:
+                wt_op = self.alloc(Cin * Kt)
+                g.add("lr_weight_tap", conv.weight, wt_op, Cout, Cin, kh * kw, 1)
             if igemm:                                             # dx = conv(dy, mirrored taps) (+ residual): same kernel
                 g.add("lr_conv3x3_bf16", y.grad, wt_op, x.grad, dx_residual, 0, F, Hs, Ws, Cout, Cin, 1)
                 return

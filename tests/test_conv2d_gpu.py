@@ -74,6 +74,30 @@ def test_im2col_reads_uint8_frames_in_place(cuda_device, k, stride, pad):
     torch.testing.assert_close(got, ref, rtol=1e-6, atol=1e-6)
 
 
+@pytest.mark.parametrize("H,W,dt", [(88, 88, torch.float32), (88, 88, torch.bfloat16), (21, 30, torch.float32), (44, 44, torch.bfloat16)])
+def test_stem_patch_rows_7x7_stride2(cuda_device, H, W, dt):
+    """The ResNet stem's patch matrix (7x7 / stride 2 / pad 3 on uint8 frames, row pitch 152 = 147 columns + zero tail)
+    takes the staged one-block-per-output-row kernel; fp32 and bf16 rows, odd sizes, against unfold."""
+    from multimodal_lipread_b200 import _lib as L
+    from multimodal_lipread_b200.model_base import video_layout
+    torch.manual_seed(H)
+    B, T = 2, 3
+    lips = torch.randint(0, 256, (B, T, H, W, 3), dtype=torch.uint8)
+    x = (lips.float() / 255.0).permute(0, 1, 4, 2, 3).reshape(B * T, 3, H, W)
+    ref = Fn.unfold(x, 7, padding=3, stride=2)
+    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    d = lips.cuda()
+    (is_u8, _, _, _, _, sb, st, sc, sh, sw), scale = video_layout(d)
+    col = torch.full((B * T * Ho * Wo, 152), float("nan"), device="cuda", dtype=dt)
+    fn = L.lib.lr_im2col if dt == torch.float32 else L.lib.lr_im2col_h
+    L.check(fn(d.data_ptr(), int(is_u8), float(scale), B * T, T, sb, st, sc, sh, sw, H, W, 3, 7, 7, 2, 3, 0, Ho, Wo,
+               col.data_ptr(), 152, torch.cuda.current_stream().cuda_stream))
+    got = col[:, :147].float().cpu().view(B * T, Ho * Wo, 147).permute(0, 2, 1)
+    want = ref if dt == torch.float32 else ref.to(torch.bfloat16).float()
+    torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
+    assert col[:, 147:].float().abs().sum().item() == 0
+
+
 @pytest.mark.parametrize("k,stride,pad,H,W", [(2, 2, 0, 8, 11), (3, 2, 1, 9, 10), (3, 2, 1, 22, 22)])
 def test_maxpool_fwd_bwd(cuda_device, k, stride, pad, H, W):
     from multimodal_lipread_b200 import kernels as K
