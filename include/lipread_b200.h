@@ -408,6 +408,10 @@ int lr_maxpool_bwd_h(const void* dy, const unsigned char* arg, void* dx, int F, 
  *   lr_conv3x3_wgrad_bf16  dwp[Cout][9*Cin] (fp32, tap-major) += dy^T * shifted(x), split over pixel blocks, TMA reduce-add.
  * replaces: torchvision BasicBlock conv1 / conv2 of the ResNet-18 trunks (video/models/resnet_lstm.py:79-110,
  * audio_video/models/ef_cnn_lstm_resnet.py:62-64,86, audio/models/resnet_model.py:12-17), forward, dgrad and wgrad. */
+/* up[f, 2 ho, 2 wo, :] = dy[f, ho, wo, :], zero elsewhere, on the input grid [F, Hi, Wi, C] (bf16, C % 8 == 0): the
+ * input gradient of a 3x3 / stride-2 / pad-1 convolution (torchvision BasicBlock conv1 of layer2 / 3 / 4,
+ * video/models/resnet_lstm.py:79-110) is then lr_conv3x3_bf16(up, mirrored taps, flip = 1) -- no transposed patch matrix. */
+int lr_zero_stuff2_h(const void* dy, void* up, int F, int Ho, int Wo, int Hi, int Wi, int C, lr_stream_t stream);
 int lr_conv3x3_bf16(const void* x, const void* wt, void* y, const void* R, double* stats, int F, int H, int W, int Cin,
                     int N, int flip, lr_stream_t stream);
 int lr_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dwp, int F, int H, int W, int Cin, int Cout,

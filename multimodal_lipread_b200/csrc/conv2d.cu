@@ -297,6 +297,27 @@ maxpool_bwd_kernel(const T* __restrict__ dy, const unsigned char* __restrict__ a
     }
 }
 
+// ------------------------------------------------------------------------------------------ zero stuffing
+// up[f, 2 ho, 2 wo, :] = dy[f, ho, wo, :], zero elsewhere, on the INPUT grid [F, Hi, Wi, C] of a stride-2 convolution.
+// The input gradient of a 3x3 / stride-2 / pad-1 convolution is the stride-1 correlation of this map with the mirrored
+// taps -- i.e. exactly what the implicit-GEMM kernel computes with flip = 1 -- so the transposed patch matrix
+// ([input pixels][9 Cout], three quarters of it zeros: 1 GB for the first stride-2 block of the benchmark) is never
+// written.  One 16-byte store per thread (8 bf16 channels).
+__global__ void __launch_bounds__(TH)
+zero_stuff2_kernel(const uint4* __restrict__ dy, uint4* __restrict__ up, int F, int Ho, int Wo, int Hi, int Wi, int c8n) {
+    const long long total = (long long)F * Hi * Wi * c8n;
+    for (long long i = (long long)blockIdx.x * TH + threadIdx.x; i < total; i += (long long)gridDim.x * TH) {
+        const int c = (int)(i % c8n);
+        long long t = i / c8n;
+        const int w = (int)(t % Wi); t /= Wi;
+        const int h = (int)(t % Hi), f = (int)(t / Hi);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (!((h | w) & 1) && (h >> 1) < Ho && (w >> 1) < Wo)
+            v = dy[(((long long)f * Ho + (h >> 1)) * Wo + (w >> 1)) * c8n + c];
+        up[i] = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ dropout
 // Counter-based generator: keep(i) = hash(seed, step, i) >= p.  `step` lives on the device and is advanced by
 // lr_rng_tick once per training step, so a captured CUDA graph draws a fresh mask on every replay.
@@ -488,6 +509,19 @@ extern "C" int lr_maxpool_bwd(const float* dy, const unsigned char* arg, float* 
 extern "C" int lr_maxpool_bwd_h(const void* dy, const unsigned char* arg, void* dx, int F, int H, int W, int C, int k,
                                 int stride, int pad, lr_stream_t stream) {
     return maxpool_bwd_impl<nn::bf16>(static_cast<const nn::bf16*>(dy), arg, static_cast<nn::bf16*>(dx), F, H, W, C, k, stride, pad, stream);
+}
+
+extern "C" int lr_zero_stuff2_h(const void* dy, void* up, int F, int Ho, int Wo, int Hi, int Wi, int C, lr_stream_t stream) {
+    LR_CHECK_ARG(F >= 0 && Ho > 0 && Wo > 0 && Hi >= 2 * Ho - 1 && Wi >= 2 * Wo - 1 && C > 0 && (C & 7) == 0,
+                 "lr_zero_stuff2_h: bad shape (C %% 8, Hi >= 2 Ho - 1)");
+    if (F == 0) return LR_OK;
+    LR_CHECK_ARG(dy && up, "lr_zero_stuff2_h: null pointer");
+    LR_CHECK_ALIGN(dy); LR_CHECK_ALIGN(up);
+    c2::zero_stuff2_kernel<<<c2::grid_for((long long)F * Hi * Wi * (C >> 3)), c2::TH, 0, stream>>>(
+        static_cast<const uint4*>(dy), static_cast<uint4*>(up), F, Ho, Wo, Hi, Wi, C >> 3);
+    lr::count_launch();
+    LR_CHECK_LAUNCH("zero_stuff2_kernel");
+    return LR_OK;
 }
 
 extern "C" int lr_dropout_fwd(const float* x, float* y, unsigned char* mask, long long n, float p,

@@ -919,6 +919,13 @@ class Plan:
             if igemm:                                             # dx = conv(dy, mirrored taps) (+ residual): same kernel
                 g.add("lr_conv3x3_bf16", y.grad, wt_op, x.grad, dx_residual, 0, F, Hs, Ws, Cout, Cin, 1)
                 return
+            if (hh and kh == 3 and kw == 3 and st_ == 2 and pd == 1 and pw == 1 and Cin % 64 == 0 and Cout % 64 == 0
+                    and Ws <= 128 and os.environ.get("LIPREAD_IGEMM", "1") == "1"):
+                # stride 2: dy zero-stuffed onto the input grid, then the same stride-1 implicit-GEMM kernel
+                up = self.workspace(rows_in * Cout, h=True)
+                g.add("lr_zero_stuff2_h", y.grad, up, F, Ho, Wo, Hs, Ws, Cout)
+                g.add("lr_conv3x3_bf16", up, wt_op, x.grad, dx_residual, 0, F, Hs, Ws, Cout, Cin, 1)
+                return
             colT = self.workspace(rows_in * Kt, h=hh)
             g.add("lr_im2col_tap" + sfx, y.grad, F, Ho, Wo, Cout, kh, kw, st_, pd, pw, 1, Hs, Ws, colT)
             self.gemm_auto(g, colT, Kt, 0, wt_op, Kt, 0, x.grad, Cin, rows_in, Cin, Kt, R=dx_residual, ldr=Cin, h=hh)

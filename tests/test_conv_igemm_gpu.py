@@ -63,3 +63,30 @@ def test_conv3x3_forward_dgrad_wgrad(cuda_device, F, H, W, Cin, Cout):
     wref = g0.double() + _tap(wref)
     err = (dwp.double() - wref).abs().max().item()
     assert err <= 3e-5 * wref.abs().max().item() + 1e-4, (err, wref.abs().max().item())
+
+
+@pytest.mark.parametrize("F,Hi,Wi,Cin,Cout", [(9, 22, 22, 64, 128), (11, 11, 11, 128, 256), (23, 6, 6, 256, 512), (3, 10, 15, 64, 64),
+                                              (4, 21, 30, 64, 128)])
+def test_stride2_input_gradient_through_zero_stuffing(cuda_device, F, Hi, Wi, Cin, Cout):
+    """The input gradient of a 3x3 / stride-2 / pad-1 convolution (BasicBlock conv1 of layer2 / 3 / 4) as
+    lr_zero_stuff2_h + lr_conv3x3_bf16(flip = 1) against conv_transpose2d in float64 on the same bf16 operands, even and
+    odd input sizes, with a residual."""
+    L = _lib()
+    g = torch.Generator().manual_seed(F * 17 + Hi + Cin)
+    Ho, Wo = (Hi - 1) // 2 + 1, (Wi - 1) // 2 + 1
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(torch.bfloat16).cuda()
+    dy = torch.randn(F, Ho, Wo, Cout, generator=g).to(torch.bfloat16).cuda()
+    res = torch.randn(F, Hi, Wi, Cin, generator=g).to(torch.bfloat16).cuda()
+    up = torch.full((F, Hi, Wi, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(L.lib.lr_zero_stuff2_h(dy.data_ptr(), up.data_ptr(), F, Ho, Wo, Hi, Wi, Cout, _s()))
+    want_up = torch.zeros(F, Hi, Wi, Cout, dtype=torch.bfloat16, device="cuda")
+    want_up[:, 0:2 * Ho:2, 0:2 * Wo:2] = dy
+    assert torch.equal(up, want_up)
+    wtd = w.permute(1, 2, 3, 0).reshape(Cin, -1).contiguous()
+    dx = torch.full((F, Hi, Wi, Cin), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(L.lib.lr_conv3x3_bf16(up.data_ptr(), wtd.data_ptr(), dx.data_ptr(), res.data_ptr(), 0, F, Hi, Wi, Cout, Cin, 1, _s()))
+    x0 = torch.zeros(F, Cin, Hi, Wi, dtype=torch.float64, device="cuda", requires_grad=True)
+    Fn.conv2d(x0, w.double(), stride=2, padding=1).backward(dy.double().permute(0, 3, 1, 2))
+    dref = x0.grad.permute(0, 2, 3, 1) + res.double()
+    err = (dx.double() - dref).abs().max().item()
+    assert err <= 2.0 ** -8 * dref.abs().max().item(), (err, dref.abs().max().item())
