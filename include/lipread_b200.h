@@ -223,6 +223,9 @@ int lr_im2col_tap(const float* x, int F, int Hs, int Ws, int C, int kh, int kw, 
 int lr_weight_tap(const float* src, float* dst, int Cout, int Cin, int kk, int mode, lr_stream_t stream);
 /* modes 0 and 1 straight into the bf16 operand of the tensor-core convolutions (precision "bf16") */
 int lr_weight_tap_h(const float* src, void* dst, int Cout, int Cin, int kk, int mode, lr_stream_t stream);
+/* All tap-major bf16 operands of a model in one launch: `table` = n device entries of four 64-bit words
+ * {src (const float*), dst (bf16*), Cout | Cin << 32, kk | mode << 32}, modes 0 / 1; max_elems = the largest Cout*Cin*kk. */
+int lr_weight_tap_batch_h(const void* table, int n, long long max_elems, lr_stream_t stream);
 /* wt[c][k*kk + rs] (row pitch ldt) = w[k][c][rs]: the dgrad weight of a dense convolution. */
 int lr_weight_transpose(const float* w, float* wt, int Cout, int Cin, int kk, long long ldt, lr_stream_t stream);
 

@@ -210,6 +210,23 @@ weight_tap_kernel(const float* __restrict__ src, TD* __restrict__ dst, int Cout,
     }
 }
 
+// Every tap-major bf16 operand of a model in ONE launch (modes 0 and 1 of weight_tap_kernel): the weights only change in
+// the optimizer step, so all re-layouts of a training step run up front from a device table -- 38 launches of ~9 us
+// each in the ResNet-18 plan become one.  blockIdx.y = table entry.
+struct WTapEntry { const float* src; nn::bf16* dst; int Cout, Cin, kk, mode; };
+static_assert(sizeof(WTapEntry) == 32, "the host packs an entry as four 64-bit words");
+__global__ void __launch_bounds__(TH)
+weight_tap_batch_kernel(const WTapEntry* __restrict__ tab) {
+    const WTapEntry e = tab[blockIdx.y];
+    const int n = e.Cout * e.Cin * e.kk;
+    for (int i = blockIdx.x * TH + threadIdx.x; i < n; i += gridDim.x * TH) {
+        int k, c, rs;
+        if (e.mode == 0) { c = i % e.Cin; const int t = i / e.Cin; rs = t % e.kk; k = t / e.kk; }
+        else { k = i % e.Cout; const int t = i / e.Cout; rs = t % e.kk; c = t / e.kk; }
+        e.dst[i] = __float2bfloat16_rn(e.src[(k * e.Cin + c) * e.kk + rs]);
+    }
+}
+
 // wt[c][k][rs] = w[k][c][rs]  (row pitch of wt = ldt >= Cout*kk, tail zeroed by the caller once)
 __global__ void __launch_bounds__(TH)
 weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin, int kk, long long ldt) {
@@ -448,6 +465,19 @@ extern "C" int lr_weight_tap_h(const float* src, void* dst, int Cout, int Cin, i
         src, static_cast<nn::bf16*>(dst), Cout, Cin, kk, mode);
     lr::count_launch();
     LR_CHECK_LAUNCH("weight_tap_kernel");
+    return LR_OK;
+}
+
+extern "C" int lr_weight_tap_batch_h(const void* table, int n, long long max_elems, lr_stream_t stream) {
+    LR_CHECK_ARG(n >= 0 && max_elems >= 0 && max_elems < (1LL << 31), "lr_weight_tap_batch_h: bad argument");
+    if (n == 0 || max_elems == 0) return LR_OK;
+    LR_CHECK_ARG(table, "lr_weight_tap_batch_h: null pointer");
+    LR_CHECK_ALIGN(table);
+    long long bx = (max_elems + 4LL * c2::TH - 1) / (4LL * c2::TH);          // about four elements per thread for the largest
+    if (bx > 256) bx = 256;
+    c2::weight_tap_batch_kernel<<<dim3((unsigned)bx, (unsigned)n), c2::TH, 0, stream>>>(static_cast<const c2::WTapEntry*>(table));
+    lr::count_launch();
+    LR_CHECK_LAUNCH("weight_tap_batch_kernel");
     return LR_OK;
 }
 

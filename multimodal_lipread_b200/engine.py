@@ -320,6 +320,7 @@ class Plan:
         # tcgen05 kind::f16 on a bf16 shadow of the weights; per-frame vectors, heads, LSTM stay fp32 / tf32
         self.h = precision == "bf16"
         self._uses_shadow = False
+        self.weight_taps = []          # (weight, bf16 tap-major operand, Cout, Cin, taps, mode): re-laid out once per step
         self.fwd, self.bwd_rev = OpList(), []          # bwd_rev: groups appended in forward order, run reversed
         self.bufs = []
         self.sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
@@ -835,7 +836,7 @@ class Plan:
         if tap and hh:                                         # tap-major bf16 operand in one launch
             wmat = None
             wop_tap = self.alloc(Cout * K, torch.bfloat16)
-            self.fwd.add("lr_weight_tap_h", conv.weight, wop_tap, Cout, Cin, kh * kw, 0)
+            self.weight_taps.append((conv.weight, wop_tap, Cout, Cin, kh * kw, 0))     # one batched launch per step
         elif tap:
             wmat = self.alloc(Cout * K)
             self.fwd.add("lr_weight_tap", conv.weight, wmat, Cout, Cin, kh * kw, 0)
@@ -912,7 +913,7 @@ class Plan:
         if tap:
             if hh:
                 wt_op = self.alloc(Cin * Kt, torch.bfloat16)
-                g.add("lr_weight_tap_h", conv.weight, wt_op, Cout, Cin, kh * kw, 1)
+                self.weight_taps.append((conv.weight, wt_op, Cout, Cin, kh * kw, 1))
             else:
                 wt_op = self.alloc(Cin * Kt)
                 g.add("lr_weight_tap", conv.weight, wt_op, Cout, Cin, kh * kw, 1)

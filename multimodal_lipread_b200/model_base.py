@@ -207,6 +207,11 @@ class ModelPlan(engine.Plan):
         self.pre.add("lr_memset", self.stats, self.stats.numel() * 8)
         if self._uses_shadow:                          # precision "bf16": refresh the bf16 shadow of the weights
             self.pre.add("lr_cast_bf16", self.flat.flat, self.flat.shadow(), self.flat.numel)
+        if self.weight_taps:                           # every tap-major bf16 conv operand of the plan, one launch
+            rows = [[w.data_ptr(), d.data_ptr(), co | (ci << 32), kk | (mode << 32)] for w, d, co, ci, kk, mode in self.weight_taps]
+            self.wtap_table = torch.tensor(rows, dtype=torch.int64, device=self.dev)
+            self.bufs.append(self.wtap_table)
+            self.pre.add("lr_weight_tap_batch_h", self.wtap_table, len(rows), max(co * ci * kk for _, _, co, ci, kk, _ in self.weight_taps))
         if self.rng_step is not None:
             self.pre.add("lr_rng_tick", self.rng_step)
         self.pre_bwd = engine.OpList()
