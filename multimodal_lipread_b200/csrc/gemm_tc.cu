@@ -37,7 +37,7 @@
 
 namespace tc {
 
-constexpr int BM = 128, MAX_STAGES = 4, THREADS = 192, MAX_MT = 8;
+constexpr int BM = 128, MAX_STAGES = 8, THREADS = 192, MAX_MT = 8;
 constexpr int A_STAGE_BYTES = BM * 128;        // 16 KB: 128 rows of one 128-byte swizzle span
 // per operand type: elements per 128-byte span = reduce-elements per stage (K-major) = MN-elements per chunk (MN-major)
 template <typename TO> struct Op { static constexpr int BK = 128 / (int)sizeof(TO); };
@@ -46,6 +46,7 @@ constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;                    // four 32-
 
 struct P {
     int M, N, K, BN, stages;
+    int sw;              // bytes per shared-memory operand row = swizzle span: 128, or 64 / 32 for thin K (K-major bf16 only)
     int mt;              // consecutive M tiles per CTA (1 unless ksplit == 1 and the output leaves through TMA)
     int tile_cols;       // TMEM columns per tile
     int kchunk;          // reduce-dimension elements handled by one CTA (multiple of BK); gridDim.z CTAs split K
@@ -127,6 +128,14 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
 }
+// the same for a 64- or 32-byte row (thin K: K <= 32 / 16 bf16 elements): rows at a `sw`-byte pitch, 8-row groups
+// 8 * sw bytes apart, layout type 4 = SWIZZLE_64B, 6 = SWIZZLE_32B (TMA writes it with the matching swizzle mode).
+// A 128 x 16 operand then takes 4 KB of shared memory instead of a 16 KB slot that is three quarters zero fill, so
+// four times as many tiles are in flight per SM.
+__device__ __forceinline__ uint64_t make_desc_k_sw(uint32_t saddr, int sw) {
+    const uint64_t lt = sw == 128 ? 2ull : (sw == 64 ? 4ull : 6ull);
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((8 * sw) >> 4) << 32) | (1ull << 46) | (lt << 61);
+}
 // MN-major operand.  For 32-bit (tf32) operands the only MN-major shared-memory layout the tensor core accepts
 // is the 128-byte swizzle with a 32-byte base (layout type 1, CUTLASS Layout_MN_SW128_32B_Atom; TMA writes it
 // with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): the tile is stored as chunks of 32 MN-contiguous floats; inside a
@@ -200,8 +209,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int kend = min(p.K, kbeg + p.kchunk);
     const int num_kb = (kend - kbeg + BK - 1) / BK;
     const int b_chunks = (p.BN + BK - 1) / BK;
-    const uint32_t b_stage_bytes = B_MN ? (uint32_t)b_chunks * CHUNK_BYTES : (uint32_t)p.BN * 128u;
-    const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+    const uint32_t a_stage_bytes = (A_MN || B_MN) ? (uint32_t)A_STAGE_BYTES : (uint32_t)BM * (uint32_t)p.sw;
+    const uint32_t b_stage_bytes = B_MN ? (uint32_t)b_chunks * CHUNK_BYTES : (uint32_t)p.BN * (uint32_t)((A_MN || B_MN) ? 128 : p.sw);
+    const uint32_t stage_bytes = a_stage_bytes + b_stage_bytes;
     const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;        // 1024 B alignment for SWIZZLE_128B
     const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[MAX_STAGES]);
     const uint32_t tmem_full = smem_u32(&bars[2 * MAX_STAGES]);
@@ -241,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
                     if (it < 6) LR_STAMP(2 + it);
-                    const uint32_t a_dst = tiles + s * stage_bytes, b_dst = a_dst + A_STAGE_BYTES;
+                    const uint32_t a_dst = tiles + s * stage_bytes, b_dst = a_dst + a_stage_bytes;
                     mbar_expect_tx(full0 + 8 * s, stage_bytes);
                     const int k0 = kbeg + kb * BK;
                     if (A_MN) {
@@ -270,14 +280,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(full0 + 8 * s, ph);
                     if (it < 6) LR_STAMP(8 + it);
                     fence_after();
-                    const uint32_t a_src = tiles + s * stage_bytes, b_src = a_src + A_STAGE_BYTES;
-                    const uint64_t adesc = A_MN ? (H ? make_desc_mn_sw128_b16(a_src) : make_desc_mn_sw128(a_src)) : make_desc_k_sw128(a_src);
-                    const uint64_t bdesc = B_MN ? (H ? make_desc_mn_sw128_b16(b_src) : make_desc_mn_sw128(b_src)) : make_desc_k_sw128(b_src);
+                    const uint32_t a_src = tiles + s * stage_bytes, b_src = a_src + a_stage_bytes;
+                    const bool thin = !(A_MN || B_MN) && p.sw != 128;                 // both operands K-major at a thin span
+                    const uint64_t adesc = A_MN ? (H ? make_desc_mn_sw128_b16(a_src) : make_desc_mn_sw128(a_src))
+                                                : (thin ? make_desc_k_sw(a_src, p.sw) : make_desc_k_sw128(a_src));
+                    const uint64_t bdesc = B_MN ? (H ? make_desc_mn_sw128_b16(b_src) : make_desc_mn_sw128(b_src))
+                                                : (thin ? make_desc_k_sw(b_src, p.sw) : make_desc_k_sw128(b_src));
+                    const int nk = thin ? p.sw / 32 : 4;                              // MMAs (32 bytes of reduce depth each) per stage
                     // one MMA consumes 32 bytes of reduce-depth (8 tf32 / 16 bf16 elements): K-major: 32 bytes along the
                     // swizzled row (2 address units); MN-major: 8 / 16 reduce-rows of 128 bytes (64 / 128 address units)
                     constexpr int MN_STEP = H ? 128 : 64;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
+                        if (k >= nk) break;
                         if (H) mma_bf16(tmem_t, adesc + (A_MN ? MN_STEP : 2) * k, bdesc + (B_MN ? MN_STEP : 2) * k, idesc,
                                         (kb > 0 || k > 0) ? 1u : 0u);
                         else mma_tf32(tmem_t, adesc + (A_MN ? MN_STEP : 2) * k, bdesc + (B_MN ? MN_STEP : 2) * k, idesc,
@@ -597,7 +612,7 @@ static EncodeTiledFn encode_fn() {
 // row-major matrix [rows][cols] (ld elements, fp32 or bf16) -> tensor map with a {box_cols, box_rows} box whose
 // inner extent is one 128-byte span, 128 B swizzle (the 32-byte-atom flavour for MN-major fp32 operands)
 static int make_map(CUtensorMap* map, const void* base, bool is_bf16, long long rows, long long cols, long long ld,
-                    int box_cols, int box_rows, bool atom32 = false) {
+                    int box_cols, int box_rows, bool atom32 = false, int sw = 128) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return lr::fail(LR_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     const size_t es = is_bf16 ? 2 : 4;
@@ -607,7 +622,8 @@ static int make_map(CUtensorMap* map, const void* base, bool is_bf16, long long 
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                      const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                            : (sw == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (sw == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B)),
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return lr::fail(LR_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return LR_OK;
@@ -669,10 +685,16 @@ static int launch(const void* A, long long lda, int a_trans, const void* B, long
             p.mt = mt;
         }
     }
+    // thin K (K-major bf16 operands, one k-block, K <= 32): 32- / 64-byte operand rows instead of the 128-byte span
+    static const bool thin_env = !(getenv("LIPREAD_GEMM_THIN") && getenv("LIPREAD_GEMM_THIN")[0] == '0');
+    p.sw = 128;
+    if (thin_env && H && !a_trans && !b_trans && nz == 1 && num_kb == 1 && K <= 32) p.sw = K <= 16 ? 32 : 64;
     const int total_kb = num_kb * p.mt;
     static const int st_env = getenv("LIPREAD_GEMM_STAGES") ? atoi(getenv("LIPREAD_GEMM_STAGES")) : 0;
-    // batched tiles: two ring slots (smem per CTA stays small enough for three CTAs per SM: more loads in flight)
-    const int max_stages = st_env >= 1 && st_env <= MAX_STAGES ? st_env : (p.mt > 1 ? 2 : MAX_STAGES);
+    // batched tiles: two ring slots of the 128-byte span (smem per CTA stays small enough for three CTAs per SM: more
+    // loads in flight); thin spans are 4 / 2 times smaller, so every tile of the CTA gets its own slot
+    const int dflt_stages = p.mt > 1 ? (p.sw == 128 ? 2 : (p.sw == 64 ? 4 : 8)) : 4;
+    const int max_stages = st_env >= 1 && st_env <= MAX_STAGES ? st_env : dflt_stages;
     p.stages = total_kb < max_stages ? total_kb : max_stages;
     CUtensorMap ma, mb, mc;
     if (p.tma_out) {
@@ -681,12 +703,14 @@ static int launch(const void* A, long long lda, int a_trans, const void* B, long
     } else {
         memset(&mc, 0, sizeof(mc));
     }
-    int rc = a_trans ? make_map(&ma, A, H, K, M, lda, BK, BK, !H) : make_map(&ma, A, H, M, K, lda, BK, BM);
+    const int bk_box = p.sw == 128 ? BK : p.sw / (int)sizeof(TO);      // elements per operand row of the span
+    int rc = a_trans ? make_map(&ma, A, H, K, M, lda, BK, BK, !H) : make_map(&ma, A, H, M, K, lda, bk_box, BM, false, p.sw);
     if (rc) return rc;
-    rc = b_trans ? make_map(&mb, B, H, K, N, ldb, BK, BK, !H) : make_map(&mb, B, H, N, K, ldb, BK, bn);
+    rc = b_trans ? make_map(&mb, B, H, K, N, ldb, BK, BK, !H) : make_map(&mb, B, H, N, K, ldb, bk_box, bn, false, p.sw);
     if (rc) return rc;
-    const size_t b_stage = b_trans ? (size_t)((bn + BK - 1) / BK) * (size_t)BK * 128 : (size_t)bn * 128;
-    size_t smem = (size_t)p.stages * (A_STAGE_BYTES + b_stage);
+    const size_t b_stage = b_trans ? (size_t)((bn + BK - 1) / BK) * (size_t)BK * 128 : (size_t)bn * (size_t)p.sw;
+    const size_t a_stage = (a_trans || b_trans) ? (size_t)A_STAGE_BYTES : (size_t)BM * (size_t)p.sw;
+    size_t smem = (size_t)p.stages * (a_stage + b_stage);
     if (p.mt > 1) smem += 32768;                                // staging boxes of the epilogue behind the ring
     else if (smem < (size_t)EPI_BYTES) smem = EPI_BYTES;        // one tile: the epilogue slabs reuse the pipeline buffers
     smem += 1024;
