@@ -21,6 +21,7 @@
 // partial of dh_{t-1} for ALL H units, and scatters 32-unit slices to their owners through distributed shared memory,
 // where they are added in fixed source order (deterministic).
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -41,6 +42,7 @@ struct Fwd {
     float* out; long long ldo;
     float* gates; float* cst; float* hprev;
     int B, T, H, nsteps, reverse;
+    int dbg;                             // timing probes only (LIPREAD_LSTM_DBG bit mask; results are garbage when set)
 };
 struct Bwd {
     const float* dout; long long ldo;
@@ -55,6 +57,8 @@ __device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, unsigned rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
@@ -127,19 +131,39 @@ lstm_fwd_tc_kernel(const Fwd p) {
     __nv_bfloat16* const Hs = reinterpret_cast<__nv_bfloat16*>(gbase + G_::A_BYTES + 2 * G_::HB_BYTES + MT * G_::G_BYTES);
 
     // W_hh slice -> the A operand: tile m, k-block kb: [128 rows][128 B], 16-byte chunk j of row r at j ^ (r & 7)
-    for (int idx = tid; idx < MT * 128 * (H / 8); idx += TH) {
-        const int r = idx / (H / 8), jc = idx - r * (H / 8);
-        const int m = r >> 7, rr = r & 127, g = rr >> 5, ul = rr & 31;
-        const float4* src = reinterpret_cast<const float4*>(p.whh + (long long)(g * H + (int)c * UC + 32 * m + ul) * H + 8 * jc);
-        const uint4 v = pack8(__ldg(src), __ldg(src + 1));
-        const int kb = jc >> 3, j = jc & 7;
-        *reinterpret_cast<uint4*>(gA + (size_t)(m * KB + kb) * 16384 + rr * 128 + ((j ^ (rr & 7)) << 4)) = v;
+    // (four chunks = eight 16-byte loads in flight per thread: the 256 KB fp32 slice is a latency chain otherwise)
+    for (int idx0 = tid; idx0 < MT * 128 * (H / 8); idx0 += 4 * TH) {
+        float4 lo[4], hi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * TH;
+            if (idx < MT * 128 * (H / 8)) {
+                const int r = idx / (H / 8), jc = idx - r * (H / 8);
+                const int m = r >> 7, rr = r & 127, g = rr >> 5, ul = rr & 31;
+                const float4* src = reinterpret_cast<const float4*>(p.whh + (long long)(g * H + (int)c * UC + 32 * m + ul) * H + 8 * jc);
+                lo[u] = __ldg(src); hi[u] = __ldg(src + 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * TH;
+            if (idx < MT * 128 * (H / 8)) {
+                const int r = idx / (H / 8), jc = idx - r * (H / 8);
+                const int m = r >> 7, rr = r & 127;
+                const int kb = jc >> 3, j = jc & 7;
+                *reinterpret_cast<uint4*>(gA + (size_t)(m * KB + kb) * 16384 + rr * 128 + ((j ^ (rr & 7)) << 4)) = pack8(lo[u], hi[u]);
+            }
+        }
     }
     if (tid == 0) {
         for (int m = 0; m < MT; ++m) mbar_init(smem_u32(&bars[m]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    constexpr uint32_t TCOLS = MT * 32 < 32 ? 32 : MT * 32;
+    // accumulators per tile.  Measured (profiles/r2_lstm_microbench.txt): the 32 MMAs of a step take 1.24 us; spreading
+    // them over 4 independent accumulators changes nothing (137 -> 138 us at H = 512), i.e. the chain is bound by the
+    // operand fetch of a 128 x 32 x 16 MMA (4 KB of W per instruction), not by the accumulation dependency: one it is
+    constexpr int NA = 1;
+    constexpr uint32_t TCOLS = MT * NA * 32 < 32 ? 32 : MT * NA * 32;
     if (warp == CW) tmem_alloc(smem_u32(&tmem_slot), TCOLS);
     fence_proxy_async();                                  // the A operand was written through the generic proxy
     fence_before();
@@ -183,7 +207,9 @@ lstm_fwd_tc_kernel(const Fwd p) {
         const uint32_t sHprev = sH0 + (uint32_t)((s & 1) ^ 1) * G_::HB_BYTES;     // h_{s-1}
         const uint32_t sHnext = sH0 + (uint32_t)(s & 1) * G_::HB_BYTES;           // h_s
         if (s > 0) {
-            if (NC > 1) cluster_sync(); else __syncthreads();                     // h_{s-1} is complete in every CTA
+            // h_{s-1} is complete in every CTA: the barrier was arrived at right after each thread's part of the exchange
+            // (end of the previous step), so the output stores of that step and this step's fetches overlap its latency
+            if (NC > 1 && !(p.dbg & 8)) cluster_wait(); else __syncthreads();
             if (warp == CW && lane == 0) {
                 fence_proxy_async_all();
                 fence_after();
@@ -191,18 +217,22 @@ lstm_fwd_tc_kernel(const Fwd p) {
 #pragma unroll 1
                 for (int m = 0; m < MT; ++m) {
 #pragma unroll 1
-                    for (int kb = 0; kb < KB; ++kb) {
+                    for (int kb = 0; kb < ((p.dbg & 2) ? 0 : KB); ++kb) {
                         const uint64_t ad = desc_k_sw128(sA + (uint32_t)(m * KB + kb) * 16384u);
                         const uint64_t bd = desc_k_sw128(sHprev + (uint32_t)kb * 4096u);
+                        // NA independent accumulators per tile (k-block kb -> accumulator kb % NA), summed by the epilogue:
+                        // a 128 x 32 x 16 MMA is so short that a single accumulation chain is latency bound
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) mma_bf16(tmem + (uint32_t)(32 * m), ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k)
+                            mma_bf16(tmem + (uint32_t)(32 * (m * NA + (kb % NA))), ad + 2 * k, bd + 2 * k, idesc, (kb >= NA || k) ? 1u : 0u);
                     }
                     mma_commit(smem_u32(&bars[m]));        // tile m's cells run while the MMAs of tile m + 1 .. are in flight
                 }
             }
         }
+        const bool more = s + 1 < p.nsteps;
+        float sv[MT][2][6];                                // i, f, g, o, c, h of this step's cells: stored after the exchange
         if (warp < CW) {
-            const bool more = s + 1 < p.nsteps;
 #pragma unroll
             for (int m = 0; m < MT; ++m) {
                 const int col = (int)c * UC + 32 * m + ul;
@@ -211,28 +241,29 @@ lstm_fwd_tc_kernel(const Fwd p) {
                     mbar_wait(smem_u32(&bars[m]), (uint32_t)(s - 1) & 1u);
                     fence_after();
                     float v[8];
-                    tmem_ld8(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * m + 8 * cq), v);
+                    tmem_ld8(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * m * NA + 8 * cq), v);
+#pragma unroll
+                    for (int a = 1; a < NA; ++a) {
+                        float w[8];
+                        tmem_ld8(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * (m * NA + a) + 8 * cq), w);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] += w[i];
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) Gm[(32 * q + lane) * GP + 8 * cq + i] = v[i];
                     compute_sync();
                 }
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
-                    const int bl = bl0 + i, b = b0 + bl;
+                    const int bl = bl0 + i;
                     float a[4];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) a[g] = (s > 0 ? Gm[(32 * g + ul) * GP + bl] : 0.f) + xp[m][g][i] + bias[m][g];
                     const float ig = sigm(a[0]), fg = sigm(a[1]), gg = tanh_(a[2]), og = sigm(a[3]);
                     const float cn = fg * cstate[m][i] + ig * gg;
                     const float hn = og * tanh_(cn);
-                    if (b < p.B) {
-                        const long long row = (long long)b * p.T + t;
-                        if (p.gates) { float* gp = p.gates + row * 4 * H; gp[col] = ig; gp[H + col] = fg; gp[2 * H + col] = gg; gp[3 * H + col] = og; }
-                        if (p.cst) p.cst[row * H + col] = cn;
-                        if (p.hprev) p.hprev[row * H + col] = hlast[m][i];
-                        p.out[row * p.ldo + col] = hn;
-                    }
-                    cstate[m][i] = cn; hlast[m][i] = hn;
+                    sv[m][i][0] = ig; sv[m][i][1] = fg; sv[m][i][2] = gg; sv[m][i][3] = og; sv[m][i][4] = cn; sv[m][i][5] = hn;
+                    cstate[m][i] = cn;
                     if (more) {
                         if (NC > 1) {
                             Hs[bl * HSP + 32 * m + ul] = __float2bfloat16(hn);
@@ -245,22 +276,47 @@ lstm_fwd_tc_kernel(const Fwd p) {
                 }
             }
             if (more) {
-                fetch_xp(s + 1);
                 if (NC > 1) {
-                    // h_s (bf16) -> the next step's operand buffer of every CTA of the cluster, 16 bytes at a time
+                    // h_s (bf16) -> the next step's operand buffer of every CTA of the cluster, 16 bytes at a time:
+                    // (chunk, destination) pairs dealt to all 512 threads, consecutive lanes = consecutive chunks of a row
                     compute_sync();                        // the staged h_s is complete
-                    for (int idx = tid; idx < 32 * (UC / 8); idx += CW * 32) {
-                        const int bl = idx / (UC / 8), jc = idx - bl * (UC / 8);
+                    for (int idx = tid; idx < ((p.dbg & 1) ? 0 : 32 * (UC / 8) * NC); idx += CW * 32) {
+                        const int ch = idx % (32 * (UC / 8));
+                        const unsigned d = (unsigned)(idx / (32 * (UC / 8)));
+                        const int bl = ch / (UC / 8), jc = ch - bl * (UC / 8);
                         const uint4 v = *reinterpret_cast<const uint4*>(Hs + bl * HSP + 8 * jc);
                         const int colg = (int)c * UC + 8 * jc, kb = colg >> 6, j = (colg & 63) >> 3;
                         const uint32_t dst = sHnext + (uint32_t)kb * 4096u + (uint32_t)bl * 128u + (uint32_t)((j ^ (bl & 7)) << 4);
-#pragma unroll 4
-                        for (unsigned d = 0; d < (unsigned)NC; ++d) st_cluster_v4(map_to_rank(dst, d), v);
+                        st_cluster_v4(map_to_rank(dst, d), v);
                     }
                 }
                 fence_proxy_async_all();                   // generic-proxy writes -> visible to the tensor core's reads
             }
             fence_before();
+        }
+        if (more && NC > 1 && !(p.dbg & 8)) cluster_arrive();   // this thread's part of h_s is on its way
+        if (warp < CW) {
+            // ---- off the critical path: this step's outputs and the next step's input projection
+            if (more && !(p.dbg & 16)) fetch_xp(s + 1);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                const int col = (int)c * UC + 32 * m + ul;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int b = b0 + bl0 + i;
+                    if (b < p.B && !(p.dbg & 4)) {
+                        const long long row = (long long)b * p.T + t;
+                        if (p.gates) {
+                            float* gp = p.gates + row * 4 * H;
+                            gp[col] = sv[m][i][0]; gp[H + col] = sv[m][i][1]; gp[2 * H + col] = sv[m][i][2]; gp[3 * H + col] = sv[m][i][3];
+                        }
+                        if (p.cst) p.cst[row * H + col] = sv[m][i][4];
+                        if (p.hprev) p.hprev[row * H + col] = hlast[m][i];
+                        p.out[row * p.ldo + col] = sv[m][i][5];
+                    }
+                    hlast[m][i] = sv[m][i][5];
+                }
+            }
         }
     }
     if (NC > 1) cluster_sync(); else __syncthreads();      // nobody leaves while its shared memory may still be written
@@ -357,9 +413,11 @@ lstm_bwd_tc_kernel(const Bwd p) {
         }
     };
     if (warp < CW) fetch(p.nsteps - 1);
+    if (NC > 1 && p.nsteps > 1) cluster_arrive();              // pairs with the first iteration's wait (the buffer starts free)
 
     for (int s = p.nsteps - 1; s >= 0; --s) {
         const int t = p.reverse ? p.T - 1 - s : s;
+        float pdv[MT][2][4];
         if (warp < CW) {
             // ---- dgates of the CTA's units at step t: fp32 out, bf16 straight into the B operand (k-blocks of 64 local
             // gate rows r = 128 m + 32 g + u, [32 batch rows][128 B] swizzled)
@@ -375,10 +433,8 @@ lstm_bwd_tc_kernel(const Bwd p) {
                     const float dct = dc[m][i] + dht * og * (1.f - tc * tc);
                     const float pd[4] = {dct * gg * ig * (1.f - ig), dct * cprev * fg * (1.f - fg),
                                          dct * ig * (1.f - gg * gg), dht * tc * og * (1.f - og)};
-                    if (b < p.B) {
-                        float* o = p.dgates + ((long long)b * p.T + t) * G4;
-                        o[col] = pd[0]; o[H + col] = pd[1]; o[2 * H + col] = pd[2]; o[3 * H + col] = pd[3];
-                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) pdv[m][i][g] = pd[g];   // stored to HBM after the MMAs have been issued
                     dc[m][i] = dct * fg;                     // rows beyond B: all inputs are zero, everything stays zero
                     if (s > 0) {
 #pragma unroll
@@ -391,14 +447,37 @@ lstm_bwd_tc_kernel(const Bwd p) {
                 }
             }
         }
-        if (s == 0) break;                                  // no step before the first one: dh_{-1} is not needed
+        auto store_dgates = [&]() {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                const int col = (int)c * UC + 32 * m + ul;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int b = b0 + bl0 + i;
+                    if (b < p.B) {
+                        float* o = p.dgates + ((long long)b * p.T + t) * G4;
+                        o[col] = pdv[m][i][0]; o[H + col] = pdv[m][i][1]; o[2 * H + col] = pdv[m][i][2]; o[3 * H + col] = pdv[m][i][3];
+                    }
+                }
+            }
+        };
+        if (s == 0) {                                       // no step before the first one: dh_{-1} is not needed
+            if (warp < CW) store_dgates();
+            break;
+        }
         if (warp < CW) {
-            fetch(s - 1);
             fence_proxy_async();
             fence_before();
         }
-        // the B operand is complete; the receive buffer of the previous step has been consumed by every CTA
-        if (NC > 1) cluster_sync(); else __syncthreads();
+        // the B operand is complete (a CTA-local matter).  That every CTA has consumed the receive buffer of the previous
+        // step is a cluster matter, but only the scatter below needs it: the barrier was ARRIVED at right after the sums
+        // were read (end of the previous iteration / before the loop) and is waited for just before the scatter, so its
+        // latency is off the MMA's critical path
+        __syncthreads();
+        if (warp < CW) {                                    // while the MMAs run: this step's dgates to HBM, next step's inputs
+            store_dgates();
+            fetch(s - 1);
+        }
         if (warp == CW && lane == 0) {
             fence_proxy_async();
             fence_after();
@@ -414,6 +493,7 @@ lstm_bwd_tc_kernel(const Bwd p) {
                 }
             mma_commit(smem_u32(&bars[0]));
         }
+        if (NC > 1) cluster_wait();                            // every CTA's receive buffer is free (arrived: see above)
         if (warp < CW) {
             mbar_wait(smem_u32(&bars[0]), (uint32_t)(p.nsteps - 1 - s) & 1u);
             fence_after();
@@ -449,6 +529,8 @@ lstm_bwd_tc_kernel(const Bwd p) {
                     dh[m][i] = a;
                 }
         }
+        if (NC > 1 && s > 1) cluster_arrive();                 // this CTA's receive buffer may be overwritten again (the
+                                                               // next iteration waits for it unless it is the last one)
     }
     if (NC > 1) cluster_sync(); else __syncthreads();
     if (warp == CW) {
@@ -494,6 +576,8 @@ extern "C" int lr_lstm_fwd_tc(const float* xproj, long long ldx, const float* bh
     lt::Fwd p;
     p.xproj = xproj; p.ldx = ldx; p.bhh = bhh; p.whh = whh; p.out = out; p.ldo = ldo; p.gates = gates; p.cst = cst; p.hprev = hprev;
     p.B = B; p.T = T; p.H = H; p.nsteps = nsteps; p.reverse = reverse;
+    static const int dbg = getenv("LIPREAD_LSTM_DBG") ? atoi(getenv("LIPREAD_LSTM_DBG")) : 0;
+    p.dbg = dbg;
     int rc;
     if (H == 128) rc = lt::launch<128>(lt::lstm_fwd_tc_kernel<128>, p, B, lt::Geo<128>::FWD_SMEM, stream, "lstm_fwd_tc_kernel");
     else if (H == 256) rc = lt::launch<256>(lt::lstm_fwd_tc_kernel<256>, p, B, lt::Geo<256>::FWD_SMEM, stream, "lstm_fwd_tc_kernel");
