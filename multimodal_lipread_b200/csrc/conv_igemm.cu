@@ -16,6 +16,8 @@
 //   warp 0      TMA producer (one lane)          warp 1      TMEM allocation + MMA issue (one lane)
 //   warps 2..5  epilogue: tcgen05.ld -> (+ residual) -> bf16 -> swizzled staging -> coalesced 16-byte stores, and the
 //               per-channel sum / sum of squares of the rounded values (train-mode BatchNorm statistics)
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace ig {
@@ -321,6 +323,18 @@ extern "C" int lr_conv3x3_bf16(const void* x, const void* wt, void* y, const voi
     const size_t stage = (size_t)p.nm * 16384 + (size_t)p.BN * 128;
     int stages = (int)((200 * 1024 - 1024) / stage);
     if (stages > ig::MAX_STAGES) stages = ig::MAX_STAGES;
+    {   // The kernel is one tile per CTA: load ramp, main loop and epilogue of a CTA are serial.  With more CTAs than SMs a
+        // ring that lets TWO CTAs share an SM (one's epilogue under the other's main loop) beats a deeper ring for one:
+        // measured (profiles/r2_conv_ring_depth.txt) 22x22x64: 131 -> 84 us, 11x11x128: 74 -> 53, 6x6x256: 57 -> 43;
+        // the 3x3x512 layers have fewer CTAs than SMs and keep the deep ring (51 us; 63 with two stages).
+        static const int cap_env = getenv("LIPREAD_CONV_STAGES") ? atoi(getenv("LIPREAD_CONV_STAGES")) : 0;
+        int cap = cap_env;
+        if (cap < 1 && (long long)tiles * (N / p.BN) > lr::sm_count()) {
+            cap = (int)((113 * 1024 - 1024) / stage);
+            if (cap < 2) cap = 2;
+        }
+        if (cap >= 1 && stages > cap) stages = cap;
+    }
     if (stages > num_kb) stages = num_kb;
     p.stages = stages;
     CUtensorMap mx, mw;
@@ -370,6 +384,15 @@ extern "C" int lr_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dwp, 
     const size_t stage = (size_t)6 * p.krp * 128;        // sized for a full 4-chunk N tile
     int stages = (int)((200 * 1024 - 1024) / stage);
     if (stages > ig::MAX_STAGES) stages = ig::MAX_STAGES;
+    {   // as in the forward kernel: a ring that lets two CTAs share an SM (config 2: 7.13 -> 7.04 ms with it)
+        static const int cap_env = getenv("LIPREAD_WGRAD_STAGES") ? atoi(getenv("LIPREAD_WGRAD_STAGES")) : 0;
+        int cap = cap_env;
+        if (cap < 1 && (long long)mtiles * ntiles * splits > lr::sm_count()) {
+            cap = (int)((113 * 1024 - 1024) / stage);
+            if (cap < 1) cap = 1;
+        }
+        if (cap >= 1 && stages > cap) stages = cap;
+    }
     if (stages > p.per_cta) stages = p.per_cta;
     if (stages < 1) stages = 1;
     p.stages = stages;

@@ -694,7 +694,18 @@ static int launch(const void* A, long long lda, int a_trans, const void* B, long
     // batched tiles: two ring slots of the 128-byte span (smem per CTA stays small enough for three CTAs per SM: more
     // loads in flight); thin spans are 4 / 2 times smaller, so every tile of the CTA gets its own slot
     const int dflt_stages = p.mt > 1 ? (p.sw == 128 ? 2 : (p.sw == 64 ? 4 : 8)) : 4;
-    const int max_stages = st_env >= 1 && st_env <= MAX_STAGES ? st_env : dflt_stages;
+    int max_stages = st_env >= 1 && st_env <= MAX_STAGES ? st_env : dflt_stages;
+    {   // multi-k-block problems with more CTAs than SMs: cap the ring so that two CTAs share an SM (one tile per CTA, so
+        // one CTA's epilogue runs under the other's main loop; config 5: 13.45 -> 13.32 ms, config 2: 7.13 -> 7.07 ms)
+        static const bool occ_off = getenv("LIPREAD_GEMM_2CTA") && getenv("LIPREAD_GEMM_2CTA")[0] == '0';
+        if (!occ_off && p.mt == 1 && p.sw == 128) {
+            const size_t bst = b_trans ? (size_t)((bn + BK - 1) / BK) * (size_t)BK * 128 : (size_t)bn * 128;
+            int cap = (int)((110 * 1024) / (A_STAGE_BYTES + bst));
+            if (cap < 2) cap = 2;
+            const long long ctas = (long long)((M + BM - 1) / BM) * ((N + bn - 1) / bn) * nz;
+            if (ctas > lr::sm_count() && max_stages > cap) max_stages = cap;
+        }
+    }
     p.stages = total_kb < max_stages ? total_kb : max_stages;
     CUtensorMap ma, mb, mc;
     if (p.tma_out) {
