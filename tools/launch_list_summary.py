@@ -43,7 +43,7 @@ for k, f in sorted(fam.items(), key=lambda x: -x[1][1]):
 if len(sys.argv) > 5:
     key, out = sys.argv[4], sys.argv[5]
     opmap = {"tc::gemm_tc_kernel<bf16>": "lr_gemm_bf16", "tc::gemm_tc_kernel<tf32>": "lr_gemm_tf32", "bn::bn_act_fwd_kernel": "lr_bn_act_fwd_h",
-             "cv::conv3x3_kernel": "lr_conv3x3_bf16", "cv::conv3x3_wgrad_kernel": "lr_conv3x3_wgrad_bf16"}
+             "ig::conv3x3_kernel": "lr_conv3x3_bf16", "ig::conv3x3_wgrad_kernel": "lr_conv3x3_wgrad_bf16"}
     fams = {}
     for k, f in fam.items():
         if k in opmap: fams[opmap[k]] = {"dram_bytes": f[2], "launches": f[0]}
