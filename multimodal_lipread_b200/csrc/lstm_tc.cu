@@ -93,11 +93,12 @@ __device__ __forceinline__ uint4 pack8(const float4& a, const float4& b) {
 }
 
 template <int H> struct Geo {
-    static constexpr int MT = 512 / H;               // 128-row gate tiles per CTA
+    static constexpr int MT = H >= 256 ? 512 / H : 1;  // 128-row gate tiles per CTA (H = 128: one tile, 4 CTAs -- a single CTA
+                                                      // with four tiles has 8 cells per thread and step and was slower)
     static constexpr int UC = 32 * MT;               // hidden units per CTA
-    static constexpr int NC = H / UC;                // CTAs per cluster: 1, 4, 16
+    static constexpr int NC = H / UC;                // CTAs per cluster: 4, 4, 16
     static constexpr int KB = H / 64;                // 64-element k-blocks of the forward product
-    static constexpr uint32_t A_BYTES = 128u * 1024u;
+    static constexpr uint32_t A_BYTES = (uint32_t)MT * 128u * (uint32_t)H * 2u;    // the resident W_hh slice: 32 / 128 / 128 KB
     static constexpr uint32_t HB_BYTES = KB * 4096u;                 // one h operand buffer: [32 rows][H] bf16, swizzled
     static constexpr uint32_t G_BYTES = 128u * GP * 4u;              // 16 896
     static constexpr int HSP = UC + 8;                               // staging pitch (bf16 elements): 16-byte aligned rows

@@ -431,11 +431,10 @@ class Plan:
     # ---- op emitters ----------------------------------------------------------------------------------
     def lstm_op(self, which, H, nsteps):
         """Name of the recurrence kernel: the tensor-core walk (csrc/lstm_tc.cu: bf16 W_hh / h operands, tcgen05) under
-        precision "bf16" for H = 256 / 512 and walks of more than one step, else the fp32 kernels.  Measured at B = 32,
-        T = 29 (tools/microbench.py lstm, profiles/r2_lstm_microbench.txt): H = 512 forward 483 -> 139 us, backward
-        580 -> 223 us; H = 256 237 -> 142 / 270 -> 179 us; at H = 128 the fp32 8-CTA cluster kernel (131 / 144 us) still
-        beats the single-CTA tensor-core walk (201 / 160 us: eight cells per thread and step), so it keeps that size."""
-        tc = self.h and H in (256, 512) and nsteps > 1 and os.environ.get("LIPREAD_LSTM_TC", "1") != "0"
+        precision "bf16" for H = 128 / 256 / 512 and walks of more than one step, else the fp32 kernels.  Measured at
+        B = 32, T = 29 (tools/microbench.py lstm, profiles/r2_lstm_microbench.txt), forward / backward: H = 512
+        483 / 580 -> 137 / 196 us, H = 256 237 / 270 -> 127 / 145 us, H = 128 132 / 144 -> 73 / 74 us (4-CTA cluster)."""
+        tc = self.h and H in (128, 256, 512) and nsteps > 1 and os.environ.get("LIPREAD_LSTM_TC", "1") != "0"
         return f"lr_lstm_{which}_tc" if tc else f"lr_lstm_{which}"
 
     def gemm(self, ops, A, lda, at, B, ldb, bt, C, ldc, M, N, K, bias=0, act=ACT_NONE, R=0, ldr=0, stats=0, ksplit=1,
