@@ -44,6 +44,27 @@ __device__ __forceinline__ void build_pixel_table(const Geo& d, int* tab) {
     for (int rc = threadIdx.x; rc < d.rows_t * d.cols_t; rc += TH) tab[rc] = ((rc / d.cols_t) << 16) | (rc % d.cols_t);
 }
 
+// The integer side of the main loops was the bottleneck of these kernels (ncu, round 2: IMAD / IADD3 / ISETP 45 % of the
+// executed instructions, FFMA 7 %: three integer divisions per row segment and one more per unit): the decomposition of
+// a flat item index it -> (unit, row, segment) does not depend on the round, so it is tabulated once per CTA, and the
+// (frame, first row) of the round's units once per round.
+constexpr int MAX_ITEMS = 1024;
+__device__ __forceinline__ void build_item_table(const Geo& d, int* itab) {
+    const int per_unit = d.RB * d.nseg;
+    for (int it = threadIdx.x; it < d.UB * per_unit && it < MAX_ITEMS; it += TH) {
+        const int ul = it / per_unit, rs = it - ul * per_unit, ro = rs / d.nseg;
+        itab[it] = (ul << 20) | (ro << 10) | (rs - ro * d.nseg);
+    }
+}
+// utab[ul] = (frame, first row of the band) of unit u0 + ul; frame = -1 past the last unit
+__device__ __forceinline__ void build_unit_table(const Geo& d, int u0, int2* utab) {
+    if ((int)threadIdx.x < d.UB) {
+        const int u = u0 + (int)threadIdx.x;
+        const int f = u / d.nb;
+        utab[threadIdx.x] = u < (int)d.units ? make_int2(f, (u - f * d.nb) * d.RB) : make_int2(-1, 0);
+    }
+}
+
 // Asynchronously stage tile[ul][r][col][c] = src[f, row0(band) + r, col0 + col, chunk*CC + c] (zero outside
 // [0,SH) x [0,SW) and past the last unit) for the UB units starting at u0; cp.async keeps many 16-byte requests
 // in flight per thread without a register round trip, so a round's loads overlap the previous round's math.
@@ -81,7 +102,7 @@ __device__ __forceinline__ void load_weights(const float* __restrict__ w, int c,
 }
 
 // ------------------------------------------------------------------------------------------ forward
-template <typename T, int K, int S, int WS>
+template <typename T, int K, int S, int WS, int CCT>
 __global__ void __launch_bounds__(TH)
 fwd_kernel(const Geo d, const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y,
            double* __restrict__ stats) {
@@ -89,12 +110,15 @@ fwd_kernel(const Geo d, const T* __restrict__ x, const float* __restrict__ w, T*
     T* smem = reinterpret_cast<T*>(smem_raw);
     __shared__ float ssum[TH], ssq[TH];                 // one slot per thread: [row lane][channel], added in lane order
     __shared__ int tab[MAX_PIX];
+    __shared__ int itab[MAX_ITEMS];
+    __shared__ int2 utab[MAX_UB];
     build_pixel_table(d, tab);
+    build_item_table(d, itab);
     __syncthreads();
-    const int cl = threadIdx.x % d.CC, rl = threadIdx.x / d.CC, nrl = TH / d.CC;
-    const int chunk = blockIdx.y, c = chunk * d.CC + cl;
+    const int cl = threadIdx.x % CCT, rl = threadIdx.x / CCT, nrl = TH / CCT;
+    const int chunk = blockIdx.y, c = chunk * CCT + cl;
     const bool ok = c < d.C;
-    const int tile_floats = d.UB * d.rows_t * d.cols_t * d.CC;
+    const int tile_floats = d.UB * d.rows_t * d.cols_t * CCT;
     const int rounds = (int)((d.units + d.UB - 1) / d.UB);
     float wr[K * K];
     load_weights<K>(w, c, ok, wr);
@@ -107,29 +131,28 @@ fwd_kernel(const Geo d, const T* __restrict__ x, const float* __restrict__ w, T*
         const int nxt = rd + gridDim.x;
         if (nxt < rounds) stage_async(d, x, smem + (buf ^ 1) * tile_floats, tab, nxt * d.UB, chunk, d.H, d.W, d.RB * S, 0, -d.pad, -d.pad);
         cp_async_commit();
+        build_unit_table(d, rd * d.UB, utab);
         cp_async_wait<1>();                             // this round's tile has landed (the prefetch may be in flight)
         __syncthreads();
         const T* tile = smem + buf * tile_floats;
-        const int u0 = rd * d.UB;
         const int per_unit = d.RB * d.nseg;
         for (int it = rl; it < d.UB * per_unit && ok; it += nrl) {       // flat over (unit, row, segment): balanced lanes
           {
-            const int ul = it / per_unit, rs = it - ul * per_unit;
-            const int u = u0 + ul;
-            if (u >= (int)d.units) break;
-            const int f = d.nb == 1 ? u : u / d.nb, hob = (u - f * d.nb) * d.RB;
-            const int ro = rs / d.nseg, seg = rs - ro * d.nseg;
+            const int e = itab[it], ul = e >> 20, ro = (e >> 10) & 1023, seg = e & 1023;
+            const int2 uf = utab[ul];
+            if (uf.x < 0) break;
+            const int f = uf.x, hob = uf.y;
             const int ho = hob + ro, wo0 = seg * WS;
             if (ho >= d.Ho) continue;
             float acc[WS];
 #pragma unroll
             for (int j = 0; j < WS; ++j) acc[j] = 0.f;
-            const T* base = tile + ((long long)(ul * d.rows_t + ro * S) * d.cols_t + wo0 * S) * d.CC + cl;
+            const T* base = tile + ((ul * d.rows_t + ro * S) * d.cols_t + wo0 * S) * CCT + cl;
 #pragma unroll
             for (int kh = 0; kh < K; ++kh) {
                 float xr[NX];
 #pragma unroll
-                for (int i = 0; i < NX; ++i) xr[i] = nn::ld1(base + (kh * d.cols_t + i) * d.CC);
+                for (int i = 0; i < NX; ++i) xr[i] = nn::ld1(base + (kh * d.cols_t + i) * CCT);
 #pragma unroll
                 for (int j = 0; j < WS; ++j)
 #pragma unroll
@@ -153,11 +176,11 @@ fwd_kernel(const Geo d, const T* __restrict__ x, const float* __restrict__ w, T*
         // atomics add 24-bit partials into 53-bit sums, exact unless the partials span more than 2^29
         ssum[threadIdx.x] = ok ? ls : 0.f; ssq[threadIdx.x] = ok ? lq : 0.f;
         __syncthreads();
-        if (threadIdx.x < d.CC && chunk * d.CC + threadIdx.x < d.C) {
+        if (threadIdx.x < CCT && chunk * CCT + threadIdx.x < d.C) {
             float a = 0.f, b = 0.f;
-            for (int l = 0; l < nrl; ++l) { a += ssum[l * d.CC + threadIdx.x]; b += ssq[l * d.CC + threadIdx.x]; }
-            nn::atomic_add_double(stats + chunk * d.CC + threadIdx.x, (double)a);
-            nn::atomic_add_double(stats + d.C + chunk * d.CC + threadIdx.x, (double)b);
+            for (int l = 0; l < nrl; ++l) { a += ssum[l * CCT + threadIdx.x]; b += ssq[l * CCT + threadIdx.x]; }
+            nn::atomic_add_double(stats + chunk * CCT + threadIdx.x, (double)a);
+            nn::atomic_add_double(stats + d.C + chunk * CCT + threadIdx.x, (double)b);
         }
     }
 }
@@ -185,19 +208,22 @@ __device__ __forceinline__ void stage_dy_async(const Geo& d, const T* __restrict
     }
 }
 
-template <typename T, int K, int S, int WS>
+template <typename T, int K, int S, int WS, int CCT>
 __global__ void __launch_bounds__(TH)
 wgrad_kernel(const Geo d, const T* __restrict__ dy, const T* __restrict__ x, float* __restrict__ dwt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* smem = reinterpret_cast<T*>(smem_raw);
     __shared__ float red[K * K][32];
     __shared__ int tab[MAX_PIX];
+    __shared__ int itab[MAX_ITEMS];
+    __shared__ int2 utab[MAX_UB];
     build_pixel_table(d, tab);
-    const int cl = threadIdx.x % d.CC, rl = threadIdx.x / d.CC, nrl = TH / d.CC;
-    const int chunk = blockIdx.y, c = chunk * d.CC + cl;
+    build_item_table(d, itab);
+    const int cl = threadIdx.x % CCT, rl = threadIdx.x / CCT, nrl = TH / CCT;
+    const int chunk = blockIdx.y, c = chunk * CCT + cl;
     const bool ok = c < d.C;
     const int gw = d.nseg * WS;                                           // padded dy row length
-    const int x_floats = d.UB * d.rows_t * d.cols_t * d.CC, g_floats = d.UB * d.RB * gw * d.CC;
+    const int x_floats = d.UB * d.rows_t * d.cols_t * CCT, g_floats = d.UB * d.RB * gw * CCT;
     const int buf_floats = x_floats + g_floats;
     const int rounds = (int)((d.units + d.UB - 1) / d.UB);
     for (int i = threadIdx.x; i < K * K * 32; i += TH) (&red[0][0])[i] = 0.f;
@@ -220,29 +246,28 @@ wgrad_kernel(const Geo d, const T* __restrict__ dy, const T* __restrict__ x, flo
             stage_dy_async(d, dy, nb_ + x_floats, nxt * d.UB, chunk, gw);
         }
         cp_async_commit();
+        build_unit_table(d, rd * d.UB, utab);
         cp_async_wait<1>();
         __syncthreads();
         const T* tile = smem + buf * buf_floats;
         const T* gt = tile + x_floats;
-        const int u0 = rd * d.UB;
         if (ok) {
             const int per_unit = d.RB * d.nseg;
             for (int it = rl; it < d.UB * per_unit; it += nrl) {
               {
-                const int ul = it / per_unit, rs = it - ul * per_unit;
-                if (u0 + ul >= (int)d.units) break;
-                const int ro = rs / d.nseg, seg = rs - ro * d.nseg;
+                const int e = itab[it], ul = e >> 20, ro = (e >> 10) & 1023, seg = e & 1023;
+                if (utab[ul].x < 0) break;
                 const int wo0 = seg * WS;
                 float g[WS];
-                const T* gb = gt + ((long long)(ul * d.RB + ro) * gw + wo0) * d.CC + cl;
+                const T* gb = gt + ((ul * d.RB + ro) * gw + wo0) * CCT + cl;
 #pragma unroll
-                for (int j = 0; j < WS; ++j) g[j] = nn::ld1(gb + j * d.CC);
-                const T* base = tile + ((long long)(ul * d.rows_t + ro * S) * d.cols_t + wo0 * S) * d.CC + cl;
+                for (int j = 0; j < WS; ++j) g[j] = nn::ld1(gb + j * CCT);
+                const T* base = tile + ((ul * d.rows_t + ro * S) * d.cols_t + wo0 * S) * CCT + cl;
 #pragma unroll
                 for (int kh = 0; kh < K; ++kh) {
                     float xr[NX];
 #pragma unroll
-                    for (int i = 0; i < NX; ++i) xr[i] = nn::ld1(base + (kh * d.cols_t + i) * d.CC);
+                    for (int i = 0; i < NX; ++i) xr[i] = nn::ld1(base + (kh * d.cols_t + i) * CCT);
 #pragma unroll
                     for (int kw = 0; kw < K; ++kw)
 #pragma unroll
@@ -260,8 +285,8 @@ wgrad_kernel(const Geo d, const T* __restrict__ dy, const T* __restrict__ x, flo
         for (int t = 0; t < K * K; ++t) atomicAdd(&red[t][cl], acc[t]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < K * K * d.CC; i += TH) {
-        const int t = i / d.CC, j = i % d.CC, cc = chunk * d.CC + j;
+    for (int i = threadIdx.x; i < K * K * CCT; i += TH) {
+        const int t = i / CCT, j = i % CCT, cc = chunk * CCT + j;
         if (cc < d.C) atomicAdd(&dwt[cc * K * K + t], red[t][j]);
     }
 }
@@ -273,7 +298,7 @@ wgrad_kernel(const Geo d, const T* __restrict__ dy, const T* __restrict__ x, flo
 template <int S>
 __host__ __device__ constexpr int floor_div(int a) { return S == 1 ? a : (a >= 0 ? a / 2 : -((-a + 1) / 2)); }
 
-template <typename T, int K, int S, int WS>
+template <typename T, int K, int S, int WS, int CCT>
 __global__ void __launch_bounds__(TH)
 dgrad_kernel(const Geo d, const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -281,12 +306,15 @@ dgrad_kernel(const Geo d, const T* __restrict__ dy, const float* __restrict__ w,
     static_assert(S == 1 || (WS % 2) == 0, "stride-2 dgrad needs an even row segment");
     constexpr int SH_ = S == 2 ? 1 : 0, P = K / 2;
     __shared__ int tab[MAX_PIX];
+    __shared__ int itab[MAX_ITEMS];
+    __shared__ int2 utab[MAX_UB];
     build_pixel_table(d, tab);
+    build_item_table(d, itab);
     __syncthreads();
-    const int cl = threadIdx.x % d.CC, rl = threadIdx.x / d.CC, nrl = TH / d.CC;
-    const int chunk = blockIdx.y, c = chunk * d.CC + cl;
+    const int cl = threadIdx.x % CCT, rl = threadIdx.x / CCT, nrl = TH / CCT;
+    const int chunk = blockIdx.y, c = chunk * CCT + cl;
     const bool ok = c < d.C;
-    const int tile_floats = d.UB * d.rows_t * d.cols_t * d.CC;
+    const int tile_floats = d.UB * d.rows_t * d.cols_t * CCT;
     const int rounds = (int)((d.units + d.UB - 1) / d.UB);
     float wr[K * K];
     load_weights<K>(w, c, ok, wr);
@@ -300,18 +328,17 @@ dgrad_kernel(const Geo d, const T* __restrict__ dy, const float* __restrict__ w,
         const int nxt = rd + gridDim.x;
         if (nxt < rounds) stage_async(d, dy, smem + (buf ^ 1) * tile_floats, tab, nxt * d.UB, chunk, d.Ho, d.Wo, d.RB, SH_, P - (K - 1), d.lo_c);
         cp_async_commit();
+        build_unit_table(d, rd * d.UB, utab);
         cp_async_wait<1>();
         __syncthreads();
         const T* tile = smem + buf * tile_floats;
-        const int u0 = rd * d.UB;
         const int per_unit = d.RB * d.nseg;
         for (int it = rl; it < d.UB * per_unit && ok; it += nrl) {
           {
-            const int ul = it / per_unit, rs = it - ul * per_unit;
-            const int u = u0 + ul;
-            if (u >= (int)d.units) break;
-            const int f = d.nb == 1 ? u : u / d.nb, hi0 = (u - f * d.nb) * d.RB;
-            const int ri = rs / d.nseg, seg = rs - ri * d.nseg;
+            const int e = itab[it], ul = e >> 20, ri = (e >> 10) & 1023, seg = e & 1023;
+            const int2 uf = utab[ul];
+            if (uf.x < 0) break;
+            const int f = uf.x, hi0 = uf.y;
             const int hi = hi0 + ri, wi0 = seg * WS;
             if (hi >= d.H) continue;
             const int lo_r = (hi0 + P - (K - 1)) >> SH_;
@@ -324,10 +351,10 @@ dgrad_kernel(const Geo d, const T* __restrict__ dy, const float* __restrict__ w,
                 const int hn = hi + P - kh;
                 if (S == 2 && (hn & 1)) continue;
                 const int tr = (hn >> SH_) - lo_r;
-                const T* row = tile + ((long long)(ul * d.rows_t + tr) * d.cols_t + tc0) * d.CC + cl;
+                const T* row = tile + ((ul * d.rows_t + tr) * d.cols_t + tc0) * CCT + cl;
                 float gr[NG];
 #pragma unroll
-                for (int i = 0; i < NG; ++i) gr[i] = nn::ld1(row + i * d.CC);
+                for (int i = 0; i < NG; ++i) gr[i] = nn::ld1(row + i * CCT);
 #pragma unroll
                 for (int j = 0; j < WS; ++j)
 #pragma unroll
@@ -388,6 +415,7 @@ static Geo make_geo(int F, int H, int W, int C, int k, int stride, int mode /*0 
     d.nb = ((mode == 2 ? H : d.Ho) + d.RB - 1) / d.RB;
     d.units = (long long)F * d.nb;
     if (d.units < d.UB) d.UB = (int)d.units;
+    while (d.UB > 1 && d.UB * d.RB * d.nseg > MAX_ITEMS) --d.UB;        // the item table of a round (build_item_table)
     return d;
 }
 // es: bytes per staged element (4 = fp32, 2 = bf16).  The tile GEOMETRY (make_geo) is the same for both storage
@@ -412,11 +440,18 @@ static dim3 persistent_grid(const Geo& d, int ctas_per_sm) {
 // a CUDA graph (tools that re-launch graph kernel nodes one by one -- ncu -- use the function's current limit).
 constexpr int SMEM_CEILING = 160 * 1024;
 
+// CC (channels per chunk: 16 or 32) is a template parameter of the kernels: every shared-memory tile offset of the main
+// loops is then a compile-time multiple of it, i.e. an immediate of the load instead of an IMAD + 64-bit add per tap
+#define DW_LAUNCH_CC(KERNEL, K_, S_, WS_, CC_, ...)                                      \
+    do {                                                                                 \
+        err = lr::ensure_max_dynamic_smem(KERNEL<T, K_, S_, WS_, CC_>, SMEM_CEILING);    \
+        if (err == cudaSuccess && smem > (size_t)SMEM_CEILING) err = cudaErrorInvalidValue; \
+        if (err == cudaSuccess) KERNEL<T, K_, S_, WS_, CC_><<<grid, TH, smem, stream>>>(__VA_ARGS__); \
+    } while (0)
 #define DW_LAUNCH(KERNEL, K_, S_, WS_, ...)                                              \
     do {                                                                                 \
-        err = lr::ensure_max_dynamic_smem(KERNEL<T, K_, S_, WS_>, SMEM_CEILING);         \
-        if (err == cudaSuccess && smem > (size_t)SMEM_CEILING) err = cudaErrorInvalidValue; \
-        if (err == cudaSuccess) KERNEL<T, K_, S_, WS_><<<grid, TH, smem, stream>>>(__VA_ARGS__); \
+        if (d.CC == 16) DW_LAUNCH_CC(KERNEL, K_, S_, WS_, 16, __VA_ARGS__);              \
+        else DW_LAUNCH_CC(KERNEL, K_, S_, WS_, 32, __VA_ARGS__);                         \
     } while (0)
 #define DW_DISPATCH_WS(KERNEL, K_, S_, ...)                                              \
     switch (ws) {                                                                        \
