@@ -117,7 +117,7 @@ fwd_kernel(const Geo d, const T* __restrict__ x, const float* __restrict__ w, T*
     __syncthreads();
     const int cl = threadIdx.x % CCT, rl = threadIdx.x / CCT, nrl = TH / CCT;
     const int chunk = blockIdx.y, c = chunk * CCT + cl;
-    const bool ok = c < d.C;
+    const bool ok = c < d.C && rl < nrl;               // (CC = 24: the last 16 threads have no row lane)
     const int tile_floats = d.UB * d.rows_t * d.cols_t * CCT;
     const int rounds = (int)((d.units + d.UB - 1) / d.UB);
     float wr[K * K];
@@ -221,7 +221,7 @@ wgrad_kernel(const Geo d, const T* __restrict__ dy, const T* __restrict__ x, flo
     build_item_table(d, itab);
     const int cl = threadIdx.x % CCT, rl = threadIdx.x / CCT, nrl = TH / CCT;
     const int chunk = blockIdx.y, c = chunk * CCT + cl;
-    const bool ok = c < d.C;
+    const bool ok = c < d.C && rl < nrl;               // (CC = 24: the last 16 threads have no row lane)
     const int gw = d.nseg * WS;                                           // padded dy row length
     const int x_floats = d.UB * d.rows_t * d.cols_t * CCT, g_floats = d.UB * d.RB * gw * CCT;
     const int buf_floats = x_floats + g_floats;
@@ -313,7 +313,7 @@ dgrad_kernel(const Geo d, const T* __restrict__ dy, const float* __restrict__ w,
     __syncthreads();
     const int cl = threadIdx.x % CCT, rl = threadIdx.x / CCT, nrl = TH / CCT;
     const int chunk = blockIdx.y, c = chunk * CCT + cl;
-    const bool ok = c < d.C;
+    const bool ok = c < d.C && rl < nrl;               // (CC = 24: the last 16 threads have no row lane)
     const int tile_floats = d.UB * d.rows_t * d.cols_t * CCT;
     const int rounds = (int)((d.units + d.UB - 1) / d.UB);
     float wr[K * K];
@@ -375,6 +375,8 @@ dgrad_kernel(const Geo d, const T* __restrict__ dy, const float* __restrict__ w,
 }
 
 // ------------------------------------------------------------------------------------------ host side
+// row segment (adjacent outputs per thread and row).  (12-wide segments -- a whole 11-wide row per item -- were measured:
+// 22x22x72 s2 forward 53 -> 51 us, dgrad 63 -> 59, wgrad 68 -> 72: not worth three more instantiations per kernel.)
 static int pick_ws(int width, bool even_needed) {
     if (!even_needed && width <= 3) return 3;
     if (width <= 6 || width == 11 || width == 12) return 6;
@@ -385,7 +387,9 @@ static Geo make_geo(int F, int H, int W, int C, int k, int stride, int mode /*0 
     Geo d;
     d.F = F; d.H = H; d.W = W; d.C = C; d.k = k; d.stride = stride; d.pad = k / 2;
     d.Ho = (H + 2 * d.pad - k) / stride + 1; d.Wo = (W + 2 * d.pad - k) / stride + 1;
-    d.CC = C == 16 ? 16 : 32;
+    // channels per chunk: 32 lanes of a warp = 32 channels; 24 when that tiles C exactly and 32 does not (C = 72: three
+    // full chunks instead of two full ones and one at a quarter)
+    d.CC = C == 16 ? 16 : ((C % 32) != 0 && (C % 24) == 0 ? 24 : 32);
     d.lo_c = 0;
     const int width = mode == 2 ? W : d.Wo;
     d.nseg = (width + ws - 1) / ws;
@@ -451,6 +455,7 @@ constexpr int SMEM_CEILING = 160 * 1024;
 #define DW_LAUNCH(KERNEL, K_, S_, WS_, ...)                                              \
     do {                                                                                 \
         if (d.CC == 16) DW_LAUNCH_CC(KERNEL, K_, S_, WS_, 16, __VA_ARGS__);              \
+        else if (d.CC == 24) DW_LAUNCH_CC(KERNEL, K_, S_, WS_, 24, __VA_ARGS__);         \
         else DW_LAUNCH_CC(KERNEL, K_, S_, WS_, 32, __VA_ARGS__);                         \
     } while (0)
 #define DW_DISPATCH_WS(KERNEL, K_, S_, ...)                                              \
