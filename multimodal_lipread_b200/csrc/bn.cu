@@ -52,7 +52,11 @@ __device__ __forceinline__ Coef coef4(const Bn& b, int c) {
 }
 
 // z = act(x * scale + shift) (+ residual).  Block (0,0) also performs the running-statistics update.
-template <typename T, bool RES>
+// ACT is a template parameter (round 2): with a run-time activation every element paid an indirect branch and the
+// divergence bookkeeping around it (ncu: BRA / BRX / BSSY / BSYNC / FSETP / FSEL ~25 % of the executed instructions),
+// every access a 64-bit multiply (IMAD 20 %), and a `break` inside the unrolled row loop pushed the in-flight vectors to
+// local memory.  The rows of a thread are now walked with running pointers and a per-pass valid count.
+template <typename T, bool RES, int ACT>
 __global__ void __launch_bounds__(TH, 4)
 bn_act_fwd_kernel(const Bn b, const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ z,
                   int rows_per_block, int res_pre, int gw) {
@@ -79,33 +83,35 @@ bn_act_fwd_kernel(const Bn b, const T* __restrict__ x, const T* __restrict__ res
     // (with a residual stream the rows in flight stay at 4: RES is a template flag so that its array vanishes otherwise)
     constexpr int U = (sizeof(T) == 2 && !RES) ? 8 : 4;
     const long long step = map.rpp;
-    for (long long r = r0 + map.rlane; r < r1; r += U * step) {
+    const long long rs = step * b.C;                                  // elements between two rows of this thread
+    long long r = r0 + map.rlane;
+    const T* px = x + r * b.C + c;
+    const T* pq = RES ? res + r * b.C + c : nullptr;
+    T* pz = z + r * b.C + c;
+    const bool pre = RES && res_pre;
+    for (; r < r1; r += U * step, px += U * rs, pz += U * rs) {
+        const int nv = (int)min((long long)U, (r1 - r + step - 1) / step);     // valid rows of this pass
         typename nn::Raw4<T>::type vr[U], qr[RES ? U : 1];
 #pragma unroll
-        for (int u = 0; u < U; ++u) if (r + u * step < r1) vr[u] = nn::ldraw(x + (r + u * step) * b.C + c);
+        for (int u = 0; u < U; ++u) if (u < nv) vr[u] = nn::ldraw(px + u * rs);
         if (RES) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) if (r + u * step < r1) qr[u] = nn::ldraw(res + (r + u * step) * b.C + c);
+            for (int u = 0; u < U; ++u) if (u < nv) qr[u] = nn::ldraw(pq + u * rs);
+            pq += U * rs;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (r + u * step >= r1) break;
-            const float4 v = nn::cvt4(vr[u]);
-            float4 o;
-            if (RES && res_pre) {               // ResNet BasicBlock: act(bn(x) + identity)
-                const float4 q = nn::cvt4(qr[u]);
-                o.x = nn::act_fwd(fmaf(v.x, k.scale.x, k.shift.x) + q.x, b.act);
-                o.y = nn::act_fwd(fmaf(v.y, k.scale.y, k.shift.y) + q.y, b.act);
-                o.z = nn::act_fwd(fmaf(v.z, k.scale.z, k.shift.z) + q.z, b.act);
-                o.w = nn::act_fwd(fmaf(v.w, k.scale.w, k.shift.w) + q.w, b.act);
-            } else {
-                o.x = nn::act_fwd(fmaf(v.x, k.scale.x, k.shift.x), b.act);
-                o.y = nn::act_fwd(fmaf(v.y, k.scale.y, k.shift.y), b.act);
-                o.z = nn::act_fwd(fmaf(v.z, k.scale.z, k.shift.z), b.act);
-                o.w = nn::act_fwd(fmaf(v.w, k.scale.w, k.shift.w), b.act);
-                if (RES) { const float4 q = nn::cvt4(qr[u]); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+            if (u < nv) {
+                const float4 v = nn::cvt4(vr[u]);
+                float4 o = make_float4(fmaf(v.x, k.scale.x, k.shift.x), fmaf(v.y, k.scale.y, k.shift.y),
+                                       fmaf(v.z, k.scale.z, k.shift.z), fmaf(v.w, k.scale.w, k.shift.w));
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (RES) q = nn::cvt4(qr[u]);
+                if (pre) { o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }   // ResNet BasicBlock: act(bn(x) + identity)
+                o.x = nn::act_fwd(o.x, ACT); o.y = nn::act_fwd(o.y, ACT); o.z = nn::act_fwd(o.z, ACT); o.w = nn::act_fwd(o.w, ACT);
+                if (RES && !pre) { o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+                nn::st4(pz + u * rs, o);
             }
-            nn::st4(z + (r + u * step) * b.C + c, o);
         }
     }
 }
@@ -121,7 +127,7 @@ __device__ __forceinline__ float4 mask_by_out(float4 g, const float4 z, int act)
 // backward pass 1: dy = dz * act'(u), u = x*scale + shift;  sums[c] += dy, sums[C+c] += dy * xhat
 // ZO: the derivative goes through the saved OUTPUT zo (ResNet pre-activation residual blocks): a third stream, so the
 // rows in flight stay at 4 there; otherwise bf16 keeps 8 rows (the same bytes as fp32's 4) in flight.
-template <typename T, bool ZO>
+template <typename T, bool ZO, int ACT>
 __global__ void __launch_bounds__(TH, 3)
 bn_act_bwd_reduce_kernel(const Bn b, const T* __restrict__ x, const T* __restrict__ dz,
                          const T* __restrict__ zo, double* __restrict__ sums, int rows_per_block, int gw) {
@@ -138,31 +144,39 @@ bn_act_bwd_reduce_kernel(const Bn b, const T* __restrict__ x, const T* __restric
         float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
         const unsigned long long keep = nn::l2_policy_evict_last();     // the apply pass re-reads x and dz right away
         constexpr int U = (sizeof(T) == 2 && !ZO) ? 8 : 4;
+        constexpr int GA = ZO ? LR_ACT_NONE : ACT;                      // ZO: the mask comes from the forward output
         const long long step = map.rpp;
-        for (long long r = r0 + map.rlane; r < r1; r += U * step) {
+        const long long rs = step * b.C;
+        long long r = r0 + map.rlane;
+        const T* px = x + r * b.C + c;
+        const T* pg = dz + r * b.C + c;
+        const T* pzo = ZO ? zo + r * b.C + c : nullptr;
+        for (; r < r1; r += U * step, px += U * rs, pg += U * rs) {
+            const int nv = (int)min((long long)U, (r1 - r + step - 1) / step);
             typename nn::Raw4<T>::type vv[U], gg[U], zz[ZO ? U : 1];
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (r + u * step < r1) {
-                    vv[u] = nn::ldraw_hint(x + (r + u * step) * b.C + c, keep); gg[u] = nn::ldraw_hint(dz + (r + u * step) * b.C + c, keep);
-                    if (ZO) zz[u] = nn::ldraw_hint(zo + (r + u * step) * b.C + c, keep);
+                if (u < nv) {
+                    vv[u] = nn::ldraw_hint(px + u * rs, keep); gg[u] = nn::ldraw_hint(pg + u * rs, keep);
+                    if (ZO) zz[u] = nn::ldraw_hint(pzo + u * rs, keep);
                 }
+            if (ZO) pzo += U * rs;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (r + u * step >= r1) break;
-                const float4 v = nn::cvt4(vv[u]);
-                float4 g = nn::cvt4(gg[u]);
-                if (ZO) g = mask_by_out(g, nn::cvt4(zz[u]), b.act);
-                const int ga = ZO ? LR_ACT_NONE : b.act;
-                const float d0 = g.x * nn::act_grad(fmaf(v.x, k.scale.x, k.shift.x), ga);
-                const float d1 = g.y * nn::act_grad(fmaf(v.y, k.scale.y, k.shift.y), ga);
-                const float d2 = g.z * nn::act_grad(fmaf(v.z, k.scale.z, k.shift.z), ga);
-                const float d3 = g.w * nn::act_grad(fmaf(v.w, k.scale.w, k.shift.w), ga);
-                s1.x += d0; s1.y += d1; s1.z += d2; s1.w += d3;
-                s2.x = fmaf(d0, (v.x - k.mean.x) * k.invstd.x, s2.x);
-                s2.y = fmaf(d1, (v.y - k.mean.y) * k.invstd.y, s2.y);
-                s2.z = fmaf(d2, (v.z - k.mean.z) * k.invstd.z, s2.z);
-                s2.w = fmaf(d3, (v.w - k.mean.w) * k.invstd.w, s2.w);
+                if (u < nv) {
+                    const float4 v = nn::cvt4(vv[u]);
+                    float4 g = nn::cvt4(gg[u]);
+                    if (ZO) g = mask_by_out(g, nn::cvt4(zz[u]), ACT);
+                    const float d0 = g.x * nn::act_grad(fmaf(v.x, k.scale.x, k.shift.x), GA);
+                    const float d1 = g.y * nn::act_grad(fmaf(v.y, k.scale.y, k.shift.y), GA);
+                    const float d2 = g.z * nn::act_grad(fmaf(v.z, k.scale.z, k.shift.z), GA);
+                    const float d3 = g.w * nn::act_grad(fmaf(v.w, k.scale.w, k.shift.w), GA);
+                    s1.x += d0; s1.y += d1; s1.z += d2; s1.w += d3;
+                    s2.x = fmaf(d0, (v.x - k.mean.x) * k.invstd.x, s2.x);
+                    s2.y = fmaf(d1, (v.y - k.mean.y) * k.invstd.y, s2.y);
+                    s2.z = fmaf(d2, (v.z - k.mean.z) * k.invstd.z, s2.z);
+                    s2.w = fmaf(d3, (v.w - k.mean.w) * k.invstd.w, s2.w);
+                }
             }
         }
         atomicAdd(&sh[c], s1.x); atomicAdd(&sh[c + 1], s1.y); atomicAdd(&sh[c + 2], s1.z); atomicAdd(&sh[c + 3], s1.w);
@@ -179,7 +193,7 @@ bn_act_bwd_reduce_kernel(const Bn b, const T* __restrict__ x, const T* __restric
 // backward pass 2: dx = gamma*invstd * (dy - mean(dy) - xhat * mean(dy*xhat))   (training)
 //                  dx = gamma*invstd * dy                                        (eval)
 // block (0,0) writes dgamma += sum(dy*xhat), dbeta += sum(dy).
-template <typename T, bool ZO>
+template <typename T, bool ZO, int ACT>
 __global__ void __launch_bounds__(TH, 3)
 bn_act_bwd_apply_kernel(const Bn b, const T* __restrict__ x, const T* __restrict__ dz,
                         const T* __restrict__ zo, T* __restrict__ dres,
@@ -214,33 +228,42 @@ bn_act_bwd_apply_kernel(const Bn b, const T* __restrict__ x, const T* __restrict
     const long long r1 = min(b.rows, r0 + rows_per_block);
     const unsigned long long drop = nn::l2_policy_evict_first();       // last use of x and dz
     constexpr int U = (sizeof(T) == 2 && !ZO) ? 8 : 4;
+    constexpr int GA = ZO ? LR_ACT_NONE : ACT;
     const long long step = map.rpp;
-    for (long long rb = r0 + map.rlane; rb < r1; rb += U * step) {
-      typename nn::Raw4<T>::type vv[U], gg[U], zz[ZO ? U : 1];
+    const long long rs = step * b.C;
+    long long r = r0 + map.rlane;
+    const T* px = x + r * b.C + c;
+    const T* pg = dz + r * b.C + c;
+    const T* pzo = ZO ? zo + r * b.C + c : nullptr;
+    T* pdr = (ZO && dres) ? dres + r * b.C + c : nullptr;
+    T* po = dx + r * b.C + c;
+    for (; r < r1; r += U * step, px += U * rs, pg += U * rs, po += U * rs) {
+        const int nv = (int)min((long long)U, (r1 - r + step - 1) / step);
+        typename nn::Raw4<T>::type vv[U], gg[U], zz[ZO ? U : 1];
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-          if (rb + u * step < r1) {
-              vv[u] = nn::ldraw_hint(x + (rb + u * step) * b.C + c, drop); gg[u] = nn::ldraw_hint(dz + (rb + u * step) * b.C + c, drop);
-              if (ZO) zz[u] = nn::ldraw_hint(zo + (rb + u * step) * b.C + c, drop);
-          }
+        for (int u = 0; u < U; ++u)
+            if (u < nv) {
+                vv[u] = nn::ldraw_hint(px + u * rs, drop); gg[u] = nn::ldraw_hint(pg + u * rs, drop);
+                if (ZO) zz[u] = nn::ldraw_hint(pzo + u * rs, drop);
+            }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long r = rb + u * step;
-        if (r >= r1) break;
-        const float4 v = nn::cvt4(vv[u]);
-        float4 g = nn::cvt4(gg[u]);
-        if (ZO) {
-            g = mask_by_out(g, nn::cvt4(zz[u]), b.act);
-            if (dres) nn::st4(dres + r * b.C + c, g);                         // gradient of the identity branch
+        for (int u = 0; u < U; ++u) {
+            if (u < nv) {
+                const float4 v = nn::cvt4(vv[u]);
+                float4 g = nn::cvt4(gg[u]);
+                if (ZO) {
+                    g = mask_by_out(g, nn::cvt4(zz[u]), ACT);
+                    if (pdr) nn::st4(pdr + u * rs, g);                             // gradient of the identity branch
+                }
+                float4 o;
+                o.x = sc[0] * (g.x * nn::act_grad(fmaf(v.x, sc[0], sh[0]), GA)) - fmaf(v.x - mu[0], ka[0], kd[0]);
+                o.y = sc[1] * (g.y * nn::act_grad(fmaf(v.y, sc[1], sh[1]), GA)) - fmaf(v.y - mu[1], ka[1], kd[1]);
+                o.z = sc[2] * (g.z * nn::act_grad(fmaf(v.z, sc[2], sh[2]), GA)) - fmaf(v.z - mu[2], ka[2], kd[2]);
+                o.w = sc[3] * (g.w * nn::act_grad(fmaf(v.w, sc[3], sh[3]), GA)) - fmaf(v.w - mu[3], ka[3], kd[3]);
+                nn::st4(po + u * rs, o);
+            }
         }
-        const int ga = ZO ? LR_ACT_NONE : b.act;
-        float4 o;
-        o.x = sc[0] * (g.x * nn::act_grad(fmaf(v.x, sc[0], sh[0]), ga)) - fmaf(v.x - mu[0], ka[0], kd[0]);
-        o.y = sc[1] * (g.y * nn::act_grad(fmaf(v.y, sc[1], sh[1]), ga)) - fmaf(v.y - mu[1], ka[1], kd[1]);
-        o.z = sc[2] * (g.z * nn::act_grad(fmaf(v.z, sc[2], sh[2]), ga)) - fmaf(v.z - mu[2], ka[2], kd[2]);
-        o.w = sc[3] * (g.w * nn::act_grad(fmaf(v.w, sc[3], sh[3]), ga)) - fmaf(v.w - mu[3], ka[3], kd[3]);
-        nn::st4(dx + r * b.C + c, o);
-      }
+        if (ZO) { pzo += U * rs; if (pdr) pdr += U * rs; }
     }
 }
 
@@ -396,8 +419,19 @@ static int bn_act_fwd_impl(const T* x, const double* stats, const float* gamma, 
     LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(z); LR_CHECK_ALIGN(residual);
     dim3 grid; int gw; const int rpb = rows_per_block_for(rows, C, &grid, &gw);
     const bn::Bn b = make_bn(rows, C, stats, gamma, beta, running_mean, running_var, num_batches_tracked, eps, momentum, act, training);
-    if (residual) bn::bn_act_fwd_kernel<T, true><<<grid, bn::TH, 0, stream>>>(b, x, residual, z, rpb, res_pre, gw);
-    else bn::bn_act_fwd_kernel<T, false><<<grid, bn::TH, 0, stream>>>(b, x, residual, z, rpb, res_pre, gw);
+#define LR_BN_FWD(ACT_)                                                                                         \
+    do {                                                                                                        \
+        if (residual) bn::bn_act_fwd_kernel<T, true, ACT_><<<grid, bn::TH, 0, stream>>>(b, x, residual, z, rpb, res_pre, gw); \
+        else bn::bn_act_fwd_kernel<T, false, ACT_><<<grid, bn::TH, 0, stream>>>(b, x, residual, z, rpb, res_pre, gw);        \
+    } while (0)
+    switch (act) {
+        case LR_ACT_RELU: LR_BN_FWD(LR_ACT_RELU); break;
+        case LR_ACT_HSWISH: LR_BN_FWD(LR_ACT_HSWISH); break;
+        case LR_ACT_HSIGMOID: LR_BN_FWD(LR_ACT_HSIGMOID); break;
+        case LR_ACT_RELU6: LR_BN_FWD(LR_ACT_RELU6); break;
+        default: LR_BN_FWD(LR_ACT_NONE); break;
+    }
+#undef LR_BN_FWD
     lr::count_launch();
     LR_CHECK_LAUNCH("bn_act_fwd_kernel");
     return LR_OK;
@@ -432,12 +466,24 @@ static int bn_act_bwd_impl(const T* x, const double* stats, const float* gamma, 
     dim3 grid; int gw; const int rpb = rows_per_block_for(rows, C, &grid, &gw);
     const bn::Bn b = make_bn(rows, C, stats, gamma, beta, const_cast<float*>(running_mean),
                              const_cast<float*>(running_var), nullptr, eps, 0.f, act, training);
-    if (z_out) bn::bn_act_bwd_reduce_kernel<T, true><<<grid, bn::TH, 2 * C * sizeof(float), stream>>>(b, x, dz, z_out, sums, rpb, gw);
-    else bn::bn_act_bwd_reduce_kernel<T, false><<<grid, bn::TH, 2 * C * sizeof(float), stream>>>(b, x, dz, z_out, sums, rpb, gw);
-    lr::count_launch();
+    const size_t smem = 2 * (size_t)C * sizeof(float);
+#define LR_BN_BWD(ACT_)                                                                                         \
+    do {                                                                                                        \
+        if (z_out) bn::bn_act_bwd_reduce_kernel<T, true, ACT_><<<grid, bn::TH, smem, stream>>>(b, x, dz, z_out, sums, rpb, gw); \
+        else bn::bn_act_bwd_reduce_kernel<T, false, ACT_><<<grid, bn::TH, smem, stream>>>(b, x, dz, z_out, sums, rpb, gw);      \
+        lr::count_launch();                                                                                     \
+        if (z_out) bn::bn_act_bwd_apply_kernel<T, true, ACT_><<<grid, bn::TH, 0, stream>>>(b, x, dz, z_out, dres, sums, dx, dgamma, dbeta, rpb, gw); \
+        else bn::bn_act_bwd_apply_kernel<T, false, ACT_><<<grid, bn::TH, 0, stream>>>(b, x, dz, z_out, dres, sums, dx, dgamma, dbeta, rpb, gw);      \
+    } while (0)
+    switch (act) {
+        case LR_ACT_RELU: LR_BN_BWD(LR_ACT_RELU); break;
+        case LR_ACT_HSWISH: LR_BN_BWD(LR_ACT_HSWISH); break;
+        case LR_ACT_HSIGMOID: LR_BN_BWD(LR_ACT_HSIGMOID); break;
+        case LR_ACT_RELU6: LR_BN_BWD(LR_ACT_RELU6); break;
+        default: LR_BN_BWD(LR_ACT_NONE); break;
+    }
+#undef LR_BN_BWD
     LR_CHECK_LAUNCH("bn_act_bwd_reduce_kernel");
-    if (z_out) bn::bn_act_bwd_apply_kernel<T, true><<<grid, bn::TH, 0, stream>>>(b, x, dz, z_out, dres, sums, dx, dgamma, dbeta, rpb, gw);
-    else bn::bn_act_bwd_apply_kernel<T, false><<<grid, bn::TH, 0, stream>>>(b, x, dz, z_out, dres, sums, dx, dgamma, dbeta, rpb, gw);
     lr::count_launch();
     LR_CHECK_LAUNCH("bn_act_bwd_apply_kernel");
     return LR_OK;
