@@ -286,11 +286,29 @@ frame_reduce_kernel(const T* __restrict__ a, const T* __restrict__ g, float* __r
         if (map.active) {
             const int c = map.cg * 4;
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = map.rlane; r < HW; r += map.rpp) {
-                const long long off = (f * HW + r) * C + c;
-                float4 v = nn::ld4(a + off);
-                if (mode == 1) { const float4 q = nn::ld4(g + off); v.x *= q.x; v.y *= q.y; v.z *= q.z; v.w *= q.w; }
-                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            // four rows in flight per thread (the loads go out together; the additions keep their index order), the
+            // rows of a thread walked with running pointers
+            constexpr int U = 4;
+            const long long rs = (long long)map.rpp * C;
+            const T* pa = a + (f * HW + map.rlane) * C + c;
+            const T* pg = mode == 1 ? g + (f * HW + map.rlane) * C + c : nullptr;
+            for (int r = map.rlane; r < HW; r += U * map.rpp, pa += U * rs) {
+                const int nv = min(U, (HW - r + map.rpp - 1) / map.rpp);
+                typename nn::Raw4<T>::type va[U], vg[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (u < nv) va[u] = nn::ldraw(pa + u * rs);
+                if (mode == 1) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) if (u < nv) vg[u] = nn::ldraw(pg + u * rs);
+                    pg += U * rs;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (u < nv) {
+                        float4 v = nn::cvt4(va[u]);
+                        if (mode == 1) { const float4 q = nn::cvt4(vg[u]); v.x *= q.x; v.y *= q.y; v.z *= q.z; v.w *= q.w; }
+                        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                    }
             }
             *reinterpret_cast<float4*>(&sh[(map.rlane * w + (map.cg - cg0)) * 4]) = s;
         }
@@ -308,27 +326,48 @@ frame_reduce_kernel(const T* __restrict__ a, const T* __restrict__ g, float* __r
 //   SE forward            : a = activation, s = gate, dp = null
 //   SE backward           : a = db, s = gate, dp = gradient of the pooled value
 //   avg-pool backward     : a = null, dp = gradient of the pooled value
-template <typename T>
+// (round 2: a block walks whole frames -- the first version divided a 64-bit row index by HW for every 4-channel vector
+// and re-read the gate for every row; now the gate / pooled gradient of a frame sit in registers, four rows are in flight
+// per thread, and the rows are walked with running pointers)
+template <typename T, bool HAS_A, bool HAS_DP>
 __global__ void __launch_bounds__(TH)
 frame_scale_kernel(const T* __restrict__ a, const float* __restrict__ s, const float* __restrict__ dp,
-                   T* __restrict__ out, long long rows, int HW, int C, float inv_hw, int rows_per_block, int gw) {
+                   T* __restrict__ out, int F, int HW, int C, float inv_hw, int gw) {
     const nn::CgMap map(C, blockIdx.y * gw, gw);
     if (!map.active) return;
     const int c = map.cg * 4;
-    const long long r0 = (long long)blockIdx.x * rows_per_block;
-    const long long r1 = min(rows, r0 + rows_per_block);
-    for (long long r = r0 + map.rlane; r < r1; r += map.rpp) {
-        const long long f = r / HW;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a) {
-            const float4 v = nn::ld4(a + r * C + c), g = nn::ld4(s + f * C + c);
-            o.x = v.x * g.x; o.y = v.y * g.y; o.z = v.z * g.z; o.w = v.w * g.w;
+    constexpr int U = 4;
+    const long long rs = (long long)map.rpp * C;
+    for (int f = blockIdx.x; f < F; f += gridDim.x) {
+        float4 gate = make_float4(0.f, 0.f, 0.f, 0.f), add = gate;
+        if (HAS_A) gate = nn::ld4(s + (long long)f * C + c);
+        if (HAS_DP) add = nn::ld4(dp + (long long)f * C + c);
+        const long long base = ((long long)f * HW + map.rlane) * C + c;
+        const T* pa = HAS_A ? a + base : nullptr;
+        T* po = out + base;
+        for (int r = map.rlane; r < HW; r += U * map.rpp, po += U * rs) {
+            const int nv = min(U, (HW - r + map.rpp - 1) / map.rpp);
+            typename nn::Raw4<T>::type va[U];
+            if (HAS_A) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) if (u < nv) va[u] = nn::ldraw(pa + u * rs);
+                pa += U * rs;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (u < nv) {
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (HAS_A) {
+                        const float4 v = nn::cvt4(va[u]);
+                        o.x = v.x * gate.x; o.y = v.y * gate.y; o.z = v.z * gate.z; o.w = v.w * gate.w;
+                    }
+                    if (HAS_DP) {                                  // the same fused operation as the first version
+                        o.x = fmaf(add.x, inv_hw, o.x); o.y = fmaf(add.y, inv_hw, o.y);
+                        o.z = fmaf(add.z, inv_hw, o.z); o.w = fmaf(add.w, inv_hw, o.w);
+                    }
+                    nn::st4(po + u * rs, o);
+                }
         }
-        if (dp) {
-            const float4 d = nn::ld4(dp + f * C + c);
-            o.x = fmaf(d.x, inv_hw, o.x); o.y = fmaf(d.y, inv_hw, o.y); o.z = fmaf(d.z, inv_hw, o.z); o.w = fmaf(d.w, inv_hw, o.w);
-        }
-        nn::st4(out + r * C + c, o);
     }
 }
 
@@ -534,9 +573,15 @@ static int frame_scale_impl(const T* a, const float* s, const float* dp, T* out,
     if (F == 0) return LR_OK;
     LR_CHECK_ARG(out, "lr_frame_scale: null pointer");
     LR_CHECK_ALIGN(a); LR_CHECK_ALIGN(s); LR_CHECK_ALIGN(dp); LR_CHECK_ALIGN(out);
-    const long long rows = (long long)F * HW;
-    dim3 grid; int gw; const int rpb = rows_per_block_for(rows, C, &grid, &gw, 8);
-    bn::frame_scale_kernel<T><<<grid, bn::TH, 0, stream>>>(a, s, dp, out, rows, HW, C, 1.f / (float)HW, rpb, gw);
+    const int gw = nn::cg_col_width(C);
+    const int ncols = ((C >> 2) + gw - 1) / gw;
+    int gx = (8 * lr::sm_count() + ncols - 1) / ncols;          // about eight blocks per SM in all, never more than frames
+    if (gx > F) gx = F;
+    const dim3 grid((unsigned)gx, (unsigned)ncols);
+    const float inv_hw = 1.f / (float)HW;
+    if (a && dp) bn::frame_scale_kernel<T, true, true><<<grid, bn::TH, 0, stream>>>(a, s, dp, out, F, HW, C, inv_hw, gw);
+    else if (a) bn::frame_scale_kernel<T, true, false><<<grid, bn::TH, 0, stream>>>(a, s, dp, out, F, HW, C, inv_hw, gw);
+    else bn::frame_scale_kernel<T, false, true><<<grid, bn::TH, 0, stream>>>(a, s, dp, out, F, HW, C, inv_hw, gw);
     lr::count_launch();
     LR_CHECK_LAUNCH("frame_scale_kernel");
     return LR_OK;
