@@ -55,6 +55,10 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(p.nm * p.BN)) tmem_cols <<= 1;
 
+    if (threadIdx.x == 32) {                               // the descriptors' first fetch overlaps the CTA's set-up
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+    }
     for (int i = threadIdx.x; i < 4 * 128; i += THREADS) { (&s_sum[0][0])[i] = 0.f; (&s_sq[0][0])[i] = 0.f; }
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }

@@ -220,6 +220,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     while (tmem_cols < (uint32_t)(p.mt * p.tile_cols)) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) LR_STAMP(0);
+    if (threadIdx.x == 32) {                               // the descriptors' first fetch overlaps the CTA's set-up
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        if (p.tma_out || sizeof(TC) == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+    }
     for (int i = threadIdx.x; i < 256; i += THREADS) {
 #pragma unroll
         for (int w = 0; w < 4; ++w) { s_sum[w][i] = 0.f; s_sq[w][i] = 0.f; }
