@@ -1232,9 +1232,9 @@ class Plan:
         f2d, _ = self.dropout(f2, df2, F * E, p2, dy=ds2)
         return self.layer_norm(h, f2d, layer.norm2, F, ds2)
 
-    # ---- torchvision ResNet (BasicBlock) -------------------------------------------------------------------
+    # ---- torchvision ResNet (BasicBlock / Bottleneck) ------------------------------------------------------
     def resnet_features(self, net, frames, x=None):
-        """torchvision resnet18/34 children()[:-2] (conv1, bn1, relu, maxpool, layer1..4) on frames given as
+        """torchvision resnet18/34/50 children()[:-2] (conv1, bn1, relu, maxpool, layer1..4) on frames given as
         (tensor, layout, scale) -> last activation T2.  video/models/resnet_lstm.py:90-93,
         audio/models/resnet_model.py:12-17.  x: a T2 input instead of raw frames when the image is itself computed and
         needs a gradient (audio/models/lstm_resnet_model.py:47-49)."""
@@ -1250,14 +1250,43 @@ class Plan:
         cur = self.maxpool(a, k, s_, p_)
         for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
             for blk in layer:
-                cur = self.basic_block(blk, cur)
+                cur = self.bottleneck_block(blk, cur) if type(blk).__name__ == "Bottleneck" else self.basic_block(blk, cur)
         return cur
+
+    def bottleneck_block(self, blk, x):
+        """torchvision Bottleneck (resnet50, video/models/resnet_lstm.py:84): relu(bn3(conv3(relu(bn2(conv2(relu(bn1(
+        conv1(x)))))))) + identity), conv1 / conv3 1x1, conv2 3x3 carrying the stride, identity = x or bn_d(conv_d(x))."""
+        ident, dmask, ds_raw = x, None, None
+        # backward groups run in reverse registration order: bn3, conv3, bn2, conv2, bn1, conv1, [bn_d, conv_d]
+        if blk.downsample is not None:
+            dconv, dbn = blk.downsample[0], blk.downsample[1]
+            ds_raw = self.dense_conv(x, dconv)
+            ident = T2(self, ds_raw.F, ds_raw.H, ds_raw.W, ds_raw.C, h=ds_raw.h)
+            self.bn_act(ds_raw, dbn, ACT_NONE, ident)
+        raw1 = self.dense_conv(x, blk.conv1)
+        h1 = T2(self, raw1.F, raw1.H, raw1.W, raw1.C, h=raw1.h)
+        self.bn_act(raw1, blk.bn1, ACT_RELU, h1)
+        raw2 = self.dense_conv(h1, blk.conv2)
+        h2 = T2(self, raw2.F, raw2.H, raw2.W, raw2.C, h=raw2.h)
+        self.bn_act(raw2, blk.bn2, ACT_RELU, h2)
+        raw3 = self.dense_conv(h2, blk.conv3)
+        out = T2(self, raw3.F, raw3.H, raw3.W, raw3.C, h=raw3.h)
+        if self.with_backward:
+            dmask = ident.grad if ds_raw is not None else self.alloc_like(out, out.rows * out.C)
+        self.bn_act(raw3, blk.bn3, ACT_RELU, out, residual=ident, res_pre=True, dres=dmask)
+        if self.with_backward:
+            self.dense_conv_bwd(raw3)
+            self.dense_conv_bwd(raw2)
+            self.dense_conv_bwd(raw1, dx_residual=(0 if ds_raw is not None else dmask))
+            if ds_raw is not None:
+                self.dense_conv_bwd(ds_raw, dx_residual=x.grad)
+        return out
 
     def basic_block(self, blk, x):
         """torchvision BasicBlock: relu(bn2(conv2(relu(bn1(conv1(x))))) + identity), identity = x or
         bn_d(conv_d(x)) when the shape changes."""
         if type(blk).__name__ != "BasicBlock":
-            raise NotImplementedError(f"{type(blk).__name__} blocks (resnet50) have no lipread_b200 plan yet")
+            raise NotImplementedError(f"{type(blk).__name__} blocks have no lipread_b200 plan")
         ident, dmask = x, None
         ds_raw = None
         # Backward groups run in reverse registration order: bn2, conv2, bn1, conv1, [bn_d, conv_d].  conv1 writes

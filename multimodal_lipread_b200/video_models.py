@@ -12,7 +12,7 @@ import types
 
 import torch
 import torch.nn as nn
-from torchvision.models import mobilenet_v2, resnet18, resnet34
+from torchvision.models import mobilenet_v2, resnet18, resnet34, resnet50
 
 from . import engine
 from ._lib import ACT_RELU
@@ -281,6 +281,8 @@ class ResNet2DBiLSTM(PlanModel):
             base = resnet18(weights=None)
         elif resnet_version == 34:
             base = resnet34(weights=None)
+        elif resnet_version == 50:
+            base = resnet50(weights=None)
         else:
             raise ValueError(f"Unsupported ResNet version: {resnet_version}")
         if pretrained_state_dict is not None:
@@ -292,8 +294,7 @@ class ResNet2DBiLSTM(PlanModel):
         # CNN: that pass moves every BatchNorm's running statistics once and sets num_batches_tracked to 1.  Reproduced
         # at construction (host, once) so that state_dicts and eval-mode outputs agree with the reference's from step 0.
         with torch.no_grad():
-            self.cnn_features(torch.zeros(1, 3, 44, 44))
-        cnn_output_dim = 512
+            cnn_output_dim = self.cnn_features(torch.zeros(1, 3, 44, 44)).shape[1]     # 512, or 2048 for resnet50
         self.time_distributed_cnn = TimeDistributed(nn.Sequential(self.cnn_features, self.global_pool, nn.Flatten()))
         self.bilstm = nn.LSTM(input_size=cnn_output_dim, hidden_size=feature_dim // 2, num_layers=2, bidirectional=True,
                               batch_first=True, dropout=dropout if dropout > 0 else 0)

@@ -165,24 +165,29 @@ class _TimeDistributed(nn.Module):
 
 
 class ResNet2DBiLSTMOracle(nn.Module):
-    """video/models/resnet_lstm.py:56-156 (resnet_version 18): conv1 re-initialised, CNN registered twice
-    (cnn_features / time_distributed_cnn.module.0), 2-layer BiLSTM(512, feature_dim/2), x[:, -1] -> ReLU -> Dropout -> fc."""
+    """video/models/resnet_lstm.py:56-156 (model.resnet_version 18 / 34 / 50, :79-86): conv1 re-initialised, CNN registered
+    twice (cnn_features / time_distributed_cnn.module.0), 2-layer BiLSTM(512 [2048 for resnet50], feature_dim/2),
+    x[:, -1] -> ReLU -> Dropout -> fc."""
 
     def __init__(self, num_classes, config=None):
         super().__init__()
         config = config or DictConfig()
         feature_dim = config.get("model.feature_dim", 1024)
         dropout = config.get("model.dropout", 0.5)
-        base = resnet18(weights=None)
+        version = config.get("model.resnet_version", 18)
+        if version not in (18, 34, 50):
+            raise ValueError(f"Unsupported ResNet version: {version}")
+        import torchvision.models as tvm
+        base = {18: tvm.resnet18, 34: tvm.resnet34, 50: tvm.resnet50}[version](weights=None)
         base.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
         self.cnn_features = nn.Sequential(*list(base.children())[:-2])
         self.global_pool = nn.AdaptiveAvgPool2d((1, 1))
         # resnet_lstm.py:98-103: the LSTM input size is measured with a dummy pass through the freshly built CNN, which
         # is in train mode -- every BatchNorm's running statistics move once and num_batches_tracked becomes 1
         with torch.no_grad():
-            self.global_pool(self.cnn_features(torch.zeros(1, 3, 44, 44)))
+            cnn_dim = self.global_pool(self.cnn_features(torch.zeros(1, 3, 44, 44))).view(-1).size(0)
         self.time_distributed_cnn = _TimeDistributed(nn.Sequential(self.cnn_features, self.global_pool, nn.Flatten()))
-        self.bilstm = nn.LSTM(512, feature_dim // 2, num_layers=2, bidirectional=True, batch_first=True,
+        self.bilstm = nn.LSTM(cnn_dim, feature_dim // 2, num_layers=2, bidirectional=True, batch_first=True,
                               dropout=dropout if dropout > 0 else 0)
         self.relu = nn.ReLU()
         self.dropout = nn.Dropout(dropout) if dropout > 0 else nn.Identity()

@@ -136,7 +136,7 @@ class DCfg:
         return self.d.get(key, default)
 
 
-def golden_models():
+def golden_models(only_resnet_variants=False):
     """Configs 1, 2, 4: the reference's own AudioResNet / ResNet2DBiLSTM / EarlyFusionAVMobileNet with dropout set to 0
     (the only change: p is a constructor argument / module attribute), one train step each."""
     out = {}
@@ -171,6 +171,21 @@ def golden_models():
         out[f"{name}_running_mean_sum"] = np.array([v.double().sum().item() for k, v in sd.items() if k.endswith("running_mean")])
         out[f"{name}_B"], out[f"{name}_T"], out[f"{name}_size"] = np.array(B), np.array(T), np.array(size)
         print(name, "loss", loss.item(), "n_params", sum(p.numel() for p in model.parameters()))
+
+    # video resnet_lstm with model.resnet_version 34 / 50 (video/models/resnet_lstm.py:79-86): BasicBlock [3,4,6,3] and
+    # Bottleneck trunks.  `--resnet-variants` adds just these records to the committed file.
+    B, T, size, C = 2, 4, 44, 40
+    mod = load_ref("video", "models.resnet_lstm")
+    mel, video, labels = data(B, size, T, C)
+    for version in (34, 50):
+        torch.manual_seed(0)
+        model = mod.ResNet2DBiLSTM(C, DCfg({"model.dropout": 0.0, "model.resnet_version": version}))
+        record(f"video_resnet{version}_lstm", model, (video,), labels, 5e-5, 1e-5, B, T, size)
+    if only_resnet_variants:
+        old = dict(np.load(os.path.join(HERE, "models_golden.npz")))
+        old.update(out)
+        np.savez_compressed(os.path.join(HERE, "models_golden.npz"), **old)
+        return
 
     # config 4: audio_video early_fusion_mobilenet (lr 3e-4, av_config.yaml:23)
     B, T, size, C = 3, 8, 44, 40
@@ -399,6 +414,9 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     if "--dataset-only" in sys.argv:
         golden_dataset()
+        sys.exit(0)
+    if "--resnet-variants" in sys.argv:
+        golden_models(only_resnet_variants=True)
         sys.exit(0)
     if "--models-only" not in sys.argv:
         golden_dataset()

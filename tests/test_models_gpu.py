@@ -132,6 +132,8 @@ def _case(name, precision="fp32"):
         ref = O.EarlyFusionResNetOracle(C, lstm_dropout=0.0, head_dropout=0.0)
     elif name == "video_resnet_lstm":
         ref = O.ResNet2DBiLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}}))
+    elif name in ("video_resnet34_lstm", "video_resnet50_lstm"):         # model.resnet_version (resnet_lstm.py:79-86)
+        ref = O.ResNet2DBiLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0, "resnet_version": int(name[12:14])}}))
     elif name == "audio_resnet":
         ref = O.AudioResNetOracle(C, dropout_rate=0.0)
     elif name == "acv_late_fusion_mobile":
@@ -179,6 +181,8 @@ def _case(name, precision="fp32"):
         ours = AV.EarlyFusionAV(C, cfg, precision=precision)
     elif name == "video_resnet_lstm":
         ours = video_models.ResNet2DBiLSTM(C, cfg, precision=precision)
+    elif name in ("video_resnet34_lstm", "video_resnet50_lstm"):
+        ours = video_models.ResNet2DBiLSTM(C, Cfg(dict(NO_DROP, **{"model.resnet_version": int(name[12:14])})), precision=precision)
     elif name == "audio_resnet":
         ours = audio_models.AudioResNet(C, dropout_rate=0.0, precision=precision)
     elif name == "acv_late_fusion_mobile":
@@ -253,6 +257,9 @@ def _inputs_for(name, mel, lips):
     ("early_fusion_resnet", 2, 5, 44),
     ("video_resnet_lstm", 2, 5, 44),
     ("video_resnet_lstm", 2, 3, 88),
+    ("video_resnet34_lstm", 2, 4, 44),
+    ("video_resnet50_lstm", 2, 4, 44),
+    ("video_resnet50_lstm", 2, 3, 88),
     ("audio_resnet", 4, 1, 44),
     ("acv_late_fusion_mobile", 3, 6, 44),
     ("video_mobilenet_lstm", 3, 6, 44),
@@ -331,7 +338,7 @@ def test_train_step_matches_oracle(cuda_device, name, B, T, size):
     assert _rel(out, out_ref) <= 5e-3, _rel(out, out_ref)          # weights moved by the two (slightly different) Adam steps
 
 
-@pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
+@pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "video_resnet34_lstm", "video_resnet50_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
                                   "acv_late_fusion_resnet", "video_vgg_lstm", "video_cnn", "video_resnet_attn", "video_resnet_trans", "video_shufflenet_lstm", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm", "audio_lstm_resnet", "audio_lstm_resnet_attn", "audio_lstm_resnet_trans",
                                   "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast",
                                   "acv_middle_fusion_mobile", "acv_middle_fusion_resnet", "acv_early_fusion_mobile", "acv_early_fusion_resnet"])

@@ -113,7 +113,7 @@ def models_golden(golden_dir):
     return np.load(os.path.join(golden_dir, "models_golden.npz"))
 
 
-@pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
+@pytest.mark.parametrize("name", ["early_fusion_mobilenet", "video_resnet_lstm", "video_resnet34_lstm", "video_resnet50_lstm", "audio_resnet", "acv_late_fusion_mobile", "video_mobilenet_lstm",
                                   "acv_late_fusion_resnet", "video_vgg_lstm", "video_cnn", "video_resnet_attn", "video_resnet_trans", "video_shufflenet_lstm", "audio_resnet_lstm", "audio_vgg", "audio_vgg_lstm", "audio_lstm_resnet", "audio_lstm_resnet_attn", "audio_lstm_resnet_trans",
                                   "late_fusion_mobilenet", "middle_fusion_mobilenet", "early_fusion_fast", "late_fusion_fast",
                                   "acv_middle_fusion_mobile", "acv_middle_fusion_resnet", "acv_early_fusion_mobile", "acv_early_fusion_resnet"])
@@ -127,6 +127,8 @@ def test_model_oracles_match_reference(models_golden, name):
         model, lr, wd = O.EarlyFusionMobileNetOracle(C, lstm_dropout=0.0, head_dropout=0.0), 3e-4, 0.0
     elif name == "video_resnet_lstm":
         model, lr, wd = O.ResNet2DBiLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0}})), 5e-5, 1e-5
+    elif name in ("video_resnet34_lstm", "video_resnet50_lstm"):
+        model, lr, wd = O.ResNet2DBiLSTMOracle(C, O.DictConfig({"model": {"dropout": 0.0, "resnet_version": int(name[12:14])}})), 5e-5, 1e-5
     elif name == "acv_late_fusion_mobile":
         model, lr, wd = O.LateFusionMobileOracle(C, lstm_dropout=0.0), 1e-5, 0.0
     elif name == "video_vgg_lstm":
@@ -183,6 +185,8 @@ def test_model_oracles_match_reference(models_golden, name):
               "acv_late_fusion_resnet": (mel, synthetic.make_cues(B), video)}.get(name, (mel, video))
     if name.startswith("acv_"):
         inputs = (mel, synthetic.make_cues(B), video)
+    if name.startswith("video_"):
+        inputs = (video,)
     opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
     logits, loss = O.train_step_generic(model, opt, inputs, labels)
     np.testing.assert_allclose(logits.numpy(), g[f"{name}_logits"], rtol=1e-5, atol=1e-6)
