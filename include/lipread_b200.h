@@ -189,6 +189,18 @@ int lr_frame_reduce(const float* a, const float* g, float* p, int F, int HW, int
  * SE excitation forward, SE backward, average-pool backward. */
 int lr_frame_scale(const float* a, const float* s, const float* dp, float* out, int F, int HW, int C,
                    lr_stream_t stream);
+/* Squeeze-Excitation gate on the pooled per-frame vectors p [F, C] in ONE launch per direction (torchvision
+ * SqueezeExcitation: fc1 -> activation -> fc2 -> scale_activation, the MobileNetV3 trunk the reference builds in
+ * audio_video/models/middle_fusion_fast.py:15-17 and early_fusion.py:58-60):
+ *   forward : h1 = act1(p . w1^T + b1) [F, Cs],  s = act2(h1 . w2^T + b2) [F, C]      (w1 [Cs, C], w2 [C, Cs], fp32 FMA,
+ *             fixed summation order: bit-reproducible)
+ *   backward: ds [F, C] holds dL/ds on entry and dz2 = ds * act2'(s) on exit; dz1 = (dz2 . w2) * act1'(h1) [F, Cs];
+ *             dp = dz1 . w1 [F, C].  The weight gradients are the caller's (dz2^T h1, dz1^T p and their column sums).
+ * act1 / act2: LR_ACT_NONE, RELU, RELU6 or HSIGMOID (derivatives taken through the outputs).  C, Cs multiples of 4. */
+int lr_se_fc_fwd(const float* p, const float* w1, const float* b1, const float* w2, const float* b2, float* h1,
+                 float* s, int F, int C, int Cs, int act1, int act2, lr_stream_t stream);
+int lr_se_fc_bwd(float* ds, const float* s, const float* h1, const float* w1, const float* w2, float* dz1, float* dp,
+                 int F, int C, int Cs, int act1, int act2, lr_stream_t stream);
 /* y = act(x) element-wise (x == y allowed). */
 int lr_act_fwd(const float* x, float* y, long long n, int act, lr_stream_t stream);
 /* dy *= act'(.) expressed through the activation OUTPUT y (ReLU, ReLU6, hard-sigmoid), in place. */

@@ -756,18 +756,34 @@ class Plan:
         p, h1, s = self.alloc(F * C), self.alloc(F * Cs), self.alloc(F * C)      # per-frame vectors: always fp32
         out = T2(self, a.F, a.H, a.W, C, h=a.h)
         sfx = "_h" if a.h else ""
+        a1, a2 = _act_code(se.activation), _act_code(se.scale_activation)
+        # fc1 -> act -> fc2 -> scale_act on the pooled vectors as ONE launch (csrc/se.cu), and one for the chain
+        # dz2 -> dz1 -> dp of the backward; LIPREAD_SE_FUSED=0 keeps the four / six separate GEMM / activation launches
+        fused = (os.environ.get("LIPREAD_SE_FUSED", "1") == "1" and C % 4 == 0 and Cs % 4 == 0 and C <= 2048
+                 and se.fc1.bias is not None and se.fc2.bias is not None
+                 and all(x in (ACT_NONE, ACT_RELU, ACT_RELU6, ACT_HSIGMOID) for x in (a1, a2)))
         self.fwd.add("lr_frame_reduce" + sfx, a.val, 0, p, F, HW, C, 0)
-        self.linear(p, C, F, se.fc1.weight, se.fc1.bias, h1, Cs, act=_act_code(se.activation))
-        self.linear(h1, Cs, F, se.fc2.weight, se.fc2.bias, s, C, act=_act_code(se.scale_activation))
+        # (forward of the widest gates: 308 MFLOP of fp32 FMA at C = 576 take 31 us in the row-block kernel, the two
+        # tensor-core GEMM launches 20; the backward chain wins at every width: 19 us against four launches / 37 us)
+        if fused and C * Cs <= int(os.environ.get("LIPREAD_SE_FWD_MAX", 40000)):
+            self.fwd.add("lr_se_fc_fwd", p, se.fc1.weight, se.fc1.bias, se.fc2.weight, se.fc2.bias, h1, s, F, C, Cs, a1, a2)
+        else:
+            self.linear(p, C, F, se.fc1.weight, se.fc1.bias, h1, Cs, act=a1)
+            self.linear(h1, Cs, F, se.fc2.weight, se.fc2.bias, s, C, act=a2)
         self.fwd.add("lr_frame_scale" + sfx, a.val, s, 0, out.val, F, HW, C)
         if self.with_backward:
             ds, dh1, dp = self.alloc(F * C), self.alloc(F * Cs), self.alloc(F * C)
             g = self.bgroup()
             g.add("lr_frame_reduce" + sfx, out.grad, a.val, ds, F, HW, C, 1)
-            g.add("lr_act_bwd", ds, s, F * C, _act_code(se.scale_activation))
-            self.linear_bwd(g, h1, Cs, F, se.fc2.weight, se.fc2.bias, ds, C, dx=dh1, ldx=Cs)
-            g.add("lr_act_bwd", dh1, h1, F * Cs, _act_code(se.activation))
-            self.linear_bwd(g, p, C, F, se.fc1.weight, se.fc1.bias, dh1, Cs, dx=dp, ldx=C)
+            if fused:
+                g.add("lr_se_fc_bwd", ds, s, h1, se.fc1.weight, se.fc2.weight, dh1, dp, F, C, Cs, a1, a2)
+                self.linear_bwd(g, h1, Cs, F, se.fc2.weight, se.fc2.bias, ds, C)        # weight gradients: leaf launches
+                self.linear_bwd(g, p, C, F, se.fc1.weight, se.fc1.bias, dh1, Cs)
+            else:
+                g.add("lr_act_bwd", ds, s, F * C, a2)
+                self.linear_bwd(g, h1, Cs, F, se.fc2.weight, se.fc2.bias, ds, C, dx=dh1, ldx=Cs)
+                g.add("lr_act_bwd", dh1, h1, F * Cs, a1)
+                self.linear_bwd(g, p, C, F, se.fc1.weight, se.fc1.bias, dh1, Cs, dx=dp, ldx=C)
             g.add("lr_frame_scale" + sfx, out.grad, s, dp, a.grad, F, HW, C)
         return out
 

@@ -125,6 +125,16 @@ def frame_reduce(a, g, p, F, HW, C, mode):
     check(lib.lr_frame_reduce(_p(a), _p(g), _p(p), F, HW, C, mode, _s()))
 
 
+def se_fc_fwd(p, w1, b1, w2, b2, h1, s, F, C, Cs, act1=ACT_RELU, act2=ACT_HSIGMOID):
+    """h1 = act1(p w1^T + b1), s = act2(h1 w2^T + b2): the SE gate of the pooled vectors in one launch."""
+    check(lib.lr_se_fc_fwd(_p(p), _p(w1), _p(b1), _p(w2), _p(b2), _p(h1), _p(s), F, C, Cs, act1, act2, _s()))
+
+
+def se_fc_bwd(ds, s, h1, w1, w2, dz1, dp, F, C, Cs, act1=ACT_RELU, act2=ACT_HSIGMOID):
+    """ds <- dz2 = ds * act2'(s); dz1 = (dz2 w2) * act1'(h1); dp = dz1 w1."""
+    check(lib.lr_se_fc_bwd(_p(ds), _p(s), _p(h1), _p(w1), _p(w2), _p(dz1), _p(dp), F, C, Cs, act1, act2, _s()))
+
+
 def frame_scale(a, s, dp, out, F, HW, C):
     check(lib.lr_frame_scale(_p(a), _p(s), _p(dp), _p(out), F, HW, C, _s()))
 

@@ -174,10 +174,11 @@ def golden_models(only_resnet_variants=False):
 
     # video resnet_lstm with model.resnet_version 34 / 50 (video/models/resnet_lstm.py:79-86): BasicBlock [3,4,6,3] and
     # Bottleneck trunks.  `--resnet-variants` adds just these records to the committed file.
-    B, T, size, C = 2, 4, 44, 40
+    # (resnet34 at 88 px / 18 frames: with 8 frames of 44 px its 36 BatchNorms see <= 32 values per channel in layer4 and
+    # the fp32 gradients of the REFERENCE itself move by ~1 % under round-off -- not a parity case)
     mod = load_ref("video", "models.resnet_lstm")
-    mel, video, labels = data(B, size, T, C)
-    for version in (34, 50):
+    for version, (B, T, size, C) in ((34, (3, 6, 88, 40)), (50, (2, 4, 44, 40))):
+        mel, video, labels = data(B, size, T, C)
         torch.manual_seed(0)
         model = mod.ResNet2DBiLSTM(C, DCfg({"model.dropout": 0.0, "model.resnet_version": version}))
         record(f"video_resnet{version}_lstm", model, (video,), labels, 5e-5, 1e-5, B, T, size)

@@ -219,6 +219,43 @@ def test_frame_ops_and_small_kernels(K):
     assert torch.equal(dst[:, 5:25], src[:, 20:40]) and dst[:, :5].abs().sum() == 0 and dst[:, 25:].abs().sum() == 0
 
 
+@pytest.mark.parametrize("F,C,Cs", [(928, 576, 144), (928, 16, 8), (61, 240, 64), (7, 96, 24), (100, 288, 72), (9, 120, 32)])
+def test_se_gate_single_launch_kernels(K, F, C, Cs):
+    """lr_se_fc_fwd / lr_se_fc_bwd against torchvision's SqueezeExcitation arithmetic (fc1 -> ReLU -> fc2 -> Hardsigmoid
+    on the pooled vectors) and torch autograd; the forward is bit-reproducible."""
+    g = torch.Generator().manual_seed(F + C)
+    p = torch.randn(F, C, generator=g)
+    w1 = torch.randn(Cs, C, generator=g) / C ** 0.5
+    b1 = torch.randn(Cs, generator=g) * 0.1
+    w2 = torch.randn(C, Cs, generator=g) * (3.0 / Cs ** 0.5)          # pre-activations spread over the hard-sigmoid's kinks
+    b2 = torch.randn(C, generator=g) * 0.5
+    ds = torch.randn(F, C, generator=g)
+    pr, w1r, b1r, w2r, b2r = (t.double().requires_grad_(True) for t in (p, w1, b1, w2, b2))
+    h1_ref = Fn.relu(pr @ w1r.t() + b1r)
+    s_ref = Fn.hardsigmoid(h1_ref @ w2r.t() + b2r)
+    s_ref.backward(ds.double())
+    h1, s = torch.empty(F, Cs, device="cuda"), torch.empty(F, C, device="cuda")
+    args = [t.cuda() for t in (p, w1, b1, w2, b2)]
+    K.se_fc_fwd(*args, h1, s, F, C, Cs)
+    _close(h1, h1_ref, rtol=1e-5)
+    _close(s, s_ref, rtol=1e-5)
+    h1b, sb = torch.empty_like(h1), torch.empty_like(s)
+    K.se_fc_fwd(*args, h1b, sb, F, C, Cs)
+    assert torch.equal(h1, h1b) and torch.equal(s, sb)
+    # backward on the reference's own h1 / s so that no kink is crossed by forward round-off
+    h1d, sd = h1_ref.detach().float().cuda(), s_ref.detach().float().cuda()
+    dsd = ds.clone().cuda()
+    dz1, dp = torch.empty(F, Cs, device="cuda"), torch.empty(F, C, device="cuda")
+    K.se_fc_bwd(dsd, sd, h1d, args[1], args[3], dz1, dp, F, C, Cs)
+    inside = ((s_ref > 0) & (s_ref < 1)).detach()
+    _close(dsd, ds.double() * inside / 6.0, rtol=1e-6)
+    _close(dp, pr.grad, rtol=2e-5)
+    # the weight gradients the caller forms from dz2 / dz1
+    _close(dsd.t() @ h1d, w2r.grad, rtol=1e-4)
+    _close(dz1.t() @ args[0], w1r.grad, rtol=1e-4)
+    _close(dz1.sum(0), b1r.grad, rtol=1e-4)
+
+
 @pytest.mark.parametrize("H,I,B,T", [(128, 576, 6, 29), (32, 20, 5, 4), (256, 64, 33, 7), (128, 48, 32, 5), (512, 32, 3, 4)])
 def test_lstm_direction_kernels(K, H, I, B, T):
     """Both directions of a bidirectional nn.LSTM layer, full sequence with external gradients at every t."""

@@ -257,7 +257,7 @@ def _inputs_for(name, mel, lips):
     ("early_fusion_resnet", 2, 5, 44),
     ("video_resnet_lstm", 2, 5, 44),
     ("video_resnet_lstm", 2, 3, 88),
-    ("video_resnet34_lstm", 2, 4, 44),
+    ("video_resnet34_lstm", 4, 8, 88),
     ("video_resnet50_lstm", 2, 4, 44),
     ("video_resnet50_lstm", 2, 3, 88),
     ("audio_resnet", 4, 1, 44),
@@ -469,6 +469,7 @@ def test_benchmarked_resnet_configuration_matches_oracle(cuda_device):
 
 
 @pytest.mark.parametrize("name,B,T,size,graph", [("video_resnet_lstm", 2, 5, 88, False), ("video_resnet_lstm", 32, 29, 88, True),
+                                                 ("video_resnet34_lstm", 2, 5, 88, False), ("video_resnet50_lstm", 4, 8, 88, True),
                                                  ("audio_resnet", 8, 1, 44, False), ("early_fusion_mobilenet", 4, 8, 88, False),
                                                  ("acv_late_fusion_mobile", 3, 6, 88, False)])
 def test_bf16_storage_mode_of_the_other_configs(cuda_device, name, B, T, size, graph):
