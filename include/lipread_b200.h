@@ -189,6 +189,17 @@ int lr_frame_reduce(const float* a, const float* g, float* p, int F, int HW, int
  * SE excitation forward, SE backward, average-pool backward. */
 int lr_frame_scale(const float* a, const float* s, const float* dp, float* out, int F, int HW, int C,
                    lr_stream_t stream);
+/* Linear layers on at most 32 rows (heads: one row per clip), output columns spread over CTAs, fp32 FMA in a fixed order:
+ *   lr_linear_small_fwd  : y[m, n] = act(b[n] + sum_k x[m*ldx + k] * w[n*K + k])             (nn.Linear [+ activation])
+ *   lr_linear_small_dgrad: dx[m, k] = sum_n dy[m*ldy + n] * w[n*K + k] (+ r[m*ldr + k])     (its input gradient)
+ * M <= 32; K and the row pitches multiples of 4 (forward: K <= 1600), dgrad: N multiple of 4 (<= 1088), K multiple of 32.
+ * Replaces the tile-GEMM launches of the classifier MLPs (audio_video/models/middle_fusion_fast.py:20-25,38-39) and of
+ * the single reverse LSTM step, which were latency chains of one or two CTAs. */
+int lr_linear_small_fwd(const float* x, long long ldx, const float* w, const float* b, float* y, long long ldy, int M,
+                        int N, int K, int act, lr_stream_t stream);
+int lr_linear_small_dgrad(const float* dy, long long ldy, const float* w, float* dx, long long ldx, const float* r,
+                          long long ldr, int M, int N, int K, lr_stream_t stream);
+
 /* Squeeze-Excitation gate on the pooled per-frame vectors p [F, C] in ONE launch per direction (torchvision
  * SqueezeExcitation: fc1 -> activation -> fc2 -> scale_activation, the MobileNetV3 trunk the reference builds in
  * audio_video/models/middle_fusion_fast.py:15-17 and early_fusion.py:58-60):

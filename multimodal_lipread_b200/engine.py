@@ -203,6 +203,9 @@ def op_algorithmic_bytes(name, args):
     return None
 
 
+_SMALL_LINEAR = os.environ.get("LIPREAD_SMALL_LINEAR", "1") == "1"      # 0: heads through the tile GEMMs (A/B switch)
+
+
 def _conv_geometry(conv):
     """(kh, kw, stride, pad_h, pad_w) of an nn.Conv2d -- or of an nn.Conv1d seen as a 1 x k window over [B, 1, T, C]."""
     assert conv.groups == 1
@@ -485,6 +488,11 @@ class Plan:
 
     def linear(self, x, lda, M, w, b, out, ldc, act=ACT_NONE, stats=0, ksplit=1):
         N, K = w.shape[0], w[0].numel()
+        if (ksplit == 1 and M <= 32 and not stats and K % 4 == 0 and lda % 4 == 0 and 32 <= K <= 1600 and _SMALL_LINEAR
+                and act in (ACT_NONE, ACT_RELU, ACT_RELU6, ACT_HSIGMOID, ACT_HSWISH)):
+            # heads (one row per clip): output columns over CTAs instead of a one-CTA tile chain (csrc/rowgemm.cu)
+            self.fwd.add("lr_linear_small_fwd", x, lda, w, (b if b is not None else 0), out, ldc, M, N, K, act)
+            return
         if ksplit > 1:
             # forward split-K is the ORDERED kind (partials in a workspace, reduced in slice order): bit-reproducible
             ws = self.alloc(ksplit * M * N)
@@ -503,6 +511,10 @@ class Plan:
         if b is not None:
             g.add("lr_colsum_h" if h else "lr_colsum", dy, ldy, M, N, self.flat.g(b), leaf=True)
         if dx is not None:
+            if (not h and M <= 32 and N % 4 == 0 and N <= 1088 and K % 32 == 0 and ldy % 4 == 0 and ldx % 4 == 0
+                    and ((isinstance(dx_residual, int) and dx_residual == 0) or ldr % 4 == 0) and _SMALL_LINEAR):
+                g.add("lr_linear_small_dgrad", dy, ldy, w, dx, ldx, dx_residual, ldr, M, N, K)
+                return
             self.gemm_auto(g, dy, ldy, 0, (self.wh(w) if h else w), K, 1, dx, ldx, M, K, N, R=dx_residual, ldr=ldr, h=h)
 
     def bn_act(self, x, bn, act, out, residual=None, res_pre=False, dres=None):
@@ -1060,16 +1072,19 @@ class Plan:
         l = L - 1
         xp_f, hs_f = self.alloc(F * G4), self.alloc(F * H)
         gates_f, c_f, hp_f = self.alloc(F * G4), self.alloc(F * H), self.alloc(F * H)
+        optr = out if isinstance(out, int) else out.data_ptr()
+        xp_r, gates_r, c_r = self.alloc(B * G4), self.alloc(B * G4), self.alloc(B * H)
+        cur_last = (cur if isinstance(cur, int) else cur.data_ptr()) + 4 * (T - 1) * Icur
+        # the reverse direction's single step depends on the features only: a side branch next to the forward walk
+        with self.fwd.side_branch():
+            self.linear(cur_last, T * Icur, B, par("weight_ih", l, 1), par("bias_ih", l, 1), xp_r, G4)
+            self.fwd.add("lr_lstm_fwd", xp_r, G4, par("bias_hh", l, 1), par("weight_hh", l, 1), optr + 4 * H, ldo, gates_r, c_r, 0,
+                         B, 1, H, 1, 1)
         self.linear(cur, Icur, F, par("weight_ih", l, 0), par("bias_ih", l, 0), xp_f, G4)
         self.fwd.add(self.lstm_op("fwd", H, T), xp_f, G4, par("bias_hh", l, 0), par("weight_hh", l, 0), hs_f, H, gates_f, c_f, hp_f,
                      B, T, H, T, 0)
-        optr = out if isinstance(out, int) else out.data_ptr()
         self.fwd.add("lr_copy2d", optr, ldo, hs_f.data_ptr() + 4 * (T - 1) * H, T * H, B, H)
-        xp_r, gates_r, c_r = self.alloc(B * G4), self.alloc(B * G4), self.alloc(B * H)
-        cur_last = (cur if isinstance(cur, int) else cur.data_ptr()) + 4 * (T - 1) * Icur
-        self.linear(cur_last, T * Icur, B, par("weight_ih", l, 1), par("bias_ih", l, 1), xp_r, G4)
-        self.fwd.add("lr_lstm_fwd", xp_r, G4, par("bias_hh", l, 1), par("weight_hh", l, 1), optr + 4 * H, ldo, gates_r, c_r, 0,
-                     B, 1, H, 1, 1)
+        self.fwd.join()
         if self.with_backward:
             dptr = dout if isinstance(dout, int) else dout.data_ptr()
             dg_f, dg_r = self.alloc(F * G4), self.alloc(B * G4)

@@ -125,6 +125,16 @@ def frame_reduce(a, g, p, F, HW, C, mode):
     check(lib.lr_frame_reduce(_p(a), _p(g), _p(p), F, HW, C, mode, _s()))
 
 
+def linear_small_fwd(x, ldx, w, b, y, ldy, M, N, K, act=ACT_NONE):
+    """y = act(x w^T + b) on M <= 32 rows."""
+    check(lib.lr_linear_small_fwd(_p(x), ldx, _p(w), _p(b), _p(y), ldy, M, N, K, act, _s()))
+
+
+def linear_small_dgrad(dy, ldy, w, dx, ldx, M, N, K, r=None, ldr=0):
+    """dx = dy w (+ r) on M <= 32 rows."""
+    check(lib.lr_linear_small_dgrad(_p(dy), ldy, _p(w), _p(dx), ldx, _p(r), ldr, M, N, K, _s()))
+
+
 def se_fc_fwd(p, w1, b1, w2, b2, h1, s, F, C, Cs, act1=ACT_RELU, act2=ACT_HSIGMOID):
     """h1 = act1(p w1^T + b1), s = act2(h1 w2^T + b2): the SE gate of the pooled vectors in one launch."""
     check(lib.lr_se_fc_fwd(_p(p), _p(w1), _p(b1), _p(w2), _p(b2), _p(h1), _p(s), F, C, Cs, act1, act2, _s()))

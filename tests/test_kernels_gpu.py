@@ -219,6 +219,38 @@ def test_frame_ops_and_small_kernels(K):
     assert torch.equal(dst[:, 5:25], src[:, 20:40]) and dst[:, :5].abs().sum() == 0 and dst[:, 25:].abs().sum() == 0
 
 
+@pytest.mark.parametrize("M,N,K_,act,strided", [(32, 256, 384, 1, False), (32, 40, 256, 0, False), (32, 512, 576, 0, True),
+                                                (5, 13, 36, 3, False), (1, 8, 1600, 2, False), (17, 100, 132, 0, True)])
+def test_small_row_linear_forward(K, M, N, K_, act, strided):
+    """lr_linear_small_fwd against nn.Linear (+ activation) on <= 32 rows, contiguous and strided (x[:, -1] of a
+    [B, T, I] sequence) inputs; bit-reproducible."""
+    g = torch.Generator().manual_seed(M * 31 + N)
+    T = 3 if strided else 1
+    xs = torch.randn(M, T, K_, generator=g)
+    w, b = torch.randn(N, K_, generator=g) / K_ ** 0.5, torch.randn(N, generator=g)
+    ref = ACTS[act](xs[:, -1] @ w.t() + b)
+    xd = xs.cuda()
+    y = torch.full((M, N + 3), 7.0, device="cuda")
+    xv = xd[:, -1]
+    K.linear_small_fwd(xv, T * K_, w.cuda(), b.cuda(), y, N + 3, M, N, K_, act)
+    _close(y[:, :N], ref, rtol=2e-5)
+    assert (y[:, N:] == 7.0).all()
+    y2 = torch.empty_like(y)
+    K.linear_small_fwd(xv, T * K_, w.cuda(), b.cuda(), y2, N + 3, M, N, K_, act)
+    assert torch.equal(y[:, :N], y2[:, :N])
+
+
+@pytest.mark.parametrize("M,N,K_,res", [(32, 256, 384, False), (32, 40, 256, False), (32, 512, 576, True), (7, 12, 64, True),
+                                        (1, 1088, 32, False)])
+def test_small_row_linear_input_gradient(K, M, N, K_, res):
+    g = torch.Generator().manual_seed(M + N + K_)
+    dy, w, r = torch.randn(M, N, generator=g), torch.randn(N, K_, generator=g), torch.randn(M, K_, generator=g)
+    ref = dy @ w + (r if res else 0)
+    dx = r.clone().cuda() if res else torch.empty(M, K_, device="cuda")
+    K.linear_small_dgrad(dy.cuda(), N, w.cuda(), dx, K_, M, N, K_, r=(dx if res else None), ldr=(K_ if res else 0))   # r aliases dx
+    _close(dx, ref, rtol=2e-5)
+
+
 @pytest.mark.parametrize("F,C,Cs", [(928, 576, 144), (928, 16, 8), (61, 240, 64), (7, 96, 24), (100, 288, 72), (9, 120, 32)])
 def test_se_gate_single_launch_kernels(K, F, C, Cs):
     """lr_se_fc_fwd / lr_se_fc_bwd against torchvision's SqueezeExcitation arithmetic (fc1 -> ReLU -> fc2 -> Hardsigmoid
