@@ -264,3 +264,13 @@ def test_im2col_and_maxpool_h(cuda_device):
     Kn.im2col_tap(xh.float(), F, 22, 22, 64, 3, 3, 1, 1, 0, 22, 22, colf2)
     L.check(L.lib.lr_im2col_tap_h(_p(xh), F, 22, 22, 64, 3, 3, 1, 1, 1, 0, 22, 22, _p(colh2), _s()))
     assert torch.equal(colh2.float(), colf2)
+    # the stride-2 3x3 and 1x1 (downsample) windows, forward and transposed (dgrad) forms: the 16-byte kernels
+    for k, pad, tr in ((3, 1, 0), (1, 0, 0), (1, 0, 1), (3, 1, 1)):
+        Hd = 22 if tr else 11                                  # transposed: destination = the stride-2 conv's input grid
+        Hs = 11 if tr else 22
+        src = _bf(torch.randn(F, Hs, Hs, 64, generator=g)).cuda()
+        cf = torch.empty(F * Hd * Hd, k * k * 64, device="cuda")
+        ch = torch.empty(F * Hd * Hd, k * k * 64, device="cuda", dtype=torch.bfloat16)
+        Kn.im2col_tap(src.float(), F, Hs, Hs, 64, k, k, 2, pad, bool(tr), Hd, Hd, cf)
+        L.check(L.lib.lr_im2col_tap_h(_p(src), F, Hs, Hs, 64, k, k, 2, pad, pad, tr, Hd, Hd, _p(ch), _s()))
+        assert torch.equal(ch.float(), cf), (k, tr)
