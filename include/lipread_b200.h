@@ -442,6 +442,13 @@ int lr_conv3x3_bf16(const void* x, const void* wt, void* y, const void* R, doubl
                     int N, int flip, lr_stream_t stream);
 int lr_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dwp, int F, int H, int W, int Cin, int Cout,
                           lr_stream_t stream);
+/* The same for 3x3 / STRIDE 2 / pad 1 (torchvision BasicBlock conv1 of layer2 / 3 / 4): x [F, Hi, Wi, Cin] with Hi, Wi even,
+ * y / dy on the [F, Hi/2, Wi/2] grid.  The input is mapped as the 5-D tensor ((column parity, C), Wi/2, row parity, Hi/2, F),
+ * in which every tap of the stride-2 window is a dense box: forward and weight gradient without a patch matrix. */
+int lr_conv3x3s2_bf16(const void* x, const void* wt, void* y, double* stats, int F, int Hi, int Wi, int Cin, int N,
+                      lr_stream_t stream);
+int lr_conv3x3s2_wgrad_bf16(const void* dy, const void* x, float* dwp, int F, int Hi, int Wi, int Cin, int Cout,
+                            lr_stream_t stream);
 
 #ifdef __cplusplus
 }

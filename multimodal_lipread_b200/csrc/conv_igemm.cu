@@ -16,6 +16,13 @@
 //   warp 0      TMA producer (one lane)          warp 1      TMEM allocation + MMA issue (one lane)
 //   warps 2..5  epilogue: tcgen05.ld -> (+ residual) -> bf16 -> swizzled staging -> coalesced 16-byte stores, and the
 //               per-channel sum / sum of squares of the rounded values (train-mode BatchNorm statistics)
+//
+// Stride 2 (the first convolution of layer2 / 3 / 4; forward and wgrad; s2 = 1): the tile grid is the OUTPUT grid
+// (H, W) = (Hi / 2, Wi / 2) and input pixel (2 ho + r - 1, 2 wo + s - 1) has FIXED row / column parities for a given tap, so
+// the input is mapped as the 5-D tensor ((pw, C), Wi / 2, ph, Hi / 2, F) and the tap's operand is again one dense box:
+// (64 channels at parity pw, W, 1, bh, bf) at ((pw) * Cin + c0, -1 or 0, ph, h0 - 1 or h0, f0).  Same bytes, same shared
+// memory layout, same zero fill at the borders -- no patch matrix for these layers either.  (Their input gradient is
+// the stride-1 kernel on the zero-stuffed dy, see lr_zero_stuff2_h.)
 #include <cstdlib>
 
 #include "tc_common.cuh"
@@ -30,7 +37,7 @@ struct FP {
     int F, H, W, Cin, N;        // N: output channels of this call (Cout forward, Cin of the conv for dgrad)
     int bh, bf, tpf;            // box (64, W, bh, bf); tpf = tiles per frame when bf == 1 (else 0: a tile = bf whole frames)
     int rows, nm;               // pixels per tile (<= 256), M = 128 accumulators per tile (1 or 2)
-    int BN, stages, flip;
+    int BN, stages, flip, s2;
     nn::bf16* y; const nn::bf16* R; double* stats;
 };
 
@@ -81,7 +88,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 const int dr = p.flip ? 1 - r : r - 1, dq = p.flip ? 1 - q : q - 1;
                 const uint32_t a_dst = tiles + s * stage_bytes, b_dst = a_dst + a_bytes;
                 mbar_expect_tx(full0 + 8 * s, tx_bytes);
-                tma_load_4d(a_dst, &tmX, full0 + 8 * s, cc * 64, dq, h0 + dr, f0);
+                if (!p.s2) tma_load_4d(a_dst, &tmX, full0 + 8 * s, cc * 64, dq, h0 + dr, f0);
+                else tma_load_5d(a_dst, &tmX, full0 + 8 * s, (dq & 1) * p.Cin + cc * 64, dq < 0 ? -1 : 0, dr & 1,
+                                 h0 + (dr < 0 ? -1 : 0), f0);
                 tma_load_2d(b_dst, &tmW, full0 + 8 * s, tap * p.Cin + cc * 64, n0);
             }
         }
@@ -182,7 +191,7 @@ struct WP {
     int kr, krp;                // pixels per block, padded to a multiple of 16 (pad rows of the x tile stay zero)
     int nblocks, per_cta;       // pixel blocks in all, per CTA (grid.z splits them)
     int nch;                    // 64-column chunks of this N tile (<= 4): chunk q -> tap q / (Cin/64), channels (q % ..) * 64
-    int stages;
+    int stages, s2;
 };
 
 __global__ void __launch_bounds__(THREADS)
@@ -243,7 +252,9 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
                 for (int j = 0; j < nch; ++j) {
                     const int qq = q0 + j, tap = qq / cchunks, cc = qq - tap * cchunks;
                     const int r = tap / 3, t = tap - r * 3;
-                    tma_load_4d(b_dst + (uint32_t)j * chunk_bytes, &tmX, full0 + 8 * s, cc * 64, t - 1, h0 + r - 1, f0);
+                    if (!p.s2) tma_load_4d(b_dst + (uint32_t)j * chunk_bytes, &tmX, full0 + 8 * s, cc * 64, t - 1, h0 + r - 1, f0);
+                    else tma_load_5d(b_dst + (uint32_t)j * chunk_bytes, &tmX, full0 + 8 * s, ((t - 1) & 1) * p.Cin + cc * 64,
+                                     t == 0 ? -1 : 0, (r - 1) & 1, h0 + (r == 0 ? -1 : 0), f0);
                 }
             }
         }
@@ -298,6 +309,13 @@ static int x_map(CUtensorMap* m, const void* x, int F, int H, int W, int C, int 
     const int box[4] = {64, W, bh, bf};
     return make_map(m, x, true, 4, dims, strides, box);
 }
+// input of a stride-2 window: ((pw, C), Wi / 2, ph, Hi / 2, F); box = (64, Wo, 1, bh, bf) on the OUTPUT grid (Hi, Wi even)
+static int x_map_s2(CUtensorMap* m, const void* x, int F, int Hi, int Wi, int C, int bh, int bf) {
+    const long long dims[5] = {2LL * C, Wi / 2, 2, Hi / 2, F};
+    const long long strides[4] = {2LL * C * 2, (long long)Wi * C * 2, 2LL * Wi * C * 2, (long long)Hi * Wi * C * 2};
+    const int box[5] = {64, Wi / 2, 1, bh, bf};
+    return make_map(m, x, true, 5, dims, strides, box);
+}
 
 }  // namespace ig
 
@@ -305,14 +323,15 @@ static int x_map(CUtensorMap* m, const void* x, int F, int H, int W, int C, int 
     LR_CHECK_ARG(F >= 0 && H > 0 && W > 0 && W <= 128, name ": bad image shape (W <= 128)");                  \
     if (F == 0) return LR_OK
 
-extern "C" int lr_conv3x3_bf16(const void* x, const void* wt, void* y, const void* R, double* stats, int F, int H, int W,
-                               int Cin, int N, int flip, lr_stream_t stream) {
+// H, W: the OUTPUT grid (= the input grid for stride 1; the input is 2H x 2W for s2)
+static int conv3x3_impl(const void* x, const void* wt, void* y, const void* R, double* stats, int F, int H, int W,
+                        int Cin, int N, int flip, int s2, lr_stream_t stream) {
     LR_IG_CHECK("lr_conv3x3_bf16");
     LR_CHECK_ARG(Cin > 0 && (Cin & 63) == 0 && N > 0 && (N & 63) == 0, "lr_conv3x3_bf16: channels must be multiples of 64");
     LR_CHECK_ARG(x && wt && y, "lr_conv3x3_bf16: null pointer");
     LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(wt); LR_CHECK_ALIGN(y); LR_CHECK_ALIGN(R);
     ig::FP p;
-    p.F = F; p.H = H; p.W = W; p.Cin = Cin; p.N = N; p.flip = flip ? 1 : 0;
+    p.F = F; p.H = H; p.W = W; p.Cin = Cin; p.N = N; p.flip = flip ? 1 : 0; p.s2 = s2;
     p.y = static_cast<nn::bf16*>(y); p.R = static_cast<const nn::bf16*>(R); p.stats = stats;
     int tiles;
     if (H * W <= 256) {
@@ -342,7 +361,7 @@ extern "C" int lr_conv3x3_bf16(const void* x, const void* wt, void* y, const voi
     if (stages > num_kb) stages = num_kb;
     p.stages = stages;
     CUtensorMap mx, mw;
-    int rc = ig::x_map(&mx, x, F, H, W, Cin, p.bh, p.bf);
+    int rc = s2 ? ig::x_map_s2(&mx, x, F, 2 * H, 2 * W, Cin, p.bh, p.bf) : ig::x_map(&mx, x, F, H, W, Cin, p.bh, p.bf);
     if (rc) return rc;
     {
         const long long dims[2] = {9LL * Cin, N};
@@ -363,14 +382,24 @@ extern "C" int lr_conv3x3_bf16(const void* x, const void* wt, void* y, const voi
     return LR_OK;
 }
 
-extern "C" int lr_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dwp, int F, int H, int W, int Cin, int Cout,
-                                     lr_stream_t stream) {
+extern "C" int lr_conv3x3_bf16(const void* x, const void* wt, void* y, const void* R, double* stats, int F, int H, int W,
+                               int Cin, int N, int flip, lr_stream_t stream) {
+    return conv3x3_impl(x, wt, y, R, stats, F, H, W, Cin, N, flip, 0, stream);
+}
+extern "C" int lr_conv3x3s2_bf16(const void* x, const void* wt, void* y, double* stats, int F, int Hi, int Wi, int Cin,
+                                 int N, lr_stream_t stream) {
+    LR_CHECK_ARG(Hi > 0 && Wi > 0 && (Hi & 1) == 0 && (Wi & 1) == 0, "lr_conv3x3s2_bf16: the input height and width must be even");
+    return conv3x3_impl(x, wt, y, nullptr, stats, F, Hi / 2, Wi / 2, Cin, N, 0, 1, stream);
+}
+
+static int conv3x3_wgrad_impl(const void* dy, const void* x, float* dwp, int F, int H, int W, int Cin, int Cout, int s2,
+                              lr_stream_t stream) {
     LR_IG_CHECK("lr_conv3x3_wgrad_bf16");
     LR_CHECK_ARG(Cin > 0 && (Cin & 63) == 0 && Cout > 0 && (Cout & 7) == 0, "lr_conv3x3_wgrad_bf16: Cin %% 64, Cout %% 8");
     LR_CHECK_ARG(dy && x && dwp, "lr_conv3x3_wgrad_bf16: null pointer");
     LR_CHECK_ALIGN(dy); LR_CHECK_ALIGN(x); LR_CHECK_ALIGN(dwp);
     ig::WP p;
-    p.F = F; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+    p.F = F; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.s2 = s2;
     if (H * W <= 128) {
         p.bh = H; p.bf = 128 / (H * W); if (p.bf > F) p.bf = F;
         p.tpf = 0; p.nblocks = (F + p.bf - 1) / p.bf;
@@ -404,7 +433,7 @@ extern "C" int lr_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dwp, 
     CUtensorMap md, mx, mc;
     int rc = ig::x_map(&md, dy, F, H, W, Cout, p.bh, p.bf);
     if (rc) return rc;
-    rc = ig::x_map(&mx, x, F, H, W, Cin, p.bh, p.bf);
+    rc = s2 ? ig::x_map_s2(&mx, x, F, 2 * H, 2 * W, Cin, p.bh, p.bf) : ig::x_map(&mx, x, F, H, W, Cin, p.bh, p.bf);
     if (rc) return rc;
     {
         const long long dims[2] = {9LL * Cin, Cout};
@@ -423,4 +452,14 @@ extern "C" int lr_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dwp, 
     lr::count_launch();
     LR_CHECK_LAUNCH("conv3x3_wgrad_kernel");
     return LR_OK;
+}
+
+extern "C" int lr_conv3x3_wgrad_bf16(const void* dy, const void* x, float* dwp, int F, int H, int W, int Cin, int Cout,
+                                     lr_stream_t stream) {
+    return conv3x3_wgrad_impl(dy, x, dwp, F, H, W, Cin, Cout, 0, stream);
+}
+extern "C" int lr_conv3x3s2_wgrad_bf16(const void* dy, const void* x, float* dwp, int F, int Hi, int Wi, int Cin, int Cout,
+                                       lr_stream_t stream) {
+    LR_CHECK_ARG(Hi > 0 && Wi > 0 && (Hi & 1) == 0 && (Wi & 1) == 0, "lr_conv3x3s2_wgrad_bf16: the input height and width must be even");
+    return conv3x3_wgrad_impl(dy, x, dwp, F, Hi / 2, Wi / 2, Cin, Cout, 1, stream);
 }

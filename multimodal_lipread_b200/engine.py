@@ -849,9 +849,14 @@ class Plan:
         # straight from the activation through a 4-D TMA box, no patch matrix is written or read
         igemm = (hh and tap and kh == 3 and kw == 3 and st_ == 1 and pd == 1 and pw == 1 and Cin % 64 == 0
                  and Cout % 64 == 0 and Ws <= 128 and os.environ.get("LIPREAD_IGEMM", "1") == "1")
+        # the same for stride 2 on even input sizes (BasicBlock conv1 of layer2 / 3 / 4): forward and weight gradient read
+        # the input through the 5-D parity view, the input gradient goes through the zero-stuffed dy
+        igemm_s2 = (hh and tap and kh == 3 and kw == 3 and st_ == 2 and pd == 1 and pw == 1 and Cin % 64 == 0
+                    and Cout % 64 == 0 and Hs % 2 == 0 and Ws % 2 == 0 and Ws <= 256 and conv.bias is None and act == ACT_NONE
+                    and os.environ.get("LIPREAD_IGEMM", "1") == "1" and os.environ.get("LIPREAD_IGEMM_S2", "1") == "1")
         if pointwise:
             col = xptr
-        elif igemm:
+        elif igemm or igemm_s2:
             col = None
         elif tap:
             col = self.alloc(rows * K, adt)
@@ -889,6 +894,8 @@ class Plan:
             raise NotImplementedError("implicit-GEMM conv: bias / fused activation (the ResNet convs have neither)")
         if igemm:
             self.fwd.add("lr_conv3x3_bf16", xptr, wop, y.val, 0, stt_, F, Hs, Ws, Cin, Cout, 0)
+        elif igemm_s2:
+            self.fwd.add("lr_conv3x3s2_bf16", xptr, wop, y.val, stt_, F, Hs, Ws, Cin, Cout)
         else:
             self.gemm_auto(self.fwd, col, ldk, 0, wop, ldk, 0, y.val, Cout, rows, Cout, ldk,
                            bias=(conv.bias if conv.bias is not None else 0), act=act, stats=stt_, h=hh)
@@ -896,6 +903,7 @@ class Plan:
             g = self.bgroup()
             y._conv_bwd = (g, x, conv, col, ldk, wmat, src, (F, Hs, Ws, Ho, Wo), need_dx and frames is None, tap)
             y._igemm = igemm
+            y._igemm_s2 = igemm_s2
         return y
 
     def dense_conv_bwd(self, y, dx_residual=0):
@@ -917,6 +925,8 @@ class Plan:
             g.add("lr_memset", dwp, Cout * K * 4, leaf=True)
             if igemm:
                 g.add("lr_conv3x3_wgrad_bf16", y.grad, x.val, dwp, F, Hs, Ws, Cin, Cout, leaf=True)
+            elif getattr(y, "_igemm_s2", False):
+                g.add("lr_conv3x3s2_wgrad_bf16", y.grad, x.val, dwp, F, Hs, Ws, Cin, Cout, leaf=True)
             else:
                 self.gemm_auto(g, y.grad, Cout, 1, col, K, 1, dwp, K, Cout, K, rows, split_ok=True, h=hh)
             g.add("lr_weight_tap", dwp, dw, Cout, Cin, kh * kw, 2, leaf=True)

@@ -90,3 +90,35 @@ def test_stride2_input_gradient_through_zero_stuffing(cuda_device, F, Hi, Wi, Ci
     dref = x0.grad.permute(0, 2, 3, 1) + res.double()
     err = (dx.double() - dref).abs().max().item()
     assert err <= 2.0 ** -8 * dref.abs().max().item(), (err, dref.abs().max().item())
+
+
+@pytest.mark.parametrize("F,Hi,Wi,Cin,Cout", [(9, 22, 22, 64, 128), (23, 12, 12, 128, 256), (61, 6, 6, 256, 512), (3, 10, 16, 64, 64),
+                                              (2, 44, 44, 64, 128), (5, 20, 30, 64, 64), (40, 4, 4, 128, 64)])
+def test_stride2_forward_and_weight_gradient_without_patch_matrix(cuda_device, F, Hi, Wi, Cin, Cout):
+    """lr_conv3x3s2_bf16 / lr_conv3x3s2_wgrad_bf16 (the 5-D parity view of the input: every tap of the stride-2 window is
+    a dense TMA box) against conv2d(stride=2, padding=1) and its weight gradient in float64 on the same bf16 operands."""
+    L = _lib()
+    g = torch.Generator().manual_seed(F * 19 + Hi + Cin)
+    Ho, Wo = Hi // 2, Wi // 2
+    x = torch.randn(F, Hi, Wi, Cin, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).to(torch.bfloat16).cuda()
+    dy = torch.randn(F, Ho, Wo, Cout, generator=g).to(torch.bfloat16).cuda()
+    xd, wd, dyd = x.double().permute(0, 3, 1, 2), w.double(), dy.double().permute(0, 3, 1, 2)
+    y = torch.full((F, Ho, Wo, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+    wt = _tap(w)
+    L.check(L.lib.lr_conv3x3s2_bf16(x.data_ptr(), wt.data_ptr(), y.data_ptr(), stats.data_ptr(), F, Hi, Wi, Cin, Cout, _s()))
+    ref = Fn.conv2d(xd, wd, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert ref.shape[1:3] == (Ho, Wo) and torch.isfinite(y.float()).all()
+    err = (y.double() - ref).abs().max().item()
+    assert err <= 2.0 ** -8 * ref.abs().max().item(), (err, ref.abs().max().item())
+    yd = y.double().reshape(-1, Cout)
+    assert torch.allclose(stats[:Cout], yd.sum(0), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(stats[Cout:], (yd * yd).sum(0), rtol=1e-5, atol=1e-3)
+    g0 = torch.randn(Cout, 9 * Cin, generator=g).cuda()
+    dwp = g0.clone()
+    L.check(L.lib.lr_conv3x3s2_wgrad_bf16(dy.data_ptr(), x.data_ptr(), dwp.data_ptr(), F, Hi, Wi, Cin, Cout, _s()))
+    wref = torch.nn.grad.conv2d_weight(xd, (Cout, Cin, 3, 3), dyd, stride=2, padding=1)
+    wref = g0.double() + _tap(wref)
+    err = (dwp.double() - wref).abs().max().item()
+    assert err <= 3e-5 * wref.abs().max().item() + 1e-4, (err, wref.abs().max().item())
