@@ -34,6 +34,7 @@ linear_small_fwd_kernel(const float* __restrict__ x, long long ldx, const float*
                         const float* __restrict__ b, float* __restrict__ y, long long ldy, int M, int N, int K, int act) {
     extern __shared__ __align__(16) float X[];            // [32][K], rows >= M zero
     const int K4 = K >> 2;
+#pragma unroll 8
     for (int e = threadIdx.x; e < RM * K4; e += TH) {
         const int m = e / K4, k = (e - m * K4) * 4;
         nn::st4(X + m * K + k, m < M ? __ldg(reinterpret_cast<const float4*>(x + m * ldx + k)) : make_float4(0.f, 0.f, 0.f, 0.f));
@@ -77,6 +78,7 @@ linear_small_dgrad_kernel(const float* __restrict__ dy, long long ldy, const flo
     float* D = smd;                                        // [32][N], rows >= M zero
     float* red = D + RM * N;                               // [16][32][32]
     const int N4 = N >> 2;
+#pragma unroll 8
     for (int e = threadIdx.x; e < RM * N4; e += TH) {
         const int m = e / N4, n = (e - m * N4) * 4;
         nn::st4(D + m * N + n, m < M ? __ldg(reinterpret_cast<const float4*>(dy + m * ldy + n)) : make_float4(0.f, 0.f, 0.f, 0.f));
